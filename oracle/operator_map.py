@@ -1,0 +1,93 @@
+"""H_eff matvec (oracle; test-only).  Restates src/operator_map.jl:3-42."""
+from __future__ import annotations
+
+import itertools
+
+import numpy as np
+
+from .tensor import Tensor, contract, noprime
+
+
+def _pair_cost(la, da, lb, db):
+    """flops ~ product of all distinct index dims; returns (cost, labels, dims) of the result."""
+    dims = dict(zip(la, da))
+    dims.update(zip(lb, db))
+    cost = 1
+    for l in dims:
+        cost *= dims[l]
+    out = [l for l in la if l not in lb] + [l for l in lb if l not in la]
+    return cost, out, [dims[l] for l in out]
+
+
+def optimal_sequence(tensors):
+    """Exhaustive optimal pairwise contraction order (UPSTREAM `contraction_sequence(...; alg="optimal")`,
+    src/operator_map.jl:7).  Returns a nested tuple of tensor indices."""
+    n = len(tensors)
+    full = (1 << n) - 1
+    best = {}
+    for i, t in enumerate(tensors):
+        best[1 << i] = (0, i, list(t.labels), list(t.data.shape))
+    for size in range(2, n + 1):
+        for subset in itertools.combinations(range(n), size):
+            mask = sum(1 << i for i in subset)
+            res = None
+            sub = mask
+            a = (sub - 1) & mask
+            while a:
+                b = mask ^ a
+                if a < b and a in best and b in best:
+                    ca, ta, la, da = best[a]
+                    cb, tb, lb, db = best[b]
+                    c, lo, do = _pair_cost(la, da, lb, db)
+                    tot = ca + cb + c
+                    if res is None or tot < res[0]:
+                        res = (tot, (ta, tb), lo, do)
+                a = (a - 1) & mask
+            best[mask] = res
+    return best[full][1], best[full][0]
+
+
+def _contract_sequence(tensors, seq):
+    if isinstance(seq, int):
+        return tensors[seq]
+    a, b = seq
+    return contract(_contract_sequence(tensors, a), _contract_sequence(tensors, b))
+
+
+def optimal_map(P, psi: Tensor) -> Tensor:
+    """src/operator_map.jl:3-10."""
+    envs = [P.environment(e) for e in P.incident_edges()]
+    site_ops = [P.operator[s] for s in P.sites()]
+    lst = envs + site_ops + [psi]
+    seq, _ = optimal_sequence(lst)
+    out = _contract_sequence(lst, seq)
+    return noprime(out).permute(psi.labels)
+
+
+def operator_map(P, psi: Tensor) -> Tensor:
+    """src/operator_map.jl:15-42 -- fixed order: environments on first(region), site operators,
+    remaining environments; on-edge (0-site) branch contracts the two environments only."""
+    out = psi
+    if P.on_edge():
+        for e in P.incident_edges():
+            out = contract(out, P.environment(e))
+    else:
+        region = P.sites()
+        ie = P.incident_edges()
+        for e in ie:
+            if e[1] == region[0]:
+                out = contract(out, P.environment(e))
+        for s in region:
+            out = contract(out, P.operator[s])
+        for e in ie:
+            if e[1] != region[0]:
+                out = contract(out, P.environment(e))
+    return noprime(out).permute(psi.labels)
+
+
+def matvec_flops(P, psi: Tensor):
+    """Flop count of the optimal sequence (real multiply-adds x2)."""
+    envs = [P.environment(e) for e in P.incident_edges()]
+    site_ops = [P.operator[s] for s in P.sites()]
+    _, cost = optimal_sequence(envs + site_ops + [psi])
+    return 2 * cost

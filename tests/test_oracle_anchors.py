@@ -1,0 +1,150 @@
+"""Pins the oracle on everything the reference itself pins for the hot path:
+the shipped constant (examples/dmrg.jl:41-43), the tree-DMRG energy check
+(test/dmrg/test_tree_dmrg.jl:53,67), the TDVP checks (test/tdvp/test_tree_tdvp.jl:65-77), the
+Euler-tour properties (test/test_euler_tour.jl:13-25), plus independent ED / dense expm."""
+import numpy as np
+import pytest
+
+from oracle.ed import ed_ground_state, ed_time_evolution, state_vector, dense_hamiltonian, ttno_dense
+from oracle.graph import build_tree, chain_plus_ancilla, path_graph, named_comb_tree
+from oracle.models import heisenberg_opsum, ising_opsum, product_ttn, spin_ops, ttno, random_ttn
+from oracle.region_plans import euler_tour_edges, euler_tour_vertices, tdvp_regions
+from oracle.sweep import dmrg, tdvp
+from oracle.local_solvers import exponentiate_solver, runge_kutta_solver
+
+
+def neel(g, st, even_up=True):
+    out = {}
+    for j, v in enumerate(g.vertices, start=1):
+        up = (j % 2 == 0) if even_up else (j % 2 == 1)
+        out[v] = st["Up"] if up else st["Dn"]
+    return out
+
+
+def test_euler_tour_properties():
+    g = build_tree(3, 3)
+    tour = euler_tour_edges(g, (0, 0))
+    for a, b in zip(tour[:-1], tour[1:]):
+        assert a[1] == b[0]
+    for (u, v) in g.edges:
+        assert (u, v) in tour and (v, u) in tour
+    assert len(tour) == 2 * len(g.edges)
+    vt = euler_tour_vertices(g, (0, 0))
+    for v in g.vertices:
+        assert v in vt
+
+
+@pytest.mark.parametrize("graph", [path_graph(6), build_tree(3, 2), named_comb_tree([2, 3, 1])])
+def test_ttno_equals_dense_hamiltonian(graph):
+    d, ops, _ = spin_ops("S=1/2")
+    for os_ in (heisenberg_opsum(graph), ising_opsum(graph, 1.0, 0.7)):
+        H = ttno(os_, graph, ops)
+        assert np.abs(ttno_dense(H, graph, d) - dense_hamiltonian(os_, graph, ops, sparse=False)).max() < 1e-13
+
+
+def test_reference_constant_s1_n10():
+    """examples/dmrg.jl:26-43 shape (2-site, no expansion): Exact energy = -12.8945601."""
+    g = path_graph(10)
+    d, ops, st = spin_ops("S=1")
+    H = ttno(heisenberg_opsum(g), g, ops)
+    psi0 = product_ttn(g, d, neel(g, st))
+    trunc = dict(cutoff=1e-12, maxdim=[10, 40, 80, 160])
+    E, psi = dmrg(H, psi0, nsweeps=5, nsites=2, inserter_kwargs=dict(trunc=trunc))
+    assert abs(E - (-12.8945601)) < 5e-8
+    assert abs(E - (-12.894560132211)) < 5e-9
+
+
+def test_tree_dmrg_two_site_and_one_site_expansion():
+    """test/dmrg/test_tree_dmrg.jl:15-67."""
+    g = build_tree(3, 3)
+    d, ops, st = spin_ops("S=1/2")
+    os_ = heisenberg_opsum(g)
+    H = ttno(os_, g, ops)
+    psi0 = product_ttn(g, d, neel(g, st))
+    Ex, _ = ed_ground_state(os_, g, ops)
+    assert abs(Ex - (-4.046057854359)) < 1e-10
+    trunc = dict(cutoff=1e-5, maxdim=40)
+    E, _ = dmrg(H, psi0, nsweeps=5, nsites=2, inserter_kwargs=dict(trunc=trunc))
+    assert abs(E - Ex) < 1e-5
+    E, _ = dmrg(H, psi0, nsweeps=5, nsites=1,
+                extracter_kwargs=dict(trunc=trunc, subspace_algorithm="densitymatrix"),
+                inserter_kwargs=dict(trunc=trunc))
+    assert abs(E - Ex) < 1e-5
+
+
+def test_config1_heisenberg_n20_energy():
+    """BASELINE config 1: S=1/2 N=20, 2-site, maxdim 100, cutoff 1e-12; ED -8.682473334399."""
+    g = path_graph(20)
+    d, ops, st = spin_ops("S=1/2")
+    H = ttno(heisenberg_opsum(g), g, ops)
+    psi0 = product_ttn(g, d, neel(g, st))
+    E, psi = dmrg(H, psi0, nsweeps=5, nsites=2, inserter_kwargs=dict(trunc=dict(cutoff=1e-12, maxdim=100)))
+    assert abs(E - (-8.682473334399)) < 1e-9
+    assert psi.maxlinkdim() <= 100
+
+
+@pytest.mark.parametrize("order", [2, 4])
+def test_tdvp_two_site_vs_dense_expm(order):
+    """examples/quench_evolution.jl:20-84 shape; fidelity target >= 1 - 1e-8."""
+    g = path_graph(8)
+    d, ops, st = spin_ops("S=1/2")
+    os_ = heisenberg_opsum(g)
+    H = ttno(os_, g, ops)
+    psi0 = product_ttn(g, d, neel(g, st, even_up=False))
+    tp = list(np.arange(0, 0.5 + 1e-9, 0.05))
+    vx = ed_time_evolution(os_, g, ops, state_vector(psi0), tp, normalize=True)
+    psit = tdvp(H, psi0, tp, nsites=2, tdvp_order=order,
+                updater_kwargs=dict(solver=runge_kutta_solver, order=4),
+                inserter_kwargs=dict(trunc=dict(maxdim=5000, cutoff=1e-14), normalize=True))
+    assert 1 - abs(np.vdot(vx, state_vector(psit))) < 1e-8
+
+
+def test_tdvp_exponentiate_solver_matches_rk4():
+    g = path_graph(6)
+    d, ops, st = spin_ops("S=1/2")
+    os_ = heisenberg_opsum(g)
+    H = ttno(os_, g, ops)
+    psi0 = product_ttn(g, d, neel(g, st, even_up=False))
+    tp = [0.0, 0.05, 0.1]
+    vx = ed_time_evolution(os_, g, ops, state_vector(psi0), tp, normalize=True)
+    psit = tdvp(H, psi0, tp, nsites=2, tdvp_order=2, updater_kwargs=dict(solver=exponentiate_solver),
+                inserter_kwargs=dict(trunc=dict(cutoff=1e-14), normalize=True))
+    assert 1 - abs(np.vdot(vx, state_vector(psit))) < 1e-9
+
+
+def test_tree_tdvp_regression():
+    """test/tdvp/test_tree_tdvp.jl:24-77 (chain + ancilla): norms, overlaps and accumulated phase."""
+    N = 10
+    g = chain_plus_ancilla(N)
+    d, ops, st = spin_ops("S=1/2")
+    from oracle.models import OpSum
+    os_ = OpSum()
+    for j in range(1, N):
+        os_.add(1.0, "Sz", j, "Sz", j + 1)
+        os_.add(0.5, "S+", j, "S-", j + 1)
+        os_.add(0.5, "S-", j, "S+", j + 1)
+    H = ttno(os_, g, ops)
+    psi0 = product_ttn(g, d, neel(g, st))
+    trunc = dict(cutoff=1e-10, maxdim=100)
+    E, gs = dmrg(H, psi0, nsweeps=5, nsites=2, inserter_kwargs=dict(trunc=trunc))
+    tmax = 0.10
+    tp = list(np.arange(0, tmax + 1e-9, 0.02))
+    psi1 = tdvp(H, gs, tp, nsites=1, inserter_kwargs=dict(trunc=trunc))
+    psi2 = tdvp(H, gs, tp, nsites=2, inserter_kwargs=dict(trunc=trunc))
+    v0, v1, v2 = state_vector(gs), state_vector(psi1), state_vector(psi2)
+    assert np.linalg.norm(v1) > 0.999 and np.linalg.norm(v2) > 0.999
+    assert abs(np.vdot(v1, v0)) > 0.99
+    assert abs(np.vdot(v1, v2)) > 0.99
+    z = np.vdot(v1, v0)
+    assert abs(np.arctan(z.imag / z.real) - E * tmax) < 1e-4
+
+
+def test_tdvp_plan_structure():
+    g = path_graph(5)
+    plan = tdvp_regions(g, 0.1, updater_kwargs={}, tdvp_order=2, nsites=2, sweep=1)
+    regs = [r for r, _ in plan]
+    # forward half-sweep: (N-1) two-site + (N-2) one-site regions; second half reversed
+    assert len(regs) == 2 * (4 + 3)
+    assert regs[len(regs) // 2:] == [list(reversed(r)) for r in reversed(regs[: len(regs) // 2])]
+    ts = [k["updater_kwargs"]["time_step"] for _, k in plan[:7]]
+    assert ts == [0.05, -0.05, 0.05, -0.05, 0.05, -0.05, 0.05]
