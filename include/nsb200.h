@@ -1,0 +1,223 @@
+/* nsb200.h -- C ABI of libnsb200.so, the B200-native sweep engine behind the NetworkSolvers.jl
+ * hook API (extracter / updater / inserter).
+ *
+ * Every entry point returns an int status (NSB_OK == 0, negative on failure) and never throws or
+ * aborts across the boundary; nsb_last_error(ctx) gives the message.  All tensors are dense,
+ * column-major (first index fastest -- Julia / ITensor dense storage order), element type f64 or
+ * complex f64 (interleaved re,im).  The library owns every device allocation behind opaque
+ * handles; host buffers are caller-owned and are copied synchronously.
+ *
+ * Index ("leg") encoding, used by every leg list below: a leg is a pair of int32 (a, b)
+ *     (v, NSB_SITE)      the site index of vertex v          (ket / operator "in" index)
+ *     (v, NSB_SITE_OUT)  the primed site index of vertex v   (operator "out" index, MPO only)
+ *     (v, n), n >= 0     the link index on the tree edge {v, n}  (state link, or operator link
+ *                        when the tensor is an operator tensor)
+ *
+ * Reference interfaces each entry point replaces (paths relative to the reference repo):
+ *   nsb_extract          src/extracter.jl:3-17   (itn.orthogonalize, prod(psi[v]), subspace_expand,
+ *                                                 itn.position)
+ *   nsb_update_eigsolve  src/eigsolve.jl:14-28 -> src/local_solvers/eigsolve.jl:3-29
+ *                                                 (KrylovKit.eigsolve over optimal_map)
+ *   nsb_update_exp       src/applyexp.jl:18-48 -> src/local_solvers/{runge_kutta,exponentiate}.jl
+ *   nsb_insert           src/inserter.jl:3-33    (it.factorize + truncation, set_ortho_region)
+ *   nsb_matvec_*         src/operator_map.jl:3-10 / :15-42 (optimal_map / operator_map)
+ *   nsb_network_create / nsb_site_upload / nsb_mpo_upload
+ *                        src/eigsolve.jl:69-74, src/applyexp.jl:84-89 (EigsolveProblem /
+ *                        ApplyExpProblem construction: permute_indices + itn.ProjTTN)
+ *   nsb_maxlinkdim       itn.maxlinkdim in the sweep printers src/eigsolve.jl:39, src/applyexp.jl:56
+ *   nsb_range_finder     src/sketched_linear_algebra/range_finder.jl:6-64
+ */
+#ifndef NSB200_H
+#define NSB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* status codes */
+#define NSB_OK 0
+#define NSB_EINVAL (-1)
+#define NSB_ENOMEM (-2)
+#define NSB_ECUDA (-3)
+#define NSB_ENCCL (-4)
+#define NSB_ENOTCONV (-5)
+#define NSB_EUNSUPPORTED (-6) /* e.g. region length not in {1,2}; mirrors src/inserter.jl:26 */
+#define NSB_EINTERNAL (-7)
+
+/* dtypes */
+#define NSB_F64 0
+#define NSB_C128 1
+
+/* leg codes */
+#define NSB_SITE (-1)
+#define NSB_SITE_OUT (-2)
+
+/* local solvers for nsb_update_exp (src/applyexp.jl:24 `solver=`) */
+#define NSB_SOLVER_RK 0     /* runge_kutta_solver, order in nsb_krylov.rk_order (2 or 4) */
+#define NSB_SOLVER_KRYLOV 1 /* exponentiate_solver */
+
+/* subspace expansion back-ends (src/subspace/subspace.jl:8-26) */
+#define NSB_EXPAND_NONE 0
+#define NSB_EXPAND_DENSITYMATRIX 1
+
+/* phase timers */
+#define NSB_T_GAUGE 0
+#define NSB_T_THETA 1
+#define NSB_T_EXPAND 2
+#define NSB_T_ENV 3
+#define NSB_T_MATVEC 4
+#define NSB_T_KRYLOV 5
+#define NSB_T_FACTORIZE 6
+#define NSB_T_OTHER 7
+#define NSB_NUM_TIMERS 8
+
+typedef struct nsb_ctx nsb_ctx;
+typedef struct nsb_net nsb_net;
+
+typedef struct {
+  double cutoff;  /* src/truncation_parameters.jl: default 0.0 */
+  int64_t mindim; /* default 1 */
+  int64_t maxdim; /* default INT64_MAX */
+} nsb_trunc;
+
+typedef struct {
+  int32_t algorithm;       /* NSB_EXPAND_* */
+  int32_t north_pass;      /* default 1 (src/subspace/densitymatrix.jl:10) */
+  double expansion_factor; /* default 1.5 (src/subspace/subspace.jl:5) */
+  int64_t max_expand;      /* default INT64_MAX */
+} nsb_expand;
+
+typedef struct {
+  int32_t krylovdim; /* eigsolve default 3, exponentiate default 30 */
+  int32_t maxiter;   /* eigsolve default 1, exponentiate default 100 */
+  double tol;        /* eigsolve default 1e-14, exponentiate default 1e-12 */
+  int32_t which;     /* 0 = :SR (smallest real), 1 = :LR */
+  int32_t eager;     /* eigsolve default 0, exponentiate default 1 */
+  int32_t rk_order;  /* runge_kutta_solver order, 2 or 4 (default 4) */
+  int32_t reserved;
+} nsb_krylov;
+
+typedef struct {
+  int32_t expanded;    /* 1 if the subspace expansion enlarged a bond, else 0 (soft-fail == 0) */
+  int32_t env_builds;  /* environments (re)built by this call */
+  int32_t qr_steps;    /* gauge-move QR steps performed */
+  int32_t local_rank;  /* number of legs of the local tensor */
+  int64_t local_numel; /* elements of the local tensor */
+} nsb_extract_info;
+
+typedef struct {
+  int32_t nmatvec;   /* H_eff applications */
+  int32_t krylovdim; /* Krylov dimension actually reached (last restart) */
+  int32_t converged;
+  int32_t reserved;
+  double residual; /* eigsolve: |beta * y_K| ; exponentiate: accumulated error estimate */
+} nsb_solve_info;
+
+typedef struct {
+  int64_t newdim;  /* dimension of the new bond (2-site), or current bond for 1-site */
+  double truncerr; /* discarded weight / total weight (NDTensors truncate! rule) */
+  int32_t decomp;  /* 0 none (1-site), 1 svd, 2 eigen, 3 qr */
+  int32_t jacobi_sweeps;
+} nsb_insert_info;
+
+typedef struct {
+  uint64_t kernel_launches;
+  uint64_t gemm_calls;
+  double gemm_flops;
+  uint64_t permute_bytes;
+  uint64_t matvecs;
+  uint64_t env_builds;
+  uint64_t qr_calls;
+  uint64_t svd_calls;
+  uint64_t jacobi_sweeps;
+} nsb_counters;
+
+/* ---- context ------------------------------------------------------------------------------ */
+int nsb_ctx_create(int device, nsb_ctx** out);
+int nsb_ctx_destroy(nsb_ctx* ctx);
+const char* nsb_last_error(nsb_ctx* ctx); /* ctx may be NULL: last error of the calling thread */
+const char* nsb_version(void);
+int nsb_ctx_set_option(nsb_ctx* ctx, const char* key, int64_t value); /* "gemm_impl": 0 auto,1 naive,2 dmma,3 dmma+tma */
+int nsb_ctx_counters(nsb_ctx* ctx, nsb_counters* out);
+int nsb_ctx_counters_reset(nsb_ctx* ctx);
+int nsb_ctx_synchronize(nsb_ctx* ctx);
+int nsb_timers_enable(nsb_ctx* ctx, int on);
+int nsb_timers_get(nsb_ctx* ctx, double* ms_out /* NSB_NUM_TIMERS */);
+int nsb_timers_reset(nsb_ctx* ctx);
+int nsb_mem_info(nsb_ctx* ctx, int64_t* free_bytes, int64_t* total_bytes, int64_t* pool_used_bytes);
+
+/* multi-GPU: one process per GPU; rank 0 creates the id, the host side (torch.distributed, MPI ...)
+ * broadcasts the 128 bytes, every rank calls nsb_comm_init.  After that nsb_net_set_shard splits
+ * the matvec across ranks. */
+int nsb_comm_unique_id(char id_out[128]);
+int nsb_comm_init(nsb_ctx* ctx, const char id[128], int rank, int nranks);
+int nsb_comm_destroy(nsb_ctx* ctx);
+
+/* ---- network (state + operator on a tree) -------------------------------------------------- */
+int nsb_network_create(nsb_ctx* ctx, int32_t nverts, const int32_t* edges /* 2*nedges */, int32_t nedges,
+                       const int64_t* site_dims /* nverts */, int32_t dtype, nsb_net** out);
+int nsb_network_destroy(nsb_net* net);
+int nsb_site_upload(nsb_net* net, int32_t v, int32_t rank, const int32_t* legs /* 2*rank */,
+                    const int64_t* dims, const void* host);
+int nsb_site_info(nsb_net* net, int32_t v, int32_t* rank, int32_t* legs /* cap 2*16 */, int64_t* dims /* cap 16 */);
+int nsb_site_download(nsb_net* net, int32_t v, void* host);
+int nsb_site_fill_random(nsb_net* net, int32_t v, int32_t rank, const int32_t* legs, const int64_t* dims,
+                         uint64_t seed, double scale);
+int nsb_mpo_upload(nsb_net* net, int32_t v, int32_t rank, const int32_t* legs, const int64_t* dims,
+                   const void* host);
+int nsb_set_ortho_region(nsb_net* net, const int32_t* verts, int32_t n);
+int nsb_get_ortho_region(nsb_net* net, int32_t* verts /* cap nverts */, int32_t* n);
+int nsb_linkdim(nsb_net* net, int32_t u, int32_t v, int64_t* dim);
+int nsb_maxlinkdim(nsb_net* net, int64_t* dim);
+int nsb_env_drop_all(nsb_net* net); /* forget cached environments (ProjTTN(H) freshly constructed) */
+int nsb_env_count(nsb_net* net, int32_t* n);
+
+/* ---- the three hooks ---------------------------------------------------------------------- */
+int nsb_extract(nsb_net* net, const int32_t* region, int32_t nreg, const nsb_trunc* trunc /* extracter's */,
+                const nsb_expand* expand /* NULL == none */, nsb_extract_info* info /* nullable */);
+int nsb_update_eigsolve(nsb_net* net, const nsb_krylov* params, double* eigval, nsb_solve_info* info);
+int nsb_update_exp(nsb_net* net, double t_re, double t_im, int32_t solver, const nsb_krylov* params,
+                   int32_t nsites, int32_t next_vertex /* 1-site TDVP: next hop, -1 if none */,
+                   nsb_solve_info* info);
+int nsb_insert(nsb_net* net, const nsb_trunc* trunc /* inserter's */, int32_t normalize, int32_t set_ortho,
+               nsb_insert_info* info);
+
+/* ---- pieces exposed for tests and benchmarks ---------------------------------------------- */
+int nsb_local_info(nsb_net* net, int32_t* rank, int32_t* legs /* cap 2*16 */, int64_t* dims /* cap 16 */);
+int nsb_local_download(nsb_net* net, void* host);
+int nsb_local_upload(nsb_net* net, const void* host);
+/* theta' = H_eff theta through the reference-facing call with HOST buffers (H2D + matvec + D2H). */
+int nsb_matvec_host(nsb_net* net, const void* host_in, void* host_out);
+/* theta' = H_eff theta, `reps` times, device resident (output kept internally; download optional). */
+int nsb_matvec_device(nsb_net* net, int32_t reps, void* host_out /* nullable */);
+/* analytic flop count (real flops) of one H_eff application at the current position */
+int nsb_matvec_flops(nsb_net* net, double* flops);
+/* norm of the state = norm of the orthogonality-centre tensor (requires a single-vertex centre) */
+int nsb_norm(nsb_net* net, double* out);
+
+/* ---- dense helpers (test hooks for the kernels under the hooks) ---------------------------- */
+/* C(m x n) = op(A) op(B); opX: 0 = N, 1 = T, 2 = C (conj-transpose), 3 = conj (no transpose). */
+int nsb_gemm_host(nsb_ctx* ctx, int32_t dtype, int32_t opa, int32_t opb, int64_t m, int64_t n, int64_t k,
+                  const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int32_t impl);
+/* time `reps` device-resident GEMMs of that shape (random data); returns avg ms per GEMM */
+int nsb_gemm_bench(nsb_ctx* ctx, int32_t dtype, int32_t opa, int32_t opb, int64_t m, int64_t n, int64_t k,
+                   int32_t impl, int32_t reps, double* ms_out);
+/* truncated factorisation of a host matrix (rows x cols): U (rows x newdim), C = U^H M (newdim x cols),
+ * spectrum (sigma^2, descending, length min(rows, cols)) -- src/inserter.jl:23 semantics. */
+int nsb_factorize_host(nsb_ctx* ctx, int32_t dtype, int64_t rows, int64_t cols, const void* M,
+                       const nsb_trunc* trunc, void* U /* rows*min */, void* C /* min*cols */,
+                       double* spectrum, nsb_insert_info* info);
+/* thin QR of a host matrix (rows x cols): Q (rows x k), R (k x cols), k = min(rows, cols). */
+int nsb_qr_host(nsb_ctx* ctx, int32_t dtype, int64_t rows, int64_t cols, const void* M, void* Q, void* R);
+/* blocked randomised range finder for a host matrix A (m x n): orthonormal Q (m x rank) with
+ * rank <= max_rank + oversample (src/sketched_linear_algebra/range_finder.jl:6-64). */
+int nsb_range_finder_host(nsb_ctx* ctx, int32_t dtype, int64_t m, int64_t n, const void* A, int64_t max_rank,
+                          int32_t oversample, int32_t north_pass, double orthogonal_threshold, uint64_t seed,
+                          void* Q /* m*(max_rank+oversample) */, int64_t* rank_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NSB200_H */

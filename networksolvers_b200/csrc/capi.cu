@@ -1,0 +1,431 @@
+// extern "C" boundary of libnsb200.so (declared in include/nsb200.h).  Nothing throws across it.
+#include <nccl.h>
+
+#include <random>
+
+#include "net.h"
+
+namespace nsb {
+
+bool g_timers_enabled = false;
+static thread_local std::string tl_error;
+
+void* Ctx::alloc(size_t bytes) {
+  void* p = nullptr;
+  cudaError_t e = cudaMallocFromPoolAsync(&p, bytes, pool, stream);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    // one retry after letting in-flight frees complete
+    cudaStreamSynchronize(stream);
+    e = cudaMallocFromPoolAsync(&p, bytes, pool, stream);
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    throw Error(NSB_ENOMEM, std::string("device allocation of ") + std::to_string(bytes) + " bytes failed: " + cudaGetErrorString(e));
+  }
+  return p;
+}
+void Ctx::free(void* p) { if (p) cudaFreeAsync(p, stream); }
+
+PhaseTimer::PhaseTimer(Ctx* c, int i) : ctx(c), idx(i), e0(nullptr), e1(nullptr), active(g_timers_enabled) {
+  if (!active) return;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cudaEventRecord(e0, ctx->stream);
+}
+PhaseTimer::~PhaseTimer() {
+  if (!active) return;
+  cudaEventRecord(e1, ctx->stream);
+  cudaEventSynchronize(e1);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  ctx->timers_ms[idx] += ms;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+}
+
+}  // namespace nsb
+
+using namespace nsb;
+
+struct nsb_ctx { Ctx c; };
+struct nsb_net { NetBase* n; nsb_ctx* ctx; };
+
+static int fail(Ctx* ctx, int code, const std::string& msg) {
+  tl_error = msg;
+  if (ctx) ctx->last_error = msg;
+  return code;
+}
+
+#define NSB_TRY(ctxp) try {
+#define NSB_CATCH(ctxp)                                                        \
+  }                                                                            \
+  catch (const nsb::Error& e) { return fail((ctxp), e.code, e.what()); }       \
+  catch (const std::bad_alloc&) { return fail((ctxp), NSB_ENOMEM, "host allocation failed"); } \
+  catch (const std::exception& e) { return fail((ctxp), NSB_EINTERNAL, e.what()); } \
+  catch (...) { return fail((ctxp), NSB_EINTERNAL, "unknown error"); }         \
+  return NSB_OK;
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+const char* nsb_version(void) { return "nsb200 0.1 (sm_100a)"; }
+
+const char* nsb_last_error(nsb_ctx* ctx) { return ctx ? ctx->c.last_error.c_str() : tl_error.c_str(); }
+
+int nsb_ctx_create(int device, nsb_ctx** out) {
+  if (!out) return fail(nullptr, NSB_EINVAL, "nsb_ctx_create: null output");
+  *out = nullptr;
+  nsb_ctx* h = nullptr;
+  NSB_TRY(nullptr)
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    throw Error(NSB_ECUDA, "no CUDA device available: the B200 path has no CPU fallback");
+  }
+  NSB_REQUIRE(device >= 0 && device < ndev, NSB_EINVAL, "bad device ordinal");
+  NSB_CUDA(cudaSetDevice(device));
+  h = new nsb_ctx();
+  Ctx& c = h->c;
+  c.device = device;
+  cudaDeviceProp prop;
+  NSB_CUDA(cudaGetDeviceProperties(&prop, device));
+  c.num_sms = prop.multiProcessorCount;
+  c.smem_optin = prop.sharedMemPerBlockOptin;
+  NSB_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  NSB_CUDA(cudaDeviceGetDefaultMemPool(&c.pool, device));
+  uint64_t thresh = UINT64_MAX;
+  NSB_CUDA(cudaMemPoolSetAttribute(c.pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+  NSB_CUDA(cudaMalloc(&c.d_scratch, sizeof(double) * Ctx::SCRATCH_DOUBLES));
+  NSB_CUDA(cudaMallocHost(&c.h_pinned, sizeof(double) * Ctx::SCRATCH_DOUBLES));
+  *out = h;
+  NSB_CATCH(nullptr)
+}
+
+int nsb_ctx_destroy(nsb_ctx* ctx) {
+  if (!ctx) return NSB_OK;
+  cudaSetDevice(ctx->c.device);
+  if (ctx->c.nccl_comm) { ncclCommDestroy((ncclComm_t)ctx->c.nccl_comm); ctx->c.nccl_comm = nullptr; }
+  cudaStreamSynchronize(ctx->c.stream);
+  if (ctx->c.d_scratch) cudaFree(ctx->c.d_scratch);
+  if (ctx->c.h_pinned) cudaFreeHost(ctx->c.h_pinned);
+  cudaStreamDestroy(ctx->c.stream);
+  delete ctx;
+  return NSB_OK;
+}
+
+int nsb_ctx_set_option(nsb_ctx* ctx, const char* key, int64_t value) {
+  if (!ctx || !key) return fail(nullptr, NSB_EINVAL, "null argument");
+  NSB_TRY(&ctx->c)
+  std::string k(key);
+  if (k == "gemm_impl") { NSB_REQUIRE(value >= 0 && value <= 3, NSB_EINVAL, "gemm_impl must be 0..3"); ctx->c.gemm_impl = (int)value; }
+  else throw Error(NSB_EINVAL, "unknown option " + k);
+  NSB_CATCH(&ctx->c)
+}
+
+int nsb_ctx_counters(nsb_ctx* ctx, nsb_counters* out) {
+  if (!ctx || !out) return fail(nullptr, NSB_EINVAL, "null argument");
+  const Counters& c = ctx->c.cnt;
+  out->kernel_launches = c.kernel_launches; out->gemm_calls = c.gemm_calls; out->gemm_flops = c.gemm_flops;
+  out->permute_bytes = c.permute_bytes; out->matvecs = c.matvecs; out->env_builds = c.env_builds;
+  out->qr_calls = c.qr_calls; out->svd_calls = c.svd_calls; out->jacobi_sweeps = c.jacobi_sweeps;
+  return NSB_OK;
+}
+int nsb_ctx_counters_reset(nsb_ctx* ctx) { if (!ctx) return NSB_EINVAL; ctx->c.cnt = Counters(); return NSB_OK; }
+int nsb_ctx_synchronize(nsb_ctx* ctx) {
+  if (!ctx) return NSB_EINVAL;
+  NSB_TRY(&ctx->c) ctx->c.sync(); NSB_CATCH(&ctx->c)
+}
+int nsb_timers_enable(nsb_ctx* ctx, int on) { (void)ctx; g_timers_enabled = on != 0; return NSB_OK; }
+int nsb_timers_get(nsb_ctx* ctx, double* ms_out) {
+  if (!ctx || !ms_out) return NSB_EINVAL;
+  for (int i = 0; i < NSB_NUM_TIMERS; ++i) ms_out[i] = ctx->c.timers_ms[i];
+  return NSB_OK;
+}
+int nsb_timers_reset(nsb_ctx* ctx) { if (!ctx) return NSB_EINVAL; for (auto& t : ctx->c.timers_ms) t = 0; return NSB_OK; }
+int nsb_mem_info(nsb_ctx* ctx, int64_t* free_bytes, int64_t* total_bytes, int64_t* pool_used_bytes) {
+  if (!ctx) return NSB_EINVAL;
+  NSB_TRY(&ctx->c)
+  size_t f, t;
+  NSB_CUDA(cudaMemGetInfo(&f, &t));
+  if (free_bytes) *free_bytes = (int64_t)f;
+  if (total_bytes) *total_bytes = (int64_t)t;
+  if (pool_used_bytes) { uint64_t u = 0; NSB_CUDA(cudaMemPoolGetAttribute(ctx->c.pool, cudaMemPoolAttrUsedMemCurrent, &u)); *pool_used_bytes = (int64_t)u; }
+  NSB_CATCH(&ctx->c)
+}
+
+// ---- NCCL plumbing -------------------------------------------------------------------------------
+int nsb_comm_unique_id(char id_out[128]) {
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  ncclUniqueId id;
+  if (ncclGetUniqueId(&id) != ncclSuccess) return fail(nullptr, NSB_ENCCL, "ncclGetUniqueId failed");
+  memcpy(id_out, &id, 128);
+  return NSB_OK;
+}
+int nsb_comm_init(nsb_ctx* ctx, const char id[128], int rank, int nranks) {
+  if (!ctx) return NSB_EINVAL;
+  NSB_TRY(&ctx->c)
+  NSB_CUDA(cudaSetDevice(ctx->c.device));
+  ncclUniqueId uid;
+  memcpy(&uid, id, 128);
+  ncclComm_t comm;
+  ncclResult_t r = ncclCommInitRank(&comm, nranks, uid, rank);
+  if (r != ncclSuccess) throw Error(NSB_ENCCL, std::string("ncclCommInitRank: ") + ncclGetErrorString(r));
+  ctx->c.nccl_comm = comm;
+  ctx->c.rank = rank;
+  ctx->c.nranks = nranks;
+  NSB_CATCH(&ctx->c)
+}
+int nsb_comm_destroy(nsb_ctx* ctx) {
+  if (!ctx) return NSB_EINVAL;
+  if (ctx->c.nccl_comm) { ncclCommDestroy((ncclComm_t)ctx->c.nccl_comm); ctx->c.nccl_comm = nullptr; }
+  ctx->c.rank = 0; ctx->c.nranks = 1;
+  return NSB_OK;
+}
+
+// ---- network -------------------------------------------------------------------------------------
+int nsb_network_create(nsb_ctx* ctx, int32_t nverts, const int32_t* edges, int32_t nedges, const int64_t* site_dims,
+                       int32_t dtype, nsb_net** out) {
+  if (!ctx || !out || !site_dims || (nedges > 0 && !edges)) return fail(ctx ? &ctx->c : nullptr, NSB_EINVAL, "null argument");
+  *out = nullptr;
+  NSB_TRY(&ctx->c)
+  NSB_CUDA(cudaSetDevice(ctx->c.device));
+  NetBase* n = nullptr;
+  if (dtype == NSB_F64) n = new Net<double>(&ctx->c, nverts, edges, nedges, site_dims);
+  else if (dtype == NSB_C128) n = new Net<cdouble>(&ctx->c, nverts, edges, nedges, site_dims);
+  else throw Error(NSB_EINVAL, "dtype must be NSB_F64 or NSB_C128");
+  nsb_net* h = new nsb_net();
+  h->n = n; h->ctx = ctx;
+  *out = h;
+  NSB_CATCH(&ctx->c)
+}
+int nsb_network_destroy(nsb_net* net) {
+  if (!net) return NSB_OK;
+  cudaSetDevice(net->ctx->c.device);
+  delete net->n;
+  delete net;
+  return NSB_OK;
+}
+
+#define NET_CALL(net, body)                              \
+  if (!(net)) return fail(nullptr, NSB_EINVAL, "null network"); \
+  Ctx* cx__ = &(net)->ctx->c;                            \
+  NSB_TRY(cx__)                                          \
+  NSB_CUDA(cudaSetDevice(cx__->device));                 \
+  body;                                                  \
+  NSB_CATCH(cx__)
+
+int nsb_site_upload(nsb_net* net, int32_t v, int32_t rank, const int32_t* legs, const int64_t* dims, const void* host) {
+  NET_CALL(net, NSB_REQUIRE(legs && dims && host && rank >= 1 && rank <= MAX_RANK, NSB_EINVAL, "bad arguments"); net->n->site_upload(v, rank, legs, dims, host))
+}
+int nsb_site_info(nsb_net* net, int32_t v, int32_t* rank, int32_t* legs, int64_t* dims) {
+  NET_CALL(net, NSB_REQUIRE(rank, NSB_EINVAL, "null rank"); net->n->site_info(v, rank, legs, dims))
+}
+int nsb_site_download(nsb_net* net, int32_t v, void* host) {
+  NET_CALL(net, NSB_REQUIRE(host, NSB_EINVAL, "null buffer"); net->n->site_download(v, host))
+}
+int nsb_site_fill_random(nsb_net* net, int32_t v, int32_t rank, const int32_t* legs, const int64_t* dims, uint64_t seed, double scale) {
+  NET_CALL(net, NSB_REQUIRE(legs && dims && rank >= 1 && rank <= MAX_RANK, NSB_EINVAL, "bad arguments"); net->n->site_fill_random(v, rank, legs, dims, seed, scale))
+}
+int nsb_mpo_upload(nsb_net* net, int32_t v, int32_t rank, const int32_t* legs, const int64_t* dims, const void* host) {
+  NET_CALL(net, NSB_REQUIRE(legs && dims && host && rank >= 2 && rank <= MAX_RANK, NSB_EINVAL, "bad arguments"); net->n->mpo_upload(v, rank, legs, dims, host))
+}
+int nsb_set_ortho_region(nsb_net* net, const int32_t* verts, int32_t n) {
+  NET_CALL(net, NSB_REQUIRE(n >= 0 && (n == 0 || verts), NSB_EINVAL, "bad arguments"); net->n->set_ortho_region(verts, n))
+}
+int nsb_get_ortho_region(nsb_net* net, int32_t* verts, int32_t* n) {
+  NET_CALL(net, NSB_REQUIRE(n, NSB_EINVAL, "null n"); net->n->get_ortho_region(verts, n))
+}
+int nsb_linkdim(nsb_net* net, int32_t u, int32_t v, int64_t* dim) {
+  NET_CALL(net, NSB_REQUIRE(dim, NSB_EINVAL, "null dim"); *dim = net->n->linkdim(u, v))
+}
+int nsb_maxlinkdim(nsb_net* net, int64_t* dim) {
+  NET_CALL(net, NSB_REQUIRE(dim, NSB_EINVAL, "null dim"); *dim = net->n->maxlinkdim())
+}
+int nsb_env_drop_all(nsb_net* net) { NET_CALL(net, net->n->env_drop_all()) }
+int nsb_env_count(nsb_net* net, int32_t* n) { NET_CALL(net, NSB_REQUIRE(n, NSB_EINVAL, "null n"); *n = net->n->env_count()) }
+
+int nsb_extract(nsb_net* net, const int32_t* region, int32_t nreg, const nsb_trunc* trunc, const nsb_expand* expand, nsb_extract_info* info) {
+  NET_CALL(net, NSB_REQUIRE(region, NSB_EINVAL, "null region"); net->n->extract(region, nreg, trunc, expand, info))
+}
+int nsb_update_eigsolve(nsb_net* net, const nsb_krylov* params, double* eigval, nsb_solve_info* info) {
+  NET_CALL(net, net->n->update_eigsolve(params, eigval, info))
+}
+int nsb_update_exp(nsb_net* net, double t_re, double t_im, int32_t solver, const nsb_krylov* params, int32_t nsites,
+                   int32_t next_vertex, nsb_solve_info* info) {
+  NET_CALL(net, net->n->update_exp(t_re, t_im, solver, params, nsites, next_vertex, info))
+}
+int nsb_insert(nsb_net* net, const nsb_trunc* trunc, int32_t normalize, int32_t set_ortho, nsb_insert_info* info) {
+  NET_CALL(net, net->n->insert(trunc, normalize, set_ortho, info))
+}
+int nsb_local_info(nsb_net* net, int32_t* rank, int32_t* legs, int64_t* dims) {
+  NET_CALL(net, NSB_REQUIRE(rank, NSB_EINVAL, "null rank"); net->n->local_info(rank, legs, dims))
+}
+int nsb_local_download(nsb_net* net, void* host) { NET_CALL(net, NSB_REQUIRE(host, NSB_EINVAL, "null buffer"); net->n->local_download(host)) }
+int nsb_local_upload(nsb_net* net, const void* host) { NET_CALL(net, NSB_REQUIRE(host, NSB_EINVAL, "null buffer"); net->n->local_upload(host)) }
+int nsb_matvec_host(nsb_net* net, const void* host_in, void* host_out) {
+  NET_CALL(net, NSB_REQUIRE(host_in && host_out, NSB_EINVAL, "null buffer"); net->n->matvec_host(host_in, host_out))
+}
+int nsb_matvec_device(nsb_net* net, int32_t reps, void* host_out) { NET_CALL(net, net->n->matvec_device(reps, host_out)) }
+int nsb_matvec_flops(nsb_net* net, double* flops) { NET_CALL(net, NSB_REQUIRE(flops, NSB_EINVAL, "null"); *flops = net->n->matvec_flops()) }
+int nsb_norm(nsb_net* net, double* out) { NET_CALL(net, NSB_REQUIRE(out, NSB_EINVAL, "null"); *out = net->n->norm()) }
+
+#pragma GCC visibility pop
+}  // extern "C"
+
+// ---- dense helpers -------------------------------------------------------------------------------
+template <typename T>
+static void gemm_host_impl(Ctx* c, int opa, int opb, int64_t m, int64_t n, int64_t k, const void* A, int64_t lda,
+                           const void* B, int64_t ldb, void* C, int64_t ldc, int impl) {
+  int64_t acols = (opa == OP_N || opa == OP_CONJ) ? k : m, bcols = (opb == OP_N || opb == OP_CONJ) ? n : k;
+  DevBuf dA(c, sizeof(T) * lda * acols), dB(c, sizeof(T) * ldb * bcols), dC(c, sizeof(T) * ldc * n);
+  NSB_CUDA(cudaMemcpyAsync(dA.ptr, A, sizeof(T) * lda * acols, cudaMemcpyHostToDevice, c->stream));
+  NSB_CUDA(cudaMemcpyAsync(dB.ptr, B, sizeof(T) * ldb * bcols, cudaMemcpyHostToDevice, c->stream));
+  NSB_CUDA(cudaMemsetAsync(dC.ptr, 0xff, sizeof(T) * ldc * n, c->stream));   // NaN-fill: catches unwritten tiles
+  gemm<T>(c, opa, opb, m, n, k, from_complex<T>(1.0, 0.0), (const T*)dA.ptr, lda, 0, (const T*)dB.ptr, ldb, 0, zero_<T>(),
+          (T*)dC.ptr, ldc, 0, 1, impl);
+  NSB_CUDA(cudaMemcpyAsync(C, dC.ptr, sizeof(T) * ldc * n, cudaMemcpyDeviceToHost, c->stream));
+  c->sync();
+}
+extern "C" __attribute__((visibility("default"))) int nsb_gemm_host(nsb_ctx* ctx, int32_t dtype, int32_t opa, int32_t opb, int64_t m, int64_t n, int64_t k, const void* A,
+                  int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int32_t impl) {
+  if (!ctx) return NSB_EINVAL;
+  NSB_TRY(&ctx->c)
+  NSB_CUDA(cudaSetDevice(ctx->c.device));
+  NSB_REQUIRE(A && B && C && m > 0 && n > 0 && k > 0, NSB_EINVAL, "bad arguments");
+  if (dtype == NSB_F64) gemm_host_impl<double>(&ctx->c, opa, opb, m, n, k, A, lda, B, ldb, C, ldc, impl);
+  else gemm_host_impl<cdouble>(&ctx->c, opa, opb, m, n, k, A, lda, B, ldb, C, ldc, impl);
+  NSB_CATCH(&ctx->c)
+}
+
+template <typename T>
+static double gemm_bench_impl(Ctx* c, int opa, int opb, int64_t m, int64_t n, int64_t k, int impl, int reps) {
+  int64_t lda = (opa == OP_N || opa == OP_CONJ) ? m : k, acols = (opa == OP_N || opa == OP_CONJ) ? k : m;
+  int64_t ldb = (opb == OP_N || opb == OP_CONJ) ? k : n, bcols = (opb == OP_N || opb == OP_CONJ) ? n : k;
+  DevBuf dA(c, sizeof(T) * lda * acols), dB(c, sizeof(T) * ldb * bcols), dC(c, sizeof(T) * m * n);
+  fill_normal<T>(c, (T*)dA.ptr, lda * acols, 11, 1.0);
+  fill_normal<T>(c, (T*)dB.ptr, ldb * bcols, 12, 1.0);
+  auto run = [&]() {
+    gemm<T>(c, opa, opb, m, n, k, from_complex<T>(1.0, 0.0), (const T*)dA.ptr, lda, 0, (const T*)dB.ptr, ldb, 0, zero_<T>(),
+            (T*)dC.ptr, m, 0, 1, impl);
+  };
+  for (int i = 0; i < 2; ++i) run();
+  cudaEvent_t e0, e1;
+  NSB_CUDA(cudaEventCreate(&e0)); NSB_CUDA(cudaEventCreate(&e1));
+  NSB_CUDA(cudaEventRecord(e0, c->stream));
+  for (int i = 0; i < reps; ++i) run();
+  NSB_CUDA(cudaEventRecord(e1, c->stream));
+  NSB_CUDA(cudaEventSynchronize(e1));
+  float ms = 0;
+  NSB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return ms / reps;
+}
+extern "C" __attribute__((visibility("default"))) int nsb_gemm_bench(nsb_ctx* ctx, int32_t dtype, int32_t opa, int32_t opb, int64_t m, int64_t n, int64_t k, int32_t impl,
+                   int32_t reps, double* ms_out) {
+  if (!ctx || !ms_out) return NSB_EINVAL;
+  NSB_TRY(&ctx->c)
+  NSB_CUDA(cudaSetDevice(ctx->c.device));
+  NSB_REQUIRE(m > 0 && n > 0 && k > 0 && reps > 0, NSB_EINVAL, "bad arguments");
+  *ms_out = dtype == NSB_F64 ? gemm_bench_impl<double>(&ctx->c, opa, opb, m, n, k, impl, reps)
+                             : gemm_bench_impl<cdouble>(&ctx->c, opa, opb, m, n, k, impl, reps);
+  NSB_CATCH(&ctx->c)
+}
+
+template <typename T>
+static void factorize_host_impl(Ctx* c, int64_t rows, int64_t cols, const void* M, const nsb_trunc* trunc, void* U, void* C,
+                                double* spectrum, nsb_insert_info* info) {
+  nsb_trunc tr = trunc ? *trunc : nsb_trunc{0.0, 1, INT64_MAX};
+  DevBuf dM(c, sizeof(T) * rows * cols), Ub, Cb;
+  NSB_CUDA(cudaMemcpyAsync(dM.ptr, M, sizeof(T) * rows * cols, cudaMemcpyHostToDevice, c->stream));
+  std::vector<double> spec;
+  FactorInfo fi = factorize_left<T>(c, (const T*)dM.ptr, rows, cols, rows, false, tr.cutoff, tr.mindim, tr.maxdim, false, Ub, Cb, spec);
+  if (U) NSB_CUDA(cudaMemcpyAsync(U, Ub.ptr, sizeof(T) * rows * fi.newdim, cudaMemcpyDeviceToHost, c->stream));
+  if (C) NSB_CUDA(cudaMemcpyAsync(C, Cb.ptr, sizeof(T) * fi.newdim * cols, cudaMemcpyDeviceToHost, c->stream));
+  c->sync();
+  if (spectrum) for (size_t i = 0; i < spec.size(); ++i) spectrum[i] = spec[i];
+  if (info) { info->newdim = fi.newdim; info->truncerr = fi.truncerr; info->decomp = fi.decomp; info->jacobi_sweeps = fi.sweeps; }
+}
+extern "C" __attribute__((visibility("default"))) int nsb_factorize_host(nsb_ctx* ctx, int32_t dtype, int64_t rows, int64_t cols, const void* M, const nsb_trunc* trunc, void* U,
+                       void* C, double* spectrum, nsb_insert_info* info) {
+  if (!ctx) return NSB_EINVAL;
+  NSB_TRY(&ctx->c)
+  NSB_CUDA(cudaSetDevice(ctx->c.device));
+  NSB_REQUIRE(M && rows > 0 && cols > 0, NSB_EINVAL, "bad arguments");
+  if (dtype == NSB_F64) factorize_host_impl<double>(&ctx->c, rows, cols, M, trunc, U, C, spectrum, info);
+  else factorize_host_impl<cdouble>(&ctx->c, rows, cols, M, trunc, U, C, spectrum, info);
+  NSB_CATCH(&ctx->c)
+}
+
+template <typename T>
+static void qr_host_impl(Ctx* c, int64_t rows, int64_t cols, const void* M, void* Q, void* R) {
+  int64_t k = std::min(rows, cols);
+  DevBuf dM(c, sizeof(T) * rows * cols), dQ(c, sizeof(T) * rows * k), dR(c, sizeof(T) * k * cols);
+  NSB_CUDA(cudaMemcpyAsync(dM.ptr, M, sizeof(T) * rows * cols, cudaMemcpyHostToDevice, c->stream));
+  qr_thin<T>(c, (T*)dM.ptr, rows, cols, rows, (T*)dQ.ptr, rows, (T*)dR.ptr, k);
+  NSB_CUDA(cudaMemcpyAsync(Q, dQ.ptr, sizeof(T) * rows * k, cudaMemcpyDeviceToHost, c->stream));
+  NSB_CUDA(cudaMemcpyAsync(R, dR.ptr, sizeof(T) * k * cols, cudaMemcpyDeviceToHost, c->stream));
+  c->sync();
+}
+extern "C" __attribute__((visibility("default"))) int nsb_qr_host(nsb_ctx* ctx, int32_t dtype, int64_t rows, int64_t cols, const void* M, void* Q, void* R) {
+  if (!ctx) return NSB_EINVAL;
+  NSB_TRY(&ctx->c)
+  NSB_CUDA(cudaSetDevice(ctx->c.device));
+  NSB_REQUIRE(M && Q && R && rows > 0 && cols > 0, NSB_EINVAL, "bad arguments");
+  if (dtype == NSB_F64) qr_host_impl<double>(&ctx->c, rows, cols, M, Q, R);
+  else qr_host_impl<cdouble>(&ctx->c, rows, cols, M, Q, R);
+  NSB_CATCH(&ctx->c)
+}
+
+// Blocked randomised range finder: probes are drawn in panels of up to 32 vectors, Y = A * Omega by one GEMM,
+// then the reference's vector-at-a-time rule (north_pass Gram-Schmidt passes against all previous vectors,
+// stop at the first vector whose residual norm falls below orthogonal_threshold) is applied inside the panel.
+template <typename T>
+static int64_t range_finder_impl(Ctx* c, int64_t m, int64_t n, const void* A, int64_t max_rank, int oversample, int north_pass,
+                                 double thr, uint64_t seed, void* Qh) {
+  if (max_rank <= 0) return 0;
+  max_rank = std::min(max_rank, std::min(m, n));
+  int64_t sketch = std::min(max_rank + oversample, std::min(m, n));
+  DevBuf dA(c, sizeof(T) * m * n), dQ(c, sizeof(T) * m * sketch);
+  NSB_CUDA(cudaMemcpyAsync(dA.ptr, A, sizeof(T) * m * n, cudaMemcpyHostToDevice, c->stream));
+  T* Q = (T*)dQ.ptr;
+  int64_t have = 0;
+  const int64_t panel = 32;
+  DevBuf dOm(c, sizeof(T) * n * panel);
+  bool stop = false;
+  while (have < sketch && !stop) {
+    int64_t pb = std::min(panel, sketch - have);
+    fill_normal<T>(c, (T*)dOm.ptr, n * pb, seed + 7919 * (uint64_t)have, 1.0);
+    gemm<T>(c, OP_N, OP_N, m, pb, n, from_complex<T>(1.0, 0.0), (const T*)dA.ptr, m, 0, (const T*)dOm.ptr, n, 0, zero_<T>(),
+            Q + have * m, m, 0, 1);
+    for (int64_t j = 0; j < pb; ++j) {
+      T* q = Q + (have)*m;
+      for (int pass = 0; pass < north_pass; ++pass)
+        for (int64_t i = 0; i < have; ++i) {
+          double cr, ci;
+          vec_dot<T>(c, m, Q + i * m, q, &cr, &ci);
+          vec_axpy<T>(c, m, from_complex<T>(-cr, -ci), Q + i * m, q);
+        }
+      double nrm = vec_nrm2<T>(c, m, q);
+      if (nrm < thr) { stop = true; break; }
+      vec_scale<T>(c, m, from_complex<T>(1.0 / nrm, 0.0), q);
+      ++have;
+    }
+  }
+  NSB_CUDA(cudaMemcpyAsync(Qh, Q, sizeof(T) * m * have, cudaMemcpyDeviceToHost, c->stream));
+  c->sync();
+  return have;
+}
+extern "C" __attribute__((visibility("default"))) int nsb_range_finder_host(nsb_ctx* ctx, int32_t dtype, int64_t m, int64_t n, const void* A, int64_t max_rank, int32_t oversample,
+                          int32_t north_pass, double orthogonal_threshold, uint64_t seed, void* Q, int64_t* rank_out) {
+  if (!ctx) return NSB_EINVAL;
+  NSB_TRY(&ctx->c)
+  NSB_CUDA(cudaSetDevice(ctx->c.device));
+  NSB_REQUIRE(A && Q && rank_out && m > 0 && n > 0, NSB_EINVAL, "bad arguments");
+  *rank_out = dtype == NSB_F64 ? range_finder_impl<double>(&ctx->c, m, n, A, max_rank, oversample, north_pass, orthogonal_threshold, seed, Q)
+                               : range_finder_impl<cdouble>(&ctx->c, m, n, A, max_rank, oversample, north_pass, orthogonal_threshold, seed, Q);
+  NSB_CATCH(&ctx->c)
+}
+
+

@@ -1,0 +1,139 @@
+// nsb200 -- common declarations shared by all translation units of libnsb200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <cuComplex.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include <memory>
+#include <complex>
+
+#include "../../include/nsb200.h"
+
+namespace nsb {
+
+struct Error : public std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define NSB_CUDA(x)                                                                          \
+  do {                                                                                       \
+    cudaError_t e__ = (x);                                                                   \
+    if (e__ != cudaSuccess)                                                                  \
+      throw ::nsb::Error(NSB_ECUDA, std::string(#x) + ": " + cudaGetErrorString(e__) + " (" + \
+                                        __FILE__ + ":" + std::to_string(__LINE__) + ")");   \
+  } while (0)
+
+#define NSB_REQUIRE(cond, code, msg)                                                    \
+  do {                                                                                  \
+    if (!(cond)) throw ::nsb::Error((code), std::string(msg) + " [" #cond "] (" +      \
+                                                 __FILE__ + ":" + std::to_string(__LINE__) + ")"); \
+  } while (0)
+
+typedef cuDoubleComplex cdouble;
+
+template <typename T> struct ScalarTraits;
+template <> struct ScalarTraits<double> {
+  static constexpr bool is_complex = false;
+  static constexpr int dtype = NSB_F64;
+};
+template <> struct ScalarTraits<cdouble> {
+  static constexpr bool is_complex = true;
+  static constexpr int dtype = NSB_C128;
+};
+
+// host <-> device scalar helpers
+__host__ __device__ inline double re(double x) { return x; }
+__host__ __device__ inline double re(cdouble x) { return x.x; }
+__host__ __device__ inline double im(double) { return 0.0; }
+__host__ __device__ inline double im(cdouble x) { return x.y; }
+__host__ __device__ inline double conj_(double x) { return x; }
+__host__ __device__ inline cdouble conj_(cdouble x) { return make_cuDoubleComplex(x.x, -x.y); }
+__host__ __device__ inline double mul_(double a, double b) { return a * b; }
+__host__ __device__ inline cdouble mul_(cdouble a, cdouble b) {
+  return make_cuDoubleComplex(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__host__ __device__ inline double add_(double a, double b) { return a + b; }
+__host__ __device__ inline cdouble add_(cdouble a, cdouble b) { return make_cuDoubleComplex(a.x + b.x, a.y + b.y); }
+__host__ __device__ inline void fma_(double& acc, double a, double b) { acc = fma(a, b, acc); }
+__host__ __device__ inline void fma_(cdouble& acc, cdouble a, cdouble b) {
+  acc.x = fma(a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x);
+  acc.y = fma(a.x, b.y, acc.y); acc.y = fma(a.y, b.x, acc.y);
+}
+__host__ __device__ inline double abs2_(double a) { return a * a; }
+__host__ __device__ inline double abs2_(cdouble a) { return a.x * a.x + a.y * a.y; }
+template <typename T> __host__ __device__ inline T zero_();
+template <> __host__ __device__ inline double zero_<double>() { return 0.0; }
+template <> __host__ __device__ inline cdouble zero_<cdouble>() { return make_cuDoubleComplex(0.0, 0.0); }
+template <typename T> __host__ __device__ inline T from_complex(double r, double i);
+template <> __host__ __device__ inline double from_complex<double>(double r, double) { return r; }
+template <> __host__ __device__ inline cdouble from_complex<cdouble>(double r, double i) { return make_cuDoubleComplex(r, i); }
+
+// ---------------------------------------------------------------------------------------------
+// Context: one device, one stream, stream-ordered memory pool, counters, timers.
+// ---------------------------------------------------------------------------------------------
+struct Counters {
+  uint64_t kernel_launches = 0;
+  uint64_t gemm_calls = 0;
+  double gemm_flops = 0;       // real flops issued by GEMM kernels
+  uint64_t permute_bytes = 0;  // bytes moved by layout permutes (0 on the chain hot path)
+  uint64_t matvecs = 0;
+  uint64_t env_builds = 0;
+  uint64_t qr_calls = 0;
+  uint64_t svd_calls = 0;
+  uint64_t jacobi_sweeps = 0;
+};
+
+struct Ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaMemPool_t pool = nullptr;
+  int num_sms = 148;
+  size_t smem_optin = 0;
+  std::string last_error;
+  Counters cnt;
+  int gemm_impl = 0;   // 0 = auto, 1 = naive, 2 = dmma cp.async, 3 = dmma TMA
+  // multi-GPU (optional): NCCL communicator + rank info, see shard.cu
+  void* nccl_comm = nullptr;
+  int rank = 0, nranks = 1;
+  // phase timers (ms), CUDA-event based: extract / matvec / krylov_vec / factorize / env
+  double timers_ms[NSB_NUM_TIMERS] = {0};
+  // small scratch areas for reductions / scalar read-back
+  double* d_scratch = nullptr;   // SCRATCH_DOUBLES doubles on the device
+  double* h_pinned = nullptr;    // SCRATCH_DOUBLES doubles of pinned host memory
+  static constexpr int SCRATCH_DOUBLES = 16384;
+  void* alloc(size_t bytes);
+  void free(void* p);
+  void sync() { NSB_CUDA(cudaStreamSynchronize(stream)); }
+};
+
+// RAII device buffer (stream-ordered)
+struct DevBuf {
+  Ctx* ctx = nullptr;
+  void* ptr = nullptr;
+  size_t bytes = 0;
+  DevBuf() {}
+  DevBuf(Ctx* c, size_t b) : ctx(c), bytes(b) { ptr = b ? c->alloc(b) : nullptr; }
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept { *this = std::move(o); }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) { release(); ctx = o.ctx; ptr = o.ptr; bytes = o.bytes; o.ptr = nullptr; o.bytes = 0; }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void release() { if (ptr && ctx) ctx->free(ptr); ptr = nullptr; bytes = 0; }
+};
+
+struct PhaseTimer {  // accumulates elapsed device time of a phase into ctx->timers_ms[idx]
+  Ctx* ctx; int idx; cudaEvent_t e0, e1; bool active;
+  PhaseTimer(Ctx* c, int i);
+  ~PhaseTimer();
+};
+extern bool g_timers_enabled;
+
+}  // namespace nsb

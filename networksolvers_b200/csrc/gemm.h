@@ -1,0 +1,19 @@
+// FP64 / complex-FP64 GEMM on sm_100a DMMA (mma.sync f64) -- interface.
+#pragma once
+#include "common.h"
+
+namespace nsb {
+
+enum GemmOp { OP_N = 0, OP_T = 1, OP_C = 2, OP_CONJ = 3 };
+enum GemmImpl { GEMM_AUTO = 0, GEMM_NAIVE = 1, GEMM_DMMA = 2, GEMM_TMA = 3 };
+
+// C[b] (M x N, ldc) = alpha * op(A[b]) (M x K) * op(B[b]) (K x N) + beta * C[b], column-major,
+// b = 0..batch-1 with element strides strideA/B/C (0 = broadcast).
+template <typename T>
+void gemm(Ctx* ctx, int opa, int opb, int64_t M, int64_t N, int64_t K, T alpha, const T* A, int64_t lda,
+          int64_t strideA, const T* B, int64_t ldb, int64_t strideB, T beta, T* C, int64_t ldc,
+          int64_t strideC, int64_t batch, int impl = GEMM_AUTO);
+
+const char* gemm_last_impl_name();
+
+}  // namespace nsb

@@ -1,0 +1,31 @@
+// Dense factorizations on device: Householder thin QR (gauge moves, K8) and the truncating
+// factorization of the inserter (K9) by one-sided Jacobi (Hestenes) SVD.
+#pragma once
+#include "common.h"
+
+namespace nsb {
+
+// NDTensors truncate! rule on a descending spectrum P (eigenvalues of rho = sigma^2).
+// Returns number kept; truncerr = discarded weight / total weight.
+int64_t truncate_spectrum(const std::vector<double>& P, double cutoff, int64_t mindim, int64_t maxdim, double* truncerr);
+
+// Thin QR of A (rows x cols, lda; destroyed): Q (rows x k, ldq), R (k x cols, ldr), k = min(rows, cols).
+template <typename T>
+void qr_thin(Ctx* ctx, T* A, int64_t rows, int64_t cols, int64_t lda, T* Q, int64_t ldq, T* R, int64_t ldr);
+
+struct FactorInfo { int64_t newdim = 0; double truncerr = 0; int decomp = 0; int sweeps = 0; };
+
+// Truncated left-orthogonal factorization M = U C (src/inserter.jl:23 / ITensors.factorize with ortho="left"):
+//   U (rows x newdim) orthonormal columns = leading left singular vectors, C = U^H M (newdim x cols).
+// Spectrum (sigma^2 descending, all min(rows, cols) values) returned on the host.
+// The decision rule cutoff <= 1e-12 -> "svd", else "eigen" only changes the label: both are computed by the
+// same one-sided Jacobi iteration, which is at least as accurate as either LAPACK route.
+// trans_in: the logical matrix is the transpose of the stored one, M(r, c) = buf[c + r * ld].
+// sqrt_spectrum: truncate on sigma instead of sigma^2 (input is already a density matrix rho = S S^H, whose
+//                singular values are the eigenvalues the reference's `eigen(rho; ...)` truncates on).
+template <typename T>
+FactorInfo factorize_left(Ctx* ctx, const T* M, int64_t rows, int64_t cols, int64_t ld, bool trans_in, double cutoff,
+                          int64_t mindim, int64_t maxdim, bool sqrt_spectrum, DevBuf& U, DevBuf& C,
+                          std::vector<double>& spectrum);
+
+}  // namespace nsb

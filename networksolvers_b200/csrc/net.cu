@@ -1,0 +1,1004 @@
+// Network state, projected-operator environments and the three region hooks (see net.h).
+//
+// Reference behaviour restated here (paths relative to the reference repo; UPSTREAM = ITensorNetworks /
+// ITensors / KrylovKit rules):
+//   Net::extract          src/extracter.jl:3-17
+//   Net::orthogonalize    UPSTREAM itn.orthogonalize (App. A.3)
+//   Net::position/make_env UPSTREAM itn.position / make_environment (App. A.2)
+//   Net::apply_heff       src/operator_map.jl:15-42 (fixed order: one environment on the first site, site
+//                         operators as early as possible, remaining environments)
+//   Net::update_eigsolve  src/eigsolve.jl:14-28 + KrylovKit.eigsolve Lanczos (App. A.6)
+//   Net::update_exp       src/applyexp.jl:18-48 + src/local_solvers/runge_kutta.jl:2-25 / KrylovKit.exponentiate (A.7)
+//   Net::insert           src/inserter.jl:3-33 + ITensors.factorize (App. A.4, A.5)
+//   Net::expand_densitymatrix  src/subspace/densitymatrix.jl:5-74, src/subspace/subspace.jl:28-48
+#include "net.h"
+
+#include <algorithm>
+#include <cmath>
+#include <functional>
+
+namespace nsb {
+
+// ------------------------------------------------------------------------------------------------
+// small host dense helpers
+// ------------------------------------------------------------------------------------------------
+void host_sym_eig(int n, std::vector<double>& A, std::vector<double>& evals, std::vector<double>& V) {
+  V.assign((size_t)n * n, 0.0);
+  for (int i = 0; i < n; ++i) V[i + (size_t)i * n] = 1.0;
+  auto a = [&](int i, int j) -> double& { return A[i + (size_t)j * n]; };
+  for (int sweep = 0; sweep < 100; ++sweep) {
+    double off = 0.0, diag = 0.0;
+    for (int i = 0; i < n; ++i) { diag += a(i, i) * a(i, i); for (int j = i + 1; j < n; ++j) off += a(i, j) * a(i, j); }
+    if (off <= 1e-60 || off <= 1e-34 * diag) break;
+    for (int p = 0; p < n - 1; ++p)
+      for (int q = p + 1; q < n; ++q) {
+        double apq = a(p, q);
+        if (apq == 0.0) continue;
+        double zeta = (a(q, q) - a(p, p)) / (2.0 * apq);
+        double t = std::copysign(1.0, zeta) / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
+        double c = 1.0 / std::sqrt(1.0 + t * t), s = c * t;
+        for (int k = 0; k < n; ++k) { double akp = a(k, p), akq = a(k, q); a(k, p) = c * akp - s * akq; a(k, q) = s * akp + c * akq; }
+        for (int k = 0; k < n; ++k) { double apk = a(p, k), aqk = a(q, k); a(p, k) = c * apk - s * aqk; a(q, k) = s * apk + c * aqk; }
+        for (int k = 0; k < n; ++k) { double vkp = V[k + (size_t)p * n], vkq = V[k + (size_t)q * n]; V[k + (size_t)p * n] = c * vkp - s * vkq; V[k + (size_t)q * n] = s * vkp + c * vkq; }
+      }
+  }
+  std::vector<int> order(n);
+  for (int i = 0; i < n; ++i) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](int x, int y) { return a(x, x) < a(y, y); });
+  evals.resize(n);
+  std::vector<double> Vs((size_t)n * n);
+  for (int j = 0; j < n; ++j) { evals[j] = a(order[j], order[j]); for (int k = 0; k < n; ++k) Vs[k + (size_t)j * n] = V[k + (size_t)order[j] * n]; }
+  V.swap(Vs);
+}
+
+void host_expm_complex(int n, std::vector<std::complex<double>>& A) {
+  typedef std::complex<double> C;
+  double nrm = 0.0;
+  for (int j = 0; j < n; ++j) { double s = 0.0; for (int i = 0; i < n; ++i) s += std::abs(A[i + (size_t)j * n]); nrm = std::max(nrm, s); }
+  int sq = 0;
+  while (nrm > 0.25) { nrm *= 0.5; ++sq; }
+  double scale = std::ldexp(1.0, -sq);
+  std::vector<C> X((size_t)n * n), term((size_t)n * n, C(0)), E((size_t)n * n, C(0)), tmp((size_t)n * n);
+  for (size_t i = 0; i < X.size(); ++i) X[i] = A[i] * scale;
+  for (int i = 0; i < n; ++i) { term[i + (size_t)i * n] = 1.0; E[i + (size_t)i * n] = 1.0; }
+  auto matmul = [&](const std::vector<C>& P, const std::vector<C>& Q, std::vector<C>& R) {
+    for (int j = 0; j < n; ++j)
+      for (int i = 0; i < n; ++i) {
+        C s(0);
+        for (int k = 0; k < n; ++k) s += P[i + (size_t)k * n] * Q[k + (size_t)j * n];
+        R[i + (size_t)j * n] = s;
+      }
+  };
+  for (int k = 1; k <= 24; ++k) {
+    matmul(term, X, tmp);
+    for (size_t i = 0; i < tmp.size(); ++i) { term[i] = tmp[i] / (double)k; E[i] += term[i]; }
+  }
+  for (int s = 0; s < sq; ++s) { matmul(E, E, tmp); E.swap(tmp); }
+  A.swap(E);
+}
+
+// ------------------------------------------------------------------------------------------------
+// construction, labels, I/O
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+Net<T>::Net(Ctx* c, int nv, const int32_t* e, int ne, const int64_t* sd) {
+  ctx = c;
+  dtype = ScalarTraits<T>::dtype;
+  NSB_REQUIRE(nv >= 1 && ne == nv - 1, NSB_EINVAL, "network must be a tree (nedges == nverts - 1)");
+  nverts = nv;
+  adj.resize(nv);
+  site_dims.assign(sd, sd + nv);
+  for (int i = 0; i < ne; ++i) {
+    int u = e[2 * i], v = e[2 * i + 1];
+    NSB_REQUIRE(u >= 0 && u < nv && v >= 0 && v < nv && u != v, NSB_EINVAL, "bad edge");
+    NSB_REQUIRE(!eid.count({u, v}), NSB_EINVAL, "duplicate edge");
+    edges.push_back({u, v});
+    eid[{u, v}] = i;
+    eid[{v, u}] = i;
+    adj[u].push_back(v);
+    adj[v].push_back(u);
+  }
+  std::vector<int> seen;
+  if (nv > 1) { subtree(0, -1, seen); NSB_REQUIRE((int)seen.size() == nv, NSB_EINVAL, "graph is not connected"); }
+  psi.resize(nv);
+  W.resize(nv);
+  ver.assign(nv, 0);
+  for (int v = 0; v < nv; ++v) ortho.push_back(v);
+}
+
+template <typename T>
+std::vector<Label> Net<T>::canonical_labels(int v) const {
+  std::vector<Label> out;
+  if (!adj[v].empty()) out.push_back(llink(v, adj[v][0]));
+  out.push_back(lsite(v));
+  for (size_t i = 1; i < adj[v].size(); ++i) out.push_back(llink(v, adj[v][i]));
+  return out;
+}
+
+template <typename T>
+std::vector<Label> Net<T>::decode_legs(int rank, const int32_t* legs, bool is_operator) const {
+  std::vector<Label> out;
+  for (int i = 0; i < rank; ++i) {
+    int a = legs[2 * i], b = legs[2 * i + 1];
+    NSB_REQUIRE(a >= 0 && a < nverts, NSB_EINVAL, "leg: bad vertex");
+    if (b == NSB_SITE) out.push_back(lsite(a, 0));
+    else if (b == NSB_SITE_OUT) out.push_back(lsite(a, 1));
+    else {
+      NSB_REQUIRE(b >= 0 && b < nverts && eid.count({a, b}), NSB_EINVAL, "leg: not an edge of the tree");
+      out.push_back(is_operator ? lop(a, b) : llink(a, b));
+    }
+  }
+  return out;
+}
+
+template <typename T>
+void Net<T>::encode_legs(const std::vector<Label>& labels, int32_t* legs) const {
+  for (size_t i = 0; i < labels.size(); ++i) {
+    Label l = labels[i];
+    int kind = label_kind(l), id = label_id(l);
+    if (kind == LK_SITE) { legs[2 * i] = id; legs[2 * i + 1] = label_plev(l) == 0 ? NSB_SITE : NSB_SITE_OUT; }
+    else if (kind == LK_LINK || kind == LK_OP) { legs[2 * i] = edges[id].first; legs[2 * i + 1] = edges[id].second; }
+    else { legs[2 * i] = -100 - id; legs[2 * i + 1] = -3; }
+  }
+}
+
+template <typename T>
+void Net<T>::canonicalize(int v) {
+  std::vector<Label> can = canonical_labels(v);
+  if (psi[v].labels != can) psi[v] = permuted(ctx, psi[v], can);
+}
+
+template <typename T>
+void Net<T>::site_upload(int v, int rank, const int32_t* legs, const int64_t* dims, const void* host) {
+  NSB_REQUIRE(v >= 0 && v < nverts, NSB_EINVAL, "site_upload: bad vertex");
+  std::vector<Label> labels = decode_legs(rank, legs, false);
+  std::vector<Label> can = canonical_labels(v);
+  {
+    std::vector<Label> a = labels, b = can;
+    std::sort(a.begin(), a.end()); std::sort(b.begin(), b.end());
+    NSB_REQUIRE(a == b, NSB_EINVAL, "site_upload: legs must be the site index and one link per neighbour");
+  }
+  std::vector<int64_t> d(dims, dims + rank);
+  for (int i = 0; i < rank; ++i) {
+    NSB_REQUIRE(d[i] >= 1, NSB_EINVAL, "site_upload: bad dimension");
+    if (label_kind(labels[i]) == LK_SITE) NSB_REQUIRE(d[i] == site_dims[v], NSB_EINVAL, "site_upload: site dimension mismatch");
+  }
+  DTensor<T> t(ctx, d, labels);
+  NSB_CUDA(cudaMemcpyAsync(t.data(), host, sizeof(T) * t.numel(), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->sync();
+  uint64_t pb = ctx->cnt.permute_bytes;
+  psi[v] = t;
+  canonicalize(v);
+  ctx->cnt.permute_bytes = pb;
+  ver[v]++;
+}
+
+template <typename T>
+void Net<T>::site_fill_random(int v, int rank, const int32_t* legs, const int64_t* dims, uint64_t seed, double scale) {
+  NSB_REQUIRE(v >= 0 && v < nverts, NSB_EINVAL, "site_fill_random: bad vertex");
+  std::vector<Label> labels = decode_legs(rank, legs, false);
+  std::vector<int64_t> d(dims, dims + rank);
+  DTensor<T> t(ctx, d, labels);
+  fill_normal<T>(ctx, t.data(), t.numel(), seed, scale);
+  uint64_t pb = ctx->cnt.permute_bytes;
+  psi[v] = t;
+  canonicalize(v);
+  ctx->cnt.permute_bytes = pb;
+  ver[v]++;
+}
+
+template <typename T>
+void Net<T>::site_info(int v, int32_t* rank, int32_t* legs, int64_t* dims) {
+  NSB_REQUIRE(v >= 0 && v < nverts && psi[v].valid(), NSB_EINVAL, "site_info: no tensor");
+  *rank = psi[v].rank();
+  if (legs) encode_legs(psi[v].labels, legs);
+  if (legs)  // orient link legs as (v, neighbour)
+    for (int i = 0; i < psi[v].rank(); ++i)
+      if (legs[2 * i + 1] >= 0 && legs[2 * i] != v) std::swap(legs[2 * i], legs[2 * i + 1]);
+  if (dims) for (int i = 0; i < psi[v].rank(); ++i) dims[i] = psi[v].dims[i];
+}
+
+template <typename T>
+void Net<T>::site_download(int v, void* host) {
+  NSB_REQUIRE(v >= 0 && v < nverts && psi[v].valid(), NSB_EINVAL, "site_download: no tensor");
+  NSB_CUDA(cudaMemcpyAsync(host, psi[v].data(), sizeof(T) * psi[v].numel(), cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->sync();
+}
+
+template <typename T>
+void Net<T>::mpo_upload(int v, int rank, const int32_t* legs, const int64_t* dims, const void* host) {
+  NSB_REQUIRE(v >= 0 && v < nverts, NSB_EINVAL, "mpo_upload: bad vertex");
+  std::vector<Label> labels = decode_legs(rank, legs, true);
+  NSB_REQUIRE(rank == (int)adj[v].size() + 2, NSB_EINVAL, "mpo_upload: need one operator link per neighbour plus site in/out");
+  std::vector<int64_t> d(dims, dims + rank);
+  DTensor<T> t(ctx, d, labels);
+  NSB_REQUIRE(t.find(lsite(v, 0)) >= 0 && t.find(lsite(v, 1)) >= 0, NSB_EINVAL, "mpo_upload: site in/out legs missing");
+  NSB_CUDA(cudaMemcpyAsync(t.data(), host, sizeof(T) * t.numel(), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->sync();
+  W[v] = t;
+  envs.clear();
+  plan.clear();
+}
+
+template <typename T>
+void Net<T>::set_ortho_region(const int32_t* verts, int n) {
+  ortho.assign(verts, verts + n);
+}
+template <typename T>
+void Net<T>::get_ortho_region(int32_t* verts, int32_t* n) {
+  *n = (int)ortho.size();
+  if (verts) for (size_t i = 0; i < ortho.size(); ++i) verts[i] = ortho[i];
+}
+template <typename T>
+int64_t Net<T>::linkdim(int u, int v) {
+  NSB_REQUIRE(eid.count({u, v}) && psi[u].valid(), NSB_EINVAL, "linkdim: bad edge");
+  return psi[u].dim_of(llink(u, v));
+}
+template <typename T>
+int64_t Net<T>::maxlinkdim() {
+  int64_t m = 1;
+  for (auto& e : edges) m = std::max(m, linkdim(e.first, e.second));
+  return m;
+}
+
+// ------------------------------------------------------------------------------------------------
+// graph helpers
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+void Net<T>::subtree(int u, int v, std::vector<int>& out) const {
+  std::vector<int> stack{u};
+  std::vector<char> seen(nverts, 0);
+  seen[u] = 1;
+  if (v >= 0) seen[v] = 1;
+  while (!stack.empty()) {
+    int x = stack.back(); stack.pop_back();
+    out.push_back(x);
+    for (int n : adj[x]) if (!seen[n]) { seen[n] = 1; stack.push_back(n); }
+  }
+}
+
+template <typename T>
+std::vector<int> Net<T>::path(int a, int b) const {
+  std::vector<int> parent(nverts, -2), stack{a};
+  parent[a] = -1;
+  while (!stack.empty()) {
+    int x = stack.back(); stack.pop_back();
+    for (int n : adj[x]) if (parent[n] == -2) { parent[n] = x; stack.push_back(n); }
+  }
+  std::vector<int> p{b};
+  while (p.back() != a) p.push_back(parent[p.back()]);
+  std::reverse(p.begin(), p.end());
+  return p;
+}
+
+// ------------------------------------------------------------------------------------------------
+// gauge moves
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+void Net<T>::qr_step(int a, int b) {
+  Label l = llink(a, b);
+  DTensor<T> A = psi[a];
+  std::vector<Label> order;
+  for (Label x : A.labels) if (x != l) order.push_back(x);
+  order.push_back(l);
+  DTensor<T> Ap = permuted(ctx, A, order);
+  if (Ap.data() == A.data()) Ap = clone(ctx, A);   // qr_thin destroys its input
+  int64_t cols = Ap.dims.back(), rows = Ap.numel() / cols, k = std::min(rows, cols);
+  std::vector<int64_t> qd(Ap.dims.begin(), Ap.dims.end() - 1);
+  qd.push_back(k);
+  DTensor<T> Q(ctx, qd, order);
+  Label aux = make_label(LK_AUX, 1);
+  DTensor<T> R(ctx, {k, cols}, {aux, l});
+  qr_thin<T>(ctx, Ap.data(), rows, cols, rows, Q.data(), rows, R.data(), k);
+  psi[a] = Q;
+  canonicalize(a);
+  ver[a]++;
+  DTensor<T> nb = contract(ctx, psi[b], R, false, false, 1);   // psi[b] with l replaced by aux
+  std::vector<Label> nl = nb.labels;
+  for (auto& x : nl) if (x == aux) x = l;
+  psi[b] = nb.relabeled(nl);
+  canonicalize(b);
+  ver[b]++;
+}
+
+template <typename T>
+int Net<T>::orthogonalize(const std::vector<int>& target) {
+  {
+    std::set<int> s1(target.begin(), target.end()), s2(ortho.begin(), ortho.end());
+    if (s1 == s2) return 0;
+  }
+  // BFS from target[0]
+  int root = target[0];
+  std::vector<int> parent(nverts, -2), dist(nverts, 0), queue{root};
+  parent[root] = -1;
+  for (size_t qi = 0; qi < queue.size(); ++qi) {
+    int x = queue[qi];
+    for (int n : adj[x]) if (parent[n] == -2) { parent[n] = x; dist[n] = dist[x] + 1; queue.push_back(n); }
+  }
+  std::vector<char> mark(nverts, 0);
+  auto mark_path = [&](int t) { while (t != -1 && !mark[t]) { mark[t] = 1; t = parent[t]; } };
+  for (int t : target) mark_path(t);
+  for (int t : ortho) mark_path(t);
+  std::vector<int> order;
+  for (int v = 0; v < nverts; ++v) if (mark[v] && v != root) order.push_back(v);
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return dist[x] > dist[y]; });
+  std::set<int> tset(target.begin(), target.end());
+  int steps = 0;
+  for (int v : order) {
+    int p = parent[v];
+    if (tset.count(v) && tset.count(p)) continue;
+    qr_step(v, p);
+    ++steps;
+  }
+  ortho = target;
+  return steps;
+}
+
+// ------------------------------------------------------------------------------------------------
+// local tensor, environments, H_eff
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+DTensor<T> Net<T>::build_theta(const std::vector<int>& reg) {
+  if (reg.size() == 1) return clone(ctx, psi[reg[0]]);
+  return contract(ctx, psi[reg[0]], psi[reg[1]], false, false, 1);
+}
+
+template <typename T>
+std::vector<Label> Net<T>::w_out_labels(const DTensor<T>& X, const DTensor<T>& Wv, int v, const std::vector<int>& reg) const {
+  std::vector<Label> out;
+  auto is_new = [&](Label l) { return X.find(l) < 0; };
+  auto placed = [&](Label l) { return std::find(out.begin(), out.end(), l) != out.end(); };
+  for (Label lab : X.labels) {
+    if (Wv.find(lab) >= 0) {  // contracted
+      if (lab == lsite(v, 0)) {
+        out.push_back(lsite(v, 1));
+        for (Label wl : Wv.labels) {   // operator link to the next site of the region
+          if (label_kind(wl) != LK_OP || !is_new(wl)) continue;
+          auto e = edges[label_id(wl)];
+          int other = (e.first == v) ? e.second : e.first;
+          if (std::find(reg.begin(), reg.end(), other) != reg.end() && !placed(wl)) out.push_back(wl);
+        }
+      }
+      continue;
+    }
+    out.push_back(lab);
+    if (label_kind(lab) == LK_LINK && label_plev(lab) == 0) {
+      Label ol = make_label(LK_OP, label_id(lab), 0);
+      if (Wv.find(ol) >= 0 && is_new(ol) && !placed(ol)) out.push_back(ol);
+    }
+  }
+  for (Label wl : Wv.labels) if (is_new(wl) && !placed(wl)) out.push_back(wl);
+  return out;
+}
+
+template <typename T>
+int Net<T>::make_env(int u, int v) {
+  auto key = std::make_pair(u, v);
+  if (envs.count(key)) return 0;
+  int built = 0;
+  std::vector<int> others;
+  for (int n : adj[u]) if (n != v) others.push_back(n);
+  for (int n : others) built += make_env(n, u);
+  NSB_REQUIRE(psi[u].valid() && W[u].valid(), NSB_EINVAL, "make_env: state or operator tensor missing");
+  DTensor<T> X = psi[u];
+  size_t start = 0;
+  if (!others.empty()) { X = contract(ctx, X, envs.at({others[0], u}).t, false, false, 1); start = 1; }
+  {
+    SmallOp<T> op;
+    std::vector<int> reg{u};
+    X = apply_small(ctx, op, X, W[u], w_out_labels(X, W[u], u, reg));
+  }
+  for (size_t i = start; i < others.size(); ++i) X = contract(ctx, X, envs.at({others[i], u}).t, false, false, 1);
+  DTensor<T> bra = psi[u].primed();
+  std::vector<Label> want{llink(u, v, 0), lop(u, v), llink(u, v, 1)};
+  std::vector<Label> l1, l2;
+  bool d1 = contract_direct_labels(bra, X, &l1), d2 = contract_direct_labels(X, bra, &l2);
+  DTensor<T> E;
+  if (d1 && l1 == want) E = contract(ctx, bra, X, true, false, 1);
+  else if (d2 && l2 == want) E = contract(ctx, X, bra, false, true, 1);
+  else E = contract(ctx, X, bra, false, true, 0);
+  if (E.labels != want) E = permuted(ctx, E, want);
+  Env env;
+  env.t = E;
+  env.deps.push_back({u, ver[u]});
+  for (int n : others) for (auto& d : envs.at({n, u}).deps) env.deps.push_back(d);
+  envs[key] = env;
+  ctx->cnt.env_builds++;
+  return built + 1;
+}
+
+template <typename T>
+void Net<T>::build_plan() {
+  plan.clear();
+  for (size_t i = 0; i < pos.size(); ++i) {
+    int v = pos[i];
+    std::vector<int> ext;
+    for (int n : adj[v]) if (std::find(pos.begin(), pos.end(), n) == pos.end()) ext.push_back(n);
+    size_t start = 0;
+    if (i == 0 && !ext.empty()) {
+      Step s; s.type = 0; s.u = ext[0]; s.v = v;
+      plan.push_back(std::move(s));
+      start = 1;
+    }
+    { Step s; s.type = 1; s.u = v; s.v = v; plan.push_back(std::move(s)); }
+    for (size_t j = start; j < ext.size(); ++j) {
+      Step s; s.type = 0; s.u = ext[j]; s.v = v;
+      plan.push_back(std::move(s));
+    }
+  }
+}
+
+template <typename T>
+int Net<T>::position(const std::vector<int>& reg) {
+  // drop environments built from tensors that have changed since
+  for (auto it = envs.begin(); it != envs.end();) {
+    bool ok = true;
+    for (auto& d : it->second.deps) if (ver[d.first] != d.second) { ok = false; break; }
+    if (ok) ++it; else it = envs.erase(it);
+  }
+  pos = reg;
+  pos_on_edge = false;
+  int built = 0;
+  for (int v : reg)
+    for (int n : adj[v])
+      if (std::find(reg.begin(), reg.end(), n) == reg.end()) built += make_env(n, v);
+  build_plan();
+  return built;
+}
+
+template <typename T>
+DTensor<T> Net<T>::apply_heff(const DTensor<T>& x) {
+  DTensor<T> X = x;
+  for (auto& s : plan) {
+    if (s.type == 0) X = contract(ctx, X, envs.at({s.u, s.v}).t, false, false, 1);
+    else X = apply_small(ctx, s.op, X, W[s.v], w_out_labels(X, W[s.v], s.v, pos));
+  }
+  X = X.noprime();
+  if (X.labels != x.labels) X = permuted(ctx, X, x.labels);
+  ctx->cnt.matvecs++;
+  return X;
+}
+
+template <typename T>
+double Net<T>::matvec_flops() {
+  NSB_REQUIRE(theta.valid() && !plan.empty(), NSB_EINVAL, "matvec_flops: no local problem (call nsb_extract first)");
+  // dry run over labels/dims
+  std::vector<Label> lab = theta.labels;
+  std::vector<int64_t> dim = theta.dims;
+  double flops = 0.0;
+  auto numel = [&]() { double n = 1; for (auto d : dim) n *= (double)d; return n; };
+  for (auto& s : plan) {
+    const DTensor<T>& Y = (s.type == 0) ? envs.at({s.u, s.v}).t : W[s.v];
+    double kprod = 1, nprod = 1;
+    std::vector<Label> nl;
+    std::vector<int64_t> nd;
+    for (size_t i = 0; i < lab.size(); ++i) {
+      if (Y.find(lab[i]) >= 0) kprod *= (double)dim[i];
+      else { nl.push_back(lab[i]); nd.push_back(dim[i]); }
+    }
+    for (int j = 0; j < Y.rank(); ++j)
+      if (std::find(lab.begin(), lab.end(), Y.labels[j]) == lab.end()) { nprod *= (double)Y.dims[j]; nl.push_back(Y.labels[j]); nd.push_back(Y.dims[j]); }
+    flops += 2.0 * numel() * nprod;   // (numel / kprod) * kprod * nprod multiply-adds
+    (void)kprod;
+    lab = nl; dim = nd;
+  }
+  return flops * (ScalarTraits<T>::is_complex ? 4.0 : 1.0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// subspace expansion (density matrix)
+// ------------------------------------------------------------------------------------------------
+static int64_t compute_expansion(int64_t current_dim, int64_t basis_size, double expansion_factor, int64_t max_expand, int64_t maxdim) {
+  int64_t e = (int64_t)std::ceil(expansion_factor * (double)current_dim);
+  e = std::min(max_expand, e);
+  e = std::min(basis_size - current_dim, e);
+  e = std::min(maxdim - current_dim, e);
+  return std::max<int64_t>(0, e);
+}
+
+template <typename T>
+bool Net<T>::expand_densitymatrix(const nsb_trunc& trunc, const nsb_expand& ex) {
+  if (pos.empty() || pos_on_edge) return false;
+  std::vector<int> prev_set;
+  for (int p : pos) if (std::find(region.begin(), region.end(), p) == region.end()) prev_set.push_back(p);
+  if (prev_set.size() != 1) return false;
+  int prev = prev_set[0];
+  std::vector<int> nexts;
+  for (int v : region) if (eid.count({v, prev})) nexts.push_back(v);
+  if (nexts.empty()) return false;
+  NSB_REQUIRE(nexts.size() == 1, NSB_EINTERNAL, "expansion: ambiguous next vertex");
+  int next = nexts[0];
+  const Label a = llink(prev, next);
+  DTensor<T> A = psi[prev];
+  int64_t cur = A.dim_of(a), nb = A.numel() / cur;
+  int64_t kexp = compute_expansion(cur, nb, ex.expansion_factor, ex.max_expand, trunc.maxdim);
+  if (kexp <= 0) return false;
+  const T one = from_complex<T>(1.0, 0.0), zero = zero_<T>(), mone = from_complex<T>(-1.0, 0.0);
+
+  // sqrt_rho = A * (environments of the previous position that do not touch the new region) * W[prev]
+  std::vector<int> ext;
+  for (int n : adj[prev]) {
+    if (std::find(pos.begin(), pos.end(), n) != pos.end()) continue;      // not an incident edge of the old position
+    if (std::find(region.begin(), region.end(), n) != region.end()) continue;
+    ext.push_back(n);
+  }
+  for (int n : ext) make_env(n, prev);   // present already on every plan the reference generates
+  DTensor<T> X = A;
+  size_t start = 0;
+  if (!ext.empty()) { X = contract(ctx, X, envs.at({ext[0], prev}).t, false, false, 1); start = 1; }
+  {
+    SmallOp<T> op;
+    std::vector<int> reg{prev};
+    X = apply_small(ctx, op, X, W[prev], w_out_labels(X, W[prev], prev, reg));
+  }
+  for (size_t i = start; i < ext.size(); ++i) X = contract(ctx, X, envs.at({ext[i], prev}).t, false, false, 1);
+  // Operator links toward neighbours of `prev` that were skipped stay open, exactly as in the reference.
+  std::vector<Label> basis, basis_p;
+  for (Label l : A.labels) if (l != a) { basis.push_back(l); basis_p.push_back(label_setplev(l, 1)); }
+  std::vector<Label> sorder = basis_p;
+  std::vector<Label> rest;
+  for (Label l : X.labels) if (std::find(basis_p.begin(), basis_p.end(), l) == basis_p.end()) rest.push_back(l);
+  sorder.insert(sorder.end(), rest.begin(), rest.end());
+  DTensor<T> S = permuted(ctx, X, sorder);
+  if (S.data() == X.data() && X.data() == A.data()) S = clone(ctx, S);
+  int64_t ncol = S.numel() / nb;
+  std::vector<Label> aorder = basis;
+  aorder.push_back(a);
+  DTensor<T> Ap = permuted(ctx, A, aorder);     // nb x cur
+  DevBuf tmpbuf(ctx, sizeof(T) * cur * std::max(ncol, kexp + cur));
+  T* tmp = (T*)tmpbuf.ptr;
+  for (int pass = 0; pass < ex.north_pass; ++pass) {
+    gemm<T>(ctx, OP_C, OP_N, cur, ncol, nb, one, Ap.data(), nb, 0, S.data(), nb, 0, zero, tmp, cur, 0, 1);
+    gemm<T>(ctx, OP_N, OP_N, nb, ncol, cur, mone, Ap.data(), nb, 0, tmp, cur, 0, one, S.data(), nb, 0, 1);
+  }
+  DevBuf rho(ctx, sizeof(T) * nb * nb);
+  gemm<T>(ctx, OP_N, OP_C, nb, nb, ncol, one, S.data(), nb, 0, S.data(), nb, 0, zero, (T*)rho.ptr, nb, 0, 1);
+  DevBuf Ub, Cb;
+  std::vector<double> spec;
+  FactorInfo fi = factorize_left<T>(ctx, (T*)rho.ptr, nb, nb, nb, false, trunc.cutoff, trunc.mindim, kexp, true, Ub, Cb, spec);
+  int64_t ku = fi.newdim;
+  T* U = (T*)Ub.ptr;
+  for (int pass = 0; pass < ex.north_pass; ++pass) {
+    gemm<T>(ctx, OP_C, OP_N, cur, ku, nb, one, Ap.data(), nb, 0, U, nb, 0, zero, tmp, cur, 0, 1);
+    gemm<T>(ctx, OP_N, OP_N, nb, ku, cur, mone, Ap.data(), nb, 0, tmp, cur, 0, one, U, nb, 0, 1);
+  }
+  gemm<T>(ctx, OP_C, OP_N, cur, ku, nb, one, Ap.data(), nb, 0, U, nb, 0, zero, tmp, cur, 0, 1);
+  double ovl = vec_nrm2<T>(ctx, cur * ku, tmp);
+  if (ovl > 1e-10) {
+    fprintf(stderr, "Warning: |U*A| = %.3E in subspace expansion\n", ovl);
+    return false;
+  }
+  // Ax = [A, U] along a;  expander = Ax^H A
+  int64_t nx = cur + ku;
+  std::vector<int64_t> axd;
+  for (Label l : basis) axd.push_back(A.dim_of(l));
+  axd.push_back(nx);
+  DTensor<T> Ax(ctx, axd, aorder);
+  vec_copy<T>(ctx, nb * cur, Ap.data(), Ax.data());
+  vec_copy<T>(ctx, nb * ku, U, Ax.data() + nb * cur);
+  Label aux = make_label(LK_AUX, 2);
+  DTensor<T> E(ctx, {nx, cur}, {aux, a});
+  gemm<T>(ctx, OP_C, OP_N, nx, cur, nb, one, Ax.data(), nb, 0, Ap.data(), nb, 0, zero, E.data(), nx, 0, 1);
+  auto relabel_aux = [&](DTensor<T> t) {
+    std::vector<Label> nl = t.labels;
+    for (auto& x : nl) if (x == aux) x = a;
+    return t.relabeled(nl);
+  };
+  psi[prev] = Ax;
+  canonicalize(prev);
+  ver[prev]++;
+  psi[next] = relabel_aux(contract(ctx, psi[next], E, false, false, 1));
+  canonicalize(next);
+  ver[next]++;
+  theta = relabel_aux(contract(ctx, theta, E, false, false, 1));
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the hooks
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+void Net<T>::extract(const int32_t* reg, int nreg, const nsb_trunc* trunc, const nsb_expand* expand, nsb_extract_info* info) {
+  NSB_REQUIRE(nreg == 1 || nreg == 2, NSB_EUNSUPPORTED, "Region of this length not currently supported");
+  std::vector<int> r(reg, reg + nreg);
+  for (int v : r) NSB_REQUIRE(v >= 0 && v < nverts && psi[v].valid() && W[v].valid(), NSB_EINVAL, "extract: bad vertex or missing tensor");
+  if (nreg == 2) NSB_REQUIRE(eid.count({r[0], r[1]}), NSB_EINVAL, "extract: two-site region must be an edge");
+  nsb_trunc tr = trunc ? *trunc : nsb_trunc{0.0, 1, INT64_MAX};
+  int qr_steps, built;
+  {
+    PhaseTimer pt(ctx, NSB_T_GAUGE);
+    qr_steps = orthogonalize(r);
+  }
+  region = r;
+  {
+    PhaseTimer pt(ctx, NSB_T_THETA);
+    theta = build_theta(r);
+  }
+  bool expanded = false;
+  if (expand && expand->algorithm == NSB_EXPAND_DENSITYMATRIX) {
+    PhaseTimer pt(ctx, NSB_T_EXPAND);
+    expanded = expand_densitymatrix(tr, *expand);
+  } else if (expand && expand->algorithm != NSB_EXPAND_NONE) {
+    throw Error(NSB_EUNSUPPORTED, "Subspace expansion not defined for requested subspace_algorithm");
+  }
+  {
+    PhaseTimer pt(ctx, NSB_T_ENV);
+    built = position(r);
+  }
+  if (info) {
+    info->expanded = expanded ? 1 : 0;
+    info->env_builds = built;
+    info->qr_steps = qr_steps;
+    info->local_rank = theta.rank();
+    info->local_numel = theta.numel();
+  }
+}
+
+template <typename T>
+void Net<T>::update_eigsolve(const nsb_krylov* kp, double* eigval, nsb_solve_info* info) {
+  NSB_REQUIRE(theta.valid() && !plan.empty(), NSB_EINVAL, "update_eigsolve: call nsb_extract first");
+  nsb_krylov p = kp ? *kp : nsb_krylov{3, 1, 1e-14, 0, 0, 4, 0};
+  NSB_REQUIRE(p.maxiter == 1, NSB_EUNSUPPORTED, "eigsolve: only maxiter == 1 (no restart) is implemented, as used by the reference");
+  NSB_REQUIRE(p.krylovdim >= 1, NSB_EINVAL, "eigsolve: krylovdim must be >= 1");
+  const int64_t n = theta.numel();
+  const int kmax = (int)std::min<int64_t>(p.krylovdim, n);
+  std::vector<DTensor<T>> V;
+  std::vector<double> alphas, betas;
+  double beta = 0.0, beta_prev = 0.0;
+  int nmv = 0;
+  DTensor<T> v = clone(ctx, theta);
+  {
+    PhaseTimer pt(ctx, NSB_T_KRYLOV);
+    double nrm = vec_nrm2<T>(ctx, n, v.data());
+    NSB_REQUIRE(nrm > 0.0, NSB_EINVAL, "eigsolve: zero initial vector");
+    vec_scale<T>(ctx, n, from_complex<T>(1.0 / nrm, 0.0), v.data());
+  }
+  while (true) {
+    V.push_back(v);
+    DTensor<T> w;
+    {
+      PhaseTimer pt(ctx, NSB_T_MATVEC);
+      w = apply_heff(v);
+      ++nmv;
+    }
+    PhaseTimer pt(ctx, NSB_T_KRYLOV);
+    if (w.data() == v.data()) w = clone(ctx, w);
+    double ar, ai;
+    vec_dot<T>(ctx, n, v.data(), w.data(), &ar, &ai);
+    double alpha = ar;
+    vec_axpy<T>(ctx, n, from_complex<T>(-alpha, 0.0), v.data(), w.data());
+    if (V.size() > 1) vec_axpy<T>(ctx, n, from_complex<T>(-beta_prev, 0.0), V[V.size() - 2].data(), w.data());
+    // full re-orthogonalisation against the whole basis (second modified Gram-Schmidt pass)
+    for (size_t i = 0; i < V.size(); ++i) {
+      double cr, ci;
+      vec_dot<T>(ctx, n, V[i].data(), w.data(), &cr, &ci);
+      vec_axpy<T>(ctx, n, from_complex<T>(-cr, -ci), V[i].data(), w.data());
+      if (i + 1 == V.size()) alpha += cr;
+    }
+    alphas.push_back(alpha);
+    beta = vec_nrm2<T>(ctx, n, w.data());
+    int K = (int)V.size();
+    if (K == kmax || beta <= p.tol || (p.eager && K >= 1)) break;
+    betas.push_back(beta);
+    beta_prev = beta;
+    vec_scale<T>(ctx, n, from_complex<T>(1.0 / beta, 0.0), w.data());
+    v = w;
+  }
+  PhaseTimer pt(ctx, NSB_T_KRYLOV);
+  int K = (int)V.size();
+  std::vector<double> Tm((size_t)K * K, 0.0), evals, evecs;
+  for (int i = 0; i < K; ++i) Tm[i + (size_t)i * K] = alphas[i];
+  for (int i = 0; i + 1 < K; ++i) { Tm[i + (size_t)(i + 1) * K] = betas[i]; Tm[(i + 1) + (size_t)i * K] = betas[i]; }
+  host_sym_eig(K, Tm, evals, evecs);
+  int idx = (p.which == 0) ? 0 : K - 1;
+  std::vector<const T*> ptrs(K);
+  std::vector<T> coef(K);
+  for (int i = 0; i < K; ++i) { ptrs[i] = V[i].data(); coef[i] = from_complex<T>(evecs[i + (size_t)idx * K], 0.0); }
+  DTensor<T> x(ctx, theta.dims, theta.labels);
+  vec_lincomb<T>(ctx, n, K, ptrs.data(), coef.data(), x.data());
+  theta = x;
+  if (eigval) *eigval = evals[idx];
+  if (info) {
+    info->nmatvec = nmv;
+    info->krylovdim = K;
+    info->residual = std::fabs(beta * evecs[(K - 1) + (size_t)idx * K]);
+    info->converged = info->residual <= p.tol ? 1 : 0;
+    info->reserved = 0;
+  }
+}
+
+template <typename T> struct CplxScalar;
+template <> struct CplxScalar<double> {
+  static bool ok(double, double im) { return im == 0.0; }
+  static double make(double re, double) { return re; }
+};
+template <> struct CplxScalar<cdouble> {
+  static bool ok(double, double) { return true; }
+  static cdouble make(double re, double im) { return make_cuDoubleComplex(re, im); }
+};
+
+template <typename T>
+void Net<T>::update_exp(double tre, double tim, int solver, const nsb_krylov* kp, int nsites, int next_vertex, nsb_solve_info* info) {
+  NSB_REQUIRE(theta.valid() && !plan.empty(), NSB_EINVAL, "update_exp: call nsb_extract first");
+  NSB_REQUIRE(CplxScalar<T>::ok(tre, tim), NSB_EINVAL, "update_exp: complex exponent needs a complex128 network");
+  NSB_REQUIRE(!(nsites == 1 && next_vertex >= 0), NSB_EUNSUPPORTED,
+              "1-site applyexp backward (on-edge) step is not implemented yet (SURVEY 8f row 1)");
+  const int64_t n = theta.numel();
+  typedef std::complex<double> C;
+  const C t(tre, tim);
+  auto S = [&](C z) { return CplxScalar<T>::make(z.real(), z.imag()); };
+  auto H = [&](const DTensor<T>& x) {
+    PhaseTimer pt(ctx, NSB_T_MATVEC);
+    DTensor<T> y = apply_heff(x);
+    if (y.data() == x.data()) y = clone(ctx, y);
+    return y;
+  };
+  int nmv = 0;
+  if (solver == NSB_SOLVER_RK) {
+    int order = kp ? kp->rk_order : 4;
+    if (order == 0) order = 4;
+    if (order == 4) {
+      // src/local_solvers/runge_kutta.jl:8-14
+      DTensor<T> k1 = H(theta);
+      DTensor<T> k2 = H(k1);  { PhaseTimer pt(ctx, NSB_T_KRYLOV); vec_scale<T>(ctx, n, S(t / 2.0), k2.data()); vec_axpy<T>(ctx, n, S(1.0), k1.data(), k2.data()); }
+      DTensor<T> k3 = H(k2);  { PhaseTimer pt(ctx, NSB_T_KRYLOV); vec_scale<T>(ctx, n, S(t / 2.0), k3.data()); vec_axpy<T>(ctx, n, S(1.0), k1.data(), k3.data()); }
+      DTensor<T> k4 = H(k3);  { PhaseTimer pt(ctx, NSB_T_KRYLOV); vec_scale<T>(ctx, n, S(t), k4.data()); vec_axpy<T>(ctx, n, S(1.0), k1.data(), k4.data()); }
+      nmv = 4;
+      PhaseTimer pt(ctx, NSB_T_KRYLOV);
+      const T* ptrs[5] = {theta.data(), k1.data(), k2.data(), k3.data(), k4.data()};
+      T coef[5] = {S(1.0), S(t / 6.0), S(t / 3.0), S(t / 3.0), S(t / 6.0)};
+      DTensor<T> out(ctx, theta.dims, theta.labels);
+      vec_lincomb<T>(ctx, n, 5, ptrs, coef, out.data());
+      theta = out;
+    } else if (order == 2) {
+      // src/local_solvers/runge_kutta.jl:2-6
+      DTensor<T> h1 = H(theta);
+      DTensor<T> h2 = H(h1);
+      nmv = 2;
+      PhaseTimer pt(ctx, NSB_T_KRYLOV);
+      const T* ptrs[3] = {theta.data(), h1.data(), h2.data()};
+      T coef[3] = {S(1.0), S(t), S(t * t / 2.0)};
+      DTensor<T> out(ctx, theta.dims, theta.labels);
+      vec_lincomb<T>(ctx, n, 3, ptrs, coef, out.data());
+      theta = out;
+    } else {
+      throw Error(NSB_EINVAL, "For runge_kutta_solver, must specify `order` keyword (2 or 4)");
+    }
+    if (info) { info->nmatvec = nmv; info->krylovdim = 0; info->converged = 1; info->residual = 0.0; info->reserved = 0; }
+    return;
+  }
+  NSB_REQUIRE(solver == NSB_SOLVER_KRYLOV, NSB_EINVAL, "update_exp: unknown solver");
+  // KrylovKit.exponentiate = expintegrator with p = 1 (Lanczos): exp(tA) u0 = u0 + t phi_1(tA) A u0
+  nsb_krylov p = kp ? *kp : nsb_krylov{30, 100, 1e-12, 0, 1, 4, 0};
+  const double tau = std::abs(t);
+  if (tau == 0.0) { if (info) { info->nmatvec = 0; info->krylovdim = 0; info->converged = 1; info->residual = 0; info->reserved = 0; } return; }
+  const C sgn = t / tau;
+  const double eta = p.tol / tau, gamma = 0.8;
+  double totalerr = 0.0, tau0 = 0.0, dtau = tau;
+  int numiter = 1, converged = 0, lastK = 0;
+  DTensor<T> w0 = clone(ctx, theta);
+  DTensor<T> w1 = H(w0); ++nmv;
+  const int kmax = (int)std::min<int64_t>(p.krylovdim, n);
+  bool done = false;
+  while (!done) {
+    double beta = vec_nrm2<T>(ctx, n, w1.data());
+    if (beta < p.tol) { converged = 1; break; }
+    std::vector<DTensor<T>> V;
+    std::vector<double> alphas, betas;
+    DTensor<T> r;
+    double resnorm = 0.0;
+    { DTensor<T> v0 = clone(ctx, w1); vec_scale<T>(ctx, n, from_complex<T>(1.0 / beta, 0.0), v0.data()); V.push_back(v0); }
+    auto expand = [&]() {
+      DTensor<T>& v = V.back();
+      DTensor<T> w = H(v); ++nmv;
+      PhaseTimer pt(ctx, NSB_T_KRYLOV);
+      double ar, ai;
+      vec_dot<T>(ctx, n, v.data(), w.data(), &ar, &ai);
+      double a = ar;
+      vec_axpy<T>(ctx, n, from_complex<T>(-a, 0.0), v.data(), w.data());
+      if (V.size() > 1) vec_axpy<T>(ctx, n, from_complex<T>(-betas.back(), 0.0), V[V.size() - 2].data(), w.data());
+      for (size_t i = 0; i < V.size(); ++i) {
+        double cr, ci;
+        vec_dot<T>(ctx, n, V[i].data(), w.data(), &cr, &ci);
+        vec_axpy<T>(ctx, n, from_complex<T>(-cr, -ci), V[i].data(), w.data());
+        if (i + 1 == V.size()) a += cr;
+      }
+      alphas.push_back(a);
+      r = w;
+      resnorm = vec_nrm2<T>(ctx, n, w.data());
+    };
+    expand();
+    while (true) {
+      int K = (int)V.size();
+      lastK = K;
+      bool stepped = false;
+      double step = 0.0, eps = 0.0, omega = 0.0, q = K / 2.0;
+      std::vector<C> E;
+      auto small_exp = [&](double dt) {
+        int m = K + 2;
+        E.assign((size_t)m * m, C(0));
+        for (int i = 0; i < K; ++i) E[i + (size_t)i * m] = sgn * dt * alphas[i];
+        for (int i = 0; i + 1 < K; ++i) { E[i + (size_t)(i + 1) * m] = sgn * dt * betas[i]; E[(i + 1) + (size_t)i * m] = sgn * dt * betas[i]; }
+        E[0 + (size_t)K * m] = 1.0;
+        E[K + (size_t)(K + 1) * m] = 1.0;
+        host_expm_complex(m, E);
+        return std::abs(dt * beta * resnorm * E[(K - 1) + (size_t)(K + 1) * m]);
+      };
+      if (K == kmax) {
+        dtau = std::min(dtau, tau - tau0);
+        eps = small_exp(dtau);
+        omega = eps / (dtau * eta);
+        while (omega > 1.0) {
+          double eps_prev = eps, dtau_prev = dtau;
+          dtau *= std::pow(gamma / omega, 1.0 / (q + 1.0));
+          eps = small_exp(dtau);
+          omega = eps / (dtau * eta);
+          if (eps <= 0.0) break;
+          q = std::max(0.0, std::log(eps / eps_prev) / std::log(dtau / dtau_prev) - 1.0);
+        }
+        step = dtau;
+        stepped = true;
+      } else if (resnorm <= (tau - tau0) * eta || p.eager) {
+        step = tau - tau0;
+        eps = small_exp(step);
+        omega = eps / (step * eta);
+        if (omega < 1.0) stepped = true;
+      }
+      if (stepped) {
+        PhaseTimer pt(ctx, NSB_T_KRYLOV);
+        totalerr += eps;
+        int m = K + 2;
+        // w0 += beta * sgn * step * ( V * E[0:K, K] + r * E[K-1, K+1] )
+        const C f = beta * sgn * step;
+        std::vector<const T*> ptrs;
+        std::vector<T> coef;
+        for (int i = 0; i < K; ++i) { ptrs.push_back(V[i].data()); coef.push_back(S(f * E[i + (size_t)K * m])); }
+        ptrs.push_back(r.data()); coef.push_back(S(f * E[(K - 1) + (size_t)(K + 1) * m]));
+        ptrs.push_back(w0.data()); coef.push_back(S(1.0));
+        DTensor<T> nw(ctx, theta.dims, theta.labels);
+        vec_lincomb<T>(ctx, n, (int)ptrs.size(), ptrs.data(), coef.data(), nw.data());
+        w0 = nw;
+        tau0 += step;
+        if (K == kmax && omega < gamma) dtau *= std::pow(gamma / std::max(omega, 1e-300), 1.0 / (q + 1.0));
+      }
+      if (tau0 >= tau * (1.0 - 1e-15)) { converged = 1; done = true; break; }
+      if (stepped) break;
+      if (K < kmax && resnorm > 0.0) {
+        PhaseTimer pt(ctx, NSB_T_KRYLOV);
+        betas.push_back(resnorm);
+        DTensor<T> nv = r;
+        vec_scale<T>(ctx, n, from_complex<T>(1.0 / resnorm, 0.0), nv.data());
+        V.push_back(nv);
+      } else break;
+      expand();
+    }
+    if (done) break;
+    if (numiter == p.maxiter) { converged = 0; break; }
+    ++numiter;
+    w1 = H(w0); ++nmv;
+  }
+  theta = w0;
+  if (info) { info->nmatvec = nmv; info->krylovdim = lastK; info->converged = converged; info->residual = totalerr; info->reserved = 0; }
+}
+
+template <typename T>
+void Net<T>::insert(const nsb_trunc* trunc, int normalize, int set_ortho, nsb_insert_info* info) {
+  NSB_REQUIRE(theta.valid() && !region.empty(), NSB_EINVAL, "insert: call nsb_extract first");
+  nsb_trunc tr = trunc ? *trunc : nsb_trunc{0.0, 1, INT64_MAX};
+  nsb_insert_info out{0, 0.0, 0, 0};
+  int last = region.back();
+  if (region.size() == 1) {
+    psi[last] = theta;
+    canonicalize(last);
+    ver[last]++;
+    out.newdim = 0;
+  } else {
+    PhaseTimer pt(ctx, NSB_T_FACTORIZE);
+    int v1 = region[0], v2 = region[1];
+    Label bond = llink(v1, v2);
+    std::vector<Label> left, right;
+    for (Label l : theta.labels) {
+      if (psi[v1].find(l) >= 0) left.push_back(l);
+      else right.push_back(l);
+    }
+    // matricisation without a permute when theta is [left..., right...] or [right..., left...]
+    bool lr = true, rl = true;
+    for (size_t i = 0; i < theta.labels.size(); ++i) {
+      bool isl = std::find(left.begin(), left.end(), theta.labels[i]) != left.end();
+      if (i < left.size() && !isl) lr = false;
+      if (i >= left.size() && isl) lr = false;
+      if (i < right.size() && isl) rl = false;
+      if (i >= right.size() && !isl) rl = false;
+    }
+    DTensor<T> M = theta;
+    bool trans = false;
+    if (lr) trans = false;
+    else if (rl) trans = true;
+    else {
+      std::vector<Label> order = left;
+      order.insert(order.end(), right.begin(), right.end());
+      M = permuted(ctx, theta, order);
+    }
+    int64_t rows = 1, cols = 1;
+    for (Label l : left) rows *= theta.dim_of(l);
+    for (Label l : right) cols *= theta.dim_of(l);
+    DevBuf Ub, Cb;
+    std::vector<double> spec;
+    FactorInfo fi = factorize_left<T>(ctx, M.data(), rows, cols, trans ? cols : rows, trans, tr.cutoff, tr.mindim, tr.maxdim,
+                                      false, Ub, Cb, spec);
+    int64_t k = fi.newdim;
+    std::vector<int64_t> ud, cd;
+    std::vector<Label> ul = left, cl;
+    for (Label l : left) ud.push_back(theta.dim_of(l));
+    ud.push_back(k); ul.push_back(bond);
+    cd.push_back(k); cl.push_back(bond);
+    for (Label l : right) { cd.push_back(theta.dim_of(l)); cl.push_back(l); }
+    DTensor<T> Ut, Ct;
+    Ut.buf = std::make_shared<DevBuf>(std::move(Ub)); Ut.dims = ud; Ut.labels = ul;
+    Ct.buf = std::make_shared<DevBuf>(std::move(Cb)); Ct.dims = cd; Ct.labels = cl;
+    uint64_t pb = ctx->cnt.permute_bytes;
+    psi[v1] = Ut; canonicalize(v1); ver[v1]++;
+    psi[v2] = Ct; canonicalize(v2); ver[v2]++;
+    ctx->cnt.permute_bytes = pb;   // write-back of the factors in canonical (first link, site, other links) order
+    out.newdim = k;
+    out.truncerr = fi.truncerr;
+    out.decomp = fi.decomp;
+    out.jacobi_sweeps = fi.sweeps;
+  }
+  if (set_ortho) ortho = {last};
+  if (normalize) {
+    double nrm = vec_nrm2<T>(ctx, psi[last].numel(), psi[last].data());
+    if (nrm > 0) vec_scale<T>(ctx, psi[last].numel(), from_complex<T>(1.0 / nrm, 0.0), psi[last].data());
+    ver[last]++;
+  }
+  theta = DTensor<T>();
+  if (info) *info = out;
+}
+
+template <typename T>
+void Net<T>::local_info(int32_t* rank, int32_t* legs, int64_t* dims) {
+  NSB_REQUIRE(theta.valid(), NSB_EINVAL, "local_info: no local tensor");
+  *rank = theta.rank();
+  if (legs) encode_legs(theta.labels, legs);
+  if (dims) for (int i = 0; i < theta.rank(); ++i) dims[i] = theta.dims[i];
+}
+template <typename T>
+void Net<T>::local_download(void* host) {
+  NSB_REQUIRE(theta.valid(), NSB_EINVAL, "local_download: no local tensor");
+  NSB_CUDA(cudaMemcpyAsync(host, theta.data(), sizeof(T) * theta.numel(), cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->sync();
+}
+template <typename T>
+void Net<T>::local_upload(const void* host) {
+  NSB_REQUIRE(theta.valid(), NSB_EINVAL, "local_upload: no local tensor");
+  NSB_CUDA(cudaMemcpyAsync(theta.data(), host, sizeof(T) * theta.numel(), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->sync();
+}
+template <typename T>
+void Net<T>::matvec_host(const void* in, void* outp) {
+  NSB_REQUIRE(theta.valid() && !plan.empty(), NSB_EINVAL, "matvec: call nsb_extract first");
+  DTensor<T> x(ctx, theta.dims, theta.labels);
+  NSB_CUDA(cudaMemcpyAsync(x.data(), in, sizeof(T) * x.numel(), cudaMemcpyHostToDevice, ctx->stream));
+  DTensor<T> y = apply_heff(x);
+  NSB_CUDA(cudaMemcpyAsync(outp, y.data(), sizeof(T) * y.numel(), cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->sync();
+}
+template <typename T>
+void Net<T>::matvec_device(int reps, void* host_out) {
+  NSB_REQUIRE(theta.valid() && !plan.empty(), NSB_EINVAL, "matvec: call nsb_extract first");
+  for (int i = 0; i < reps; ++i) last_out = apply_heff(theta);
+  if (host_out && last_out.valid()) {
+    NSB_CUDA(cudaMemcpyAsync(host_out, last_out.data(), sizeof(T) * last_out.numel(), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->sync();
+  }
+}
+template <typename T>
+double Net<T>::norm() {
+  NSB_REQUIRE(ortho.size() == 1, NSB_EINVAL, "norm: needs a single-vertex orthogonality centre");
+  return vec_nrm2<T>(ctx, psi[ortho[0]].numel(), psi[ortho[0]].data());
+}
+
+template struct Net<double>;
+template struct Net<cdouble>;
+
+}  // namespace nsb

@@ -1,0 +1,119 @@
+// Device-resident tree tensor network state + operator + projected-operator environments, and the three
+// region hooks (extract / update / insert) that the NetworkSolvers.jl sweep driver calls.
+#pragma once
+#include <map>
+#include <set>
+
+#include "linalg.h"
+#include "tensor.h"
+
+namespace nsb {
+
+struct NetBase {
+  Ctx* ctx = nullptr;
+  int dtype = NSB_F64;
+  virtual ~NetBase() {}
+  virtual void site_upload(int v, int rank, const int32_t* legs, const int64_t* dims, const void* host) = 0;
+  virtual void site_info(int v, int32_t* rank, int32_t* legs, int64_t* dims) = 0;
+  virtual void site_download(int v, void* host) = 0;
+  virtual void site_fill_random(int v, int rank, const int32_t* legs, const int64_t* dims, uint64_t seed, double scale) = 0;
+  virtual void mpo_upload(int v, int rank, const int32_t* legs, const int64_t* dims, const void* host) = 0;
+  virtual void set_ortho_region(const int32_t* verts, int n) = 0;
+  virtual void get_ortho_region(int32_t* verts, int32_t* n) = 0;
+  virtual int64_t linkdim(int u, int v) = 0;
+  virtual int64_t maxlinkdim() = 0;
+  virtual void env_drop_all() = 0;
+  virtual int env_count() = 0;
+  virtual void extract(const int32_t* region, int nreg, const nsb_trunc* trunc, const nsb_expand* expand, nsb_extract_info* info) = 0;
+  virtual void update_eigsolve(const nsb_krylov* params, double* eigval, nsb_solve_info* info) = 0;
+  virtual void update_exp(double tre, double tim, int solver, const nsb_krylov* params, int nsites, int next_vertex, nsb_solve_info* info) = 0;
+  virtual void insert(const nsb_trunc* trunc, int normalize, int set_ortho, nsb_insert_info* info) = 0;
+  virtual void local_info(int32_t* rank, int32_t* legs, int64_t* dims) = 0;
+  virtual void local_download(void* host) = 0;
+  virtual void local_upload(const void* host) = 0;
+  virtual void matvec_host(const void* in, void* out) = 0;
+  virtual void matvec_device(int reps, void* host_out) = 0;
+  virtual double matvec_flops() = 0;
+  virtual double norm() = 0;
+};
+
+template <typename T>
+struct Net : public NetBase {
+  int nverts = 0;
+  std::vector<std::pair<int, int>> edges;
+  std::vector<std::vector<int>> adj;            // neighbours in edge-insertion order
+  std::map<std::pair<int, int>, int> eid;       // both orientations -> edge id
+  std::vector<int64_t> site_dims;
+  std::vector<DTensor<T>> psi, W;
+  std::vector<uint64_t> ver;                    // bumped whenever psi[v] changes
+  std::vector<int> ortho;                       // orthogonality region
+  // projected operator
+  std::vector<int> pos;                         // current region (vertices); empty before the first extract
+  bool pos_on_edge = false;
+  struct Env { DTensor<T> t; std::vector<std::pair<int, uint64_t>> deps; };
+  std::map<std::pair<int, int>, Env> envs;      // key (u, v): everything on u's side, pointing into v
+  // local problem
+  DTensor<T> theta;
+  std::vector<int> region;
+  struct Step { int type; int u, v; SmallOp<T> op; };   // type 0: environment (u -> v); 1: site operator at v
+  std::vector<Step> plan;
+  DTensor<T> last_out;                          // result of the last nsb_matvec_device
+
+  Net(Ctx* c, int nv, const int32_t* e, int ne, const int64_t* sd);
+
+  // labels
+  Label lsite(int v, int p = 0) const { return make_label(LK_SITE, v, p); }
+  Label llink(int u, int v, int p = 0) const { return make_label(LK_LINK, eid.at({u, v}), p); }
+  Label lop(int u, int v) const { return make_label(LK_OP, eid.at({u, v}), 0); }
+  std::vector<Label> canonical_labels(int v) const;
+  std::vector<Label> decode_legs(int rank, const int32_t* legs, bool is_operator) const;
+  void encode_legs(const std::vector<Label>& labels, int32_t* legs) const;
+  void set_site(int v, const DTensor<T>& t) { psi[v] = t; ver[v]++; }
+  void canonicalize(int v);
+
+  // graph helpers
+  std::vector<int> path(int a, int b) const;
+  void subtree(int u, int v, std::vector<int>& out) const;   // vertices on u's side of edge (u, v)
+
+  // hot path pieces
+  int orthogonalize(const std::vector<int>& target);
+  void qr_step(int a, int b);
+  DTensor<T> build_theta(const std::vector<int>& reg);
+  int position(const std::vector<int>& reg);
+  int make_env(int u, int v);
+  std::vector<Label> w_out_labels(const DTensor<T>& X, const DTensor<T>& Wv, int v, const std::vector<int>& reg) const;
+  void build_plan();
+  DTensor<T> apply_heff(const DTensor<T>& x);
+  bool expand_densitymatrix(const nsb_trunc& trunc, const nsb_expand& ex);
+
+  // NetBase
+  void site_upload(int v, int rank, const int32_t* legs, const int64_t* dims, const void* host) override;
+  void site_info(int v, int32_t* rank, int32_t* legs, int64_t* dims) override;
+  void site_download(int v, void* host) override;
+  void site_fill_random(int v, int rank, const int32_t* legs, const int64_t* dims, uint64_t seed, double scale) override;
+  void mpo_upload(int v, int rank, const int32_t* legs, const int64_t* dims, const void* host) override;
+  void set_ortho_region(const int32_t* verts, int n) override;
+  void get_ortho_region(int32_t* verts, int32_t* n) override;
+  int64_t linkdim(int u, int v) override;
+  int64_t maxlinkdim() override;
+  void env_drop_all() override { envs.clear(); pos.clear(); plan.clear(); }
+  int env_count() override { return (int)envs.size(); }
+  void extract(const int32_t* region, int nreg, const nsb_trunc* trunc, const nsb_expand* expand, nsb_extract_info* info) override;
+  void update_eigsolve(const nsb_krylov* params, double* eigval, nsb_solve_info* info) override;
+  void update_exp(double tre, double tim, int solver, const nsb_krylov* params, int nsites, int next_vertex, nsb_solve_info* info) override;
+  void insert(const nsb_trunc* trunc, int normalize, int set_ortho, nsb_insert_info* info) override;
+  void local_info(int32_t* rank, int32_t* legs, int64_t* dims) override;
+  void local_download(void* host) override;
+  void local_upload(const void* host) override;
+  void matvec_host(const void* in, void* out) override;
+  void matvec_device(int reps, void* host_out) override;
+  double matvec_flops() override;
+  double norm() override;
+};
+
+// small dense host helpers (Ritz problems of the Krylov solvers)
+void host_sym_eig(int n, std::vector<double>& A /* n*n col-major, destroyed */, std::vector<double>& evals,
+                  std::vector<double>& evecs /* n*n col-major */);
+void host_expm_complex(int n, std::vector<std::complex<double>>& A /* n*n col-major, in: A, out: exp(A) */);
+
+}  // namespace nsb

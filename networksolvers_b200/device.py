@@ -1,0 +1,354 @@
+"""Device-side objects: `Context` (one GPU, one stream) and `DeviceNetwork` (state + operator +
+projected-operator environments resident in HBM behind an opaque libnsb200 handle)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from .models import HostTTN, canonical_legs
+
+_default_ctx = None
+
+
+class Context:
+    def __init__(self, device=0):
+        lib = L.load()
+        self._lib = lib
+        h = C.c_void_p()
+        L.check(lib.nsb_ctx_create(int(device), C.byref(h)))
+        self.handle = h
+        self.device = device
+
+    def close(self):
+        if self.handle is not None and self.handle.value:
+            self._lib.nsb_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, code):
+        L.check(code, self.handle)
+
+    def set_option(self, key, value):
+        self.check(self._lib.nsb_ctx_set_option(self.handle, key.encode(), int(value)))
+
+    def synchronize(self):
+        self.check(self._lib.nsb_ctx_synchronize(self.handle))
+
+    def counters(self):
+        c = L.Counters()
+        self.check(self._lib.nsb_ctx_counters(self.handle, C.byref(c)))
+        return c.as_dict()
+
+    def reset_counters(self):
+        self.check(self._lib.nsb_ctx_counters_reset(self.handle))
+
+    def enable_timers(self, on=True):
+        self.check(self._lib.nsb_timers_enable(self.handle, 1 if on else 0))
+
+    def timers(self):
+        arr = (C.c_double * L.NSB_NUM_TIMERS)()
+        self.check(self._lib.nsb_timers_get(self.handle, arr))
+        return dict(zip(L.TIMER_NAMES, list(arr)))
+
+    def reset_timers(self):
+        self.check(self._lib.nsb_timers_reset(self.handle))
+
+    def mem_info(self):
+        f, t, u = C.c_int64(), C.c_int64(), C.c_int64()
+        self.check(self._lib.nsb_mem_info(self.handle, C.byref(f), C.byref(t), C.byref(u)))
+        return dict(free=f.value, total=t.value, pool_used=u.value)
+
+    # ---- dense helpers (kernels under the hooks, exposed for tests / benchmarks) ----
+    @staticmethod
+    def _dt(a):
+        return L.NSB_C128 if np.iscomplexobj(a) else L.NSB_F64
+
+    def gemm(self, A, B, opa="N", opb="N", impl=0):
+        """C = op(A) op(B) through the device GEMM; A, B are 2-D numpy arrays (any layout)."""
+        ops = {"N": 0, "T": 1, "C": 2, "J": 3}
+        cplx = np.iscomplexobj(A) or np.iscomplexobj(B)
+        dt = np.complex128 if cplx else np.float64
+        Af, Bf = np.asfortranarray(A, dtype=dt), np.asfortranarray(B, dtype=dt)
+        m, k = (Af.shape if opa in "NJ" else Af.shape[::-1])
+        k2, n = (Bf.shape if opb in "NJ" else Bf.shape[::-1])
+        assert k == k2, (Af.shape, Bf.shape, opa, opb)
+        Cf = np.empty((m, n), dtype=dt, order="F")
+        self.check(self._lib.nsb_gemm_host(self.handle, L.NSB_C128 if cplx else L.NSB_F64, ops[opa], ops[opb], m, n, k,
+                                            Af.ctypes.data, Af.shape[0], Bf.ctypes.data, Bf.shape[0],
+                                            Cf.ctypes.data, m, impl))
+        return Cf
+
+    def gemm_bench(self, m, n, k, opa="N", opb="N", dtype=np.float64, impl=0, reps=5):
+        ops = {"N": 0, "T": 1, "C": 2, "J": 3}
+        ms = C.c_double()
+        dt = L.NSB_C128 if np.dtype(dtype).kind == "c" else L.NSB_F64
+        self.check(self._lib.nsb_gemm_bench(self.handle, dt, ops[opa], ops[opb], m, n, k, impl, reps, C.byref(ms)))
+        return ms.value
+
+    def factorize(self, M, cutoff=0.0, mindim=1, maxdim=None):
+        """Truncated left-orthogonal factorisation M = U C.  Returns U, C, spectrum (sigma^2), info."""
+        cplx = np.iscomplexobj(M)
+        dt = np.complex128 if cplx else np.float64
+        Mf = np.asfortranarray(M, dtype=dt)
+        rows, cols = Mf.shape
+        k = min(rows, cols)
+        U = np.empty((rows, k), dtype=dt, order="F")
+        Cm = np.empty((k * cols,), dtype=dt)
+        spec = np.empty(k)
+        tr = L.Trunc(cutoff, mindim, L.INT64_MAX if maxdim is None else int(maxdim))
+        info = L.InsertInfo()
+        self.check(self._lib.nsb_factorize_host(self.handle, self._dt(Mf), rows, cols, Mf.ctypes.data, C.byref(tr),
+                                                 U.ctypes.data, Cm.ctypes.data, spec.ctypes.data_as(C.POINTER(C.c_double)),
+                                                 C.byref(info)))
+        nk = info.newdim
+        Uo = np.asfortranarray(U.reshape(-1, order="F")[: rows * nk].reshape((rows, nk), order="F"))
+        Co = Cm[: nk * cols].reshape((nk, cols), order="F")
+        return Uo, Co, spec, dict(newdim=nk, truncerr=info.truncerr, decomp=info.decomp, sweeps=info.jacobi_sweeps)
+
+    def qr(self, M):
+        cplx = np.iscomplexobj(M)
+        dt = np.complex128 if cplx else np.float64
+        Mf = np.asfortranarray(M, dtype=dt)
+        rows, cols = Mf.shape
+        k = min(rows, cols)
+        Q = np.empty((rows, k), dtype=dt, order="F")
+        R = np.empty((k, cols), dtype=dt, order="F")
+        self.check(self._lib.nsb_qr_host(self.handle, self._dt(Mf), rows, cols, Mf.ctypes.data, Q.ctypes.data, R.ctypes.data))
+        return Q, R
+
+    def range_finder(self, A, max_rank, oversample=2, north_pass=2, orthogonal_threshold=1e-12, seed=1):
+        cplx = np.iscomplexobj(A)
+        dt = np.complex128 if cplx else np.float64
+        Af = np.asfortranarray(A, dtype=dt)
+        m, n = Af.shape
+        cap = min(max_rank + oversample, m, n)
+        Q = np.empty((m, max(cap, 1)), dtype=dt, order="F")
+        rank = C.c_int64()
+        self.check(self._lib.nsb_range_finder_host(self.handle, self._dt(Af), m, n, Af.ctypes.data, max_rank, oversample,
+                                                    north_pass, orthogonal_threshold, seed, Q.ctypes.data, C.byref(rank)))
+        return Q[:, : rank.value]
+
+
+def default_context():
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+class DeviceNetwork:
+    """State + operator of one sweep problem on the device.  Built from host tensors by
+    `EigsolveProblem` / `ApplyExpProblem` construction (the counterpart of `permute_indices` +
+    `itn.ProjTTN(H)` in src/eigsolve.jl:69-74, src/applyexp.jl:84-89)."""
+
+    def __init__(self, operator: HostTTN, state: HostTTN, dtype=None, ctx: Context = None):
+        self.ctx = ctx or default_context()
+        self._lib = self.ctx._lib
+        g = state.graph
+        assert g.is_tree(), "the network must be a tree"
+        self.graph = g
+        self.verts = g.vertices
+        self.vid = {v: i for i, v in enumerate(self.verts)}
+        if dtype is None:
+            dtype = np.result_type(operator.dtype(), state.dtype())
+        self.dtype = np.dtype(np.complex128 if np.dtype(dtype).kind == "c" else np.float64)
+        self._dt = L.NSB_C128 if self.dtype.kind == "c" else L.NSB_F64
+        edges = np.array([[self.vid[u], self.vid[v]] for u, v in g.edges], dtype=np.int32).reshape(-1)
+        sdims = np.array([state.tensors[v].shape[state.legs[v].index(("site", v))] for v in self.verts], dtype=np.int64)
+        h = C.c_void_p()
+        self.ctx.check(self._lib.nsb_network_create(self.ctx.handle, len(self.verts),
+                                                     edges.ctypes.data_as(C.POINTER(C.c_int32)), len(g.edges),
+                                                     sdims.ctypes.data_as(C.POINTER(C.c_int64)), self._dt, C.byref(h)))
+        self.handle = h
+        for v in self.verts:
+            self._upload(v, operator.tensors[v], operator.legs[v], True)
+            self._upload(v, state.tensors[v], state.legs[v], False)
+        self.set_ortho_region(state.ortho_region)
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle.value:
+            self._lib.nsb_network_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- leg encoding -------------------------------------------------------------------------
+    def _encode(self, legs):
+        out = []
+        for l in legs:
+            if l[0] == "site":
+                out += [self.vid[l[1]], L.NSB_SITE]
+            elif l[0] == "site_out":
+                out += [self.vid[l[1]], L.NSB_SITE_OUT]
+            else:
+                out += [self.vid[l[1]], self.vid[l[2]]]
+        return np.array(out, dtype=np.int32)
+
+    def _decode(self, legs_arr, rank, owner=None):
+        out = []
+        for i in range(rank):
+            a, b = int(legs_arr[2 * i]), int(legs_arr[2 * i + 1])
+            if b == L.NSB_SITE:
+                out.append(("site", self.verts[a]))
+            elif b == L.NSB_SITE_OUT:
+                out.append(("site_out", self.verts[a]))
+            elif b >= 0:
+                u, v = self.verts[a], self.verts[b]
+                if owner is not None and u != owner:
+                    u, v = v, u
+                out.append(("link", u, v))
+            else:
+                out.append(("aux", a))
+        return out
+
+    def _upload(self, v, arr, legs, is_operator):
+        a = np.asfortranarray(arr, dtype=self.dtype)
+        enc = self._encode(legs)
+        dims = np.array(a.shape, dtype=np.int64)
+        fn = self._lib.nsb_mpo_upload if is_operator else self._lib.nsb_site_upload
+        self.ctx.check(fn(self.handle, self.vid[v], a.ndim, enc.ctypes.data_as(C.POINTER(C.c_int32)),
+                          dims.ctypes.data_as(C.POINTER(C.c_int64)), a.ctypes.data))
+
+    def fill_random(self, v, dims_by_leg, seed, scale):
+        legs = canonical_legs(self.graph, v)
+        enc = self._encode(legs)
+        dims = np.array([dims_by_leg[l] for l in legs], dtype=np.int64)
+        self.ctx.check(self._lib.nsb_site_fill_random(self.handle, self.vid[v], len(legs),
+                                                       enc.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                       dims.ctypes.data_as(C.POINTER(C.c_int64)), seed, scale))
+
+    # ---- state access -------------------------------------------------------------------------
+    def site(self, v):
+        rank = C.c_int32()
+        legs = (C.c_int32 * 32)()
+        dims = (C.c_int64 * 16)()
+        self.ctx.check(self._lib.nsb_site_info(self.handle, self.vid[v], C.byref(rank), legs, dims))
+        shape = [dims[i] for i in range(rank.value)]
+        out = np.empty(shape, dtype=self.dtype, order="F")
+        self.ctx.check(self._lib.nsb_site_download(self.handle, self.vid[v], out.ctypes.data))
+        return out, self._decode(legs, rank.value, owner=v)
+
+    def to_host(self) -> HostTTN:
+        tensors, legs = {}, {}
+        for v in self.verts:
+            tensors[v], legs[v] = self.site(v)
+        return HostTTN(self.graph, tensors, legs, ortho_region=self.ortho_region())
+
+    def set_ortho_region(self, verts):
+        arr = np.array([self.vid[v] for v in verts], dtype=np.int32)
+        self.ctx.check(self._lib.nsb_set_ortho_region(self.handle, arr.ctypes.data_as(C.POINTER(C.c_int32)), len(arr)))
+
+    def ortho_region(self):
+        arr = (C.c_int32 * len(self.verts))()
+        n = C.c_int32()
+        self.ctx.check(self._lib.nsb_get_ortho_region(self.handle, arr, C.byref(n)))
+        return [self.verts[arr[i]] for i in range(n.value)]
+
+    def linkdim(self, u, v):
+        d = C.c_int64()
+        self.ctx.check(self._lib.nsb_linkdim(self.handle, self.vid[u], self.vid[v], C.byref(d)))
+        return d.value
+
+    def linkdims(self):
+        return {(u, v): self.linkdim(u, v) for u, v in self.graph.edges}
+
+    def maxlinkdim(self):
+        d = C.c_int64()
+        self.ctx.check(self._lib.nsb_maxlinkdim(self.handle, C.byref(d)))
+        return d.value
+
+    def norm(self):
+        d = C.c_double()
+        self.ctx.check(self._lib.nsb_norm(self.handle, C.byref(d)))
+        return d.value
+
+    def env_count(self):
+        n = C.c_int32()
+        self.ctx.check(self._lib.nsb_env_count(self.handle, C.byref(n)))
+        return n.value
+
+    # ---- hooks --------------------------------------------------------------------------------
+    def extract(self, region, trunc=None, expand=None):
+        reg = np.array([self.vid[v] for v in region], dtype=np.int32)
+        tr = L.Trunc(*(trunc or (0.0, 1, L.INT64_MAX)))
+        info = L.ExtractInfo()
+        ex = None
+        if expand is not None:
+            ex = L.Expand(expand["algorithm"], expand.get("north_pass", 1), expand.get("expansion_factor", 1.5),
+                          expand.get("max_expand", L.INT64_MAX))
+        self.ctx.check(self._lib.nsb_extract(self.handle, reg.ctypes.data_as(C.POINTER(C.c_int32)), len(reg), C.byref(tr),
+                                              C.byref(ex) if ex is not None else None, C.byref(info)))
+        return info
+
+    def update_eigsolve(self, krylovdim=3, maxiter=1, tol=1e-14, which="SR", eager=False):
+        kp = L.Krylov(krylovdim, maxiter, tol, 0 if which in ("SR", ":SR") else 1, 1 if eager else 0, 4, 0)
+        val = C.c_double()
+        info = L.SolveInfo()
+        self.ctx.check(self._lib.nsb_update_eigsolve(self.handle, C.byref(kp), C.byref(val), C.byref(info)))
+        return val.value, info
+
+    def update_exp(self, t, solver="rk", order=4, krylovdim=30, maxiter=100, tol=1e-12, eager=True, nsites=2,
+                   next_vertex=None):
+        t = complex(t)
+        kp = L.Krylov(krylovdim, maxiter, tol, 0, 1 if eager else 0, order, 0)
+        info = L.SolveInfo()
+        nv = -1 if next_vertex is None else self.vid[next_vertex]
+        self.ctx.check(self._lib.nsb_update_exp(self.handle, t.real, t.imag,
+                                                 L.NSB_SOLVER_RK if solver == "rk" else L.NSB_SOLVER_KRYLOV,
+                                                 C.byref(kp), nsites, nv, C.byref(info)))
+        return info
+
+    def insert(self, trunc=None, normalize=False, set_ortho=True):
+        tr = L.Trunc(*(trunc or (0.0, 1, L.INT64_MAX)))
+        info = L.InsertInfo()
+        self.ctx.check(self._lib.nsb_insert(self.handle, C.byref(tr), 1 if normalize else 0, 1 if set_ortho else 0,
+                                             C.byref(info)))
+        return info
+
+    # ---- local tensor -------------------------------------------------------------------------
+    def local_info(self):
+        rank = C.c_int32()
+        legs = (C.c_int32 * 32)()
+        dims = (C.c_int64 * 16)()
+        self.ctx.check(self._lib.nsb_local_info(self.handle, C.byref(rank), legs, dims))
+        return self._decode(legs, rank.value), [dims[i] for i in range(rank.value)]
+
+    def local_download(self):
+        legs, dims = self.local_info()
+        out = np.empty(dims, dtype=self.dtype, order="F")
+        self.ctx.check(self._lib.nsb_local_download(self.handle, out.ctypes.data))
+        return out, legs
+
+    def local_upload(self, arr):
+        a = np.asfortranarray(arr, dtype=self.dtype)
+        self.ctx.check(self._lib.nsb_local_upload(self.handle, a.ctypes.data))
+
+    def matvec_host(self, x):
+        a = np.asfortranarray(x, dtype=self.dtype)
+        out = np.empty(a.shape, dtype=self.dtype, order="F")
+        self.ctx.check(self._lib.nsb_matvec_host(self.handle, a.ctypes.data, out.ctypes.data))
+        return out
+
+    def matvec_device(self, reps=1, download=False):
+        out = None
+        if download:
+            _, dims = self.local_info()
+            out = np.empty(dims, dtype=self.dtype, order="F")
+        self.ctx.check(self._lib.nsb_matvec_device(self.handle, reps, out.ctypes.data if out is not None else None))
+        return out
+
+    def matvec_flops(self):
+        f = C.c_double()
+        self.ctx.check(self._lib.nsb_matvec_flops(self.handle, C.byref(f)))
+        return f.value

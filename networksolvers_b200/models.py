@@ -1,0 +1,232 @@
+"""Host-side tensor networks: site types, product / random states and the tree-tensor-network operator
+of a sum of one- and two-site terms.  These stand in for the ITensor constructors the reference's callers
+use before they reach the solver entry points (`siteinds`, `ttn(state, sites)`, `random_mps`,
+`mpo(opsum, sites)` / `ttn(opsum, sites)`; examples/dmrg.jl:12-24,59-61).  Everything here is small
+host data handed to the device library through `DeviceNetwork`.
+
+A host tensor is a numpy array plus a list of legs, one per axis:
+    ("site", v)            physical index of vertex v (ket / operator input)
+    ("site_out", v)        primed physical index (operator output)
+    ("link", v, n)         bond on the tree edge {v, n}
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .graphs import NamedGraph, default_root_vertex, _dfs
+
+
+class SiteType:
+    def __init__(self, name):
+        self.name = name
+        if name in ("S=1/2", "S=½"):
+            sz = np.diag([0.5, -0.5])
+            sp = np.array([[0.0, 1.0], [0.0, 0.0]])
+            self.states = {"Up": 0, "Dn": 1}
+        elif name == "S=1":
+            sz = np.diag([1.0, 0.0, -1.0])
+            sp = np.sqrt(2.0) * np.diag([1.0, 1.0], k=1)
+            self.states = {"Up": 0, "Z0": 1, "Dn": 2}
+        else:
+            raise ValueError(f"unknown site type {name}")
+        sm = sp.T.copy()
+        self.dim = sz.shape[0]
+        self.ops = {"Id": np.eye(self.dim), "Sz": sz, "S+": sp, "S-": sm, "Sx": (sp + sm) / 2,
+                    "X": (sp + sm) if self.dim == 2 else (sp + sm) / 2, "Z": 2 * sz if self.dim == 2 else sz}
+
+    def op(self, name):
+        return self.ops[name]
+
+
+class SiteSet:
+    """`siteinds(site_type, graph)`."""
+
+    def __init__(self, site_type, graph):
+        self.graph = graph
+        self.type = site_type if isinstance(site_type, SiteType) else SiteType(site_type)
+        self.dim = self.type.dim
+
+
+def siteinds(site_type, graph_or_n):
+    from .graphs import path_graph
+    g = path_graph(graph_or_n) if isinstance(graph_or_n, int) else graph_or_n
+    return SiteSet(site_type, g)
+
+
+class OpSum:
+    def __init__(self):
+        self.terms = []
+
+    def add(self, coef, *ops_and_sites):
+        assert len(ops_and_sites) in (2, 4)
+        self.terms.append((coef,) + tuple(ops_and_sites))
+        return self
+
+    __iadd__ = lambda self, t: self.add(*t)  # os += (c, "Sz", i, "Sz", j)
+
+
+def heisenberg(graph):
+    os = OpSum()
+    for u, v in graph.edges:
+        os.add(1.0, "Sz", u, "Sz", v)
+        os.add(0.5, "S+", u, "S-", v)
+        os.add(0.5, "S-", u, "S+", v)
+    return os
+
+
+def transverse_ising(graph, J=1.0, h=1.0):
+    os = OpSum()
+    for u, v in graph.edges:
+        os.add(-J, "Z", u, "Z", v)
+    for v in graph.vertices:
+        os.add(-h, "X", v)
+    return os
+
+
+class HostTTN:
+    """Tensors on the vertices of a tree: `tensors[v]` (numpy, C-contiguous logical layout) with `legs[v]`."""
+
+    def __init__(self, graph, tensors, legs, ortho_region=None, site_dim=None):
+        self.graph = graph
+        self.tensors = dict(tensors)
+        self.legs = {v: list(l) for v, l in legs.items()}
+        self.ortho_region = list(ortho_region) if ortho_region is not None else list(graph.vertices)
+        self.site_dim = site_dim
+
+    def __getitem__(self, v):
+        return self.tensors[v]
+
+    def linkdim(self, u, v):
+        return self.tensors[u].shape[self.legs[u].index(("link", u, v))]
+
+    def maxlinkdim(self):
+        return max([self.linkdim(u, v) for u, v in self.graph.edges] or [1])
+
+    def dtype(self):
+        return np.result_type(*[t.dtype for t in self.tensors.values()])
+
+    def to_dense(self):
+        """Contract to a dense vector (small networks only); site order = graph.vertices."""
+        verts = self.graph.vertices
+        post, parent = _dfs(self.graph, verts[0])
+        letters = {}
+
+        def sym(leg):
+            key = leg if leg[0] != "link" else ("link",) + tuple(sorted(leg[1:], key=repr))
+            return letters.setdefault(key, len(letters))
+
+        operands = []
+        for v in verts:
+            operands += [self.tensors[v], [sym(l) for l in self.legs[v]]]
+        out = [sym(("site", v)) for v in verts]
+        return np.einsum(*operands, out).reshape(-1)
+
+
+def canonical_legs(graph, v):
+    """(first link, site, other links) -- the layout `permute_indices` produces (src/permute_indices.jl:4-18)."""
+    nb = graph.neighbors(v)
+    return ([("link", v, nb[0])] if nb else []) + [("site", v)] + [("link", v, n) for n in nb[1:]]
+
+
+def product_state(sites: SiteSet, state, dtype=float):
+    """`ttn(state, sites)`: state maps vertex -> state name (e.g. "Up") or basis index."""
+    g = sites.graph
+    tensors, legs = {}, {}
+    for v in g.vertices:
+        s = state[v] if not callable(state) else state(v)
+        idx = sites.type.states[s] if isinstance(s, str) else int(s)
+        lg = canonical_legs(g, v)
+        arr = np.zeros([sites.dim if l[0] == "site" else 1 for l in lg], dtype=dtype)
+        arr.reshape(-1)[idx] = 1.0
+        tensors[v], legs[v] = arr, lg
+    return HostTTN(g, tensors, legs, site_dim=sites.dim)
+
+
+def _side_size(g, u, v):
+    seen, todo = {u}, [u]
+    while todo:
+        x = todo.pop()
+        for n in g.neighbors(x):
+            if n not in seen and not (x == u and n == v):
+                seen.add(n)
+                todo.append(n)
+    return len(seen)
+
+
+def bond_dims(graph, d, chi):
+    nv = len(graph.vertices)
+    out = {}
+    for u, v in graph.edges:
+        k = _side_size(graph, u, v)
+        k = min(k, nv - k)
+        out[(u, v)] = out[(v, u)] = int(min(chi, d ** min(k, 40)))
+    return out
+
+
+def random_state(sites: SiteSet, link_space, seed=1234, dtype=float):
+    """`random_mps(sites; link_space)`-like synthetic state: i.i.d. N(0,1) entries scaled by 1/sqrt(size);
+    the gauge is left to the first `extracter` call (orthogonality region = all vertices)."""
+    g = sites.graph
+    rng = np.random.default_rng(seed)
+    dims = bond_dims(g, sites.dim, link_space)
+    tensors, legs = {}, {}
+    for v in g.vertices:
+        lg = canonical_legs(g, v)
+        shape = [sites.dim if l[0] == "site" else dims[(l[1], l[2])] for l in lg]
+        arr = rng.standard_normal(shape)
+        if np.issubdtype(np.dtype(dtype), np.complexfloating):
+            arr = arr + 1j * rng.standard_normal(shape)
+        tensors[v] = (arr / np.sqrt(arr.size / shape[0] if len(shape) > 1 else 1.0)).astype(dtype)
+        legs[v] = lg
+    return HostTTN(g, tensors, legs, site_dim=sites.dim)
+
+
+def ttno(opsum: OpSum, sites: SiteSet, root=None, dtype=float):
+    """Exact finite-state-machine TTNO for one-site and nearest-neighbour two-site terms.  Operator link
+    states toward the root: 0 = identity so far, 1 = a complete term lies below, 2+k = term k of that edge
+    started below.  Link dimension 2 + (#terms on the edge): 5 for Heisenberg, 3 for Ising."""
+    g = sites.graph
+    root = default_root_vertex(g) if root is None else root
+    _, parent = _dfs(g, root)
+    d, op = sites.dim, sites.type.op
+    on_edge, on_site = {}, {}
+    for term in opsum.terms:
+        if len(term) == 3:
+            c, a, v = term
+            on_site[v] = on_site.get(v, 0) + c * op(a)
+        else:
+            c, a, u, b, v = term
+            if not g.has_edge(u, v):
+                raise ValueError(f"two-site term on {(u, v)} which is not an edge of the tree")
+            if parent.get(u) == v:
+                on_edge.setdefault(u, []).append((c, a, b))      # keyed by the child vertex
+            else:
+                on_edge.setdefault(v, []).append((c, b, a))
+    wdim = lambda child: 2 + len(on_edge.get(child, []))
+    tensors, legs = {}, {}
+    for v in g.vertices:
+        nb = g.neighbors(v)
+        kids = [n for n in nb if parent.get(n) == v]
+        up = parent[v]
+        shape = [wdim(n) if n in kids else wdim(v) for n in nb]
+        Wt = np.zeros(shape + [d, d], dtype=dtype)                # [..., out, in]
+
+        def at(up_state, kid_states):
+            return tuple((kid_states.get(n, 0) if n in kids else up_state) for n in nb)
+
+        if up is not None:
+            Wt[at(0, {})] += np.eye(d)
+            for k, (c, a, b) in enumerate(on_edge.get(v, [])):
+                Wt[at(2 + k, {})] += c * op(a)
+        for n in kids:
+            Wt[at(1, {n: 1})] += np.eye(d)
+            for k, (c, a, b) in enumerate(on_edge.get(n, [])):
+                Wt[at(1, {n: 2 + k})] += op(b)
+        if v in on_site:
+            Wt[at(1, {})] += on_site[v]
+        tensors[v] = np.swapaxes(Wt, -1, -2).copy()               # [..., in, out]
+        legs[v] = [("link", v, n) for n in nb] + [("site", v), ("site_out", v)]
+    return HostTTN(g, tensors, legs, ortho_region=[], site_dim=d)
+
+
+mpo = ttno

@@ -1,0 +1,234 @@
+"""GPU parity of the sweep hot path against the oracle, through the reference-shaped Python API which
+forwards to the C ABI (nsb_extract / nsb_update_* / nsb_insert / nsb_matvec_host).
+
+Tolerances (BASELINE.json north_star): energies 1e-10 relative, truncation errors 1e-8, TDVP fidelity
+>= 1 - 1e-8; matvec max rel err <= 1e-13 sqrt(K)."""
+import numpy as np
+import pytest
+
+from helpers import SweepRecorder, neel, oracle_array, to_oracle_ttn
+
+pytestmark = pytest.mark.gpu
+
+
+def _ns():
+    import networksolvers_b200 as ns
+    return ns
+
+
+def _oracle_sweeps(H, psi0, **kw):
+    """Run the oracle DMRG recording per-sweep energies / per-region truncation errors."""
+    from oracle import sweep as osw
+    rec = {"E": [], "terr": [], "maxdim": []}
+    osw.COUNTERS.clear()
+
+    def sweep_cb(region_iter, **k):
+        rec["E"].append(region_iter.problem.eigenvalue)
+        rec["maxdim"].append(region_iter.problem.state.maxlinkdim())
+
+    E, psi = osw.dmrg(H, psi0, sweep_callback=sweep_cb, **kw)
+    rec["terr"] = list(osw.COUNTERS.get("truncerrs", []))
+    return E, psi, rec
+
+
+def _oracle_problem_from_device(net, Ho):
+    """Oracle ProjTTN + state built from the tensors currently on the device."""
+    from oracle.projttn import ProjTTN
+    host = net.to_host()
+    return to_oracle_ttn(host), ProjTTN(Ho)
+
+
+@pytest.mark.parametrize("graph_kind,chi,region", [("chain", 16, (4, 5)), ("chain", 16, (6, 5)), ("chain", 12, (1, 2)),
+                                                   ("chain", 12, (10, 9)), ("tree", 6, ((0, 0), (1, 1))),
+                                                   ("tree", 6, ((2, 2), (2, 1)))])
+@pytest.mark.parametrize("cplx", [False, True])
+def test_matvec_matches_oracle(graph_kind, chi, region, cplx):
+    ns = _ns()
+    from oracle.operator_map import optimal_map, operator_map
+    from oracle.projttn import position
+    from oracle.tensor import Tensor
+    g = ns.path_graph(10) if graph_kind == "chain" else ns.star_of_chains(3, 2)
+    sites = ns.siteinds("S=1/2", g)
+    H = ns.ttno(ns.heisenberg(g), sites)
+    psi = ns.random_state(sites, chi, seed=5, dtype=complex if cplx else float)
+    prob = ns.EigsolveProblem(state=psi, operator=H)
+    net = prob.net
+    net.ctx.reset_counters()
+    net.extract(list(region))
+    legs, dims = net.local_info()
+    theta, _ = net.local_download()
+    out = net.matvec_host(theta)
+    # oracle on the gauge-moved tensors that are on the device now
+    Ho = to_oracle_ttn(H, operator=True)
+    psio, P = _oracle_problem_from_device(net, Ho)
+    P = position(P, psio, list(region))
+    from helpers import _olabel
+    th = Tensor(np.array(theta), [_olabel(l) for l in legs])
+    ref = optimal_map(P, th).array(th.labels)
+    ref2 = operator_map(P, th).array(th.labels)
+    K = max(dims) * 5
+    tol = 1e-13 * np.sqrt(K) * np.abs(ref).max()
+    assert np.abs(ref - ref2).max() <= tol
+    assert np.abs(out - ref).max() <= tol, np.abs(out - ref).max()
+    if graph_kind == "chain":
+        assert net.ctx.counters()["permute_bytes"] == 0, "chain hot path must be permutation-free"
+
+
+def test_dmrg_reference_example_s1_n10():
+    """examples/dmrg.jl:10-43 shape (2-site): per-sweep energies vs oracle to 1e-10, final vs -12.8945601."""
+    ns = _ns()
+    from oracle.models import spin_ops, heisenberg_opsum, ttno as ottno, product_ttn
+    from oracle.graph import path_graph as opath
+    g = ns.path_graph(10)
+    sites = ns.siteinds("S=1", g)
+    H = ns.ttno(ns.heisenberg(g), sites)
+    psi0 = ns.product_state(sites, neel(g))
+    trunc = dict(cutoff=1e-12, maxdim=[10, 40, 80, 160])
+    rec = SweepRecorder()
+    E, psi = ns.dmrg(H, psi0, nsweeps=5, nsites=2, inserter_kwargs=dict(trunc=trunc), sweep_callback=rec.sweep,
+                     region_callback=rec.region)
+    Eo, _, orec = _oracle_sweeps(to_oracle_ttn(H, True), to_oracle_ttn(psi0), nsweeps=5, nsites=2,
+                                 inserter_kwargs=dict(trunc=trunc))
+    assert abs(E - (-12.8945601)) < 5e-8
+    for a, b in zip(rec.energies, orec["E"]):
+        assert abs(a - b) <= 1e-10 * abs(b), (rec.energies, orec["E"])
+    assert rec.maxlinkdims == orec["maxdim"]
+    terr = [t for t in rec.truncerrs if t is not None]
+    assert len(terr) == len(orec["terr"])
+    assert np.abs(np.array(terr) - np.array(orec["terr"])).max() <= 1e-8
+
+
+def test_dmrg_config1_heisenberg_n20():
+    """BASELINE config 1: S=1/2 N=20, 2-site, maxdim 100, cutoff 1e-12 (SVD route)."""
+    ns = _ns()
+    g = ns.path_graph(20)
+    sites = ns.siteinds("S=1/2", g)
+    H = ns.ttno(ns.heisenberg(g), sites)
+    psi0 = ns.product_state(sites, neel(g))
+    trunc = dict(cutoff=1e-12, maxdim=100)
+    rec = SweepRecorder()
+    E, psi = ns.dmrg(H, psi0, nsweeps=4, nsites=2, inserter_kwargs=dict(trunc=trunc), sweep_callback=rec.sweep)
+    Eo, _, orec = _oracle_sweeps(to_oracle_ttn(H, True), to_oracle_ttn(psi0), nsweeps=4, nsites=2,
+                                 inserter_kwargs=dict(trunc=trunc))
+    for a, b in zip(rec.energies, orec["E"]):
+        assert abs(a - b) <= 1e-10 * abs(b), (rec.energies, orec["E"])
+    assert abs(E - (-8.682473334399)) < 1e-8
+    assert psi.maxlinkdim() <= 100
+
+
+def test_dmrg_eigen_route_cutoff():
+    """cutoff 1e-9 > 1e-12 takes the reference's "eigen" factorize branch (examples/timed_dmrg/timed_dmrg.jl:29)."""
+    ns = _ns()
+    g = ns.path_graph(12)
+    sites = ns.siteinds("S=1/2", g)
+    H = ns.ttno(ns.heisenberg(g), sites)
+    psi0 = ns.product_state(sites, neel(g))
+    trunc = dict(cutoff=1e-9, maxdim=[10, 40])
+    rec = SweepRecorder()
+    E, psi = ns.dmrg(H, psi0, nsweeps=3, nsites=2, inserter_kwargs=dict(trunc=trunc), sweep_callback=rec.sweep,
+                     region_callback=rec.region)
+    Eo, _, orec = _oracle_sweeps(to_oracle_ttn(H, True), to_oracle_ttn(psi0), nsweeps=3, nsites=2,
+                                 inserter_kwargs=dict(trunc=trunc))
+    for a, b in zip(rec.energies, orec["E"]):
+        assert abs(a - b) <= 1e-10 * abs(b)
+    terr = [t for t in rec.truncerrs if t is not None]
+    assert np.abs(np.array(terr) - np.array(orec["terr"])).max() <= 1e-8
+    assert rec.maxlinkdims == orec["maxdim"]
+
+
+def test_tree_dmrg_two_site_and_one_site_expansion():
+    """test/dmrg/test_tree_dmrg.jl:15-67: |E - E_ED| < 1e-5 (reference's own bar) and 1e-10 vs the oracle."""
+    ns = _ns()
+    g = ns.star_of_chains(3, 3)
+    sites = ns.siteinds("S=1/2", g)
+    H = ns.ttno(ns.heisenberg(g), sites)
+    psi0 = ns.product_state(sites, neel(g))
+    Ex = -4.046057854359
+    trunc = dict(cutoff=1e-5, maxdim=40)
+    rec = SweepRecorder()
+    E, psi = ns.dmrg(H, psi0, nsweeps=5, nsites=2, inserter_kwargs=dict(trunc=trunc), sweep_callback=rec.sweep)
+    assert abs(E - Ex) < 1e-5
+    Eo, _, orec = _oracle_sweeps(to_oracle_ttn(H, True), to_oracle_ttn(psi0), nsweeps=5, nsites=2,
+                                 inserter_kwargs=dict(trunc=trunc))
+    for a, b in zip(rec.energies, orec["E"]):
+        assert abs(a - b) <= 1e-10 * abs(b), (rec.energies, orec["E"])
+    rec = SweepRecorder()
+    ek = dict(trunc=trunc, subspace_algorithm="densitymatrix")
+    E, psi = ns.dmrg(H, psi0, nsweeps=5, nsites=1, extracter_kwargs=ek, inserter_kwargs=dict(trunc=trunc),
+                     sweep_callback=rec.sweep)
+    assert abs(E - Ex) < 1e-5
+    Eo, _, orec = _oracle_sweeps(to_oracle_ttn(H, True), to_oracle_ttn(psi0), nsweeps=5, nsites=1, extracter_kwargs=ek,
+                                 inserter_kwargs=dict(trunc=trunc))
+    assert rec.maxlinkdims == orec["maxdim"]
+    for a, b in zip(rec.energies, orec["E"]):
+        assert abs(a - b) <= 1e-9 * abs(b), (rec.energies, orec["E"])
+
+
+def test_one_site_expansion_chain_example_settings():
+    """examples/dmrg.jl:26-36: 1-site + densitymatrix expansion (expansion_factor 1.1) on the S=1 chain."""
+    ns = _ns()
+    g = ns.path_graph(10)
+    sites = ns.siteinds("S=1", g)
+    H = ns.ttno(ns.heisenberg(g), sites)
+    psi0 = ns.product_state(sites, neel(g))
+    trunc = dict(cutoff=1e-12, maxdim=[10, 40, 80, 160])
+    ek = dict(trunc=trunc, subspace_algorithm="densitymatrix", expansion_factor=1.1)
+    rec = SweepRecorder()
+    E, psi = ns.dmrg(H, psi0, nsweeps=5, nsites=1, extracter_kwargs=ek, inserter_kwargs=dict(trunc=trunc),
+                     sweep_callback=rec.sweep)
+    Eo, _, orec = _oracle_sweeps(to_oracle_ttn(H, True), to_oracle_ttn(psi0), nsweeps=5, nsites=1, extracter_kwargs=ek,
+                                 inserter_kwargs=dict(trunc=trunc))
+    assert rec.maxlinkdims == orec["maxdim"]
+    for a, b in zip(rec.energies, orec["E"]):
+        assert abs(a - b) <= 1e-9 * abs(b), (rec.energies, orec["E"])
+    assert abs(E - (-12.8945601)) < 1e-6
+
+
+@pytest.mark.parametrize("solver_name", ["rk4", "krylov"])
+@pytest.mark.parametrize("order", [2, 4])
+def test_tdvp_two_site_fidelity(order, solver_name):
+    """examples/quench_evolution.jl:20-84 shape: fidelity vs dense expm >= 1 - 1e-8, and vs the oracle state."""
+    ns = _ns()
+    from oracle.ed import ed_time_evolution, state_vector
+    from oracle.models import heisenberg_opsum, spin_ops
+    from oracle import sweep as osw
+    from oracle.local_solvers import runge_kutta_solver as o_rk, exponentiate_solver as o_exp
+    g = ns.path_graph(8)
+    sites = ns.siteinds("S=1/2", g)
+    H = ns.ttno(ns.heisenberg(g), sites)
+    psi0 = ns.product_state(sites, neel(g, even_up=False))
+    tp = list(np.arange(0, 0.3 + 1e-9, 0.05))
+    ik = dict(trunc=dict(maxdim=5000, cutoff=1e-14), normalize=True)
+    uk = dict(solver=ns.runge_kutta_solver, order=4) if solver_name == "rk4" else dict(solver=ns.exponentiate_solver)
+    psit = ns.tdvp(H, psi0, tp, nsites=2, tdvp_order=order, updater_kwargs=uk, inserter_kwargs=ik)
+    v = psit.to_host().to_dense()
+    og = to_oracle_ttn(psi0).graph
+    d, ops, _ = spin_ops("S=1/2")
+    vx = ed_time_evolution(heisenberg_opsum(og), og, ops, psi0.to_dense(), tp, normalize=True)
+    assert 1 - abs(np.vdot(vx, v)) < 1e-8
+    ouk = dict(solver=o_rk, order=4) if solver_name == "rk4" else dict(solver=o_exp)
+    po = osw.tdvp(to_oracle_ttn(H, True), to_oracle_ttn(psi0), tp, nsites=2, tdvp_order=order, updater_kwargs=ouk,
+                  inserter_kwargs=ik)
+    vo = state_vector(po)
+    assert 1 - abs(np.vdot(vo, v)) < 1e-10
+    assert psit.maxlinkdim() == po.maxlinkdim()
+
+
+def test_error_behaviour():
+    """Error paths mirror the reference: unsupported region length (src/inserter.jl:26), unknown expansion
+    backend (src/subspace/subspace.jl:16-20), bad RK order (src/local_solvers/runge_kutta.jl:22)."""
+    ns = _ns()
+    g = ns.path_graph(6)
+    sites = ns.siteinds("S=1/2", g)
+    H = ns.ttno(ns.heisenberg(g), sites)
+    psi0 = ns.product_state(sites, neel(g))
+    prob = ns.EigsolveProblem(state=psi0, operator=H)
+    with pytest.raises(ns.NsbError) as ei:
+        prob.net.extract([1, 2, 3])
+    assert ei.value.code == -6
+    with pytest.raises(ValueError):
+        ns.dmrg(H, psi0, nsweeps=1, nsites=1, extracter_kwargs=dict(subspace_algorithm="nonsense"))
+    with pytest.raises(ValueError):
+        ns.tdvp(H, psi0, [0.0, 0.1], nsites=2, updater_kwargs=dict(solver=ns.runge_kutta_solver, order=3))
+    with pytest.raises(ValueError):
+        ns.tdvp_sub_time_steps(3)
