@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the sweep hot path on B200.
+
+Metric (BASELINE.json): H_eff matvec FP64 TFLOP/s (and 2-site DMRG region / sweep time) at chi = 4096 on the
+S=1/2 Heisenberg chain N = 100 (config 2), synthetic random state, real FP64.
+
+A "step" is one projected effective-Hamiltonian application theta' = H_eff theta (L . W . W . R contraction,
+src/operator_map.jl:3-10 of the reference) on an interior bond.  `value` = algorithmic flops
+(4 w d^2 chi^3 + 4 w^2 d^3 chi^2) x steps / device time, all operands resident in HBM.
+`e2e` = the same matvec through the reference-facing call with HOST buffers (nsb_matvec_host: H2D copy of
+theta, matvec, D2H copy of theta') timed inside the region.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference          # the reference-equivalent CPU path on the host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W_MPO, D_SITE = 5, 2
+
+
+def matvec_flops(chi_l, chi_r, d=D_SITE, w=W_MPO, cplx=False):
+    """Algorithmic flops of the fixed-order matvec for theta[chi_l, d, d, chi_r]."""
+    f = 2.0 * w * chi_l * chi_l * d * d * chi_r          # L . theta
+    f += 2.0 * chi_l * d * chi_r * (w * d) * (d * w)       # W1
+    f += 2.0 * chi_l * d * chi_r * (w * d) * (d * w)       # W2
+    f += 2.0 * chi_l * d * d * chi_r * w * chi_r           # . R
+    return f * (4.0 if cplx else 1.0)
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for nm, val in zip(names, r[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_problem(chi, nsites, ctx, dtype=np.float64):
+    import networksolvers_b200 as ns
+    g = ns.path_graph(nsites)
+    sites = ns.siteinds("S=1/2", g)
+    H = ns.ttno(ns.heisenberg(g), sites)
+    mid = nsites // 2
+    region = [mid, mid + 1]
+    net = ns.DeviceNetwork.synthetic(H, sites, chi, seed=1234, dtype=dtype, ctx=ctx, ortho_region=region)
+    return net, region
+
+
+def cpu_matvec_sample(chi, reps=3, threads=None):
+    """Reference-equivalent CPU path (oracle restatement of optimal_map, NumPy/BLAS) on the host cores for a
+    bounded sample: `reps` matvecs at bond dimension `chi` with synthetic environments."""
+    from oracle.operator_map import optimal_map
+    from oracle.projttn import ProjTTN
+    from oracle.models import TTN
+    from oracle.graph import path_graph
+    from oracle.tensor import Tensor, site, link, oplink
+    rng = np.random.default_rng(1234)
+    g = path_graph(4)
+    d, w = D_SITE, W_MPO
+    Wt = {}
+    for v in (2, 3):
+        Wt[v] = Tensor(rng.standard_normal((w, w, d, d)), [oplink(v - 1, v), oplink(v, v + 1), site(v, 0), site(v, 1)])
+    Hn = TTN(g, {1: None, 2: Wt[2], 3: Wt[3], 4: None}, ortho_region=[])
+    P = ProjTTN(Hn, pos=[2, 3])
+    P.environments[(1, 2)] = Tensor(rng.standard_normal((chi, w, chi)) / chi, [link(1, 2, 0), oplink(1, 2), link(1, 2, 1)])
+    P.environments[(4, 3)] = Tensor(rng.standard_normal((chi, w, chi)) / chi, [link(3, 4, 0), oplink(3, 4), link(3, 4, 1)])
+    theta = Tensor(rng.standard_normal((chi, d, d, chi)), [link(1, 2), site(2), site(3), link(3, 4)])
+    optimal_map(P, theta)            # warm-up (BLAS thread start-up, page faults)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        optimal_map(P, theta)
+    dt = (time.perf_counter() - t0) / reps
+    return matvec_flops(chi, chi) / dt * 1e-12, dt
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        n = [p.get("num_threads") for p in threadpool_info() if p.get("user_api") == "blas"]
+        return max(n) if n else os.cpu_count()
+    except Exception:
+        return os.cpu_count()
+
+
+def run_reference(args, rank, world):
+    """`--impl reference`: the reference's own CPU implementation of the path cannot run (Julia, un-vendored
+    packages), so this times the oracle restatement on the host cores (kind = "port"), rank 0 only."""
+    if rank != 0:
+        return
+    chi = args.cpu_chi
+    for _ in range(max(args.warmup - 1, 0)):
+        cpu_matvec_sample(chi, reps=1)
+    vals = [cpu_matvec_sample(chi, reps=1) for _ in range(max(args.steps, 1))]
+    tf = float(np.mean([v[0] for v in vals]))
+    ms = float(np.mean([v[1] for v in vals]) * 1e3)
+    cores = blas_threads()
+    sample = f"{len(vals)} H_eff matvecs at chi={chi} (of chi={args.chi}), d=2, w=5, NumPy/BLAS, {cores} threads"
+    line = {"impl": "reference", "metric": "heff_matvec_fp64_tflops", "value": tf, "unit": "TFLOP/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"S=1/2 Heisenberg chain N={args.nsites}, 2-site H_eff matvec, chi={args.chi} "
+                                   f"(CPU sample at chi={chi})", "chi": args.chi, "cpu_sample_chi": chi},
+            "cpu_baseline": {"value": tf, "unit": "TFLOP/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": tf, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def pinned_array(shape, dtype):
+    try:
+        import torch
+        t = torch.empty(int(np.prod(shape)), dtype=torch.float64 if np.dtype(dtype).kind == "f" else torch.complex128,
+                        pin_memory=True)
+        return t.numpy().reshape(shape, order="F"), t
+    except Exception:
+        return np.empty(shape, dtype=dtype, order="F"), None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--chi", type=int, default=4096)
+    ap.add_argument("--nsites", type=int, default=100)
+    ap.add_argument("--cpu-chi", type=int, default=2048, help="bond dimension of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--region-step", action="store_true", help="also time full region steps (extract/eigsolve/insert)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import networksolvers_b200 as ns
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = ns.Context(local_rank)
+    net, region = build_problem(args.chi, args.nsites, ctx)
+    t_setup = time.perf_counter()
+    info = net.extract(region)
+    ctx.synchronize()
+    t_setup = time.perf_counter() - t_setup
+    legs, dims = net.local_info()
+    flops = net.matvec_flops()
+    assert abs(flops - matvec_flops(dims[0], dims[-1])) < 1e-6 * flops, (flops, dims)
+    shard = None
+    if world > 1:
+        from networksolvers_b200.parallel import setup_sharded_matvec
+        shard = setup_sharded_matvec(net, dist, rank, world)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.synchronize()
+
+    def step():
+        if shard is not None:
+            shard.matvec()
+        else:
+            net.matvec_device(1)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    ctx.reset_counters()
+    with ClockSampler(local_rank) as clk:
+        ctx.tic()
+        for _ in range(args.steps):
+            step()
+        ms_total = ctx.toc()
+    barrier()
+    launches = ctx.counters()["kernel_launches"]
+    if dist is not None:
+        tmax = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms_total = float(tmax.item())
+    ms_step = ms_total / args.steps
+    tflops = flops / (ms_step * 1e-3) * 1e-12
+
+    # ---- end-to-end through the host-buffer call (rank-local matvec; multi-GPU e2e uses the same sharded step
+    # after a host->device upload of theta) ----
+    nbytes = int(np.prod(dims)) * 8
+    hin, keep1 = pinned_array(dims, np.float64)
+    hin[...] = 0.0
+    theta0, _ = net.local_download()
+    hin[...] = theta0
+    hout, keep2 = pinned_array(dims, np.float64)
+    lib, C = ctx._lib, __import__("ctypes")
+    e2e_steps = max(3, min(args.steps, 5))
+    for _ in range(2):
+        ctx.check(lib.nsb_matvec_host(net.handle, hin.ctypes.data, hout.ctypes.data))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx.check(lib.nsb_matvec_host(net.handle, hin.ctypes.data, hout.ctypes.data))
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if dist is not None:
+        tt = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    e2e_tflops = flops * (world if shard is None and world > 1 else 1) / e2e_s * 1e-12
+
+    # ---- roofline of the dominant kernel (the DMMA GEMM), measured live on this box ----
+    roof = None
+    if rank == 0:
+        chi_l, chi_r = dims[0], dims[-1]
+        peak = ctx.dmma_peak_tflops()
+        m1, n1, k1 = W_MPO * chi_l, D_SITE * D_SITE * chi_r, chi_l          # K1: T1 = L^T theta   (TN)
+        m3, n3, k3 = chi_l * D_SITE * D_SITE, chi_r, W_MPO * chi_r          # K3: theta' = T3 R    (NN)
+        t1 = ctx.gemm_bench(m1, n1, k1, "T", "N", reps=3)
+        t3 = ctx.gemm_bench(m3, n3, k3, "N", "N", reps=3)
+        gflops = 2.0 * m1 * n1 * k1 + 2.0 * m3 * n3 * k3
+        achieved = gflops / ((t1 + t3) * 1e-3) * 1e-12
+        roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "gemm_tma_kernel<double> (K1 TN + K3 NN launches of the matvec)",
+                "k1_ms": t1, "k3_ms": t3,
+                "peak_source": "FP64 DMMA issue ceiling measured live by nsb_dmma_peak (MEASURED_PEAKS.json has no FP64 "
+                               "entry; cuBLAS DGEMM on this pool reaches 35.5-36.0, profiles/r01_microbench_fp64_peaks.jsonl)"}
+
+    extra = {}
+    if args.region_step and rank == 0 and shard is None:
+        ctx.enable_timers(True)
+        ctx.reset_timers()
+        t0 = time.perf_counter()
+        val, sinfo = net.update_eigsolve()
+        ins = net.insert((0.0, 1, args.chi))
+        ctx.synchronize()
+        extra["region_step_s"] = time.perf_counter() - t0
+        extra["region_phase_ms"] = ctx.timers()
+        extra["sweep_s_extrapolated"] = extra["region_step_s"] * 2 * (args.nsites - 1)
+        ctx.enable_timers(False)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ctf, cdt = cpu_matvec_sample(args.cpu_chi, reps=3)
+        cores = blas_threads()
+        cpu = {"value": ctf, "unit": "TFLOP/s", "cores": cores, "kind": "port",
+               "sample": f"3 H_eff matvecs at chi={args.cpu_chi} (GPU arm: chi={args.chi}), oracle restatement of optimal_map "
+                         f"(NumPy/BLAS, {cores} threads); Julia reference not runnable here"}
+
+    if rank == 0:
+        line = {"metric": "heff_matvec_fp64_tflops", "value": tflops * (world if shard is None and world > 1 else 1),
+                "unit": "TFLOP/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "strong" if shard is not None else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"S=1/2 Heisenberg chain N={args.nsites}, no QN, 2-site H_eff matvec on bond "
+                                       f"({region[0]},{region[1]}), chi={args.chi}, d=2, w=5 (BASELINE config 2)",
+                           "chi": args.chi, "local_dims": dims, "flops_per_step": flops,
+                           "l2": "inputs larger than L2 (L 0.64 GB, theta 0.5 GB, T1 2.5 GB per matvec)",
+                           "parallelism": ("replicated" if shard is None else f"theta right-bond sharded x{world} + NCCL allreduce")
+                           if world > 1 else "single GPU", "setup_s": t_setup, "env_builds": info.env_builds},
+                "e2e": {"value": e2e_tflops, "unit": "TFLOP/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+                        "ms_per_step": e2e_s * 1e3},
+                "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roof}
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        line.update(extra)
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

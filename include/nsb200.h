@@ -143,6 +143,9 @@ int nsb_ctx_set_option(nsb_ctx* ctx, const char* key, int64_t value); /* "gemm_i
 int nsb_ctx_counters(nsb_ctx* ctx, nsb_counters* out);
 int nsb_ctx_counters_reset(nsb_ctx* ctx);
 int nsb_ctx_synchronize(nsb_ctx* ctx);
+/* device-side stopwatch on the context's stream (CUDA events): tic records, toc records + waits + returns ms */
+int nsb_event_tic(nsb_ctx* ctx);
+int nsb_event_toc(nsb_ctx* ctx, double* ms_out);
 int nsb_timers_enable(nsb_ctx* ctx, int on);
 int nsb_timers_get(nsb_ctx* ctx, double* ms_out /* NSB_NUM_TIMERS */);
 int nsb_timers_reset(nsb_ctx* ctx);
@@ -204,6 +207,9 @@ int nsb_gemm_host(nsb_ctx* ctx, int32_t dtype, int32_t opa, int32_t opb, int64_t
 /* time `reps` device-resident GEMMs of that shape (random data); returns avg ms per GEMM */
 int nsb_gemm_bench(nsb_ctx* ctx, int32_t dtype, int32_t opa, int32_t opb, int64_t m, int64_t n, int64_t k,
                    int32_t impl, int32_t reps, double* ms_out);
+/* FP64 tensor-pipe (DMMA) issue ceiling of this device, measured live (register-resident mma.sync loop);
+ * the roofline denominator for the GEMM-shaped kernels (MEASURED_PEAKS.json has no FP64 entry). */
+int nsb_dmma_peak(nsb_ctx* ctx, double* tflops_out);
 /* truncated factorisation of a host matrix (rows x cols): U (rows x newdim), C = U^H M (newdim x cols),
  * spectrum (sigma^2, descending, length min(rows, cols)) -- src/inserter.jl:23 semantics. */
 int nsb_factorize_host(nsb_ctx* ctx, int32_t dtype, int64_t rows, int64_t cols, const void* M,

@@ -79,6 +79,8 @@ SIGNATURES = {
     "nsb_ctx_counters": (C.c_int, [_vp, P(Counters)]),
     "nsb_ctx_counters_reset": (C.c_int, [_vp]),
     "nsb_ctx_synchronize": (C.c_int, [_vp]),
+    "nsb_event_tic": (C.c_int, [_vp]),
+    "nsb_event_toc": (C.c_int, [_vp, P(_dbl)]),
     "nsb_timers_enable": (C.c_int, [_vp, C.c_int]),
     "nsb_timers_get": (C.c_int, [_vp, P(_dbl)]),
     "nsb_timers_reset": (C.c_int, [_vp]),
@@ -112,6 +114,7 @@ SIGNATURES = {
     "nsb_norm": (C.c_int, [_vp, P(_dbl)]),
     "nsb_gemm_host": (C.c_int, [_vp, _i32, _i32, _i32, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32]),
     "nsb_gemm_bench": (C.c_int, [_vp, _i32, _i32, _i32, _i64, _i64, _i64, _i32, _i32, P(_dbl)]),
+    "nsb_dmma_peak": (C.c_int, [_vp, P(_dbl)]),
     "nsb_factorize_host": (C.c_int, [_vp, _i32, _i64, _i64, _vp, P(Trunc), _vp, _vp, P(_dbl), P(InsertInfo)]),
     "nsb_qr_host": (C.c_int, [_vp, _i32, _i64, _i64, _vp, _vp, _vp]),
     "nsb_range_finder_host": (C.c_int, [_vp, _i32, _i64, _i64, _vp, _i64, _i32, _i32, _dbl, C.c_uint64, _vp, P(_i64)]),

@@ -48,7 +48,7 @@ PhaseTimer::~PhaseTimer() {
 
 using namespace nsb;
 
-struct nsb_ctx { Ctx c; };
+struct nsb_ctx { Ctx c; int refs = 0; bool destroyed = false; cudaEvent_t ev0 = nullptr, ev1 = nullptr; };
 struct nsb_net { NetBase* n; nsb_ctx* ctx; };
 
 static int fail(Ctx* ctx, int code, const std::string& msg) {
@@ -103,8 +103,16 @@ int nsb_ctx_create(int device, nsb_ctx** out) {
   NSB_CATCH(nullptr)
 }
 
+static void ctx_really_destroy(nsb_ctx* ctx);
+
 int nsb_ctx_destroy(nsb_ctx* ctx) {
   if (!ctx) return NSB_OK;
+  if (ctx->refs > 0) { ctx->destroyed = true; return NSB_OK; }   // networks still alive: defer
+  ctx_really_destroy(ctx);
+  return NSB_OK;
+}
+
+static void ctx_really_destroy(nsb_ctx* ctx) {
   cudaSetDevice(ctx->c.device);
   if (ctx->c.nccl_comm) { ncclCommDestroy((ncclComm_t)ctx->c.nccl_comm); ctx->c.nccl_comm = nullptr; }
   cudaStreamSynchronize(ctx->c.stream);
@@ -112,7 +120,6 @@ int nsb_ctx_destroy(nsb_ctx* ctx) {
   if (ctx->c.h_pinned) cudaFreeHost(ctx->c.h_pinned);
   cudaStreamDestroy(ctx->c.stream);
   delete ctx;
-  return NSB_OK;
 }
 
 int nsb_ctx_set_option(nsb_ctx* ctx, const char* key, int64_t value) {
@@ -136,6 +143,25 @@ int nsb_ctx_counters_reset(nsb_ctx* ctx) { if (!ctx) return NSB_EINVAL; ctx->c.c
 int nsb_ctx_synchronize(nsb_ctx* ctx) {
   if (!ctx) return NSB_EINVAL;
   NSB_TRY(&ctx->c) ctx->c.sync(); NSB_CATCH(&ctx->c)
+}
+int nsb_event_tic(nsb_ctx* ctx) {
+  if (!ctx) return NSB_EINVAL;
+  NSB_TRY(&ctx->c)
+  NSB_CUDA(cudaSetDevice(ctx->c.device));
+  if (!ctx->ev0) { NSB_CUDA(cudaEventCreate(&ctx->ev0)); NSB_CUDA(cudaEventCreate(&ctx->ev1)); }
+  NSB_CUDA(cudaEventRecord(ctx->ev0, ctx->c.stream));
+  NSB_CATCH(&ctx->c)
+}
+int nsb_event_toc(nsb_ctx* ctx, double* ms_out) {
+  if (!ctx || !ms_out) return NSB_EINVAL;
+  NSB_TRY(&ctx->c)
+  NSB_REQUIRE(ctx->ev0, NSB_EINVAL, "nsb_event_toc without nsb_event_tic");
+  NSB_CUDA(cudaEventRecord(ctx->ev1, ctx->c.stream));
+  NSB_CUDA(cudaEventSynchronize(ctx->ev1));
+  float ms = 0;
+  NSB_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  *ms_out = ms;
+  NSB_CATCH(&ctx->c)
 }
 int nsb_timers_enable(nsb_ctx* ctx, int on) { (void)ctx; g_timers_enabled = on != 0; return NSB_OK; }
 int nsb_timers_get(nsb_ctx* ctx, double* ms_out) {
@@ -197,14 +223,17 @@ int nsb_network_create(nsb_ctx* ctx, int32_t nverts, const int32_t* edges, int32
   else throw Error(NSB_EINVAL, "dtype must be NSB_F64 or NSB_C128");
   nsb_net* h = new nsb_net();
   h->n = n; h->ctx = ctx;
+  ctx->refs++;
   *out = h;
   NSB_CATCH(&ctx->c)
 }
 int nsb_network_destroy(nsb_net* net) {
   if (!net) return NSB_OK;
-  cudaSetDevice(net->ctx->c.device);
+  nsb_ctx* ctx = net->ctx;
+  cudaSetDevice(ctx->c.device);
   delete net->n;
   delete net;
+  if (--ctx->refs == 0 && ctx->destroyed) ctx_really_destroy(ctx);
   return NSB_OK;
 }
 
@@ -330,6 +359,14 @@ extern "C" __attribute__((visibility("default"))) int nsb_gemm_bench(nsb_ctx* ct
   NSB_REQUIRE(m > 0 && n > 0 && k > 0 && reps > 0, NSB_EINVAL, "bad arguments");
   *ms_out = dtype == NSB_F64 ? gemm_bench_impl<double>(&ctx->c, opa, opb, m, n, k, impl, reps)
                              : gemm_bench_impl<cdouble>(&ctx->c, opa, opb, m, n, k, impl, reps);
+  NSB_CATCH(&ctx->c)
+}
+
+extern "C" __attribute__((visibility("default"))) int nsb_dmma_peak(nsb_ctx* ctx, double* tflops_out) {
+  if (!ctx || !tflops_out) return NSB_EINVAL;
+  NSB_TRY(&ctx->c)
+  NSB_CUDA(cudaSetDevice(ctx->c.device));
+  *tflops_out = dmma_peak_tflops(&ctx->c);
   NSB_CATCH(&ctx->c)
 }
 

@@ -660,6 +660,42 @@ void gemm(Ctx* ctx, int opa, int opb, int64_t M, int64_t N, int64_t K, T alpha, 
   g_last_impl = "dmma_cpasync";
 }
 
+// ------------------------------------------------------------------------------------------------
+// FP64 tensor-pipe ceiling probe: register-resident DMMA issue loop (no memory traffic)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) dmma_peak_kernel(double* out, int iters) {
+  double a[4], b[2], c[8][4];
+  for (int i = 0; i < 4; ++i) a[i] = 1.0 + 1e-9 * (threadIdx.x + i);
+  for (int i = 0; i < 2; ++i) b[i] = 1e-9 * (threadIdx.x + i);
+  for (int j = 0; j < 8; ++j) for (int i = 0; i < 4; ++i) c[j][i] = 0.0;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mma_16x8x8(c[j], a[0], a[1], a[2], a[3], b[0], b[1]);
+  }
+  double s = 0;
+  for (int j = 0; j < 8; ++j) for (int i = 0; i < 4; ++i) s += c[j][i];
+  if (s == 123.456) out[0] = s;
+}
+
+double dmma_peak_tflops(Ctx* ctx) {
+  const int iters = 8192, warps = 16;
+  cudaEvent_t e0, e1;
+  NSB_CUDA(cudaEventCreate(&e0)); NSB_CUDA(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    NSB_CUDA(cudaEventRecord(e0, ctx->stream));
+    dmma_peak_kernel<<<ctx->num_sms, warps * 32, 0, ctx->stream>>>(ctx->d_scratch, iters);
+    NSB_CUDA(cudaEventRecord(e1, ctx->stream));
+    NSB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    NSB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    double fl = 2.0 * 16 * 8 * 8 * 8.0 * iters * warps * ctx->num_sms;
+    if (rep > 0) best = std::max(best, fl / ms * 1e-9);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return best;
+}
+
 template void gemm<double>(Ctx*, int, int, int64_t, int64_t, int64_t, double, const double*, int64_t, int64_t,
                            const double*, int64_t, int64_t, double, double*, int64_t, int64_t, int64_t, int);
 template void gemm<cdouble>(Ctx*, int, int, int64_t, int64_t, int64_t, cdouble, const cdouble*, int64_t, int64_t,

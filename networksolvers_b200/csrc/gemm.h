@@ -16,4 +16,7 @@ void gemm(Ctx* ctx, int opa, int opb, int64_t M, int64_t N, int64_t K, T alpha, 
 
 const char* gemm_last_impl_name();
 
+// Measured FP64 DMMA issue ceiling of this device (register-resident mma.sync loop), TFLOP/s.
+double dmma_peak_tflops(Ctx* ctx);
+
 }  // namespace nsb

@@ -49,6 +49,14 @@ class Context:
     def reset_counters(self):
         self.check(self._lib.nsb_ctx_counters_reset(self.handle))
 
+    def tic(self):
+        self.check(self._lib.nsb_event_tic(self.handle))
+
+    def toc(self):
+        ms = C.c_double()
+        self.check(self._lib.nsb_event_toc(self.handle, C.byref(ms)))
+        return ms.value
+
     def enable_timers(self, on=True):
         self.check(self._lib.nsb_timers_enable(self.handle, 1 if on else 0))
 
@@ -91,6 +99,11 @@ class Context:
         dt = L.NSB_C128 if np.dtype(dtype).kind == "c" else L.NSB_F64
         self.check(self._lib.nsb_gemm_bench(self.handle, dt, ops[opa], ops[opb], m, n, k, impl, reps, C.byref(ms)))
         return ms.value
+
+    def dmma_peak_tflops(self):
+        v = C.c_double()
+        self.check(self._lib.nsb_dmma_peak(self.handle, C.byref(v)))
+        return v.value
 
     def factorize(self, M, cutoff=0.0, mindim=1, maxdim=None):
         """Truncated left-orthogonal factorisation M = U C.  Returns U, C, spectrum (sigma^2), info."""
@@ -171,6 +184,26 @@ class DeviceNetwork:
             self._upload(v, operator.tensors[v], operator.legs[v], True)
             self._upload(v, state.tensors[v], state.legs[v], False)
         self.set_ortho_region(state.ortho_region)
+
+    @classmethod
+    def synthetic(cls, operator: HostTTN, sites, chi, seed=1234, dtype=np.float64, ctx=None, ortho_region=None):
+        """Network whose state tensors are filled on the device (Philox N(0,1), scaled so that environments stay
+        O(1)) with uniform bond dimension chi capped by d^k at the ends: the synthetic state of SURVEY 8(d)
+        config 2, without moving 25 GiB over PCIe."""
+        from .models import product_state, bond_dims
+        g = sites.graph
+        placeholder = product_state(sites, {v: 0 for v in g.vertices})
+        net = cls(operator, placeholder, dtype=dtype, ctx=ctx)
+        dims = bond_dims(g, sites.dim, chi)
+        for i, v in enumerate(g.vertices):
+            legs = canonical_legs(g, v)
+            d = {l: (sites.dim if l[0] == "site" else dims[(l[1], l[2])]) for l in legs}
+            numel = int(np.prod([d[l] for l in legs]))
+            scale = 1.0 / np.sqrt(max(numel / d[legs[-1]], 1.0)) if len(legs) > 1 else 1.0
+            net.fill_random(v, d, seed + 7 * i, scale)
+        if ortho_region is not None:
+            net.set_ortho_region(ortho_region)
+        return net
 
     def close(self):
         if getattr(self, "handle", None) is not None and self.handle.value:

@@ -53,8 +53,8 @@ def test_matvec_matches_oracle(graph_kind, chi, region, cplx):
     psi = ns.random_state(sites, chi, seed=5, dtype=complex if cplx else float)
     prob = ns.EigsolveProblem(state=psi, operator=H)
     net = prob.net
+    net.extract(list(region))          # includes the initial gauge walk (QR steps may permute)
     net.ctx.reset_counters()
-    net.extract(list(region))
     legs, dims = net.local_info()
     theta, _ = net.local_download()
     out = net.matvec_host(theta)
@@ -232,3 +232,26 @@ def test_error_behaviour():
         ns.tdvp(H, psi0, [0.0, 0.1], nsites=2, updater_kwargs=dict(solver=ns.runge_kutta_solver, order=3))
     with pytest.raises(ValueError):
         ns.tdvp_sub_time_steps(3)
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_chain_region_steps_are_permutation_free(cplx):
+    """After the initial gauge walk, extract (theta build + environment update), the Lanczos update and the
+    insert of consecutive 2-site chain regions move no data through layout permutes, in both directions."""
+    ns = _ns()
+    g = ns.path_graph(10)
+    sites = ns.siteinds("S=1/2", g)
+    H = ns.ttno(ns.heisenberg(g), sites)
+    psi = ns.random_state(sites, 16, seed=5, dtype=complex if cplx else float)
+    net = ns.EigsolveProblem(state=psi, operator=H).net
+    net.extract([4, 5]); net.update_eigsolve(); net.insert((0.0, 1, 16))
+    net.ctx.reset_counters()
+    for region in ([5, 6], [6, 7], [7, 6], [6, 5], [5, 4]):
+        info = net.extract(region)
+        assert info.qr_steps == 0 and info.env_builds <= 1
+        val, sinfo = net.update_eigsolve()
+        assert sinfo.nmatvec == 3
+        net.insert((0.0, 1, 16))
+    c = net.ctx.counters()
+    assert c["permute_bytes"] == 0
+    assert c["matvecs"] == 15
