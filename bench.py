@@ -194,7 +194,7 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = ns.Context(local_rank)
-    net, region = build_problem(args.chi, args.nsites, ctx)
+    net, region = build_problem(args.chi, args.nsites, ctx)   # same seed on every rank: replicated state
     t_setup = time.perf_counter()
     info = net.extract(region)
     ctx.synchronize()
@@ -206,6 +206,8 @@ def main():
     if world > 1:
         from networksolvers_b200.parallel import setup_sharded_matvec
         shard = setup_sharded_matvec(net, dist, rank, world)
+        if not shard.active:
+            shard = None
 
     def barrier():
         if dist is not None:

@@ -152,11 +152,15 @@ int nsb_timers_reset(nsb_ctx* ctx);
 int nsb_mem_info(nsb_ctx* ctx, int64_t* free_bytes, int64_t* total_bytes, int64_t* pool_used_bytes);
 
 /* multi-GPU: one process per GPU; rank 0 creates the id, the host side (torch.distributed, MPI ...)
- * broadcasts the 128 bytes, every rank calls nsb_comm_init.  After that nsb_net_set_shard splits
- * the matvec across ranks. */
+ * broadcasts the 128 bytes, every rank calls nsb_comm_init. */
 int nsb_comm_unique_id(char id_out[128]);
 int nsb_comm_init(nsb_ctx* ctx, const char id[128], int rank, int nranks);
 int nsb_comm_destroy(nsb_ctx* ctx);
+/* Shard every H_eff application of this network across the ranks of the context's communicator: theta is split
+ * along its last bond, each rank contracts its slab (1/nranks of the flops) and one NCCL all-reduce sums the
+ * partial theta'.  `*active` reports whether the current position is shardable (the last bond of theta must
+ * carry the last environment); otherwise the matvec stays replicated.  All ranks must make the same calls. */
+int nsb_net_set_shard(nsb_net* net, int32_t enable, int32_t* active);
 
 /* ---- network (state + operator on a tree) -------------------------------------------------- */
 int nsb_network_create(nsb_ctx* ctx, int32_t nverts, const int32_t* edges /* 2*nedges */, int32_t nedges,

@@ -298,6 +298,9 @@ int nsb_matvec_host(nsb_net* net, const void* host_in, void* host_out) {
 }
 int nsb_matvec_device(nsb_net* net, int32_t reps, void* host_out) { NET_CALL(net, net->n->matvec_device(reps, host_out)) }
 int nsb_matvec_flops(nsb_net* net, double* flops) { NET_CALL(net, NSB_REQUIRE(flops, NSB_EINVAL, "null"); *flops = net->n->matvec_flops()) }
+int nsb_net_set_shard(nsb_net* net, int32_t enable, int32_t* active) {
+  NET_CALL(net, int a = net->n->set_shard(enable); if (active) *active = a)
+}
 int nsb_norm(nsb_net* net, double* out) { NET_CALL(net, NSB_REQUIRE(out, NSB_EINVAL, "null"); *out = net->n->norm()) }
 
 #pragma GCC visibility pop

@@ -13,6 +13,8 @@
 //   Net::expand_densitymatrix  src/subspace/densitymatrix.jl:5-74, src/subspace/subspace.jl:28-48
 #include "net.h"
 
+#include <nccl.h>
+
 #include <algorithm>
 #include <cmath>
 #include <functional>
@@ -446,9 +448,69 @@ int Net<T>::position(const std::vector<int>& reg) {
   return built;
 }
 
+template <typename T> struct NcclType;
+template <> struct NcclType<double> { static constexpr int mult = 1; };
+template <> struct NcclType<cdouble> { static constexpr int mult = 2; };
+
+// Multi-GPU partition of one H_eff application: theta is split along its last bond b across the
+// ranks; every step before the last environment acts on other modes, so it runs unchanged on the slab; the last
+// environment contraction sums over (b, m), so each rank contracts its slab with rows [lo, hi) of that
+// environment and the partial results are summed by one NCCL all-reduce.  State, environments and Krylov
+// vectors stay replicated (every rank runs the same sweep in lock step).
+template <typename T>
+void Net<T>::shard_prepare() {
+  shard_active = false;
+  if (!shard_enabled || ctx->nranks <= 1 || !ctx->nccl_comm || plan.empty() || !theta.valid()) return;
+  const Step& last = plan.back();
+  if (last.type != 0) return;
+  const DTensor<T>& E = envs.at({last.u, last.v}).t;
+  Label lb = llink(last.u, last.v, 0);
+  if (theta.labels.back() != lb || E.labels[0] != lb) return;     // last bond of theta must be that environment's ket link
+  for (size_t i = 0; i + 1 < plan.size(); ++i)
+    if (plan[i].type == 0 && plan[i].u == last.u && plan[i].v == last.v) return;
+  int64_t nb = theta.dims.back();
+  int64_t per = (nb + ctx->nranks - 1) / ctx->nranks;
+  shard_lo = std::min<int64_t>(nb, per * ctx->rank);
+  shard_hi = std::min<int64_t>(nb, shard_lo + per);
+  int64_t rows = shard_hi - shard_lo, cols = E.numel() / nb;
+  std::vector<int64_t> d = E.dims;
+  d[0] = rows;
+  shard_env = DTensor<T>(ctx, d, E.labels);
+  if (rows > 0) copy_block<T>(ctx, E.data() + shard_lo, nb, shard_env.data(), rows, rows, cols);
+  shard_active = true;
+}
+
+template <typename T>
+int Net<T>::set_shard(int enable) {
+  shard_enabled = enable != 0;
+  shard_prepare();
+  return shard_active ? 1 : 0;
+}
+
 template <typename T>
 DTensor<T> Net<T>::apply_heff(const DTensor<T>& x) {
   DTensor<T> X = x;
+  if (shard_active) {
+    DTensor<T> out(ctx, x.dims, x.labels);
+    if (shard_hi > shard_lo) {
+      X = x.last_mode_slab(shard_lo, shard_hi);
+      for (size_t i = 0; i + 1 < plan.size(); ++i) {
+        auto& s = plan[i];
+        if (s.type == 0) X = contract(ctx, X, envs.at({s.u, s.v}).t, false, false, 1);
+        else X = apply_small(ctx, s.op, X, W[s.v], w_out_labels(X, W[s.v], s.v, pos));
+      }
+      X = contract(ctx, X, shard_env, false, false, 1).noprime();
+      if (X.labels != x.labels) X = permuted(ctx, X, x.labels);
+      out = X;
+    } else {
+      vec_zero<T>(ctx, out.numel(), out.data());
+    }
+    ncclResult_t r = ncclAllReduce(out.data(), out.data(), (size_t)out.numel() * NcclType<T>::mult, ncclDouble, ncclSum,
+                                   (ncclComm_t)ctx->nccl_comm, ctx->stream);
+    if (r != ncclSuccess) throw Error(NSB_ENCCL, std::string("ncclAllReduce: ") + ncclGetErrorString(r));
+    ctx->cnt.matvecs++;
+    return out;
+  }
   for (auto& s : plan) {
     if (s.type == 0) X = contract(ctx, X, envs.at({s.u, s.v}).t, false, false, 1);
     else X = apply_small(ctx, s.op, X, W[s.v], w_out_labels(X, W[s.v], s.v, pos));
@@ -625,6 +687,7 @@ void Net<T>::extract(const int32_t* reg, int nreg, const nsb_trunc* trunc, const
     PhaseTimer pt(ctx, NSB_T_ENV);
     built = position(r);
   }
+  shard_prepare();
   if (info) {
     info->expanded = expanded ? 1 : 0;
     info->env_builds = built;

@@ -35,6 +35,7 @@ struct NetBase {
   virtual void matvec_device(int reps, void* host_out) = 0;
   virtual double matvec_flops() = 0;
   virtual double norm() = 0;
+  virtual int set_shard(int enable) = 0;   // returns 1 if the current position is sharded across ranks
 };
 
 template <typename T>
@@ -58,6 +59,11 @@ struct Net : public NetBase {
   struct Step { int type; int u, v; SmallOp<T> op; };   // type 0: environment (u -> v); 1: site operator at v
   std::vector<Step> plan;
   DTensor<T> last_out;                          // result of the last nsb_matvec_device
+  // multi-GPU: theta sharded along its last bond across the ranks of ctx->nccl_comm
+  bool shard_enabled = false, shard_active = false;
+  int64_t shard_lo = 0, shard_hi = 0;
+  DTensor<T> shard_env;                         // rows [shard_lo, shard_hi) of the last environment
+  void shard_prepare();
 
   Net(Ctx* c, int nv, const int32_t* e, int ne, const int64_t* sd);
 
@@ -109,6 +115,7 @@ struct Net : public NetBase {
   void matvec_device(int reps, void* host_out) override;
   double matvec_flops() override;
   double norm() override;
+  int set_shard(int enable) override;
 };
 
 // small dense host helpers (Ritz problems of the Krylov solvers)

@@ -23,6 +23,7 @@ inline Label label_setplev(Label l, int p) { return (Label)((l & ~(3 << 2)) | (p
 template <typename T>
 struct DTensor {
   std::shared_ptr<DevBuf> buf;
+  int64_t offset = 0;            // element offset into buf (views of a slab along the last mode)
   std::vector<int64_t> dims;
   std::vector<Label> labels;
 
@@ -31,7 +32,7 @@ struct DTensor {
     NSB_REQUIRE(d.size() == l.size(), NSB_EINTERNAL, "DTensor: rank mismatch");
     buf = std::make_shared<DevBuf>(ctx, sizeof(T) * (size_t)std::max<int64_t>(numel(), 1));
   }
-  T* data() const { return buf ? reinterpret_cast<T*>(buf->ptr) : nullptr; }
+  T* data() const { return buf ? reinterpret_cast<T*>(buf->ptr) + offset : nullptr; }
   int rank() const { return (int)dims.size(); }
   int64_t numel() const { int64_t n = 1; for (auto d : dims) n *= d; return n; }
   int find(Label l) const { for (int i = 0; i < rank(); ++i) if (labels[i] == l) return i; return -1; }
@@ -42,6 +43,15 @@ struct DTensor {
   DTensor<T> primed(int inc = 1) const {
     DTensor<T> t = *this;
     for (auto& l : t.labels) l = label_setplev(l, label_plev(l) + inc);
+    return t;
+  }
+  // view of indices [lo, hi) of the last (slowest) mode; shares the buffer
+  DTensor<T> last_mode_slab(int64_t lo, int64_t hi) const {
+    DTensor<T> t = *this;
+    int64_t inner = 1;
+    for (int i = 0; i + 1 < rank(); ++i) inner *= dims[i];
+    t.offset = offset + lo * inner;
+    t.dims.back() = hi - lo;
     return t;
   }
   DTensor<T> noprime() const {

@@ -1,0 +1,110 @@
+"""CPU tests of the host side: the C ABI exports every symbol of include/nsb200.h, the host-side control flow
+(region plans, truncation parameters, kwarg routing) matches the oracle, and there is no CPU fallback."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from networksolvers_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "nsb200.h")).read()
+    declared = set(re.findall(r"^(?:int|const char\*)\s+(nsb_\w+)\s*\(", header, flags=re.M))
+    assert len(declared) >= 40
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.load()                      # raises if a declared symbol is missing from the .so
+    for name in declared:
+        assert hasattr(lib, name)
+    assert b"sm_100a" in lib.nsb_version()
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path must fail loudly (no oracle / CPU route)."""
+    from helpers import cuda_available
+    import networksolvers_b200 as ns
+    if cuda_available():
+        pytest.skip("GPU present")
+    with pytest.raises(ns.NsbError) as ei:
+        ns.Context(0)
+    assert ei.value.code == -3
+    src = "".join(open(os.path.join(ROOT, "networksolvers_b200", f)).read()
+                  for f in os.listdir(os.path.join(ROOT, "networksolvers_b200")) if f.endswith(".py"))
+    assert "import oracle" not in src and "from oracle" not in src
+
+
+def test_region_plans_match_oracle():
+    import networksolvers_b200 as ns
+    from networksolvers_b200 import region_plans as rp
+    from oracle import region_plans as orp
+    from helpers import to_oracle_graph
+    for g in (ns.path_graph(7), ns.star_of_chains(3, 3), ns.named_comb_tree([3, 1, 2, 4])):
+        og = to_oracle_graph(g)
+        for nsites in (1, 2):
+            a = [r for r, _ in rp.euler_sweep(g, nsites=nsites)]
+            b = [r for r, _ in orp.euler_sweep(og, nsites=nsites)]
+            assert a == b
+            a = [r for r, _ in rp.post_order_dfs_sweep(g, nsites=nsites)]
+            b = [r for r, _ in orp.post_order_dfs_sweep(og, nsites=nsites)]
+            assert a == b
+            for order in (1, 2, 4):
+                pa = rp.tdvp_regions(g, 0.1, updater_kwargs=dict(x=1), tdvp_order=order, nsites=nsites, sweep=1)
+                pb = orp.tdvp_regions(og, 0.1, updater_kwargs=dict(x=1), tdvp_order=order, nsites=nsites, sweep=1)
+                assert [r for r, _ in pa] == [r for r, _ in pb]
+                assert [k["updater_kwargs"]["time_step"] for _, k in pa] == [k["updater_kwargs"]["time_step"] for _, k in pb]
+                assert all(("nsites" in ka) == ("nsites" in kb) for (_, ka), (_, kb) in zip(pa, pb))
+
+
+def test_euler_tour_reference_properties():
+    """test/test_euler_tour.jl:9-25 on the product's own implementation."""
+    import networksolvers_b200 as ns
+    g = ns.star_of_chains(3, 3)
+    tour = ns.euler_tour_edges(g, (0, 0))
+    assert all(a[1] == b[0] for a, b in zip(tour[:-1], tour[1:]))
+    for (u, v) in g.edges:
+        assert (u, v) in tour and (v, u) in tour
+    assert set(ns.euler_tour_vertices(g, (0, 0))) == set(g.vertices)
+
+
+def test_truncation_parameters_and_expansion_rule():
+    import networksolvers_b200 as ns
+    from oracle.truncation_parameters import truncation_parameters as otp
+    from oracle.subspace import compute_expansion as oce
+    for sweep in range(1, 7):
+        kw = dict(cutoff=[1e-5, 1e-8], maxdim=[10, 20, 40], mindim=2)
+        assert ns.truncation_parameters(sweep, **kw) == otp(sweep, **kw)
+    assert ns.truncation_parameters(3) == otp(3)
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        cur, basis = int(rng.integers(1, 50)), int(rng.integers(1, 200))
+        kw = dict(expansion_factor=float(rng.uniform(0.1, 2.0)), max_expand=int(rng.integers(1, 60)), maxdim=int(rng.integers(1, 120)))
+        assert ns.compute_expansion(cur, basis, **kw) == oce(cur, basis, **kw)
+
+
+def test_ttno_builder_matches_oracle_and_dense():
+    import networksolvers_b200 as ns
+    from helpers import to_oracle_ttn, to_oracle_graph
+    from oracle.ed import ttno_dense, dense_hamiltonian
+    from oracle.models import heisenberg_opsum, ising_opsum, spin_ops
+    for g in (ns.path_graph(5), ns.star_of_chains(3, 2)):
+        sites = ns.siteinds("S=1/2", g)
+        og = to_oracle_graph(g)
+        d, ops, _ = spin_ops("S=1/2")
+        for mine, theirs in ((ns.heisenberg(g), heisenberg_opsum(og)), (ns.transverse_ising(g, 1.0, 0.7), ising_opsum(og, 1.0, 0.7))):
+            H = ns.ttno(mine, sites)
+            M = ttno_dense(to_oracle_ttn(H, operator=True), og, d)
+            assert np.abs(M - dense_hamiltonian(theirs, og, ops, sparse=False)).max() < 1e-13
+
+
+def test_shard_bounds_partition():
+    from networksolvers_b200.parallel import shard_bounds
+    for dim in (1, 5, 7, 4096, 4097):
+        for n in (1, 2, 3, 8):
+            cover = []
+            for r in range(n):
+                lo, hi = shard_bounds(dim, r, n)
+                assert 0 <= lo <= hi <= dim
+                cover += list(range(lo, hi))
+            assert cover == list(range(dim))

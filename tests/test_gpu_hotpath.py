@@ -255,3 +255,17 @@ def test_chain_region_steps_are_permutation_free(cplx):
     c = net.ctx.counters()
     assert c["permute_bytes"] == 0
     assert c["matvecs"] == 15
+
+
+def test_sharded_matvec_two_gpus():
+    """theta sharded along its last bond over 2 ranks + NCCL all-reduce == single-GPU matvec."""
+    import os, subprocess, sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29531", os.path.join(root, "tests", "_nccl_shard_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "NCCL_SHARD_OK 2" in r.stdout
