@@ -1,5 +1,5 @@
 // extern "C" boundary of libnsb200.so (declared in include/nsb200.h).  Nothing throws across it.
-#include <nccl.h>
+#include "nccl_dyn.h"
 
 #include <random>
 
@@ -114,7 +114,7 @@ int nsb_ctx_destroy(nsb_ctx* ctx) {
 
 static void ctx_really_destroy(nsb_ctx* ctx) {
   cudaSetDevice(ctx->c.device);
-  if (ctx->c.nccl_comm) { ncclCommDestroy((ncclComm_t)ctx->c.nccl_comm); ctx->c.nccl_comm = nullptr; }
+  if (ctx->c.nccl_comm) { try { nccl_api().CommDestroy((ncclComm_t)ctx->c.nccl_comm); } catch (...) {} ctx->c.nccl_comm = nullptr; }
   cudaStreamSynchronize(ctx->c.stream);
   if (ctx->c.d_scratch) cudaFree(ctx->c.d_scratch);
   if (ctx->c.h_pinned) cudaFreeHost(ctx->c.h_pinned);
@@ -184,10 +184,11 @@ int nsb_mem_info(nsb_ctx* ctx, int64_t* free_bytes, int64_t* total_bytes, int64_
 // ---- NCCL plumbing -------------------------------------------------------------------------------
 int nsb_comm_unique_id(char id_out[128]) {
   static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  NSB_TRY(nullptr)
   ncclUniqueId id;
-  if (ncclGetUniqueId(&id) != ncclSuccess) return fail(nullptr, NSB_ENCCL, "ncclGetUniqueId failed");
+  if (nccl_api().GetUniqueId(&id) != ncclSuccess) throw Error(NSB_ENCCL, "ncclGetUniqueId failed");
   memcpy(id_out, &id, 128);
-  return NSB_OK;
+  NSB_CATCH(nullptr)
 }
 int nsb_comm_init(nsb_ctx* ctx, const char id[128], int rank, int nranks) {
   if (!ctx) return NSB_EINVAL;
@@ -196,8 +197,8 @@ int nsb_comm_init(nsb_ctx* ctx, const char id[128], int rank, int nranks) {
   ncclUniqueId uid;
   memcpy(&uid, id, 128);
   ncclComm_t comm;
-  ncclResult_t r = ncclCommInitRank(&comm, nranks, uid, rank);
-  if (r != ncclSuccess) throw Error(NSB_ENCCL, std::string("ncclCommInitRank: ") + ncclGetErrorString(r));
+  ncclResult_t r = nccl_api().CommInitRank(&comm, nranks, uid, rank);
+  if (r != ncclSuccess) throw Error(NSB_ENCCL, std::string("ncclCommInitRank: ") + nccl_api().GetErrorString(r));
   ctx->c.nccl_comm = comm;
   ctx->c.rank = rank;
   ctx->c.nranks = nranks;
@@ -205,7 +206,7 @@ int nsb_comm_init(nsb_ctx* ctx, const char id[128], int rank, int nranks) {
 }
 int nsb_comm_destroy(nsb_ctx* ctx) {
   if (!ctx) return NSB_EINVAL;
-  if (ctx->c.nccl_comm) { ncclCommDestroy((ncclComm_t)ctx->c.nccl_comm); ctx->c.nccl_comm = nullptr; }
+  if (ctx->c.nccl_comm) { try { nccl_api().CommDestroy((ncclComm_t)ctx->c.nccl_comm); } catch (...) {} ctx->c.nccl_comm = nullptr; }
   ctx->c.rank = 0; ctx->c.nranks = 1;
   return NSB_OK;
 }

@@ -1,0 +1,46 @@
+// NCCL is bound lazily at the first communicator call: symbols already present in the process (e.g. the NCCL that
+// torch loaded) are preferred, otherwise libnccl.so.2 is dlopen'ed.  This keeps libnsb200.so loadable without NCCL
+// and avoids two NCCL builds with the same SONAME in one process.
+#pragma once
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include "common.h"
+
+namespace nsb {
+
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*ReduceScatter)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+
+inline NcclApi& nccl_api() {
+  static NcclApi api;
+  if (api.ok) return api;
+  void* h = RTLD_DEFAULT;
+  if (!dlsym(RTLD_DEFAULT, "ncclCommInitRank")) {
+    h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) throw Error(NSB_ENCCL, std::string("cannot load NCCL: ") + dlerror());
+  }
+  auto sym = [&](const char* name) {
+    void* p = dlsym(h, name);
+    if (!p) throw Error(NSB_ENCCL, std::string("NCCL symbol missing: ") + name);
+    return p;
+  };
+  api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+  api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+  api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+  api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
+  api.ReduceScatter = reinterpret_cast<decltype(api.ReduceScatter)>(sym("ncclReduceScatter"));
+  api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+  api.ok = true;
+  return api;
+}
+
+}  // namespace nsb

@@ -13,7 +13,7 @@
 //   Net::expand_densitymatrix  src/subspace/densitymatrix.jl:5-74, src/subspace/subspace.jl:28-48
 #include "net.h"
 
-#include <nccl.h>
+#include "nccl_dyn.h"
 
 #include <algorithm>
 #include <cmath>
@@ -505,9 +505,9 @@ DTensor<T> Net<T>::apply_heff(const DTensor<T>& x) {
     } else {
       vec_zero<T>(ctx, out.numel(), out.data());
     }
-    ncclResult_t r = ncclAllReduce(out.data(), out.data(), (size_t)out.numel() * NcclType<T>::mult, ncclDouble, ncclSum,
-                                   (ncclComm_t)ctx->nccl_comm, ctx->stream);
-    if (r != ncclSuccess) throw Error(NSB_ENCCL, std::string("ncclAllReduce: ") + ncclGetErrorString(r));
+    ncclResult_t r = nccl_api().AllReduce(out.data(), out.data(), (size_t)out.numel() * NcclType<T>::mult, ncclDouble, ncclSum,
+                                          (ncclComm_t)ctx->nccl_comm, ctx->stream);
+    if (r != ncclSuccess) throw Error(NSB_ENCCL, std::string("ncclAllReduce: ") + nccl_api().GetErrorString(r));
     ctx->cnt.matvecs++;
     return out;
   }
