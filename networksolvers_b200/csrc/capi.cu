@@ -127,6 +127,8 @@ int nsb_ctx_set_option(nsb_ctx* ctx, const char* key, int64_t value) {
   NSB_TRY(&ctx->c)
   std::string k(key);
   if (k == "gemm_impl") { NSB_REQUIRE(value >= 0 && value <= 3, NSB_EINVAL, "gemm_impl must be 0..3"); ctx->c.gemm_impl = (int)value; }
+  else if (k == "jacobi_block_min_n") { NSB_REQUIRE(value >= 0, NSB_EINVAL, "jacobi_block_min_n must be >= 0"); g_jacobi_block_min_n = (int)value; }
+  else if (k == "jacobi_precondition") { g_jacobi_precondition = value != 0; }
   else throw Error(NSB_EINVAL, "unknown option " + k);
   NSB_CATCH(&ctx->c)
 }

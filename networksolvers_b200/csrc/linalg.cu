@@ -1,6 +1,7 @@
 // Householder QR and one-sided Jacobi SVD on device (see linalg.h).
 #include "linalg.h"
 #include "ops.h"
+#include "gemm.h"
 
 #include <algorithm>
 #include <cmath>
@@ -259,6 +260,246 @@ static int jacobi_onesided(Ctx* ctx, T* G, int64_t ldg, int64_t m, int64_t n, T*
   return sweep;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// blocked one-sided Jacobi: column blocks of width B are paired (round-robin over blocks); for each pair the
+// 2B x 2B Gram matrix is formed by the DMMA GEMM, diagonalised inside one CTA (two-sided cyclic Jacobi on the
+// upper triangle in shared memory, rotations accumulated in R), and the pair is updated with one GEMM
+// [G_I G_J] <- [G_I G_J] R (same for V).  All O(m n^2) work per sweep is GEMM.
+// ------------------------------------------------------------------------------------------------
+template <typename T> struct JacobiBlk;
+template <> struct JacobiBlk<double> { static constexpr int B = 64; };
+template <> struct JacobiBlk<cdouble> { static constexpr int B = 32; };
+
+template <typename T> __device__ __forceinline__ T cmul_conj_a(T a, T b);   // conj(a) * b
+template <> __device__ __forceinline__ double cmul_conj_a<double>(double a, double b) { return a * b; }
+template <> __device__ __forceinline__ cdouble cmul_conj_a<cdouble>(cdouble a, cdouble b) { return mul_(conj_(a), b); }
+
+template <typename T, int N2>
+__global__ void __launch_bounds__(1024) herm_eig_kernel(const T* __restrict__ Sg, T* __restrict__ Rg,
+                                                        unsigned long long* __restrict__ maxoff, double abs_floor,
+                                                        double outer_tol) {
+  // abs_floor = eps * (largest diagonal entry of the global Gram matrix): couplings below it cannot change any
+  // sigma^2 by more than LAPACK-level absolute accuracy and are treated as converged.
+  constexpr int NP = N2 / 2, RING = N2 - 1, TRI = N2 * (N2 + 1) / 2;
+  constexpr int LOG_N2 = (N2 == 128) ? 7 : 6, LOG_NP = LOG_N2 - 1;
+  static_assert(N2 == 128 || N2 == 64, "N2 must be 64 or 128");
+  extern __shared__ __align__(16) char smraw[];
+  T* tri = reinterpret_cast<T*>(smraw);           // upper triangle, idx(i<=j) = i + j(j+1)/2
+  T* R = tri + TRI;                               // N2 x N2 column-major
+  T* J = R + N2 * N2;                             // NP x 4 : j11 j12 j21 j22
+  __shared__ unsigned long long smax;
+  __shared__ double red[40];
+  __shared__ short pq[N2];                        // p[a] = pq[2a], q[a] = pq[2a+1]
+  const int tid = threadIdx.x, nth = blockDim.x;
+  const T* S = Sg + (size_t)blockIdx.x * N2 * N2;
+  auto tix = [](int i, int j) { return i + ((j * (j + 1)) >> 1); };
+  auto get = [&](int i, int j) -> T { return i <= j ? tri[tix(i, j)] : conj_(tri[tix(j, i)]); };
+  auto put = [&](int i, int j, T v) { if (i <= j) tri[tix(i, j)] = v; else tri[tix(j, i)] = conj_(v); };
+  for (int e = tid; e < N2 * N2; e += nth) {
+    int i = e & (N2 - 1), j = e >> LOG_N2;
+    if (i <= j) {
+      T v = S[i + (size_t)j * N2];
+      if (i == j) v = from_complex<T>(re(v), 0.0);
+      tri[tix(i, j)] = v;
+    }
+    R[e] = from_complex<T>(i == j ? 1.0 : 0.0, 0.0);
+  }
+  __syncthreads();
+  {  // off-diagonal measure of the incoming Gram matrix (outer convergence), relative with the absolute floor
+    double v = 0.0;
+    for (int e = tid; e < N2 * N2; e += nth) {
+      int i = e & (N2 - 1), j = e >> LOG_N2;
+      if (i < j) {
+        double a = sqrt(abs2_(tri[tix(i, j)]));
+        double den = fmax(sqrt(fabs(re(tri[tix(i, i)]) * re(tri[tix(j, j)]))), abs_floor / outer_tol);
+        if (a > 0.0 && den > 0.0) v = fmax(v, a / den);
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    if (tid == 0) {
+      double m = 0.0;
+      for (int w = 0; w < (nth + 31) / 32; ++w) m = fmax(m, red[w]);
+      atomicMax(maxoff, (unsigned long long)__double_as_longlong(m));
+      red[32] = m;
+    }
+    __syncthreads();
+    if (red[32] <= outer_tol) {   // this pair is already orthogonal to the outer tolerance: R = I exactly
+      T* Ro = Rg + (size_t)blockIdx.x * N2 * N2;
+      for (int e = tid; e < N2 * N2; e += nth) Ro[e] = R[e];
+      return;
+    }
+  }
+  const double tol = 2.220446049250313e-16 * (N2 / 2);   // rounding noise of the updated couplings is O(eps sqrt(N2))
+  for (int sweep = 0; sweep < 20; ++sweep) {
+    if (tid == 0) smax = 0ull;
+    __syncthreads();
+    for (int r = 0; r < RING; ++r) {
+      // phase A: rotation of every pair from its diagonal 2x2 block
+      int rotated = 0;
+      if (tid < NP) {
+        int a = tid, p, q;
+        if (a == 0) { p = RING; q = r; }
+        else { p = r + a; if (p >= RING) p -= RING; q = r + RING - a; if (q >= RING) q -= RING; }
+        pq[2 * a] = (short)p; pq[2 * a + 1] = (short)q;
+        double alpha = re(tri[tix(p, p)]), beta = re(tri[tix(q, q)]);
+        T g = get(p, q);
+        double gabs = sqrt(abs2_(g)), den = sqrt(fabs(alpha * beta));
+        T j11 = from_complex<T>(1.0, 0.0), j12 = zero_<T>(), j21 = zero_<T>(), j22 = from_complex<T>(1.0, 0.0);
+        if (gabs > abs_floor && gabs > tol * den) {
+          atomicMax(&smax, (unsigned long long)__double_as_longlong(den > 0.0 ? gabs / den : 1.0));
+          double zeta = (beta - alpha) / (2.0 * gabs);
+          double tt = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          double c = 1.0 / sqrt(1.0 + tt * tt), sn = c * tt;
+          double pr = re(g) / gabs, pi = -im(g) / gabs;       // conj(phase)
+          j11 = from_complex<T>(c, 0.0);
+          j12 = from_complex<T>(sn, 0.0);
+          j21 = from_complex<T>(-sn * pr, -sn * pi);
+          j22 = from_complex<T>(c * pr, c * pi);
+          tri[tix(p, p)] = from_complex<T>(alpha - tt * gabs, 0.0);
+          tri[tix(q, q)] = from_complex<T>(beta + tt * gabs, 0.0);
+          put(p, q, zero_<T>());
+        }
+        J[4 * a] = j11; J[4 * a + 1] = j12; J[4 * a + 2] = j21; J[4 * a + 3] = j22;
+        rotated = (re(j12) != 0.0 || im(j12) != 0.0) ? 1 : 0;
+      }
+      if (!__syncthreads_or(rotated)) continue;   // no pair rotated in this step: nothing to update
+      // phase B: off-diagonal pair-pair blocks  B' = Ja^H B Jb, and the columns of R
+      for (int blk = tid; blk < NP * NP; blk += nth) {
+        int a = blk >> LOG_NP, b = blk & (NP - 1);
+        if (a >= b) continue;
+        int pa = pq[2 * a], qa = pq[2 * a + 1], pb = pq[2 * b], qb = pq[2 * b + 1];
+        T b11 = get(pa, pb), b12 = get(pa, qb), b21 = get(qa, pb), b22 = get(qa, qb);
+        T a11 = J[4 * a], a12 = J[4 * a + 1], a21 = J[4 * a + 2], a22 = J[4 * a + 3];
+        T c11 = J[4 * b], c12 = J[4 * b + 1], c21 = J[4 * b + 2], c22 = J[4 * b + 3];
+        T m11 = add_(cmul_conj_a<T>(a11, b11), cmul_conj_a<T>(a21, b21));
+        T m12 = add_(cmul_conj_a<T>(a11, b12), cmul_conj_a<T>(a21, b22));
+        T m21 = add_(cmul_conj_a<T>(a12, b11), cmul_conj_a<T>(a22, b21));
+        T m22 = add_(cmul_conj_a<T>(a12, b12), cmul_conj_a<T>(a22, b22));
+        put(pa, pb, add_(mul_(m11, c11), mul_(m12, c21)));
+        put(pa, qb, add_(mul_(m11, c12), mul_(m12, c22)));
+        put(qa, pb, add_(mul_(m21, c11), mul_(m22, c21)));
+        put(qa, qb, add_(mul_(m21, c12), mul_(m22, c22)));
+      }
+      for (int it = tid; it < N2 * NP; it += nth) {
+        int i = it & (N2 - 1), a = it >> LOG_N2;
+        int p = pq[2 * a], q = pq[2 * a + 1];
+        T x = R[i + p * N2], y = R[i + q * N2];
+        R[i + p * N2] = add_(mul_(x, J[4 * a]), mul_(y, J[4 * a + 2]));
+        R[i + q * N2] = add_(mul_(x, J[4 * a + 1]), mul_(y, J[4 * a + 3]));
+      }
+      __syncthreads();
+    }
+    double off = __longlong_as_double((long long)smax);
+    __syncthreads();
+    if (off <= tol) break;
+  }
+  T* Ro = Rg + (size_t)blockIdx.x * N2 * N2;
+  for (int e = tid; e < N2 * N2; e += nth) Ro[e] = R[e];
+}
+
+template <typename T>
+__global__ void block_gather_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t rows, int64_t bw,
+                                    const int32_t* __restrict__ src_slot_of_dst, int nslots) {
+  int64_t per = rows * bw, total = per * nslots;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t d = i / per, off = i % per;
+    dst[i] = src[(int64_t)src_slot_of_dst[d] * per + off];
+  }
+}
+
+int g_jacobi_block_min_n = 512;
+int g_jacobi_precondition = 1;
+
+template <typename T>
+static int jacobi_blocked(Ctx* ctx, T* G, int64_t m, int64_t n, T* V, int64_t nv) {
+  constexpr int B = JacobiBlk<T>::B, N2 = 2 * B;
+  int64_t nblk = (n + B - 1) / B;
+  if (nblk < 2) nblk = 2;
+  if (nblk % 2) ++nblk;
+  const int64_t npad = nblk * B, npairs = nblk / 2, h = npairs;
+  DevBuf GA(ctx, sizeof(T) * m * npad), GB(ctx, sizeof(T) * m * npad), VA(ctx, sizeof(T) * nv * npad), VB(ctx, sizeof(T) * nv * npad);
+  DevBuf Sb(ctx, sizeof(T) * N2 * N2 * npairs), Rb(ctx, sizeof(T) * N2 * N2 * npairs), mapb(ctx, sizeof(int32_t) * nblk);
+  vec_zero<T>(ctx, m * npad, (T*)GA.ptr);
+  vec_zero<T>(ctx, nv * npad, (T*)VA.ptr);
+  // de Rijk ordering: columns enter sorted by decreasing norm (graded spectra converge in far fewer sweeps)
+  double smax2 = 0.0;
+  {
+    DevBuf nrm(ctx, sizeof(double) * n), sidx(ctx, sizeof(int32_t) * n);
+    col_norms2<T>(ctx, G, m, n, m, (double*)nrm.ptr);
+    std::vector<double> hn(n);
+    NSB_CUDA(cudaMemcpyAsync(hn.data(), nrm.ptr, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->sync();
+    for (double x : hn) smax2 += x;   // ||G||_F^2 >= sigma_max^2, preserved by the rotations
+    std::vector<int32_t> ord(n);
+    std::iota(ord.begin(), ord.end(), 0);
+    std::stable_sort(ord.begin(), ord.end(), [&](int32_t a, int32_t b) { return hn[a] > hn[b]; });
+    NSB_CUDA(cudaMemcpyAsync(sidx.ptr, ord.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+    gather_cols<T>(ctx, G, m, m, (const int32_t*)sidx.ptr, n, nullptr, (T*)GA.ptr, m);
+    gather_cols<T>(ctx, V, nv, nv, (const int32_t*)sidx.ptr, n, nullptr, (T*)VA.ptr, nv);
+    ctx->sync();
+  }
+  // round-robin block permutation (constant over rounds): slot 2i = top[i], slot 2i+1 = bottom[i]
+  std::vector<int32_t> src_of_dst(nblk), blockid(nblk), tmp(nblk);
+  for (int64_t s = 0; s < nblk; ++s) { src_of_dst[s] = (int32_t)s; blockid[s] = (int32_t)s; }
+  if (h > 1) {
+    src_of_dst[0] = 0;
+    src_of_dst[2] = 1;                                              // bottom[0] -> top[1]
+    for (int64_t i = 2; i < h; ++i) src_of_dst[2 * i] = (int32_t)(2 * (i - 1));        // top[i-1] -> top[i]
+    for (int64_t i = 0; i + 1 < h; ++i) src_of_dst[2 * i + 1] = (int32_t)(2 * (i + 1) + 1);  // bottom[i+1] -> bottom[i]
+    src_of_dst[2 * (h - 1) + 1] = (int32_t)(2 * (h - 1));           // top[h-1] -> bottom[h-1]
+  }
+  NSB_CUDA(cudaMemcpyAsync(mapb.ptr, src_of_dst.data(), sizeof(int32_t) * nblk, cudaMemcpyHostToDevice, ctx->stream));
+  auto kern = herm_eig_kernel<T, N2>;
+  size_t smem = sizeof(T) * ((size_t)N2 * (N2 + 1) / 2 + (size_t)N2 * N2 + 4 * (N2 / 2));
+  static bool configured = false;
+  if (!configured) { NSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = true; }
+  const T one = from_complex<T>(1.0, 0.0), zero = zero_<T>();
+  // the Gram entries of orthogonal columns carry rounding noise ~ eps sqrt(m) (max over n^2/2 pairs several times that)
+  const double tol = 10.0 * std::sqrt((double)std::max<int64_t>(m, 1)) * 2.220446049250313e-16;
+  unsigned long long* dmax = reinterpret_cast<unsigned long long*>(ctx->d_scratch);
+  T *ga = (T*)GA.ptr, *gb = (T*)GB.ptr, *va = (T*)VA.ptr, *vb = (T*)VB.ptr;
+  const double abs_floor = 2.220446049250313e-16 * smax2;
+  int sweep = 0;
+  const int64_t rounds = std::max<int64_t>(nblk - 1, 1);
+  for (; sweep < 30; ++sweep) {
+    NSB_CUDA(cudaMemsetAsync(dmax, 0, sizeof(unsigned long long), ctx->stream));
+    for (int64_t r = 0; r < rounds; ++r) {
+      gemm<T>(ctx, OP_C, OP_N, N2, N2, m, one, ga, m, m * N2, ga, m, m * N2, zero, (T*)Sb.ptr, N2, (int64_t)N2 * N2, npairs);
+      kern<<<(unsigned)npairs, 1024, smem, ctx->stream>>>((const T*)Sb.ptr, (T*)Rb.ptr, dmax, abs_floor, tol);
+      LAUNCH_CHECK(ctx);
+      gemm<T>(ctx, OP_N, OP_N, m, N2, N2, one, ga, m, m * N2, (const T*)Rb.ptr, N2, (int64_t)N2 * N2, zero, gb, m, m * N2, npairs);
+      gemm<T>(ctx, OP_N, OP_N, nv, N2, N2, one, va, nv, nv * N2, (const T*)Rb.ptr, N2, (int64_t)N2 * N2, zero, vb, nv, nv * N2, npairs);
+      int grid = ctx->num_sms * 8;
+      block_gather_kernel<T><<<grid, 256, 0, ctx->stream>>>(gb, ga, m, B, (const int32_t*)mapb.ptr, (int)nblk);
+      LAUNCH_CHECK(ctx);
+      block_gather_kernel<T><<<grid, 256, 0, ctx->stream>>>(vb, va, nv, B, (const int32_t*)mapb.ptr, (int)nblk);
+      LAUNCH_CHECK(ctx);
+      for (int64_t s = 0; s < nblk; ++s) tmp[s] = blockid[src_of_dst[s]];
+      blockid.swap(tmp);
+    }
+    NSB_CUDA(cudaMemcpyAsync(ctx->h_pinned, dmax, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    NSB_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->cnt.jacobi_sweeps++;
+    if (getenv("NSB_DEBUG_JACOBI")) fprintf(stderr, "[jacobi_blocked] n=%ld m=%ld sweep %d offmax %.3e tol %.3e floor %.3e\n", (long)n, (long)m, sweep, ctx->h_pinned[0], tol, abs_floor);
+    if (ctx->h_pinned[0] <= tol) { ++sweep; break; }
+  }
+  // collect the n real columns (padding columns never mix: their Gram rows are exactly zero)
+  std::vector<int32_t> cols;
+  cols.reserve(n);
+  for (int64_t s = 0; s < nblk; ++s)
+    for (int j = 0; j < B; ++j)
+      if ((int64_t)blockid[s] * B + j < n) cols.push_back((int32_t)(s * B + j));
+  DevBuf idx(ctx, sizeof(int32_t) * n);
+  NSB_CUDA(cudaMemcpyAsync(idx.ptr, cols.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+  gather_cols<T>(ctx, ga, m, m, (const int32_t*)idx.ptr, n, nullptr, G, m);
+  gather_cols<T>(ctx, va, nv, nv, (const int32_t*)idx.ptr, n, nullptr, V, nv);
+  ctx->sync();
+  return sweep;
+}
+
 template <typename T>
 FactorInfo factorize_left(Ctx* ctx, const T* M, int64_t rows, int64_t cols, int64_t ld, bool trans_in, double cutoff,
                           int64_t mindim, int64_t maxdim, bool sqrt_spectrum, DevBuf& U, DevBuf& C,
@@ -269,18 +510,57 @@ FactorInfo factorize_left(Ctx* ctx, const T* M, int64_t rows, int64_t cols, int6
   NSB_REQUIRE(k > 0, NSB_EINVAL, "factorize: empty matrix");
   info.decomp = (cutoff <= 1e-12) ? 1 : 2;
   maxdim = std::min<int64_t>(maxdim, k);
-  const bool left = rows <= cols;   // rotate the smaller side
-  const int64_t n = left ? rows : cols, m = left ? cols : rows;
-  DevBuf G(ctx, sizeof(T) * m * n), V(ctx, sizeof(T) * n * n);
-  if (left) {   // G = M^H (cols x rows)
+  if (rows > cols) {
+    // tall matrix: thin QR first, then factorise the square R from the left so that U = Q U_r is orthonormal
+    // by construction (product of orthogonal transformations)
+    DevBuf Mc(ctx, sizeof(T) * rows * cols), Q(ctx, sizeof(T) * rows * cols), R(ctx, sizeof(T) * cols * cols);
+    if (!trans_in) copy_block<T>(ctx, M, ld, (T*)Mc.ptr, rows, rows, cols);
+    else transpose_conj<T>(ctx, M, cols, rows, ld, (T*)Mc.ptr, rows, false);
+    qr_thin<T>(ctx, (T*)Mc.ptr, rows, cols, rows, (T*)Q.ptr, rows, (T*)R.ptr, cols);
+    DevBuf Ur;
+    ctx->cnt.svd_calls--;
+    FactorInfo fi = factorize_left<T>(ctx, (const T*)R.ptr, cols, cols, cols, false, cutoff, mindim, maxdim, sqrt_spectrum, Ur, C, spectrum);
+    U = DevBuf(ctx, sizeof(T) * rows * fi.newdim);
+    gemm<T>(ctx, OP_N, OP_N, rows, fi.newdim, cols, from_complex<T>(1.0, 0.0), (const T*)Q.ptr, rows, 0, (const T*)Ur.ptr, cols, 0,
+            zero_<T>(), (T*)U.ptr, rows, 0, 1);
+    ctx->sync();
+    return fi;
+  }
+  const bool left = true;           // rows <= cols: rotate the row side, U = accumulated rotations
+  const int64_t n = rows, m = cols;
+  DevBuf G(ctx, sizeof(T) * m * n), V(ctx, sizeof(T) * n * n), Qm;
+  std::vector<int32_t> pcol;        // column permutation of the preconditioned path
+  const bool precond = (n >= g_jacobi_block_min_n) && g_jacobi_precondition;
+  if (!precond) {   // G = M^H (cols x rows)
     if (!trans_in) transpose_conj<T>(ctx, M, rows, cols, ld, (T*)G.ptr, m, true);
     else conj_copy_block<T>(ctx, M, ld, (T*)G.ptr, m, cols, rows);            // stored (cols x rows): conj only
-  } else {      // G = M (rows x cols)
-    if (!trans_in) copy_block<T>(ctx, M, ld, (T*)G.ptr, m, rows, cols);
-    else transpose_conj<T>(ctx, M, cols, rows, ld, (T*)G.ptr, m, false);      // stored (cols x rows): transpose
+  } else {
+    // Drmac-Veselic preconditioning: M P = Qm Rm (Householder QR, columns pre-sorted by decreasing norm), then
+    // one-sided Jacobi on X = Rm^H (lower trapezoidal), whose columns are already nearly orthogonal:
+    //   X J = W Sigma  =>  M P = (Qm J) Sigma W^H,  U = Qm J is a product of orthogonal transformations.
+    DevBuf Mw(ctx, sizeof(T) * rows * cols), Ms(ctx, sizeof(T) * rows * cols);
+    if (!trans_in) copy_block<T>(ctx, M, ld, (T*)Mw.ptr, rows, rows, cols);
+    else transpose_conj<T>(ctx, M, cols, rows, ld, (T*)Mw.ptr, rows, false);
+    DevBuf nrm(ctx, sizeof(double) * cols), pidx(ctx, sizeof(int32_t) * cols);
+    col_norms2<T>(ctx, (T*)Mw.ptr, rows, cols, rows, (double*)nrm.ptr);
+    std::vector<double> hn(cols);
+    NSB_CUDA(cudaMemcpyAsync(hn.data(), nrm.ptr, sizeof(double) * cols, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->sync();
+    pcol.resize(cols);
+    std::iota(pcol.begin(), pcol.end(), 0);
+    std::stable_sort(pcol.begin(), pcol.end(), [&](int32_t a, int32_t b) { return hn[a] > hn[b]; });
+    NSB_CUDA(cudaMemcpyAsync(pidx.ptr, pcol.data(), sizeof(int32_t) * cols, cudaMemcpyHostToDevice, ctx->stream));
+    gather_cols<T>(ctx, (T*)Mw.ptr, rows, rows, (const int32_t*)pidx.ptr, cols, nullptr, (T*)Ms.ptr, rows);
+    ctx->sync();
+    Qm = DevBuf(ctx, sizeof(T) * rows * rows);
+    DevBuf Rm(ctx, sizeof(T) * rows * cols);
+    qr_thin<T>(ctx, (T*)Ms.ptr, rows, cols, rows, (T*)Qm.ptr, rows, (T*)Rm.ptr, rows);
+    transpose_conj<T>(ctx, (T*)Rm.ptr, rows, cols, rows, (T*)G.ptr, m, true);   // G = Rm^H (cols x rows)
+    ctx->sync();
   }
   set_identity<T>(ctx, (T*)V.ptr, n, n, n);
-  info.sweeps = jacobi_onesided<T>(ctx, (T*)G.ptr, m, m, n, (T*)V.ptr, n, n);
+  if (n >= g_jacobi_block_min_n) info.sweeps = jacobi_blocked<T>(ctx, (T*)G.ptr, m, n, (T*)V.ptr, n);
+  else info.sweeps = jacobi_onesided<T>(ctx, (T*)G.ptr, m, m, n, (T*)V.ptr, n, n);
 
   DevBuf norms(ctx, sizeof(double) * n);
   col_norms2<T>(ctx, (T*)G.ptr, m, n, m, (double*)norms.ptr);
@@ -301,24 +581,25 @@ FactorInfo factorize_left(Ctx* ctx, const T* M, int64_t rows, int64_t cols, int6
   NSB_CUDA(cudaMemcpyAsync(idx.ptr, order.data(), sizeof(int32_t) * nkeep, cudaMemcpyHostToDevice, ctx->stream));
   U = DevBuf(ctx, sizeof(T) * rows * nkeep);
   C = DevBuf(ctx, sizeof(T) * nkeep * cols);
-  if (left) {
-    // U = V[:, order] (rows x nkeep);  C = (G[:, order])^H
-    gather_cols<T>(ctx, (T*)V.ptr, n, rows, (int32_t*)idx.ptr, nkeep, nullptr, (T*)U.ptr, rows);
+  (void)left;
+  {
+    // U = V[:, order] (rows x nkeep)  [times Qm when preconditioned];  C = (G[:, order])^H  [columns un-permuted]
     DevBuf tmp(ctx, sizeof(T) * cols * nkeep);
     gather_cols<T>(ctx, (T*)G.ptr, m, cols, (int32_t*)idx.ptr, nkeep, nullptr, (T*)tmp.ptr, cols);
-    transpose_conj<T>(ctx, (T*)tmp.ptr, cols, nkeep, cols, (T*)C.ptr, nkeep, true);
-    ctx->sync();
-  } else {
-    // M V = W Sigma:  U = G[:, order] / sigma;  C = (V[:, order] * sigma)^H
-    std::vector<double> inv(nkeep), sig(nkeep);
-    for (int64_t i = 0; i < nkeep; ++i) { sig[i] = std::sqrt(std::max(P[order[i]], 0.0)); inv[i] = sig[i] > 0 ? 1.0 / sig[i] : 0.0; }
-    NSB_CUDA(cudaMemcpyAsync(scl.ptr, inv.data(), sizeof(double) * nkeep, cudaMemcpyHostToDevice, ctx->stream));
-    gather_cols<T>(ctx, (T*)G.ptr, m, rows, (int32_t*)idx.ptr, nkeep, (double*)scl.ptr, (T*)U.ptr, rows);
-    ctx->sync();
-    NSB_CUDA(cudaMemcpyAsync(scl.ptr, sig.data(), sizeof(double) * nkeep, cudaMemcpyHostToDevice, ctx->stream));
-    DevBuf tmp(ctx, sizeof(T) * cols * nkeep);
-    gather_cols<T>(ctx, (T*)V.ptr, n, cols, (int32_t*)idx.ptr, nkeep, (double*)scl.ptr, (T*)tmp.ptr, cols);
-    transpose_conj<T>(ctx, (T*)tmp.ptr, cols, nkeep, cols, (T*)C.ptr, nkeep, true);
+    if (!precond) {
+      gather_cols<T>(ctx, (T*)V.ptr, n, rows, (int32_t*)idx.ptr, nkeep, nullptr, (T*)U.ptr, rows);
+      transpose_conj<T>(ctx, (T*)tmp.ptr, cols, nkeep, cols, (T*)C.ptr, nkeep, true);
+    } else {
+      DevBuf Vk(ctx, sizeof(T) * rows * nkeep), tmp2(ctx, sizeof(T) * cols * nkeep), inv(ctx, sizeof(int32_t) * cols);
+      gather_cols<T>(ctx, (T*)V.ptr, n, rows, (int32_t*)idx.ptr, nkeep, nullptr, (T*)Vk.ptr, rows);
+      gemm<T>(ctx, OP_N, OP_N, rows, nkeep, rows, from_complex<T>(1.0, 0.0), (const T*)Qm.ptr, rows, 0, (const T*)Vk.ptr, rows, 0,
+              zero_<T>(), (T*)U.ptr, rows, 0, 1);
+      std::vector<int32_t> ip(cols);
+      for (int64_t j = 0; j < cols; ++j) ip[pcol[j]] = (int32_t)j;       // original column c sits at permuted position ip[c]
+      NSB_CUDA(cudaMemcpyAsync(inv.ptr, ip.data(), sizeof(int32_t) * cols, cudaMemcpyHostToDevice, ctx->stream));
+      gather_rows<T>(ctx, (T*)tmp.ptr, cols, (const int32_t*)inv.ptr, cols, nkeep, (T*)tmp2.ptr, cols);
+      transpose_conj<T>(ctx, (T*)tmp2.ptr, cols, nkeep, cols, (T*)C.ptr, nkeep, true);
+    }
     ctx->sync();
   }
   return info;

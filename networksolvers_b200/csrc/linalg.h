@@ -13,6 +13,9 @@ int64_t truncate_spectrum(const std::vector<double>& P, double cutoff, int64_t m
 template <typename T>
 void qr_thin(Ctx* ctx, T* A, int64_t rows, int64_t cols, int64_t lda, T* Q, int64_t ldq, T* R, int64_t ldr);
 
+extern int g_jacobi_precondition;  // 1: QR-precondition the blocked Jacobi (Drmac-Veselic)
+extern int g_jacobi_block_min_n;   // column count from which the blocked (GEMM-rich) Jacobi is used
+
 struct FactorInfo { int64_t newdim = 0; double truncerr = 0; int decomp = 0; int sweeps = 0; };
 
 // Truncated left-orthogonal factorization M = U C (src/inserter.jl:23 / ITensors.factorize with ortho="left"):

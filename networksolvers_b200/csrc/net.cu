@@ -780,168 +780,234 @@ template <> struct CplxScalar<cdouble> {
   static cdouble make(double re, double im) { return make_cuDoubleComplex(re, im); }
 };
 
+// Local exponential solvers on an arbitrary device operator H: x -> H x (same vector shape).
+//   solver RK: src/local_solvers/runge_kutta.jl:2-25;  solver KRYLOV: KrylovKit.exponentiate (expintegrator, p = 1).
 template <typename T>
-void Net<T>::update_exp(double tre, double tim, int solver, const nsb_krylov* kp, int nsites, int next_vertex, nsb_solve_info* info) {
-  NSB_REQUIRE(theta.valid() && !plan.empty(), NSB_EINVAL, "update_exp: call nsb_extract first");
-  NSB_REQUIRE(CplxScalar<T>::ok(tre, tim), NSB_EINVAL, "update_exp: complex exponent needs a complex128 network");
-  NSB_REQUIRE(!(nsites == 1 && next_vertex >= 0), NSB_EUNSUPPORTED,
-              "1-site applyexp backward (on-edge) step is not implemented yet (SURVEY 8f row 1)");
-  const int64_t n = theta.numel();
+DTensor<T> Net<T>::exp_solve(const std::function<DTensor<T>(const DTensor<T>&)>& Hraw, std::complex<double> t, const DTensor<T>& x0,
+                             int solver, const nsb_krylov* kp, int* nmv_out, int* lastK_out, int* conv_out, double* err_out) {
+  const int64_t n = x0.numel();
   typedef std::complex<double> C;
-  const C t(tre, tim);
   auto S = [&](C z) { return CplxScalar<T>::make(z.real(), z.imag()); };
+  int nmv = 0;
   auto H = [&](const DTensor<T>& x) {
     PhaseTimer pt(ctx, NSB_T_MATVEC);
-    DTensor<T> y = apply_heff(x);
+    DTensor<T> y = Hraw(x);
     if (y.data() == x.data()) y = clone(ctx, y);
+    ++nmv;
     return y;
   };
-  int nmv = 0;
+  DTensor<T> result;
+  int lastK = 0, converged = 1;
+  double totalerr = 0.0;
   if (solver == NSB_SOLVER_RK) {
     int order = kp ? kp->rk_order : 4;
     if (order == 0) order = 4;
     if (order == 4) {
-      // src/local_solvers/runge_kutta.jl:8-14
-      DTensor<T> k1 = H(theta);
+      DTensor<T> k1 = H(x0);
       DTensor<T> k2 = H(k1);  { PhaseTimer pt(ctx, NSB_T_KRYLOV); vec_scale<T>(ctx, n, S(t / 2.0), k2.data()); vec_axpy<T>(ctx, n, S(1.0), k1.data(), k2.data()); }
       DTensor<T> k3 = H(k2);  { PhaseTimer pt(ctx, NSB_T_KRYLOV); vec_scale<T>(ctx, n, S(t / 2.0), k3.data()); vec_axpy<T>(ctx, n, S(1.0), k1.data(), k3.data()); }
       DTensor<T> k4 = H(k3);  { PhaseTimer pt(ctx, NSB_T_KRYLOV); vec_scale<T>(ctx, n, S(t), k4.data()); vec_axpy<T>(ctx, n, S(1.0), k1.data(), k4.data()); }
-      nmv = 4;
       PhaseTimer pt(ctx, NSB_T_KRYLOV);
-      const T* ptrs[5] = {theta.data(), k1.data(), k2.data(), k3.data(), k4.data()};
+      const T* ptrs[5] = {x0.data(), k1.data(), k2.data(), k3.data(), k4.data()};
       T coef[5] = {S(1.0), S(t / 6.0), S(t / 3.0), S(t / 3.0), S(t / 6.0)};
-      DTensor<T> out(ctx, theta.dims, theta.labels);
-      vec_lincomb<T>(ctx, n, 5, ptrs, coef, out.data());
-      theta = out;
+      result = DTensor<T>(ctx, x0.dims, x0.labels);
+      vec_lincomb<T>(ctx, n, 5, ptrs, coef, result.data());
     } else if (order == 2) {
-      // src/local_solvers/runge_kutta.jl:2-6
-      DTensor<T> h1 = H(theta);
+      DTensor<T> h1 = H(x0);
       DTensor<T> h2 = H(h1);
-      nmv = 2;
       PhaseTimer pt(ctx, NSB_T_KRYLOV);
-      const T* ptrs[3] = {theta.data(), h1.data(), h2.data()};
+      const T* ptrs[3] = {x0.data(), h1.data(), h2.data()};
       T coef[3] = {S(1.0), S(t), S(t * t / 2.0)};
-      DTensor<T> out(ctx, theta.dims, theta.labels);
-      vec_lincomb<T>(ctx, n, 3, ptrs, coef, out.data());
-      theta = out;
+      result = DTensor<T>(ctx, x0.dims, x0.labels);
+      vec_lincomb<T>(ctx, n, 3, ptrs, coef, result.data());
     } else {
       throw Error(NSB_EINVAL, "For runge_kutta_solver, must specify `order` keyword (2 or 4)");
     }
-    if (info) { info->nmatvec = nmv; info->krylovdim = 0; info->converged = 1; info->residual = 0.0; info->reserved = 0; }
-    return;
-  }
-  NSB_REQUIRE(solver == NSB_SOLVER_KRYLOV, NSB_EINVAL, "update_exp: unknown solver");
-  // KrylovKit.exponentiate = expintegrator with p = 1 (Lanczos): exp(tA) u0 = u0 + t phi_1(tA) A u0
-  nsb_krylov p = kp ? *kp : nsb_krylov{30, 100, 1e-12, 0, 1, 4, 0};
-  const double tau = std::abs(t);
-  if (tau == 0.0) { if (info) { info->nmatvec = 0; info->krylovdim = 0; info->converged = 1; info->residual = 0; info->reserved = 0; } return; }
-  const C sgn = t / tau;
-  const double eta = p.tol / tau, gamma = 0.8;
-  double totalerr = 0.0, tau0 = 0.0, dtau = tau;
-  int numiter = 1, converged = 0, lastK = 0;
-  DTensor<T> w0 = clone(ctx, theta);
-  DTensor<T> w1 = H(w0); ++nmv;
-  const int kmax = (int)std::min<int64_t>(p.krylovdim, n);
-  bool done = false;
-  while (!done) {
-    double beta = vec_nrm2<T>(ctx, n, w1.data());
-    if (beta < p.tol) { converged = 1; break; }
-    std::vector<DTensor<T>> V;
-    std::vector<double> alphas, betas;
-    DTensor<T> r;
-    double resnorm = 0.0;
-    { DTensor<T> v0 = clone(ctx, w1); vec_scale<T>(ctx, n, from_complex<T>(1.0 / beta, 0.0), v0.data()); V.push_back(v0); }
-    auto expand = [&]() {
-      DTensor<T>& v = V.back();
-      DTensor<T> w = H(v); ++nmv;
-      PhaseTimer pt(ctx, NSB_T_KRYLOV);
-      double ar, ai;
-      vec_dot<T>(ctx, n, v.data(), w.data(), &ar, &ai);
-      double a = ar;
-      vec_axpy<T>(ctx, n, from_complex<T>(-a, 0.0), v.data(), w.data());
-      if (V.size() > 1) vec_axpy<T>(ctx, n, from_complex<T>(-betas.back(), 0.0), V[V.size() - 2].data(), w.data());
-      for (size_t i = 0; i < V.size(); ++i) {
-        double cr, ci;
-        vec_dot<T>(ctx, n, V[i].data(), w.data(), &cr, &ci);
-        vec_axpy<T>(ctx, n, from_complex<T>(-cr, -ci), V[i].data(), w.data());
-        if (i + 1 == V.size()) a += cr;
-      }
-      alphas.push_back(a);
-      r = w;
-      resnorm = vec_nrm2<T>(ctx, n, w.data());
-    };
-    expand();
-    while (true) {
-      int K = (int)V.size();
-      lastK = K;
-      bool stepped = false;
-      double step = 0.0, eps = 0.0, omega = 0.0, q = K / 2.0;
-      std::vector<C> E;
-      auto small_exp = [&](double dt) {
-        int m = K + 2;
-        E.assign((size_t)m * m, C(0));
-        for (int i = 0; i < K; ++i) E[i + (size_t)i * m] = sgn * dt * alphas[i];
-        for (int i = 0; i + 1 < K; ++i) { E[i + (size_t)(i + 1) * m] = sgn * dt * betas[i]; E[(i + 1) + (size_t)i * m] = sgn * dt * betas[i]; }
-        E[0 + (size_t)K * m] = 1.0;
-        E[K + (size_t)(K + 1) * m] = 1.0;
-        host_expm_complex(m, E);
-        return std::abs(dt * beta * resnorm * E[(K - 1) + (size_t)(K + 1) * m]);
-      };
-      if (K == kmax) {
-        dtau = std::min(dtau, tau - tau0);
-        eps = small_exp(dtau);
-        omega = eps / (dtau * eta);
-        while (omega > 1.0) {
-          double eps_prev = eps, dtau_prev = dtau;
-          dtau *= std::pow(gamma / omega, 1.0 / (q + 1.0));
-          eps = small_exp(dtau);
-          omega = eps / (dtau * eta);
-          if (eps <= 0.0) break;
-          q = std::max(0.0, std::log(eps / eps_prev) / std::log(dtau / dtau_prev) - 1.0);
+  } else {
+    NSB_REQUIRE(solver == NSB_SOLVER_KRYLOV, NSB_EINVAL, "update_exp: unknown solver");
+    nsb_krylov p = kp ? *kp : nsb_krylov{30, 100, 1e-12, 0, 1, 4, 0};
+    const double tau = std::abs(t);
+    if (tau == 0.0) {
+      result = clone(ctx, x0);
+    } else {
+      const C sgn = t / tau;
+      const double eta = p.tol / tau, gamma = 0.8;
+      double tau0 = 0.0, dtau = tau;
+      int numiter = 1;
+      converged = 0;
+      DTensor<T> w0 = clone(ctx, x0);
+      DTensor<T> w1 = H(w0);
+      const int kmax = (int)std::min<int64_t>(p.krylovdim, n);
+      bool done = false;
+      while (!done) {
+        double beta = vec_nrm2<T>(ctx, n, w1.data());
+        if (beta < p.tol) { converged = 1; break; }
+        std::vector<DTensor<T>> V;
+        std::vector<double> alphas, betas;
+        DTensor<T> r;
+        double resnorm = 0.0;
+        { DTensor<T> v0 = clone(ctx, w1); vec_scale<T>(ctx, n, from_complex<T>(1.0 / beta, 0.0), v0.data()); V.push_back(v0); }
+        auto expand = [&]() {
+          DTensor<T>& v = V.back();
+          DTensor<T> w = H(v);
+          PhaseTimer pt(ctx, NSB_T_KRYLOV);
+          double ar, ai;
+          vec_dot<T>(ctx, n, v.data(), w.data(), &ar, &ai);
+          double a = ar;
+          vec_axpy<T>(ctx, n, from_complex<T>(-a, 0.0), v.data(), w.data());
+          if (V.size() > 1) vec_axpy<T>(ctx, n, from_complex<T>(-betas.back(), 0.0), V[V.size() - 2].data(), w.data());
+          for (size_t i = 0; i < V.size(); ++i) {
+            double cr, ci;
+            vec_dot<T>(ctx, n, V[i].data(), w.data(), &cr, &ci);
+            vec_axpy<T>(ctx, n, from_complex<T>(-cr, -ci), V[i].data(), w.data());
+            if (i + 1 == V.size()) a += cr;
+          }
+          alphas.push_back(a);
+          r = w;
+          resnorm = vec_nrm2<T>(ctx, n, w.data());
+        };
+        expand();
+        while (true) {
+          int K = (int)V.size();
+          lastK = K;
+          bool stepped = false;
+          double step = 0.0, eps = 0.0, omega = 0.0, q = K / 2.0;
+          std::vector<C> E;
+          auto small_exp = [&](double dt) {
+            int m = K + 2;
+            E.assign((size_t)m * m, C(0));
+            for (int i = 0; i < K; ++i) E[i + (size_t)i * m] = sgn * dt * alphas[i];
+            for (int i = 0; i + 1 < K; ++i) { E[i + (size_t)(i + 1) * m] = sgn * dt * betas[i]; E[(i + 1) + (size_t)i * m] = sgn * dt * betas[i]; }
+            E[0 + (size_t)K * m] = 1.0;
+            E[K + (size_t)(K + 1) * m] = 1.0;
+            host_expm_complex(m, E);
+            return std::abs(dt * beta * resnorm * E[(K - 1) + (size_t)(K + 1) * m]);
+          };
+          if (K == kmax) {
+            dtau = std::min(dtau, tau - tau0);
+            eps = small_exp(dtau);
+            omega = eps / (dtau * eta);
+            while (omega > 1.0) {
+              double eps_prev = eps, dtau_prev = dtau;
+              dtau *= std::pow(gamma / omega, 1.0 / (q + 1.0));
+              eps = small_exp(dtau);
+              omega = eps / (dtau * eta);
+              if (eps <= 0.0) break;
+              q = std::max(0.0, std::log(eps / eps_prev) / std::log(dtau / dtau_prev) - 1.0);
+            }
+            step = dtau;
+            stepped = true;
+          } else if (resnorm <= (tau - tau0) * eta || p.eager) {
+            step = tau - tau0;
+            eps = small_exp(step);
+            omega = eps / (step * eta);
+            if (omega < 1.0) stepped = true;
+          }
+          if (stepped) {
+            PhaseTimer pt(ctx, NSB_T_KRYLOV);
+            totalerr += eps;
+            int m = K + 2;
+            const C f = beta * sgn * step;
+            std::vector<const T*> ptrs;
+            std::vector<T> coef;
+            for (int i = 0; i < K; ++i) { ptrs.push_back(V[i].data()); coef.push_back(S(f * E[i + (size_t)K * m])); }
+            ptrs.push_back(r.data()); coef.push_back(S(f * E[(K - 1) + (size_t)(K + 1) * m]));
+            ptrs.push_back(w0.data()); coef.push_back(S(1.0));
+            DTensor<T> nw(ctx, x0.dims, x0.labels);
+            vec_lincomb<T>(ctx, n, (int)ptrs.size(), ptrs.data(), coef.data(), nw.data());
+            w0 = nw;
+            tau0 += step;
+            if (K == kmax && omega < gamma) dtau *= std::pow(gamma / std::max(omega, 1e-300), 1.0 / (q + 1.0));
+          }
+          if (tau0 >= tau * (1.0 - 1e-15)) { converged = 1; done = true; break; }
+          if (stepped) break;
+          if (K < kmax && resnorm > 0.0) {
+            PhaseTimer pt(ctx, NSB_T_KRYLOV);
+            betas.push_back(resnorm);
+            DTensor<T> nv = r;
+            vec_scale<T>(ctx, n, from_complex<T>(1.0 / resnorm, 0.0), nv.data());
+            V.push_back(nv);
+          } else break;
+          expand();
         }
-        step = dtau;
-        stepped = true;
-      } else if (resnorm <= (tau - tau0) * eta || p.eager) {
-        step = tau - tau0;
-        eps = small_exp(step);
-        omega = eps / (step * eta);
-        if (omega < 1.0) stepped = true;
+        if (done) break;
+        if (numiter == p.maxiter) { converged = 0; break; }
+        ++numiter;
+        w1 = H(w0);
       }
-      if (stepped) {
-        PhaseTimer pt(ctx, NSB_T_KRYLOV);
-        totalerr += eps;
-        int m = K + 2;
-        // w0 += beta * sgn * step * ( V * E[0:K, K] + r * E[K-1, K+1] )
-        const C f = beta * sgn * step;
-        std::vector<const T*> ptrs;
-        std::vector<T> coef;
-        for (int i = 0; i < K; ++i) { ptrs.push_back(V[i].data()); coef.push_back(S(f * E[i + (size_t)K * m])); }
-        ptrs.push_back(r.data()); coef.push_back(S(f * E[(K - 1) + (size_t)(K + 1) * m]));
-        ptrs.push_back(w0.data()); coef.push_back(S(1.0));
-        DTensor<T> nw(ctx, theta.dims, theta.labels);
-        vec_lincomb<T>(ctx, n, (int)ptrs.size(), ptrs.data(), coef.data(), nw.data());
-        w0 = nw;
-        tau0 += step;
-        if (K == kmax && omega < gamma) dtau *= std::pow(gamma / std::max(omega, 1e-300), 1.0 / (q + 1.0));
-      }
-      if (tau0 >= tau * (1.0 - 1e-15)) { converged = 1; done = true; break; }
-      if (stepped) break;
-      if (K < kmax && resnorm > 0.0) {
-        PhaseTimer pt(ctx, NSB_T_KRYLOV);
-        betas.push_back(resnorm);
-        DTensor<T> nv = r;
-        vec_scale<T>(ctx, n, from_complex<T>(1.0 / resnorm, 0.0), nv.data());
-        V.push_back(nv);
-      } else break;
-      expand();
+      result = w0;
     }
-    if (done) break;
-    if (numiter == p.maxiter) { converged = 0; break; }
-    ++numiter;
-    w1 = H(w0); ++nmv;
   }
-  theta = w0;
-  if (info) { info->nmatvec = nmv; info->krylovdim = lastK; info->converged = converged; info->residual = totalerr; info->reserved = 0; }
+  if (nmv_out) *nmv_out += nmv;
+  if (lastK_out) *lastK_out = lastK;
+  if (conv_out) *conv_out = converged;
+  if (err_out) *err_out += totalerr;
+  return result;
+}
+
+template <typename T>
+void Net<T>::update_exp(double tre, double tim, int solver, const nsb_krylov* kp, int nsites, int next_vertex, nsb_solve_info* info) {
+  NSB_REQUIRE(theta.valid() && !plan.empty(), NSB_EINVAL, "update_exp: call nsb_extract first");
+  NSB_REQUIRE(CplxScalar<T>::ok(tre, tim), NSB_EINVAL, "update_exp: complex exponent needs a complex128 network");
+  typedef std::complex<double> C;
+  const C t(tre, tim);
+  int nmv = 0, lastK = 0, conv = 1;
+  double err = 0.0;
+  // forward step (src/applyexp.jl:28)
+  theta = exp_solve([&](const DTensor<T>& x) { return apply_heff(x); }, t, theta, solver, kp, &nmv, &lastK, &conv, &err);
+  if (nsites == 1 && next_vertex >= 0) {
+    // src/applyexp.jl:30-42: QR-split the evolved site tensor toward the next region, move the projected
+    // operator onto the edge (0-site H_eff = the two environments), evolve R backward by -t, recombine.
+    NSB_REQUIRE(region.size() == 1, NSB_EINVAL, "update_exp: nsites == 1 needs a one-site region");
+    const int v1 = region[0], v2 = next_vertex;
+    NSB_REQUIRE(eid.count({v1, v2}), NSB_EINVAL, "update_exp: next_vertex is not a neighbour of the region");
+    const Label l = llink(v1, v2);
+    std::vector<Label> order;
+    for (Label x : theta.labels) if (x != l) order.push_back(x);
+    order.push_back(l);
+    DTensor<T> Ap = permuted(ctx, theta, order);
+    if (Ap.data() == theta.data()) Ap = clone(ctx, theta);
+    const int64_t cols = Ap.dims.back(), rows = Ap.numel() / cols, k = std::min(rows, cols);
+    std::vector<int64_t> qd(Ap.dims.begin(), Ap.dims.end() - 1);
+    qd.push_back(k);
+    DTensor<T> Q(ctx, qd, order);                                  // [others..., l] with dim(l) = k
+    const Label ax = make_label(LK_AUX, 3, 0);
+    DTensor<T> R(ctx, {k, cols}, {ax, l});
+    {
+      PhaseTimer pt(ctx, NSB_T_GAUGE);
+      qr_thin<T>(ctx, Ap.data(), rows, cols, rows, Q.data(), rows, R.data(), k);
+    }
+    DTensor<T> E1, E2;
+    {
+      PhaseTimer pt(ctx, NSB_T_ENV);
+      psi[v1] = Q;                   // the inserter overwrites psi[v1] with the recombined tensor afterwards
+      canonicalize(v1);
+      ver[v1]++;
+      envs.erase({v1, v2});
+      make_env(v2, v1);              // present already (incident to the current region)
+      make_env(v1, v2);
+      E1 = envs.at({v1, v2}).t;      // [l(k), op, l'(k)]  ->  relabel its link to the auxiliary QR index
+      std::vector<Label> nl = E1.labels;
+      for (auto& x : nl) if (label_kind(x) == LK_LINK) x = make_label(LK_AUX, 3, label_plev(x));
+      E1 = E1.relabeled(nl);
+      E2 = envs.at({v2, v1}).t;      // [l, op, l']
+    }
+    auto Hedge = [&](const DTensor<T>& x) {      // src/operator_map.jl:17-20 (on-edge branch)
+      DTensor<T> y = contract(ctx, x, E2, false, false, 1);        // [ax, op, l']
+      y = contract(ctx, y, E1, false, false, 1).noprime();         // [ax', l'] -> [ax, l]
+      if (y.labels != x.labels) y = permuted(ctx, y, x.labels);
+      ctx->cnt.matvecs++;
+      return y;
+    };
+    DTensor<T> Rt = exp_solve(Hedge, -t, R, solver, kp, &nmv, &lastK, &conv, &err);
+    // local_state = psi[v1] * R_t
+    std::vector<Label> ql = order;
+    ql.back() = ax;
+    DTensor<T> th = contract(ctx, Q.relabeled(ql), Rt, false, false, 1);
+    if (th.labels != theta.labels) th = permuted(ctx, th, theta.labels);
+    theta = th;
+  }
+  if (info) { info->nmatvec = nmv; info->krylovdim = lastK; info->converged = conv; info->residual = err; info->reserved = 0; }
 }
 
 template <typename T>

@@ -1,6 +1,8 @@
 // Device-resident tree tensor network state + operator + projected-operator environments, and the three
 // region hooks (extract / update / insert) that the NetworkSolvers.jl sweep driver calls.
 #pragma once
+#include <complex>
+#include <functional>
 #include <map>
 #include <set>
 
@@ -91,6 +93,8 @@ struct Net : public NetBase {
   void build_plan();
   DTensor<T> apply_heff(const DTensor<T>& x);
   bool expand_densitymatrix(const nsb_trunc& trunc, const nsb_expand& ex);
+  DTensor<T> exp_solve(const std::function<DTensor<T>(const DTensor<T>&)>& H, std::complex<double> t, const DTensor<T>& x0,
+                       int solver, const nsb_krylov* kp, int* nmv, int* lastK, int* conv, double* err);
 
   // NetBase
   void site_upload(int v, int rank, const int32_t* legs, const int64_t* dims, const void* host) override;

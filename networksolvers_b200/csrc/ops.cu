@@ -317,6 +317,22 @@ void gather_cols(Ctx* ctx, const T* in, int64_t ld, int64_t rows, const int32_t*
 }
 
 template <typename T>
+__global__ void gather_rows_kernel(const T* __restrict__ in, int64_t ld, const int32_t* __restrict__ idx, int64_t nrows,
+                                   int64_t ncols, T* __restrict__ out, int64_t ldo) {
+  int64_t total = nrows * ncols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i % nrows, c = i / nrows;
+    out[r + c * ldo] = in[(int64_t)idx[r] + c * ld];
+  }
+}
+template <typename T>
+void gather_rows(Ctx* ctx, const T* in, int64_t ld, const int32_t* idx_dev, int64_t nrows, int64_t ncols, T* out, int64_t ldo) {
+  if (nrows == 0 || ncols == 0) return;
+  gather_rows_kernel<T><<<grid_for(ctx, nrows * ncols, 256), 256, 0, ctx->stream>>>(in, ld, idx_dev, nrows, ncols, out, ldo);
+  LAUNCH_CHECK(ctx);
+}
+
+template <typename T>
 __global__ void concat_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ out, int64_t pre,
                               int64_t a, int64_t b, int64_t post) {
   int64_t ab = a + b, total = pre * ab * post;
@@ -430,6 +446,7 @@ void col_norms2(Ctx* ctx, const T* A, int64_t rows, int64_t cols, int64_t ld, do
   template void transpose_conj<T>(Ctx*, const T*, int64_t, int64_t, int64_t, T*, int64_t, bool);                       \
   template void copy_block<T>(Ctx*, const T*, int64_t, T*, int64_t, int64_t, int64_t);                                 \
   template void gather_cols<T>(Ctx*, const T*, int64_t, int64_t, const int32_t*, int64_t, const double*, T*, int64_t); \
+  template void gather_rows<T>(Ctx*, const T*, int64_t, const int32_t*, int64_t, int64_t, T*, int64_t);              \
   template void concat_mode<T>(Ctx*, const T*, const T*, T*, int64_t, int64_t, int64_t, int64_t);                      \
   template void fill_normal<T>(Ctx*, T*, int64_t, uint64_t, double);                                                   \
   template void set_identity<T>(Ctx*, T*, int64_t, int64_t, int64_t);                                                  \

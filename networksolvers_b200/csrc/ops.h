@@ -38,6 +38,8 @@ template <typename T> void transpose_conj(Ctx* ctx, const T* in, int64_t rows, i
 template <typename T> void copy_block(Ctx* ctx, const T* in, int64_t ldi, T* out, int64_t ldo, int64_t rows, int64_t cols);
 // gather columns: out[:, j] = scale[j] * in[:, idx[j]]  (scale nullable)
 template <typename T> void gather_cols(Ctx* ctx, const T* in, int64_t ld, int64_t rows, const int32_t* idx_dev, int64_t ncols, const double* scale_dev, T* out, int64_t ldo);
+// gather rows: out[i, :] = in[idx[i], :]
+template <typename T> void gather_rows(Ctx* ctx, const T* in, int64_t ld, const int32_t* idx_dev, int64_t nrows, int64_t ncols, T* out, int64_t ldo);
 // concatenate along one mode: out[pre, a+b, post] from A[pre, a, post], B[pre, b, post] (B nullable => zero pad)
 template <typename T> void concat_mode(Ctx* ctx, const T* A, const T* B, T* out, int64_t pre, int64_t a, int64_t b, int64_t post);
 // Philox-4x32 N(0,1) fill (real and imaginary parts independent), scaled

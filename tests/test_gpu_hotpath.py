@@ -269,3 +269,67 @@ def test_sharded_matvec_two_gpus():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "NCCL_SHARD_OK 2" in r.stdout
+
+
+def test_tree_tdvp_one_site_and_two_site_regression():
+    """test/tdvp/test_tree_tdvp.jl:24-77 (chain + ancilla tree): 1-site TDVP (QR split + on-edge backward step,
+    src/applyexp.jl:30-42) and 2-site TDVP from the DMRG ground state; the reference's own asserts plus parity
+    with the oracle states."""
+    ns = _ns()
+    from oracle import sweep as osw
+    from oracle.ed import state_vector
+    N = 10
+    g = ns.NamedGraph()
+    for j in range(1, N + 1):
+        g.add_vertex(j)
+    for j in range(1, N):
+        g.add_edge(j, j + 1)
+    g.add_vertex(0)
+    g.add_edge(0, N // 2)
+    sites = ns.siteinds("S=1/2", g)
+    os_ = ns.OpSum()
+    for j in range(1, N):
+        os_.add(1.0, "Sz", j, "Sz", j + 1)
+        os_.add(0.5, "S+", j, "S-", j + 1)
+        os_.add(0.5, "S-", j, "S+", j + 1)
+    H = ns.ttno(os_, sites)
+    psi0 = ns.product_state(sites, neel(g))
+    trunc = dict(cutoff=1e-10, maxdim=100)
+    E, gs = ns.dmrg(H, psi0, nsweeps=5, nsites=2, inserter_kwargs=dict(trunc=trunc))
+    gs_host = gs.to_host()
+    tmax = 0.10
+    tp = list(np.arange(0, tmax + 1e-9, 0.02))
+    psi1 = ns.tdvp(H, gs_host, tp, nsites=1, inserter_kwargs=dict(trunc=trunc))
+    psi2 = ns.tdvp(H, gs_host, tp, nsites=2, inserter_kwargs=dict(trunc=trunc))
+    v0, v1, v2 = gs_host.to_dense(), psi1.to_host().to_dense(), psi2.to_host().to_dense()
+    assert np.linalg.norm(v1) > 0.999 and np.linalg.norm(v2) > 0.999
+    assert abs(np.vdot(v1, v0)) > 0.99
+    assert abs(np.vdot(v1, v2)) > 0.99
+    z = np.vdot(v1, v0)
+    assert abs(np.arctan(z.imag / z.real) - E * tmax) < 1e-4
+    # parity with the oracle evolving the same initial state
+    Ho, gso = to_oracle_ttn(H, True), to_oracle_ttn(gs_host)
+    o1 = state_vector(osw.tdvp(Ho, gso, tp, nsites=1, inserter_kwargs=dict(trunc=trunc)))
+    o2 = state_vector(osw.tdvp(Ho, gso, tp, nsites=2, inserter_kwargs=dict(trunc=trunc)))
+    assert 1 - abs(np.vdot(o1, v1)) / (np.linalg.norm(o1) * np.linalg.norm(v1)) < 1e-8
+    assert 1 - abs(np.vdot(o2, v2)) / (np.linalg.norm(o2) * np.linalg.norm(v2)) < 1e-8
+    assert abs(np.linalg.norm(o1) - np.linalg.norm(v1)) < 1e-8
+
+
+def test_one_site_tdvp_chain_krylov_solver():
+    """1-site TDVP with the Krylov exponentiate solver on a chain, vs the oracle."""
+    ns = _ns()
+    from oracle import sweep as osw
+    from oracle.ed import state_vector
+    from oracle.local_solvers import exponentiate_solver as o_exp
+    g = ns.path_graph(6)
+    sites = ns.siteinds("S=1/2", g)
+    H = ns.ttno(ns.heisenberg(g), sites)
+    psi = ns.random_state(sites, 8, seed=3, dtype=complex)
+    tp = [0.0, 0.05, 0.1]
+    out = ns.tdvp(H, psi, tp, nsites=1, tdvp_order=2, updater_kwargs=dict(solver=ns.exponentiate_solver))
+    v = out.to_host().to_dense()
+    vo = state_vector(osw.tdvp(to_oracle_ttn(H, True), to_oracle_ttn(psi), tp, nsites=1, tdvp_order=2,
+                               updater_kwargs=dict(solver=o_exp)))
+    assert 1 - abs(np.vdot(vo, v)) / (np.linalg.norm(vo) * np.linalg.norm(v)) < 1e-9
+    assert abs(np.linalg.norm(vo) - np.linalg.norm(v)) < 1e-9 * np.linalg.norm(vo)

@@ -137,3 +137,29 @@ def test_range_finder(ctx, cplx):
     assert Q.shape[1] == 5
     A2 = _rand(rng, (40, 40), cplx)
     assert ctx.range_finder(A2, max_rank=0).shape[1] == 0
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("shape", [(40, 40), (130, 100), (100, 130), (260, 200), (200, 333)])
+def test_factorize_blocked_jacobi(ctx, cplx, shape):
+    """The blocked (GEMM-rich) Jacobi path, forced at small sizes, against LAPACK."""
+    rng = np.random.default_rng(29)
+    M = _rand(rng, shape, cplx) * np.exp(-0.05 * np.arange(shape[1]))[None, :]
+    ctx.set_option("jacobi_block_min_n", 0)
+    try:
+        U, Cm, spec, info = ctx.factorize(M, cutoff=0.0)
+        U2, C2, spec2, info2 = ctx.factorize(M, cutoff=1e-10, maxdim=shape[1] // 3)
+    finally:
+        ctx.set_option("jacobi_block_min_n", 512)
+    s = np.linalg.svd(M, compute_uv=False)
+    k = min(shape)
+    assert info["newdim"] == k
+    assert np.abs(spec - s**2).max() <= 1e-12 * s[0] ** 2
+    assert np.abs(U.conj().T @ U - np.eye(k)).max() < 1e-12
+    assert np.abs(U @ Cm - M).max() < 1e-12 * max(1.0, s[0])
+    from oracle.tensor import truncate_spectrum
+    nk, terr = truncate_spectrum(s**2, cutoff=1e-10, mindim=1, maxdim=shape[1] // 3)
+    assert info2["newdim"] == nk and abs(info2["truncerr"] - terr) <= 1e-8 * max(terr, 1e-30) + 1e-18
+    Ub, sb, Vb = np.linalg.svd(M, full_matrices=False)
+    best = (Ub[:, :nk] * sb[:nk]) @ Vb[:nk]
+    assert np.abs(U2 @ C2 - best).max() < 1e-10 * max(1.0, s[0])
