@@ -119,7 +119,7 @@ class HostTTN:
         for v in verts:
             operands += [self.tensors[v], [sym(l) for l in self.legs[v]]]
         out = [sym(("site", v)) for v in verts]
-        return np.einsum(*operands, out).reshape(-1)
+        return np.einsum(*operands, out, optimize="greedy").reshape(-1)
 
 
 def canonical_legs(graph, v):
