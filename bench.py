@@ -28,6 +28,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 W_MPO, D_SITE = 5, 2
+# DRAM traffic per K3 launch measured by ncu --set full (profiles/), keyed by chi
+NCU_TRAFFIC_BYTES = {4096: 16.929995e9 + 533.289216e6}
 
 
 def matvec_flops(chi_l, chi_r, d=D_SITE, w=W_MPO, cplx=False):
@@ -273,8 +275,7 @@ def main():
         t3 = ctx.gemm_bench(m3, n3, k3, "N", "N", reps=3)
         gflops = 2.0 * m1 * n1 * k1 + 2.0 * m3 * n3 * k3
         achieved = gflops / ((t1 + t3) * 1e-3) * 1e-12
-        roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "gemm_tma_kernel<double> (K1 TN + K3 NN launches of the matvec)",
+XX: "gemm_tma_kernel<double> (K1 TN + K3 NN launches of the matvec)",
                 "k1_ms": t1, "k3_ms": t3,
                 "peak_source": "FP64 DMMA issue ceiling measured live by nsb_dmma_peak (MEASURED_PEAKS.json has no FP64 "
                                "entry; cuBLAS DGEMM on this pool reaches 35.5-36.0, profiles/r01_microbench_fp64_peaks.jsonl)"}
