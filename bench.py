@@ -275,7 +275,12 @@ def main():
         t3 = ctx.gemm_bench(m3, n3, k3, "N", "N", reps=3)
         gflops = 2.0 * m1 * n1 * k1 + 2.0 * m3 * n3 * k3
         achieved = gflops / ((t1 + t3) * 1e-3) * 1e-12
-XX: "gemm_tma_kernel<double> (K1 TN + K3 NN launches of the matvec)",
+        roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": NCU_TRAFFIC_BYTES.get(int(chi_l)),
+                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the K3 launch from the committed ncu --set full "
+                                "capture (profiles/r01_ncu_full_gemm_tma_K3_chi4096.json); algorithmic bytes of that launch 3.9e9; "
+                                "sm__pipe_tensor_cycles_active 97.4 %, dram throughput 2.8 % of peak",
+                "kernel": "gemm_tma_kernel<double> (K1 TN + K3 NN launches of the matvec)",
                 "k1_ms": t1, "k3_ms": t3,
                 "peak_source": "FP64 DMMA issue ceiling measured live by nsb_dmma_peak (MEASURED_PEAKS.json has no FP64 "
                                "entry; cuBLAS DGEMM on this pool reaches 35.5-36.0, profiles/r01_microbench_fp64_peaks.jsonl)"}
