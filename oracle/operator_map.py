@@ -54,12 +54,19 @@ def _contract_sequence(tensors, seq):
     return contract(_contract_sequence(tensors, a), _contract_sequence(tensors, b))
 
 
+_SEQ_CACHE = {}
+
+
 def optimal_map(P, psi: Tensor) -> Tensor:
-    """src/operator_map.jl:3-10."""
+    """src/operator_map.jl:3-10.  The reference recomputes the optimal sequence on every call (a cheap search in
+    Julia); here it is memoised on the operand signature so that the Python search does not distort CPU timings."""
     envs = [P.environment(e) for e in P.incident_edges()]
     site_ops = [P.operator[s] for s in P.sites()]
     lst = envs + site_ops + [psi]
-    seq, _ = optimal_sequence(lst)
+    key = tuple((t.labels, t.data.shape) for t in lst)
+    if key not in _SEQ_CACHE:
+        _SEQ_CACHE[key] = optimal_sequence(lst)[0]
+    seq = _SEQ_CACHE[key]
     out = _contract_sequence(lst, seq)
     return noprime(out).permute(psi.labels)
 
