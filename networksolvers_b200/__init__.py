@@ -7,7 +7,7 @@ three hooks that forward to the C ABI.  There is no CPU fallback.
 """
 from ._lib import NsbError, LIB_PATH  # noqa: F401
 from .graphs import NamedGraph, path_graph, named_comb_tree, star_of_chains, default_root_vertex  # noqa: F401
-from .models import (SiteType, SiteSet, siteinds, OpSum, heisenberg, transverse_ising, HostTTN, product_state,  # noqa: F401
+from .models import (SiteType, SiteSet, siteinds, OpSum, heisenberg, transverse_ising, hubbard, HostTTN, product_state,  # noqa: F401
                      random_state, ttno, mpo)
 from .device import Context, DeviceNetwork, default_context  # noqa: F401
 from .region_plans import (euler_tour_edges, euler_tour_vertices, euler_sweep, post_order_dfs_plan,  # noqa: F401

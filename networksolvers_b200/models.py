@@ -27,6 +27,19 @@ class SiteType:
             sz = np.diag([1.0, 0.0, -1.0])
             sp = np.sqrt(2.0) * np.diag([1.0, 1.0], k=1)
             self.states = {"Up": 0, "Z0": 1, "Dn": 2}
+        elif name == "Electron":
+            # basis Emp, Up, Dn, UpDn; the in-site Jordan-Wigner sign sits in the Dn operators (ITensors convention)
+            cup = np.zeros((4, 4)); cup[0, 1] = 1.0; cup[2, 3] = 1.0
+            cdn = np.zeros((4, 4)); cdn[0, 2] = 1.0; cdn[1, 3] = -1.0
+            F = np.diag([1.0, -1.0, -1.0, 1.0])
+            self.dim = 4
+            self.states = {"Emp": 0, "Up": 1, "Dn": 2, "UpDn": 3}
+            self.ops = {"Id": np.eye(4), "F": F, "Cup": cup, "Cdagup": cup.T.copy(), "Cdn": cdn, "Cdagdn": cdn.T.copy(),
+                        "Nup": cup.T @ cup, "Ndn": cdn.T @ cdn, "Nupdn": (cup.T @ cup) @ (cdn.T @ cdn),
+                        "CdagupF": cup.T @ F, "CupF": -(cup @ F), "CdagdnF": cdn.T @ F, "CdnF": -(cdn @ F)}
+            self.ops["Ntot"] = self.ops["Nup"] + self.ops["Ndn"]
+            self.ops["Sz"] = 0.5 * (self.ops["Nup"] - self.ops["Ndn"])
+            return
         else:
             raise ValueError(f"unknown site type {name}")
         sm = sp.T.copy()
@@ -80,6 +93,21 @@ def transverse_ising(graph, J=1.0, h=1.0):
         os.add(-J, "Z", u, "Z", v)
     for v in graph.vertices:
         os.add(-h, "X", v)
+    return os
+
+
+def hubbard(graph, t=1.0, U=4.0):
+    """Nearest-neighbour Hubbard model on a chain-ordered tree edge list (u before v in Jordan-Wigner order):
+    -t sum (c^dag_{u s} c_{v s} + h.c.) + U sum n_up n_dn, written with in-site string factors so that every term is a
+    product of two local operators (MPO bond dimension 6)."""
+    os = OpSum()
+    for u, v in graph.edges:
+        os.add(-t, "CdagupF", u, "Cup", v)
+        os.add(-t, "CupF", u, "Cdagup", v)
+        os.add(-t, "CdagdnF", u, "Cdn", v)
+        os.add(-t, "CdnF", u, "Cdagdn", v)
+    for v in graph.vertices:
+        os.add(U, "Nupdn", v)
     return os
 
 

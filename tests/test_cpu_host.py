@@ -108,3 +108,36 @@ def test_shard_bounds_partition():
                 assert 0 <= lo <= hi <= dim
                 cover += list(range(lo, hi))
             assert cover == list(range(dim))
+
+
+def test_hubbard_ttno_matches_oracle_and_jordan_wigner():
+    """Electron sites / Hubbard chain (BASELINE config 3 Hamiltonian, dense form): w = 6 MPO equals the oracle's and
+    its spectrum equals an independent Jordan-Wigner construction on 2N spinless modes."""
+    import itertools
+    import networksolvers_b200 as ns
+    from helpers import to_oracle_ttn, to_oracle_graph
+    from oracle.ed import ttno_dense
+    from oracle.models import electron_ops, hubbard_chain_opsum, ttno as ottno
+    N = 3
+    g = ns.path_graph(N)
+    sites = ns.siteinds("Electron", g)
+    H = ns.ttno(ns.hubbard(g, 1.0, 4.0), sites)
+    assert H[2].shape == (6, 6, 4, 4)
+    og = to_oracle_graph(g)
+    M = ttno_dense(to_oracle_ttn(H, operator=True), og, 4)
+    d, ops, _ = electron_ops()
+    Mo = ttno_dense(ottno(hubbard_chain_opsum(og, 1.0, 4.0), og, ops), og, 4)
+    assert np.abs(M - Mo).max() < 1e-14
+    a, Z, I2 = np.array([[0, 1], [0, 0]], float), np.diag([1.0, -1.0]), np.eye(2)
+    nm = 2 * N
+
+    def mode(k):
+        out = np.array([[1.0]])
+        for m in [Z] * k + [a] + [I2] * (nm - k - 1):
+            out = np.kron(out, m)
+        return out
+
+    c = [mode(k) for k in range(nm)]
+    Hf = sum(-1.0 * (c[2 * j + s].T @ c[2 * (j + 1) + s] + c[2 * (j + 1) + s].T @ c[2 * j + s]) for j in range(N - 1) for s in (0, 1))
+    Hf = Hf + sum(4.0 * (c[2 * j].T @ c[2 * j]) @ (c[2 * j + 1].T @ c[2 * j + 1]) for j in range(N))
+    assert np.abs(np.linalg.eigvalsh(M) - np.linalg.eigvalsh(Hf)).max() < 1e-12

@@ -333,3 +333,27 @@ def test_one_site_tdvp_chain_krylov_solver():
                                updater_kwargs=dict(solver=o_exp)))
     assert 1 - abs(np.vdot(vo, v)) / (np.linalg.norm(vo) * np.linalg.norm(v)) < 1e-9
     assert abs(np.linalg.norm(vo) - np.linalg.norm(v)) < 1e-9 * np.linalg.norm(vo)
+
+
+def test_dmrg_hubbard_dense_matches_oracle_and_ed():
+    """BASELINE config 3 Hamiltonian (Hubbard chain, d = 4, w = 6) in dense (no-QN) form, 2-site DMRG with
+    density-matrix expansion: energies vs the oracle (1e-10) and vs exact diagonalisation."""
+    ns = _ns()
+    g = ns.path_graph(6)
+    sites = ns.siteinds("Electron", g)
+    H = ns.ttno(ns.hubbard(g, 1.0, 4.0), sites)
+    psi0 = ns.product_state(sites, {v: ("Up" if v % 2 else "Dn") for v in g.vertices})
+    trunc = dict(cutoff=1e-10, maxdim=[10, 20, 60])
+    ek = dict(trunc=trunc, subspace_algorithm="densitymatrix", expansion_factor=1.1)
+    rec = SweepRecorder()
+    E, psi = ns.dmrg(H, psi0, nsweeps=5, nsites=2, extracter_kwargs=ek, inserter_kwargs=dict(trunc=trunc), sweep_callback=rec.sweep)
+    Eo, _, orec = _oracle_sweeps(to_oracle_ttn(H, True), to_oracle_ttn(psi0), nsweeps=5, nsites=2, extracter_kwargs=ek,
+                                 inserter_kwargs=dict(trunc=trunc))
+    for a, b in zip(rec.energies, orec["E"]):
+        assert abs(a - b) <= 1e-9 * abs(b), (rec.energies, orec["E"])
+    from oracle.ed import ttno_dense
+    Hd = ttno_dense(to_oracle_ttn(H, True), to_oracle_ttn(psi0).graph, 4)
+    # ground state within the half-filled Sz = 0 sector reached from the Neel start
+    w = np.linalg.eigvalsh(Hd)
+    assert E >= w[0] - 1e-9
+    assert abs(E - Eo) < 1e-8
