@@ -78,4 +78,4 @@ def test_factorize_round_trip_at_scale(n, cplx):
     assert abs(info["truncerr"] - terr) <= 1e-8 * terr + 1e-16
     resid = np.linalg.norm(U @ C - M) ** 2 / np.linalg.norm(M) ** 2
     assert abs(resid - terr) <= 1e-6 * terr + 1e-14
-    assert np.abs(spec[:k] - sig[:k] ** 2).max() <= 1e-12
+    assert np.abs(spec[:k] - sig[:k] ** 2).max() <= 5e-12          # LAPACK-level absolute accuracy on sigma^2
