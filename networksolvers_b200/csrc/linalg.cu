@@ -410,8 +410,9 @@ __global__ void block_gather_kernel(const T* __restrict__ src, T* __restrict__ d
   }
 }
 
-int g_jacobi_block_min_n = 512;
+int g_jacobi_block_min_n = 48;        // below this the unblocked kernel is used
 int g_jacobi_precondition = 1;
+int g_jacobi_precondition_min_n = 1024;   // QR preconditioning pays off only once the sweep count matters
 
 template <typename T>
 static int jacobi_blocked(Ctx* ctx, T* G, int64_t m, int64_t n, T* V, int64_t nv) {
@@ -530,7 +531,7 @@ FactorInfo factorize_left(Ctx* ctx, const T* M, int64_t rows, int64_t cols, int6
   const int64_t n = rows, m = cols;
   DevBuf G(ctx, sizeof(T) * m * n), V(ctx, sizeof(T) * n * n), Qm;
   std::vector<int32_t> pcol;        // column permutation of the preconditioned path
-  const bool precond = (n >= g_jacobi_block_min_n) && g_jacobi_precondition;
+  const bool precond = (n >= g_jacobi_block_min_n) && g_jacobi_precondition && (n >= g_jacobi_precondition_min_n);
   if (!precond) {   // G = M^H (cols x rows)
     if (!trans_in) transpose_conj<T>(ctx, M, rows, cols, ld, (T*)G.ptr, m, true);
     else conj_copy_block<T>(ctx, M, ld, (T*)G.ptr, m, cols, rows);            // stored (cols x rows): conj only

@@ -146,11 +146,13 @@ def test_factorize_blocked_jacobi(ctx, cplx, shape):
     rng = np.random.default_rng(29)
     M = _rand(rng, shape, cplx) * np.exp(-0.05 * np.arange(shape[1]))[None, :]
     ctx.set_option("jacobi_block_min_n", 0)
+    ctx.set_option("jacobi_precondition_min_n", 0)
     try:
         U, Cm, spec, info = ctx.factorize(M, cutoff=0.0)
         U2, C2, spec2, info2 = ctx.factorize(M, cutoff=1e-10, maxdim=shape[1] // 3)
     finally:
-        ctx.set_option("jacobi_block_min_n", 512)
+        ctx.set_option("jacobi_block_min_n", 48)
+        ctx.set_option("jacobi_precondition_min_n", 1024)
     s = np.linalg.svd(M, compute_uv=False)
     k = min(shape)
     assert info["newdim"] == k
