@@ -181,6 +181,17 @@ int nsb_maxlinkdim(nsb_net* net, int64_t* dim);
 int nsb_env_drop_all(nsb_net* net); /* forget cached environments (ProjTTN(H) freshly constructed) */
 int nsb_env_count(nsb_net* net, int32_t* n);
 
+/* ---- abelian quantum numbers (QN-conserving ITensors: `siteinds(...; conserve_qns=true)`, examples/dmrg.jl:10) ----
+ * Tensors stay dense (symmetry-forbidden entries are exact zeros); with QNs enabled the three factorisations on the
+ * path (nsb_insert, the expansion's eigen, the gauge QR) are done sector by sector with the merged-spectrum truncation
+ * of NDTensors, so no step ever mixes sectors.  Every basis state of the link on edge {u, v} carries the charge
+ * (nq int32 components) of the subtree on u's side; the other side is total - charge.  A site tensor must be non-zero
+ * only where  charge(site state) + sum over neighbours n of charge(subtree beyond n) == total. */
+int nsb_qn_enable(nsb_net* net, int32_t nq /* 1..4 */, const int32_t* total_charge /* nq */);
+int nsb_qn_set_site(nsb_net* net, int32_t v, const int32_t* charges /* site_dim x nq, state-major */);
+int nsb_qn_set_link(nsb_net* net, int32_t u, int32_t v, const int32_t* charges /* linkdim x nq: subtree on u's side */);
+int nsb_qn_get_link(nsb_net* net, int32_t u, int32_t v, int32_t* charges_out /* linkdim x nq: subtree on u's side */);
+
 /* ---- the three hooks ---------------------------------------------------------------------- */
 int nsb_extract(nsb_net* net, const int32_t* region, int32_t nreg, const nsb_trunc* trunc /* extracter's */,
                 const nsb_expand* expand /* NULL == none */, nsb_extract_info* info /* nullable */);

@@ -305,6 +305,18 @@ int nsb_matvec_flops(nsb_net* net, double* flops) { NET_CALL(net, NSB_REQUIRE(fl
 int nsb_net_set_shard(nsb_net* net, int32_t enable, int32_t* active) {
   NET_CALL(net, int a = net->n->set_shard(enable); if (active) *active = a)
 }
+int nsb_qn_enable(nsb_net* net, int32_t nq, const int32_t* total) {
+  NET_CALL(net, NSB_REQUIRE(total, NSB_EINVAL, "null"); net->n->qn_enable(nq, total))
+}
+int nsb_qn_set_site(nsb_net* net, int32_t v, const int32_t* charges) {
+  NET_CALL(net, NSB_REQUIRE(charges, NSB_EINVAL, "null"); net->n->qn_set_site(v, charges))
+}
+int nsb_qn_set_link(nsb_net* net, int32_t u, int32_t v, const int32_t* charges) {
+  NET_CALL(net, NSB_REQUIRE(charges, NSB_EINVAL, "null"); net->n->qn_set_link(u, v, charges))
+}
+int nsb_qn_get_link(nsb_net* net, int32_t u, int32_t v, int32_t* charges_out) {
+  NET_CALL(net, NSB_REQUIRE(charges_out, NSB_EINVAL, "null"); net->n->qn_get_link(u, v, charges_out))
+}
 int nsb_norm(nsb_net* net, double* out) { NET_CALL(net, NSB_REQUIRE(out, NSB_EINVAL, "null"); *out = net->n->norm()) }
 
 #pragma GCC visibility pop

@@ -288,10 +288,25 @@ void Net<T>::qr_step(int a, int b) {
   int64_t cols = Ap.dims.back(), rows = Ap.numel() / cols, k = std::min(rows, cols);
   std::vector<int64_t> qd(Ap.dims.begin(), Ap.dims.end() - 1);
   qd.push_back(k);
-  DTensor<T> Q(ctx, qd, order);
   Label aux = make_label(LK_AUX, 1);
-  DTensor<T> R(ctx, {k, cols}, {aux, l});
-  qr_thin<T>(ctx, Ap.data(), rows, cols, rows, Q.data(), rows, R.data(), k);
+  DTensor<T> Q, R;
+  if (qn_on) {
+    std::vector<Label> others(order.begin(), order.end() - 1);
+    std::vector<int64_t> odims(Ap.dims.begin(), Ap.dims.end() - 1);
+    std::vector<int64_t> rk = multi_keys(a, others, odims, false);                 // charge of a's side of {a, b}
+    std::vector<int64_t> ck = multi_keys(b, {l}, {cols}, false);                   // the same, as labelled on the link
+    DevBuf Qb, Rb;
+    std::vector<int64_t> newk;
+    qr_qn(Ap.data(), rows, cols, rk, ck, Qb, Rb, &k, newk);
+    qd.back() = k;
+    Q.buf = std::make_shared<DevBuf>(std::move(Qb)); Q.dims = qd; Q.labels = order;
+    R.buf = std::make_shared<DevBuf>(std::move(Rb)); R.dims = {k, cols}; R.labels = {aux, l};
+    qn_store_link(a, b, newk);
+  } else {
+    Q = DTensor<T>(ctx, qd, order);
+    R = DTensor<T>(ctx, {k, cols}, {aux, l});
+    qr_thin<T>(ctx, Ap.data(), rows, cols, rows, Q.data(), rows, R.data(), k);
+  }
   psi[a] = Q;
   canonicalize(a);
   ver[a]++;
@@ -617,7 +632,16 @@ bool Net<T>::expand_densitymatrix(const nsb_trunc& trunc, const nsb_expand& ex) 
   gemm<T>(ctx, OP_N, OP_C, nb, nb, ncol, one, S.data(), nb, 0, S.data(), nb, 0, zero, (T*)rho.ptr, nb, 0, 1);
   DevBuf Ub, Cb;
   std::vector<double> spec;
-  FactorInfo fi = factorize_left<T>(ctx, (T*)rho.ptr, nb, nb, nb, false, trunc.cutoff, trunc.mindim, kexp, true, Ub, Cb, spec);
+  std::vector<int64_t> exp_keys;
+  FactorInfo fi;
+  if (qn_on) {
+    std::vector<int64_t> bdims;
+    for (Label l : basis) bdims.push_back(A.dim_of(l));
+    std::vector<int64_t> keys = multi_keys(prev, basis, bdims, false);   // charge of prev's side of {prev, next}
+    fi = factorize_qn((T*)rho.ptr, nb, nb, keys, keys, trunc.cutoff, trunc.mindim, kexp, true, Ub, Cb, exp_keys);
+  } else {
+    fi = factorize_left<T>(ctx, (T*)rho.ptr, nb, nb, nb, false, trunc.cutoff, trunc.mindim, kexp, true, Ub, Cb, spec);
+  }
   int64_t ku = fi.newdim;
   T* U = (T*)Ub.ptr;
   for (int pass = 0; pass < ex.north_pass; ++pass) {
@@ -646,6 +670,17 @@ bool Net<T>::expand_densitymatrix(const nsb_trunc& trunc, const nsb_expand& ex) 
     for (auto& x : nl) if (x == aux) x = a;
     return t.relabeled(nl);
   };
+  if (qn_on) {   // the new states of the bond carry the charges of their symmetry blocks (prev's side)
+    std::vector<int64_t> oldc = side_charge(next, prev);
+    std::vector<int64_t> keys(cur + ku);
+    for (int64_t i = 0; i < cur; ++i) {
+      int64_t k = 0;
+      for (int c = 0; c < nq; ++c) k |= ((oldc[i * nq + c] + 32768) & 0xffff) << (16 * c);
+      keys[i] = k;
+    }
+    for (int64_t i = 0; i < ku; ++i) keys[cur + i] = exp_keys[i];
+    qn_store_link(prev, next, keys);
+  }
   psi[prev] = Ax;
   canonicalize(prev);
   ver[prev]++;
@@ -970,12 +1005,30 @@ void Net<T>::update_exp(double tre, double tim, int solver, const nsb_krylov* kp
     const int64_t cols = Ap.dims.back(), rows = Ap.numel() / cols, k = std::min(rows, cols);
     std::vector<int64_t> qd(Ap.dims.begin(), Ap.dims.end() - 1);
     qd.push_back(k);
-    DTensor<T> Q(ctx, qd, order);                                  // [others..., l] with dim(l) = k
     const Label ax = make_label(LK_AUX, 3, 0);
-    DTensor<T> R(ctx, {k, cols}, {ax, l});
+    DTensor<T> Q, R;                                               // Q: [others..., l] with dim(l) = k;  R: [ax, l]
+    std::vector<int64_t> saved_link;
+    int saved_side = -1;
     {
       PhaseTimer pt(ctx, NSB_T_GAUGE);
-      qr_thin<T>(ctx, Ap.data(), rows, cols, rows, Q.data(), rows, R.data(), k);
+      int64_t kk = k;
+      if (qn_on) {
+        int e = eid.at({v1, v2});
+        saved_link = qn_link[e]; saved_side = qn_side[e];
+        std::vector<Label> others(order.begin(), order.end() - 1);
+        std::vector<int64_t> odims(Ap.dims.begin(), Ap.dims.end() - 1);
+        std::vector<int64_t> rk = multi_keys(v1, others, odims, false), ck = multi_keys(v2, {l}, {cols}, false), newk;
+        DevBuf Qb, Rb;
+        qr_qn(Ap.data(), rows, cols, rk, ck, Qb, Rb, &kk, newk);
+        qd.back() = kk;
+        Q.buf = std::make_shared<DevBuf>(std::move(Qb)); Q.dims = qd; Q.labels = order;
+        R.buf = std::make_shared<DevBuf>(std::move(Rb)); R.dims = {kk, cols}; R.labels = {ax, l};
+        qn_store_link(v1, v2, newk);
+      } else {
+        Q = DTensor<T>(ctx, qd, order);
+        R = DTensor<T>(ctx, {k, cols}, {ax, l});
+        qr_thin<T>(ctx, Ap.data(), rows, cols, rows, Q.data(), rows, R.data(), k);
+      }
     }
     DTensor<T> E1, E2;
     {
@@ -1006,6 +1059,7 @@ void Net<T>::update_exp(double tre, double tim, int solver, const nsb_krylov* kp
     DTensor<T> th = contract(ctx, Q.relabeled(ql), Rt, false, false, 1);
     if (th.labels != theta.labels) th = permuted(ctx, th, theta.labels);
     theta = th;
+    if (qn_on) { int e = eid.at({v1, v2}); qn_link[e] = saved_link; qn_side[e] = saved_side; }   // bond of theta is the original one
   }
   if (info) { info->nmatvec = nmv; info->krylovdim = lastK; info->converged = conv; info->residual = err; info->reserved = 0; }
 }
@@ -1053,8 +1107,25 @@ void Net<T>::insert(const nsb_trunc* trunc, int normalize, int set_ortho, nsb_in
     for (Label l : right) cols *= theta.dim_of(l);
     DevBuf Ub, Cb;
     std::vector<double> spec;
-    FactorInfo fi = factorize_left<T>(ctx, M.data(), rows, cols, trans ? cols : rows, trans, tr.cutoff, tr.mindim, tr.maxdim,
-                                      false, Ub, Cb, spec);
+    FactorInfo fi;
+    if (qn_on) {
+      if (trans) {   // block-wise path wants the contiguous [left..., right...] matricisation
+        std::vector<Label> order = left;
+        order.insert(order.end(), right.begin(), right.end());
+        M = permuted(ctx, theta, order);
+        trans = false;
+      }
+      std::vector<int64_t> ld_, rd_;
+      for (Label l : left) ld_.push_back(theta.dim_of(l));
+      for (Label l : right) rd_.push_back(theta.dim_of(l));
+      std::vector<int64_t> rk = multi_keys(v1, left, ld_, false);      // charge of v1's side of the new bond
+      std::vector<int64_t> ck = multi_keys(v2, right, rd_, true);      // total - (charge of v2's side)
+      std::vector<int64_t> newk;
+      fi = factorize_qn(M.data(), rows, cols, rk, ck, tr.cutoff, tr.mindim, tr.maxdim, false, Ub, Cb, newk);
+      qn_store_link(v1, v2, newk);
+    } else {
+      fi = factorize_left<T>(ctx, M.data(), rows, cols, trans ? cols : rows, trans, tr.cutoff, tr.mindim, tr.maxdim, false, Ub, Cb, spec);
+    }
     int64_t k = fi.newdim;
     std::vector<int64_t> ud, cd;
     std::vector<Label> ul = left, cl;

@@ -38,6 +38,11 @@ struct NetBase {
   virtual double matvec_flops() = 0;
   virtual double norm() = 0;
   virtual int set_shard(int enable) = 0;   // returns 1 if the current position is sharded across ranks
+  // abelian quantum numbers (dense storage, block-wise factorisations)
+  virtual void qn_enable(int nq, const int32_t* total) = 0;
+  virtual void qn_set_site(int v, const int32_t* charges) = 0;
+  virtual void qn_set_link(int u, int v, const int32_t* charges) = 0;
+  virtual void qn_get_link(int u, int v, int32_t* charges_out) = 0;
 };
 
 template <typename T>
@@ -66,6 +71,21 @@ struct Net : public NetBase {
   int64_t shard_lo = 0, shard_hi = 0;
   DTensor<T> shard_env;                         // rows [shard_lo, shard_hi) of the last environment
   void shard_prepare();
+  // QN bookkeeping: every basis state of a link carries the charge of the subtree on the side of qn_side[e]
+  bool qn_on = false;
+  int nq = 0;
+  std::vector<int64_t> qn_total;
+  std::vector<std::vector<int64_t>> qn_site, qn_link;   // [v][state*nq + c], [edge][state*nq + c]
+  std::vector<int> qn_side;                             // per edge: vertex whose side the charges describe
+  std::vector<int64_t> side_charge(int v, int n) const;                       // charges of the subtree on n's side of {v, n}
+  std::vector<int64_t> leg_charges(int owner, Label l) const;
+  std::vector<int64_t> multi_keys(int owner, const std::vector<Label>& labels, const std::vector<int64_t>& dims, bool complement) const;
+  void qn_store_link(int v, int n, const std::vector<int64_t>& keys_on_v_side);
+  FactorInfo factorize_qn(const T* M, int64_t rows, int64_t cols, const std::vector<int64_t>& rk, const std::vector<int64_t>& ck,
+                          double cutoff, int64_t mindim, int64_t maxdim, bool sqrt_spectrum, DevBuf& U, DevBuf& C,
+                          std::vector<int64_t>& new_keys);
+  void qr_qn(const T* M, int64_t rows, int64_t cols, const std::vector<int64_t>& rk, const std::vector<int64_t>& ck, DevBuf& Q,
+             DevBuf& R, int64_t* kout, std::vector<int64_t>& new_keys);
 
   Net(Ctx* c, int nv, const int32_t* e, int ne, const int64_t* sd);
 
@@ -120,6 +140,10 @@ struct Net : public NetBase {
   double matvec_flops() override;
   double norm() override;
   int set_shard(int enable) override;
+  void qn_enable(int nq, const int32_t* total) override;
+  void qn_set_site(int v, const int32_t* charges) override;
+  void qn_set_link(int u, int v, const int32_t* charges) override;
+  void qn_get_link(int u, int v, int32_t* charges_out) override;
 };
 
 // small dense host helpers (Ritz problems of the Krylov solvers)

@@ -184,6 +184,29 @@ class DeviceNetwork:
             self._upload(v, operator.tensors[v], operator.legs[v], True)
             self._upload(v, state.tensors[v], state.legs[v], False)
         self.set_ortho_region(state.ortho_region)
+        self.qn_enabled = False
+        if getattr(state, "qn", None) is not None:
+            self._upload_qn(state.qn)
+
+    def _upload_qn(self, qn):
+        tot = np.ascontiguousarray(qn["total"], dtype=np.int32)
+        i32p = C.POINTER(C.c_int32)
+        self.ctx.check(self._lib.nsb_qn_enable(self.handle, len(tot), tot.ctypes.data_as(i32p)))
+        for v in self.verts:
+            a = np.ascontiguousarray(qn["site"][v], dtype=np.int32)
+            self.ctx.check(self._lib.nsb_qn_set_site(self.handle, self.vid[v], a.ctypes.data_as(i32p)))
+        for (u, v), arr in qn["link"].items():
+            a = np.ascontiguousarray(arr, dtype=np.int32)
+            self.ctx.check(self._lib.nsb_qn_set_link(self.handle, self.vid[u], self.vid[v], a.ctypes.data_as(i32p)))
+        self.qn_enabled = True
+        self._qn_static = dict(total=np.array(qn["total"]), site={v: np.array(a) for v, a in qn["site"].items()})
+
+    def link_charges(self, u, v):
+        """Charges (linkdim, nq) of the subtree on u's side of the edge {u, v}."""
+        nq = len(self._qn_static["total"])
+        out = np.empty((self.linkdim(u, v), nq), dtype=np.int32)
+        self.ctx.check(self._lib.nsb_qn_get_link(self.handle, self.vid[u], self.vid[v], out.ctypes.data_as(C.POINTER(C.c_int32))))
+        return out.astype(np.int64)
 
     @classmethod
     def synthetic(cls, operator: HostTTN, sites, chi, seed=1234, dtype=np.float64, ctx=None, ortho_region=None):
@@ -276,7 +299,10 @@ class DeviceNetwork:
         tensors, legs = {}, {}
         for v in self.verts:
             tensors[v], legs[v] = self.site(v)
-        return HostTTN(self.graph, tensors, legs, ortho_region=self.ortho_region())
+        qn = None
+        if self.qn_enabled:
+            qn = dict(self._qn_static, link={(u, v): self.link_charges(u, v) for u, v in self.graph.edges})
+        return HostTTN(self.graph, tensors, legs, ortho_region=self.ortho_region(), qn=qn)
 
     def set_ortho_region(self, verts):
         arr = np.array([self.vid[v] for v in verts], dtype=np.int32)

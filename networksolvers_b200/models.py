@@ -54,16 +54,17 @@ class SiteType:
 class SiteSet:
     """`siteinds(site_type, graph)`."""
 
-    def __init__(self, site_type, graph):
+    def __init__(self, site_type, graph, conserve_qns=False):
         self.graph = graph
         self.type = site_type if isinstance(site_type, SiteType) else SiteType(site_type)
         self.dim = self.type.dim
+        self.conserve_qns = conserve_qns
 
 
-def siteinds(site_type, graph_or_n):
+def siteinds(site_type, graph_or_n, conserve_qns=False):
     from .graphs import path_graph
     g = path_graph(graph_or_n) if isinstance(graph_or_n, int) else graph_or_n
-    return SiteSet(site_type, g)
+    return SiteSet(site_type, g, conserve_qns=conserve_qns)
 
 
 class OpSum:
@@ -114,7 +115,8 @@ def hubbard(graph, t=1.0, U=4.0):
 class HostTTN:
     """Tensors on the vertices of a tree: `tensors[v]` (numpy, C-contiguous logical layout) with `legs[v]`."""
 
-    def __init__(self, graph, tensors, legs, ortho_region=None, site_dim=None):
+    def __init__(self, graph, tensors, legs, ortho_region=None, site_dim=None, qn=None):
+        self.qn = qn          # None, or dict(total=(nq,), site={v: (d, nq)}, link={(u, v): (dim, nq) on u's side})
         self.graph = graph
         self.tensors = dict(tensors)
         self.legs = {v: list(l) for v, l in legs.items()}
@@ -156,18 +158,44 @@ def canonical_legs(graph, v):
     return ([("link", v, nb[0])] if nb else []) + [("site", v)] + [("link", v, n) for n in nb[1:]]
 
 
-def product_state(sites: SiteSet, state, dtype=float):
-    """`ttn(state, sites)`: state maps vertex -> state name (e.g. "Up") or basis index."""
+SITE_CHARGES = {"S=1/2": [[1], [-1]], "S=½": [[1], [-1]], "S=1": [[2], [0], [-2]],
+                "Electron": [[0, 0], [1, 1], [1, -1], [2, 0]]}      # (2 Sz) for spins, (Nf, 2 Sz) for electrons
+
+
+def _side_vertices(g, u, v):
+    seen, todo = {u}, [u]
+    while todo:
+        x = todo.pop()
+        for n in g.neighbors(x):
+            if n not in seen and not (x == u and n == v):
+                seen.add(n)
+                todo.append(n)
+    return seen
+
+
+def product_state(sites: SiteSet, state, dtype=float, conserve_qns=None):
+    """`ttn(state, sites)`: state maps vertex -> state name (e.g. "Up") or basis index.  With conserve_qns (or
+    `siteinds(...; conserve_qns=True)`) the state carries its abelian charges and every later factorisation is done
+    sector by sector."""
     g = sites.graph
+    conserve = sites.conserve_qns if conserve_qns is None else conserve_qns
     tensors, legs = {}, {}
+    chosen = {}
     for v in g.vertices:
         s = state[v] if not callable(state) else state(v)
         idx = sites.type.states[s] if isinstance(s, str) else int(s)
+        chosen[v] = idx
         lg = canonical_legs(g, v)
         arr = np.zeros([sites.dim if l[0] == "site" else 1 for l in lg], dtype=dtype)
         arr.reshape(-1)[idx] = 1.0
         tensors[v], legs[v] = arr, lg
-    return HostTTN(g, tensors, legs, site_dim=sites.dim)
+    qn = None
+    if conserve:
+        sc = np.array(SITE_CHARGES[sites.type.name], dtype=np.int64)
+        total = sum(sc[chosen[v]] for v in g.vertices)
+        link = {(u, v): sum(sc[chosen[x]] for x in _side_vertices(g, u, v))[None, :] for u, v in g.edges}
+        qn = dict(total=np.asarray(total), site={v: sc for v in g.vertices}, link=link)
+    return HostTTN(g, tensors, legs, site_dim=sites.dim, qn=qn)
 
 
 def _side_size(g, u, v):

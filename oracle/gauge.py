@@ -37,7 +37,21 @@ def qr_step(psi, a, b):
     A, B = psi[a], psi[b]
     l = link(a, b)
     left = [x for x in A.labels if x != l]
-    Q, R = qr(A, left, _TMP)                     # Q: left + [TMP];  R: [TMP, l]
+    if getattr(psi, "qn", None) is not None:
+        import numpy as np
+        from .qn import label_charges, multi_index_charges, qr_qn
+        from .tensor import Tensor
+        qn = psi.qn
+        M = A.array(left + [l]).reshape(-1, A.dim(l))
+        row_keys = multi_index_charges([label_charges(qn, a, x) for x in left])
+        col_keys = qn.side_charge(b, a)
+        Qm, Rm, newk = qr_qn(M, row_keys, col_keys)
+        k = Qm.shape[1]
+        Q = Tensor(Qm.reshape([A.dim(x) for x in left] + [k]), left + [_TMP])
+        R = Tensor(Rm, [_TMP, l])
+        qn.set_link(a, b, newk)
+    else:
+        Q, R = qr(A, left, _TMP)                 # Q: left + [TMP];  R: [TMP, l]
     psi[a] = Q.relabel({_TMP: l})
     RB = contract(R, B)                          # sums over l
     psi[b] = RB.relabel({_TMP: l}).permute(B.labels)

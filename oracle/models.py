@@ -124,10 +124,11 @@ def _opmat(ops, name):
 class TTN:
     """Tree tensor network state/operator container (stands in for itn.TreeTensorNetwork)."""
 
-    def __init__(self, graph, tensors, ortho_region=None):
+    def __init__(self, graph, tensors, ortho_region=None, qn=None):
         self.graph = graph
         self.tensors = dict(tensors)
         self.ortho_region = list(ortho_region) if ortho_region is not None else list(graph.vertices)
+        self.qn = qn            # oracle.qn.QNInfo or None (dense, no symmetry bookkeeping)
 
     def __getitem__(self, v):
         return self.tensors[v]
@@ -136,7 +137,7 @@ class TTN:
         self.tensors[v] = t
 
     def copy(self):
-        return TTN(self.graph, dict(self.tensors), list(self.ortho_region))
+        return TTN(self.graph, dict(self.tensors), list(self.ortho_region), self.qn.copy() if self.qn is not None else None)
 
     def linkdim(self, u, v):
         return self.tensors[u].dim(link(u, v))
@@ -257,4 +258,24 @@ def random_ttn(g: NamedGraph, d, chi, seed=1234, dtype=float, root=None, orthogo
     psi = orthogonalize(psi, tgt)
     c = tgt[0]
     psi[c] = psi[c] / psi[c].norm()
+    return psi
+
+
+def site_charges(site_type):
+    """Per-basis-state charges: S=1/2 -> (2 Sz); S=1 -> (2 Sz); Electron -> (Nf, 2 Sz)."""
+    if site_type in ("S=1/2", "S=½"):
+        return np.array([[1], [-1]])
+    if site_type == "S=1":
+        return np.array([[2], [0], [-2]])
+    if site_type == "Electron":
+        return np.array([[0, 0], [1, 1], [1, -1], [2, 0]])
+    raise ValueError(site_type)
+
+
+def product_ttn_qn(g: NamedGraph, site_type, d, state_index, dtype=float):
+    """Product state with QN bookkeeping (`siteinds(...; conserve_qns=true)` + `ttn(state, sites)`)."""
+    from .qn import product_state_qn
+    psi = product_ttn(g, d, state_index, dtype=dtype)
+    sc = site_charges(site_type)
+    psi.qn = product_state_qn(g, {v: sc for v in g.vertices}, state_index, sc.shape[1])
     return psi

@@ -86,7 +86,17 @@ def subspace_expand_densitymatrix(problem, local_state, region_iterator, *, nort
     for _ in range(north_pass):
         sqrt_rho = conj_proj_A(sqrt_rho)
     rho = contract(sqrt_rho, dag(noprime(sqrt_rho)))       # labels: basis' (plev 1), basis (plev 0)
-    D, U, _ = eigen_trunc(rho, basis, _U, **trunc)         # U: basis (plev 0) + [u]
+    qn = getattr(psi, "qn", None)
+    if qn is not None:
+        from .qn import label_charges, multi_index_charges, eigen_trunc_qn
+        basis_p = [(k, n, p + 1) for (k, n, p) in basis]
+        nbasis = int(np.prod([A.dim(l) for l in basis]))
+        Mr = rho.array(basis_p + list(basis)).reshape(nbasis, nbasis)
+        keys = multi_index_charges([label_charges(qn, prev_vertex, x) for x in basis])
+        D, Um, newk, _ = eigen_trunc_qn(Mr, keys, **trunc)
+        U = Tensor(Um.reshape([A.dim(l) for l in basis] + [Um.shape[1]]), list(basis) + [_U])
+    else:
+        D, U, _ = eigen_trunc(rho, basis, _U, **trunc)     # U: basis (plev 0) + [u]
 
     Apa = prime(A, [a])
 
@@ -102,6 +112,9 @@ def subspace_expand_densitymatrix(problem, local_state, region_iterator, *, nort
 
     Ax = directsum(A, a, U, _U, newlabel=_AX)
     expander = contract(dag(Ax), A)                        # labels: [ax, a]
+    if qn is not None:
+        old = qn.side_charge(next_vertex, prev_vertex)     # charges of the subtree on prev's side
+        qn.set_link(prev_vertex, next_vertex, np.concatenate([old, newk], axis=0))
     psi[prev_vertex] = Ax.relabel({_AX: a})
     tmp = ("x", "a_old", 0)
     exp2 = expander.relabel({a: tmp}).relabel({_AX: a})    # [a(new), a_old]

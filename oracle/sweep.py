@@ -129,7 +129,10 @@ def inserter(problem, local_tensor, region_iter, *, normalize=False, set_orthogo
     elif len(region) == 2:
         a, b = region
         left = [l for l in psi[a].labels if l in local_tensor.labels]
-        U, C, info = factorize(local_tensor, left, link(a, b), **trunc)
+        if psi.qn is not None:
+            U, C, info = _factorize_qn(psi, local_tensor, a, b, left, **trunc)
+        else:
+            U, C, info = factorize(local_tensor, left, link(a, b), **trunc)
         psi[a] = U
         COUNTERS["last_truncerr"] = info["truncerr"]
         COUNTERS.setdefault("truncerrs", []).append(info["truncerr"])
@@ -142,6 +145,27 @@ def inserter(problem, local_tensor, region_iter, *, normalize=False, set_orthogo
     if normalize:
         psi[v] = psi[v] / psi[v].norm()
     return problem.setproperties(state=psi)
+
+
+def _factorize_qn(psi, theta, a, b, left, *, cutoff, mindim, maxdim):
+    """QN-conserving `factorize` (block-wise, merged-spectrum truncation); updates psi.qn for the new bond."""
+    from .qn import label_charges, multi_index_charges, svd_trunc_qn
+    qn = psi.qn
+    right = [l for l in theta.labels if l not in left]
+    dl = int(np.prod([theta.dim(l) for l in left]))
+    dr = int(np.prod([theta.dim(l) for l in right]))
+    M = theta.array(left + right).reshape(dl, dr)
+    row_keys = multi_index_charges([label_charges(qn, a, x) for x in left])
+    col_keys = qn.total[None, :] - multi_index_charges([label_charges(qn, b, x) for x in right])
+    maxdim = min(maxdim, dl, dr)
+    use_eigen = cutoff > 1e-12
+    Um, spec, Rm, newk, terr = svd_trunc_qn(M, row_keys, col_keys, cutoff=cutoff, mindim=mindim, maxdim=maxdim, use_eigen=use_eigen)
+    k = Um.shape[1]
+    bond = link(a, b)
+    U = Tensor(Um.reshape([theta.dim(l) for l in left] + [k]), left + [bond])
+    C = Tensor(Rm.reshape([k] + [theta.dim(l) for l in right]), [bond] + right)
+    qn.set_link(a, b, newk)
+    return U, C, {"decomp": "eigen" if use_eigen else "svd", "truncerr": terr, "spectrum": spec}
 
 
 def updater(problem, local_state, region_iter, **kws):

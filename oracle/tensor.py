@@ -229,7 +229,7 @@ def eigen_trunc(rho: Tensor, left, newlabel, *, cutoff=None, mindim=1, maxdim=No
     """
     left = list(left)
     right = [(k, n, p + 1) for (k, n, p) in left]
-    M = rho.array(left + right)
+    M = rho.array(right + left)          # rows = primed (output) basis, cols = unprimed: rho * U = U' * D
     d = int(np.prod([rho.dim(l) for l in left]))
     M = M.reshape(d, d)
     M = 0.5 * (M + M.conj().T)

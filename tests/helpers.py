@@ -66,3 +66,22 @@ class SweepRecorder:
         p = region_iter.problem
         self.energies.append(getattr(p, "eigenvalue", None))
         self.maxlinkdims.append(p.state.maxlinkdim())
+
+
+def to_oracle_qn(host):
+    """HostTTN.qn (dict) -> oracle.qn.QNInfo"""
+    from oracle.qn import QNInfo
+    from oracle.tensor import edge_key
+    if host.qn is None:
+        return None
+    link, side = {}, {}
+    for (u, v), arr in host.qn["link"].items():
+        link[edge_key(u, v)] = np.array(arr)
+        side[edge_key(u, v)] = u
+    return QNInfo(host.qn["total"], host.qn["site"], link, side)
+
+
+def to_oracle_ttn_qn(host):
+    psi = to_oracle_ttn(host)
+    psi.qn = to_oracle_qn(host)
+    return psi
