@@ -148,3 +148,32 @@ def test_tdvp_plan_structure():
     assert regs[len(regs) // 2:] == [list(reversed(r)) for r in reversed(regs[: len(regs) // 2])]
     ts = [k["updater_kwargs"]["time_step"] for _, k in plan[:7]]
     assert ts == [0.05, -0.05, 0.05, -0.05, 0.05, -0.05, 0.05]
+
+
+def test_qn_oracle_hubbard_sector_ground_state():
+    """QN-conserving oracle (block-wise factorisations, merged truncation): Hubbard N=6 stays in the (3,3) sector of
+    the start state and converges to that sector's exact ground state; dense and QN runs agree on the S=1 chain."""
+    import itertools
+    from oracle.models import electron_ops, hubbard_chain_opsum, product_ttn_qn
+    from oracle.qn import check_state_symmetric
+    g = path_graph(6)
+    d, ops, st = electron_ops()
+    H = ttno(hubbard_chain_opsum(g, 1.0, 4.0), g, ops)
+    psi0 = product_ttn_qn(g, "Electron", 4, {v: (st["Up"] if v % 2 else st["Dn"]) for v in g.vertices})
+    trunc = dict(cutoff=1e-10, maxdim=[10, 20, 60])
+    ek = dict(trunc=trunc, subspace_algorithm="densitymatrix", expansion_factor=1.1)
+    E, psi = dmrg(H, psi0, nsweeps=6, nsites=2, extracter_kwargs=ek, inserter_kwargs=dict(trunc=trunc))
+    Hd = ttno_dense(H, g, 4)
+    sector = [i for i, c in enumerate(itertools.product(range(4), repeat=6))
+              if sum(x in (1, 3) for x in c) == 3 and sum(x in (2, 3) for x in c) == 3]
+    Esec = np.linalg.eigvalsh(Hd[np.ix_(sector, sector)])[0]
+    assert abs(E - Esec) < 1e-8
+    assert check_state_symmetric(psi)
+    g = path_graph(10)
+    d, ops, st = spin_ops("S=1")
+    H = ttno(heisenberg_opsum(g), g, ops)
+    idx = neel(g, st)
+    trunc = dict(cutoff=1e-12, maxdim=[10, 40, 80, 160])
+    Eq, _ = dmrg(H, product_ttn_qn(g, "S=1", 3, idx), nsweeps=4, nsites=2, inserter_kwargs=dict(trunc=trunc))
+    Ed, _ = dmrg(H, product_ttn(g, d, idx), nsweeps=4, nsites=2, inserter_kwargs=dict(trunc=trunc))
+    assert abs(Eq - Ed) < 1e-9
