@@ -96,7 +96,7 @@ def subspace_expand_densitymatrix(problem, local_state, region_iterator, *, nort
         D, Um, newk, _ = eigen_trunc_qn(Mr, keys, **trunc)
         U = Tensor(Um.reshape([A.dim(l) for l in basis] + [Um.shape[1]]), list(basis) + [_U])
     else:
-        D, U, _ = eigen_trunc(rho, basis, _U, **trunc)     # U: basis (plev 0) + [u]
+        D, U, _ = eigen_trunc(rho, basis, _U, rows_primed=True, **trunc)     # U: basis (plev 0) + [u]
 
     Apa = prime(A, [a])
 

@@ -221,7 +221,7 @@ def svd_trunc(T: Tensor, left, newlabel, *, cutoff=None, mindim=1, maxdim=None):
     return Ut, s, Vt, terr
 
 
-def eigen_trunc(rho: Tensor, left, newlabel, *, cutoff=None, mindim=1, maxdim=None):
+def eigen_trunc(rho: Tensor, left, newlabel, *, cutoff=None, mindim=1, maxdim=None, rows_primed=False):
     """Hermitian eigendecomposition, eigenvalues descending, truncated by A.5.
 
     UPSTREAM `eigen(rho; ishermitian=true, cutoff, mindim, maxdim)` (App. A.8).
@@ -229,7 +229,9 @@ def eigen_trunc(rho: Tensor, left, newlabel, *, cutoff=None, mindim=1, maxdim=No
     """
     left = list(left)
     right = [(k, n, p + 1) for (k, n, p) in left]
-    M = rho.array(right + left)          # rows = primed (output) basis, cols = unprimed: rho * U = U' * D
+    # the matrix whose eigenvectors are wanted: rows = the index set that rho maps *to*.  factorize builds
+    # rho[l, l'] = theta theta^dagger (rows unprimed); the expansion builds rho[b', b] = S S^dagger (rows primed).
+    M = rho.array(right + left) if rows_primed else rho.array(left + right)
     d = int(np.prod([rho.dim(l) for l in left]))
     M = M.reshape(d, d)
     M = 0.5 * (M + M.conj().T)
