@@ -176,7 +176,7 @@ def main():
     ap.add_argument("--nsites", type=int, default=100)
     ap.add_argument("--cpu-chi", type=int, default=2048, help="bond dimension of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--region-step", action="store_true", help="also time full region steps (extract/eigsolve/insert)")
+    ap.add_argument("--no-region-step", action="store_true", help="skip the full region step (3-matvec Lanczos + truncating insert)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -286,7 +286,7 @@ def main():
                                "entry; cuBLAS DGEMM on this pool reaches 35.5-36.0, profiles/r01_microbench_fp64_peaks.jsonl)"}
 
     extra = {}
-    if args.region_step and rank == 0 and shard is None:
+    if not args.no_region_step and rank == 0 and shard is None:
         ctx.enable_timers(True)
         ctx.reset_timers()
         t0 = time.perf_counter()
@@ -295,6 +295,9 @@ def main():
         ctx.synchronize()
         extra["region_step_s"] = time.perf_counter() - t0
         extra["region_phase_ms"] = ctx.timers()
+        extra["region_newdim"] = int(ins.newdim)
+        extra["sweep_regions"] = 2 * (args.nsites - 1)
+        # one interior region step x number of regions of an Euler-tour sweep (end regions are cheaper): upper estimate
         extra["sweep_s_extrapolated"] = extra["region_step_s"] * 2 * (args.nsites - 1)
         ctx.enable_timers(False)
 

@@ -163,6 +163,92 @@ void qr_thin(Ctx* ctx, T* A, int64_t rows, int64_t cols, int64_t lda, T* Q, int6
   }
 }
 
+// Column-pivoted Householder QR (rank revealing; used as the preconditioner of the blocked Jacobi SVD):
+//   A P = Q R,  |R_jj| non-increasing.  perm_out[j] = original column placed at position j.
+__global__ void __launch_bounds__(256) pivot_select_kernel(double* __restrict__ cn, int64_t j, int64_t cols, int32_t* __restrict__ piv) {
+  __shared__ double sv[256];
+  __shared__ int si[256];
+  double best = -1.0; int bi = (int)j;
+  for (int64_t c = j + threadIdx.x; c < cols; c += blockDim.x) if (cn[c] > best) { best = cn[c]; bi = (int)c; }
+  sv[threadIdx.x] = best; si[threadIdx.x] = bi;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      if (sv[threadIdx.x + o] > sv[threadIdx.x] || (sv[threadIdx.x + o] == sv[threadIdx.x] && si[threadIdx.x + o] < si[threadIdx.x])) {
+        sv[threadIdx.x] = sv[threadIdx.x + o]; si[threadIdx.x] = si[threadIdx.x + o];
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    int p = si[0];
+    piv[j] = p;
+    double t = cn[j]; cn[j] = cn[p]; cn[p] = t;
+  }
+}
+template <typename T>
+__global__ void swap_cols_kernel(T* __restrict__ A, int64_t lda, int64_t rows, int64_t j, const int32_t* __restrict__ piv) {
+  int64_t p = piv[j];
+  if (p == j) return;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+    T a = A[r + j * lda], b = A[r + p * lda];
+    A[r + j * lda] = b; A[r + p * lda] = a;
+  }
+}
+template <typename T>
+__global__ void norm_downdate_kernel(const T* __restrict__ A, int64_t lda, int64_t j, int64_t cols, double* __restrict__ cn) {
+  for (int64_t c = j + 1 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < cols; c += (int64_t)gridDim.x * blockDim.x) {
+    double v = cn[c] - abs2_(A[j + c * lda]);
+    cn[c] = v > 0.0 ? v : 0.0;
+  }
+}
+
+template <typename T>
+void qr_pivoted_thin(Ctx* ctx, T* A, int64_t rows, int64_t cols, int64_t lda, T* Q, int64_t ldq, T* R, int64_t ldr,
+                     std::vector<int32_t>& perm_out) {
+  int64_t k = std::min(rows, cols);
+  ctx->cnt.qr_calls++;
+  DevBuf tau(ctx, sizeof(T) * k), cn(ctx, sizeof(double) * cols), piv(ctx, sizeof(int32_t) * k);
+  T* dtau = (T*)tau.ptr;
+  col_norms2<T>(ctx, A, rows, cols, lda, (double*)cn.ptr);
+  int maxgrid = ctx->num_sms * 4;
+  for (int64_t j = 0; j < k; ++j) {
+    if (j > 0 && j % 64 == 0 && j < cols)   // refresh the trailing norms (the downdate loses accuracy by cancellation)
+      col_norms2<T>(ctx, A + j + j * lda, rows - j, cols - j, lda, (double*)cn.ptr + j);
+    pivot_select_kernel<<<1, 256, 0, ctx->stream>>>((double*)cn.ptr, j, cols, (int32_t*)piv.ptr);
+    LAUNCH_CHECK(ctx);
+    swap_cols_kernel<T><<<std::max(1, (int)std::min<int64_t>((rows + 255) / 256, maxgrid)), 256, 0, ctx->stream>>>(A, lda, rows, j, (const int32_t*)piv.ptr);
+    LAUNCH_CHECK(ctx);
+    house_gen_kernel<T><<<1, 256, 0, ctx->stream>>>(A, rows, lda, j, dtau);
+    LAUNCH_CHECK(ctx);
+    if (j + 1 < cols) {
+      int grid = (int)std::min<int64_t>(cols - j - 1, maxgrid);
+      house_apply_kernel<T><<<grid, 256, 0, ctx->stream>>>(A, lda, rows, j, dtau, 1, A, lda, j + 1, cols);
+      LAUNCH_CHECK(ctx);
+      norm_downdate_kernel<T><<<std::max(1, (int)std::min<int64_t>((cols - j + 255) / 256, maxgrid)), 256, 0, ctx->stream>>>(A, lda, j, cols, (double*)cn.ptr);
+      LAUNCH_CHECK(ctx);
+    }
+  }
+  {
+    int64_t total = k * cols;
+    int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)ctx->num_sms * 8);
+    extract_r_kernel<T><<<grid, 256, 0, ctx->stream>>>(A, lda, k, cols, R, ldr);
+    LAUNCH_CHECK(ctx);
+  }
+  set_identity<T>(ctx, Q, rows, k, ldq);
+  for (int64_t j = k - 1; j >= 0; --j) {
+    int grid = (int)std::min<int64_t>(k - j, maxgrid);
+    house_apply_kernel<T><<<grid, 256, 0, ctx->stream>>>(A, lda, rows, j, dtau, 0, Q, ldq, j, k);
+    LAUNCH_CHECK(ctx);
+  }
+  std::vector<int32_t> hp(k);
+  NSB_CUDA(cudaMemcpyAsync(hp.data(), piv.ptr, sizeof(int32_t) * k, cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->sync();
+  perm_out.resize(cols);
+  std::iota(perm_out.begin(), perm_out.end(), 0);
+  for (int64_t j = 0; j < k; ++j) std::swap(perm_out[j], perm_out[hp[j]]);
+}
+
 // ------------------------------------------------------------------------------------------------
 // one-sided Jacobi: orthogonalise the n columns of G (m x n), accumulating the rotations in V (nv x n)
 // ------------------------------------------------------------------------------------------------
@@ -278,7 +364,7 @@ template <> __device__ __forceinline__ cdouble cmul_conj_a<cdouble>(cdouble a, c
 template <typename T, int N2>
 __global__ void __launch_bounds__(1024) herm_eig_kernel(const T* __restrict__ Sg, T* __restrict__ Rg,
                                                         unsigned long long* __restrict__ maxoff, double abs_floor,
-                                                        double outer_tol) {
+                                                        double outer_tol, int inner_cap) {
   // abs_floor = eps * (largest diagonal entry of the global Gram matrix): couplings below it cannot change any
   // sigma^2 by more than LAPACK-level absolute accuracy and are treated as converged.
   constexpr int NP = N2 / 2, RING = N2 - 1, TRI = N2 * (N2 + 1) / 2;
@@ -333,8 +419,8 @@ __global__ void __launch_bounds__(1024) herm_eig_kernel(const T* __restrict__ Sg
     }
   }
   const double tol = 2.220446049250313e-16 * (N2 / 2);   // rounding noise of the updated couplings is O(eps sqrt(N2))
-  for (int sweep = 0; sweep < 20; ++sweep) {
-    if (tid == 0) smax = 0ull;
+  for (int sweep = 0; sweep < inner_cap; ++sweep) {
+    if (tid == 0) { smax = 0ull; atomicAdd(maxoff + 1, 1ull); }
     __syncthreads();
     for (int r = 0; r < RING; ++r) {
       // phase A: rotation of every pair from its diagonal 2x2 block
@@ -346,14 +432,16 @@ __global__ void __launch_bounds__(1024) herm_eig_kernel(const T* __restrict__ Sg
         pq[2 * a] = (short)p; pq[2 * a + 1] = (short)q;
         double alpha = re(tri[tix(p, p)]), beta = re(tri[tix(q, q)]);
         T g = get(p, q);
-        double gabs = sqrt(abs2_(g)), den = sqrt(fabs(alpha * beta));
+        const double g2 = abs2_(g), ab = fabs(alpha * beta);
         T j11 = from_complex<T>(1.0, 0.0), j12 = zero_<T>(), j21 = zero_<T>(), j22 = from_complex<T>(1.0, 0.0);
-        if (gabs > abs_floor && gabs > tol * den) {
-          atomicMax(&smax, (unsigned long long)__double_as_longlong(den > 0.0 ? gabs / den : 1.0));
-          double zeta = (beta - alpha) / (2.0 * gabs);
+        if (g2 > abs_floor * abs_floor && g2 > tol * tol * ab) {
+          // squared relative coupling for the sweep-level convergence test (no sqrt / divide on the critical path)
+          atomicMax(&smax, (unsigned long long)__double_as_longlong(ab > 0.0 ? g2 / ab : 1.0));
+          const double gabs = sqrt(g2), ginv = 1.0 / gabs;
+          double zeta = (beta - alpha) * (0.5 * ginv);
           double tt = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-          double c = 1.0 / sqrt(1.0 + tt * tt), sn = c * tt;
-          double pr = re(g) / gabs, pi = -im(g) / gabs;       // conj(phase)
+          double c = rsqrt(1.0 + tt * tt), sn = c * tt;
+          double pr = re(g) * ginv, pi = -im(g) * ginv;       // conj(phase)
           j11 = from_complex<T>(c, 0.0);
           j12 = from_complex<T>(sn, 0.0);
           j21 = from_complex<T>(-sn * pr, -sn * pi);
@@ -392,9 +480,9 @@ __global__ void __launch_bounds__(1024) herm_eig_kernel(const T* __restrict__ Sg
       }
       __syncthreads();
     }
-    double off = __longlong_as_double((long long)smax);
+    double off = __longlong_as_double((long long)smax);   // squared
     __syncthreads();
-    if (off <= tol) break;
+    if (off <= tol * tol) break;
   }
   T* Ro = Rg + (size_t)blockIdx.x * N2 * N2;
   for (int e = tid; e < N2 * N2; e += nth) Ro[e] = R[e];
@@ -412,6 +500,7 @@ __global__ void block_gather_kernel(const T* __restrict__ src, T* __restrict__ d
 
 int g_jacobi_block_min_n = 48;        // below this the unblocked kernel is used
 int g_jacobi_precondition = 1;
+int g_jacobi_inner_cap = 3;   // inner sweeps per pair solve; the outer iteration finishes the job (measured optimum)
 int g_jacobi_precondition_min_n = 1024;   // QR preconditioning pays off only once the sweep count matters
 
 template <typename T>
@@ -466,10 +555,10 @@ static int jacobi_blocked(Ctx* ctx, T* G, int64_t m, int64_t n, T* V, int64_t nv
   int sweep = 0;
   const int64_t rounds = std::max<int64_t>(nblk - 1, 1);
   for (; sweep < 30; ++sweep) {
-    NSB_CUDA(cudaMemsetAsync(dmax, 0, sizeof(unsigned long long), ctx->stream));
+    NSB_CUDA(cudaMemsetAsync(dmax, 0, 2 * sizeof(unsigned long long), ctx->stream));
     for (int64_t r = 0; r < rounds; ++r) {
       gemm<T>(ctx, OP_C, OP_N, N2, N2, m, one, ga, m, m * N2, ga, m, m * N2, zero, (T*)Sb.ptr, N2, (int64_t)N2 * N2, npairs);
-      kern<<<(unsigned)npairs, 1024, smem, ctx->stream>>>((const T*)Sb.ptr, (T*)Rb.ptr, dmax, abs_floor, tol);
+      kern<<<(unsigned)npairs, 1024, smem, ctx->stream>>>((const T*)Sb.ptr, (T*)Rb.ptr, dmax, abs_floor, tol, g_jacobi_inner_cap);
       LAUNCH_CHECK(ctx);
       gemm<T>(ctx, OP_N, OP_N, m, N2, N2, one, ga, m, m * N2, (const T*)Rb.ptr, N2, (int64_t)N2 * N2, zero, gb, m, m * N2, npairs);
       gemm<T>(ctx, OP_N, OP_N, nv, N2, N2, one, va, nv, nv * N2, (const T*)Rb.ptr, N2, (int64_t)N2 * N2, zero, vb, nv, nv * N2, npairs);
@@ -481,10 +570,14 @@ static int jacobi_blocked(Ctx* ctx, T* G, int64_t m, int64_t n, T* V, int64_t nv
       for (int64_t s = 0; s < nblk; ++s) tmp[s] = blockid[src_of_dst[s]];
       blockid.swap(tmp);
     }
-    NSB_CUDA(cudaMemcpyAsync(ctx->h_pinned, dmax, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    NSB_CUDA(cudaMemcpyAsync(ctx->h_pinned, dmax, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     NSB_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->cnt.jacobi_sweeps++;
-    if (getenv("NSB_DEBUG_JACOBI")) fprintf(stderr, "[jacobi_blocked] n=%ld m=%ld sweep %d offmax %.3e tol %.3e floor %.3e\n", (long)n, (long)m, sweep, ctx->h_pinned[0], tol, abs_floor);
+    if (getenv("NSB_DEBUG_JACOBI")) {
+      unsigned long long inner; memcpy(&inner, &ctx->h_pinned[1], 8);
+      fprintf(stderr, "[jacobi_blocked] n=%ld m=%ld sweep %d offmax %.3e tol %.3e floor %.3e inner sweeps/pair-solve %.2f\n", (long)n, (long)m,
+              sweep, ctx->h_pinned[0], tol, abs_floor, (double)inner / (double)(rounds * npairs));
+    }
     if (ctx->h_pinned[0] <= tol) { ++sweep; break; }
   }
   // collect the n real columns (padding columns never mix: their Gram rows are exactly zero)
@@ -539,23 +632,12 @@ FactorInfo factorize_left(Ctx* ctx, const T* M, int64_t rows, int64_t cols, int6
     // Drmac-Veselic preconditioning: M P = Qm Rm (Householder QR, columns pre-sorted by decreasing norm), then
     // one-sided Jacobi on X = Rm^H (lower trapezoidal), whose columns are already nearly orthogonal:
     //   X J = W Sigma  =>  M P = (Qm J) Sigma W^H,  U = Qm J is a product of orthogonal transformations.
-    DevBuf Mw(ctx, sizeof(T) * rows * cols), Ms(ctx, sizeof(T) * rows * cols);
+    DevBuf Mw(ctx, sizeof(T) * rows * cols);
     if (!trans_in) copy_block<T>(ctx, M, ld, (T*)Mw.ptr, rows, rows, cols);
     else transpose_conj<T>(ctx, M, cols, rows, ld, (T*)Mw.ptr, rows, false);
-    DevBuf nrm(ctx, sizeof(double) * cols), pidx(ctx, sizeof(int32_t) * cols);
-    col_norms2<T>(ctx, (T*)Mw.ptr, rows, cols, rows, (double*)nrm.ptr);
-    std::vector<double> hn(cols);
-    NSB_CUDA(cudaMemcpyAsync(hn.data(), nrm.ptr, sizeof(double) * cols, cudaMemcpyDeviceToHost, ctx->stream));
-    ctx->sync();
-    pcol.resize(cols);
-    std::iota(pcol.begin(), pcol.end(), 0);
-    std::stable_sort(pcol.begin(), pcol.end(), [&](int32_t a, int32_t b) { return hn[a] > hn[b]; });
-    NSB_CUDA(cudaMemcpyAsync(pidx.ptr, pcol.data(), sizeof(int32_t) * cols, cudaMemcpyHostToDevice, ctx->stream));
-    gather_cols<T>(ctx, (T*)Mw.ptr, rows, rows, (const int32_t*)pidx.ptr, cols, nullptr, (T*)Ms.ptr, rows);
-    ctx->sync();
     Qm = DevBuf(ctx, sizeof(T) * rows * rows);
     DevBuf Rm(ctx, sizeof(T) * rows * cols);
-    qr_thin<T>(ctx, (T*)Ms.ptr, rows, cols, rows, (T*)Qm.ptr, rows, (T*)Rm.ptr, rows);
+    qr_pivoted_thin<T>(ctx, (T*)Mw.ptr, rows, cols, rows, (T*)Qm.ptr, rows, (T*)Rm.ptr, rows, pcol);
     transpose_conj<T>(ctx, (T*)Rm.ptr, rows, cols, rows, (T*)G.ptr, m, true);   // G = Rm^H (cols x rows)
     ctx->sync();
   }
