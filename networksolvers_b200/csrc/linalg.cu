@@ -500,7 +500,8 @@ __global__ void block_gather_kernel(const T* __restrict__ src, T* __restrict__ d
 
 int g_jacobi_block_min_n = 48;        // below this the unblocked kernel is used
 int g_jacobi_precondition = 1;
-int g_jacobi_inner_cap = 3;   // inner sweeps per pair solve; the outer iteration finishes the job (measured optimum)
+int g_jacobi_inner_cap = 1;   // inner sweeps per pair solve; the outer iteration finishes the job (measured optimum)
+int g_jacobi_pivot = 0;       // column pivoting in the preconditioning QR (measured: same sweep count, more launches)
 int g_jacobi_precondition_min_n = 1024;   // QR preconditioning pays off only once the sweep count matters
 
 template <typename T>
@@ -637,7 +638,13 @@ FactorInfo factorize_left(Ctx* ctx, const T* M, int64_t rows, int64_t cols, int6
     else transpose_conj<T>(ctx, M, cols, rows, ld, (T*)Mw.ptr, rows, false);
     Qm = DevBuf(ctx, sizeof(T) * rows * rows);
     DevBuf Rm(ctx, sizeof(T) * rows * cols);
-    qr_pivoted_thin<T>(ctx, (T*)Mw.ptr, rows, cols, rows, (T*)Qm.ptr, rows, (T*)Rm.ptr, rows, pcol);
+    if (g_jacobi_pivot) {
+      qr_pivoted_thin<T>(ctx, (T*)Mw.ptr, rows, cols, rows, (T*)Qm.ptr, rows, (T*)Rm.ptr, rows, pcol);
+    } else {
+      pcol.resize(cols);
+      std::iota(pcol.begin(), pcol.end(), 0);
+      qr_thin<T>(ctx, (T*)Mw.ptr, rows, cols, rows, (T*)Qm.ptr, rows, (T*)Rm.ptr, rows);
+    }
     transpose_conj<T>(ctx, (T*)Rm.ptr, rows, cols, rows, (T*)G.ptr, m, true);   // G = Rm^H (cols x rows)
     ctx->sync();
   }

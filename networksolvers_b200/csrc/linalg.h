@@ -14,6 +14,7 @@ template <typename T>
 void qr_thin(Ctx* ctx, T* A, int64_t rows, int64_t cols, int64_t lda, T* Q, int64_t ldq, T* R, int64_t ldr);
 
 extern int g_jacobi_precondition;  // 1: QR-precondition the blocked Jacobi (Drmac-Veselic)
+extern int g_jacobi_pivot;
 extern int g_jacobi_inner_cap;
 extern int g_jacobi_precondition_min_n;
 extern int g_jacobi_block_min_n;   // column count from which the blocked (GEMM-rich) Jacobi is used
