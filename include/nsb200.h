@@ -161,6 +161,12 @@ int nsb_comm_destroy(nsb_ctx* ctx);
  * partial theta'.  `*active` reports whether the current position is shardable (the last bond of theta must
  * carry the last environment); otherwise the matvec stays replicated.  All ranks must make the same calls. */
 int nsb_net_set_shard(nsb_net* net, int32_t enable, int32_t* active);
+/* Fused GEMM + reduce-scatter (ctx option "shard_fused" = 1): the last GEMM of the sharded matvec writes every output
+ * tile straight into the owning rank's staging window over NVLink peer memory (P2P stores from the epilogue), the owner
+ * sums the nranks partial slabs locally and one all-gather completes theta'.  Every rank creates a window of at least
+ * (bytes of the local tensor) and opens the windows of all peers (cudaIpc handles exchanged by the host). */
+int nsb_peer_window_create(nsb_ctx* ctx, int64_t bytes, char handle_out[64]);
+int nsb_peer_window_open(nsb_ctx* ctx, int32_t peer_rank, const char handle[64]);
 
 /* ---- network (state + operator on a tree) -------------------------------------------------- */
 int nsb_network_create(nsb_ctx* ctx, int32_t nverts, const int32_t* edges /* 2*nedges */, int32_t nedges,

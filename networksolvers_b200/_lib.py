@@ -89,6 +89,8 @@ SIGNATURES = {
     "nsb_comm_init": (C.c_int, [_vp, C.c_char_p, C.c_int, C.c_int]),
     "nsb_comm_destroy": (C.c_int, [_vp]),
     "nsb_net_set_shard": (C.c_int, [_vp, _i32, P(_i32)]),
+    "nsb_peer_window_create": (C.c_int, [_vp, _i64, C.c_char_p]),
+    "nsb_peer_window_open": (C.c_int, [_vp, _i32, C.c_char_p]),
     "nsb_network_create": (C.c_int, [_vp, _i32, P(_i32), _i32, P(_i64), _i32, P(_vp)]),
     "nsb_network_destroy": (C.c_int, [_vp]),
     "nsb_site_upload": (C.c_int, [_vp, _i32, _i32, P(_i32), P(_i64), _vp]),

@@ -129,6 +129,7 @@ int nsb_ctx_set_option(nsb_ctx* ctx, const char* key, int64_t value) {
   if (k == "gemm_impl") { NSB_REQUIRE(value >= 0 && value <= 3, NSB_EINVAL, "gemm_impl must be 0..3"); ctx->c.gemm_impl = (int)value; }
   else if (k == "jacobi_block_min_n") { NSB_REQUIRE(value >= 0, NSB_EINVAL, "jacobi_block_min_n must be >= 0"); g_jacobi_block_min_n = (int)value; }
   else if (k == "jacobi_precondition") { g_jacobi_precondition = value != 0; }
+  else if (k == "shard_fused") { ctx->c.shard_fused = value != 0; }
   else if (k == "jacobi_pivot") { g_jacobi_pivot = value != 0; }
   else if (k == "jacobi_inner_cap") { NSB_REQUIRE(value >= 1, NSB_EINVAL, "jacobi_inner_cap >= 1"); g_jacobi_inner_cap = (int)value; }
   else if (k == "jacobi_precondition_min_n") { g_jacobi_precondition_min_n = (int)value; }
@@ -214,6 +215,36 @@ int nsb_comm_destroy(nsb_ctx* ctx) {
   if (ctx->c.nccl_comm) { try { nccl_api().CommDestroy((ncclComm_t)ctx->c.nccl_comm); } catch (...) {} ctx->c.nccl_comm = nullptr; }
   ctx->c.rank = 0; ctx->c.nranks = 1;
   return NSB_OK;
+}
+
+// ---- peer-memory windows (fused GEMM + reduce-scatter epilogue) ------------------------------------
+int nsb_peer_window_create(nsb_ctx* ctx, int64_t bytes, char handle_out[64]) {
+  if (!ctx || !handle_out) return NSB_EINVAL;
+  NSB_TRY(&ctx->c)
+  NSB_CUDA(cudaSetDevice(ctx->c.device));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+  if (ctx->c.win_local && ctx->c.win_bytes < (size_t)bytes) { NSB_CUDA(cudaFree(ctx->c.win_local)); ctx->c.win_local = nullptr; }
+  if (!ctx->c.win_local) { NSB_CUDA(cudaMalloc(&ctx->c.win_local, (size_t)bytes)); ctx->c.win_bytes = (size_t)bytes; }
+  cudaIpcMemHandle_t h;
+  NSB_CUDA(cudaIpcGetMemHandle(&h, ctx->c.win_local));
+  memcpy(handle_out, &h, 64);
+  ctx->c.win_peer[ctx->c.rank] = ctx->c.win_local;
+  NSB_CATCH(&ctx->c)
+}
+int nsb_peer_window_open(nsb_ctx* ctx, int32_t peer_rank, const char handle[64]) {
+  if (!ctx || !handle) return NSB_EINVAL;
+  NSB_TRY(&ctx->c)
+  NSB_CUDA(cudaSetDevice(ctx->c.device));
+  NSB_REQUIRE(peer_rank >= 0 && peer_rank < 8 && peer_rank < ctx->c.nranks, NSB_EINVAL, "bad peer rank");
+  if (peer_rank == ctx->c.rank) { ctx->c.win_peer[peer_rank] = ctx->c.win_local; }
+  else {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    void* p = nullptr;
+    NSB_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->c.win_peer[peer_rank] = p;
+  }
+  NSB_CATCH(&ctx->c)
 }
 
 // ---- network -------------------------------------------------------------------------------------

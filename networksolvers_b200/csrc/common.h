@@ -100,6 +100,11 @@ struct Ctx {
   // multi-GPU (optional): NCCL communicator + rank info, see shard.cu
   void* nccl_comm = nullptr;
   int rank = 0, nranks = 1;
+  // peer-memory staging windows for the fused GEMM + reduce-scatter epilogue (cudaIpc-mapped)
+  void* win_local = nullptr;
+  size_t win_bytes = 0;
+  void* win_peer[8] = {nullptr};
+  int shard_fused = 0;
   // phase timers (ms), CUDA-event based: extract / matvec / krylov_vec / factorize / env
   double timers_ms[NSB_NUM_TIMERS] = {0};
   // small scratch areas for reductions / scalar read-back

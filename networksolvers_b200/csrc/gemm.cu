@@ -36,6 +36,7 @@ struct GemmParams {
   int alignedA, alignedB;   // 16-byte alignment of every chunk source
   int bcoordA, bcoordB;     // 0 when the operand is broadcast over the batch (stride 0)
   int64_t tiles_m, tiles_n;
+  PeerOut peer;             // nranks > 1: fused reduce-scatter epilogue over peer memory
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -235,8 +236,14 @@ __device__ __forceinline__ void store_tile(const AccReal& acc, const GemmParams<
         int64_t n = n0 + wn * 32 + ni * 8 + 2 * t + (e & 1);
         if (m < p.M && n < p.N) {
           double r = p.alpha * acc.v[mi][ni][e];
-          if (has_beta) r += p.beta * C[m + n * p.ldc];
-          C[m + n * p.ldc] = r;
+          if (p.peer.nranks > 1) {
+            int64_t owner = n / p.peer.slab_cols;
+            double* dst = reinterpret_cast<double*>(p.peer.ptr[owner]) + p.peer.rank * p.peer.slab_elems;
+            dst[m + (n - owner * p.peer.slab_cols) * p.M] = r;
+          } else {
+            if (has_beta) r += p.beta * C[m + n * p.ldc];
+            C[m + n * p.ldc] = r;
+          }
         }
       }
 }
@@ -315,8 +322,14 @@ __device__ __forceinline__ void store_tile(const AccCplx& acc, const GemmParams<
         int64_t n = n0 + wn * 32 + ni * 8 + 2 * t + (e & 1);
         if (m < p.M && n < p.N) {
           cdouble r = mul_(p.alpha, make_cuDoubleComplex(acc.re[mi][ni][e], acc.im[mi][ni][e]));
-          if (has_beta) r = add_(r, mul_(p.beta, C[m + n * p.ldc]));
-          C[m + n * p.ldc] = r;
+          if (p.peer.nranks > 1) {
+            int64_t owner = n / p.peer.slab_cols;
+            cdouble* dst = reinterpret_cast<cdouble*>(p.peer.ptr[owner]) + p.peer.rank * p.peer.slab_elems;
+            dst[m + (n - owner * p.peer.slab_cols) * p.M] = r;
+          } else {
+            if (has_beta) r = add_(r, mul_(p.beta, C[m + n * p.ldc]));
+            C[m + n * p.ldc] = r;
+          }
         }
       }
 }
@@ -602,7 +615,7 @@ static bool launch_tma(Ctx* ctx, const GemmParams<T>& p) {
 template <typename T>
 void gemm(Ctx* ctx, int opa, int opb, int64_t M, int64_t N, int64_t K, T alpha, const T* A, int64_t lda,
           int64_t strideA, const T* B, int64_t ldb, int64_t strideB, T beta, T* C, int64_t ldc,
-          int64_t strideC, int64_t batch, int impl) {
+          int64_t strideC, int64_t batch, int impl, const PeerOut* peer) {
   if (M <= 0 || N <= 0 || batch <= 0) return;
   NSB_REQUIRE(K >= 0, NSB_EINVAL, "gemm: negative K");
   typedef TileCfg<T> Cfg;
@@ -611,6 +624,7 @@ void gemm(Ctx* ctx, int opa, int opb, int64_t M, int64_t N, int64_t K, T alpha, 
   p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldb = ldb; p.ldc = ldc;
   p.strideA = strideA; p.strideB = strideB; p.strideC = strideC; p.batch = batch;
   p.alpha = alpha; p.beta = beta;
+  if (peer) { NSB_REQUIRE(batch == 1 && peer->nranks <= 8, NSB_EINVAL, "gemm: peer epilogue needs batch == 1"); p.peer = *peer; }
   p.a_kmajor = (opa == OP_T || opa == OP_C);
   p.b_kmajor = (opb == OP_N || opb == OP_CONJ);
   p.sa = (ScalarTraits<T>::is_complex && (opa == OP_C || opa == OP_CONJ)) ? -1.0 : 1.0;
@@ -626,6 +640,7 @@ void gemm(Ctx* ctx, int opa, int opb, int64_t M, int64_t N, int64_t K, T alpha, 
   p.bcoordB = (strideB != 0 && batch > 1) ? 1 : 0;
 
   if (impl == GEMM_AUTO) impl = ctx->gemm_impl;
+  if (peer && (impl == GEMM_AUTO || impl == GEMM_NAIVE)) impl = GEMM_TMA;
   if (impl == GEMM_AUTO) {
     double work = (double)M * (double)N * (double)(K > 0 ? K : 1) * (double)batch;
     impl = (work < 32.0 * 32.0 * 32.0) ? GEMM_NAIVE : GEMM_TMA;
@@ -697,8 +712,8 @@ double dmma_peak_tflops(Ctx* ctx) {
 }
 
 template void gemm<double>(Ctx*, int, int, int64_t, int64_t, int64_t, double, const double*, int64_t, int64_t,
-                           const double*, int64_t, int64_t, double, double*, int64_t, int64_t, int64_t, int);
+                           const double*, int64_t, int64_t, double, double*, int64_t, int64_t, int64_t, int, const PeerOut*);
 template void gemm<cdouble>(Ctx*, int, int, int64_t, int64_t, int64_t, cdouble, const cdouble*, int64_t, int64_t,
-                            const cdouble*, int64_t, int64_t, cdouble, cdouble*, int64_t, int64_t, int64_t, int);
+                            const cdouble*, int64_t, int64_t, cdouble, cdouble*, int64_t, int64_t, int64_t, int, const PeerOut*);
 
 }  // namespace nsb

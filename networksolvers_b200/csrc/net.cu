@@ -514,6 +514,37 @@ DTensor<T> Net<T>::apply_heff(const DTensor<T>& x) {
         if (s.type == 0) X = contract(ctx, X, envs.at({s.u, s.v}).t, false, false, 1);
         else X = apply_small(ctx, s.op, X, W[s.v], w_out_labels(X, W[s.v], s.v, pos));
       }
+      // fused path: the last GEMM writes its tiles into the owners' staging windows over NVLink (P2P stores from the
+      // epilogue), the owner sums the partial slabs, one all-gather completes theta'
+      std::vector<Label> pl;
+      const int G = ctx->nranks;
+      const int64_t nb = x.dims.back();
+      bool fused = ctx->shard_fused && G <= 8 && nb % G == 0 && ctx->win_local &&
+                   ctx->win_bytes >= sizeof(T) * (size_t)x.numel() && contract_direct_labels(X, shard_env, &pl);
+      if (fused) {
+        for (auto& l : pl) l = label_setplev(l, 0);
+        int shared = 0;
+        for (Label l : X.labels) if (shard_env.find(l) >= 0) ++shared;
+        fused = (pl == x.labels) && shared == 2 && shard_env.find(X.labels.back()) >= 0 && shard_env.find(X.labels[X.rank() - 2]) >= 0;
+        for (int g = 0; g < G && fused; ++g) if (!ctx->win_peer[g]) fused = false;
+      }
+      if (fused) {
+        int64_t Kc = X.dims[X.rank() - 1] * X.dims[X.rank() - 2], P = X.numel() / Kc, N = nb;
+        PeerOut po;
+        for (int g = 0; g < G; ++g) po.ptr[g] = ctx->win_peer[g];
+        po.nranks = G; po.rank = ctx->rank; po.slab_cols = N / G; po.slab_elems = P * (N / G);
+        gemm<T>(ctx, OP_N, OP_N, P, N, Kc, from_complex<T>(1.0, 0.0), X.data(), P, 0, shard_env.data(), Kc, 0, zero_<T>(),
+                out.data(), P, 0, 1, GEMM_AUTO, &po);
+        // all ranks' stores must have landed before the owner reduces: a one-element all-reduce is the stream-ordered barrier
+        ncclResult_t r = nccl_api().AllReduce(ctx->d_scratch + 8, ctx->d_scratch + 8, 1, ncclDouble, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream);
+        if (r != ncclSuccess) throw Error(NSB_ENCCL, std::string("ncclAllReduce(barrier): ") + nccl_api().GetErrorString(r));
+        sum_slabs<T>(ctx, (const T*)ctx->win_local, G, po.slab_elems, out.data() + (int64_t)ctx->rank * po.slab_elems);
+        r = nccl_api().AllGather(out.data() + (int64_t)ctx->rank * po.slab_elems, out.data(), (size_t)po.slab_elems * NcclType<T>::mult, ncclDouble,
+                                 (ncclComm_t)ctx->nccl_comm, ctx->stream);
+        if (r != ncclSuccess) throw Error(NSB_ENCCL, std::string("ncclAllGather: ") + nccl_api().GetErrorString(r));
+        ctx->cnt.matvecs++;
+        return out;
+      }
       X = contract(ctx, X, shard_env, false, false, 1).noprime();
       if (X.labels != x.labels) X = permuted(ctx, X, x.labels);
       out = X;

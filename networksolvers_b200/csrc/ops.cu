@@ -405,6 +405,21 @@ void set_identity(Ctx* ctx, T* x, int64_t rows, int64_t cols, int64_t ld) {
 }
 
 template <typename T>
+__global__ void sum_slabs_kernel(const T* __restrict__ in, int nslabs, int64_t slab, T* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < slab; i += (int64_t)gridDim.x * blockDim.x) {
+    T acc = in[i];
+    for (int s = 1; s < nslabs; ++s) acc = add_(acc, in[(int64_t)s * slab + i]);
+    out[i] = acc;
+  }
+}
+template <typename T>
+void sum_slabs(Ctx* ctx, const T* in, int nslabs, int64_t slab, T* out) {
+  if (slab == 0) return;
+  sum_slabs_kernel<T><<<grid_for(ctx, slab, 256), 256, 0, ctx->stream>>>(in, nslabs, slab, out);
+  LAUNCH_CHECK(ctx);
+}
+
+template <typename T>
 __global__ void __launch_bounds__(256) col_norms2_kernel(const T* __restrict__ A, int64_t rows, int64_t cols, int64_t ld,
                                                          double* __restrict__ out) {
   for (int64_t c = blockIdx.x; c < cols; c += gridDim.x) {
@@ -450,6 +465,7 @@ void col_norms2(Ctx* ctx, const T* A, int64_t rows, int64_t cols, int64_t ld, do
   template void concat_mode<T>(Ctx*, const T*, const T*, T*, int64_t, int64_t, int64_t, int64_t);                      \
   template void fill_normal<T>(Ctx*, T*, int64_t, uint64_t, double);                                                   \
   template void set_identity<T>(Ctx*, T*, int64_t, int64_t, int64_t);                                                  \
+  template void sum_slabs<T>(Ctx*, const T*, int, int64_t, T*);                                                        \
   template void col_norms2<T>(Ctx*, const T*, int64_t, int64_t, int64_t, double*);
 INST(double)
 INST(cdouble)

@@ -45,6 +45,8 @@ template <typename T> void concat_mode(Ctx* ctx, const T* A, const T* B, T* out,
 // Philox-4x32 N(0,1) fill (real and imaginary parts independent), scaled
 template <typename T> void fill_normal(Ctx* ctx, T* x, int64_t n, uint64_t seed, double scale);
 template <typename T> void set_identity(Ctx* ctx, T* x, int64_t rows, int64_t cols, int64_t ld);
+// out[i] = sum_{s < nslabs} in[s * slab + i]   (owner-side reduction of the fused reduce-scatter)
+template <typename T> void sum_slabs(Ctx* ctx, const T* in, int nslabs, int64_t slab, T* out);
 // column squared norms of a (rows x cols) matrix
 template <typename T> void col_norms2(Ctx* ctx, const T* A, int64_t rows, int64_t cols, int64_t ld, double* out_dev);
 

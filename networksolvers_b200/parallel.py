@@ -43,10 +43,31 @@ class ShardedMatvec:
         self.net.matvec_device(reps)
 
 
-def setup_sharded_matvec(net, dist, rank, world):
+def setup_peer_windows(ctx, dist, rank, world, nbytes):
+    """Create this rank's staging window and map every peer's (cudaIpc handles travel through torch.distributed)."""
+    import torch
+    lib = ctx._lib
+    buf = C.create_string_buffer(64)
+    ctx.check(lib.nsb_peer_window_create(ctx.handle, int(nbytes), buf))
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    mine = torch.tensor(list(buf.raw), dtype=torch.uint8, device=dev)
+    allh = [torch.zeros(64, dtype=torch.uint8, device=dev) for _ in range(world)]
+    dist.all_gather(allh, mine)
+    for r in range(world):
+        ctx.check(lib.nsb_peer_window_open(ctx.handle, r, bytes(allh[r].cpu().tolist())))
+    dist.barrier()
+
+
+def setup_sharded_matvec(net, dist, rank, world, fused=False, init=True):
     """Enable the sharded H_eff application on `net` (after nsb_extract).  Returns a handle whose `.matvec()`
-    runs one sharded application; `.active` is False when the current position cannot be sharded."""
-    init_comm(net.ctx, dist, rank, world)
+    runs one sharded application; `.active` is False when the current position cannot be sharded.  With
+    `fused=True` the last GEMM reduces through peer-memory stores in its epilogue (see include/nsb200.h)."""
+    if init:
+        init_comm(net.ctx, dist, rank, world)
+    if fused:
+        _, dims = net.local_info()
+        setup_peer_windows(net.ctx, dist, rank, world, int(np.prod(dims)) * net.dtype.itemsize)
+    net.ctx.set_option("shard_fused", 1 if fused else 0)
     active = C.c_int32()
     net.ctx.check(net._lib.nsb_net_set_shard(net.handle, 1, C.byref(active)))
     return ShardedMatvec(net, bool(active.value))

@@ -19,11 +19,12 @@ def main():
     import networksolvers_b200 as ns
     from networksolvers_b200.parallel import setup_sharded_matvec
     ctx = ns.Context(local)
-    for cplx in (False, True):
+    comm_ready = False
+    for cplx, fused in ((False, False), (True, False), (False, True), (True, True)):
         g = ns.path_graph(12)
         sites = ns.siteinds("S=1/2", g)
         H = ns.ttno(ns.heisenberg(g), sites)
-        psi = ns.random_state(sites, 50, seed=9, dtype=complex if cplx else float)
+        psi = ns.random_state(sites, 48, seed=9, dtype=complex if cplx else float)
         net = ns.EigsolveProblem(state=psi, operator=H, ctx=ctx).net
         net.extract([6, 7])
         ref = net.matvec_device(1, download=True)
@@ -31,14 +32,9 @@ def main():
         # same problem again, sharded
         net2 = ns.EigsolveProblem(state=psi, operator=H, ctx=ctx).net
         net2.extract([6, 7])
-        sh = setup_sharded_matvec(net2, dist, rank, world) if not cplx else None
-        if cplx:
-            import ctypes as C
-            act = C.c_int32()
-            ctx.check(ctx._lib.nsb_net_set_shard(net2.handle, 1, C.byref(act)))
-            assert act.value == 1
-        else:
-            assert sh.active
+        sh = setup_sharded_matvec(net2, dist, rank, world, fused=fused, init=not comm_ready)
+        comm_ready = True
+        assert sh.active
         out = net2.matvec_device(1, download=True)
         err = np.abs(out - ref).max() / np.abs(ref).max()
         assert err < 1e-13, err
