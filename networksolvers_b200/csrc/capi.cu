@@ -237,12 +237,16 @@ int nsb_peer_window_open(nsb_ctx* ctx, int32_t peer_rank, const char handle[64])
   NSB_CUDA(cudaSetDevice(ctx->c.device));
   NSB_REQUIRE(peer_rank >= 0 && peer_rank < 8 && peer_rank < ctx->c.nranks, NSB_EINVAL, "bad peer rank");
   if (peer_rank == ctx->c.rank) { ctx->c.win_peer[peer_rank] = ctx->c.win_local; }
-  else {
+  else if (ctx->c.win_peer[peer_rank] && memcmp(ctx->c.win_peer_handle[peer_rank], handle, 64) == 0) {
+    // same allocation already mapped
+  } else {
+    if (ctx->c.win_peer[peer_rank]) { cudaIpcCloseMemHandle(ctx->c.win_peer[peer_rank]); ctx->c.win_peer[peer_rank] = nullptr; }
     cudaIpcMemHandle_t h;
     memcpy(&h, handle, 64);
     void* p = nullptr;
     NSB_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
     ctx->c.win_peer[peer_rank] = p;
+    memcpy(ctx->c.win_peer_handle[peer_rank], handle, 64);
   }
   NSB_CATCH(&ctx->c)
 }

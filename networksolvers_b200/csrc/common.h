@@ -104,6 +104,7 @@ struct Ctx {
   void* win_local = nullptr;
   size_t win_bytes = 0;
   void* win_peer[8] = {nullptr};
+  char win_peer_handle[8][64] = {{0}};
   int shard_fused = 0;
   // phase timers (ms), CUDA-event based: extract / matvec / krylov_vec / factorize / env
   double timers_ms[NSB_NUM_TIMERS] = {0};
