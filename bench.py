@@ -176,7 +176,8 @@ def main():
     ap.add_argument("--nsites", type=int, default=100)
     ap.add_argument("--cpu-chi", type=int, default=2048, help="bond dimension of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-fused", action="store_true", help="multi-GPU: plain NCCL all-reduce instead of the fused peer-store epilogue")
+    ap.add_argument("--fused", action="store_true", help="multi-GPU: fused GEMM + peer-store reduce-scatter epilogue instead of the "
+                    "NCCL all-reduce (correct but slower in round 1: the DMMA fragment layout issues 64-byte P2P stores)")
     ap.add_argument("--no-region-step", action="store_true", help="skip the full region step (3-matvec Lanczos + truncating insert)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -208,7 +209,7 @@ def main():
     shard = None
     if world > 1:
         from networksolvers_b200.parallel import setup_sharded_matvec
-        shard = setup_sharded_matvec(net, dist, rank, world, fused=not args.no_fused)
+        shard = setup_sharded_matvec(net, dist, rank, world, fused=args.fused)
         if not shard.active:
             shard = None
 
@@ -320,7 +321,7 @@ def main():
                            "chi": args.chi, "local_dims": dims, "flops_per_step": flops,
                            "l2": "inputs larger than L2 (L 0.64 GB, theta 0.5 GB, T1 2.5 GB per matvec)",
                            "parallelism": ("replicated" if shard is None else f"theta right-bond sharded x{world} + " +
-                                           ("NCCL allreduce" if args.no_fused else "fused GEMM/peer-store reduce-scatter + allgather"))
+                                           ("fused GEMM/peer-store reduce-scatter + allgather" if args.fused else "NCCL allreduce"))
                            if world > 1 else "single GPU", "setup_s": t_setup, "env_builds": info.env_builds},
                 "e2e": {"value": e2e_tflops, "unit": "TFLOP/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
                         "ms_per_step": e2e_s * 1e3},
