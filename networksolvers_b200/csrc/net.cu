@@ -388,6 +388,16 @@ std::vector<Label> Net<T>::w_out_labels(const DTensor<T>& X, const DTensor<T>& W
   return out;
 }
 
+// Output label order of the merged two-site operator = the order the two single-site applications would produce.
+template <typename T>
+std::vector<Label> Net<T>::merged_out_labels(const DTensor<T>& X, int a, int b) const {
+  DTensor<T> fake;                       // labels / dims only
+  fake.labels = w_out_labels(X, W[a], a, pos);
+  fake.dims.resize(fake.labels.size(), 1);
+  fake.buf = X.buf;
+  return w_out_labels(fake, W[b], b, pos);
+}
+
 template <typename T>
 int Net<T>::make_env(int u, int v) {
   auto key = std::make_pair(u, v);
@@ -441,6 +451,25 @@ void Net<T>::build_plan() {
     for (size_t j = start; j < ext.size(); ++j) {
       Step s; s.type = 0; s.u = ext[j]; s.v = v;
       plan.push_back(std::move(s));
+    }
+  }
+  // merge two consecutive site-operator steps (chain-like 2-site regions) into one pass over the big intermediate
+  for (size_t i = 0; i + 1 < plan.size(); ++i) {
+    if (plan[i].type == 1 && plan[i + 1].type == 1) {
+      int a = plan[i].v, b = plan[i + 1].v;
+      const DTensor<T>&Wa = W[a], &Wb = W[b];
+      int64_t kk = 1, nn = 1;   // contracted / new extents of the merged operator
+      kk = site_dims[a] * site_dims[b];
+      nn = kk;
+      for (int j = 0; j < Wa.rank(); ++j) if (label_kind(Wa.labels[j]) == LK_OP && Wb.find(Wa.labels[j]) < 0) { kk *= Wa.dims[j]; nn *= Wa.dims[j]; }
+      for (int j = 0; j < Wb.rank(); ++j) if (label_kind(Wb.labels[j]) == LK_OP && Wa.find(Wb.labels[j]) < 0) { kk *= Wb.dims[j]; nn *= Wb.dims[j]; }
+      if (kk * nn > 64 * 64 * 16) continue;   // (upper bound on K*N; keeps the operator in shared memory)
+      Step m; m.type = 2; m.u = a; m.v = b;
+      uint64_t pb = ctx->cnt.permute_bytes;
+      m.Wm = contract(ctx, Wa, Wb, false, false, 0);
+      ctx->cnt.permute_bytes = pb;
+      plan[i] = std::move(m);
+      plan.erase(plan.begin() + i + 1);
     }
   }
 }
@@ -512,7 +541,8 @@ DTensor<T> Net<T>::apply_heff(const DTensor<T>& x) {
       for (size_t i = 0; i + 1 < plan.size(); ++i) {
         auto& s = plan[i];
         if (s.type == 0) X = contract(ctx, X, envs.at({s.u, s.v}).t, false, false, 1);
-        else X = apply_small(ctx, s.op, X, W[s.v], w_out_labels(X, W[s.v], s.v, pos));
+        else if (s.type == 1) X = apply_small(ctx, s.op, X, W[s.v], w_out_labels(X, W[s.v], s.v, pos));
+        else X = apply_small(ctx, s.op, X, s.Wm, merged_out_labels(X, s.u, s.v));
       }
       // fused path: the last GEMM writes its tiles into the owners' staging windows over NVLink (P2P stores from the
       // epilogue), the owner sums the partial slabs, one all-gather completes theta'
@@ -559,7 +589,8 @@ DTensor<T> Net<T>::apply_heff(const DTensor<T>& x) {
   }
   for (auto& s : plan) {
     if (s.type == 0) X = contract(ctx, X, envs.at({s.u, s.v}).t, false, false, 1);
-    else X = apply_small(ctx, s.op, X, W[s.v], w_out_labels(X, W[s.v], s.v, pos));
+    else if (s.type == 1) X = apply_small(ctx, s.op, X, W[s.v], w_out_labels(X, W[s.v], s.v, pos));
+    else X = apply_small(ctx, s.op, X, s.Wm, merged_out_labels(X, s.u, s.v));
   }
   X = X.noprime();
   if (X.labels != x.labels) X = permuted(ctx, X, x.labels);
@@ -575,8 +606,16 @@ double Net<T>::matvec_flops() {
   std::vector<int64_t> dim = theta.dims;
   double flops = 0.0;
   auto numel = [&]() { double n = 1; for (auto d : dim) n *= (double)d; return n; };
+  // a merged two-site operator is counted as the two single-site applications it replaces (algorithmic count)
+  struct Item { const DTensor<T>* t; };
+  std::vector<const DTensor<T>*> seq;
   for (auto& s : plan) {
-    const DTensor<T>& Y = (s.type == 0) ? envs.at({s.u, s.v}).t : W[s.v];
+    if (s.type == 0) seq.push_back(&envs.at({s.u, s.v}).t);
+    else if (s.type == 1) seq.push_back(&W[s.v]);
+    else { seq.push_back(&W[s.u]); seq.push_back(&W[s.v]); }
+  }
+  for (const DTensor<T>* Yp : seq) {
+    const DTensor<T>& Y = *Yp;
     double kprod = 1, nprod = 1;
     std::vector<Label> nl;
     std::vector<int64_t> nd;

@@ -63,7 +63,9 @@ struct Net : public NetBase {
   // local problem
   DTensor<T> theta;
   std::vector<int> region;
-  struct Step { int type; int u, v; SmallOp<T> op; };   // type 0: environment (u -> v); 1: site operator at v
+  // type 0: environment (u -> v); 1: site operator at v; 2: the two site operators of a 2-site region merged into one
+  // small operator (u = first site, v = second site, Wm = W[u] * W[v] over their shared operator link)
+  struct Step { int type; int u, v; SmallOp<T> op; DTensor<T> Wm; };
   std::vector<Step> plan;
   DTensor<T> last_out;                          // result of the last nsb_matvec_device
   // multi-GPU: theta sharded along its last bond across the ranks of ctx->nccl_comm
@@ -110,6 +112,7 @@ struct Net : public NetBase {
   int position(const std::vector<int>& reg);
   int make_env(int u, int v);
   std::vector<Label> w_out_labels(const DTensor<T>& X, const DTensor<T>& Wv, int v, const std::vector<int>& reg) const;
+  std::vector<Label> merged_out_labels(const DTensor<T>& X, int a, int b) const;
   void build_plan();
   DTensor<T> apply_heff(const DTensor<T>& x);
   bool expand_densitymatrix(const nsb_trunc& trunc, const nsb_expand& ex);

@@ -100,13 +100,16 @@ void small_apply(Ctx* ctx, const T* X, T* out, const T* W, int nbig, const int64
   int64_t total = 1;
   for (int m = 0; m < nbig; ++m) { bd.dims[m] = big_dims[m]; bd.xs[m] = xs_big[m]; bd.os[m] = os_big[m]; total *= big_dims[m]; }
   if (total == 0 || N == 0) return;
-  constexpr int NCH = 8;
+  // output chunk per pass over X: one pass when N <= 32 (accumulators stay in registers), else chunks of 16
+  const int NCH = (N <= 8) ? 8 : (N <= 16 ? 16 : (N <= 32 && !ScalarTraits<T>::is_complex ? 32 : 16));
   size_t smem = sizeof(T) * (size_t)K * NCH + sizeof(int64_t) * (size_t)K;
   NSB_REQUIRE(smem <= 48 * 1024, NSB_EUNSUPPORTED, "small_apply: operator too large for the small-operator path");
   int ny = (N + NCH - 1) / NCH;
   int gx = grid_for(ctx, total, 256, 4);
   dim3 grid(gx, ny);
-  small_apply_kernel<T, NCH><<<grid, 256, smem, ctx->stream>>>(X, out, W, bd, K, k_off, N, n_off, total);
+  if (NCH == 8) small_apply_kernel<T, 8><<<grid, 256, smem, ctx->stream>>>(X, out, W, bd, K, k_off, N, n_off, total);
+  else if (NCH == 16) small_apply_kernel<T, 16><<<grid, 256, smem, ctx->stream>>>(X, out, W, bd, K, k_off, N, n_off, total);
+  else small_apply_kernel<T, 32><<<grid, 256, smem, ctx->stream>>>(X, out, W, bd, K, k_off, N, n_off, total);
   LAUNCH_CHECK(ctx);
 }
 

@@ -369,3 +369,31 @@ def test_dmrg_hubbard_dense_matches_oracle_and_ed():
     assert E >= w[0] - 1e-9                                  # variational
     assert min(abs(rec.energies[2] - Esec), abs(rec.energies[2] - w[0])) < 1e-3 or E < Esec
     assert all(b <= a + 1e-9 for a, b in zip(rec.energies[:-1], rec.energies[1:]))   # monotone over sweeps
+
+
+def test_tdvp_two_site_with_expansion_quench_example():
+    """examples/quench_evolution.jl:20-57 exactly: 2-site TDVP, tdvp_order 4, RK4, densitymatrix expansion
+    (expansion_factor 1.2, max_expand 4), cutoff 1e-14, normalize -- complex arithmetic through the expansion path."""
+    ns = _ns()
+    from oracle.ed import ed_time_evolution, state_vector
+    from oracle.models import heisenberg_opsum, spin_ops
+    from oracle import sweep as osw
+    from oracle.local_solvers import runge_kutta_solver as o_rk
+    g = ns.path_graph(8)
+    sites = ns.siteinds("S=1/2", g)
+    H = ns.ttno(ns.heisenberg(g), sites)
+    psi0 = ns.product_state(sites, neel(g, even_up=False))
+    tp = list(np.arange(0, 0.2 + 1e-9, 0.05))
+    ek = dict(subspace_algorithm="densitymatrix", expansion_factor=1.2, max_expand=4)
+    ik = dict(trunc=dict(maxdim=5000, cutoff=1e-14), normalize=True)
+    psit = ns.tdvp(H, psi0, tp, nsites=2, tdvp_order=4, extracter_kwargs=ek, updater_kwargs=dict(solver=ns.runge_kutta_solver, order=4),
+                   inserter_kwargs=ik)
+    v = psit.to_host().to_dense()
+    og = to_oracle_ttn(psi0).graph
+    d, ops, _ = spin_ops("S=1/2")
+    vx = ed_time_evolution(heisenberg_opsum(og), og, ops, psi0.to_dense(), tp, normalize=True)
+    assert 1 - abs(np.vdot(vx, v)) < 1e-8
+    po = osw.tdvp(to_oracle_ttn(H, True), to_oracle_ttn(psi0), tp, nsites=2, tdvp_order=4, extracter_kwargs=ek,
+                  updater_kwargs=dict(solver=o_rk, order=4), inserter_kwargs=ik)
+    vo = state_vector(po)
+    assert 1 - abs(np.vdot(vo, v)) < 1e-9
