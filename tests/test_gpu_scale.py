@@ -22,6 +22,7 @@ def test_heff_hermitian_and_linear(chi, nsites, cplx):
     dt = np.complex128 if cplx else np.float64
     ns, net, region = _net(chi, nsites, dt)
     net.extract(region)
+    net.ctx.reset_counters()             # the default context is shared by all tests of the session
     legs, dims = net.local_info()
     assert dims == [chi, 2, 2, chi]
     rng = np.random.default_rng(1)
