@@ -1,0 +1,109 @@
+"""CPU checks of the divide & conquer logic the device eigensolver shares with the host (csrc/dc_secular.h):
+deflation planning + secular root finder + Gu-Eisenstat vectors, driven through tests/dc_cpu_harness.cpp
+(compiled here with g++).  The kernels / GEMMs of csrc/eigh.cu are covered by tests/test_gpu_eigh.py."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EPS = np.finfo(float).eps
+
+
+@pytest.fixture(scope="module")
+def lib(tmp_path_factory):
+    out = tmp_path_factory.mktemp("dc") / "libdc_cpu.so"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", os.path.join(HERE, "dc_cpu_harness.cpp"), "-o", str(out)])
+    lib = C.CDLL(str(out))
+    lib.dc_secular_root.restype = C.c_double
+    lib.dc_leaf_bounds.restype = C.c_int64
+    return lib
+
+
+def dc_eigh_tridiag(lib, d, e, leaf):
+    n = len(d)
+    bounds = np.zeros(n + 2, dtype=np.int64)
+    nb1 = lib.dc_leaf_bounds(C.c_int64(n), C.c_int64(leaf), bounds.ctypes.data_as(C.c_void_p), C.c_int64(len(bounds)))
+    bounds = bounds[:nb1].copy()
+    dm = d.copy()
+    for x in bounds[1:-1]:
+        dm[x - 1] -= abs(e[x - 1])
+        dm[x] -= abs(e[x - 1])
+    D = np.zeros(n)
+    Z = np.zeros((n, n), order="F")
+    for k in range(len(bounds) - 1):
+        lo, hi = bounds[k], bounds[k + 1]
+        T = np.diag(dm[lo:hi]) + np.diag(e[lo:hi - 1], 1) + np.diag(e[lo:hi - 1], -1)
+        w, v = np.linalg.eigh(T)
+        D[lo:hi] = w
+        Z[lo:hi, lo:hi] = v
+    stats = np.zeros(3, dtype=np.int64)
+    e = np.ascontiguousarray(e)
+    rc = lib.dc_merge_all(C.c_int64(n), e.ctypes.data_as(C.c_void_p), bounds.ctypes.data_as(C.c_void_p), C.c_int64(len(bounds) - 1),
+                          D.ctypes.data_as(C.c_void_p), Z.ctypes.data_as(C.c_void_p), stats.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    return D, Z, stats
+
+
+def tridiag_cases(n, rng):
+    from scipy.linalg import hessenberg
+    def tri(A):
+        H = hessenberg(A)
+        return np.diag(H).copy(), np.diag(H, -1).copy()
+    M = rng.standard_normal((n, n))
+    yield "gauss", tri(M + M.T)
+    G = rng.standard_normal((n, 2 * n))
+    yield "wishart", tri(G @ G.T)
+    Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    yield "graded", tri((Q * np.exp(-40.0 * np.arange(n) / n)) @ Q.T)
+    yield "lowrank", tri((Q[:, :3] * np.array([1.0, 0.5, 1e-3])) @ Q[:, :3].T)
+    yield "identity+rank1", tri(np.eye(n) + 1e-3 * np.outer(Q[:, 0], Q[:, 0]))
+    cl = np.repeat(np.arange(1, n // 8 + 2), 8)[:n].astype(float)
+    yield "clustered", tri((Q * cl) @ Q.T)
+    yield "wilkinson", (np.abs(np.arange(n) - n // 2).astype(float), np.ones(n - 1))
+    yield "hopping", (np.zeros(n), -np.ones(n - 1))
+    yield "decoupled", (rng.standard_normal(n), np.where(np.arange(n - 1) % 7 == 3, 0.0, rng.standard_normal(n - 1)))
+
+
+@pytest.mark.parametrize("n,leaf", [(37, 8), (128, 16), (301, 32)])
+def test_dc_matches_eigh(lib, n, leaf):
+    rng = np.random.default_rng(n)
+    for name, (d, e) in tridiag_cases(n, rng):
+        T = np.diag(d) + np.diag(e, 1) + np.diag(e, -1)
+        D, Z, stats = dc_eigh_tridiag(lib, d, e, leaf)
+        nrm = max(np.linalg.norm(T, 2), 1e-300)
+        res = np.linalg.norm(T @ Z - Z * D[None, :]) / (nrm * n)
+        orth = np.linalg.norm(Z.T @ Z - np.eye(n)) / n
+        err = np.max(np.abs(np.sort(D) - np.linalg.eigvalsh(T))) / nrm
+        assert res < 20 * EPS and orth < 20 * EPS and err < 50 * EPS, (name, n, res, orth, err, stats)
+        assert stats[1] < 60, (name, stats)
+
+
+def test_secular_root_relative_accuracy(lib):
+    """d_j - lambda_i must be accurate to a few ulps even when lambda_i is within 1e-14 of a pole."""
+    from fractions import Fraction
+    rng = np.random.default_rng(5)
+    K = 12
+    d = np.sort(rng.standard_normal(K))
+    z = rng.standard_normal(K)
+    z[3] = 1e-7          # root hugging d[3]
+    z /= np.linalg.norm(z)
+    z2 = z * z
+    rho = 0.7
+    for i in range(K):
+        delta = np.zeros(K)
+        it = C.c_int(0)
+        lam = lib.dc_secular_root(C.c_int(K), C.c_int(i), d.ctypes.data_as(C.c_void_p), z2.ctypes.data_as(C.c_void_p), C.c_double(rho),
+                                  delta.ctypes.data_as(C.c_void_p), C.byref(it))
+        # exact rational evaluation of the secular function at the implied lambda = d_org - delta_org
+        org = int(np.argmin(np.abs(delta)))
+        lam_q = Fraction(d[org]) - Fraction(delta[org])
+        f = 1 + Fraction(rho) * sum(Fraction(z2[j]) / (Fraction(d[j]) - lam_q) for j in range(K))
+        scale = 1 + float(Fraction(rho) * sum(abs(Fraction(z2[j]) / (Fraction(d[j]) - lam_q)) for j in range(K)))
+        assert abs(float(f)) <= 64 * EPS * scale, (i, float(f), scale)
+        for j in range(K):
+            exact = float(Fraction(d[j]) - lam_q)
+            assert abs(delta[j] - exact) <= 4 * EPS * abs(exact), (i, j)
+        assert d[i] < lam and (i == K - 1 or lam < d[i + 1])
