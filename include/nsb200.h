@@ -139,7 +139,7 @@ int nsb_ctx_create(int device, nsb_ctx** out);
 int nsb_ctx_destroy(nsb_ctx* ctx);
 const char* nsb_last_error(nsb_ctx* ctx); /* ctx may be NULL: last error of the calling thread */
 const char* nsb_version(void);
-int nsb_ctx_set_option(nsb_ctx* ctx, const char* key, int64_t value); /* "gemm_impl": 0 auto,1 naive,2 dmma,3 dmma+tma */
+int nsb_ctx_set_option(nsb_ctx* ctx, const char* key, int64_t value); /* "gemm_impl": 0 auto,1 naive,2 dmma,3 dmma+tma; "eigh_min_n": matrix size from which the truncating factorisation takes the Gram + eigh route (0 = never) */
 int nsb_ctx_counters(nsb_ctx* ctx, nsb_counters* out);
 int nsb_ctx_counters_reset(nsb_ctx* ctx);
 int nsb_ctx_synchronize(nsb_ctx* ctx);
@@ -236,6 +236,11 @@ int nsb_dmma_peak(nsb_ctx* ctx, double* tflops_out);
 int nsb_factorize_host(nsb_ctx* ctx, int32_t dtype, int64_t rows, int64_t cols, const void* M,
                        const nsb_trunc* trunc, void* U /* rows*min */, void* C /* min*cols */,
                        double* spectrum, nsb_insert_info* info);
+/* Hermitian eigen-decomposition of a host matrix A (n x n, full storage): w ascending, U (n x n, nullable) with
+ * A U = U diag(w).  The device eigensolver behind the large-matrix `eigen` route of nsb_insert / nsb_factorize_host
+ * (ITensors.factorize which_decomp = "eigen") and of the expansion's eigen(rho)
+ * (src/subspace/densitymatrix.jl:53). */
+int nsb_eigh_host(nsb_ctx* ctx, int32_t dtype, int64_t n, const void* A, double* w, void* U);
 /* thin QR of a host matrix (rows x cols): Q (rows x k), R (k x cols), k = min(rows, cols). */
 int nsb_qr_host(nsb_ctx* ctx, int32_t dtype, int64_t rows, int64_t cols, const void* M, void* Q, void* R);
 /* blocked randomised range finder for a host matrix A (m x n): orthonormal Q (m x rank) with

@@ -122,6 +122,7 @@ SIGNATURES = {
     "nsb_gemm_host": (C.c_int, [_vp, _i32, _i32, _i32, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32]),
     "nsb_gemm_bench": (C.c_int, [_vp, _i32, _i32, _i32, _i64, _i64, _i64, _i32, _i32, P(_dbl)]),
     "nsb_dmma_peak": (C.c_int, [_vp, P(_dbl)]),
+    "nsb_eigh_host": (C.c_int, [_vp, _i32, _i64, _vp, P(_dbl), _vp]),
     "nsb_factorize_host": (C.c_int, [_vp, _i32, _i64, _i64, _vp, P(Trunc), _vp, _vp, P(_dbl), P(InsertInfo)]),
     "nsb_qr_host": (C.c_int, [_vp, _i32, _i64, _i64, _vp, _vp, _vp]),
     "nsb_range_finder_host": (C.c_int, [_vp, _i32, _i64, _i64, _vp, _i64, _i32, _i32, _dbl, C.c_uint64, _vp, P(_i64)]),

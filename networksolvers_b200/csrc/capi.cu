@@ -4,6 +4,8 @@
 #include <random>
 
 #include "net.h"
+#include "eigh.h"
+#include <algorithm>
 
 namespace nsb {
 
@@ -133,6 +135,8 @@ int nsb_ctx_set_option(nsb_ctx* ctx, const char* key, int64_t value) {
   else if (k == "jacobi_pivot") { g_jacobi_pivot = value != 0; }
   else if (k == "jacobi_inner_cap") { NSB_REQUIRE(value >= 1, NSB_EINVAL, "jacobi_inner_cap >= 1"); g_jacobi_inner_cap = (int)value; }
   else if (k == "jacobi_precondition_min_n") { g_jacobi_precondition_min_n = (int)value; }
+  else if (k == "eigh_min_n") { g_eigh_min_n = (int)value; }
+  else if (k == "eigh_nb") { NSB_REQUIRE(value >= 2 && value <= 128 && value % 2 == 0, NSB_EINVAL, "eigh_nb must be even, 2..128"); g_eigh_nb = (int)value; }
   else throw Error(NSB_EINVAL, "unknown option " + k);
   NSB_CATCH(&ctx->c)
 }
@@ -448,6 +452,32 @@ extern "C" __attribute__((visibility("default"))) int nsb_factorize_host(nsb_ctx
   NSB_REQUIRE(M && rows > 0 && cols > 0, NSB_EINVAL, "bad arguments");
   if (dtype == NSB_F64) factorize_host_impl<double>(&ctx->c, rows, cols, M, trunc, U, C, spectrum, info);
   else factorize_host_impl<cdouble>(&ctx->c, rows, cols, M, trunc, U, C, spectrum, info);
+  NSB_CATCH(&ctx->c)
+}
+
+template <typename T>
+static void eigh_host_impl(Ctx* c, int64_t n, const void* A, double* w, void* U) {
+  DevBuf dA(c, sizeof(T) * n * n), dU(c, sizeof(T) * n * n);
+  NSB_CUDA(cudaMemcpyAsync(dA.ptr, A, sizeof(T) * n * n, cudaMemcpyHostToDevice, c->stream));
+  Eigh<T> eg;
+  eg.factor(c, (T*)dA.ptr, n, n);
+  std::vector<int32_t> order(n);
+  for (int64_t i = 0; i < n; ++i) order[i] = (int32_t)i;
+  std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return eg.w[a] < eg.w[b]; });
+  for (int64_t i = 0; i < n; ++i) w[i] = eg.w[order[i]];
+  if (U) {
+    eg.vectors(order.data(), n, (T*)dU.ptr, n);
+    NSB_CUDA(cudaMemcpyAsync(U, dU.ptr, sizeof(T) * n * n, cudaMemcpyDeviceToHost, c->stream));
+  }
+  c->sync();
+}
+extern "C" __attribute__((visibility("default"))) int nsb_eigh_host(nsb_ctx* ctx, int32_t dtype, int64_t n, const void* A, double* w, void* U) {
+  if (!ctx) return NSB_EINVAL;
+  NSB_TRY(&ctx->c)
+  NSB_CUDA(cudaSetDevice(ctx->c.device));
+  NSB_REQUIRE(A && w && n > 0, NSB_EINVAL, "bad arguments");
+  if (dtype == NSB_F64) eigh_host_impl<double>(&ctx->c, n, A, w, U);
+  else eigh_host_impl<cdouble>(&ctx->c, n, A, w, U);
   NSB_CATCH(&ctx->c)
 }
 

@@ -1,0 +1,594 @@
+// Hermitian eigensolver on device: blocked tridiagonalisation, divide & conquer, WY back-transformation (eigh.h).
+// The formulas follow tools/proto_eigh.py statement by statement (NumPy prototype, checked against LAPACK);
+// the D&C bookkeeping (dc_secular.h) is additionally exercised on the CPU by tests/test_cpu_dc.py.
+#include "eigh.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdlib>
+
+#include "dc_secular.h"
+#include "gemm.h"
+#include "linalg.h"
+#include "ops.h"
+
+namespace nsb {
+
+int g_eigh_min_n = 1024;
+int g_eigh_nb = 64;
+
+#define LAUNCH_CHECK(ctx) do { (ctx)->cnt.kernel_launches++; NSB_CUDA(cudaGetLastError()); } while (0)
+
+static bool eigh_debug() { static int v = -1; if (v < 0) v = getenv("NSB_DEBUG_EIGH") ? 1 : 0; return v == 1; }
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+namespace {
+
+constexpr int MAXNB = 128;
+
+__device__ __forceinline__ double sub_(double a, double b) { return a - b; }
+__device__ __forceinline__ cdouble sub_(cdouble a, cdouble b) { return make_cuDoubleComplex(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double neg_(double a) { return -a; }
+__device__ __forceinline__ cdouble neg_(cdouble a) { return make_cuDoubleComplex(-a.x, -a.y); }
+
+// block-wide sums of NV doubles per thread (blockDim <= 1024); result valid in all threads
+template <int NV>
+__device__ __forceinline__ void blk_sum(double (&v)[NV], double* sh /* NV * 32 + NV doubles */) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+  __syncthreads();
+  if (lane == 0)
+#pragma unroll
+    for (int i = 0; i < NV; ++i) sh[i * 32 + w] = v[i];
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double s = 0.0;
+    for (int j = 0; j < nw; ++j) s += sh[threadIdx.x * 32 + j];
+    sh[NV * 32 + threadIdx.x] = s;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = sh[NV * 32 + i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage 1: tridiagonalisation (LAPACK xHETRD 'L' convention, full storage)
+// ------------------------------------------------------------------------------------------------
+// (1) column j of A is brought up to date with the i reflectors of the current panel:
+//     A[j:, j] -= V[j:, :i] conj(W[j, :i]) + W[j:, :i] conj(V[j, :i]);  d[j] = Re A[j, j]
+template <typename T>
+__global__ void __launch_bounds__(256) trd_col_update_kernel(T* __restrict__ A, int64_t lda, int64_t n, int64_t j,
+                                                             const T* __restrict__ V, const T* __restrict__ W, int64_t ldp,
+                                                             int i, double* __restrict__ d_out) {
+  __shared__ T sv[MAXNB], sw[MAXNB];
+  for (int k = threadIdx.x; k < i; k += blockDim.x) {
+    sv[k] = conj_(V[j + (int64_t)k * ldp]);
+    sw[k] = conj_(W[j + (int64_t)k * ldp]);
+  }
+  __syncthreads();
+  const int64_t r = j + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  T acc = zero_<T>();
+  for (int k = 0; k < i; ++k) {
+    fma_(acc, V[r + (int64_t)k * ldp], sw[k]);
+    fma_(acc, W[r + (int64_t)k * ldp], sv[k]);
+  }
+  const T a = sub_(A[r + j * lda], acc);
+  A[r + j * lda] = a;
+  if (r == j) d_out[j] = re(a);
+}
+
+// (2) Householder reflector from x = A[j+1:, j]:  (I - tau v v^H)^H x = beta e_0, beta real, v[0] = 1.
+//     vcol is the panel column (row 0 based); rows <= j stay zero.
+template <typename T>
+__global__ void __launch_bounds__(256) trd_house_kernel(const T* __restrict__ A, int64_t lda, int64_t n, int64_t j,
+                                                        T* __restrict__ vcol, T* __restrict__ taus, double* __restrict__ e_out) {
+  __shared__ double sh[33];
+  const T* x = A + j * lda;
+  double s[1] = {0.0};
+  for (int64_t r = j + 2 + threadIdx.x; r < n; r += blockDim.x) s[0] += abs2_(x[r]);
+  blk_sum<1>(s, sh);
+  const T alpha = x[j + 1];
+  const double sigma = s[0], ar = re(alpha), ai = im(alpha);
+  if (sigma == 0.0 && ai == 0.0) {
+    for (int64_t r = j + 2 + threadIdx.x; r < n; r += blockDim.x) vcol[r] = zero_<T>();
+    if (threadIdx.x == 0) { vcol[j + 1] = from_complex<T>(1.0, 0.0); taus[j] = zero_<T>(); e_out[j] = ar; }
+    return;
+  }
+  const double beta = -copysign(sqrt(ar * ar + ai * ai + sigma), ar);
+  const double dr = ar - beta, di = ai, den = dr * dr + di * di;
+  const T scale = from_complex<T>(dr / den, -di / den);   // 1 / (alpha - beta)
+  for (int64_t r = j + 2 + threadIdx.x; r < n; r += blockDim.x) vcol[r] = mul_(scale, x[r]);
+  if (threadIdx.x == 0) {
+    vcol[j + 1] = from_complex<T>(1.0, 0.0);
+    taus[j] = from_complex<T>((beta - ar) / beta, -ai / beta);
+    e_out[j] = beta;
+  }
+}
+
+// (3) out[c] = sum_r conj(col_c[r]) v[r] over the columns of [A_trail (m x m) | W (m x i) | V (m x i)]:
+//     the Hermitian matrix-vector product as column dot products (coalesced), plus W^H v and V^H v.
+template <typename T, int CPB>
+__global__ void __launch_bounds__(256) trd_gemv_kernel(const T* __restrict__ At, int64_t lda, int64_t m,
+                                                       const T* __restrict__ Wp, const T* __restrict__ Vp, int64_t ldp, int i,
+                                                       const T* __restrict__ v, T* __restrict__ out) {
+  __shared__ double sh[2 * CPB * 32 + 2 * CPB];
+  const int64_t ncol = m + 2 * (int64_t)i, c0 = (int64_t)blockIdx.x * CPB;
+  const T* cols[CPB];
+#pragma unroll
+  for (int q = 0; q < CPB; ++q) {
+    const int64_t c = c0 + q;
+    cols[q] = c < m ? At + c * lda : (c < m + i ? Wp + (c - m) * ldp : (c < ncol ? Vp + (c - m - i) * ldp : nullptr));
+  }
+  double acc[2 * CPB];
+#pragma unroll
+  for (int q = 0; q < 2 * CPB; ++q) acc[q] = 0.0;
+  for (int64_t r = threadIdx.x; r < m; r += blockDim.x) {
+    const T x = v[r];
+#pragma unroll
+    for (int q = 0; q < CPB; ++q) {
+      if (cols[q]) {
+        const T a = cols[q][r];
+        acc[2 * q] += re(a) * re(x) + im(a) * im(x);
+        acc[2 * q + 1] += re(a) * im(x) - im(a) * re(x);
+      }
+    }
+  }
+  blk_sum<2 * CPB>(acc, sh);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int q = 0; q < CPB; ++q)
+      if (c0 + q < ncol) out[c0 + q] = from_complex<T>(acc[2 * q], acc[2 * q + 1]);
+  }
+}
+
+// (4a) w0 = tau (y - V p1 - W p2), p1 = W^H v, p2 = V^H v;  per-CTA partial of w0^H v
+template <typename T>
+__global__ void __launch_bounds__(256) trd_w1_kernel(const T* __restrict__ y, const T* __restrict__ Vp, T* __restrict__ Wp,
+                                                     int64_t ldp, int i, int64_t m, const T* __restrict__ tau_j,
+                                                     double* __restrict__ partial) {
+  __shared__ T p1[MAXNB], p2[MAXNB];
+  __shared__ double sh[2 * 32 + 2];
+  for (int k = threadIdx.x; k < i; k += blockDim.x) { p1[k] = y[m + k]; p2[k] = y[m + i + k]; }
+  __syncthreads();
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double dot[2] = {0.0, 0.0};
+  if (r < m) {
+    T acc = y[r];
+    for (int k = 0; k < i; ++k) {
+      fma_(acc, neg_(Vp[r + (int64_t)k * ldp]), p1[k]);
+      fma_(acc, neg_(Wp[r + (int64_t)k * ldp]), p2[k]);
+    }
+    const T w0 = mul_(*tau_j, acc);
+    Wp[r + (int64_t)i * ldp] = w0;
+    const T vv = Vp[r + (int64_t)i * ldp];
+    dot[0] = re(w0) * re(vv) + im(w0) * im(vv);
+    dot[1] = re(w0) * im(vv) - im(w0) * re(vv);
+  }
+  blk_sum<2>(dot, sh);
+  if (threadIdx.x == 0) { partial[2 * blockIdx.x] = dot[0]; partial[2 * blockIdx.x + 1] = dot[1]; }
+}
+
+// (4b) w = w0 - 1/2 tau (w0^H v) v
+template <typename T>
+__global__ void __launch_bounds__(256) trd_w2_kernel(const T* __restrict__ Vp, T* __restrict__ Wp, int64_t ldp, int i, int64_t m,
+                                                     const T* __restrict__ tau_j, const double* __restrict__ partial, int nparts) {
+  double sr = 0.0, si = 0.0;
+  for (int k = 0; k < nparts; ++k) { sr += partial[2 * k]; si += partial[2 * k + 1]; }
+  const T alpha = mul_(*tau_j, from_complex<T>(-0.5 * sr, -0.5 * si));
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < m) {
+    T w = Wp[r + (int64_t)i * ldp];
+    fma_(w, alpha, Vp[r + (int64_t)i * ldp]);
+    Wp[r + (int64_t)i * ldp] = w;
+  }
+}
+
+template <typename T>
+__global__ void trd_last_diag_kernel(const T* __restrict__ A, int64_t lda, int64_t n, double* __restrict__ d_out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) d_out[n - 1] = re(A[(n - 1) + (n - 1) * lda]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage 3 helpers: T factor of a reflector block (H_0 ... H_{w-1} = I - V T V^H), real -> T conversion
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) larft_kernel(const T* __restrict__ S /* V^H V, w x w */, int w, const T* __restrict__ tau,
+                                                    T* __restrict__ Tm /* w x w */) {
+  for (int e = threadIdx.x; e < w * w; e += blockDim.x) Tm[e] = zero_<T>();
+  __syncthreads();
+  for (int i = 0; i < w; ++i) {
+    const int r = threadIdx.x;
+    if (r < i) {
+      T acc = zero_<T>();
+      for (int k = r; k < i; ++k) fma_(acc, Tm[r + k * w], S[k + i * w]);
+      Tm[r + i * w] = mul_(neg_(tau[i]), acc);
+    } else if (r == i) {
+      Tm[i + i * w] = tau[i];
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T>
+__global__ void real_to_T_kernel(const double* __restrict__ in, int64_t ldi, T* __restrict__ out, int64_t ldo, int64_t rows,
+                                 int64_t cols) {
+  const int64_t total = rows * cols;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e % rows, c = e / rows;
+    out[r + c * ldo] = from_complex<T>(in[r + c * ldi], 0.0);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage 2: divide & conquer kernels (FP64)
+// ------------------------------------------------------------------------------------------------
+constexpr int LEAF = 128;
+
+__global__ void __launch_bounds__(256) dc_leaf_build_kernel(const double* __restrict__ dmod, const double* __restrict__ e,
+                                                            const int64_t* __restrict__ bounds, double* __restrict__ S) {
+  const int64_t lo = bounds[blockIdx.x], hi = bounds[blockIdx.x + 1];
+  const int s = (int)(hi - lo);
+  double* Sl = S + (size_t)blockIdx.x * LEAF * LEAF;
+  for (int idx = threadIdx.x; idx < LEAF * LEAF; idx += blockDim.x) {
+    const int r = idx % LEAF, c = idx / LEAF;
+    double v = 0.0;
+    if (r < s && c < s) {
+      if (r == c) v = dmod[lo + r];
+      else if (r == c + 1) v = e[lo + c];
+      else if (c == r + 1) v = e[lo + r];
+    }
+    Sl[idx] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) dc_leaf_scatter_kernel(const double* __restrict__ R, const double* __restrict__ ev,
+                                                              const int64_t* __restrict__ bounds, double* __restrict__ Z,
+                                                              int64_t ldz, double* __restrict__ D) {
+  const int64_t lo = bounds[blockIdx.x], hi = bounds[blockIdx.x + 1];
+  const int s = (int)(hi - lo);
+  const double* Rl = R + (size_t)blockIdx.x * LEAF * LEAF;
+  for (int idx = threadIdx.x; idx < s * s; idx += blockDim.x) {
+    const int r = idx % s, c = idx / s;
+    Z[(lo + r) + (lo + c) * ldz] = Rl[r + c * LEAF];
+  }
+  for (int c = threadIdx.x; c < s; c += blockDim.x) D[lo + c] = ev[(size_t)blockIdx.x * LEAF + c];
+}
+
+__global__ void dc_zrows_kernel(const double* __restrict__ Z, int64_t ldz, const int32_t* __restrict__ rowsel,
+                                double* __restrict__ zout, int64_t n) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n) zout[c] = Z[rowsel[c] + c * ldz];
+}
+
+// Givens rotations of the deflation step on the eigenvector columns (each thread owns one row; in order)
+__global__ void __launch_bounds__(256) dc_rot_kernel(double* __restrict__ Zb, int64_t ldz, int64_t N, int nrot,
+                                                     const int32_t* __restrict__ rp, const int32_t* __restrict__ rn,
+                                                     const double* __restrict__ rc, const double* __restrict__ rs) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= N) return;
+  for (int t = 0; t < nrot; ++t) {
+    const int64_t p = rp[t], q = rn[t];
+    const double c = rc[t], s = rs[t];
+    const double x = Zb[r + p * ldz], y = Zb[r + q * ldz];
+    Zb[r + p * ldz] = c * x + s * y;
+    Zb[r + q * ldz] = c * y - s * x;
+  }
+}
+
+// one thread per root: Dt[i + j ldt] = d_j - lambda_i
+__global__ void __launch_bounds__(128) dc_secular_kernel(int K, const double* __restrict__ dl, const double* __restrict__ z2,
+                                                         double rho, double* __restrict__ Dt, int64_t ldt, double* __restrict__ lam) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < K) lam[i] = dc::secular_root(K, i, dl, z2, rho, Dt + i, ldt);
+}
+
+// Gu-Eisenstat: zhat_j = sign(z_j) sqrt( -prod_i (d_j - lam_i) / prod_{i != j} (d_j - d_i) ), one CTA per j
+__global__ void __launch_bounds__(128) dc_zhat_kernel(int K, const double* __restrict__ Dt, int64_t ldt, const double* __restrict__ dl,
+                                                      const double* __restrict__ zz, double* __restrict__ zh) {
+  __shared__ double sh[4];
+  const int j = blockIdx.x;
+  const double dj = dl[j];
+  double pr = 1.0;
+  for (int i = threadIdx.x; i < K; i += blockDim.x) {
+    const double num = Dt[i + (int64_t)j * ldt];
+    pr *= (i == j) ? num : num / (dj - dl[i]);
+  }
+  for (int o = 16; o > 0; o >>= 1) pr *= __shfl_xor_sync(0xffffffffu, pr, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = pr;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double p = 1.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) p *= sh[w];
+    zh[j] = copysign(sqrt(fabs(p)), zz[j]);
+  }
+}
+
+__global__ void __launch_bounds__(128) dc_vecnorm_kernel(int K, const double* __restrict__ Dt, int64_t ldt, const double* __restrict__ zh,
+                                                         double* __restrict__ invn) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K) return;
+  double s = 0.0;
+  for (int j = 0; j < K; ++j) {
+    const double v = zh[j] / Dt[i + (int64_t)j * ldt];
+    s += v * v;
+  }
+  invn[i] = 1.0 / sqrt(s);
+}
+
+__global__ void dc_vecscale_kernel(int K, double* __restrict__ Dt, int64_t ldt, const double* __restrict__ zh,
+                                   const double* __restrict__ invn) {
+  const int64_t total = (int64_t)K * K;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e % K), j = (int)(e / K);
+    const int64_t a = i + (int64_t)j * ldt;
+    Dt[a] = zh[j] / Dt[a] * invn[i];   // Ut[i, j]: component j of eigenvector i
+  }
+}
+
+template <typename V>
+void h2d(Ctx* ctx, void* dst, const std::vector<V>& src, size_t count) {
+  if (count) NSB_CUDA(cudaMemcpyAsync(dst, src.data(), sizeof(V) * count, cudaMemcpyHostToDevice, ctx->stream));
+}
+
+// T = Z diag(D) Z^T for the tridiagonal (d, e); Z (n x n, ld n) on device, D on the host (unsorted).
+void dc_solve(Ctx* ctx, int64_t n, const std::vector<double>& d, const std::vector<double>& e, DevBuf& Zout,
+              std::vector<double>& D, int64_t* nondeflated) {
+  std::vector<int64_t> b = dc::leaf_bounds(n, LEAF);
+  const int nleaf = (int)b.size() - 1;
+  std::vector<double> dmod(d);
+  double tnorm = 0.0;
+  for (int64_t i = 0; i < n; ++i) tnorm = std::max(tnorm, std::fabs(d[i]) + (i > 0 ? std::fabs(e[i - 1]) : 0.0) + (i + 1 < n ? std::fabs(e[i]) : 0.0));
+  for (int k = 1; k < nleaf; ++k) {
+    const int64_t x = b[k];
+    dmod[x - 1] -= std::fabs(e[x - 1]);
+    dmod[x] -= std::fabs(e[x - 1]);
+  }
+  const size_t nn = (size_t)n * n;
+  DevBuf Z1(ctx, sizeof(double) * nn), Z2(ctx, sizeof(double) * nn);
+  DevBuf dmod_d(ctx, sizeof(double) * n), e_d(ctx, sizeof(double) * std::max<int64_t>(n, 1)), b_d(ctx, sizeof(int64_t) * b.size());
+  DevBuf D_d(ctx, sizeof(double) * n);
+  D.assign(n, 0.0);
+  {
+    DevBuf S(ctx, sizeof(double) * (size_t)nleaf * LEAF * LEAF), R(ctx, sizeof(double) * (size_t)nleaf * LEAF * LEAF),
+        ev(ctx, sizeof(double) * (size_t)nleaf * LEAF);
+    h2d(ctx, dmod_d.ptr, dmod, n);
+    h2d(ctx, e_d.ptr, e, e.size());
+    h2d(ctx, b_d.ptr, b, b.size());
+    dc_leaf_build_kernel<<<nleaf, 256, 0, ctx->stream>>>((const double*)dmod_d.ptr, (const double*)e_d.ptr, (const int64_t*)b_d.ptr, (double*)S.ptr);
+    LAUNCH_CHECK(ctx);
+    herm_eig_batch128(ctx, (const double*)S.ptr, (double*)R.ptr, (double*)ev.ptr, nleaf, 0.0, 40);
+    NSB_CUDA(cudaMemsetAsync(Z1.ptr, 0, sizeof(double) * nn, ctx->stream));
+    NSB_CUDA(cudaMemsetAsync(Z2.ptr, 0, sizeof(double) * nn, ctx->stream));
+    dc_leaf_scatter_kernel<<<nleaf, 256, 0, ctx->stream>>>((const double*)R.ptr, (const double*)ev.ptr, (const int64_t*)b_d.ptr, (double*)Z1.ptr, n,
+                                                         (double*)D_d.ptr);
+    LAUNCH_CHECK(ctx);
+    NSB_CUDA(cudaMemcpyAsync(D.data(), D_d.ptr, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->sync();
+  }
+  const bool dbg = eigh_debug();
+  double tl = dbg ? now_s() : 0.0;
+  if (dbg) fprintf(stderr, "[eigh/dc] %d leaves solved\n", nleaf);
+  if (nondeflated) *nondeflated = 0;
+  if (nleaf > 1) {
+    DevBuf Dt(ctx, sizeof(double) * nn), Zg(ctx, sizeof(double) * nn);
+    DevBuf z_d(ctx, sizeof(double) * n), lam_d(ctx, sizeof(double) * n), dl_d(ctx, sizeof(double) * n), z2_d(ctx, sizeof(double) * n),
+        zz_d(ctx, sizeof(double) * n), zh_d(ctx, sizeof(double) * n), invn_d(ctx, sizeof(double) * n), rc_d(ctx, sizeof(double) * n),
+        rs_d(ctx, sizeof(double) * n);
+    DevBuf rowsel_d(ctx, sizeof(int32_t) * n), nd_d(ctx, sizeof(int32_t) * n), df_d(ctx, sizeof(int32_t) * n), rp_d(ctx, sizeof(int32_t) * n),
+        rn_d(ctx, sizeof(int32_t) * n);
+    std::vector<double> z(n), lam(n), h_dl(n), h_z2(n), h_zz(n), h_rc(n), h_rs(n);
+    std::vector<int32_t> rowsel(n), h_nd(n), h_df(n), h_rp(n), h_rn(n);
+    struct MInfo { int64_t lo, hi; int K, ndf, nrot; double rho; std::vector<double> Ddf; };
+    double* Zc = (double*)Z1.ptr;
+    double* Zn = (double*)Z2.ptr;
+    dc::MergePlan mp;
+    const double isq = 1.0 / std::sqrt(2.0);
+    while (b.size() > 2) {
+      const size_t nm = (b.size() - 1) / 2;
+      for (size_t k = 0; k < nm; ++k) {
+        const int64_t lo = b[2 * k], mid = b[2 * k + 1], hi = b[2 * k + 2];
+        for (int64_t c = lo; c < mid; ++c) rowsel[c] = (int32_t)(mid - 1);
+        for (int64_t c = mid; c < hi; ++c) rowsel[c] = (int32_t)mid;
+      }
+      h2d(ctx, rowsel_d.ptr, rowsel, n);
+      dc_zrows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(Zc, n, (const int32_t*)rowsel_d.ptr, (double*)z_d.ptr, n);
+      LAUNCH_CHECK(ctx);
+      NSB_CUDA(cudaMemcpyAsync(z.data(), z_d.ptr, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+      ctx->sync();
+      std::vector<MInfo> ms(nm);
+      for (size_t k = 0; k < nm; ++k) {
+        const int64_t lo = b[2 * k], mid = b[2 * k + 1], hi = b[2 * k + 2], N = hi - lo;
+        const double beta = e[mid - 1], sgn = beta < 0.0 ? -1.0 : 1.0;
+        MInfo& m = ms[k];
+        m.lo = lo; m.hi = hi; m.rho = 2.0 * std::fabs(beta);
+        for (int64_t c = lo; c < mid; ++c) z[c] *= isq;
+        for (int64_t c = mid; c < hi; ++c) z[c] *= sgn * isq;
+        dc::plan_merge(D.data() + lo, z.data() + lo, N, m.rho, mp);
+        m.K = (int)mp.nd.size(); m.ndf = (int)mp.df.size(); m.nrot = (int)mp.rot_p.size();
+        for (int t = 0; t < m.K; ++t) {
+          const int32_t j = mp.nd[t];
+          h_nd[lo + t] = j; h_dl[lo + t] = mp.D[j]; h_zz[lo + t] = mp.z[j]; h_z2[lo + t] = mp.z[j] * mp.z[j];
+        }
+        m.Ddf.resize(m.ndf);
+        for (int t = 0; t < m.ndf; ++t) { h_df[lo + t] = mp.df[t]; m.Ddf[t] = mp.D[mp.df[t]]; }
+        for (int t = 0; t < m.nrot; ++t) { h_rp[lo + t] = mp.rot_p[t]; h_rn[lo + t] = mp.rot_n[t]; h_rc[lo + t] = mp.rot_c[t]; h_rs[lo + t] = mp.rot_s[t]; }
+        if (nondeflated) *nondeflated += m.K;
+      }
+      h2d(ctx, nd_d.ptr, h_nd, n); h2d(ctx, df_d.ptr, h_df, n); h2d(ctx, dl_d.ptr, h_dl, n); h2d(ctx, zz_d.ptr, h_zz, n);
+      h2d(ctx, z2_d.ptr, h_z2, n); h2d(ctx, rp_d.ptr, h_rp, n); h2d(ctx, rn_d.ptr, h_rn, n); h2d(ctx, rc_d.ptr, h_rc, n);
+      h2d(ctx, rs_d.ptr, h_rs, n);
+      for (size_t k = 0; k < nm; ++k) {
+        const MInfo& m = ms[k];
+        const int64_t lo = m.lo, N = m.hi - m.lo, off = lo + lo * n;
+        const int K = m.K;
+        double* Zb = Zc + off;
+        double* Znb = Zn + off;
+        if (m.nrot > 0) {
+          dc_rot_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(Zb, n, N, m.nrot, (const int32_t*)rp_d.ptr + lo, (const int32_t*)rn_d.ptr + lo,
+                                                                              (const double*)rc_d.ptr + lo, (const double*)rs_d.ptr + lo);
+          LAUNCH_CHECK(ctx);
+        }
+        if (m.ndf > 0) gather_cols<double>(ctx, Zb, n, N, (const int32_t*)df_d.ptr + lo, m.ndf, nullptr, Znb + (int64_t)K * n, n);
+        if (K > 0) {
+          double* Dtb = (double*)Dt.ptr + off;
+          double* Zgb = (double*)Zg.ptr + off;
+          const double* dl = (const double*)dl_d.ptr + lo;
+          gather_cols<double>(ctx, Zb, n, N, (const int32_t*)nd_d.ptr + lo, K, nullptr, Zgb, n);
+          dc_secular_kernel<<<(K + 127) / 128, 128, 0, ctx->stream>>>(K, dl, (const double*)z2_d.ptr + lo, m.rho, Dtb, n, (double*)lam_d.ptr + lo);
+          LAUNCH_CHECK(ctx);
+          dc_zhat_kernel<<<K, 128, 0, ctx->stream>>>(K, Dtb, n, dl, (const double*)zz_d.ptr + lo, (double*)zh_d.ptr + lo);
+          LAUNCH_CHECK(ctx);
+          dc_vecnorm_kernel<<<(K + 127) / 128, 128, 0, ctx->stream>>>(K, Dtb, n, (const double*)zh_d.ptr + lo, (double*)invn_d.ptr + lo);
+          LAUNCH_CHECK(ctx);
+          const int grid = (int)std::min<int64_t>(((int64_t)K * K + 255) / 256, (int64_t)ctx->num_sms * 8);
+          dc_vecscale_kernel<<<grid, 256, 0, ctx->stream>>>(K, Dtb, n, (const double*)zh_d.ptr + lo, (const double*)invn_d.ptr + lo);
+          LAUNCH_CHECK(ctx);
+          gemm<double>(ctx, OP_N, OP_T, N, K, K, 1.0, Zgb, n, 0, Dtb, n, 0, 0.0, Znb, n, 0, 1);
+        }
+      }
+      NSB_CUDA(cudaMemcpyAsync(lam.data(), lam_d.ptr, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+      ctx->sync();
+      std::vector<int64_t> nbnd;
+      nbnd.push_back(b[0]);
+      for (size_t k = 0; k < nm; ++k) {
+        const MInfo& m = ms[k];
+        for (int t = 0; t < m.K; ++t) D[m.lo + t] = lam[m.lo + t];
+        for (int t = 0; t < m.ndf; ++t) D[m.lo + m.K + t] = m.Ddf[t];
+        nbnd.push_back(m.hi);
+      }
+      b.swap(nbnd);
+      std::swap(Zc, Zn);
+      if (dbg) {
+        int64_t ksum = 0, rsum = 0;
+        for (const MInfo& m : ms) { ksum += m.K; rsum += m.nrot; }
+        fprintf(stderr, "[eigh/dc] level with %zu merges: %.1f ms, non-deflated %ld of %ld, rotations %ld\n", nm, (now_s() - tl) * 1e3,
+                (long)ksum, (long)n, (long)rsum);
+        tl = now_s();
+      }
+    }
+    if (Zc == (double*)Z2.ptr) std::swap(Z1, Z2);
+  }
+  (void)tnorm;
+  Zout = std::move(Z1);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// driver
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+void Eigh<T>::factor(Ctx* c, T* A, int64_t n_, int64_t lda) {
+  ctx = c;
+  n = n_;
+  NSB_REQUIRE(n >= 1, NSB_EINVAL, "eigh: empty matrix");
+  const int nb = std::max(2, std::min(g_eigh_nb, MAXNB)) & ~1;
+  const T one = from_complex<T>(1.0, 0.0), mone = from_complex<T>(-1.0, 0.0);
+  Vall = DevBuf(ctx, sizeof(T) * (size_t)n * n);
+  taus = DevBuf(ctx, sizeof(T) * n);
+  NSB_CUDA(cudaMemsetAsync(Vall.ptr, 0, sizeof(T) * (size_t)n * n, ctx->stream));
+  NSB_CUDA(cudaMemsetAsync(taus.ptr, 0, sizeof(T) * n, ctx->stream));
+  DevBuf d_d(ctx, sizeof(double) * n), e_d(ctx, sizeof(double) * n);
+  NSB_CUDA(cudaMemsetAsync(e_d.ptr, 0, sizeof(double) * n, ctx->stream));
+  DevBuf Wb(ctx, sizeof(T) * (size_t)n * nb), yb(ctx, sizeof(T) * (n + 2 * nb));
+  const int maxparts = (int)((n + 255) / 256) + 1;
+  DevBuf part(ctx, sizeof(double) * 2 * maxparts);
+  T* Vp0 = (T*)Vall.ptr;
+  T* Wp = (T*)Wb.ptr;
+  T* dtau = (T*)taus.ptr;
+  const int64_t nref = n - 1;
+  constexpr int CPB = 4;
+  const bool dbg = eigh_debug();
+  double t0 = 0.0;
+  if (dbg) { ctx->sync(); t0 = now_s(); }
+  for (int64_t p = 0; p < nref; p += nb) {
+    const int w = (int)std::min<int64_t>(nb, nref - p);
+    T* Vp = Vp0 + p * n;   // panel columns p .. p + w - 1 of Vall (ld n)
+    for (int i = 0; i < w; ++i) {
+      const int64_t j = p + i, m = n - j - 1;
+      trd_col_update_kernel<T><<<(unsigned)((n - j + 255) / 256), 256, 0, ctx->stream>>>(A, lda, n, j, Vp, Wp, n, i, (double*)d_d.ptr);
+      LAUNCH_CHECK(ctx);
+      trd_house_kernel<T><<<1, 256, 0, ctx->stream>>>(A, lda, n, j, Vp + (int64_t)i * n, dtau, (double*)e_d.ptr);
+      LAUNCH_CHECK(ctx);
+      const int64_t ncol = m + 2 * (int64_t)i;
+      trd_gemv_kernel<T, CPB><<<(unsigned)((ncol + CPB - 1) / CPB), 256, 0, ctx->stream>>>(
+          A + (j + 1) + (j + 1) * lda, lda, m, Wp + (j + 1), Vp + (j + 1), n, i, Vp + (int64_t)i * n + (j + 1), (T*)yb.ptr);
+      LAUNCH_CHECK(ctx);
+      const int nparts = (int)((m + 255) / 256);
+      trd_w1_kernel<T><<<nparts, 256, 0, ctx->stream>>>((const T*)yb.ptr, Vp + (j + 1), Wp + (j + 1), n, i, m, dtau + j, (double*)part.ptr);
+      LAUNCH_CHECK(ctx);
+      trd_w2_kernel<T><<<nparts, 256, 0, ctx->stream>>>(Vp + (j + 1), Wp + (j + 1), n, i, m, dtau + j, (const double*)part.ptr, nparts);
+      LAUNCH_CHECK(ctx);
+    }
+    const int64_t q = p + w, mt = n - q;
+    if (mt > 0) {   // A_trail -= V W^H + W V^H (full square: both triangles stay valid for the column dot products)
+      gemm<T>(ctx, OP_N, OP_C, mt, mt, w, mone, Vp + q, n, 0, Wp + q, n, 0, one, A + q + q * lda, lda, 0, 1);
+      gemm<T>(ctx, OP_N, OP_C, mt, mt, w, mone, Wp + q, n, 0, Vp + q, n, 0, one, A + q + q * lda, lda, 0, 1);
+    }
+  }
+  trd_last_diag_kernel<T><<<1, 32, 0, ctx->stream>>>(A, lda, n, (double*)d_d.ptr);
+  LAUNCH_CHECK(ctx);
+  std::vector<double> d(n), e(std::max<int64_t>(n - 1, 0));
+  NSB_CUDA(cudaMemcpyAsync(d.data(), d_d.ptr, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (n > 1) NSB_CUDA(cudaMemcpyAsync(e.data(), e_d.ptr, sizeof(double) * (n - 1), cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->sync();
+  Wb.release(); yb.release();
+  const double t1 = dbg ? now_s() : 0.0;
+  dc_solve(ctx, n, d, e, Z, w, &dc_nondeflated);
+  if (dbg) {
+    ctx->sync();
+    fprintf(stderr, "[eigh] n=%ld nb=%d tridiagonalise %.1f ms, divide&conquer %.1f ms (non-deflated %ld)\n", (long)n, nb,
+            (t1 - t0) * 1e3, (now_s() - t1) * 1e3, (long)dc_nondeflated);
+  }
+}
+
+template <typename T>
+void Eigh<T>::vectors(const int32_t* idx_host, int64_t k, T* U, int64_t ldu) {
+  if (k <= 0) return;
+  const int nb = std::max(2, std::min(g_eigh_nb, MAXNB)) & ~1;
+  const T one = from_complex<T>(1.0, 0.0), mone = from_complex<T>(-1.0, 0.0), zero = zero_<T>();
+  DevBuf idx(ctx, sizeof(int32_t) * k);
+  NSB_CUDA(cudaMemcpyAsync(idx.ptr, idx_host, sizeof(int32_t) * k, cudaMemcpyHostToDevice, ctx->stream));
+  if (ScalarTraits<T>::is_complex) {
+    DevBuf Zs(ctx, sizeof(double) * (size_t)n * k);
+    gather_cols<double>(ctx, (const double*)Z.ptr, n, n, (const int32_t*)idx.ptr, k, nullptr, (double*)Zs.ptr, n);
+    const int grid = (int)std::min<int64_t>((n * k + 255) / 256, (int64_t)ctx->num_sms * 8);
+    real_to_T_kernel<T><<<grid, 256, 0, ctx->stream>>>((const double*)Zs.ptr, n, U, ldu, n, k);
+    LAUNCH_CHECK(ctx);
+    ctx->sync();   // Zs is released at scope exit (stream-ordered free would also do; keep it simple)
+  } else {
+    gather_cols<double>(ctx, (const double*)Z.ptr, n, n, (const int32_t*)idx.ptr, k, nullptr, reinterpret_cast<double*>(U), ldu);
+  }
+  const int64_t nref = n - 1;
+  if (nref <= 0) { ctx->sync(); return; }
+  DevBuf S(ctx, sizeof(T) * nb * nb), Tm(ctx, sizeof(T) * nb * nb), Y(ctx, sizeof(T) * (size_t)nb * k), Y2(ctx, sizeof(T) * (size_t)nb * k);
+  const T* Vp0 = (const T*)Vall.ptr;
+  const T* dtau = (const T*)taus.ptr;
+  const int64_t last = ((nref - 1) / nb) * nb;
+  const bool dbg = eigh_debug();
+  double t0 = 0.0;
+  if (dbg) { ctx->sync(); t0 = now_s(); }
+  for (int64_t p = last; p >= 0; p -= nb) {
+    const int w = (int)std::min<int64_t>(nb, nref - p);
+    const T* Vp = Vp0 + p * n + p;   // rows p.. (row p of this panel is zero: harmless, keeps the operands 16-byte aligned)
+    const int64_t mp = n - p;
+    gemm<T>(ctx, OP_C, OP_N, w, w, mp, one, Vp, n, 0, Vp, n, 0, zero, (T*)S.ptr, w, 0, 1);
+    larft_kernel<T><<<1, 128, 0, ctx->stream>>>((const T*)S.ptr, w, dtau + p, (T*)Tm.ptr);
+    LAUNCH_CHECK(ctx);
+    gemm<T>(ctx, OP_C, OP_N, w, k, mp, one, Vp, n, 0, U + p, ldu, 0, zero, (T*)Y.ptr, w, 0, 1);
+    gemm<T>(ctx, OP_N, OP_N, w, k, w, one, (const T*)Tm.ptr, w, 0, (const T*)Y.ptr, w, 0, zero, (T*)Y2.ptr, w, 0, 1);
+    gemm<T>(ctx, OP_N, OP_N, mp, k, w, mone, Vp, n, 0, (const T*)Y2.ptr, w, 0, one, U + p, ldu, 0, 1);
+  }
+  ctx->sync();
+  if (dbg) fprintf(stderr, "[eigh] n=%ld k=%ld back-transformation %.1f ms\n", (long)n, (long)k, (now_s() - t0) * 1e3);
+}
+
+template struct Eigh<double>;
+template struct Eigh<cdouble>;
+
+}  // namespace nsb

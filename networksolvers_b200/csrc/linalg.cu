@@ -2,6 +2,7 @@
 #include "linalg.h"
 #include "ops.h"
 #include "gemm.h"
+#include "eigh.h"
 
 #include <algorithm>
 #include <cmath>
@@ -364,7 +365,10 @@ template <> __device__ __forceinline__ cdouble cmul_conj_a<cdouble>(cdouble a, c
 template <typename T, int N2>
 __global__ void __launch_bounds__(1024) herm_eig_kernel(const T* __restrict__ Sg, T* __restrict__ Rg,
                                                         unsigned long long* __restrict__ maxoff, double abs_floor,
-                                                        double outer_tol, int inner_cap) {
+                                                        double outer_tol, int inner_cap, double* __restrict__ evals = nullptr,
+                                                        int force = 0) {
+  // evals (optional): N2 diagonal entries of the rotated matrix per problem (eigenvalue i <-> column i of R).
+  // force: always run the inner sweeps (stand-alone eigensolver use: no outer iteration finishes the job).
   // abs_floor = eps * (largest diagonal entry of the global Gram matrix): couplings below it cannot change any
   // sigma^2 by more than LAPACK-level absolute accuracy and are treated as converged.
   constexpr int NP = N2 / 2, RING = N2 - 1, TRI = N2 * (N2 + 1) / 2;
@@ -412,13 +416,26 @@ __global__ void __launch_bounds__(1024) herm_eig_kernel(const T* __restrict__ Sg
       red[32] = m;
     }
     __syncthreads();
-    if (red[32] <= outer_tol) {   // this pair is already orthogonal to the outer tolerance: R = I exactly
+    if (!force && red[32] <= outer_tol) {   // this pair is already orthogonal to the outer tolerance: R = I exactly
       T* Ro = Rg + (size_t)blockIdx.x * N2 * N2;
       for (int e = tid; e < N2 * N2; e += nth) Ro[e] = R[e];
       return;
     }
   }
   const double tol = 2.220446049250313e-16 * (N2 / 2);   // rounding noise of the updated couplings is O(eps sqrt(N2))
+  double afl = abs_floor;
+  if (force) {   // stand-alone use: absolute floor from this problem's own scale, eps * max |S_ij|
+    double v = 0.0;
+    for (int e = tid; e < TRI; e += nth) v = fmax(v, sqrt(abs2_(tri[e])));
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    double m = 0.0;
+    for (int w = 0; w < (nth + 31) / 32; ++w) m = fmax(m, red[w]);
+    afl = fmax(afl, 2.220446049250313e-16 * m);
+    __syncthreads();
+  }
   for (int sweep = 0; sweep < inner_cap; ++sweep) {
     if (tid == 0) { smax = 0ull; atomicAdd(maxoff + 1, 1ull); }
     __syncthreads();
@@ -434,7 +451,7 @@ __global__ void __launch_bounds__(1024) herm_eig_kernel(const T* __restrict__ Sg
         T g = get(p, q);
         const double g2 = abs2_(g), ab = fabs(alpha * beta);
         T j11 = from_complex<T>(1.0, 0.0), j12 = zero_<T>(), j21 = zero_<T>(), j22 = from_complex<T>(1.0, 0.0);
-        if (g2 > abs_floor * abs_floor && g2 > tol * tol * ab) {
+        if (g2 > afl * afl && g2 > tol * tol * ab) {
           // squared relative coupling for the sweep-level convergence test (no sqrt / divide on the critical path)
           atomicMax(&smax, (unsigned long long)__double_as_longlong(ab > 0.0 ? g2 / ab : 1.0));
           const double gabs = sqrt(g2), ginv = 1.0 / gabs;
@@ -486,6 +503,22 @@ __global__ void __launch_bounds__(1024) herm_eig_kernel(const T* __restrict__ Sg
   }
   T* Ro = Rg + (size_t)blockIdx.x * N2 * N2;
   for (int e = tid; e < N2 * N2; e += nth) Ro[e] = R[e];
+  if (evals) for (int i = tid; i < N2; i += nth) evals[(size_t)blockIdx.x * N2 + i] = re(tri[tix(i, i)]);
+}
+
+// Batched dense symmetric eigensolver for 128 x 128 problems (leaves of the divide & conquer in eigh.cu):
+// S, R: batch x 128 x 128 column-major; evals: batch x 128.  Eigenvalue i belongs to column i of R (unsorted).
+void herm_eig_batch128(Ctx* ctx, const double* S, double* R, double* evals, int batch, double abs_floor, int max_sweeps) {
+  if (batch <= 0) return;
+  constexpr int N2 = 128;
+  auto kern = herm_eig_kernel<double, N2>;
+  size_t smem = sizeof(double) * ((size_t)N2 * (N2 + 1) / 2 + (size_t)N2 * N2 + 4 * (N2 / 2));
+  static bool configured = false;
+  if (!configured) { NSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = true; }
+  unsigned long long* dmax = reinterpret_cast<unsigned long long*>(ctx->d_scratch);
+  NSB_CUDA(cudaMemsetAsync(dmax, 0, 2 * sizeof(unsigned long long), ctx->stream));
+  kern<<<(unsigned)batch, 1024, smem, ctx->stream>>>(S, R, dmax, abs_floor, 1e-300, max_sweeps, evals, 1);
+  LAUNCH_CHECK(ctx);
 }
 
 template <typename T>
@@ -559,7 +592,7 @@ static int jacobi_blocked(Ctx* ctx, T* G, int64_t m, int64_t n, T* V, int64_t nv
     NSB_CUDA(cudaMemsetAsync(dmax, 0, 2 * sizeof(unsigned long long), ctx->stream));
     for (int64_t r = 0; r < rounds; ++r) {
       gemm<T>(ctx, OP_C, OP_N, N2, N2, m, one, ga, m, m * N2, ga, m, m * N2, zero, (T*)Sb.ptr, N2, (int64_t)N2 * N2, npairs);
-      kern<<<(unsigned)npairs, 1024, smem, ctx->stream>>>((const T*)Sb.ptr, (T*)Rb.ptr, dmax, abs_floor, tol, g_jacobi_inner_cap);
+      kern<<<(unsigned)npairs, 1024, smem, ctx->stream>>>((const T*)Sb.ptr, (T*)Rb.ptr, dmax, abs_floor, tol, g_jacobi_inner_cap, nullptr, 0);
       LAUNCH_CHECK(ctx);
       gemm<T>(ctx, OP_N, OP_N, m, N2, N2, one, ga, m, m * N2, (const T*)Rb.ptr, N2, (int64_t)N2 * N2, zero, gb, m, m * N2, npairs);
       gemm<T>(ctx, OP_N, OP_N, nv, N2, N2, one, va, nv, nv * N2, (const T*)Rb.ptr, N2, (int64_t)N2 * N2, zero, vb, nv, nv * N2, npairs);
@@ -595,10 +628,62 @@ static int jacobi_blocked(Ctx* ctx, T* G, int64_t m, int64_t n, T* V, int64_t nv
   return sweep;
 }
 
+// Large matrices (rows <= cols, rows >= g_eigh_min_n): the reference's `eigen` route (App. A.4) -- rho = M M^H by
+// one GEMM, Hermitian eigen-decomposition (tridiagonalisation + divide & conquer, eigh.cu), truncation rule on the
+// eigenvalues, back-transformation of the kept eigenvectors only, C = U^H M by one GEMM.
+template <typename T>
+static FactorInfo factorize_left_eigh(Ctx* ctx, const T* M, int64_t rows, int64_t cols, int64_t ld, bool trans_in, double cutoff,
+                                      int64_t mindim, int64_t maxdim, bool sqrt_spectrum, DevBuf& U, DevBuf& C,
+                                      std::vector<double>& spectrum) {
+  FactorInfo info;
+  info.decomp = (cutoff <= 1e-12) ? 1 : 2;
+  const int64_t n = rows;
+  const T one = from_complex<T>(1.0, 0.0), zero = zero_<T>();
+  // sqrt_spectrum with a square input: M is itself the Hermitian PSD density matrix of `eigen(rho; ...)`
+  // (src/subspace/densitymatrix.jl:53): decompose it directly, its eigenvalues are the spectrum
+  const bool direct = sqrt_spectrum && rows == cols;
+  Eigh<T> eg;
+  {
+    DevBuf rho(ctx, sizeof(T) * (size_t)n * n);
+    if (direct) {
+      if (!trans_in) copy_block<T>(ctx, M, ld, (T*)rho.ptr, n, n, n);
+      else transpose_conj<T>(ctx, M, cols, rows, ld, (T*)rho.ptr, n, false);
+    } else if (!trans_in) {
+      gemm<T>(ctx, OP_N, OP_C, n, n, cols, one, M, ld, 0, M, ld, 0, zero, (T*)rho.ptr, n, 0, 1);
+    } else {   // logical M(r, c) = buf[c + r ld]:  rho = buf^T conj(buf)
+      gemm<T>(ctx, OP_T, OP_CONJ, n, n, cols, one, M, ld, 0, M, ld, 0, zero, (T*)rho.ptr, n, 0, 1);
+    }
+    eg.factor(ctx, (T*)rho.ptr, n, n);
+  }
+  std::vector<int32_t> order(n);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return eg.w[a] > eg.w[b]; });
+  spectrum.resize(n);
+  for (int64_t i = 0; i < n; ++i) {
+    const double lam = eg.w[order[i]];
+    spectrum[i] = (sqrt_spectrum && !direct) ? std::sqrt(std::max(lam, 0.0)) : lam;
+  }
+  double terr = 0.0;
+  const int64_t nkeep = truncate_spectrum(spectrum, cutoff, mindim, maxdim, &terr);
+  for (double& x : spectrum) x = std::max(x, 0.0);
+  info.newdim = nkeep;
+  info.truncerr = terr;
+  U = DevBuf(ctx, sizeof(T) * rows * nkeep);
+  C = DevBuf(ctx, sizeof(T) * nkeep * cols);
+  eg.vectors(order.data(), nkeep, (T*)U.ptr, rows);
+  gemm<T>(ctx, OP_C, trans_in ? OP_T : OP_N, nkeep, cols, rows, one, (const T*)U.ptr, rows, 0, M, ld, 0, zero, (T*)C.ptr, nkeep, 0, 1);
+  ctx->sync();
+  return info;
+}
+
 template <typename T>
 FactorInfo factorize_left(Ctx* ctx, const T* M, int64_t rows, int64_t cols, int64_t ld, bool trans_in, double cutoff,
                           int64_t mindim, int64_t maxdim, bool sqrt_spectrum, DevBuf& U, DevBuf& C,
                           std::vector<double>& spectrum) {
+  if (g_eigh_min_n > 0 && rows <= cols && rows >= g_eigh_min_n) {
+    ctx->cnt.svd_calls++;
+    return factorize_left_eigh<T>(ctx, M, rows, cols, ld, trans_in, cutoff, mindim, std::min<int64_t>(maxdim, rows), sqrt_spectrum, U, C, spectrum);
+  }
   FactorInfo info;
   ctx->cnt.svd_calls++;
   const int64_t k = std::min(rows, cols);

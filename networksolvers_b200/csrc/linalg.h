@@ -13,6 +13,9 @@ int64_t truncate_spectrum(const std::vector<double>& P, double cutoff, int64_t m
 template <typename T>
 void qr_thin(Ctx* ctx, T* A, int64_t rows, int64_t cols, int64_t lda, T* Q, int64_t ldq, T* R, int64_t ldr);
 
+// Batched 128 x 128 dense symmetric eigensolver (two-sided Jacobi inside one CTA); eigenvalue i <-> column i of R.
+void herm_eig_batch128(Ctx* ctx, const double* S, double* R, double* evals, int batch, double abs_floor, int max_sweeps);
+
 extern int g_jacobi_precondition;  // 1: QR-precondition the blocked Jacobi (Drmac-Veselic)
 extern int g_jacobi_pivot;
 extern int g_jacobi_inner_cap;

@@ -125,6 +125,18 @@ class Context:
         Co = Cm[: nk * cols].reshape((nk, cols), order="F")
         return Uo, Co, spec, dict(newdim=nk, truncerr=info.truncerr, decomp=info.decomp, sweeps=info.jacobi_sweeps)
 
+    def eigh(self, A, vectors=True):
+        """Hermitian eigen-decomposition on the device (tridiagonalisation + divide & conquer): w ascending, U."""
+        cplx = np.iscomplexobj(A)
+        dt = np.complex128 if cplx else np.float64
+        Af = np.asfortranarray(A, dtype=dt)
+        n = Af.shape[0]
+        w = np.empty(n)
+        U = np.empty((n, n), dtype=dt, order="F") if vectors else None
+        self.check(self._lib.nsb_eigh_host(self.handle, self._dt(Af), n, Af.ctypes.data, w.ctypes.data_as(C.POINTER(C.c_double)),
+                                            U.ctypes.data if vectors else None))
+        return (w, U) if vectors else w
+
     def qr(self, M):
         cplx = np.iscomplexobj(M)
         dt = np.complex128 if cplx else np.float64

@@ -1,0 +1,146 @@
+"""GPU parity of the device Hermitian eigensolver (csrc/eigh.cu: blocked tridiagonalisation + divide & conquer +
+WY back-transformation) and of the Gram + eigh route of the truncating factorisation, against NumPy/LAPACK and the
+oracle's truncation rule, called through the C ABI (nsb_eigh_host / nsb_factorize_host / the DMRG hooks)."""
+import numpy as np
+import pytest
+
+from helpers import SweepRecorder, neel, to_oracle_ttn
+
+pytestmark = pytest.mark.gpu
+EPS = np.finfo(float).eps
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import networksolvers_b200 as ns
+    return ns.default_context()
+
+
+@pytest.fixture
+def eigh_route(ctx):
+    """Force the Gram + eigh route for every matrix size, restore the default afterwards."""
+    ctx.set_option("eigh_min_n", 2)
+    yield ctx
+    ctx.set_option("eigh_min_n", 1024)
+    ctx.set_option("eigh_nb", 64)
+
+
+def _cases(n, rng):
+    M = rng.standard_normal((n, n))
+    yield "gauss", M + M.T
+    G = rng.standard_normal((n, 2 * n))
+    yield "wishart", G @ G.T
+    Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    yield "graded", (Q * np.exp(-40.0 * np.arange(n) / n)) @ Q.T
+    yield "lowrank", (Q[:, :3] * np.array([1.0, 0.5, 1e-3])) @ Q[:, :3].T
+    yield "identity+rank1", np.eye(n) + 1e-3 * np.outer(Q[:, 0], Q[:, 0])
+    cl = np.repeat(np.arange(1, n // 8 + 2), 8)[:n].astype(float)
+    yield "clustered", (Q * cl) @ Q.T
+    Mc = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    yield "complex", Mc + Mc.conj().T
+    Gc = rng.standard_normal((n, n + 3)) + 1j * rng.standard_normal((n, n + 3))
+    yield "complex gram", Gc @ Gc.conj().T
+
+
+@pytest.mark.parametrize("n,nb", [(1, 64), (2, 64), (5, 64), (64, 64), (129, 64), (300, 32), (700, 64), (1100, 128)])
+def test_eigh_matches_lapack(ctx, n, nb):
+    rng = np.random.default_rng(n)
+    ctx.set_option("eigh_nb", nb)
+    try:
+        for name, A in _cases(n, rng):
+            w, U = ctx.eigh(A)
+            nrm = max(np.linalg.norm(A, 2), 1e-300)
+            res = np.linalg.norm(A @ U - U * w[None, :]) / (nrm * n)
+            orth = np.linalg.norm(U.conj().T @ U - np.eye(n)) / n
+            err = np.abs(w - np.linalg.eigvalsh(A)).max() / nrm
+            assert res < 30 * EPS and orth < 30 * EPS and err < 100 * EPS, (name, n, res, orth, err)
+    finally:
+        ctx.set_option("eigh_nb", 64)
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("shape", [(8, 8), (20, 33), (33, 20), (96, 96), (200, 333), (260, 200), (640, 640)])
+def test_factorize_eigh_route_full_spectrum(eigh_route, cplx, shape):
+    """Eigen route, no truncation: spectrum = sigma^2 of LAPACK (absolute accuracy eps sigma_1^2), U orthonormal,
+    U C = M."""
+    rng = np.random.default_rng(23)
+    M = rng.standard_normal(shape) + (1j * rng.standard_normal(shape) if cplx else 0.0)
+    U, Cm, spec, info = eigh_route.factorize(M, cutoff=0.0)
+    s = np.linalg.svd(M, compute_uv=False)
+    k = min(shape)
+    assert info["newdim"] == k
+    assert np.abs(spec - s**2).max() <= 1e-12 * s[0] ** 2
+    assert np.abs(U.conj().T @ U - np.eye(k)).max() < 1e-12
+    assert np.abs(U @ Cm - M).max() < 1e-11 * max(1.0, s[0])
+
+
+@pytest.mark.parametrize("cutoff,maxdim", [(1e-12, None), (1e-8, None), (1e-4, None), (0.0, 10), (1e-6, 7)])
+def test_factorize_eigh_route_truncation_rule(eigh_route, cutoff, maxdim):
+    """Truncation rule (NDTensors truncate!) vs the oracle on a decaying spectrum."""
+    from oracle.tensor import truncate_spectrum
+    rng = np.random.default_rng(17)
+    n = 160
+    Uo, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    Vo, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    sig = np.exp(-0.2 * np.arange(n))
+    M = (Uo * sig) @ Vo.T
+    U, Cm, spec, info = eigh_route.factorize(M, cutoff=cutoff, maxdim=maxdim)
+    nk, terr = truncate_spectrum(np.maximum(np.linalg.eigvalsh(M @ M.T)[::-1], 0.0), cutoff=cutoff, mindim=1, maxdim=maxdim)
+    assert info["newdim"] == nk
+    assert abs(info["truncerr"] - terr) <= 1e-8 * max(terr, 1e-30) + 1e-15
+    best = (Uo[:, :nk] * sig[:nk]) @ Vo[:, :nk].T
+    assert np.abs(U @ Cm - best).max() < 1e-7 * max(sig[nk - 1], 1e-8) + 1e-10
+
+
+def _oracle_sweeps(H, psi0, **kw):
+    from oracle.sweep import dmrg
+    rec = {"E": [], "maxdim": [], "terr": []}
+
+    def sweep_cb(problem=None, sweep=None, **_):
+        rec["E"].append(problem.eigenvalue)
+        rec["maxdim"].append(problem.state.maxlinkdim())
+
+    def region_cb(problem=None, **_):
+        rec["terr"].append(problem.last_truncerr)
+
+    E, psi = dmrg(H, psi0, sweep_callback=sweep_cb, region_callback=region_cb, **kw)
+    return E, psi, rec
+
+
+@pytest.mark.parametrize("cutoff", [1e-12, 1e-9])
+def test_dmrg_energies_with_eigh_route(eigh_route, cutoff):
+    """2-site DMRG (S=1/2 Heisenberg N=14) with every factorisation on the Gram + eigh route: per-sweep energies
+    within 1e-10 relative and truncation errors within 1e-8 of the oracle (LAPACK svd / eigh)."""
+    import networksolvers_b200 as ns
+    g = ns.path_graph(14)
+    sites = ns.siteinds("S=1/2", g)
+    H = ns.ttno(ns.heisenberg(g), sites)
+    psi0 = ns.product_state(sites, neel(g))
+    trunc = dict(cutoff=cutoff, maxdim=[10, 20, 40])
+    rec = SweepRecorder()
+    E, psi = ns.dmrg(H, psi0, nsweeps=3, nsites=2, inserter_kwargs=dict(trunc=trunc), sweep_callback=rec.sweep,
+                     region_callback=rec.region)
+    Eo, _, orec = _oracle_sweeps(to_oracle_ttn(H, True), to_oracle_ttn(psi0), nsweeps=3, nsites=2,
+                                 inserter_kwargs=dict(trunc=trunc))
+    for a, b in zip(rec.energies, orec["E"]):
+        assert abs(a - b) <= 1e-10 * abs(b), (rec.energies, orec["E"])
+    terr = [t for t in rec.truncerrs if t is not None]
+    assert np.abs(np.array(terr) - np.array(orec["terr"])).max() <= 1e-8
+    assert rec.maxlinkdims == orec["maxdim"]
+
+
+def test_eigh_large_residual(ctx):
+    """n = 2048 Wishart matrix: residual and orthogonality at LAPACK level, timing printed for the log."""
+    import time
+    rng = np.random.default_rng(3)
+    n = 2048
+    G = rng.standard_normal((n, n))
+    A = G @ G.T
+    t0 = time.perf_counter()
+    w, U = ctx.eigh(A)
+    dt = time.perf_counter() - t0
+    nrm = np.linalg.norm(A, 2)
+    res = np.linalg.norm(A @ U - U * w[None, :]) / (nrm * n)
+    orth = np.linalg.norm(U.T @ U - np.eye(n)) / n
+    print(f"eigh n={n}: {dt:.3f} s (incl. H2D/D2H) resid {res:.2e} orth {orth:.2e}")
+    assert res < 30 * EPS and orth < 30 * EPS
