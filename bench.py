@@ -178,7 +178,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fused", action="store_true", help="multi-GPU: fused GEMM + peer-store reduce-scatter epilogue instead of the "
                     "NCCL all-reduce (correct but slower in round 1: the DMMA fragment layout issues 64-byte P2P stores)")
-    ap.add_argument("--no-region-step", action="store_true", help="skip the full region step (3-matvec Lanczos + truncating insert)")
+    ap.add_argument("--no-region-step", action="store_true", help="skip the full region steps (extract + 3-matvec Lanczos + truncating insert)")
+    ap.add_argument("--region-steps", type=int, default=3, help="consecutive region steps timed after the matvec benchmark")
+    ap.add_argument("--cutoff", type=float, default=0.0, help="inserter cutoff of the region steps (0: maxdim-limited, SVD-route label; "
+                    "1e-9: the reference's timed_dmrg setting, eigen-route label)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -289,17 +292,35 @@ def main():
 
     extra = {}
     if not args.no_region_step and rank == 0 and shard is None:
+        # Consecutive full region steps of a left-to-right 2-site sweep through the three hooks (extract = gauge +
+        # theta build + environment update; eigsolve = 3-matvec Lanczos; insert = truncating factorisation), starting
+        # on the benchmark bond.  The first step re-uses the environments built during set-up; the later ones include
+        # the one environment update a sweep step needs.
         ctx.enable_timers(True)
-        ctx.reset_timers()
-        t0 = time.perf_counter()
-        val, sinfo = net.update_eigsolve()
-        ins = net.insert((0.0, 1, args.chi))
-        ctx.synchronize()
-        extra["region_step_s"] = time.perf_counter() - t0
-        extra["region_phase_ms"] = ctx.timers()
-        extra["region_newdim"] = int(ins.newdim)
+        tr = (args.cutoff, 1, args.chi)
+        steps, phases, newdims = [], [], []
+        for r in range(max(args.region_steps, 1)):
+            reg = [region[0] + r, region[1] + r]
+            if reg[1] > args.nsites:
+                break
+            ctx.reset_timers()
+            ctx.synchronize()
+            t0 = time.perf_counter()
+            net.extract(reg)
+            val, sinfo = net.update_eigsolve()
+            ins = net.insert(tr)
+            ctx.synchronize()
+            steps.append(time.perf_counter() - t0)
+            phases.append(ctx.timers())
+            newdims.append(int(ins.newdim))
+        full = steps[1:] if len(steps) > 1 else steps
+        extra["region_step_s"] = float(np.mean(full))
+        extra["region_steps_s"] = steps
+        extra["region_phase_ms"] = {k: float(np.mean([ph[k] for ph in (phases[1:] if len(phases) > 1 else phases)])) for k in phases[0]}
+        extra["region_newdim"] = newdims
+        extra["region_trunc"] = {"cutoff": args.cutoff, "maxdim": args.chi}
         extra["sweep_regions"] = 2 * (args.nsites - 1)
-        # one interior region step x number of regions of an Euler-tour sweep (end regions are cheaper): upper estimate
+        # interior region step x number of regions of an Euler-tour sweep (end regions are cheaper): upper estimate
         extra["sweep_s_extrapolated"] = extra["region_step_s"] * 2 * (args.nsites - 1)
         ctx.enable_timers(False)
 

@@ -30,14 +30,16 @@ def _cases(n, rng):
     yield "gauss", M + M.T
     G = rng.standard_normal((n, 2 * n))
     yield "wishart", G @ G.T
+    Mc = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    yield "complex", Mc + Mc.conj().T
+    if n < 8:
+        return
     Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
     yield "graded", (Q * np.exp(-40.0 * np.arange(n) / n)) @ Q.T
     yield "lowrank", (Q[:, :3] * np.array([1.0, 0.5, 1e-3])) @ Q[:, :3].T
     yield "identity+rank1", np.eye(n) + 1e-3 * np.outer(Q[:, 0], Q[:, 0])
     cl = np.repeat(np.arange(1, n // 8 + 2), 8)[:n].astype(float)
     yield "clustered", (Q * cl) @ Q.T
-    Mc = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
-    yield "complex", Mc + Mc.conj().T
     Gc = rng.standard_normal((n, n + 3)) + 1j * rng.standard_normal((n, n + 3))
     yield "complex gram", Gc @ Gc.conj().T
 
