@@ -95,17 +95,17 @@ def test_factorize_eigh_route_truncation_rule(eigh_route, cutoff, maxdim):
 
 
 def _oracle_sweeps(H, psi0, **kw):
-    from oracle.sweep import dmrg
-    rec = {"E": [], "maxdim": [], "terr": []}
+    """Run the oracle DMRG recording per-sweep energies / per-region truncation errors."""
+    from oracle import sweep as osw
+    rec = {"E": [], "terr": [], "maxdim": []}
+    osw.COUNTERS.clear()
 
-    def sweep_cb(problem=None, sweep=None, **_):
-        rec["E"].append(problem.eigenvalue)
-        rec["maxdim"].append(problem.state.maxlinkdim())
+    def sweep_cb(region_iter, **k):
+        rec["E"].append(region_iter.problem.eigenvalue)
+        rec["maxdim"].append(region_iter.problem.state.maxlinkdim())
 
-    def region_cb(problem=None, **_):
-        rec["terr"].append(problem.last_truncerr)
-
-    E, psi = dmrg(H, psi0, sweep_callback=sweep_cb, region_callback=region_cb, **kw)
+    E, psi = osw.dmrg(H, psi0, sweep_callback=sweep_cb, **kw)
+    rec["terr"] = list(osw.COUNTERS.get("truncerrs", []))
     return E, psi, rec
 
 
