@@ -8,6 +8,8 @@
 #include <cmath>
 #include <cstdlib>
 
+#include <cooperative_groups.h>
+
 #include "dc_secular.h"
 #include "gemm.h"
 #include "linalg.h"
@@ -17,6 +19,9 @@ namespace nsb {
 
 int g_eigh_min_n = 1024;
 int g_eigh_nb = 64;
+int g_eigh_coop = 1;    // tridiagonalisation panels as one cooperative kernel (2 grid barriers per column); 0: five launches per column
+int g_eigh_coop_ctas = 3;   // CTAs per SM of the cooperative panel kernel
+int g_eigh_wb = 256;   // reflectors per compact-WY block of the back-transformation (<= 256)
 
 #define LAUNCH_CHECK(ctx) do { (ctx)->cnt.kernel_launches++; NSB_CUDA(cudaGetLastError()); } while (0)
 
@@ -188,6 +193,168 @@ __global__ void __launch_bounds__(256) trd_w2_kernel(const T* __restrict__ Vp, T
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// One tridiagonalisation panel as a single cooperative kernel: per column two grid-wide barriers.
+//   phase AD(i): finish w_{i-1} = tau (y - V p1 - W p2) + alpha v on the thread's own rows, bring column j = p + i
+//                up to date, partial sums of |A[j+2:, j]|^2                                         -> barrier
+//   phase C(i):  every CTA derives (beta, tau, scale) from the partials, v = scale x (v[0] = 1) is formed on the
+//                fly and stored, persistent column-dot products y = A_trail^H v, p1 = W^H v, p2 = V^H v,
+//                partial sums of y^H v                                                              -> barrier
+// alpha = -1/2 tau (w0^H v) needs no third barrier: w0^H v = conj(tau) (y^H v - 2 Re p1^H p2) because V^H v = p2
+// and W^H v = p1.  Same arithmetic as the five-kernel path up to the order of the reductions.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct TrdPanelArgs {
+  T* A; int64_t lda, n, p; int w;
+  T* Vp; T* Wp; int64_t ldp;      // panel column 0, row 0 based
+  T* taus; double* d; double* e;
+  T* y;                           // >= n + 2 MAXNB scratch: y (m), p1 (i), p2 (i) of the current column
+  double* part;                   // gridDim.x partials of sigma
+  double* part2;                  // 2 gridDim.x partials of y^H v
+};
+
+template <typename T, int CPB>
+__global__ void __launch_bounds__(256) trd_panel_kernel(const TrdPanelArgs<T> a) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  __shared__ T sv[MAXNB], sw[MAXNB], p1[MAXNB], p2[MAXNB];
+  __shared__ double sh[2 * CPB * 32 + 2 * CPB];
+  const int tid = threadIdx.x, nblk = gridDim.x;
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + tid, gsize = (int64_t)nblk * blockDim.x;
+  const int64_t n = a.n, lda = a.lda, ldp = a.ldp;
+  const T one = from_complex<T>(1.0, 0.0);
+  T tau_prev = zero_<T>();
+  for (int i = 0; i <= a.w; ++i) {   // i == w: only finishes the last w
+    const int64_t j = a.p + i;
+    const int ip = i - 1;
+    // ---------------- phase AD ----------------
+    T alpha = zero_<T>();
+    if (i > 0) {
+      const int64_t mprev = n - j;   // length of y of column j - 1 (rows j .. n-1)
+      for (int k = tid; k < ip; k += blockDim.x) { p1[k] = a.y[mprev + k]; p2[k] = a.y[mprev + ip + k]; }
+      double s2[2] = {0.0, 0.0};
+      for (int k = tid; k < nblk; k += blockDim.x) { s2[0] += a.part2[2 * k]; s2[1] += a.part2[2 * k + 1]; }
+      blk_sum<2>(s2, sh);            // (its barriers also publish p1 / p2)
+      double cross = 0.0;
+      for (int k = 0; k < ip; ++k) cross += re(p1[k]) * re(p2[k]) + im(p1[k]) * im(p2[k]);
+      const T w0hv = mul_(conj_(tau_prev), from_complex<T>(s2[0] - 2.0 * cross, s2[1]));
+      alpha = mul_(tau_prev, from_complex<T>(-0.5 * re(w0hv), -0.5 * im(w0hv)));
+    }
+    if (i < a.w) {
+      for (int k = tid; k < ip; k += blockDim.x) { sv[k] = conj_(a.Vp[j + (int64_t)k * ldp]); sw[k] = conj_(a.Wp[j + (int64_t)k * ldp]); }
+      if (i > 0 && tid < 32) {       // row j of the column being finished: V[j, ip] = 1, W[j, ip] = w_{ip}[j]
+        double ar = 0.0, ai = 0.0;
+        for (int k = tid; k < ip; k += 32) {
+          T t = mul_(a.Vp[j + (int64_t)k * ldp], p1[k]);
+          fma_(t, a.Wp[j + (int64_t)k * ldp], p2[k]);
+          ar += re(t); ai += im(t);
+        }
+        for (int o = 16; o > 0; o >>= 1) { ar += __shfl_xor_sync(0xffffffffu, ar, o); ai += __shfl_xor_sync(0xffffffffu, ai, o); }
+        if (tid == 0) {
+          T wj = mul_(tau_prev, sub_(a.y[0], from_complex<T>(ar, ai)));
+          wj = add_(wj, alpha);
+          sv[ip] = one;
+          sw[ip] = conj_(wj);
+        }
+      }
+    }
+    __syncthreads();
+    double sig[1] = {0.0};
+    for (int64_t r = j + gtid; r < n; r += gsize) {
+      T accw = zero_<T>(), accu = zero_<T>();
+      for (int k = 0; k < ip; ++k) {
+        const T vk = a.Vp[r + (int64_t)k * ldp], wk = a.Wp[r + (int64_t)k * ldp];
+        fma_(accw, vk, p1[k]);
+        fma_(accw, wk, p2[k]);
+        if (i < a.w) { fma_(accu, vk, sw[k]); fma_(accu, wk, sv[k]); }
+      }
+      if (i > 0) {
+        const T vip = a.Vp[r + (int64_t)ip * ldp];
+        T wr = mul_(tau_prev, sub_(a.y[r - j], accw));
+        fma_(wr, alpha, vip);
+        a.Wp[r + (int64_t)ip * ldp] = wr;
+        if (i < a.w) { fma_(accu, vip, sw[ip]); fma_(accu, wr, sv[ip]); }
+      }
+      if (i < a.w) {
+        const T av = sub_(a.A[r + j * lda], accu);
+        a.A[r + j * lda] = av;
+        if (r == j) a.d[j] = re(av);
+        if (r >= j + 2) sig[0] += abs2_(av);
+      }
+    }
+    if (i == a.w) break;
+    blk_sum<1>(sig, sh);
+    if (tid == 0) a.part[blockIdx.x] = sig[0];
+    grid.sync();
+    // ---------------- phase C ----------------
+    const int64_t m = n - j - 1;
+    double s1[1] = {0.0};
+    for (int k = tid; k < nblk; k += blockDim.x) s1[0] += a.part[k];
+    blk_sum<1>(s1, sh);
+    const double sigma = s1[0];
+    const T* xcol = a.A + (j + 1) + j * lda;
+    const T alpha0 = xcol[0];
+    const double ar = re(alpha0), ai = im(alpha0);
+    T tau = zero_<T>(), scale = zero_<T>();
+    double beta = ar;
+    if (!(sigma == 0.0 && ai == 0.0)) {
+      beta = -copysign(sqrt(ar * ar + ai * ai + sigma), ar);
+      const double dr = ar - beta, di = ai, den = dr * dr + di * di;
+      scale = from_complex<T>(dr / den, -di / den);
+      tau = from_complex<T>((beta - ar) / beta, -ai / beta);
+    }
+    tau_prev = tau;
+    if (gtid == 0) { a.taus[j] = tau; a.e[j] = beta; }
+    T* vcol = a.Vp + (int64_t)i * ldp + (j + 1);
+    for (int64_t rr = gtid; rr < m; rr += gsize) vcol[rr] = (rr == 0) ? one : mul_(scale, xcol[rr]);
+    const int64_t ncol = m + 2 * (int64_t)i, ngroups = (ncol + CPB - 1) / CPB;
+    const T* At = a.A + (j + 1) + (j + 1) * lda;
+    const T* Wr = a.Wp + (j + 1);
+    const T* Vr = a.Vp + (j + 1);
+    double yhv0 = 0.0, yhv1 = 0.0;
+    for (int64_t g = blockIdx.x; g < ngroups; g += nblk) {
+      const int64_t c0 = g * CPB;
+      const T* cols[CPB];
+#pragma unroll
+      for (int q = 0; q < CPB; ++q) {
+        const int64_t c = c0 + q;
+        cols[q] = c < m ? At + c * lda : (c < m + i ? Wr + (c - m) * ldp : (c < ncol ? Vr + (c - m - i) * ldp : nullptr));
+      }
+      double acc[2 * CPB];
+#pragma unroll
+      for (int q = 0; q < 2 * CPB; ++q) acc[q] = 0.0;
+      for (int64_t rr = tid; rr < m; rr += blockDim.x) {
+        const T x = (rr == 0) ? one : mul_(scale, xcol[rr]);
+#pragma unroll
+        for (int q = 0; q < CPB; ++q) {
+          if (cols[q]) {
+            const T v = cols[q][rr];
+            acc[2 * q] += re(v) * re(x) + im(v) * im(x);
+            acc[2 * q + 1] += re(v) * im(x) - im(v) * re(x);
+          }
+        }
+      }
+      blk_sum<2 * CPB>(acc, sh);
+      if (tid == 0) {
+#pragma unroll
+        for (int q = 0; q < CPB; ++q) {
+          const int64_t c = c0 + q;
+          if (c < ncol) {
+            a.y[c] = from_complex<T>(acc[2 * q], acc[2 * q + 1]);
+            if (c < m) {
+              const T vc = (c == 0) ? one : mul_(scale, xcol[c]);
+              yhv0 += acc[2 * q] * re(vc) + acc[2 * q + 1] * im(vc);       // conj(y_c) v_c
+              yhv1 += acc[2 * q] * im(vc) - acc[2 * q + 1] * re(vc);
+            }
+          }
+        }
+      }
+    }
+    if (tid == 0) { a.part2[2 * blockIdx.x] = yhv0; a.part2[2 * blockIdx.x + 1] = yhv1; }
+    grid.sync();
+  }
+}
+
 template <typename T>
 __global__ void trd_last_diag_kernel(const T* __restrict__ A, int64_t lda, int64_t n, double* __restrict__ d_out) {
   if (threadIdx.x == 0 && blockIdx.x == 0) d_out[n - 1] = re(A[(n - 1) + (n - 1) * lda]);
@@ -197,7 +364,7 @@ __global__ void trd_last_diag_kernel(const T* __restrict__ A, int64_t lda, int64
 // stage 3 helpers: T factor of a reflector block (H_0 ... H_{w-1} = I - V T V^H), real -> T conversion
 // ------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(128) larft_kernel(const T* __restrict__ S /* V^H V, w x w */, int w, const T* __restrict__ tau,
+__global__ void __launch_bounds__(256) larft_kernel(const T* __restrict__ S /* V^H V, w x w */, int w, const T* __restrict__ tau,
                                                     T* __restrict__ Tm /* w x w */) {
   for (int e = threadIdx.x; e < w * w; e += blockDim.x) Tm[e] = zero_<T>();
   __syncthreads();
@@ -506,10 +673,33 @@ void Eigh<T>::factor(Ctx* c, T* A, int64_t n_, int64_t lda) {
   const bool dbg = eigh_debug();
   double t0 = 0.0;
   if (dbg) { ctx->sync(); t0 = now_s(); }
+  // cooperative panel kernel: grid sized from the occupancy query so that every CTA is resident
+  int coop_grid = 0;
+  DevBuf part2;
+  if (g_eigh_coop) {
+    int per_sm = 0, coop_ok = 0;
+    NSB_CUDA(cudaDeviceGetAttribute(&coop_ok, cudaDevAttrCooperativeLaunch, ctx->device));
+    NSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trd_panel_kernel<T, CPB>, 256, 0));
+    per_sm = std::min(per_sm, std::max(1, g_eigh_coop_ctas));
+    if (coop_ok && per_sm >= 1) {
+      coop_grid = per_sm * ctx->num_sms;
+      part = DevBuf(ctx, sizeof(double) * coop_grid);
+      part2 = DevBuf(ctx, sizeof(double) * 2 * coop_grid);
+    }
+  }
   for (int64_t p = 0; p < nref; p += nb) {
     const int w = (int)std::min<int64_t>(nb, nref - p);
     T* Vp = Vp0 + p * n;   // panel columns p .. p + w - 1 of Vall (ld n)
-    for (int i = 0; i < w; ++i) {
+    if (coop_grid > 0) {
+      TrdPanelArgs<T> pa;
+      pa.A = A; pa.lda = lda; pa.n = n; pa.p = p; pa.w = w; pa.Vp = Vp; pa.Wp = Wp; pa.ldp = n;
+      pa.taus = dtau; pa.d = (double*)d_d.ptr; pa.e = (double*)e_d.ptr; pa.y = (T*)yb.ptr;
+      pa.part = (double*)part.ptr; pa.part2 = (double*)part2.ptr;
+      void* kargs[] = {(void*)&pa};
+      NSB_CUDA(cudaLaunchCooperativeKernel((void*)trd_panel_kernel<T, CPB>, dim3(coop_grid), dim3(256), kargs, 0, ctx->stream));
+      ctx->cnt.kernel_launches++;
+    }
+    for (int i = 0; coop_grid == 0 && i < w; ++i) {
       const int64_t j = p + i, m = n - j - 1;
       trd_col_update_kernel<T><<<(unsigned)((n - j + 255) / 256), 256, 0, ctx->stream>>>(A, lda, n, j, Vp, Wp, n, i, (double*)d_d.ptr);
       LAUNCH_CHECK(ctx);
@@ -550,7 +740,9 @@ void Eigh<T>::factor(Ctx* c, T* A, int64_t n_, int64_t lda) {
 template <typename T>
 void Eigh<T>::vectors(const int32_t* idx_host, int64_t k, T* U, int64_t ldu) {
   if (k <= 0) return;
-  const int nb = std::max(2, std::min(g_eigh_nb, MAXNB)) & ~1;
+  // block width of the back-transformation: independent of the tridiagonalisation panels (any run of consecutive
+  // reflectors has a compact-WY form); wide blocks make the three GEMMs per block efficient
+  const int nb = std::max(2, std::min(g_eigh_wb, 256)) & ~1;
   const T one = from_complex<T>(1.0, 0.0), mone = from_complex<T>(-1.0, 0.0), zero = zero_<T>();
   DevBuf idx(ctx, sizeof(int32_t) * k);
   NSB_CUDA(cudaMemcpyAsync(idx.ptr, idx_host, sizeof(int32_t) * k, cudaMemcpyHostToDevice, ctx->stream));
@@ -578,7 +770,7 @@ void Eigh<T>::vectors(const int32_t* idx_host, int64_t k, T* U, int64_t ldu) {
     const T* Vp = Vp0 + p * n + p;   // rows p.. (row p of this panel is zero: harmless, keeps the operands 16-byte aligned)
     const int64_t mp = n - p;
     gemm<T>(ctx, OP_C, OP_N, w, w, mp, one, Vp, n, 0, Vp, n, 0, zero, (T*)S.ptr, w, 0, 1);
-    larft_kernel<T><<<1, 128, 0, ctx->stream>>>((const T*)S.ptr, w, dtau + p, (T*)Tm.ptr);
+    larft_kernel<T><<<1, 256, 0, ctx->stream>>>((const T*)S.ptr, w, dtau + p, (T*)Tm.ptr);
     LAUNCH_CHECK(ctx);
     gemm<T>(ctx, OP_C, OP_N, w, k, mp, one, Vp, n, 0, U + p, ldu, 0, zero, (T*)Y.ptr, w, 0, 1);
     gemm<T>(ctx, OP_N, OP_N, w, k, w, one, (const T*)Tm.ptr, w, 0, (const T*)Y.ptr, w, 0, zero, (T*)Y2.ptr, w, 0, 1);

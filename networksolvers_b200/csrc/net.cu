@@ -21,6 +21,8 @@
 
 namespace nsb {
 
+int g_merge_site_ops = 1;   // 2-site regions: apply W[a] W[b] as one small-operator pass (ctx option "merge_site_ops")
+
 // ------------------------------------------------------------------------------------------------
 // small host dense helpers
 // ------------------------------------------------------------------------------------------------
@@ -454,7 +456,7 @@ void Net<T>::build_plan() {
     }
   }
   // merge two consecutive site-operator steps (chain-like 2-site regions) into one pass over the big intermediate
-  for (size_t i = 0; i + 1 < plan.size(); ++i) {
+  for (size_t i = 0; g_merge_site_ops && i + 1 < plan.size(); ++i) {
     if (plan[i].type == 1 && plan[i + 1].type == 1) {
       int a = plan[i].v, b = plan[i + 1].v;
       const DTensor<T>&Wa = W[a], &Wb = W[b];

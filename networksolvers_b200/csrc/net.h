@@ -11,6 +11,8 @@
 
 namespace nsb {
 
+extern int g_merge_site_ops;
+
 struct NetBase {
   Ctx* ctx = nullptr;
   int dtype = NSB_F64;

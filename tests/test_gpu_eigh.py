@@ -44,10 +44,13 @@ def _cases(n, rng):
     yield "complex gram", Gc @ Gc.conj().T
 
 
+@pytest.mark.parametrize("coop", [1, 0])
 @pytest.mark.parametrize("n,nb", [(1, 64), (2, 64), (5, 64), (64, 64), (129, 64), (300, 32), (700, 64), (1100, 128)])
-def test_eigh_matches_lapack(ctx, n, nb):
+def test_eigh_matches_lapack(ctx, n, nb, coop):
+    """coop = 1: one cooperative kernel per tridiagonalisation panel; coop = 0: five launches per column."""
     rng = np.random.default_rng(n)
     ctx.set_option("eigh_nb", nb)
+    ctx.set_option("eigh_coop", coop)
     try:
         for name, A in _cases(n, rng):
             w, U = ctx.eigh(A)
@@ -58,6 +61,7 @@ def test_eigh_matches_lapack(ctx, n, nb):
             assert res < 30 * EPS and orth < 30 * EPS and err < 100 * EPS, (name, n, res, orth, err)
     finally:
         ctx.set_option("eigh_nb", 64)
+        ctx.set_option("eigh_coop", 1)
 
 
 @pytest.mark.parametrize("cplx", [False, True])
