@@ -291,7 +291,7 @@ def main():
                                "entry; cuBLAS DGEMM on this pool reaches 35.5-36.0, profiles/r01_microbench_fp64_peaks.jsonl)"}
 
     extra = {}
-    if not args.no_region_step and rank == 0 and shard is None:
+    if not args.no_region_step and (world == 1 or shard is not None):   # sharded runs: every rank steps in lock step
         # Consecutive full region steps of a left-to-right 2-site sweep through the three hooks (extract = gauge +
         # theta build + environment update; eigsolve = 3-matvec Lanczos; insert = truncating factorisation), starting
         # on the benchmark bond.  The first step re-uses the environments built during set-up; the later ones include
@@ -322,6 +322,8 @@ def main():
         extra["sweep_regions"] = 2 * (args.nsites - 1)
         # interior region step x number of regions of an Euler-tour sweep (end regions are cheaper): upper estimate
         extra["sweep_s_extrapolated"] = extra["region_step_s"] * 2 * (args.nsites - 1)
+        if world > 1:
+            extra["region_parallelism"] = "H_eff applications sharded + NCCL all-reduce; environment update and factorisation replicated"
         ctx.enable_timers(False)
 
     cpu = None

@@ -32,6 +32,7 @@ namespace {
 
 constexpr int MAXNB = 128;
 
+__device__ __forceinline__ int64_t imin64(int64_t a, int64_t b) { return a < b ? a : b; }
 __device__ __forceinline__ double sub_(double a, double b) { return a - b; }
 __device__ __forceinline__ cdouble sub_(cdouble a, cdouble b) { return make_cuDoubleComplex(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ double neg_(double a) { return -a; }
@@ -217,8 +218,10 @@ template <typename T, int CPB>
 __global__ void __launch_bounds__(256) trd_panel_kernel(const TrdPanelArgs<T> a) {
   namespace cg = cooperative_groups;
   cg::grid_group grid = cg::this_grid();
+  constexpr int GEMV_CHUNK = 128;
   __shared__ T sv[MAXNB], sw[MAXNB], p1[MAXNB], p2[MAXNB];
   __shared__ double sh[2 * CPB * 32 + 2 * CPB];
+  __shared__ double spart[GEMV_CHUNK * 16];   // per column: 8 warp partials (re), 8 (im)
   const int tid = threadIdx.x, nblk = gridDim.x;
   const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + tid, gsize = (int64_t)nblk * blockDim.x;
   const int64_t n = a.n, lda = a.lda, ldp = a.ldp;
@@ -307,49 +310,68 @@ __global__ void __launch_bounds__(256) trd_panel_kernel(const TrdPanelArgs<T> a)
     if (gtid == 0) { a.taus[j] = tau; a.e[j] = beta; }
     T* vcol = a.Vp + (int64_t)i * ldp + (j + 1);
     for (int64_t rr = gtid; rr < m; rr += gsize) vcol[rr] = (rr == 0) ? one : mul_(scale, xcol[rr]);
-    const int64_t ncol = m + 2 * (int64_t)i, ngroups = (ncol + CPB - 1) / CPB;
+    // column dot products: every CTA owns a contiguous range of the ncol columns; its 8 warps stream disjoint row
+    // classes of CPB columns at a time (no block barrier inside the stream), partials meet in shared memory
+    const int64_t ncol = m + 2 * (int64_t)i;
     const T* At = a.A + (j + 1) + (j + 1) * lda;
     const T* Wr = a.Wp + (j + 1);
     const T* Vr = a.Vp + (j + 1);
-    double yhv0 = 0.0, yhv1 = 0.0;
-    for (int64_t g = blockIdx.x; g < ngroups; g += nblk) {
-      const int64_t c0 = g * CPB;
-      const T* cols[CPB];
-#pragma unroll
-      for (int q = 0; q < CPB; ++q) {
-        const int64_t c = c0 + q;
-        cols[q] = c < m ? At + c * lda : (c < m + i ? Wr + (c - m) * ldp : (c < ncol ? Vr + (c - m - i) * ldp : nullptr));
-      }
-      double acc[2 * CPB];
-#pragma unroll
-      for (int q = 0; q < 2 * CPB; ++q) acc[q] = 0.0;
-      for (int64_t rr = tid; rr < m; rr += blockDim.x) {
-        const T x = (rr == 0) ? one : mul_(scale, xcol[rr]);
-#pragma unroll
-        for (int q = 0; q < CPB; ++q) {
-          if (cols[q]) {
-            const T v = cols[q][rr];
-            acc[2 * q] += re(v) * re(x) + im(v) * im(x);
-            acc[2 * q + 1] += re(v) * im(x) - im(v) * re(x);
-          }
-        }
-      }
-      blk_sum<2 * CPB>(acc, sh);
-      if (tid == 0) {
+    const int64_t per = (ncol + nblk - 1) / nblk;
+    const int64_t cbeg = imin64(ncol, (int64_t)blockIdx.x * per), cend = imin64(ncol, cbeg + per);
+    const int warp = tid >> 5, lane = tid & 31;
+    double yhv[2] = {0.0, 0.0};
+    for (int64_t cb = cbeg; cb < cend; cb += GEMV_CHUNK) {   // (one pass unless a CTA owns more than GEMV_CHUNK columns)
+      const int64_t ce = imin64(cend, cb + GEMV_CHUNK);
+      for (int64_t c0 = cb; c0 < ce; c0 += CPB) {
+        const T* cols[CPB];
 #pragma unroll
         for (int q = 0; q < CPB; ++q) {
           const int64_t c = c0 + q;
-          if (c < ncol) {
-            a.y[c] = from_complex<T>(acc[2 * q], acc[2 * q + 1]);
-            if (c < m) {
-              const T vc = (c == 0) ? one : mul_(scale, xcol[c]);
-              yhv0 += acc[2 * q] * re(vc) + acc[2 * q + 1] * im(vc);       // conj(y_c) v_c
-              yhv1 += acc[2 * q] * im(vc) - acc[2 * q + 1] * re(vc);
+          cols[q] = c >= ce ? nullptr : (c < m ? At + c * lda : (c < m + i ? Wr + (c - m) * ldp : Vr + (c - m - i) * ldp));
+        }
+        double acc[2 * CPB];
+#pragma unroll
+        for (int q = 0; q < 2 * CPB; ++q) acc[q] = 0.0;
+#pragma unroll 2
+        for (int64_t rr = tid; rr < m; rr += blockDim.x) {
+          const T x = (rr == 0) ? one : mul_(scale, xcol[rr]);
+#pragma unroll
+          for (int q = 0; q < CPB; ++q) {
+            if (cols[q]) {
+              const T v = cols[q][rr];
+              acc[2 * q] += re(v) * re(x) + im(v) * im(x);
+              acc[2 * q + 1] += re(v) * im(x) - im(v) * re(x);
             }
           }
         }
+#pragma unroll
+        for (int q = 0; q < 2 * CPB; ++q)
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+        if (lane == 0) {
+#pragma unroll
+          for (int q = 0; q < CPB; ++q) {
+            const int64_t c = c0 + q;
+            if (c < ce) { spart[(c - cb) * 16 + warp] = acc[2 * q]; spart[(c - cb) * 16 + 8 + warp] = acc[2 * q + 1]; }
+          }
+        }
       }
+      __syncthreads();
+      for (int64_t c = cb + tid; c < ce; c += blockDim.x) {
+        double yr = 0.0, yi = 0.0;
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8) { yr += spart[(c - cb) * 16 + w8]; yi += spart[(c - cb) * 16 + 8 + w8]; }
+        a.y[c] = from_complex<T>(yr, yi);
+        if (c < m) {
+          const T vc = (c == 0) ? one : mul_(scale, xcol[c]);
+          yhv[0] += yr * re(vc) + yi * im(vc);       // conj(y_c) v_c
+          yhv[1] += yr * im(vc) - yi * re(vc);
+        }
+      }
+      __syncthreads();
     }
+    blk_sum<2>(yhv, sh);
+    const double yhv0 = yhv[0], yhv1 = yhv[1];
     if (tid == 0) { a.part2[2 * blockIdx.x] = yhv0; a.part2[2 * blockIdx.x + 1] = yhv1; }
     grid.sync();
   }

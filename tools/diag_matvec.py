@@ -5,9 +5,10 @@ import numpy as np
 import networksolvers_b200 as ns
 from bench import build_problem, ClockSampler
 chi = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+nsites = int(sys.argv[2]) if len(sys.argv) > 2 else 26
 ctx = ns.Context(0)
 def run(tag):
-    net, region = build_problem(chi, 26, ctx)
+    net, region = build_problem(chi, nsites, ctx)
     net.extract(region)
     ctx.synchronize()
     for _ in range(3):
@@ -29,8 +30,5 @@ def run(tag):
     print(tag, "single", [round(x, 2) for x in single], "back-to-back", round(b2b, 2), "host enqueue ms/matvec", round(host_enqueue * 1e3, 3),
           clk.summary(), ctx.mem_info(), flush=True)
     del net
-run("merged")
-ctx.set_option("merge_site_ops", 0)
-run("unmerged")
-ctx.set_option("merge_site_ops", 1)
+run(f"nsites={nsites}")
 print(subprocess.run(["nvidia-smi", "--query-gpu=power.draw,power.limit,clocks.sm,temperature.gpu", "--format=csv"], capture_output=True, text=True).stdout)
