@@ -13,11 +13,21 @@ bool g_timers_enabled = false;
 static thread_local std::string tl_error;
 
 void* Ctx::alloc(size_t bytes) {
+  if (bytes >= BIG_MIN) {
+    auto it = big_cache.find(bytes);
+    if (it != big_cache.end()) {
+      void* q = it->second;
+      big_cache.erase(it);
+      big_cached_bytes -= bytes;
+      return q;
+    }
+  }
   void* p = nullptr;
   cudaError_t e = cudaMallocFromPoolAsync(&p, bytes, pool, stream);
   if (e != cudaSuccess) {
     cudaGetLastError();
-    // one retry after letting in-flight frees complete
+    // one retry after returning the cached blocks and letting in-flight frees complete
+    flush_big_cache();
     cudaStreamSynchronize(stream);
     e = cudaMallocFromPoolAsync(&p, bytes, pool, stream);
   }
@@ -27,7 +37,20 @@ void* Ctx::alloc(size_t bytes) {
   }
   return p;
 }
-void Ctx::free(void* p) { if (p) cudaFreeAsync(p, stream); }
+void Ctx::free(void* p, size_t bytes) {
+  if (!p) return;
+  if (bytes >= BIG_MIN && big_cached_bytes + bytes <= big_cache_cap) {
+    big_cache.emplace(bytes, p);
+    big_cached_bytes += bytes;
+    return;
+  }
+  cudaFreeAsync(p, stream);
+}
+void Ctx::flush_big_cache() {
+  for (auto& kv : big_cache) cudaFreeAsync(kv.second, stream);
+  big_cache.clear();
+  big_cached_bytes = 0;
+}
 
 PhaseTimer::PhaseTimer(Ctx* c, int i) : ctx(c), idx(i), e0(nullptr), e1(nullptr), active(g_timers_enabled) {
   if (!active) return;
@@ -117,6 +140,7 @@ int nsb_ctx_destroy(nsb_ctx* ctx) {
 static void ctx_really_destroy(nsb_ctx* ctx) {
   cudaSetDevice(ctx->c.device);
   if (ctx->c.nccl_comm) { try { nccl_api().CommDestroy((ncclComm_t)ctx->c.nccl_comm); } catch (...) {} ctx->c.nccl_comm = nullptr; }
+  ctx->c.flush_big_cache();
   cudaStreamSynchronize(ctx->c.stream);
   if (ctx->c.d_scratch) cudaFree(ctx->c.d_scratch);
   if (ctx->c.h_pinned) cudaFreeHost(ctx->c.h_pinned);
@@ -135,6 +159,7 @@ int nsb_ctx_set_option(nsb_ctx* ctx, const char* key, int64_t value) {
   else if (k == "jacobi_pivot") { g_jacobi_pivot = value != 0; }
   else if (k == "jacobi_inner_cap") { NSB_REQUIRE(value >= 1, NSB_EINVAL, "jacobi_inner_cap >= 1"); g_jacobi_inner_cap = (int)value; }
   else if (k == "jacobi_precondition_min_n") { g_jacobi_precondition_min_n = (int)value; }
+  else if (k == "big_cache_gib") { NSB_REQUIRE(value >= 0, NSB_EINVAL, "big_cache_gib >= 0"); ctx->c.big_cache_cap = (size_t)value << 30; if (value == 0) ctx->c.flush_big_cache(); }
   else if (k == "merge_site_ops") { g_merge_site_ops = value != 0; }
   else if (k == "eigh_min_n") { g_eigh_min_n = (int)value; }
   else if (k == "eigh_coop") { g_eigh_coop = value != 0; }

@@ -10,6 +10,7 @@
 #include <vector>
 #include <memory>
 #include <complex>
+#include <map>
 
 #include "../../include/nsb200.h"
 
@@ -112,8 +113,16 @@ struct Ctx {
   double* d_scratch = nullptr;   // SCRATCH_DOUBLES doubles on the device
   double* h_pinned = nullptr;    // SCRATCH_DOUBLES doubles of pinned host memory
   static constexpr int SCRATCH_DOUBLES = 16384;
+  // Large blocks (matvec intermediates, factorisation workspaces) recur with exact sizes every region step: they are
+  // recycled through a size-keyed cache inside the context instead of going back to the driver's stream-ordered
+  // pool (single stream, so handing a freed block to a later allocation is ordered by the stream itself).
+  std::multimap<size_t, void*> big_cache;
+  size_t big_cached_bytes = 0;
+  size_t big_cache_cap = 24ull << 30;
+  static constexpr size_t BIG_MIN = 32ull << 20;
   void* alloc(size_t bytes);
-  void free(void* p);
+  void free(void* p, size_t bytes = 0);
+  void flush_big_cache();
   void sync() { NSB_CUDA(cudaStreamSynchronize(stream)); }
 };
 
@@ -132,7 +141,7 @@ struct DevBuf {
     return *this;
   }
   ~DevBuf() { release(); }
-  void release() { if (ptr && ctx) ctx->free(ptr); ptr = nullptr; bytes = 0; }
+  void release() { if (ptr && ctx) ctx->free(ptr, bytes); ptr = nullptr; bytes = 0; }
 };
 
 struct PhaseTimer {  // accumulates elapsed device time of a phase into ctx->timers_ms[idx]

@@ -226,6 +226,8 @@ __global__ void __launch_bounds__(256) trd_panel_kernel(const TrdPanelArgs<T> a)
   const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + tid, gsize = (int64_t)nblk * blockDim.x;
   const int64_t n = a.n, lda = a.lda, ldp = a.ldp;
   const T one = from_complex<T>(1.0, 0.0);
+  const bool vec_ok = (lda % 2 == 0) && (ldp % 2 == 0) && (((uintptr_t)a.A & 15) == 0) && (((uintptr_t)a.Wp & 15) == 0) &&
+                      (((uintptr_t)a.Vp & 15) == 0);
   T tau_prev = zero_<T>();
   for (int i = 0; i <= a.w; ++i) {   // i == w: only finishes the last w
     const int64_t j = a.p + i;
@@ -332,15 +334,49 @@ __global__ void __launch_bounds__(256) trd_panel_kernel(const TrdPanelArgs<T> a)
         double acc[2 * CPB];
 #pragma unroll
         for (int q = 0; q < 2 * CPB; ++q) acc[q] = 0.0;
-#pragma unroll 2
-        for (int64_t rr = tid; rr < m; rr += blockDim.x) {
-          const T x = (rr == 0) ? one : mul_(scale, xcol[rr]);
+        bool done = false;
+        if constexpr (!ScalarTraits<T>::is_complex) {
+          if (vec_ok) {   // 128-bit loads: all columns (and x) share the 16-byte phase of row j + 1
+            const int64_t start = (j + 1) & 1;
+            const int64_t npairs = (m - start) >> 1;
+            const double sc = re(scale);
+            if (tid == 0 && start == 1) {   // unaligned head row rr = 0 (x = 1)
 #pragma unroll
-          for (int q = 0; q < CPB; ++q) {
-            if (cols[q]) {
-              const T v = cols[q][rr];
-              acc[2 * q] += re(v) * re(x) + im(v) * im(x);
-              acc[2 * q + 1] += re(v) * im(x) - im(v) * re(x);
+              for (int q = 0; q < CPB; ++q) if (cols[q]) acc[2 * q] += re(cols[q][0]);
+            }
+            if (tid == 32 && ((m - start) & 1)) {   // odd tail row
+              const int64_t rr = m - 1;
+              const double x = (rr == 0) ? 1.0 : sc * re(xcol[rr]);
+#pragma unroll
+              for (int q = 0; q < CPB; ++q) if (cols[q]) acc[2 * q] += re(cols[q][rr]) * x;
+            }
+#pragma unroll 2
+            for (int64_t pi = tid; pi < npairs; pi += blockDim.x) {
+              const int64_t rr = start + 2 * pi;
+              const double2 xv = *reinterpret_cast<const double2*>(xcol + rr);
+              const double x0 = (rr == 0) ? 1.0 : sc * xv.x, x1 = sc * xv.y;
+#pragma unroll
+              for (int q = 0; q < CPB; ++q) {
+                if (cols[q]) {
+                  const double2 v = *reinterpret_cast<const double2*>(cols[q] + rr);
+                  acc[2 * q] += v.x * x0 + v.y * x1;
+                }
+              }
+            }
+            done = true;
+          }
+        }
+        if (!done) {
+#pragma unroll 2
+          for (int64_t rr = tid; rr < m; rr += blockDim.x) {
+            const T x = (rr == 0) ? one : mul_(scale, xcol[rr]);
+#pragma unroll
+            for (int q = 0; q < CPB; ++q) {
+              if (cols[q]) {
+                const T v = cols[q][rr];
+                acc[2 * q] += re(v) * re(x) + im(v) * im(x);
+                acc[2 * q + 1] += re(v) * im(x) - im(v) * re(x);
+              }
             }
           }
         }
