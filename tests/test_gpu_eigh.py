@@ -150,3 +150,49 @@ def test_eigh_large_residual(ctx):
     orth = np.linalg.norm(U.T @ U - np.eye(n)) / n
     print(f"eigh n={n}: {dt:.3f} s (incl. H2D/D2H) resid {res:.2e} orth {orth:.2e}")
     assert res < 30 * EPS and orth < 30 * EPS
+
+
+def test_one_site_expansion_with_eigh_route(eigh_route):
+    """1-site DMRG + densitymatrix expansion (examples/dmrg.jl:26-36) with the expansion's eigen(rho) and the gauge
+    factorisations on the device eigensolver (direct Hermitian path of factorize_left)."""
+    import networksolvers_b200 as ns
+    g = ns.path_graph(10)
+    sites = ns.siteinds("S=1", g)
+    H = ns.ttno(ns.heisenberg(g), sites)
+    psi0 = ns.product_state(sites, neel(g))
+    trunc = dict(cutoff=1e-12, maxdim=[10, 40, 80, 160])
+    ek = dict(trunc=trunc, subspace_algorithm="densitymatrix", expansion_factor=1.1)
+    rec = SweepRecorder()
+    E, psi = ns.dmrg(H, psi0, nsweeps=5, nsites=1, extracter_kwargs=ek, inserter_kwargs=dict(trunc=trunc),
+                     sweep_callback=rec.sweep)
+    Eo, _, orec = _oracle_sweeps(to_oracle_ttn(H, True), to_oracle_ttn(psi0), nsweeps=5, nsites=1, extracter_kwargs=ek,
+                                 inserter_kwargs=dict(trunc=trunc))
+    assert rec.maxlinkdims == orec["maxdim"]
+    for a, b in zip(rec.energies, orec["E"]):
+        assert abs(a - b) <= 1e-9 * abs(b), (rec.energies, orec["E"])
+    assert abs(E - (-12.8945601)) < 1e-6
+
+
+def test_tdvp_complex_with_eigh_route(eigh_route):
+    """2-site TDVP (complex128, examples/quench_evolution.jl shape) with every factorisation on the eigh route:
+    fidelity against dense expm >= 1 - 1e-8 and against the oracle state >= 1 - 1e-10."""
+    import networksolvers_b200 as ns
+    from oracle.ed import ed_time_evolution, state_vector
+    from oracle.models import heisenberg_opsum, spin_ops
+    from oracle import sweep as osw
+    from oracle.local_solvers import runge_kutta_solver as o_rk
+    g = ns.path_graph(8)
+    sites = ns.siteinds("S=1/2", g)
+    H = ns.ttno(ns.heisenberg(g), sites)
+    psi0 = ns.product_state(sites, neel(g, even_up=False))
+    tp = list(np.arange(0, 0.2 + 1e-9, 0.05))
+    ik = dict(trunc=dict(maxdim=5000, cutoff=1e-14), normalize=True)
+    psit = ns.tdvp(H, psi0, tp, nsites=2, tdvp_order=2, updater_kwargs=dict(solver=ns.runge_kutta_solver, order=4), inserter_kwargs=ik)
+    v = psit.to_host().to_dense()
+    og = to_oracle_ttn(psi0).graph
+    d, ops, _ = spin_ops("S=1/2")
+    vx = ed_time_evolution(heisenberg_opsum(og), og, ops, psi0.to_dense(), tp, normalize=True)
+    assert 1 - abs(np.vdot(vx, v)) < 1e-8
+    po = osw.tdvp(to_oracle_ttn(H, True), to_oracle_ttn(psi0), tp, nsites=2, tdvp_order=2, updater_kwargs=dict(solver=o_rk, order=4),
+                  inserter_kwargs=ik)
+    assert 1 - abs(np.vdot(state_vector(po), v)) < 1e-10
