@@ -219,6 +219,8 @@ __global__ void __launch_bounds__(256) trd_panel_kernel(const TrdPanelArgs<T> a)
   namespace cg = cooperative_groups;
   cg::grid_group grid = cg::this_grid();
   constexpr int GEMV_CHUNK = 128;
+  constexpr int CSET = ScalarTraits<T>::is_complex ? 8 : 16;   // columns streamed together by one warp pass
+  constexpr int NACC = ScalarTraits<T>::is_complex ? 2 : 1;
   __shared__ T sv[MAXNB], sw[MAXNB], p1[MAXNB], p2[MAXNB];
   __shared__ double sh[2 * CPB * 32 + 2 * CPB];
   __shared__ double spart[GEMV_CHUNK * 16];   // per column: 8 warp partials (re), 8 (im)
@@ -324,16 +326,17 @@ __global__ void __launch_bounds__(256) trd_panel_kernel(const TrdPanelArgs<T> a)
     double yhv[2] = {0.0, 0.0};
     for (int64_t cb = cbeg; cb < cend; cb += GEMV_CHUNK) {   // (one pass unless a CTA owns more than GEMV_CHUNK columns)
       const int64_t ce = imin64(cend, cb + GEMV_CHUNK);
-      for (int64_t c0 = cb; c0 < ce; c0 += CPB) {
-        const T* cols[CPB];
+      for (int64_t c0 = cb; c0 < ce;) {
+        // a set of up to CSET consecutive columns of one of the three matrices: base + q * stride
+        const T* base;
+        int64_t stride, segend;
+        if (c0 < m) { base = At + c0 * lda; stride = lda; segend = m; }
+        else if (c0 < m + i) { base = Wr + (c0 - m) * ldp; stride = ldp; segend = m + i; }
+        else { base = Vr + (c0 - m - i) * ldp; stride = ldp; segend = ncol; }
+        const int nset = (int)imin64(CSET, imin64(segend, ce) - c0);
+        double acc[CSET * NACC];
 #pragma unroll
-        for (int q = 0; q < CPB; ++q) {
-          const int64_t c = c0 + q;
-          cols[q] = c >= ce ? nullptr : (c < m ? At + c * lda : (c < m + i ? Wr + (c - m) * ldp : Vr + (c - m - i) * ldp));
-        }
-        double acc[2 * CPB];
-#pragma unroll
-        for (int q = 0; q < 2 * CPB; ++q) acc[q] = 0.0;
+        for (int q = 0; q < CSET * NACC; ++q) acc[q] = 0.0;
         bool done = false;
         if constexpr (!ScalarTraits<T>::is_complex) {
           if (vec_ok) {   // 128-bit loads: all columns (and x) share the 16-byte phase of row j + 1
@@ -342,55 +345,56 @@ __global__ void __launch_bounds__(256) trd_panel_kernel(const TrdPanelArgs<T> a)
             const double sc = re(scale);
             if (tid == 0 && start == 1) {   // unaligned head row rr = 0 (x = 1)
 #pragma unroll
-              for (int q = 0; q < CPB; ++q) if (cols[q]) acc[2 * q] += re(cols[q][0]);
+              for (int q = 0; q < CSET; ++q) if (q < nset) acc[q] += re(base[q * stride]);
             }
             if (tid == 32 && ((m - start) & 1)) {   // odd tail row
               const int64_t rr = m - 1;
               const double x = (rr == 0) ? 1.0 : sc * re(xcol[rr]);
 #pragma unroll
-              for (int q = 0; q < CPB; ++q) if (cols[q]) acc[2 * q] += re(cols[q][rr]) * x;
+              for (int q = 0; q < CSET; ++q) if (q < nset) acc[q] += re(base[q * stride + rr]) * x;
             }
-#pragma unroll 2
             for (int64_t pi = tid; pi < npairs; pi += blockDim.x) {
               const int64_t rr = start + 2 * pi;
               const double2 xv = *reinterpret_cast<const double2*>(xcol + rr);
               const double x0 = (rr == 0) ? 1.0 : sc * xv.x, x1 = sc * xv.y;
+              double2 v[CSET];
 #pragma unroll
-              for (int q = 0; q < CPB; ++q) {
-                if (cols[q]) {
-                  const double2 v = *reinterpret_cast<const double2*>(cols[q] + rr);
-                  acc[2 * q] += v.x * x0 + v.y * x1;
-                }
-              }
+              for (int q = 0; q < CSET; ++q)
+                v[q] = (q < nset) ? *reinterpret_cast<const double2*>(base + q * stride + rr) : make_double2(0.0, 0.0);
+#pragma unroll
+              for (int q = 0; q < CSET; ++q) acc[q] += v[q].x * x0 + v[q].y * x1;
             }
             done = true;
           }
         }
         if (!done) {
-#pragma unroll 2
           for (int64_t rr = tid; rr < m; rr += blockDim.x) {
             const T x = (rr == 0) ? one : mul_(scale, xcol[rr]);
+            T v[CSET];
 #pragma unroll
-            for (int q = 0; q < CPB; ++q) {
-              if (cols[q]) {
-                const T v = cols[q][rr];
-                acc[2 * q] += re(v) * re(x) + im(v) * im(x);
-                acc[2 * q + 1] += re(v) * im(x) - im(v) * re(x);
-              }
+            for (int q = 0; q < CSET; ++q) v[q] = (q < nset) ? base[q * stride + rr] : zero_<T>();
+#pragma unroll
+            for (int q = 0; q < CSET; ++q) {
+              acc[NACC * q] += re(v[q]) * re(x) + im(v[q]) * im(x);
+              if (NACC == 2) acc[NACC * q + NACC - 1] += re(v[q]) * im(x) - im(v[q]) * re(x);
             }
           }
         }
 #pragma unroll
-        for (int q = 0; q < 2 * CPB; ++q)
+        for (int q = 0; q < CSET * NACC; ++q)
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
         if (lane == 0) {
 #pragma unroll
-          for (int q = 0; q < CPB; ++q) {
-            const int64_t c = c0 + q;
-            if (c < ce) { spart[(c - cb) * 16 + warp] = acc[2 * q]; spart[(c - cb) * 16 + 8 + warp] = acc[2 * q + 1]; }
+          for (int q = 0; q < CSET; ++q) {
+            if (q < nset) {
+              const int64_t c = c0 + q;
+              spart[(c - cb) * 16 + warp] = acc[NACC * q];
+              spart[(c - cb) * 16 + 8 + warp] = (NACC == 2) ? acc[NACC * q + NACC - 1] : 0.0;
+            }
           }
         }
+        c0 += nset;
       }
       __syncthreads();
       for (int64_t c = cb + tid; c < ce; c += blockDim.x) {
