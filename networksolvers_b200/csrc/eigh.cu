@@ -35,6 +35,10 @@ constexpr int MAXNB = 128;
 __device__ __forceinline__ int64_t imin64(int64_t a, int64_t b) { return a < b ? a : b; }
 __device__ __forceinline__ double sub_(double a, double b) { return a - b; }
 __device__ __forceinline__ cdouble sub_(cdouble a, cdouble b) { return make_cuDoubleComplex(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double shfl_xor_T(double v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
+__device__ __forceinline__ cdouble shfl_xor_T(cdouble v, int o) {
+  return make_cuDoubleComplex(__shfl_xor_sync(0xffffffffu, v.x, o), __shfl_xor_sync(0xffffffffu, v.y, o));
+}
 __device__ __forceinline__ double neg_(double a) { return -a; }
 __device__ __forceinline__ cdouble neg_(cdouble a) { return make_cuDoubleComplex(-a.x, -a.y); }
 
@@ -267,26 +271,39 @@ __global__ void __launch_bounds__(256) trd_panel_kernel(const TrdPanelArgs<T> a)
     }
     __syncthreads();
     double sig[1] = {0.0};
-    for (int64_t r = j + gtid; r < n; r += gsize) {
-      T accw = zero_<T>(), accu = zero_<T>();
-      for (int k = 0; k < ip; ++k) {
-        const T vk = a.Vp[r + (int64_t)k * ldp], wk = a.Wp[r + (int64_t)k * ldp];
-        fma_(accw, vk, p1[k]);
-        fma_(accw, wk, p2[k]);
-        if (i < a.w) { fma_(accu, vk, sw[k]); fma_(accu, wk, sv[k]); }
-      }
-      if (i > 0) {
-        const T vip = a.Vp[r + (int64_t)ip * ldp];
-        T wr = mul_(tau_prev, sub_(a.y[r - j], accw));
-        fma_(wr, alpha, vip);
-        a.Wp[r + (int64_t)ip * ldp] = wr;
-        if (i < a.w) { fma_(accu, vip, sw[ip]); fma_(accu, wr, sv[ip]); }
-      }
-      if (i < a.w) {
-        const T av = sub_(a.A[r + j * lda], accu);
-        a.A[r + j * lda] = av;
-        if (r == j) a.d[j] = re(av);
-        if (r >= j + 2) sig[0] += abs2_(av);
+    // eight threads per row share the k loop (the panel columns), so that all of the grid's threads take part
+    {
+      const int kp = tid & 7;
+      const int64_t rows_per_pass = gsize >> 3;
+      for (int64_t rb = j + ((gtid - (tid & 31)) >> 3); rb < n; rb += rows_per_pass) {   // rb is warp-uniform
+        const int64_t r = rb + ((tid & 31) >> 3);
+        const bool valid = r < n;
+        T accw = zero_<T>(), accu = zero_<T>();
+        if (valid) {
+          for (int k = kp; k < ip; k += 8) {
+            const T vk = a.Vp[r + (int64_t)k * ldp], wk = a.Wp[r + (int64_t)k * ldp];
+            fma_(accw, vk, p1[k]);
+            fma_(accw, wk, p2[k]);
+            if (i < a.w) { fma_(accu, vk, sw[k]); fma_(accu, wk, sv[k]); }
+          }
+        }
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) { accw = add_(accw, shfl_xor_T(accw, o)); accu = add_(accu, shfl_xor_T(accu, o)); }
+        if (valid && kp == 0) {
+          if (i > 0) {
+            const T vip = a.Vp[r + (int64_t)ip * ldp];
+            T wr = mul_(tau_prev, sub_(a.y[r - j], accw));
+            fma_(wr, alpha, vip);
+            a.Wp[r + (int64_t)ip * ldp] = wr;
+            if (i < a.w) { fma_(accu, vip, sw[ip]); fma_(accu, wr, sv[ip]); }
+          }
+          if (i < a.w) {
+            const T av = sub_(a.A[r + j * lda], accu);
+            a.A[r + j * lda] = av;
+            if (r == j) a.d[j] = re(av);
+            if (r >= j + 2) sig[0] += abs2_(av);
+          }
+        }
       }
     }
     if (i == a.w) break;
