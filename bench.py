@@ -124,6 +124,20 @@ def cpu_matvec_sample(chi, reps=3, threads=None):
     return matvec_flops(chi, chi) / dt * 1e-12, dt
 
 
+def cpu_region_sample(chi, cutoff=0.0):
+    """Reference-equivalent CPU region step on the host cores, bounded sample: 3 H_eff matvecs (oracle optimal_map) +
+    the truncating factorisation of the (2 chi) x (2 chi) two-site tensor through the oracle's `factorize` rule
+    (LAPACK SVD for cutoff <= 1e-12, density-matrix eigen above), maxdim = chi."""
+    from oracle.tensor import Tensor, factorize, link, site
+    tf, dt_mv = cpu_matvec_sample(chi, reps=3)
+    rng = np.random.default_rng(4321)
+    theta = Tensor(rng.standard_normal((chi, D_SITE, D_SITE, chi)), [link(1, 2), site(2), site(3), link(3, 4)])
+    t0 = time.perf_counter()
+    factorize(theta, [link(1, 2), site(2)], link(2, 3), cutoff=cutoff, maxdim=chi)
+    dt_f = time.perf_counter() - t0
+    return {"chi": chi, "matvec_s": dt_mv, "factorize_s": dt_f, "region_s": 3 * dt_mv + dt_f}
+
+
 def blas_threads():
     try:
         from threadpoolctl import threadpool_info
@@ -333,6 +347,13 @@ def main():
         cpu = {"value": ctf, "unit": "TFLOP/s", "cores": cores, "kind": "port",
                "sample": f"3 H_eff matvecs at chi={args.cpu_chi} (GPU arm: chi={args.chi}), oracle restatement of optimal_map "
                          f"(NumPy/BLAS, {cores} threads); Julia reference not runnable here"}
+        if not args.no_region_step:
+            # the same bounded sample for a whole region step (3 matvecs + truncating factorisation, no environment
+            # update); both parts scale as chi^3, so x (chi / cpu_chi)^3 is the like-for-like estimate at the GPU's chi
+            cr = cpu_region_sample(args.cpu_chi, cutoff=args.cutoff)
+            cr["region_s_scaled_to_gpu_chi"] = cr["region_s"] * (args.chi / args.cpu_chi) ** 3
+            cr["note"] = "3 matvecs + oracle factorize (LAPACK) at the sample chi; scaled by (chi/cpu_chi)^3"
+            cpu["region_step"] = cr
 
     if rank == 0:
         line = {"metric": "heff_matvec_fp64_tflops", "value": tflops * (world if shard is None and world > 1 else 1),
