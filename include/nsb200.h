@@ -61,6 +61,7 @@ extern "C" {
 /* subspace expansion back-ends (src/subspace/subspace.jl:8-26) */
 #define NSB_EXPAND_NONE 0
 #define NSB_EXPAND_DENSITYMATRIX 1
+#define NSB_EXPAND_ORTHO 2 /* src/subspace/ortho_subspace.jl:19-77 (random expansion orthogonal to the current basis) */
 
 /* phase timers */
 #define NSB_T_GAUGE 0

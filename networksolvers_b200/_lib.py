@@ -13,7 +13,7 @@ NSB_OK = 0
 NSB_F64, NSB_C128 = 0, 1
 NSB_SITE, NSB_SITE_OUT = -1, -2
 NSB_SOLVER_RK, NSB_SOLVER_KRYLOV = 0, 1
-NSB_EXPAND_NONE, NSB_EXPAND_DENSITYMATRIX = 0, 1
+NSB_EXPAND_NONE, NSB_EXPAND_DENSITYMATRIX, NSB_EXPAND_ORTHO = 0, 1, 2
 NSB_NUM_TIMERS = 8
 TIMER_NAMES = ["gauge", "theta", "expand", "env", "matvec", "krylov", "factorize", "other"]
 INT64_MAX = 2**63 - 1

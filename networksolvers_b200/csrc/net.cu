@@ -645,6 +645,78 @@ static int64_t compute_expansion(int64_t current_dim, int64_t basis_size, double
   return std::max<int64_t>(0, e);
 }
 
+// "ortho" back-end (src/subspace/ortho_subspace.jl:19-77): enlarge the basis of the previous vertex by random
+// directions orthogonal to it.  Y = (1 - A A^H) rand(basis, ax), ax = expand_space(basis_size) (:4), truncated SVD of
+// Y (cutoff 1e-14, maxdim = compute_expansion) -> Ux, projected once more, A' = [A, Ux] along the bond, the centre
+// tensor and the local tensor are multiplied by the expander A'^H A.  (The reference's dispatcher cannot reach this
+// method -- it calls `subspace_expand`, the method is named `subspace_expand!` -- here "ortho" selects it.)
+template <typename T>
+bool Net<T>::expand_ortho(const nsb_trunc& trunc, const nsb_expand& ex) {
+  if (pos.empty() || pos_on_edge) return false;
+  NSB_REQUIRE(!qn_on, NSB_EUNSUPPORTED, "\"ortho\" subspace expansion is not defined for QN-conserving networks");
+  std::vector<int> prev_set;
+  for (int p : pos) if (std::find(region.begin(), region.end(), p) == region.end()) prev_set.push_back(p);
+  if (prev_set.size() != 1) return false;
+  int prev = prev_set[0];
+  std::vector<int> nexts;
+  for (int v : region) if (eid.count({v, prev})) nexts.push_back(v);
+  if (nexts.empty()) return false;
+  NSB_REQUIRE(nexts.size() == 1, NSB_EINTERNAL, "expansion: ambiguous next vertex");
+  int next = nexts[0];
+  const Label a = llink(prev, next);
+  DTensor<T> A = psi[prev];
+  const int64_t cur = A.dim_of(a), nb = A.numel() / cur;
+  const int64_t kexp = compute_expansion(cur, nb, ex.expansion_factor, ex.max_expand, trunc.maxdim);
+  const int64_t axd = std::max<int64_t>(nb + 1, (int64_t)std::floor(ex.expansion_factor * (double)nb));   // expand_space
+  if (kexp <= 0) return false;
+  const T one = from_complex<T>(1.0, 0.0), zero = zero_<T>(), mone = from_complex<T>(-1.0, 0.0);
+  std::vector<Label> basis;
+  for (Label l : A.labels) if (l != a) basis.push_back(l);
+  std::vector<Label> aorder = basis;
+  aorder.push_back(a);
+  DTensor<T> Ap = permuted(ctx, A, aorder);     // nb x cur
+  DevBuf Yb(ctx, sizeof(T) * nb * axd), tmpbuf(ctx, sizeof(T) * cur * std::max(axd, kexp + cur));
+  T* Y = (T*)Yb.ptr;
+  T* tmp = (T*)tmpbuf.ptr;
+  fill_normal<T>(ctx, Y, nb * axd, expand_seed++, 1.0);
+  auto project_out = [&](T* X, int64_t ncols) {   // X <- X - A (A^H X)
+    gemm<T>(ctx, OP_C, OP_N, cur, ncols, nb, one, Ap.data(), nb, 0, X, nb, 0, zero, tmp, cur, 0, 1);
+    gemm<T>(ctx, OP_N, OP_N, nb, ncols, cur, mone, Ap.data(), nb, 0, tmp, cur, 0, one, X, nb, 0, 1);
+  };
+  project_out(Y, axd);
+  if (vec_nrm2<T>(ctx, nb * axd, Y) <= 1e-15) return false;
+  DevBuf Ub, Cb;
+  std::vector<double> spec;
+  FactorInfo fi = factorize_left<T>(ctx, Y, nb, axd, nb, false, 1e-14, 1, kexp, false, Ub, Cb, spec);
+  const int64_t ku = fi.newdim;
+  T* U = (T*)Ub.ptr;
+  project_out(U, ku);
+  // Ax = [A, U] along a;  expander = Ax^H A
+  const int64_t nx = cur + ku;
+  std::vector<int64_t> axdims;
+  for (Label l : basis) axdims.push_back(A.dim_of(l));
+  axdims.push_back(nx);
+  DTensor<T> Ax(ctx, axdims, aorder);
+  vec_copy<T>(ctx, nb * cur, Ap.data(), Ax.data());
+  vec_copy<T>(ctx, nb * ku, U, Ax.data() + nb * cur);
+  Label aux = make_label(LK_AUX, 2);
+  DTensor<T> E(ctx, {nx, cur}, {aux, a});
+  gemm<T>(ctx, OP_C, OP_N, nx, cur, nb, one, Ax.data(), nb, 0, Ap.data(), nb, 0, zero, E.data(), nx, 0, 1);
+  auto relabel_aux = [&](DTensor<T> t) {
+    std::vector<Label> nl = t.labels;
+    for (auto& x : nl) if (x == aux) x = a;
+    return t.relabeled(nl);
+  };
+  psi[prev] = Ax;
+  canonicalize(prev);
+  ver[prev]++;
+  psi[next] = relabel_aux(contract(ctx, psi[next], E, false, false, 1));
+  canonicalize(next);
+  ver[next]++;
+  theta = relabel_aux(contract(ctx, theta, E, false, false, 1));
+  return true;
+}
+
 template <typename T>
 bool Net<T>::expand_densitymatrix(const nsb_trunc& trunc, const nsb_expand& ex) {
   if (pos.empty() || pos_on_edge) return false;
@@ -787,6 +859,9 @@ void Net<T>::extract(const int32_t* reg, int nreg, const nsb_trunc* trunc, const
   if (expand && expand->algorithm == NSB_EXPAND_DENSITYMATRIX) {
     PhaseTimer pt(ctx, NSB_T_EXPAND);
     expanded = expand_densitymatrix(tr, *expand);
+  } else if (expand && expand->algorithm == NSB_EXPAND_ORTHO) {
+    PhaseTimer pt(ctx, NSB_T_EXPAND);
+    expanded = expand_ortho(tr, *expand);
   } else if (expand && expand->algorithm != NSB_EXPAND_NONE) {
     throw Error(NSB_EUNSUPPORTED, "Subspace expansion not defined for requested subspace_algorithm");
   }

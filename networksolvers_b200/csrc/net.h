@@ -118,6 +118,8 @@ struct Net : public NetBase {
   void build_plan();
   DTensor<T> apply_heff(const DTensor<T>& x);
   bool expand_densitymatrix(const nsb_trunc& trunc, const nsb_expand& ex);
+  bool expand_ortho(const nsb_trunc& trunc, const nsb_expand& ex);
+  uint64_t expand_seed = 0x5eed0001ull;       // Philox stream of the random "ortho" expansion (advanced per call)
   DTensor<T> exp_solve(const std::function<DTensor<T>(const DTensor<T>&)>& H, std::complex<double> t, const DTensor<T>& x0,
                        int solver, const nsb_krylov* kp, int* nmv, int* lastK, int* conv, double* err);
 

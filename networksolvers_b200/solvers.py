@@ -173,10 +173,15 @@ def extracter(problem, region_iterator, *, sweep, trunc=None, subspace_algorithm
     region = current_region(region_iterator)
     expand = None
     if subspace_algorithm is not None:
-        if subspace_algorithm != "densitymatrix":
+        algs = {"densitymatrix": L.NSB_EXPAND_DENSITYMATRIX, "ortho": L.NSB_EXPAND_ORTHO}
+        if subspace_algorithm not in algs:
             raise ValueError("Subspace expansion (subspace_expand!) not defined for requested combination of "
                              "subspace_algorithm and problem types")
-        expand = dict(algorithm=L.NSB_EXPAND_DENSITYMATRIX, north_pass=north_pass,
+        # "ortho" (src/subspace/ortho_subspace.jl:19-77) is only defined for EigsolveProblem in the reference
+        if subspace_algorithm == "ortho" and not isinstance(problem, EigsolveProblem):
+            raise ValueError("Subspace expansion (subspace_expand!) not defined for requested combination of "
+                             "subspace_algorithm and problem types")
+        expand = dict(algorithm=algs[subspace_algorithm], north_pass=north_pass,
                       expansion_factor=default_expansion_factor() if expansion_factor is None else expansion_factor,
                       max_expand=min(default_max_expand() if max_expand is None else max_expand, L.INT64_MAX))
     info = problem.net.extract(region, _trunc_tuple(trunc), expand)

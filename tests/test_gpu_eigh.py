@@ -196,3 +196,47 @@ def test_tdvp_complex_with_eigh_route(eigh_route):
     po = osw.tdvp(to_oracle_ttn(H, True), to_oracle_ttn(psi0), tp, nsites=2, tdvp_order=2, updater_kwargs=dict(solver=o_rk, order=4),
                   inserter_kwargs=ik)
     assert 1 - abs(np.vdot(state_vector(po), v)) < 1e-10
+
+
+def test_ortho_expansion_backend(ctx):
+    """`subspace_algorithm="ortho"` (src/subspace/ortho_subspace.jl:19-77): random directions orthogonal to the basis
+    of the previous vertex.  The random numbers differ from the oracle's, so the checks are the properties the method
+    guarantees: the state is unchanged by an expansion, the enlarged basis stays orthonormal, the bond grows by
+    compute_expansion, and 1-site DMRG with it reaches the exact ground-state energy (which 1-site DMRG without
+    expansion cannot, starting from a product state)."""
+    import networksolvers_b200 as ns
+    from oracle.ed import ed_ground_state
+    from oracle.models import heisenberg_opsum, spin_ops
+    g = ns.path_graph(10)
+    sites = ns.siteinds("S=1/2", g)
+    H = ns.ttno(ns.heisenberg(g), sites)
+    psi0 = ns.product_state(sites, neel(g))
+    trunc = dict(cutoff=1e-12, maxdim=[4, 8, 16, 32, 32, 32])
+    ek = dict(trunc=trunc, subspace_algorithm="ortho", expansion_factor=1.5)
+    rec = SweepRecorder()
+    E, psi = ns.dmrg(H, psi0, nsweeps=6, nsites=1, extracter_kwargs=ek, inserter_kwargs=dict(trunc=trunc), sweep_callback=rec.sweep)
+    og = to_oracle_ttn(psi0).graph
+    d, ops, _ = spin_ops("S=1/2")
+    E0 = float(np.atleast_1d(ed_ground_state(heisenberg_opsum(og), og, ops)[0])[0])
+    assert abs(E - E0) < 1e-7, (rec.energies, E0)
+    assert rec.maxlinkdims[0] > 1 and max(rec.maxlinkdims) <= 32
+    host = psi.to_host()
+    v = host.to_dense()
+    assert abs(np.vdot(v, v) - 1.0) < 1e-10
+    # one expansion step leaves the state invariant and the previous vertex orthonormal
+    prob = ns.EigsolveProblem(host, H)
+    net = prob.net
+    net.extract([5, 6])
+    net.update_eigsolve()
+    net.insert((1e-12, 1, 32))
+    before = net.to_host().to_dense()
+    info = net.extract([6], (1e-12, 1, 64), dict(algorithm=2, north_pass=1, expansion_factor=1.5, max_expand=2**62))
+    after_host = net.to_host()
+    assert info.expanded == 1
+    A = np.asarray(after_host.tensors[5])
+    legs = after_host.legs[5]
+    bond = legs.index(("link", 5, 6))
+    Am = np.moveaxis(A, bond, -1).reshape(-1, A.shape[bond])
+    assert np.abs(Am.conj().T @ Am - np.eye(Am.shape[1])).max() < 1e-10
+    after = after_host.to_dense()
+    assert abs(abs(np.vdot(before, after)) - 1.0) < 1e-10 and abs(np.vdot(after, after) - 1.0) < 1e-10
