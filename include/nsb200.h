@@ -26,6 +26,9 @@
  *                        ApplyExpProblem construction: permute_indices + itn.ProjTTN)
  *   nsb_maxlinkdim       itn.maxlinkdim in the sweep printers src/eigsolve.jl:39, src/applyexp.jl:56
  *   nsb_range_finder     src/sketched_linear_algebra/range_finder.jl:6-64
+ *   nsb_fit_target_upload / nsb_update_fit
+ *                        src/fitting.jl:25-49 (FittingProblem extracter / updater: region environment of the
+ *                        overlap network <psi| A |x>, overlap n / sqrt(n))
  */
 #ifndef NSB200_H
 #define NSB200_H
@@ -208,6 +211,17 @@ int nsb_update_exp(nsb_net* net, double t_re, double t_im, int32_t solver, const
                    nsb_solve_info* info);
 int nsb_insert(nsb_net* net, const nsb_trunc* trunc /* inserter's */, int32_t normalize, int32_t set_ortho,
                nsb_insert_info* info);
+
+/* ---- fitting (src/fitting.jl) ----------------------------------------------------------------
+ * Uploading a target tensor for every vertex switches the network to fitting mode: the ket layer of the
+ * environments is the fixed target |x> (own link dimensions), the operator layer the uploaded operator (an identity
+ * network with links of dimension 1 for itn.truncate), the bra layer the state being fitted.  nsb_extract then leaves
+ * the region environment -- the optimal new region tensor -- as the local tensor (src/fitting.jl:25-40),
+ * nsb_update_fit returns the overlap n / sqrt(n) (:42-49), nsb_insert writes it back (normalize = 1,
+ * set_ortho = 0 as in src/fitting.jl:78). */
+int nsb_fit_target_upload(nsb_net* net, int32_t v, int32_t rank, const int32_t* legs /* 2*rank */,
+                          const int64_t* dims, const void* host);
+int nsb_update_fit(nsb_net* net, double* overlap);
 
 /* ---- pieces exposed for tests and benchmarks ---------------------------------------------- */
 int nsb_local_info(nsb_net* net, int32_t* rank, int32_t* legs /* cap 2*16 */, int64_t* dims /* cap 16 */);

@@ -94,6 +94,8 @@ SIGNATURES = {
     "nsb_network_create": (C.c_int, [_vp, _i32, P(_i32), _i32, P(_i64), _i32, P(_vp)]),
     "nsb_network_destroy": (C.c_int, [_vp]),
     "nsb_site_upload": (C.c_int, [_vp, _i32, _i32, P(_i32), P(_i64), _vp]),
+    "nsb_fit_target_upload": (C.c_int, [_vp, _i32, _i32, P(_i32), P(_i64), _vp]),
+    "nsb_update_fit": (C.c_int, [_vp, P(_dbl)]),
     "nsb_site_info": (C.c_int, [_vp, _i32, P(_i32), P(_i32), P(_i64)]),
     "nsb_site_download": (C.c_int, [_vp, _i32, _vp]),
     "nsb_site_fill_random": (C.c_int, [_vp, _i32, _i32, P(_i32), P(_i64), C.c_uint64, _dbl]),

@@ -359,6 +359,12 @@ int nsb_update_exp(nsb_net* net, double t_re, double t_im, int32_t solver, const
                    int32_t next_vertex, nsb_solve_info* info) {
   NET_CALL(net, net->n->update_exp(t_re, t_im, solver, params, nsites, next_vertex, info))
 }
+int nsb_fit_target_upload(nsb_net* net, int32_t v, int32_t rank, const int32_t* legs, const int64_t* dims, const void* host) {
+  NET_CALL(net, NSB_REQUIRE(legs && dims && host && rank >= 1 && rank <= MAX_RANK, NSB_EINVAL, "bad arguments"); net->n->fit_target_upload(v, rank, legs, dims, host))
+}
+int nsb_update_fit(nsb_net* net, double* overlap) {
+  NET_CALL(net, NSB_REQUIRE(overlap, NSB_EINVAL, "null overlap"); *overlap = net->n->update_fit())
+}
 int nsb_insert(nsb_net* net, const nsb_trunc* trunc, int32_t normalize, int32_t set_ortho, nsb_insert_info* info) {
   NET_CALL(net, net->n->insert(trunc, normalize, set_ortho, info))
 }

@@ -381,7 +381,7 @@ std::vector<Label> Net<T>::w_out_labels(const DTensor<T>& X, const DTensor<T>& W
       continue;
     }
     out.push_back(lab);
-    if (label_kind(lab) == LK_LINK && label_plev(lab) == 0) {
+    if (label_kind(lab) == LK_LINK && (label_plev(lab) == 0 || label_plev(lab) == 2)) {
       Label ol = make_label(LK_OP, label_id(lab), 0);
       if (Wv.find(ol) >= 0 && is_new(ol) && !placed(ol)) out.push_back(ol);
     }
@@ -409,7 +409,8 @@ int Net<T>::make_env(int u, int v) {
   for (int n : adj[u]) if (n != v) others.push_back(n);
   for (int n : others) built += make_env(n, u);
   NSB_REQUIRE(psi[u].valid() && W[u].valid(), NSB_EINVAL, "make_env: state or operator tensor missing");
-  DTensor<T> X = psi[u];
+  NSB_REQUIRE(!fit_mode || xket[u].valid(), NSB_EINVAL, "make_env: fitting target tensor missing");
+  DTensor<T> X = fit_mode ? xket[u] : psi[u];
   size_t start = 0;
   if (!others.empty()) { X = contract(ctx, X, envs.at({others[0], u}).t, false, false, 1); start = 1; }
   {
@@ -419,7 +420,7 @@ int Net<T>::make_env(int u, int v) {
   }
   for (size_t i = start; i < others.size(); ++i) X = contract(ctx, X, envs.at({others[i], u}).t, false, false, 1);
   DTensor<T> bra = psi[u].primed();
-  std::vector<Label> want{llink(u, v, 0), lop(u, v), llink(u, v, 1)};
+  std::vector<Label> want{fit_mode ? lxlink(u, v) : llink(u, v, 0), lop(u, v), llink(u, v, 1)};
   std::vector<Label> l1, l2;
   bool d1 = contract_direct_labels(bra, X, &l1), d2 = contract_direct_labels(X, bra, &l2);
   DTensor<T> E;
@@ -595,9 +596,51 @@ DTensor<T> Net<T>::apply_heff(const DTensor<T>& x) {
     else X = apply_small(ctx, s.op, X, s.Wm, merged_out_labels(X, s.u, s.v));
   }
   X = X.noprime();
-  if (X.labels != x.labels) X = permuted(ctx, X, x.labels);
+  if (!fit_mode && X.labels != x.labels) X = permuted(ctx, X, x.labels);   // (fitting: the result lives on psi's links)
   ctx->cnt.matvecs++;
   return X;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fitting (src/fitting.jl)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+void Net<T>::fit_target_upload(int v, int rank, const int32_t* legs, const int64_t* dims, const void* host) {
+  NSB_REQUIRE(v >= 0 && v < nverts, NSB_EINVAL, "fit_target_upload: bad vertex");
+  NSB_REQUIRE(!qn_on, NSB_EUNSUPPORTED, "fitting is not defined for QN-conserving networks");
+  std::vector<Label> labels = decode_legs(rank, legs, false);
+  {
+    std::vector<Label> a = labels, b = canonical_labels(v);
+    std::sort(a.begin(), a.end()); std::sort(b.begin(), b.end());
+    NSB_REQUIRE(a == b, NSB_EINVAL, "fit_target_upload: legs must be the site index and one link per neighbour");
+  }
+  for (auto& l : labels) if (label_kind(l) == LK_LINK) l = label_setplev(l, 2);
+  std::vector<int64_t> d(dims, dims + rank);
+  DTensor<T> t(ctx, d, labels);
+  NSB_CUDA(cudaMemcpyAsync(t.data(), host, sizeof(T) * t.numel(), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->sync();
+  if ((int)xket.size() != nverts) xket.assign(nverts, DTensor<T>());
+  xket[v] = t;
+  fit_mode = true;
+  shard_enabled = false;
+  envs.clear();
+  plan.clear();
+}
+
+// Region environment of the overlap network <psi| A |x>: the target's region tensors pushed through the plan
+// (environments built with x as the ket layer and conj(psi) as the bra layer, the operator in between).
+template <typename T>
+DTensor<T> Net<T>::fit_local() {
+  NSB_REQUIRE(!pos.empty() && !pos_on_edge, NSB_EINVAL, "fitting: region must be one or two vertices");
+  DTensor<T> x = xket[pos[0]];
+  for (size_t i = 1; i < pos.size(); ++i) x = contract(ctx, x, xket[pos[i]], false, false, 1);
+  return apply_heff(x);
+}
+
+template <typename T>
+double Net<T>::update_fit() {
+  NSB_REQUIRE(fit_mode && theta.valid(), NSB_EINVAL, "update_fit: upload a fitting target and call nsb_extract first");
+  return vec_nrm2<T>(ctx, theta.numel(), theta.data());   // n / sqrt(n), n = <local|local> (src/fitting.jl:43-44)
 }
 
 template <typename T>
@@ -870,6 +913,10 @@ void Net<T>::extract(const int32_t* reg, int nreg, const nsb_trunc* trunc, const
     built = position(r);
   }
   shard_prepare();
+  if (fit_mode) {
+    PhaseTimer pt(ctx, NSB_T_MATVEC);
+    theta = fit_local();
+  }
   if (info) {
     info->expanded = expanded ? 1 : 0;
     info->env_builds = built;

@@ -32,6 +32,8 @@ struct NetBase {
   virtual void update_eigsolve(const nsb_krylov* params, double* eigval, nsb_solve_info* info) = 0;
   virtual void update_exp(double tre, double tim, int solver, const nsb_krylov* params, int nsites, int next_vertex, nsb_solve_info* info) = 0;
   virtual void insert(const nsb_trunc* trunc, int normalize, int set_ortho, nsb_insert_info* info) = 0;
+  virtual void fit_target_upload(int v, int rank, const int32_t* legs, const int64_t* dims, const void* host) = 0;
+  virtual double update_fit() = 0;
   virtual void local_info(int32_t* rank, int32_t* legs, int64_t* dims) = 0;
   virtual void local_download(void* host) = 0;
   virtual void local_upload(const void* host) = 0;
@@ -93,6 +95,13 @@ struct Net : public NetBase {
 
   Net(Ctx* c, int nv, const int32_t* e, int ne, const int64_t* sd);
 
+  // fitting mode (src/fitting.jl): the ket layer of the environments is the fixed target network x, whose links
+  // carry prime level 2 (0 = ket links of psi, 1 = bra links of psi)
+  bool fit_mode = false;
+  std::vector<DTensor<T>> xket;
+  Label lxlink(int u, int v) const { return make_label(LK_LINK, eid.at({u, v}), 2); }
+  DTensor<T> fit_local();
+
   // labels
   Label lsite(int v, int p = 0) const { return make_label(LK_SITE, v, p); }
   Label llink(int u, int v, int p = 0) const { return make_label(LK_LINK, eid.at({u, v}), p); }
@@ -139,6 +148,8 @@ struct Net : public NetBase {
   void update_eigsolve(const nsb_krylov* params, double* eigval, nsb_solve_info* info) override;
   void update_exp(double tre, double tim, int solver, const nsb_krylov* params, int nsites, int next_vertex, nsb_solve_info* info) override;
   void insert(const nsb_trunc* trunc, int normalize, int set_ortho, nsb_insert_info* info) override;
+  void fit_target_upload(int v, int rank, const int32_t* legs, const int64_t* dims, const void* host) override;
+  double update_fit() override;
   void local_info(int32_t* rank, int32_t* legs, int64_t* dims) override;
   void local_download(void* host) override;
   void local_upload(const void* host) override;

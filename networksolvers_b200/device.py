@@ -288,6 +288,21 @@ class DeviceNetwork:
         self.ctx.check(fn(self.handle, self.vid[v], a.ndim, enc.ctypes.data_as(C.POINTER(C.c_int32)),
                           dims.ctypes.data_as(C.POINTER(C.c_int64)), a.ctypes.data))
 
+    # ---- fitting (src/fitting.jl) -------------------------------------------------------------
+    def set_fit_target(self, target: HostTTN):
+        """Upload the target network |x> (own link dimensions) and switch the network to fitting mode."""
+        for v in self.verts:
+            a = np.asfortranarray(target.tensors[v], dtype=self.dtype)
+            enc = self._encode(target.legs[v])
+            dims = np.array(a.shape, dtype=np.int64)
+            self.ctx.check(self._lib.nsb_fit_target_upload(self.handle, self.vid[v], a.ndim, enc.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                            dims.ctypes.data_as(C.POINTER(C.c_int64)), a.ctypes.data))
+
+    def update_fit(self):
+        ov = C.c_double()
+        self.ctx.check(self._lib.nsb_update_fit(self.handle, C.byref(ov)))
+        return ov.value
+
     def fill_random(self, v, dims_by_leg, seed, scale):
         legs = canonical_legs(self.graph, v)
         enc = self._encode(legs)

@@ -51,6 +51,19 @@ class SiteType:
         return self.ops[name]
 
 
+class GraphSites:
+    """Site dimensions of an existing network (graph + uniform physical dimension), for constructors that only need
+    `.graph` and `.dim`."""
+
+    def __init__(self, graph, dim):
+        self.graph, self.dim = graph, int(dim)
+
+    @classmethod
+    def of(cls, tn):
+        v = tn.graph.vertices[0]
+        return cls(tn.graph, tn.tensors[v].shape[tn.legs[v].index(("site", v))])
+
+
 class SiteSet:
     """`siteinds(site_type, graph)`."""
 
@@ -286,3 +299,47 @@ def ttno(opsum: OpSum, sites: SiteSet, root=None, dtype=float):
 
 
 mpo = ttno
+
+
+# ---- fitting helpers (src/fitting.jl:90-112) -----------------------------------------------------------------
+def identity_operator(sites: SiteSet, dtype=float):
+    """Operator network acting as the identity, every operator link of dimension 1 (the overlap network <psi|x> of
+    `itn.truncate` has no operator layer)."""
+    g = sites.graph
+    d = sites.dim
+    tensors, legs = {}, {}
+    for v in g.vertices:
+        nb = g.neighbors(v)
+        legs[v] = [("site", v), ("site_out", v)] + [("link", v, n) for n in nb]
+        tensors[v] = np.eye(d, dtype=dtype).reshape([d, d] + [1] * len(nb))
+    return HostTTN(g, tensors, legs, ortho_region=[], site_dim=d)
+
+
+def delta_state(sites: SiteSet, link_space, dtype=float):
+    """`ITensorNetwork(v -> inds -> delta(inds), siteinds; link_space)` (src/fitting.jl:91-93, :106-108)."""
+    g = sites.graph
+    d = sites.dim
+    tensors, legs = {}, {}
+    for v in g.vertices:
+        lg = canonical_legs(g, v)
+        shape = [d if l[0] == "site" else int(link_space) for l in lg]
+        t = np.zeros(shape, dtype=dtype)
+        for i in range(min(shape)):
+            t[(i,) * len(shape)] = 1.0
+        tensors[v], legs[v] = t, lg
+    return HostTTN(g, tensors, legs, ortho_region=list(g.vertices), site_dim=d)
+
+
+def random_tensornetwork(sites: SiteSet, link_space, rng, dtype=float):
+    """`itn.random_tensornetwork(rng, elt, s; link_space)`: i.i.d. normal entries, uniform link dimension, no gauge."""
+    g = sites.graph
+    d = sites.dim
+    tensors, legs = {}, {}
+    for v in g.vertices:
+        lg = canonical_legs(g, v)
+        shape = [d if l[0] == "site" else int(link_space) for l in lg]
+        t = rng.standard_normal(shape)
+        if np.issubdtype(np.dtype(dtype), np.complexfloating):
+            t = t + 1j * rng.standard_normal(shape)
+        tensors[v], legs[v] = t.astype(dtype), lg
+    return HostTTN(g, tensors, legs, ortho_region=list(g.vertices), site_dim=d)

@@ -150,6 +150,25 @@ class ApplyExpProblem(_Problem):
         return self.net
 
 
+class FittingProblem(_Problem):
+    """src/fitting.jl:8-18.  The ket being fitted is the network's state; the target |x> and the operator A of the
+    overlap network <psi| A |x> are resident on the device (DeviceNetwork.set_fit_target)."""
+
+    def __init__(self, state=None, target=None, operator=None, overlap=0.0, *, net=None, ctx=None, dtype=None):
+        if net is None:
+            net = DeviceNetwork(operator, state, dtype=dtype, ctx=ctx)
+            net.set_fit_target(target)
+        self.net = net
+        self.overlap = overlap
+        self.last_truncerr = 0.0
+        self.last_info = {}
+
+    @property
+    def state(self):
+        return DeviceState(self.net)
+
+
+overlap = lambda F: F.overlap
 eigenvalue = lambda E: E.eigenvalue
 state = lambda P: P.state
 operator = lambda P: P.operator
@@ -184,6 +203,8 @@ def extracter(problem, region_iterator, *, sweep, trunc=None, subspace_algorithm
         expand = dict(algorithm=algs[subspace_algorithm], north_pass=north_pass,
                       expansion_factor=default_expansion_factor() if expansion_factor is None else expansion_factor,
                       max_expand=min(default_max_expand() if max_expand is None else max_expand, L.INT64_MAX))
+    if isinstance(problem, FittingProblem):
+        expand = None        # src/fitting.jl:38: the expansion call is commented out in the reference
     info = problem.net.extract(region, _trunc_tuple(trunc), expand)
     problem.last_info = dict(expanded=info.expanded, env_builds=info.env_builds, qr_steps=info.qr_steps)
     return problem, LocalState(problem.net)
@@ -194,6 +215,8 @@ def updater(problem, local_state, region_iterator, **kws):
         return _updater_eigsolve(problem, local_state, region_iterator, **kws)
     if isinstance(problem, ApplyExpProblem):
         return _updater_applyexp(problem, local_state, region_iterator, **kws)
+    if isinstance(problem, FittingProblem):
+        return _updater_fitting(problem, local_state, region_iterator, **kws)
     raise TypeError(f"no updater for {type(problem).__name__}")
 
 
@@ -230,6 +253,14 @@ def _updater_applyexp(T, local_state, region_iterator, *, nsites, time_step, sol
     T = T.setproperties(current_time=T.current_time + time_step)
     T.last_info = dict(T.last_info, nmatvec=info.nmatvec)
     return T, local_state
+
+
+def _updater_fitting(F, local_state, region_iterator, *, outputlevel, **kws):
+    """src/fitting.jl:42-49: overlap = n / sqrt(n), n = <local|local>."""
+    F = F.setproperties(overlap=F.net.update_fit())
+    if outputlevel >= 2:
+        print("  Region %s: squared overlap = %.12f" % (current_region(region_iterator), F.overlap))
+    return F, local_state
 
 
 def inserter(problem, local_tensor, region_iterator, *, normalize=False, set_orthogonal_region=True, sweep,
@@ -397,6 +428,40 @@ def applyexp(*args, extracter_kwargs=None, updater_kwargs=None, inserter_kwargs=
     sweep_iter = sweep_iterator(init_prob, kws_array)
     prob = sweep_solve(sweep_iter, outputlevel=outputlevel, sweep_printer=sweep_printer, **kws)
     return prob.state
+
+
+# ---- fitting (src/fitting.jl:55-112) ---------------------------------------------------------------------------
+def fit_tensornetwork(target, operator, init_state, *, nsweeps=25, nsites=1, outputlevel=0, extracter_kwargs=None,
+                      updater_kwargs=None, inserter_kwargs=None, normalize=True, ctx=None, dtype=None, **kws):
+    """Fit `init_state` to operator |target> by sweeping (src/fitting.jl:55-84).  The reference builds the overlap
+    network with `itn.inner_network`; here its three layers are passed separately (operator=None: identity)."""
+    from .models import identity_operator, GraphSites
+    if dtype is None:
+        dtype = np.result_type(target.dtype(), init_state.dtype(), *([operator.dtype()] if operator is not None else []))
+        dtype = np.complex128 if np.issubdtype(dtype, np.complexfloating) else np.float64
+    if operator is None:
+        operator = identity_operator(GraphSites.of(init_state), dtype)
+    prob = FittingProblem(state=init_state, target=target, operator=operator, ctx=ctx, dtype=dtype)
+    ik = dict(inserter_kwargs or {}, normalize=normalize, set_orthogonal_region=False)
+    sweep_iter = sweep_iterator(prob, nsweeps, nsites=nsites, outputlevel=outputlevel,
+                                extracter_kwargs=extracter_kwargs or {}, updater_kwargs=updater_kwargs or {}, inserter_kwargs=ik)
+    conv = sweep_solve(sweep_iter, outputlevel=outputlevel, **kws)
+    return conv.state
+
+
+def truncate(tn, *, maxdim, cutoff=0.0, **kws):
+    """`itn.truncate(tn; maxdim, cutoff)` (src/fitting.jl:90-97): fit a delta-initialised network of link dimension
+    maxdim to tn."""
+    from .models import delta_state, GraphSites
+    init = delta_state(GraphSites.of(tn), maxdim, tn.dtype())
+    return fit_tensornetwork(tn, None, init, inserter_kwargs=dict(trunc=dict(cutoff=cutoff, maxdim=maxdim)), **kws)
+
+
+def apply(A, x, *, maxdim, cutoff=0.0, **kws):
+    """`itn.apply(A, x; maxdim, cutoff)` (src/fitting.jl:99-112): fit to A|x>."""
+    from .models import delta_state, GraphSites
+    init = delta_state(GraphSites.of(x), maxdim, np.result_type(A.dtype(), x.dtype()))
+    return fit_tensornetwork(x, A, init, inserter_kwargs=dict(trunc=dict(cutoff=cutoff, maxdim=maxdim)), **kws)
 
 
 def process_real_times(z):

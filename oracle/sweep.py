@@ -80,6 +80,9 @@ def region_plan(problem, **kws):
         nsites = kws.pop("nsites")
         time_step = kws.pop("time_step")
         return rp.tdvp_regions(problem.state.graph, time_step, nsites=nsites, **kws)
+    if _is_fitting(problem):
+        from . import fitting
+        return fitting.region_plan(problem, **kws)       # src/fitting.jl:51-53
     return rp.euler_sweep(problem.state.graph, **kws)
 
 
@@ -104,8 +107,16 @@ def region_iterator_action(problem, region_iter, *, extracter_kwargs=None, updat
 COUNTERS = {}
 
 
+def _is_fitting(problem):
+    from .fitting import FittingProblem
+    return isinstance(problem, FittingProblem)
+
+
 def extracter(problem, region_iter, *, sweep, trunc=None, **kws):
-    """src/extracter.jl:3-17."""
+    """src/extracter.jl:3-17 (and the FittingProblem method, src/fitting.jl:25-40)."""
+    if _is_fitting(problem):
+        from . import fitting
+        return fitting.extracter(problem, region_iter, sweep=sweep, **kws)
     trunc = truncation_parameters(sweep, **(trunc or {}))
     region = region_iter.current_region()
     psi = orthogonalize(problem.state, region)
@@ -169,6 +180,9 @@ def _factorize_qn(psi, theta, a, b, left, *, cutoff, mindim, maxdim):
 
 
 def updater(problem, local_state, region_iter, **kws):
+    if _is_fitting(problem):
+        from . import fitting
+        return fitting.updater(problem, local_state, region_iter, **kws)
     if isinstance(problem, EigsolveProblem):
         return _updater_eigsolve(problem, local_state, region_iter, **kws)
     return _updater_applyexp(problem, local_state, region_iter, **kws)
