@@ -343,3 +343,26 @@ def random_tensornetwork(sites: SiteSet, link_space, rng, dtype=float):
             t = t + 1j * rng.standard_normal(shape)
         tensors[v], legs[v] = t.astype(dtype), lg
     return HostTTN(g, tensors, legs, ortho_region=list(g.vertices), site_dim=d)
+
+
+def product_operator_sum(sites: SiteSet, terms, dtype=float):
+    """Operator network of sum_k c_k prod_v op_k(v) for arbitrary (not only neighbouring) supports: every operator link
+    has one state per term.  `terms` = [(coef, {vertex: op name, ...}), ...].  Used where the reference builds
+    `itn.ttn(opsum, sites)` with long-range terms (test/fitting/fitting_regression_test.jl:47-50)."""
+    g = sites.graph
+    d, op = sites.dim, sites.type.op
+    nt = len(terms)
+    root = g.vertices[0]
+    tensors, legs = {}, {}
+    for v in g.vertices:
+        nb = g.neighbors(v)
+        legs[v] = [("site", v), ("site_out", v)] + [("link", v, n) for n in nb]
+        t = np.zeros([d, d] + [nt] * len(nb), dtype=dtype)
+        for k, (c, ops) in enumerate(terms):
+            m = op(ops[v]) if v in ops else np.eye(d)
+            if v == root:
+                m = c * m
+            # site legs are (in, out): <out| m |in>
+            t[(slice(None), slice(None)) + (k,) * len(nb)] = np.asarray(m, dtype=dtype).T
+        tensors[v] = t
+    return HostTTN(g, tensors, legs, ortho_region=[], site_dim=d)

@@ -76,10 +76,7 @@ def test_fitting_regression_apply_on_dmrg_state():
     trunc = dict(maxdim=50, cutoff=1e-5)
     E, psi = ns.dmrg(H, psi0, nsweeps=5, nsites=2, extracter_kwargs=dict(trunc=trunc), inserter_kwargs=dict(trunc=trunc))
     psi = psi.to_host()
-    terms = ns.OpSum()
-    terms.add(1.0, "S+", 3, "S-", 5)
-    terms.add(1.0, "S-", 3, "S+", 5)
-    O = ns.ttno(terms, s)
+    O = ns.product_operator_sum(s, [(1.0, {3: "S+", 5: "S-"}), (1.0, {3: "S-", 5: "S+"})])
     Opsi = ns.apply(O, psi, maxdim=60, nsites=2, normalize=False).to_host()
     v = psi.to_dense()
     f = np.vdot(Opsi.to_dense(), v) / np.vdot(v, _dense_op(O) @ v)
