@@ -193,6 +193,7 @@ def main():
     ap.add_argument("--fused", action="store_true", help="multi-GPU: fused GEMM + peer-store reduce-scatter epilogue instead of the "
                     "NCCL all-reduce (correct but slower in round 1: the DMMA fragment layout issues 64-byte P2P stores)")
     ap.add_argument("--no-region-step", action="store_true", help="skip the full region steps (extract + 3-matvec Lanczos + truncating insert)")
+    ap.add_argument("--full-sweep", action="store_true", help="also run one real 2-site DMRG sweep over all regions (minutes at chi=4096)")
     ap.add_argument("--region-steps", type=int, default=3, help="consecutive region steps timed after the matvec benchmark")
     ap.add_argument("--cutoff", type=float, default=0.0, help="inserter cutoff of the region steps (0: maxdim-limited, SVD-route label; "
                     "1e-9: the reference's timed_dmrg setting, eigen-route label)")
@@ -338,6 +339,32 @@ def main():
         extra["sweep_s_extrapolated"] = extra["region_step_s"] * 2 * (args.nsites - 1)
         if world > 1:
             extra["region_parallelism"] = "H_eff applications sharded + NCCL all-reduce; environment update and factorisation replicated"
+        ctx.enable_timers(False)
+
+    if args.full_sweep and world == 1:
+        # One real 2-site DMRG sweep (all 2 (N - 1) regions of the Euler tour) through the public driver on a fresh
+        # synthetic state whose centre flag sits on the tour's first region (no long gauge walk before the sweep).
+        net.close()   # 95 GB of tensors and environments go back to the pool before the second network is built
+        g = ns.path_graph(args.nsites)
+        sites = ns.siteinds("S=1/2", g)
+        H = ns.ttno(ns.heisenberg(g), sites)
+        plan = ns.euler_sweep(g, nsites=2)
+        first = list(plan[0][0])
+        net2 = ns.DeviceNetwork.synthetic(H, sites, args.chi, seed=1234, ctx=ctx, ortho_region=first)
+        prob = ns.EigsolveProblem(net=net2)
+        ctx.enable_timers(True)
+        ctx.reset_timers()
+        ctx.reset_counters()
+        ctx.synchronize()
+        t0 = time.perf_counter()
+        tr = dict(cutoff=args.cutoff, maxdim=args.chi)
+        E, _ = ns.dmrg(prob, nsweeps=1, nsites=2, inserter_kwargs=dict(trunc=tr))
+        ctx.synchronize()
+        extra["full_sweep_s"] = time.perf_counter() - t0
+        extra["full_sweep_regions"] = len(plan)
+        extra["full_sweep_phase_ms"] = ctx.timers()
+        extra["full_sweep_launches"] = int(ctx.counters()["kernel_launches"])
+        extra["full_sweep_maxlinkdim"] = int(net2.maxlinkdim())
         ctx.enable_timers(False)
 
     cpu = None
