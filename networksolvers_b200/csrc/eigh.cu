@@ -21,7 +21,7 @@ int g_eigh_min_n = 1024;
 int g_eigh_nb = 64;
 int g_eigh_coop = 1;    // tridiagonalisation panels as one cooperative kernel (2 grid barriers per column); 0: five launches per column
 int g_eigh_coop_ctas = 3;   // CTAs per SM of the cooperative panel kernel
-int g_eigh_wb = 256;   // reflectors per compact-WY block of the back-transformation (<= 256)
+int g_eigh_wb = 128;   // reflectors per compact-WY block of the back-transformation (T factor in shared memory: <= 160 real, <= 96 complex)
 
 #define LAUNCH_CHECK(ctx) do { (ctx)->cnt.kernel_launches++; NSB_CUDA(cudaGetLastError()); } while (0)
 
@@ -445,19 +445,28 @@ __global__ void trd_last_diag_kernel(const T* __restrict__ A, int64_t lda, int64
 template <typename T>
 __global__ void __launch_bounds__(256) larft_kernel(const T* __restrict__ S /* V^H V, w x w */, int w, const T* __restrict__ tau,
                                                     T* __restrict__ Tm /* w x w */) {
-  for (int e = threadIdx.x; e < w * w; e += blockDim.x) Tm[e] = zero_<T>();
+  // T lives in shared memory (w x w), column i of S is staged per step; thread r owns row r of T
+  extern __shared__ __align__(16) char larft_sm[];
+  T* Ts = reinterpret_cast<T*>(larft_sm);
+  T* sc = Ts + (size_t)w * w;
+  for (int e = threadIdx.x; e < w * w; e += blockDim.x) Ts[e] = zero_<T>();
   __syncthreads();
   for (int i = 0; i < w; ++i) {
-    const int r = threadIdx.x;
-    if (r < i) {
-      T acc = zero_<T>();
-      for (int k = r; k < i; ++k) fma_(acc, Tm[r + k * w], S[k + i * w]);
-      Tm[r + i * w] = mul_(neg_(tau[i]), acc);
-    } else if (r == i) {
-      Tm[i + i * w] = tau[i];
+    for (int k = threadIdx.x; k < i; k += blockDim.x) sc[k] = S[k + i * w];
+    __syncthreads();
+    const T ti = tau[i];
+    for (int r = threadIdx.x; r <= i; r += blockDim.x) {
+      if (r < i) {
+        T acc = zero_<T>();
+        for (int k = r; k < i; ++k) fma_(acc, Ts[r + k * w], sc[k]);
+        Ts[r + i * w] = mul_(neg_(ti), acc);
+      } else {
+        Ts[i + i * w] = ti;
+      }
     }
     __syncthreads();
   }
+  for (int e = threadIdx.x; e < w * w; e += blockDim.x) Tm[e] = Ts[e];
 }
 
 template <typename T>
@@ -526,11 +535,101 @@ __global__ void __launch_bounds__(256) dc_rot_kernel(double* __restrict__ Zb, in
   }
 }
 
-// one thread per root: Dt[i + j ldt] = d_j - lambda_i
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// dc::secular_root (dc_secular.h) with the sums over the poles split across the 32 lanes of a warp; the scalar
+// iteration (bracket, two-pole rational step, bisection safeguard, stopping rule) is identical and executed
+// redundantly by every lane (the butterfly sums are bitwise equal in all lanes).
+__device__ double secular_root_warp(int K, int i, const double* __restrict__ d, const double* __restrict__ z2, double rho,
+                                    double* __restrict__ delta, int64_t stride) {
+  const int lane = threadIdx.x & 31;
+  if (K == 1) {
+    const double tau = rho * z2[0];
+    if (lane == 0) delta[0] = -tau;
+    return d[0] + tau;
+  }
+  const bool last = (i == K - 1);
+  int org;
+  double lo, hi, tau;
+  bool done = false;
+  if (last) {
+    org = K - 1;
+    double sz = 0.0;
+    for (int j = lane; j < K; j += 32) sz += z2[j];
+    sz = warp_sum(sz);
+    lo = 0.0;
+    hi = rho * sz;
+    tau = 0.5 * hi;
+  } else {
+    const double gap = d[i + 1] - d[i], half = 0.5 * gap, di = d[i];
+    double f = 0.0;
+    for (int j = lane; j < K; j += 32) f += z2[j] / ((d[j] - di) - half);
+    f = 1.0 + rho * warp_sum(f);
+    if (f > 0.0) { org = i; lo = 0.0; hi = half; }
+    else { org = i + 1; lo = -half; hi = 0.0; }
+    tau = 0.5 * (lo + hi);
+    if (f == 0.0) { tau = -half; done = true; }
+  }
+  const double dorg = d[org];
+  const int ip = last ? K - 2 : i;
+  for (int it = 0; !done && it < 100; ++it) {
+    double psi = 0.0, phi = 0.0, dpsi = 0.0, dphi = 0.0;
+    for (int j = lane; j < K; j += 32) {
+      const double dl = (d[j] - dorg) - tau, t = z2[j] / dl, t2 = t / dl;
+      if (j <= ip) { psi += t; dpsi += t2; } else { phi += t; dphi += t2; }
+    }
+    psi = rho * warp_sum(psi); phi = rho * warp_sum(phi); dpsi = rho * warp_sum(dpsi); dphi = rho * warp_sum(dphi);
+    const double g = 1.0 + psi + phi;
+    const double erretm = 1.0 + fabs(psi) + fabs(phi);
+    if (fabs(g) <= 4.0 * dc::DC_EPS * erretm) break;
+    if (g > 0.0) hi = tau; else lo = tau;
+    const double dA = (d[ip] - dorg) - tau, dB = (d[ip + 1] - dorg) - tau;
+    const double S = dpsi * dA * dA, s_ = psi - dpsi * dA;
+    const double R = dphi * dB * dB, r_ = phi - dphi * dB;
+    const double c0 = 1.0 + s_ + r_;
+    const double a = c0;
+    const double b = -(c0 * (dA + dB) + S + R);
+    const double cc = c0 * dA * dB + S * dB + R * dA;
+    double tn = 0.0;
+    bool ok = false;
+    if (a == 0.0) {
+      if (b != 0.0) { tn = tau - cc / b; ok = (tn > lo && tn < hi); }
+    } else {
+      const double disc = b * b - 4.0 * a * cc;
+      if (disc >= 0.0) {
+        const double sq = sqrt(disc);
+        const double q = -0.5 * (b + (b >= 0.0 ? sq : -sq));
+        if (q != 0.0) { tn = tau + cc / q; ok = (tn > lo && tn < hi); }
+        if (!ok) { tn = tau + q / a; ok = (tn > lo && tn < hi); }
+      }
+    }
+    if (!ok) tn = 0.5 * (lo + hi);
+    const double width = hi - lo, big = fmax(fabs(lo), fabs(hi));
+    const bool stuck = (tn == tau) || (width <= 2.0 * dc::DC_EPS * big);
+    tau = tn;
+    if (stuck) break;
+  }
+  for (int j = lane; j < K; j += 32) delta[(int64_t)j * stride] = (d[j] - dorg) - tau;
+  return dorg + tau;
+}
+
+// Dt[i + j ldt] = d_j - lambda_i.  Small problems: one thread per root (the shared host/device function);
+// large ones: one warp per root.
 __global__ void __launch_bounds__(128) dc_secular_kernel(int K, const double* __restrict__ dl, const double* __restrict__ z2,
                                                          double rho, double* __restrict__ Dt, int64_t ldt, double* __restrict__ lam) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < K) lam[i] = dc::secular_root(K, i, dl, z2, rho, Dt + i, ldt);
+}
+__global__ void __launch_bounds__(128) dc_secular_warp_kernel(int K, const double* __restrict__ dl, const double* __restrict__ z2,
+                                                              double rho, double* __restrict__ Dt, int64_t ldt, double* __restrict__ lam) {
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // warp-uniform
+  if (i >= K) return;
+  const double l = secular_root_warp(K, i, dl, z2, rho, Dt + i, ldt);
+  if ((threadIdx.x & 31) == 0) lam[i] = l;
 }
 
 // Gu-Eisenstat: zhat_j = sign(z_j) sqrt( -prod_i (d_j - lam_i) / prod_{i != j} (d_j - d_i) ), one CTA per j
@@ -554,16 +653,27 @@ __global__ void __launch_bounds__(128) dc_zhat_kernel(int K, const double* __res
   }
 }
 
-__global__ void __launch_bounds__(128) dc_vecnorm_kernel(int K, const double* __restrict__ Dt, int64_t ldt, const double* __restrict__ zh,
+// invn[i] = 1 / || zhat_j / (d_j - lam_i) ||_j : tiles of 32 roots (coalesced along i) x 8 slices of j
+__global__ void __launch_bounds__(256) dc_vecnorm_kernel(int K, const double* __restrict__ Dt, int64_t ldt, const double* __restrict__ zh,
                                                          double* __restrict__ invn) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= K) return;
+  __shared__ double sh[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + tx;
   double s = 0.0;
-  for (int j = 0; j < K; ++j) {
-    const double v = zh[j] / Dt[i + (int64_t)j * ldt];
-    s += v * v;
+  if (i < K) {
+    for (int j = ty; j < K; j += 8) {
+      const double v = zh[j] / Dt[i + (int64_t)j * ldt];
+      s += v * v;
+    }
   }
-  invn[i] = 1.0 / sqrt(s);
+  sh[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && i < K) {
+    double t = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += sh[q][tx];
+    invn[i] = 1.0 / sqrt(t);
+  }
 }
 
 __global__ void dc_vecscale_kernel(int K, double* __restrict__ Dt, int64_t ldt, const double* __restrict__ zh,
@@ -685,11 +795,12 @@ void dc_solve(Ctx* ctx, int64_t n, const std::vector<double>& d, const std::vect
           double* Zgb = (double*)Zg.ptr + off;
           const double* dl = (const double*)dl_d.ptr + lo;
           gather_cols<double>(ctx, Zb, n, N, (const int32_t*)nd_d.ptr + lo, K, nullptr, Zgb, n);
-          dc_secular_kernel<<<(K + 127) / 128, 128, 0, ctx->stream>>>(K, dl, (const double*)z2_d.ptr + lo, m.rho, Dtb, n, (double*)lam_d.ptr + lo);
+          if (K <= 128) dc_secular_kernel<<<(K + 127) / 128, 128, 0, ctx->stream>>>(K, dl, (const double*)z2_d.ptr + lo, m.rho, Dtb, n, (double*)lam_d.ptr + lo);
+          else dc_secular_warp_kernel<<<(K + 3) / 4, 128, 0, ctx->stream>>>(K, dl, (const double*)z2_d.ptr + lo, m.rho, Dtb, n, (double*)lam_d.ptr + lo);
           LAUNCH_CHECK(ctx);
           dc_zhat_kernel<<<K, 128, 0, ctx->stream>>>(K, Dtb, n, dl, (const double*)zz_d.ptr + lo, (double*)zh_d.ptr + lo);
           LAUNCH_CHECK(ctx);
-          dc_vecnorm_kernel<<<(K + 127) / 128, 128, 0, ctx->stream>>>(K, Dtb, n, (const double*)zh_d.ptr + lo, (double*)invn_d.ptr + lo);
+          dc_vecnorm_kernel<<<(K + 31) / 32, 256, 0, ctx->stream>>>(K, Dtb, n, (const double*)zh_d.ptr + lo, (double*)invn_d.ptr + lo);
           LAUNCH_CHECK(ctx);
           const int grid = (int)std::min<int64_t>(((int64_t)K * K + 255) / 256, (int64_t)ctx->num_sms * 8);
           dc_vecscale_kernel<<<grid, 256, 0, ctx->stream>>>(K, Dtb, n, (const double*)zh_d.ptr + lo, (const double*)invn_d.ptr + lo);
@@ -821,7 +932,7 @@ void Eigh<T>::vectors(const int32_t* idx_host, int64_t k, T* U, int64_t ldu) {
   if (k <= 0) return;
   // block width of the back-transformation: independent of the tridiagonalisation panels (any run of consecutive
   // reflectors has a compact-WY form); wide blocks make the three GEMMs per block efficient
-  const int nb = std::max(2, std::min(g_eigh_wb, 256)) & ~1;
+  const int nb = std::max(2, std::min(g_eigh_wb, ScalarTraits<T>::is_complex ? 96 : 160)) & ~1;   // T (nb x nb) must fit in shared memory
   const T one = from_complex<T>(1.0, 0.0), mone = from_complex<T>(-1.0, 0.0), zero = zero_<T>();
   DevBuf idx(ctx, sizeof(int32_t) * k);
   NSB_CUDA(cudaMemcpyAsync(idx.ptr, idx_host, sizeof(int32_t) * k, cudaMemcpyHostToDevice, ctx->stream));
@@ -841,6 +952,12 @@ void Eigh<T>::vectors(const int32_t* idx_host, int64_t k, T* U, int64_t ldu) {
   const T* Vp0 = (const T*)Vall.ptr;
   const T* dtau = (const T*)taus.ptr;
   const int64_t last = ((nref - 1) / nb) * nb;
+  const size_t larft_smem = sizeof(T) * ((size_t)nb * nb + nb);
+  {
+    static bool configured[2] = {false, false};
+    bool& c = configured[ScalarTraits<T>::is_complex ? 1 : 0];
+    if (!c) { NSB_CUDA(cudaFuncSetAttribute(larft_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(T) * (ScalarTraits<T>::is_complex ? (96 * 96 + 96) : (160 * 160 + 160))))); c = true; }
+  }
   const bool dbg = eigh_debug();
   double t0 = 0.0;
   if (dbg) { ctx->sync(); t0 = now_s(); }
@@ -849,7 +966,7 @@ void Eigh<T>::vectors(const int32_t* idx_host, int64_t k, T* U, int64_t ldu) {
     const T* Vp = Vp0 + p * n + p;   // rows p.. (row p of this panel is zero: harmless, keeps the operands 16-byte aligned)
     const int64_t mp = n - p;
     gemm<T>(ctx, OP_C, OP_N, w, w, mp, one, Vp, n, 0, Vp, n, 0, zero, (T*)S.ptr, w, 0, 1);
-    larft_kernel<T><<<1, 256, 0, ctx->stream>>>((const T*)S.ptr, w, dtau + p, (T*)Tm.ptr);
+    larft_kernel<T><<<1, 256, larft_smem, ctx->stream>>>((const T*)S.ptr, w, dtau + p, (T*)Tm.ptr);
     LAUNCH_CHECK(ctx);
     gemm<T>(ctx, OP_C, OP_N, w, k, mp, one, Vp, n, 0, U + p, ldu, 0, zero, (T*)Y.ptr, w, 0, 1);
     gemm<T>(ctx, OP_N, OP_N, w, k, w, one, (const T*)Tm.ptr, w, 0, (const T*)Y.ptr, w, 0, zero, (T*)Y2.ptr, w, 0, 1);
