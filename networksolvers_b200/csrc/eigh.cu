@@ -21,6 +21,7 @@ int g_eigh_min_n = 1024;
 int g_eigh_nb = 64;
 int g_eigh_coop = 1;    // tridiagonalisation panels as one cooperative kernel (2 grid barriers per column); 0: five launches per column
 int g_eigh_coop_ctas = 3;   // CTAs per SM of the cooperative panel kernel
+int g_eigh_split = 8;  // maximum number of row slabs of the split-K product Y = V^H U in the back-transformation
 int g_eigh_wb = 128;   // reflectors per compact-WY block of the back-transformation (T factor in shared memory: <= 160 real, <= 96 complex)
 
 #define LAUNCH_CHECK(ctx) do { (ctx)->cnt.kernel_launches++; NSB_CUDA(cudaGetLastError()); } while (0)
@@ -443,16 +444,24 @@ __global__ void trd_last_diag_kernel(const T* __restrict__ A, int64_t lda, int64
 // stage 3 helpers: T factor of a reflector block (H_0 ... H_{w-1} = I - V T V^H), real -> T conversion
 // ------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(256) larft_kernel(const T* __restrict__ S /* V^H V, w x w */, int w, const T* __restrict__ tau,
-                                                    T* __restrict__ Tm /* w x w */) {
-  // T lives in shared memory (w x w), column i of S is staged per step; thread r owns row r of T
+__global__ void __launch_bounds__(256) larft_kernel(const T* __restrict__ Sall /* V^H V per block, ld nb */, int nb, int64_t nref,
+                                                    const T* __restrict__ tau_all, T* __restrict__ Tall, int reps) {
+  // One CTA per reflector block b (columns b nb .. b nb + w - 1, w = min(nb, nref - b nb)).  T lives in shared memory
+  // (w x w), column i of S is staged per step; thread r owns row r of T.  The result is written `reps` times side by
+  // side (copy s at columns s w .. s w + w - 1, ld nb): [T T ... T] is the left operand of the slab-summing GEMM of the
+  // split-K back-transformation.
   extern __shared__ __align__(16) char larft_sm[];
+  const int64_t b = blockIdx.x;
+  const int w = (int)((nref - b * nb) < (int64_t)nb ? (nref - b * nb) : (int64_t)nb);
+  const T* S = Sall + (size_t)b * nb * nb;
+  const T* tau = tau_all + b * nb;
+  T* Tm = Tall + (size_t)b * nb * nb * reps;
   T* Ts = reinterpret_cast<T*>(larft_sm);
   T* sc = Ts + (size_t)w * w;
   for (int e = threadIdx.x; e < w * w; e += blockDim.x) Ts[e] = zero_<T>();
   __syncthreads();
   for (int i = 0; i < w; ++i) {
-    for (int k = threadIdx.x; k < i; k += blockDim.x) sc[k] = S[k + i * w];
+    for (int k = threadIdx.x; k < i; k += blockDim.x) sc[k] = S[k + (size_t)i * nb];
     __syncthreads();
     const T ti = tau[i];
     for (int r = threadIdx.x; r <= i; r += blockDim.x) {
@@ -466,7 +475,10 @@ __global__ void __launch_bounds__(256) larft_kernel(const T* __restrict__ S /* V
     }
     __syncthreads();
   }
-  for (int e = threadIdx.x; e < w * w; e += blockDim.x) Tm[e] = Ts[e];
+  for (int e = threadIdx.x; e < w * w * reps; e += blockDim.x) {
+    const int s = e / (w * w), rc = e - s * (w * w), r = rc % w, c = rc / w;
+    Tm[r + ((size_t)s * w + c) * nb] = Ts[rc];
+  }
 }
 
 template <typename T>
@@ -948,10 +960,16 @@ void Eigh<T>::vectors(const int32_t* idx_host, int64_t k, T* U, int64_t ldu) {
   }
   const int64_t nref = n - 1;
   if (nref <= 0) { ctx->sync(); return; }
-  DevBuf S(ctx, sizeof(T) * nb * nb), Tm(ctx, sizeof(T) * nb * nb), Y(ctx, sizeof(T) * (size_t)nb * k), Y2(ctx, sizeof(T) * (size_t)nb * k);
   const T* Vp0 = (const T*)Vall.ptr;
   const T* dtau = (const T*)taus.ptr;
-  const int64_t last = ((nref - 1) / nb) * nb;
+  const int64_t nblocks = (nref + nb - 1) / nb, nfull = nref / nb;
+  // Y = V_b^H U has only ceil(w / 128) x ceil(k / BN) output tiles but a contraction as long as the column height:
+  // split the rows into `split` slabs (one strided batch), stack the partial products and let the T-factor GEMM sum
+  // them ([T T .. T] x stack), so that all SMs work on it.
+  const int64_t tiles_y = ((nb + 127) / 128) * ((k + (ScalarTraits<T>::is_complex ? 63 : 127)) / (ScalarTraits<T>::is_complex ? 64 : 128));
+  const int split = (int)std::max<int64_t>(1, std::min<int64_t>(std::max(1, g_eigh_split), (int64_t)ctx->num_sms / std::max<int64_t>(tiles_y, 1)));
+  DevBuf Sall(ctx, sizeof(T) * (size_t)nb * nb * nblocks), Tall(ctx, sizeof(T) * (size_t)nb * nb * split * nblocks);
+  DevBuf Y(ctx, sizeof(T) * (size_t)nb * split * k), Y2(ctx, sizeof(T) * (size_t)nb * k);
   const size_t larft_smem = sizeof(T) * ((size_t)nb * nb + nb);
   {
     static bool configured[2] = {false, false};
@@ -961,19 +979,34 @@ void Eigh<T>::vectors(const int32_t* idx_host, int64_t k, T* U, int64_t ldu) {
   const bool dbg = eigh_debug();
   double t0 = 0.0;
   if (dbg) { ctx->sync(); t0 = now_s(); }
-  for (int64_t p = last; p >= 0; p -= nb) {
+  // Gram matrices S_b = V_b^H V_b of all blocks in one strided batch over the full column height (the rows of V_b above
+  // its first reflector are zero), then all T factors in one launch (one CTA per block).
+  NSB_CUDA(cudaMemsetAsync(Sall.ptr, 0, sizeof(T) * (size_t)nb * nb * nblocks, ctx->stream));
+  if (nfull > 0)
+    gemm<T>(ctx, OP_C, OP_N, nb, nb, n, one, Vp0, n, (int64_t)nb * n, Vp0, n, (int64_t)nb * n, zero, (T*)Sall.ptr, nb, (int64_t)nb * nb, nfull);
+  if (nblocks > nfull) {
+    const int64_t p = nfull * nb, w = nref - p;
+    gemm<T>(ctx, OP_C, OP_N, w, w, n - p, one, Vp0 + p * n + p, n, 0, Vp0 + p * n + p, n, 0, zero, (T*)Sall.ptr + (size_t)nfull * nb * nb, nb, 0, 1);
+  }
+  larft_kernel<T><<<(unsigned)nblocks, 256, larft_smem, ctx->stream>>>((const T*)Sall.ptr, nb, nref, dtau, (T*)Tall.ptr, split);
+  LAUNCH_CHECK(ctx);
+  for (int64_t b = nblocks - 1; b >= 0; --b) {
+    const int64_t p = b * nb;
     const int w = (int)std::min<int64_t>(nb, nref - p);
     const T* Vp = Vp0 + p * n + p;   // rows p.. (row p of this panel is zero: harmless, keeps the operands 16-byte aligned)
     const int64_t mp = n - p;
-    gemm<T>(ctx, OP_C, OP_N, w, w, mp, one, Vp, n, 0, Vp, n, 0, zero, (T*)S.ptr, w, 0, 1);
-    larft_kernel<T><<<1, 256, larft_smem, ctx->stream>>>((const T*)S.ptr, w, dtau + p, (T*)Tm.ptr);
-    LAUNCH_CHECK(ctx);
-    gemm<T>(ctx, OP_C, OP_N, w, k, mp, one, Vp, n, 0, U + p, ldu, 0, zero, (T*)Y.ptr, w, 0, 1);
-    gemm<T>(ctx, OP_N, OP_N, w, k, w, one, (const T*)Tm.ptr, w, 0, (const T*)Y.ptr, w, 0, zero, (T*)Y2.ptr, w, 0, 1);
+    const T* Tb = (const T*)Tall.ptr + (size_t)b * nb * nb * split;
+    int64_t sb = std::min<int64_t>(split, std::max<int64_t>(1, mp / 256));   // slabs of at least 256 rows
+    int64_t kc = (((mp + sb - 1) / sb) + 15) / 16 * 16;
+    const int64_t nf = mp / kc, rem = mp - nf * kc, st = nf + (rem > 0 ? 1 : 0);
+    const int64_t ldy = st * w;
+    if (nf > 0) gemm<T>(ctx, OP_C, OP_N, w, k, kc, one, Vp, n, kc, U + p, ldu, kc, zero, (T*)Y.ptr, ldy, w, nf);
+    if (rem > 0) gemm<T>(ctx, OP_C, OP_N, w, k, rem, one, Vp + nf * kc, n, 0, U + p + nf * kc, ldu, 0, zero, (T*)Y.ptr + nf * w, ldy, 0, 1);
+    gemm<T>(ctx, OP_N, OP_N, w, k, st * w, one, Tb, nb, 0, (const T*)Y.ptr, ldy, 0, zero, (T*)Y2.ptr, w, 0, 1);
     gemm<T>(ctx, OP_N, OP_N, mp, k, w, mone, Vp, n, 0, (const T*)Y2.ptr, w, 0, one, U + p, ldu, 0, 1);
   }
   ctx->sync();
-  if (dbg) fprintf(stderr, "[eigh] n=%ld k=%ld back-transformation %.1f ms\n", (long)n, (long)k, (now_s() - t0) * 1e3);
+  if (dbg) fprintf(stderr, "[eigh] n=%ld k=%ld back-transformation %.1f ms (split %d)\n", (long)n, (long)k, (now_s() - t0) * 1e3, split);
 }
 
 template struct Eigh<double>;
