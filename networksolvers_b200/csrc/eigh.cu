@@ -21,6 +21,8 @@ int g_eigh_min_n = 1024;
 int g_eigh_nb = 64;
 int g_eigh_coop = 1;    // tridiagonalisation panels as one cooperative kernel (2 grid barriers per column); 0: five launches per column
 int g_eigh_coop_ctas = 3;   // CTAs per SM of the cooperative panel kernel
+int g_eigh_sym = 1;     // real FP64, even n: symmetric (half-traffic) column-dot phase of the cooperative panel kernel
+int g_eigh_sym_tc = 0;  // column-block width of its work units (0: chosen per column from {64, 32, 16})
 int g_eigh_split = 8;  // maximum number of row slabs of the split-K product Y = V^H U in the back-transformation
 int g_eigh_wb = 128;   // reflectors per compact-WY block of the back-transformation (T factor in shared memory: <= 160 real, <= 96 complex)
 
@@ -431,6 +433,329 @@ __global__ void __launch_bounds__(256) trd_panel_kernel(const TrdPanelArgs<T> a)
     blk_sum<2>(yhv, sh);
     const double yhv0 = yhv[0], yhv1 = yhv[1];
     if (tid == 0) { a.part2[2 * blockIdx.x] = yhv0; a.part2[2 * blockIdx.x + 1] = yhv1; }
+    grid.sync();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Symmetric variant of the panel kernel (real FP64, even n, 16-byte aligned columns): phase C reads only the lower
+// triangle of the trailing matrix (plus the square diagonal blocks), half the HBM traffic of the kernel above.
+//   * coordinates: u = absolute row - R0, R0 = (j + 1) rounded down to even (128-bit loads stay aligned; the extra
+//     row u = 0 of an odd j + 1 enters with x = 0), mu = n - R0 rows.
+//   * work unit (I, J): column block J (TC columns) x row chunk I (SYM_RC = 512 rows = one pair of rows per thread),
+//     rows from the top of the diagonal block down.  Element A[u, c] gives  y_c += A[u, c] x_u  (dot, all rows of the
+//     unit) and, strictly below the diagonal block,  y_u += A[u, c] x_c  (the mirrored element, kept in registers).
+//     Units are dealt round-robin to the CTAs; every unit stores its TC dot partials and its 512 row partials, and the
+//     next phase AD sums, for row u, the partials of its column block (over I) and of its row chunk (over J) in a
+//     fixed order (deterministic, no atomics).
+//   * the 2 i panel columns (W^H v, V^H v) are units of 16 columns x 2048 rows with partials over the row chunks.
+// tools/proto_trd_sym.py is the NumPy statement of the same index scheme (checked on the CPU by tests/test_cpu_dc.py).
+// ------------------------------------------------------------------------------------------------
+constexpr int SYM_RC = 512;
+
+struct SymCfg { int R0, mu, nJ, nI, UA, nIW, UW, U, s, TC, q, nsetW; };   // n < 2^31
+
+__host__ __device__ __forceinline__ int sym_sumfloor(int J, int q) {   // sum_{J' < J} floor(J' / q)
+  const int a = J / q, b = J % q;
+  return q * (a * (a - 1) / 2) + a * b;
+}
+
+__host__ __device__ __forceinline__ SymCfg sym_cfg(int n, int j, int i, int G, int force_tc) {
+  SymCfg best{};
+  double bscore = -1e30;
+  const int R0 = (j + 1) & ~1, mu = n - R0;
+  const int tcs[3] = {64, 32, 16};
+  const double pen[3] = {0.03, 0.06, 0.12};   // traffic of the row partials relative to the matrix read
+  for (int t = 0; t < 3; ++t) {
+    if (force_tc && tcs[t] != force_tc) continue;
+    SymCfg c;
+    c.R0 = R0; c.mu = mu; c.s = (int)(j + 1 - R0); c.TC = tcs[t]; c.q = SYM_RC / c.TC;
+    c.nJ = (mu + c.TC - 1) / c.TC; c.nI = (mu + SYM_RC - 1) / SYM_RC;
+    c.UA = c.nJ * c.nI - sym_sumfloor(c.nJ, c.q);
+    c.nIW = (mu + 4 * SYM_RC - 1) / (4 * SYM_RC); c.nsetW = (i + 15) / 16; c.UW = 2 * c.nsetW * c.nIW;
+    c.U = c.UA + c.UW;
+    const int rounds = (c.U + G - 1) / G;
+    const double score = (double)c.U / ((double)G * (double)rounds) - pen[t];
+    if (score > bscore) { bscore = score; best = c; }
+  }
+  return best;
+}
+
+struct TrdSymArgs {
+  double* A; int64_t lda, n, p; int w;
+  double* Vp; double* Wp; int64_t ldp;
+  double* taus; double* d; double* e;
+  double* part;     // gridDim.x partials of sigma
+  double* part2;    // gridDim.x partials of y^T v
+  double* dotP;     // [J][I][TC] dot partials
+  double* zP;       // [I][J][SYM_RC] row partials
+  double* pP;       // [2][MAXNB][nIW] partials of W^T v, V^T v
+  int force_tc;
+};
+
+// Sum 16 per-lane values over the 32 lanes of a warp with a butterfly that halves the number of live values per
+// level (8 + 4 + 2 + 1 + 1 = 16 shuffles instead of 16 x 5): on return every lane holds the warp total of column
+// sym_col_of_lane(lane).  Shuffles share the LSU data pipe with the 128-bit loads, so their count matters.
+__device__ __forceinline__ int sym_col_of_lane(int lane) { return ((lane & 1) << 3) | ((lane & 2) << 1) | ((lane & 4) >> 1) | ((lane & 8) >> 3); }
+__device__ __forceinline__ double warp_reduce16(double (&acc)[16], int lane) {
+  const bool b0 = lane & 1, b1 = lane & 2, b2 = lane & 4, b3 = lane & 8;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const double send = b0 ? acc[q] : acc[q + 8], keep = b0 ? acc[q + 8] : acc[q];
+    acc[q] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const double send = b1 ? acc[q] : acc[q + 4], keep = b1 ? acc[q + 4] : acc[q];
+    acc[q] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const double send = b2 ? acc[q] : acc[q + 2], keep = b2 ? acc[q + 2] : acc[q];
+    acc[q] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  {
+    const double send = b3 ? acc[0] : acc[1], keep = b3 ? acc[1] : acc[0];
+    acc[0] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  return acc[0] + __shfl_xor_sync(0xffffffffu, acc[0], 16);
+}
+
+__global__ void __launch_bounds__(256, 2) trd_panel_sym_kernel(const TrdSymArgs a) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double sv[MAXNB], sw[MAXNB], p1[MAXNB], p2[MAXNB];
+  __shared__ double sh[2 * 32 + 2];
+  __shared__ double spart[2 * 64 * 8];   // per column of the unit: 8 warp partials (two buffers, alternating per unit)
+  __shared__ __align__(16) double sxw[8][16];   // per warp: x of the 16 columns of the current set
+  const int tid = threadIdx.x, nblk = gridDim.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + tid, gsize = (int64_t)nblk * blockDim.x;
+  const int64_t n = a.n, lda = a.lda, ldp = a.ldp;
+  double tau_prev = 0.0;
+  for (int i = 0; i <= a.w; ++i) {   // i == w: only finishes the last w
+    const int64_t j = a.p + i;
+    const int ip = i - 1;
+    // ---------------- phase AD ----------------
+    double alpha = 0.0;
+    SymCfg cp{};
+    if (i > 0) {
+      cp = sym_cfg((int)n, (int)j - 1, ip, nblk, a.force_tc);
+      for (int k = tid; k < ip; k += blockDim.x) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int iw = 0; iw < cp.nIW; ++iw) { s1 += a.pP[k * cp.nIW + iw]; s2 += a.pP[(MAXNB + k) * cp.nIW + iw]; }
+        p1[k] = s1; p2[k] = s2;
+      }
+      double s2[1] = {0.0};
+      for (int k = tid; k < nblk; k += blockDim.x) s2[0] += a.part2[k];
+      blk_sum<1>(s2, sh);            // (its barriers also publish p1 / p2)
+      double cross = 0.0;
+      for (int k = 0; k < ip; ++k) cross += p1[k] * p2[k];
+      const double w0hv = tau_prev * (s2[0] - 2.0 * cross);
+      alpha = tau_prev * (-0.5 * w0hv);
+    }
+    if (i < a.w) {
+      for (int k = tid; k < ip; k += blockDim.x) { sv[k] = a.Vp[j + (int64_t)k * ldp]; sw[k] = a.Wp[j + (int64_t)k * ldp]; }
+      if (i > 0 && tid < 32) {       // row j of the column being finished: V[j, ip] = 1, W[j, ip] = w_{ip}[j]
+        double ar = 0.0;
+        for (int k = tid; k < ip; k += 32) ar += a.Vp[j + (int64_t)k * ldp] * p1[k] + a.Wp[j + (int64_t)k * ldp] * p2[k];
+        double yj = 0.0;             // y of row j = local row cp.s of the previous column: column block 0, no row partials
+        for (int I = tid; I < cp.nI; I += 32) yj += a.dotP[I * cp.TC + cp.s];
+        for (int o = 16; o > 0; o >>= 1) { ar += __shfl_xor_sync(0xffffffffu, ar, o); yj += __shfl_xor_sync(0xffffffffu, yj, o); }
+        if (tid == 0) {
+          const double wj = tau_prev * (yj - ar) + alpha;
+          sv[ip] = 1.0;
+          sw[ip] = wj;
+        }
+      }
+    }
+    __syncthreads();
+    double sig[1] = {0.0};
+    {
+      const int kp = tid & 7;
+      const int64_t rows_per_pass = gsize >> 3;
+      for (int64_t rb = j + ((gtid - (tid & 31)) >> 3); rb < n; rb += rows_per_pass) {   // rb is warp-uniform
+        const int64_t r = rb + ((tid & 31) >> 3);
+        const bool valid = r < n;
+        double accw = 0.0, accu = 0.0, accy = 0.0;
+        if (valid) {
+          for (int k = kp; k < ip; k += 8) {
+            const double vk = a.Vp[r + (int64_t)k * ldp], wk = a.Wp[r + (int64_t)k * ldp];
+            accw += vk * p1[k] + wk * p2[k];
+            if (i < a.w) accu += vk * sw[k] + wk * sv[k];
+          }
+          if (i > 0) {   // y of row r from the partials of the previous column's units
+            const int u = (int)r - cp.R0, Ju = u / cp.TC, Iu = u / SYM_RC;
+            const int i0 = Ju / cp.q, nd = cp.nI - i0, nt = nd + Ju;
+            const double* dp = a.dotP + (int64_t)(Ju * cp.nI + i0) * cp.TC + (u - Ju * cp.TC);
+            const double* zp = a.zP + (int64_t)(Iu * cp.nJ) * SYM_RC + (u - Iu * SYM_RC);
+            for (int t = kp; t < nt; t += 8) accy += (t < nd) ? dp[t * cp.TC] : zp[(int64_t)(t - nd) * SYM_RC];
+          }
+        }
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+          accw += __shfl_xor_sync(0xffffffffu, accw, o);
+          accu += __shfl_xor_sync(0xffffffffu, accu, o);
+          accy += __shfl_xor_sync(0xffffffffu, accy, o);
+        }
+        if (valid && kp == 0) {
+          if (i > 0) {
+            const double vip = a.Vp[r + (int64_t)ip * ldp];
+            const double wr = tau_prev * (accy - accw) + alpha * vip;
+            a.Wp[r + (int64_t)ip * ldp] = wr;
+            if (i < a.w) accu += vip * sw[ip] + wr * sv[ip];
+          }
+          if (i < a.w) {
+            const double av = a.A[r + j * lda] - accu;
+            a.A[r + j * lda] = av;
+            if (r == j) a.d[j] = av;
+            if (r >= j + 2) sig[0] += av * av;
+          }
+        }
+      }
+    }
+    if (i == a.w) break;
+    blk_sum<1>(sig, sh);
+    if (tid == 0) a.part[blockIdx.x] = sig[0];
+    grid.sync();
+    // ---------------- phase C ----------------
+    const int64_t m = n - j - 1;
+    double s1[1] = {0.0};
+    for (int k = tid; k < nblk; k += blockDim.x) s1[0] += a.part[k];
+    blk_sum<1>(s1, sh);
+    const double sigma = s1[0];
+    const double* xcol = a.A + (j + 1) + j * lda;
+    const double ar = xcol[0];
+    double tau = 0.0, sc = 0.0, beta = ar;
+    if (sigma != 0.0) {
+      beta = -copysign(sqrt(ar * ar + sigma), ar);
+      sc = 1.0 / (ar - beta);
+      tau = (beta - ar) / beta;
+    }
+    tau_prev = tau;
+    if (gtid == 0) { a.taus[j] = tau; a.e[j] = beta; }
+    double* vcol = a.Vp + (int64_t)i * ldp + (j + 1);
+    for (int64_t rr = gtid; rr < m; rr += gsize) vcol[rr] = (rr == 0) ? 1.0 : sc * xcol[rr];
+    const SymCfg c = sym_cfg((int)n, (int)j, i, nblk, a.force_tc);
+    const double* colj = a.A + c.R0 + j * lda;            // x source: x_u = sc * colj[u] (1 at u = s, 0 above)
+    const double* Ablk = a.A + c.R0 + (int64_t)c.R0 * lda;         // element (u, uc) at Ablk[u + uc * lda]
+    const int s = c.s, TC = c.TC;
+    double yhv[1] = {0.0};
+    const int lq = (TC == 64) ? 3 : ((TC == 32) ? 4 : 5);   // q = SYM_RC / TC = 1 << lq
+    auto prefix = [&](int J) { const int aa = J >> lq, bb = J & (c.q - 1); return J * c.nI - (c.q * ((aa * (aa - 1)) >> 1) + aa * bb); };
+    int buf = 0;
+    for (int unit = blockIdx.x; unit < c.U; unit += nblk, buf ^= 1) {
+      // one block barrier per unit: the warp partials alternate between two buffers, so the writers of unit k + 2 have
+      // passed the barrier of unit k + 1, which the readers of unit k reach only after reading
+      double* sp = spart + buf * (64 * 8);
+      if (unit < c.UW) {
+        // ---- panel columns: 16 columns of W or V x 2048 rows ----
+        const int t = unit / c.nIW, iw = unit - t * c.nIW;
+        const int which = t / c.nsetW, set = t - which * c.nsetW;
+        const int k0 = set * 16, nset = min(16, i - k0);
+        const double* base = (which ? a.Vp : a.Wp) + c.R0 + (int64_t)k0 * ldp;
+        double acc[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) acc[q] = 0.0;
+        for (int it = 0; it < 4; ++it) {
+          const int u = iw * (4 * SYM_RC) + 2 * (tid + 256 * it);
+          if (u < c.mu) {
+            const double2 xv = *reinterpret_cast<const double2*>(colj + u);
+            const double x0 = (u < s) ? 0.0 : ((u == s) ? 1.0 : sc * xv.x), x1 = (u + 1 == s) ? 1.0 : sc * xv.y;
+            double2 v[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[q] = (q < nset) ? *reinterpret_cast<const double2*>(base + u + (int64_t)q * ldp) : make_double2(0.0, 0.0);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) acc[q] += v[q].x * x0 + v[q].y * x1;
+          }
+        }
+        {
+          const double tot = warp_reduce16(acc, lane);
+          if (lane < 16) sp[sym_col_of_lane(lane) * 8 + warp] = tot;
+        }
+        __syncthreads();
+        if (tid < nset) {
+          double ys = 0.0;
+#pragma unroll
+          for (int w8 = 0; w8 < 8; ++w8) ys += sp[tid * 8 + w8];
+          a.pP[(which * MAXNB + k0 + tid) * c.nIW + iw] = ys;
+        }
+      } else {
+        // ---- unit (I, J) of the trailing matrix ----
+        const int ka = unit - c.UW;
+        int lo = 0, hi = c.nJ - 1;
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (prefix(mid) <= ka) lo = mid; else hi = mid - 1;
+        }
+        const int J = lo, I = (J >> lq) + (ka - prefix(J));
+        const int cbeg = J * TC, cend = min(cbeg + TC, c.mu);
+        const int rbeg = max(I * SYM_RC, cbeg), rend = min((I + 1) * SYM_RC, c.mu);
+        const int u = I * SYM_RC + 2 * tid;
+        const bool active = (u >= rbeg) && (u < rend);
+        const bool below = active && (u >= cbeg + TC);
+        const bool wbelow = __any_sync(0xffffffffu, below);
+        double x0 = 0.0, x1 = 0.0;
+        if (active) {
+          const double2 xv = *reinterpret_cast<const double2*>(colj + u);
+          x0 = (u < s) ? 0.0 : ((u == s) ? 1.0 : sc * xv.x);
+          x1 = (u + 1 == s) ? 1.0 : sc * xv.y;
+        }
+        double z0 = 0.0, z1 = 0.0;
+        for (int set = 0; set * 16 < TC; ++set) {
+          const int c0 = cbeg + 16 * set;
+          const int nset = min(16, cend - c0);
+          if (nset <= 0) break;
+          if (wbelow) {       // x of the 16 columns of the set, staged per warp in shared memory (read back as broadcasts)
+            __syncwarp();
+            if (lane < 16) {
+              const int uc = c0 + lane;
+              sxw[warp][lane] = (lane >= nset || uc < s) ? 0.0 : ((uc == s) ? 1.0 : sc * colj[uc]);
+            }
+            __syncwarp();
+          }
+          double acc[16];
+          double2 v[16];
+          if (active) {
+            const double* base = Ablk + u + (int64_t)c0 * lda;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[q] = (q < nset) ? *reinterpret_cast<const double2*>(base + (int64_t)q * lda) : make_double2(0.0, 0.0);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[q] = make_double2(0.0, 0.0);
+          }
+#pragma unroll
+          for (int q = 0; q < 16; ++q) acc[q] = v[q].x * x0 + v[q].y * x1;
+          if (below) {
+#pragma unroll
+            for (int q = 0; q < 16; q += 2) {
+              const double2 xc = *reinterpret_cast<const double2*>(&sxw[warp][q]);
+              z0 += v[q].x * xc.x + v[q + 1].x * xc.y;
+              z1 += v[q].y * xc.x + v[q + 1].y * xc.y;
+            }
+          }
+          {
+            const double tot = warp_reduce16(acc, lane);
+            if (lane < 16) sp[(16 * set + sym_col_of_lane(lane)) * 8 + warp] = tot;
+          }
+        }
+        __syncthreads();
+        if (tid < TC && cbeg + tid < cend) {
+          double ys = 0.0;
+#pragma unroll
+          for (int w8 = 0; w8 < 8; ++w8) ys += sp[tid * 8 + w8];
+          a.dotP[(int64_t)(J * c.nI + I) * TC + tid] = ys;
+          const int uc = cbeg + tid;
+          yhv[0] += ys * ((uc < s) ? 0.0 : ((uc == s) ? 1.0 : sc * colj[uc]));
+        }
+        if (below) {
+          *reinterpret_cast<double2*>(a.zP + (int64_t)(I * c.nJ + J) * SYM_RC + 2 * tid) = make_double2(z0, z1);
+          yhv[0] += z0 * x0 + z1 * x1;
+        }
+      }
+    }
+    blk_sum<1>(yhv, sh);
+    if (tid == 0) a.part2[blockIdx.x] = yhv[0];
     grid.sync();
   }
 }
@@ -889,10 +1214,42 @@ void Eigh<T>::factor(Ctx* c, T* A, int64_t n_, int64_t lda) {
       part2 = DevBuf(ctx, sizeof(double) * 2 * coop_grid);
     }
   }
+  // symmetric (half-traffic) panel kernel: real FP64, even n, 16-byte aligned columns
+  bool use_sym = false;
+  DevBuf dotP, zP, pP;
+  if constexpr (!ScalarTraits<T>::is_complex) {
+    if (g_eigh_coop && g_eigh_sym && n >= 4 && n % 2 == 0 && lda % 2 == 0 && ((uintptr_t)A % 16) == 0 && ((uintptr_t)Vp0 % 16) == 0 &&
+        ((uintptr_t)Wp % 16) == 0) {
+      int per_sm = 0, coop_ok = 0;
+      NSB_CUDA(cudaDeviceGetAttribute(&coop_ok, cudaDevAttrCooperativeLaunch, ctx->device));
+      NSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trd_panel_sym_kernel, 256, 0));
+      per_sm = std::min(per_sm, std::max(1, g_eigh_coop_ctas));
+      if (coop_ok && per_sm >= 1) {
+        use_sym = true;
+        coop_grid = per_sm * ctx->num_sms;
+        part = DevBuf(ctx, sizeof(double) * coop_grid);
+        part2 = DevBuf(ctx, sizeof(double) * coop_grid);
+        dotP = DevBuf(ctx, sizeof(double) * (size_t)(n + 64) * (size_t)(n / SYM_RC + 2));
+        zP = DevBuf(ctx, sizeof(double) * (size_t)(n / SYM_RC + 2) * (size_t)(n / 16 + 2) * SYM_RC);
+        pP = DevBuf(ctx, sizeof(double) * 2 * MAXNB * (size_t)(n / (4 * SYM_RC) + 2));
+      }
+    }
+  }
   for (int64_t p = 0; p < nref; p += nb) {
     const int w = (int)std::min<int64_t>(nb, nref - p);
     T* Vp = Vp0 + p * n;   // panel columns p .. p + w - 1 of Vall (ld n)
-    if (coop_grid > 0) {
+    if (use_sym) {
+      if constexpr (!ScalarTraits<T>::is_complex) {
+        TrdSymArgs pa;
+        pa.A = A; pa.lda = lda; pa.n = n; pa.p = p; pa.w = w; pa.Vp = Vp; pa.Wp = Wp; pa.ldp = n;
+        pa.taus = dtau; pa.d = (double*)d_d.ptr; pa.e = (double*)e_d.ptr;
+        pa.part = (double*)part.ptr; pa.part2 = (double*)part2.ptr;
+        pa.dotP = (double*)dotP.ptr; pa.zP = (double*)zP.ptr; pa.pP = (double*)pP.ptr; pa.force_tc = g_eigh_sym_tc;
+        void* kargs[] = {(void*)&pa};
+        NSB_CUDA(cudaLaunchCooperativeKernel((void*)trd_panel_sym_kernel, dim3(coop_grid), dim3(256), kargs, 0, ctx->stream));
+        ctx->cnt.kernel_launches++;
+      }
+    } else if (coop_grid > 0) {
       TrdPanelArgs<T> pa;
       pa.A = A; pa.lda = lda; pa.n = n; pa.p = p; pa.w = w; pa.Vp = Vp; pa.Wp = Wp; pa.ldp = n;
       pa.taus = dtau; pa.d = (double*)d_d.ptr; pa.e = (double*)e_d.ptr; pa.y = (T*)yb.ptr;
@@ -934,8 +1291,8 @@ void Eigh<T>::factor(Ctx* c, T* A, int64_t n_, int64_t lda) {
   dc_solve(ctx, n, d, e, Z, w, &dc_nondeflated);
   if (dbg) {
     ctx->sync();
-    fprintf(stderr, "[eigh] n=%ld nb=%d tridiagonalise %.1f ms, divide&conquer %.1f ms (non-deflated %ld)\n", (long)n, nb,
-            (t1 - t0) * 1e3, (now_s() - t1) * 1e3, (long)dc_nondeflated);
+    fprintf(stderr, "[eigh] n=%ld nb=%d %s grid %d tridiagonalise %.1f ms, divide&conquer %.1f ms (non-deflated %ld)\n", (long)n, nb,
+            use_sym ? "sym" : "full", coop_grid, (t1 - t0) * 1e3, (now_s() - t1) * 1e3, (long)dc_nondeflated);
   }
 }
 

@@ -13,6 +13,8 @@ namespace nsb {
 extern int g_eigh_min_n;   // factorize_left takes the Gram + eigh route from this size on (<= 0: never)
 extern int g_eigh_coop;    // 1: one cooperative kernel per tridiagonalisation panel; 0: five launches per column
 extern int g_eigh_coop_ctas;
+extern int g_eigh_sym;     // symmetric (half-traffic) panel kernel for real FP64 with even n
+extern int g_eigh_sym_tc;  // its column-block width (0 = per-column choice)
 extern int g_eigh_split;   // row slabs (split-K) of Y = V^H U in the back-transformation, upper bound
 extern int g_eigh_wb;      // reflectors per compact-WY block of the back-transformation (even, <= 256)
 extern int g_eigh_nb;      // panel width of the tridiagonalisation / back-transformation (even, <= 128)

@@ -64,6 +64,35 @@ def test_eigh_matches_lapack(ctx, n, nb, coop):
         ctx.set_option("eigh_coop", 1)
 
 
+@pytest.mark.parametrize("tc", [0, 16, 32, 64])
+@pytest.mark.parametrize("n,nb", [(4, 64), (66, 64), (300, 32), (1100, 128), (1538, 64), (2600, 64)])
+def test_eigh_symmetric_panel_kernel(ctx, n, nb, tc):
+    """Real FP64, even n: the half-traffic panel kernel (lower-triangle work units, per-unit partials summed in the next
+    phase) for every unit width, against LAPACK and against the full-square kernel."""
+    rng = np.random.default_rng(7 * n + tc)
+    ctx.set_option("eigh_nb", nb)
+    ctx.set_option("eigh_sym_tc", tc)
+    try:
+        for name, A in _cases(n, rng):
+            if np.iscomplexobj(A) or (n > 2000 and name != "gauss"):
+                continue
+            ctx.set_option("eigh_sym", 1)
+            w, U = ctx.eigh(A)
+            ctx.set_option("eigh_sym", 0)
+            w0 = ctx.eigh(A, vectors=False)
+            nrm = max(np.linalg.norm(A, 2), 1e-300)
+            res = np.linalg.norm(A @ U - U * w[None, :]) / (nrm * n)
+            orth = np.linalg.norm(U.T @ U - np.eye(n)) / n
+            err = np.abs(w - np.linalg.eigvalsh(A)).max() / nrm
+            err0 = np.abs(w - w0).max() / nrm
+            tol = 100 * EPS * max(1.0, n / 1000)   # eigenvalue error bound grows with n
+            assert res < 30 * EPS and orth < 30 * EPS and err < tol and err0 < tol, (name, n, tc, res, orth, err, err0)
+    finally:
+        ctx.set_option("eigh_nb", 64)
+        ctx.set_option("eigh_sym", 1)
+        ctx.set_option("eigh_sym_tc", 0)
+
+
 @pytest.mark.parametrize("cplx", [False, True])
 @pytest.mark.parametrize("shape", [(8, 8), (20, 33), (33, 20), (96, 96), (200, 333), (260, 200), (640, 640)])
 def test_factorize_eigh_route_full_spectrum(eigh_route, cplx, shape):
