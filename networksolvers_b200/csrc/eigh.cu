@@ -443,8 +443,8 @@ __global__ void __launch_bounds__(256) trd_panel_kernel(const TrdPanelArgs<T> a)
 //   * coordinates: u = absolute row - R0, R0 = (j + 1) rounded down to even (128-bit loads stay aligned; the extra
 //     row u = 0 of an odd j + 1 enters with x = 0), mu = n - R0 rows.
 //   * work unit (I, J): column block J (TC columns) x row chunk I (SYM_RC = 512 rows = one pair of rows per thread),
-//     rows from the top of the diagonal block down.  Element A[u, c] gives  y_c += A[u, c] x_u  (dot, all rows of the
-//     unit) and, strictly below the diagonal block,  y_u += A[u, c] x_c  (the mirrored element, kept in registers).
+//     rows from the top of the diagonal block down.  Element A[u, c], u >= c, gives  y_c += A[u, c] x_u  (dot) and, for
+//     u > c,  y_u += A[u, c] x_c  (the mirrored element, kept in registers); the upper triangle is never read.
 //     Units are dealt round-robin to the CTAs; every unit stores its TC dot partials and its 512 row partials, and the
 //     next phase AD sums, for row u, the partials of its column block (over I) and of its row chunk (over J) in a
 //     fixed order (deterministic, no atomics).
@@ -586,7 +586,7 @@ __global__ void __launch_bounds__(256, 2) trd_panel_sym_kernel(const TrdSymArgs 
           }
           if (i > 0) {   // y of row r from the partials of the previous column's units
             const int u = (int)r - cp.R0, Ju = u / cp.TC, Iu = u / SYM_RC;
-            const int i0 = Ju / cp.q, nd = cp.nI - i0, nt = nd + Ju;
+            const int i0 = Ju / cp.q, nd = cp.nI - i0, nt = nd + Ju + 1;   // row partials of blocks 0 .. Ju (own block: strictly-lower part)
             const double* dp = a.dotP + (int64_t)(Ju * cp.nI + i0) * cp.TC + (u - Ju * cp.TC);
             const double* zp = a.zP + (int64_t)(Iu * cp.nJ) * SYM_RC + (u - Iu * SYM_RC);
             for (int t = kp; t < nt; t += 8) accy += (t < nd) ? dp[t * cp.TC] : zp[(int64_t)(t - nd) * SYM_RC];
@@ -693,8 +693,8 @@ __global__ void __launch_bounds__(256, 2) trd_panel_sym_kernel(const TrdSymArgs 
         const int rbeg = max(I * SYM_RC, cbeg), rend = min((I + 1) * SYM_RC, c.mu);
         const int u = I * SYM_RC + 2 * tid;
         const bool active = (u >= rbeg) && (u < rend);
-        const bool below = active && (u >= cbeg + TC);
-        const bool wbelow = __any_sync(0xffffffffu, below);
+        const bool wactive = __any_sync(0xffffffffu, active);
+        const bool wdiag = __any_sync(0xffffffffu, active && (u < cbeg + TC));   // warp touches the diagonal block: per-element masks
         double x0 = 0.0, x1 = 0.0;
         if (active) {
           const double2 xv = *reinterpret_cast<const double2*>(colj + u);
@@ -706,7 +706,7 @@ __global__ void __launch_bounds__(256, 2) trd_panel_sym_kernel(const TrdSymArgs 
           const int c0 = cbeg + 16 * set;
           const int nset = min(16, cend - c0);
           if (nset <= 0) break;
-          if (wbelow) {       // x of the 16 columns of the set, staged per warp in shared memory (read back as broadcasts)
+          if (wactive) {      // x of the 16 columns of the set, staged per warp in shared memory (read back as broadcasts)
             __syncwarp();
             if (lane < 16) {
               const int uc = c0 + lane;
@@ -724,14 +724,29 @@ __global__ void __launch_bounds__(256, 2) trd_panel_sym_kernel(const TrdSymArgs 
 #pragma unroll
             for (int q = 0; q < 16; ++q) v[q] = make_double2(0.0, 0.0);
           }
+          if (!wdiag) {
 #pragma unroll
-          for (int q = 0; q < 16; ++q) acc[q] = v[q].x * x0 + v[q].y * x1;
-          if (below) {
+            for (int q = 0; q < 16; ++q) acc[q] = v[q].x * x0 + v[q].y * x1;
+            if (active) {
 #pragma unroll
-            for (int q = 0; q < 16; q += 2) {
-              const double2 xc = *reinterpret_cast<const double2*>(&sxw[warp][q]);
-              z0 += v[q].x * xc.x + v[q + 1].x * xc.y;
-              z1 += v[q].y * xc.x + v[q + 1].y * xc.y;
+              for (int q = 0; q < 16; q += 2) {
+                const double2 xc = *reinterpret_cast<const double2*>(&sxw[warp][q]);
+                z0 += v[q].x * xc.x + v[q + 1].x * xc.y;
+                z1 += v[q].y * xc.x + v[q + 1].y * xc.y;
+              }
+            }
+          } else {
+            // diagonal block: only the lower triangle is valid.  Element (u, uc) feeds the dot product of column uc for
+            // u >= uc and the row partial of row u for u > uc (x0 = x1 = 0 on inactive lanes).
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              const int uc = c0 + q;
+              const double xc = sxw[warp][q];
+              acc[q] = ((u >= uc) ? v[q].x * x0 : 0.0) + ((u + 1 >= uc) ? v[q].y * x1 : 0.0);
+              if (active) {
+                z0 += (u > uc) ? v[q].x * xc : 0.0;
+                z1 += (u + 1 > uc) ? v[q].y * xc : 0.0;
+              }
             }
           }
           {
@@ -748,7 +763,7 @@ __global__ void __launch_bounds__(256, 2) trd_panel_sym_kernel(const TrdSymArgs 
           const int uc = cbeg + tid;
           yhv[0] += ys * ((uc < s) ? 0.0 : ((uc == s) ? 1.0 : sc * colj[uc]));
         }
-        if (below) {
+        if (active) {
           *reinterpret_cast<double2*>(a.zP + (int64_t)(I * c.nJ + J) * SYM_RC + 2 * tid) = make_double2(z0, z1);
           yhv[0] += z0 * x0 + z1 * x1;
         }
@@ -1216,7 +1231,7 @@ void Eigh<T>::factor(Ctx* c, T* A, int64_t n_, int64_t lda) {
   }
   // symmetric (half-traffic) panel kernel: real FP64, even n, 16-byte aligned columns
   bool use_sym = false;
-  DevBuf dotP, zP, pP;
+  DevBuf dotP, zP, pP, pack;
   if constexpr (!ScalarTraits<T>::is_complex) {
     if (g_eigh_coop && g_eigh_sym && n >= 4 && n % 2 == 0 && lda % 2 == 0 && ((uintptr_t)A % 16) == 0 && ((uintptr_t)Vp0 % 16) == 0 &&
         ((uintptr_t)Wp % 16) == 0) {
@@ -1232,6 +1247,7 @@ void Eigh<T>::factor(Ctx* c, T* A, int64_t n_, int64_t lda) {
         dotP = DevBuf(ctx, sizeof(double) * (size_t)(n + 64) * (size_t)(n / SYM_RC + 2));
         zP = DevBuf(ctx, sizeof(double) * (size_t)(n / SYM_RC + 2) * (size_t)(n / 16 + 2) * SYM_RC);
         pP = DevBuf(ctx, sizeof(double) * 2 * MAXNB * (size_t)(n / (4 * SYM_RC) + 2));
+        pack = DevBuf(ctx, sizeof(double) * 4 * (size_t)n * nb);   // [V W] and [W V] of the rank-2w update
       }
     }
   }
@@ -1275,7 +1291,17 @@ void Eigh<T>::factor(Ctx* c, T* A, int64_t n_, int64_t lda) {
       LAUNCH_CHECK(ctx);
     }
     const int64_t q = p + w, mt = n - q;
-    if (mt > 0) {   // A_trail -= V W^H + W V^H (full square: both triangles stay valid for the column dot products)
+    if (mt > 0 && use_sym) {
+      // A_trail -= [V W] [W V]^H as one GEMM with K = 2 w, lower-triangular output tiles only (the symmetric panel kernel
+      // never reads the upper triangle)
+      T* P1 = (T*)pack.ptr;
+      T* P2 = P1 + (size_t)n * 2 * nb;
+      copy_block<T>(ctx, Vp + q, n, P1, mt, mt, w);
+      copy_block<T>(ctx, Wp + q, n, P1 + (size_t)mt * w, mt, mt, w);
+      copy_block<T>(ctx, Wp + q, n, P2, mt, mt, w);
+      copy_block<T>(ctx, Vp + q, n, P2 + (size_t)mt * w, mt, mt, w);
+      gemm<T>(ctx, OP_N, OP_C, mt, mt, 2 * w, mone, P1, mt, 0, P2, mt, 0, one, A + q + q * lda, lda, 0, 1, GEMM_AUTO, nullptr, GEMM_LOWER_ONLY);
+    } else if (mt > 0) {   // A_trail -= V W^H + W V^H (full square: both triangles stay valid for the column dot products)
       gemm<T>(ctx, OP_N, OP_C, mt, mt, w, mone, Vp + q, n, 0, Wp + q, n, 0, one, A + q + q * lda, lda, 0, 1);
       gemm<T>(ctx, OP_N, OP_C, mt, mt, w, mone, Wp + q, n, 0, Vp + q, n, 0, one, A + q + q * lda, lda, 0, 1);
     }

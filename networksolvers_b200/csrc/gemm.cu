@@ -36,6 +36,7 @@ struct GemmParams {
   int alignedA, alignedB;   // 16-byte alignment of every chunk source
   int bcoordA, bcoordB;     // 0 when the operand is broadcast over the batch (stride 0)
   int64_t tiles_m, tiles_n;
+  int lower_only;           // skip output tiles strictly above the diagonal (symmetric rank-k updates that only need the lower triangle)
   PeerOut peer;             // nranks > 1: fused reduce-scatter epilogue over peer memory
 };
 
@@ -374,6 +375,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_dmma_kernel(const GemmPa
     int64_t tm, tn;
     tile_coords(tile % tiles_per_batch, p.tiles_m, p.tiles_n, tm, tn);
     const int64_t m0 = tm * Cfg::BM, n0 = tn * Cfg::BN;
+    if (p.lower_only && n0 >= m0 + Cfg::BM) continue;
     const T* A = p.A + b * p.strideA;
     const T* B = p.B + b * p.strideB;
     Acc acc;
@@ -476,6 +478,7 @@ gemm_tma_kernel(const GemmParams<T> p, const __grid_constant__ TmaMaps maps) {
         int64_t tm, tn;
         tile_coords(tile % tiles_per_batch, p.tiles_m, p.tiles_n, tm, tn);
         const int m0 = (int)(tm * Cfg::BM), n0 = (int)(tn * Cfg::BN);
+        if (p.lower_only && n0 >= m0 + Cfg::BM) continue;
         for (int64_t kt = 0; kt < nk; ++kt, ++it) {
           int s = it % GEMM_STAGES;
           uint32_t ph = (it / GEMM_STAGES) & 1;
@@ -514,6 +517,7 @@ gemm_tma_kernel(const GemmParams<T> p, const __grid_constant__ TmaMaps maps) {
     int64_t tm, tn;
     tile_coords(tile % tiles_per_batch, p.tiles_m, p.tiles_n, tm, tn);
     const int64_t m0 = tm * Cfg::BM, n0 = tn * Cfg::BN;
+    if (p.lower_only && n0 >= m0 + Cfg::BM) continue;
     Acc acc;
     acc_zero(acc);
     for (int64_t kt = 0; kt < nk; ++kt, ++it) {
@@ -615,7 +619,7 @@ static bool launch_tma(Ctx* ctx, const GemmParams<T>& p) {
 template <typename T>
 void gemm(Ctx* ctx, int opa, int opb, int64_t M, int64_t N, int64_t K, T alpha, const T* A, int64_t lda,
           int64_t strideA, const T* B, int64_t ldb, int64_t strideB, T beta, T* C, int64_t ldc,
-          int64_t strideC, int64_t batch, int impl, const PeerOut* peer) {
+          int64_t strideC, int64_t batch, int impl, const PeerOut* peer, int flags) {
   if (M <= 0 || N <= 0 || batch <= 0) return;
   NSB_REQUIRE(K >= 0, NSB_EINVAL, "gemm: negative K");
   typedef TileCfg<T> Cfg;
@@ -624,6 +628,7 @@ void gemm(Ctx* ctx, int opa, int opb, int64_t M, int64_t N, int64_t K, T alpha, 
   p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldb = ldb; p.ldc = ldc;
   p.strideA = strideA; p.strideB = strideB; p.strideC = strideC; p.batch = batch;
   p.alpha = alpha; p.beta = beta;
+  p.lower_only = (flags & GEMM_LOWER_ONLY) ? 1 : 0;
   if (peer) { NSB_REQUIRE(batch == 1 && peer->nranks <= 8, NSB_EINVAL, "gemm: peer epilogue needs batch == 1"); p.peer = *peer; }
   p.a_kmajor = (opa == OP_T || opa == OP_C);
   p.b_kmajor = (opb == OP_N || opb == OP_CONJ);
@@ -647,7 +652,13 @@ void gemm(Ctx* ctx, int opa, int opb, int64_t M, int64_t N, int64_t K, T alpha, 
   }
   ctx->cnt.gemm_calls++;
   ctx->cnt.kernel_launches++;
-  ctx->cnt.gemm_flops += (ScalarTraits<T>::is_complex ? 8.0 : 2.0) * (double)M * (double)N * (double)K * (double)batch;
+  double frac = 1.0;
+  if (p.lower_only) {   // executed flops: only the tiles that are not skipped
+    int64_t kept = 0;
+    for (int64_t tm = 0; tm < p.tiles_m; ++tm) kept += std::min<int64_t>(p.tiles_n, (tm * Cfg::BM + Cfg::BM - 1) / Cfg::BN + 1);
+    frac = (double)kept / (double)(p.tiles_m * p.tiles_n);
+  }
+  ctx->cnt.gemm_flops += frac * (ScalarTraits<T>::is_complex ? 8.0 : 2.0) * (double)M * (double)N * (double)K * (double)batch;
 
   if (impl == GEMM_NAIVE) {
     NSB_REQUIRE(batch <= 65535 && (N + 15) / 16 <= 65535, NSB_EINVAL, "gemm naive: grid too large");
@@ -712,8 +723,8 @@ double dmma_peak_tflops(Ctx* ctx) {
 }
 
 template void gemm<double>(Ctx*, int, int, int64_t, int64_t, int64_t, double, const double*, int64_t, int64_t,
-                           const double*, int64_t, int64_t, double, double*, int64_t, int64_t, int64_t, int, const PeerOut*);
+                           const double*, int64_t, int64_t, double, double*, int64_t, int64_t, int64_t, int, const PeerOut*, int);
 template void gemm<cdouble>(Ctx*, int, int, int64_t, int64_t, int64_t, cdouble, const cdouble*, int64_t, int64_t,
-                            const cdouble*, int64_t, int64_t, cdouble, cdouble*, int64_t, int64_t, int64_t, int, const PeerOut*);
+                            const cdouble*, int64_t, int64_t, cdouble, cdouble*, int64_t, int64_t, int64_t, int, const PeerOut*, int);
 
 }  // namespace nsb

@@ -6,6 +6,7 @@ namespace nsb {
 
 enum GemmOp { OP_N = 0, OP_T = 1, OP_C = 2, OP_CONJ = 3 };
 enum GemmImpl { GEMM_AUTO = 0, GEMM_NAIVE = 1, GEMM_DMMA = 2, GEMM_TMA = 3 };
+enum GemmFlags { GEMM_LOWER_ONLY = 1 };   // tensor-core paths skip the 128-wide output tiles strictly above the diagonal
 
 // Optional fused reduce-scatter epilogue: output column n belongs to rank n / slab_cols; the tile is written straight
 // into that rank's peer-mapped staging window (NVLink P2P stores) at slot `rank`, instead of local C.
@@ -21,7 +22,7 @@ struct PeerOut {
 template <typename T>
 void gemm(Ctx* ctx, int opa, int opb, int64_t M, int64_t N, int64_t K, T alpha, const T* A, int64_t lda,
           int64_t strideA, const T* B, int64_t ldb, int64_t strideB, T beta, T* C, int64_t ldc,
-          int64_t strideC, int64_t batch, int impl = GEMM_AUTO, const PeerOut* peer = nullptr);
+          int64_t strideC, int64_t batch, int impl = GEMM_AUTO, const PeerOut* peer = nullptr, int flags = 0);
 
 const char* gemm_last_impl_name();
 

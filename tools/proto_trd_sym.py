@@ -42,13 +42,11 @@ def phaseC(A,W,V,n,j,i,G,xfull,force_tc=0):
             I,J=decode(c,unit-c['UW']); assert (I,J) not in seen; seen.add((I,J))
             cbeg=J*TC; cend=min(cbeg+TC,mu); rbeg=max(I*RC,cbeg); rend=min((I+1)*RC,mu); z0=cbeg+TC
             assert rbeg<rend, (I,J)
-            blk=A[R0+rbeg:R0+rend, R0+cbeg:R0+cend]
+            blk=np.tril(A)[R0+rbeg:R0+rend, R0+cbeg:R0+cend]      # the upper triangle is never read
             d=np.zeros(TC); d[:cend-cbeg]=blk.T@x[rbeg:rend]; dotP[J,I,:]=d
             yhv+=d[:cend-cbeg]@x[cbeg:cend]
-            zr=max(rbeg,z0)
-            if zr<rend:
-                z=A[R0+zr:R0+rend,R0+cbeg:R0+cend]@x[cbeg:cend]
-                zP[I,J,zr-I*RC:rend-I*RC]=z; yhv+=z@x[zr:rend]
+            z=np.tril(A,-1)[R0+rbeg:R0+rend,R0+cbeg:R0+cend]@x[cbeg:cend]   # strictly lower: mirrored element
+            zP[I,J,rbeg-I*RC:rend-I*RC]=z; yhv+=z@x[rbeg:rend]
     return c,dotP,zP,pP,yhv
 def consume(c,dotP,zP,pP,ip):
     mu,TC,nI,nJ,q=c['mu'],c['TC'],c['nI'],c['nJ'],c['q']
@@ -57,19 +55,20 @@ def consume(c,dotP,zP,pP,ip):
         Ju=u//TC; Iu=u//RC
         acc=0.0
         for I in range(Ju//q,nI): acc+=dotP[Ju,I,u-Ju*TC]
-        for J in range(0,Ju): acc+=zP[Iu,J,u-Iu*RC]
+        for J in range(0,Ju+1): acc+=zP[Iu,J,u-Iu*RC]
         y[u]=acc
     p1=pP[0,:ip,:].sum(1); p2=pP[1,:ip,:].sum(1)
     return y,p1,p2
 rng=np.random.default_rng(0)
 for n,j,i,G,ftc in [(700,0,0,444,0),(700,1,1,444,0),(1100,64,0,444,16),(1100,65,1,444,32),(2300,130,2,444,64),(2300,131,3,30,64),(2300,2290,50,444,0),(2300,2297,57,444,0),(4700,7,7,444,0),(4700,6,6,296,0)]:
     A=rng.standard_normal((n,n)); A=A+A.T
+    Aup=A.copy(); A=np.tril(A)+np.triu(np.full((n,n),np.nan),1)   # poison the upper triangle
     W=rng.standard_normal((n,MAXNB)); V=rng.standard_normal((n,MAXNB))
     x=np.zeros(n); x[j+1]=1.0; x[j+2:]=rng.standard_normal(n-j-2)
     # poison rows above j+1 of x-multiplied places with finite garbage: fine
     c,dotP,zP,pP,yhv=phaseC(A,W,V,n,j,i,G,x,ftc)
     y,p1,p2=consume(c,dotP,zP,pP,i)
-    yref=A[j+1:,j+1:]@x[j+1:]
+    yref=Aup[j+1:,j+1:]@x[j+1:]
     R0=c['R0']
     err=np.abs(y[c['s']:]-yref).max()/np.abs(yref).max()
     e1=np.abs(p1-W[j+1:,:i].T@x[j+1:]).max() if i else 0; e2=np.abs(p2-V[j+1:,:i].T@x[j+1:]).max() if i else 0
