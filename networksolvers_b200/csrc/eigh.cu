@@ -1192,7 +1192,21 @@ void dc_solve(Ctx* ctx, int64_t n, const std::vector<double>& d, const std::vect
 // driver
 // ------------------------------------------------------------------------------------------------
 template <typename T>
-void Eigh<T>::factor(Ctx* c, T* A, int64_t n_, int64_t lda) {
+__global__ void mirror_lower_kernel(T* __restrict__ A, int64_t lda, int64_t n) {   // A[r, c] = conj(A[c, r]) for r < c
+  const int64_t total = n * n;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e % n, c = e / n;
+    if (r < c) A[r + c * lda] = conj_(A[c + r * lda]);
+  }
+}
+
+template <typename T>
+bool Eigh<T>::reads_lower_only(int64_t n, int64_t lda) {
+  return !ScalarTraits<T>::is_complex && g_eigh_coop && g_eigh_sym && n >= 4 && n % 2 == 0 && lda % 2 == 0 && n < (1ll << 30);
+}
+
+template <typename T>
+void Eigh<T>::factor(Ctx* c, T* A, int64_t n_, int64_t lda, bool lower_only_input) {
   ctx = c;
   n = n_;
   NSB_REQUIRE(n >= 1, NSB_EINVAL, "eigh: empty matrix");
@@ -1233,8 +1247,7 @@ void Eigh<T>::factor(Ctx* c, T* A, int64_t n_, int64_t lda) {
   bool use_sym = false;
   DevBuf dotP, zP, pP, pack;
   if constexpr (!ScalarTraits<T>::is_complex) {
-    if (g_eigh_coop && g_eigh_sym && n >= 4 && n % 2 == 0 && lda % 2 == 0 && ((uintptr_t)A % 16) == 0 && ((uintptr_t)Vp0 % 16) == 0 &&
-        ((uintptr_t)Wp % 16) == 0) {
+    if (reads_lower_only(n, lda) && ((uintptr_t)A % 16) == 0 && ((uintptr_t)Vp0 % 16) == 0 && ((uintptr_t)Wp % 16) == 0) {
       int per_sm = 0, coop_ok = 0;
       NSB_CUDA(cudaDeviceGetAttribute(&coop_ok, cudaDevAttrCooperativeLaunch, ctx->device));
       NSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trd_panel_sym_kernel, 256, 0));
@@ -1250,6 +1263,10 @@ void Eigh<T>::factor(Ctx* c, T* A, int64_t n_, int64_t lda) {
         pack = DevBuf(ctx, sizeof(double) * 4 * (size_t)n * nb);   // [V W] and [W V] of the rank-2w update
       }
     }
+  }
+  if (lower_only_input && !use_sym) {
+    mirror_lower_kernel<T><<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(A, lda, n);
+    LAUNCH_CHECK(ctx);
   }
   for (int64_t p = 0; p < nref; p += nb) {
     const int w = (int)std::min<int64_t>(nb, nref - p);

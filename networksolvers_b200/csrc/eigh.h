@@ -27,7 +27,12 @@ struct Eigh {
   std::vector<double> w;       // eigenvalues; w[i] belongs to column i of Z (unsorted)
   int64_t dc_nondeflated = 0;  // sum of secular problem sizes over all merges (diagnostic)
   // A: n x n Hermitian, full storage (both triangles), column-major with leading dimension lda; destroyed.
-  void factor(Ctx* ctx, T* A, int64_t n, int64_t lda);
+  // lower_only_input: only the lower triangle of A holds valid data (the symmetric panel kernel reads nothing else;
+  // otherwise the lower triangle is mirrored first).
+  void factor(Ctx* ctx, T* A, int64_t n, int64_t lda, bool lower_only_input = false);
+  // True when factor() will take the symmetric panel kernel for this problem, i.e. a caller that builds A by a GEMM
+  // may skip the strictly upper output tiles (GEMM_LOWER_ONLY).
+  static bool reads_lower_only(int64_t n, int64_t lda);
   // U (n x k, ldu) = Q Z[:, idx[0..k)]: eigenvectors of the original matrix for the chosen eigenvalues.
   void vectors(const int32_t* idx_host, int64_t k, T* U, int64_t ldu);
 };

@@ -645,15 +645,17 @@ static FactorInfo factorize_left_eigh(Ctx* ctx, const T* M, int64_t rows, int64_
   Eigh<T> eg;
   {
     DevBuf rho(ctx, sizeof(T) * (size_t)n * n);
+    // the Gram matrix only needs its lower triangle when the symmetric tridiagonalisation kernel will read it
+    const bool lower = !direct && Eigh<T>::reads_lower_only(n, n) && ctx->gemm_impl != GEMM_NAIVE;
     if (direct) {
       if (!trans_in) copy_block<T>(ctx, M, ld, (T*)rho.ptr, n, n, n);
       else transpose_conj<T>(ctx, M, cols, rows, ld, (T*)rho.ptr, n, false);
     } else if (!trans_in) {
-      gemm<T>(ctx, OP_N, OP_C, n, n, cols, one, M, ld, 0, M, ld, 0, zero, (T*)rho.ptr, n, 0, 1);
+      gemm<T>(ctx, OP_N, OP_C, n, n, cols, one, M, ld, 0, M, ld, 0, zero, (T*)rho.ptr, n, 0, 1, GEMM_AUTO, nullptr, lower ? GEMM_LOWER_ONLY : 0);
     } else {   // logical M(r, c) = buf[c + r ld]:  rho = buf^T conj(buf)
-      gemm<T>(ctx, OP_T, OP_CONJ, n, n, cols, one, M, ld, 0, M, ld, 0, zero, (T*)rho.ptr, n, 0, 1);
+      gemm<T>(ctx, OP_T, OP_CONJ, n, n, cols, one, M, ld, 0, M, ld, 0, zero, (T*)rho.ptr, n, 0, 1, GEMM_AUTO, nullptr, lower ? GEMM_LOWER_ONLY : 0);
     }
-    eg.factor(ctx, (T*)rho.ptr, n, n);
+    eg.factor(ctx, (T*)rho.ptr, n, n, lower);
   }
   std::vector<int32_t> order(n);
   std::iota(order.begin(), order.end(), 0);
