@@ -164,6 +164,7 @@ int nsb_ctx_set_option(nsb_ctx* ctx, const char* key, int64_t value) {
   else if (k == "eigh_min_n") { g_eigh_min_n = (int)value; }
   else if (k == "eigh_coop") { g_eigh_coop = value != 0; }
   else if (k == "eigh_coop_ctas") { NSB_REQUIRE(value >= 1 && value <= 8, NSB_EINVAL, "eigh_coop_ctas 1..8"); g_eigh_coop_ctas = (int)value; }
+  else if (k == "eigh_direct_min_n") g_eigh_direct_min_n = (int)value;
   else if (k == "eigh_sym") g_eigh_sym = value ? 1 : 0;
   else if (k == "eigh_sym_tc") { NSB_REQUIRE(value == 0 || value == 16 || value == 32 || value == 64, NSB_EINVAL, "eigh_sym_tc must be 0, 16, 32 or 64"); g_eigh_sym_tc = (int)value; }
   else if (k == "eigh_split") { NSB_REQUIRE(value >= 1 && value <= 16, NSB_EINVAL, "eigh_split 1..16"); g_eigh_split = (int)value; }

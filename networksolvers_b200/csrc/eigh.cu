@@ -18,6 +18,7 @@
 namespace nsb {
 
 int g_eigh_min_n = 1024;
+int g_eigh_direct_min_n = 96;   // same for the Hermitian input of the expansion's `eigen` (no Gram squaring involved)
 int g_eigh_nb = 64;
 int g_eigh_coop = 1;    // tridiagonalisation panels as one cooperative kernel (2 grid barriers per column); 0: five launches per column
 int g_eigh_coop_ctas = 3;   // CTAs per SM of the cooperative panel kernel
@@ -460,12 +461,12 @@ __host__ __device__ __forceinline__ int sym_sumfloor(int J, int q) {   // sum_{J
   return q * (a * (a - 1) / 2) + a * b;
 }
 
-__host__ __device__ __forceinline__ SymCfg sym_cfg(int n, int j, int i, int G, int force_tc) {
+__device__ __forceinline__ SymCfg sym_cfg(int n, int j, int i, int G, int force_tc) {
   SymCfg best{};
-  double bscore = -1e30;
+  float bscore = -1e30f;
   const int R0 = (j + 1) & ~1, mu = n - R0;
   const int tcs[3] = {64, 32, 16};
-  const double pen[3] = {0.03, 0.06, 0.12};   // traffic of the row partials relative to the matrix read
+  const float pen[3] = {0.03f, 0.06f, 0.12f};   // traffic of the row partials relative to the matrix read
   for (int t = 0; t < 3; ++t) {
     if (force_tc && tcs[t] != force_tc) continue;
     SymCfg c;
@@ -475,7 +476,7 @@ __host__ __device__ __forceinline__ SymCfg sym_cfg(int n, int j, int i, int G, i
     c.nIW = (mu + 4 * SYM_RC - 1) / (4 * SYM_RC); c.nsetW = (i + 15) / 16; c.UW = 2 * c.nsetW * c.nIW;
     c.U = c.UA + c.UW;
     const int rounds = (c.U + G - 1) / G;
-    const double score = (double)c.U / ((double)G * (double)rounds) - pen[t];
+    const float score = __fdividef((float)c.U, (float)G * (float)rounds) - pen[t];
     if (score > bscore) { bscore = score; best = c; }
   }
   return best;
@@ -578,6 +579,11 @@ __global__ void __launch_bounds__(256, 2) trd_panel_sym_kernel(const TrdSymArgs 
         const int64_t r = rb + ((tid & 31) >> 3);
         const bool valid = r < n;
         double accw = 0.0, accu = 0.0, accy = 0.0;
+        double a_rj = 0.0, vip = 0.0;   // issued early: the loads overlap the panel loops below
+        if (valid && kp == 0) {
+          if (i < a.w) a_rj = a.A[r + j * lda];
+          if (i > 0) vip = a.Vp[r + (int64_t)ip * ldp];
+        }
         if (valid) {
           for (int k = kp; k < ip; k += 8) {
             const double vk = a.Vp[r + (int64_t)k * ldp], wk = a.Wp[r + (int64_t)k * ldp];
@@ -600,13 +606,12 @@ __global__ void __launch_bounds__(256, 2) trd_panel_sym_kernel(const TrdSymArgs 
         }
         if (valid && kp == 0) {
           if (i > 0) {
-            const double vip = a.Vp[r + (int64_t)ip * ldp];
             const double wr = tau_prev * (accy - accw) + alpha * vip;
             a.Wp[r + (int64_t)ip * ldp] = wr;
             if (i < a.w) accu += vip * sw[ip] + wr * sv[ip];
           }
           if (i < a.w) {
-            const double av = a.A[r + j * lda] - accu;
+            const double av = a_rj - accu;
             a.A[r + j * lda] = av;
             if (r == j) a.d[j] = av;
             if (r >= j + 2) sig[0] += av * av;
@@ -620,12 +625,12 @@ __global__ void __launch_bounds__(256, 2) trd_panel_sym_kernel(const TrdSymArgs 
     grid.sync();
     // ---------------- phase C ----------------
     const int64_t m = n - j - 1;
+    const double* xcol = a.A + (j + 1) + j * lda;
+    const double ar = xcol[0];       // issued before the reduction below (its latency hides behind the block barriers)
     double s1[1] = {0.0};
     for (int k = tid; k < nblk; k += blockDim.x) s1[0] += a.part[k];
     blk_sum<1>(s1, sh);
     const double sigma = s1[0];
-    const double* xcol = a.A + (j + 1) + j * lda;
-    const double ar = xcol[0];
     double tau = 0.0, sc = 0.0, beta = ar;
     if (sigma != 0.0) {
       beta = -copysign(sqrt(ar * ar + sigma), ar);

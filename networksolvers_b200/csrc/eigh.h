@@ -10,6 +10,7 @@
 
 namespace nsb {
 
+extern int g_eigh_direct_min_n;   // threshold for a Hermitian (density-matrix) input, see linalg.cu
 extern int g_eigh_min_n;   // factorize_left takes the Gram + eigh route from this size on (<= 0: never)
 extern int g_eigh_coop;    // 1: one cooperative kernel per tridiagonalisation panel; 0: five launches per column
 extern int g_eigh_coop_ctas;

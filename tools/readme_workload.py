@@ -11,6 +11,8 @@ H = ns.ttno(ns.heisenberg(g), sites)
 psi0 = ns.product_state(sites, neel(g))
 trunc = dict(cutoff=1e-9, maxdim=[10, 40, 80, 160])
 ctx = ns.default_context()
+for a in sys.argv[3:]:   # context options, e.g. eigh_min_n=256
+    k, v = a.split('='); ctx.set_option(k, int(v))
 for nsites, ek in ((2, {}), (1, dict(trunc=trunc, subspace_algorithm="densitymatrix", expansion_factor=1.5))):
     ctx.reset_counters()
     ctx.enable_timers(TIMERS); ctx.reset_timers()
