@@ -107,3 +107,17 @@ def test_secular_root_relative_accuracy(lib):
             exact = float(Fraction(d[j]) - lam_q)
             assert abs(delta[j] - exact) <= 4 * EPS * abs(exact), (i, j)
         assert d[i] < lam and (i == K - 1 or lam < d[i + 1])
+
+
+def test_symmetric_panel_unit_scheme():
+    """Index scheme of trd_panel_sym_kernel (csrc/eigh.cu) restated in NumPy (tools/proto_trd_sym.py): lower-triangle
+    work units, per-unit dot / row partials, fixed-order summation -- equals the dense product A_trail v for every unit
+    width, odd and even column offsets, and never touches the (NaN-poisoned) upper triangle."""
+    import importlib.util, os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "proto_trd_sym.py")
+    spec = importlib.util.spec_from_file_location("proto_trd_sym", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    cases = [(132, 0, 0, 7, 16), (132, 1, 1, 7, 32), (700, 64, 0, 444, 64), (700, 65, 1, 296, 0), (1100, 131, 3, 30, 32),
+             (1100, 1090, 50, 444, 0), (1540, 7, 7, 296, 16)]
+    assert mod.check(cases, verbose=False) < 1e-13

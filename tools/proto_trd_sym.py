@@ -59,21 +59,30 @@ def consume(c,dotP,zP,pP,ip):
         y[u]=acc
     p1=pP[0,:ip,:].sum(1); p2=pP[1,:ip,:].sum(1)
     return y,p1,p2
-rng=np.random.default_rng(0)
-for n,j,i,G,ftc in [(700,0,0,444,0),(700,1,1,444,0),(1100,64,0,444,16),(1100,65,1,444,32),(2300,130,2,444,64),(2300,131,3,30,64),(2300,2290,50,444,0),(2300,2297,57,444,0),(4700,7,7,444,0),(4700,6,6,296,0)]:
-    A=rng.standard_normal((n,n)); A=A+A.T
-    Aup=A.copy(); A=np.tril(A)+np.triu(np.full((n,n),np.nan),1)   # poison the upper triangle
-    W=rng.standard_normal((n,MAXNB)); V=rng.standard_normal((n,MAXNB))
-    x=np.zeros(n); x[j+1]=1.0; x[j+2:]=rng.standard_normal(n-j-2)
-    # poison rows above j+1 of x-multiplied places with finite garbage: fine
-    c,dotP,zP,pP,yhv=phaseC(A,W,V,n,j,i,G,x,ftc)
-    y,p1,p2=consume(c,dotP,zP,pP,i)
-    yref=Aup[j+1:,j+1:]@x[j+1:]
-    R0=c['R0']
-    err=np.abs(y[c['s']:]-yref).max()/np.abs(yref).max()
-    e1=np.abs(p1-W[j+1:,:i].T@x[j+1:]).max() if i else 0; e2=np.abs(p2-V[j+1:,:i].T@x[j+1:]).max() if i else 0
-    ey=abs(yhv-yref@x[j+1:])/abs(yref@x[j+1:])
-    print(n,j,i,G,c['TC'],c['U'],'err',err,e1,e2,ey)
+def check(cases=None, verbose=True):
+    """Runs the unit scheme against a dense matvec with a NaN-poisoned upper triangle; returns the largest relative error."""
+    rng=np.random.default_rng(0)
+    worst=0.0
+    for n,j,i,G,ftc in cases or [(700,0,0,444,0),(700,1,1,444,0),(1100,64,0,444,16),(1100,65,1,444,32),(2300,130,2,444,64),(2300,131,3,30,64),(2300,2290,50,444,0),(2300,2297,57,444,0),(4700,7,7,444,0),(4700,6,6,296,0)]:
+        A=rng.standard_normal((n,n)); A=A+A.T
+        Aup=A.copy(); A=np.tril(A)+np.triu(np.full((n,n),np.nan),1)   # poison the upper triangle
+        W=rng.standard_normal((n,MAXNB)); V=rng.standard_normal((n,MAXNB))
+        x=np.zeros(n); x[j+1]=1.0; x[j+2:]=rng.standard_normal(n-j-2)
+        # poison rows above j+1 of x-multiplied places with finite garbage: fine
+        c,dotP,zP,pP,yhv=phaseC(A,W,V,n,j,i,G,x,ftc)
+        y,p1,p2=consume(c,dotP,zP,pP,i)
+        yref=Aup[j+1:,j+1:]@x[j+1:]
+        R0=c['R0']
+        err=np.abs(y[c['s']:]-yref).max()/np.abs(yref).max()
+        e1=np.abs(p1-W[j+1:,:i].T@x[j+1:]).max() if i else 0; e2=np.abs(p2-V[j+1:,:i].T@x[j+1:]).max() if i else 0
+        ey=abs(yhv-yref@x[j+1:])/abs(yref@x[j+1:])
+        assert np.isfinite(err) and np.isfinite(ey)
+        worst=max(worst,err,ey)
+        if verbose: print(n,j,i,G,c['TC'],c['U'],'err',err,e1,e2,ey)
+    return worst
+
+if __name__ == '__main__':
+    print('worst', check())
 # efficiency table
 for mu in (8192,6144,4096,2048,1024):
     c=cfg(mu,0,32,444); print(mu,c['TC'],c['U'],c['U']/444)
