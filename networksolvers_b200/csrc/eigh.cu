@@ -462,24 +462,22 @@ __host__ __device__ __forceinline__ int sym_sumfloor(int J, int q) {   // sum_{J
 }
 
 __device__ __forceinline__ SymCfg sym_cfg(int n, int j, int i, int G, int force_tc) {
-  SymCfg best{};
-  float bscore = -1e30f;
+  // Unit width: the widest column block that still fills one round of the grid (measured at n = 8192: fixed 64 -> 315 ms,
+  // 32 -> 330 ms, 16 -> 363 ms, 128 -> 354 ms; wide units amortise the per-unit barrier and partial stores, narrow ones
+  // keep all CTAs busy once the trailing matrix is small).
+  SymCfg c{};
   const int R0 = (j + 1) & ~1, mu = n - R0;
   const int tcs[3] = {64, 32, 16};
-  const float pen[3] = {0.03f, 0.06f, 0.12f};   // traffic of the row partials relative to the matrix read
   for (int t = 0; t < 3; ++t) {
-    if (force_tc && tcs[t] != force_tc) continue;
-    SymCfg c;
-    c.R0 = R0; c.mu = mu; c.s = (int)(j + 1 - R0); c.TC = tcs[t]; c.q = SYM_RC / c.TC;
-    c.nJ = (mu + c.TC - 1) / c.TC; c.nI = (mu + SYM_RC - 1) / SYM_RC;
+    const int TC = force_tc ? force_tc : tcs[t];
+    c.R0 = R0; c.mu = mu; c.s = j + 1 - R0; c.TC = TC; c.q = SYM_RC / TC;
+    c.nJ = (mu + TC - 1) / TC; c.nI = (mu + SYM_RC - 1) / SYM_RC;
     c.UA = c.nJ * c.nI - sym_sumfloor(c.nJ, c.q);
     c.nIW = (mu + 4 * SYM_RC - 1) / (4 * SYM_RC); c.nsetW = (i + 15) / 16; c.UW = 2 * c.nsetW * c.nIW;
     c.U = c.UA + c.UW;
-    const int rounds = (c.U + G - 1) / G;
-    const float score = __fdividef((float)c.U, (float)G * (float)rounds) - pen[t];
-    if (score > bscore) { bscore = score; best = c; }
+    if (force_tc || c.U >= G) break;
   }
-  return best;
+  return c;
 }
 
 struct TrdSymArgs {
@@ -527,7 +525,7 @@ __global__ void __launch_bounds__(256, 2) trd_panel_sym_kernel(const TrdSymArgs 
   cg::grid_group grid = cg::this_grid();
   __shared__ double sv[MAXNB], sw[MAXNB], p1[MAXNB], p2[MAXNB];
   __shared__ double sh[2 * 32 + 2];
-  __shared__ double spart[2 * 64 * 8];   // per column of the unit: 8 warp partials (two buffers, alternating per unit)
+  __shared__ double spart[2 * 128 * 8];   // per column of the unit: 8 warp partials (two buffers, alternating per unit)
   __shared__ __align__(16) double sxw[8][16];   // per warp: x of the 16 columns of the current set
   const int tid = threadIdx.x, nblk = gridDim.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -646,13 +644,13 @@ __global__ void __launch_bounds__(256, 2) trd_panel_sym_kernel(const TrdSymArgs 
     const double* Ablk = a.A + c.R0 + (int64_t)c.R0 * lda;         // element (u, uc) at Ablk[u + uc * lda]
     const int s = c.s, TC = c.TC;
     double yhv[1] = {0.0};
-    const int lq = (TC == 64) ? 3 : ((TC == 32) ? 4 : 5);   // q = SYM_RC / TC = 1 << lq
+    const int lq = (TC == 128) ? 2 : ((TC == 64) ? 3 : ((TC == 32) ? 4 : 5));   // q = SYM_RC / TC = 1 << lq
     auto prefix = [&](int J) { const int aa = J >> lq, bb = J & (c.q - 1); return J * c.nI - (c.q * ((aa * (aa - 1)) >> 1) + aa * bb); };
     int buf = 0;
     for (int unit = blockIdx.x; unit < c.U; unit += nblk, buf ^= 1) {
       // one block barrier per unit: the warp partials alternate between two buffers, so the writers of unit k + 2 have
       // passed the barrier of unit k + 1, which the readers of unit k reach only after reading
-      double* sp = spart + buf * (64 * 8);
+      double* sp = spart + buf * (128 * 8);
       if (unit < c.UW) {
         // ---- panel columns: 16 columns of W or V x 2048 rows ----
         const int t = unit / c.nIW, iw = unit - t * c.nIW;
@@ -1262,7 +1260,7 @@ void Eigh<T>::factor(Ctx* c, T* A, int64_t n_, int64_t lda, bool lower_only_inpu
         coop_grid = per_sm * ctx->num_sms;
         part = DevBuf(ctx, sizeof(double) * coop_grid);
         part2 = DevBuf(ctx, sizeof(double) * coop_grid);
-        dotP = DevBuf(ctx, sizeof(double) * (size_t)(n + 64) * (size_t)(n / SYM_RC + 2));
+        dotP = DevBuf(ctx, sizeof(double) * (size_t)(n + 128) * (size_t)(n / SYM_RC + 2));
         zP = DevBuf(ctx, sizeof(double) * (size_t)(n / SYM_RC + 2) * (size_t)(n / 16 + 2) * SYM_RC);
         pP = DevBuf(ctx, sizeof(double) * 2 * MAXNB * (size_t)(n / (4 * SYM_RC) + 2));
         pack = DevBuf(ctx, sizeof(double) * 4 * (size_t)n * nb);   // [V W] and [W V] of the rank-2w update

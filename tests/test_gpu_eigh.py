@@ -64,7 +64,7 @@ def test_eigh_matches_lapack(ctx, n, nb, coop):
         ctx.set_option("eigh_coop", 1)
 
 
-@pytest.mark.parametrize("tc", [0, 16, 32, 64])
+@pytest.mark.parametrize("tc", [0, 16, 32, 64, 128])
 @pytest.mark.parametrize("n,nb", [(4, 64), (66, 64), (300, 32), (1100, 128), (1538, 64), (2600, 64)])
 def test_eigh_symmetric_panel_kernel(ctx, n, nb, tc):
     """Real FP64, even n: the half-traffic panel kernel (lower-triangle work units, per-unit partials summed in the next

@@ -7,9 +7,11 @@ import numpy as np
 import networksolvers_b200 as ns
 ctx = ns.default_context()
 rng = np.random.default_rng(0)
+for a in [a for a in sys.argv[1:] if "=" in a]:   # context options, e.g. eigh_sym_tc=16
+    k_, v_ = a.split("="); ctx.set_option(k_, int(v_))
 sizes = [int(a) for a in sys.argv[1:] if a.isdigit()] or [1024, 2048, 4096]
 NOCHECK = "nocheck" in sys.argv   # skip the host LAPACK SVD (minutes at n = 8192)
-kinds = [a for a in sys.argv[1:] if not a.isdigit() and a != "nocheck"] or ["gauss", "graded"]
+kinds = [a for a in sys.argv[1:] if not a.isdigit() and a != "nocheck" and "=" not in a] or ["gauss", "graded"]
 for n in sizes:
     for kind in kinds:
         if kind == "gauss":

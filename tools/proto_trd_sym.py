@@ -7,15 +7,14 @@ def sumfloor(J,q):
     a,b=divmod(J,q); return q*a*(a-1)//2+a*b
 def cfg(n,j,i,G,force_tc=0):
     R0=(j+1)&~1; s=j+1-R0; mu=n-R0
-    best=None
-    for TC,pen in ((64,0.03),(32,0.06),(16,0.12)):
-        if force_tc and TC!=force_tc: continue
+    for TC in ((force_tc,) if force_tc else (64,32,16)):      # widest unit that still fills one round of the grid
         q=RC//TC; nJ=-(-mu//TC); nI=-(-mu//RC)
         UA=nJ*nI-sumfloor(nJ,q)
         nIW=-(-mu//(4*RC)); nsetW=-(-i//16); UW=2*nsetW*nIW
-        U=UA+UW; rounds=-(-U//G); eff=U/(G*rounds)-pen
-        if best is None or eff>best[0]: best=(eff,dict(R0=R0,s=s,mu=mu,TC=TC,q=q,nJ=nJ,nI=nI,UA=UA,nIW=nIW,nsetW=nsetW,UW=UW,U=U))
-    return best[1]
+        U=UA+UW
+        c=dict(R0=R0,s=s,mu=mu,TC=TC,q=q,nJ=nJ,nI=nI,UA=UA,nIW=nIW,nsetW=nsetW,UW=UW,U=U)
+        if force_tc or U>=G: break
+    return c
 def decode(c,ka):
     lo,hi=0,c['nJ']-1
     pref=lambda J: J*c['nI']-sumfloor(J,c['q'])
