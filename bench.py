@@ -167,7 +167,7 @@ def run_reference(args, rank, world):
                                    f"(CPU sample at chi={chi})", "chi": args.chi, "cpu_sample_chi": chi},
             "cpu_baseline": {"value": tf, "unit": "TFLOP/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": tf, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def pinned_array(shape, dtype):
@@ -180,7 +180,20 @@ def pinned_array(shape, dtype):
         return np.empty(shape, dtype=dtype, order="F"), None
 
 
+def emit(line):
+    """The one JSON line goes to the process's original stdout; everything else (NCCL's version banner, library
+    chatter written to fd 1 from C) was redirected to stderr at start-up."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -400,7 +413,7 @@ def main():
         if cpu is not None:
             line["cpu_baseline"] = cpu
         line.update(extra)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
