@@ -86,14 +86,14 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_problem(chi, nsites, ctx, dtype=np.float64):
+def build_problem(chi, nsites, ctx, dtype=np.float64, canonical=True):
     import networksolvers_b200 as ns
     g = ns.path_graph(nsites)
     sites = ns.siteinds("S=1/2", g)
     H = ns.ttno(ns.heisenberg(g), sites)
     mid = nsites // 2
     region = [mid, mid + 1]
-    net = ns.DeviceNetwork.synthetic(H, sites, chi, seed=1234, dtype=dtype, ctx=ctx, ortho_region=region)
+    net = ns.DeviceNetwork.synthetic(H, sites, chi, seed=1234, dtype=dtype, ctx=ctx, ortho_region=region, canonical=canonical)
     return net, region
 
 
@@ -210,6 +210,8 @@ def main():
     ap.add_argument("--region-steps", type=int, default=3, help="consecutive region steps timed after the matvec benchmark")
     ap.add_argument("--cutoff", type=float, default=0.0, help="inserter cutoff of the region steps (0: maxdim-limited, SVD-route label; "
                     "1e-9: the reference's timed_dmrg setting, eigen-route label)")
+    ap.add_argument("--no-canonical", action="store_true", help="leave the synthetic state as filled (random tensors, gauge flag only) instead of "
+                    "orthonormalising it to the benchmark bond with device QRs during set-up (about a minute at chi=4096)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -229,14 +231,17 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = ns.Context(local_rank)
-    net, region = build_problem(args.chi, args.nsites, ctx)   # same seed on every rank: replicated state
+    net, region = build_problem(args.chi, args.nsites, ctx, canonical=not args.no_canonical)   # same seed on every rank: replicated state
     t_setup = time.perf_counter()
     info = net.extract(region)
     ctx.synchronize()
     t_setup = time.perf_counter() - t_setup
     legs, dims = net.local_info()
-    flops = net.matvec_flops()
-    assert abs(flops - matvec_flops(dims[0], dims[-1])) < 1e-6 * flops, (flops, dims)
+    flops_dense = net.matvec_flops()
+    assert abs(flops_dense - matvec_flops(dims[0], dims[-1])) < 1e-6 * flops_dense, (flops_dense, dims)
+    # throughput is computed from the flops actually issued: the identity channel of the left / right
+    # environment is skipped when present, the dense-equivalent figure is reported beside it
+    flops = net.matvec_flops_executed()
     shard = None
     if world > 1:
         from networksolvers_b200.parallel import setup_sharded_matvec
@@ -259,6 +264,7 @@ def main():
     for _ in range(args.warmup):
         step()
     barrier()
+    flops = net.matvec_flops_executed() if shard is None else flops_dense   # what the applications above really issued
     ctx.reset_counters()
     with ClockSampler(local_rank) as clk:
         ctx.tic()
@@ -363,7 +369,7 @@ def main():
         H = ns.ttno(ns.heisenberg(g), sites)
         plan = ns.euler_sweep(g, nsites=2)
         first = list(plan[0][0])
-        net2 = ns.DeviceNetwork.synthetic(H, sites, args.chi, seed=1234, ctx=ctx, ortho_region=first)
+        net2 = ns.DeviceNetwork.synthetic(H, sites, args.chi, seed=1234, ctx=ctx, ortho_region=first, canonical=not args.no_canonical)
         prob = ns.EigsolveProblem(net=net2)
         ctx.enable_timers(True)
         ctx.reset_timers()
@@ -402,14 +408,18 @@ def main():
                 "scaling": "strong" if shard is not None else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"S=1/2 Heisenberg chain N={args.nsites}, no QN, 2-site H_eff matvec on bond "
                                        f"({region[0]},{region[1]}), chi={args.chi}, d=2, w=5 (BASELINE config 2)",
-                           "chi": args.chi, "local_dims": dims, "flops_per_step": flops,
+                           "chi": args.chi, "local_dims": dims, "flops_per_step": flops, "dense_flops_per_step": flops_dense,
+                           "flops_note": "value / e2e use the flops actually issued; dense_flops_per_step is the reference's "
+                                         "dense-W count 4 w d^2 chi^3 + 4 w^2 d^3 chi^2 (identity channels of L and R skipped)",
                            "l2": "inputs larger than L2 (L 0.64 GB, theta 0.5 GB, T1 2.5 GB per matvec)",
+                           "state": ("random tensors orthonormalised to the benchmark bond (device QR gauge walk)" if not args.no_canonical else "random tensors, gauge flag only"),
                            "parallelism": ("replicated" if shard is None else f"theta right-bond sharded x{world} + " +
                                            ("fused GEMM/peer-store reduce-scatter + allgather" if args.fused else "NCCL allreduce"))
                            if world > 1 else "single GPU", "setup_s": t_setup, "env_builds": info.env_builds},
                 "e2e": {"value": e2e_tflops, "unit": "TFLOP/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
                         "ms_per_step": e2e_s * 1e3},
-                "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roof}
+                "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roof,
+                "dense_equivalent_tflops": flops_dense / (ms_step * 1e-3) * 1e-12 * (world if shard is None and world > 1 else 1)}
         if cpu is not None:
             line["cpu_baseline"] = cpu
         line.update(extra)

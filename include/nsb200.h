@@ -233,6 +233,10 @@ int nsb_matvec_host(nsb_net* net, const void* host_in, void* host_out);
 int nsb_matvec_device(nsb_net* net, int32_t reps, void* host_out /* nullable */);
 /* analytic flop count (real flops) of one H_eff application at the current position */
 int nsb_matvec_flops(nsb_net* net, double* flops);
+/* flops actually issued per application: the dense count above minus the identity channel of the first / last environment
+ * when it is skipped (ctx option "skip_identity", default on; the channel with E[:, w, :] = 1 of an MPO-like operator
+ * between orthonormal bases contributes theta itself, so no GEMM work is spent on it).  Throughput is reported from this. */
+int nsb_matvec_flops_executed(nsb_net* net, double* flops);
 /* norm of the state = norm of the orthogonality-centre tensor (requires a single-vertex centre) */
 int nsb_norm(nsb_net* net, double* out);
 

@@ -120,6 +120,7 @@ SIGNATURES = {
     "nsb_matvec_host": (C.c_int, [_vp, _vp, _vp]),
     "nsb_matvec_device": (C.c_int, [_vp, _i32, _vp]),
     "nsb_matvec_flops": (C.c_int, [_vp, P(_dbl)]),
+    "nsb_matvec_flops_executed": (C.c_int, [_vp, P(_dbl)]),
     "nsb_norm": (C.c_int, [_vp, P(_dbl)]),
     "nsb_gemm_host": (C.c_int, [_vp, _i32, _i32, _i32, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32]),
     "nsb_gemm_bench": (C.c_int, [_vp, _i32, _i32, _i32, _i64, _i64, _i64, _i32, _i32, P(_dbl)]),

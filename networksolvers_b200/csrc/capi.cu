@@ -160,6 +160,7 @@ int nsb_ctx_set_option(nsb_ctx* ctx, const char* key, int64_t value) {
   else if (k == "jacobi_inner_cap") { NSB_REQUIRE(value >= 1, NSB_EINVAL, "jacobi_inner_cap >= 1"); g_jacobi_inner_cap = (int)value; }
   else if (k == "jacobi_precondition_min_n") { g_jacobi_precondition_min_n = (int)value; }
   else if (k == "big_cache_gib") { NSB_REQUIRE(value >= 0, NSB_EINVAL, "big_cache_gib >= 0"); ctx->c.big_cache_cap = (size_t)value << 30; if (value == 0) ctx->c.flush_big_cache(); }
+  else if (k == "skip_identity") { g_skip_identity = value != 0; }
   else if (k == "merge_site_ops") { g_merge_site_ops = value != 0; }
   else if (k == "eigh_min_n") { g_eigh_min_n = (int)value; }
   else if (k == "eigh_coop") { g_eigh_coop = value != 0; }
@@ -382,6 +383,9 @@ int nsb_matvec_host(nsb_net* net, const void* host_in, void* host_out) {
 }
 int nsb_matvec_device(nsb_net* net, int32_t reps, void* host_out) { NET_CALL(net, net->n->matvec_device(reps, host_out)) }
 int nsb_matvec_flops(nsb_net* net, double* flops) { NET_CALL(net, NSB_REQUIRE(flops, NSB_EINVAL, "null"); *flops = net->n->matvec_flops()) }
+int nsb_matvec_flops_executed(nsb_net* net, double* flops) {
+  NET_CALL(net, NSB_REQUIRE(flops, NSB_EINVAL, "null"); *flops = net->n->matvec_flops_executed())
+}
 int nsb_net_set_shard(nsb_net* net, int32_t enable, int32_t* active) {
   NET_CALL(net, int a = net->n->set_shard(enable); if (active) *active = a)
 }

@@ -21,6 +21,7 @@
 
 namespace nsb {
 
+int g_skip_identity = 1;    // ctx option "skip_identity"
 int g_merge_site_ops = 1;   // 2-site regions: apply W[a] W[b] as one small-operator pass (ctx option "merge_site_ops")
 
 // ------------------------------------------------------------------------------------------------
@@ -430,6 +431,11 @@ int Net<T>::make_env(int u, int v) {
   if (E.labels != want) E = permuted(ctx, E, want);
   Env env;
   env.t = E;
+  if (g_skip_identity && !fit_mode && E.rank() == 3 && E.dims[0] == E.dims[2] && E.dims[1] >= 2 && E.dims[1] <= 64) {
+    std::vector<double> dev(E.dims[1]);
+    identity_deviation<T>(ctx, E.data(), E.dims[0], E.dims[1], dev.data());
+    for (int64_t w = 0; w < E.dims[1]; ++w) if (dev[w] <= 1e-10) { env.ident = (int)w; break; }
+  }
   env.deps.push_back({u, ver[u]});
   for (int n : others) for (auto& d : envs.at({n, u}).deps) env.deps.push_back(d);
   envs[key] = env;
@@ -492,7 +498,47 @@ int Net<T>::position(const std::vector<int>& reg) {
     for (int n : adj[v])
       if (std::find(reg.begin(), reg.end(), n) == reg.end()) built += make_env(n, v);
   build_plan();
+  prepare_identity_skip();
   return built;
+}
+
+// First environment of the plan: when it has an identity channel, keep a copy without that channel ([ket, W - 1, bra]); apply_heff contracts theta with it and splices theta itself in as the
+// missing channel.  (The last environment needs no copy: its channel is a contiguous block of the contraction index.)
+template <typename T>
+void Net<T>::prepare_identity_skip() {
+  skipped_last_apply = -1.0;
+  first_ident = -1;
+  first_compact = DTensor<T>();
+  if (!g_skip_identity || fit_mode || plan.size() < 2 || plan.front().type != 0) return;
+  const Env& e = envs.at({plan.front().u, plan.front().v});
+  const DTensor<T>& E = e.t;
+  if (e.ident < 0 || E.rank() != 3) return;
+  const int64_t n = E.dims[0], Wd = E.dims[1], n2 = E.dims[2];
+  if (n != n2 || Wd < 2) return;
+  first_compact = DTensor<T>(ctx, {n, Wd - 1, n2}, E.labels);
+  const int64_t w = e.ident;   // channels [0, w) and (w, Wd) keep their order
+  if (w > 0) copy_block<T>(ctx, E.data(), n * Wd, first_compact.data(), n * (Wd - 1), n * w, n2);
+  if (w < Wd - 1) copy_block<T>(ctx, E.data() + n * (w + 1), n * Wd, first_compact.data() + n * w, n * (Wd - 1), n * (Wd - 1 - w), n2);
+  first_ident = e.ident;
+}
+
+template <typename T>
+double Net<T>::skipped_flops(const DTensor<T>& x) const {
+  // dry run of the conditions of apply_heff on the labels of x (the site-operator steps keep the big modes in place, so
+  // the tensor that meets the last environment has x's link at the same end with the operator link next to it)
+  if (!g_skip_identity || shard_active || fit_mode || plan.size() < 2 || x.rank() < 2) return 0.0;
+  double f = 0.0;
+  const double cplx = ScalarTraits<T>::is_complex ? 4.0 : 1.0;
+  if (first_ident >= 0 && first_compact.valid() && plan.front().type == 0) {
+    const DTensor<T>& E = envs.at({plan.front().u, plan.front().v}).t;
+    if (E.dims[0] == E.dims[2] && (x.labels[0] == E.labels[0] || x.labels.back() == E.labels[0])) f += 2.0 * (double)x.numel() * (double)E.dims[2];
+  }
+  if (plan.back().type == 0) {
+    const Env& e = envs.at({plan.back().u, plan.back().v});
+    if (e.ident >= 0 && e.t.rank() == 3 && e.t.dims[0] == e.t.dims[2] && (x.labels.back() == e.t.labels[0] || x.labels[0] == e.t.labels[0]))
+      f += 2.0 * (double)x.numel() * (double)e.t.dims[2];
+  }
+  return f * cplx;
 }
 
 template <typename T> struct NcclType;
@@ -590,14 +636,87 @@ DTensor<T> Net<T>::apply_heff(const DTensor<T>& x) {
     ctx->cnt.matvecs++;
     return out;
   }
-  for (auto& s : plan) {
+  size_t i0 = 0, i1 = plan.size();
+  const T one = from_complex<T>(1.0, 0.0);
+  double skipped = 0.0;
+  if (first_ident >= 0 && first_compact.valid() && !fit_mode && plan.size() >= 2 && plan[0].type == 0) {
+    // T1 = x * L over L's ket link: the channel with L[:, w*, :] = 1 is x itself -- contract with the W - 1 other
+    // channels and splice x in as the missing channel of the operator link.  Two layouts occur on the permutation-free
+    // chain path: the ket link is x's first mode (result [w, bra, rest of x]) or x's last mode (result [rest of x, w, bra]).
+    const DTensor<T>& E = envs.at({plan[0].u, plan[0].v}).t;
+    const int64_t Wd = E.dims[1];
+    const int r = X.rank();
+    std::vector<Label> pl;
+    int64_t pre = 0;
+    if (r >= 2 && E.dims[0] == E.dims[2] && contract_direct_labels(X, first_compact, &pl) && (int)pl.size() == r + 1) {
+      if (X.labels[0] == E.labels[0] && pl[0] == E.labels[1] && pl[1] == E.labels[2]) pre = 1;
+      else if (X.labels[r - 1] == E.labels[0] && pl[r - 1] == E.labels[1] && pl[r] == E.labels[2]) pre = X.numel() / X.dims[r - 1];
+    }
+    if (pre > 0) {
+      DTensor<T> Xc = contract(ctx, X, first_compact, false, false, 1);
+      NSB_REQUIRE(Xc.labels == pl, NSB_EINTERNAL, "identity skipping: unexpected layout of the first contraction");
+      const int wpos = (pre == 1) ? 0 : r - 1;
+      std::vector<int64_t> fd = Xc.dims;
+      fd[wpos] = Wd;
+      DTensor<T> Xf(ctx, fd, Xc.labels);
+      const int64_t post = X.numel() / pre;   // extent of the bra link (x minus the modes in front of the operator link)
+      insert_mode<T>(ctx, Xc.data(), X.data(), Xf.data(), pre, Wd - 1, first_ident, post);
+      X = Xf;
+      i0 = 1;
+      skipped += 2.0 * (double)x.numel() * (double)E.dims[2];
+    }
+  }
+  int last_w = -1;
+  if (g_skip_identity && !fit_mode && plan.size() >= 2 && plan.back().type == 0) {
+    const Env& e = envs.at({plan.back().u, plan.back().v});
+    if (e.ident >= 0 && e.t.rank() == 3 && e.t.dims[0] == e.t.dims[2]) { last_w = e.ident; i1 = plan.size() - 1; }
+  }
+  for (size_t i = i0; i < i1; ++i) {
+    auto& s = plan[i];
     if (s.type == 0) X = contract(ctx, X, envs.at({s.u, s.v}).t, false, false, 1);
     else if (s.type == 1) X = apply_small(ctx, s.op, X, W[s.v], w_out_labels(X, W[s.v], s.v, pos));
     else X = apply_small(ctx, s.op, X, s.Wm, merged_out_labels(X, s.u, s.v));
   }
+  if (last_w >= 0) {
+    // The last environment R[(b, w), b'] is contracted over (ket link, operator link); the block w = w* of that
+    // contraction index meets the identity, so the result starts as that block of X and the other channels are added by
+    // at most two GEMMs (beta = 1).  Layouts: (b, w) are X's last two modes (out[p, b'] = X[p, K] R[K, b']) or its first
+    // two (out[b', q] = R[K, b']^T X[K, q]).
+    const DTensor<T>& E = envs.at({plan.back().u, plan.back().v}).t;
+    const int r = X.rank();
+    const int64_t nb = E.dims[0], Wd = E.dims[1], N = E.dims[2], Kc = nb * Wd;
+    const int64_t k0 = nb * last_w, k1 = nb * (last_w + 1);    // identity block [k0, k1) of the contraction index
+    if (r >= 3 && X.labels[r - 2] == E.labels[0] && X.labels[r - 1] == E.labels[1] && X.dims[r - 2] == nb && X.dims[r - 1] == Wd) {
+      const int64_t P = X.numel() / Kc;
+      std::vector<int64_t> od(X.dims.begin(), X.dims.end() - 2);
+      std::vector<Label> ol(X.labels.begin(), X.labels.end() - 2);
+      od.push_back(N); ol.push_back(E.labels[2]);
+      DTensor<T> out(ctx, od, ol);
+      vec_copy<T>(ctx, P * nb, X.data() + P * k0, out.data());
+      if (k0 > 0) gemm<T>(ctx, OP_N, OP_N, P, N, k0, one, X.data(), P, 0, E.data(), Kc, 0, one, out.data(), P, 0, 1);
+      if (k1 < Kc) gemm<T>(ctx, OP_N, OP_N, P, N, Kc - k1, one, X.data() + P * k1, P, 0, E.data() + k1, Kc, 0, one, out.data(), P, 0, 1);
+      X = out;
+      skipped += 2.0 * (double)P * (double)nb * (double)N;
+    } else if (r >= 3 && X.labels[0] == E.labels[0] && X.labels[1] == E.labels[1] && X.dims[0] == nb && X.dims[1] == Wd) {
+      const int64_t Q = X.numel() / Kc;
+      std::vector<int64_t> od{N};
+      std::vector<Label> ol{E.labels[2]};
+      od.insert(od.end(), X.dims.begin() + 2, X.dims.end());
+      ol.insert(ol.end(), X.labels.begin() + 2, X.labels.end());
+      DTensor<T> out(ctx, od, ol);
+      copy_block<T>(ctx, X.data() + k0, Kc, out.data(), N, nb, Q);
+      if (k0 > 0) gemm<T>(ctx, OP_T, OP_N, N, Q, k0, one, E.data(), Kc, 0, X.data(), Kc, 0, one, out.data(), N, 0, 1);
+      if (k1 < Kc) gemm<T>(ctx, OP_T, OP_N, N, Q, Kc - k1, one, E.data() + k1, Kc, 0, X.data() + k1, Kc, 0, one, out.data(), N, 0, 1);
+      X = out;
+      skipped += 2.0 * (double)Q * (double)nb * (double)N;
+    } else {
+      X = contract(ctx, X, E, false, false, 1);
+    }
+  }
   X = X.noprime();
   if (!fit_mode && X.labels != x.labels) X = permuted(ctx, X, x.labels);   // (fitting: the result lives on psi's links)
   ctx->cnt.matvecs++;
+  skipped_last_apply = skipped * (ScalarTraits<T>::is_complex ? 4.0 : 1.0);
   return X;
 }
 
@@ -675,6 +794,12 @@ double Net<T>::matvec_flops() {
     lab = nl; dim = nd;
   }
   return flops * (ScalarTraits<T>::is_complex ? 4.0 : 1.0);
+}
+
+template <typename T>
+double Net<T>::matvec_flops_executed() {
+  // after an application at this position: what it really skipped; before: the dry run of the same conditions
+  return matvec_flops() - (skipped_last_apply >= 0.0 ? skipped_last_apply : skipped_flops(theta));
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -12,6 +12,7 @@
 namespace nsb {
 
 extern int g_merge_site_ops;
+extern int g_skip_identity;   // skip the identity channel of the first / last environment of an H_eff application
 
 struct NetBase {
   Ctx* ctx = nullptr;
@@ -40,6 +41,7 @@ struct NetBase {
   virtual void matvec_host(const void* in, void* out) = 0;
   virtual void matvec_device(int reps, void* host_out) = 0;
   virtual double matvec_flops() = 0;
+  virtual double matvec_flops_executed() = 0;
   virtual double norm() = 0;
   virtual int set_shard(int enable) = 0;   // returns 1 if the current position is sharded across ranks
   // abelian quantum numbers (dense storage, block-wise factorisations)
@@ -62,7 +64,9 @@ struct Net : public NetBase {
   // projected operator
   std::vector<int> pos;                         // current region (vertices); empty before the first extract
   bool pos_on_edge = false;
-  struct Env { DTensor<T> t; std::vector<std::pair<int, uint64_t>> deps; };
+  // ident: operator-link channel w with t[:, w, :] = identity to 1e-10 (the "nothing to the left / right yet" channel of an
+  // MPO-like operator between orthonormal bases), -1 if none
+  struct Env { DTensor<T> t; std::vector<std::pair<int, uint64_t>> deps; int ident = -1; };
   std::map<std::pair<int, int>, Env> envs;      // key (u, v): everything on u's side, pointing into v
   // local problem
   DTensor<T> theta;
@@ -72,6 +76,12 @@ struct Net : public NetBase {
   struct Step { int type; int u, v; SmallOp<T> op; DTensor<T> Wm; };
   std::vector<Step> plan;
   DTensor<T> last_out;                          // result of the last nsb_matvec_device
+  // identity-channel skipping (g_skip_identity): first environment of the plan without its identity channel
+  int first_ident = -1;
+  DTensor<T> first_compact;
+  void prepare_identity_skip();
+  double skipped_flops(const DTensor<T>& x) const;   // real flops per application the skipping saves (dry run)
+  double skipped_last_apply = -1.0;                  // what the last apply_heff actually skipped (< 0: none ran yet)
   // multi-GPU: theta sharded along its last bond across the ranks of ctx->nccl_comm
   bool shard_enabled = false, shard_active = false;
   int64_t shard_lo = 0, shard_hi = 0;
@@ -156,6 +166,7 @@ struct Net : public NetBase {
   void matvec_host(const void* in, void* out) override;
   void matvec_device(int reps, void* host_out) override;
   double matvec_flops() override;
+  double matvec_flops_executed() override;
   double norm() override;
   int set_shard(int enable) override;
   void qn_enable(int nq, const int32_t* total) override;

@@ -348,6 +348,63 @@ __global__ void concat_kernel(const T* __restrict__ A, const T* __restrict__ B, 
     out[i] = v;
   }
 }
+// out[pre, m + 1, post]: slice `pos` of the middle mode comes from B[pre, post], the others from A[pre, m, post] in order
+template <typename T>
+__global__ void insert_mode_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ out, int64_t pre,
+                                   int64_t m, int64_t pos, int64_t post) {
+  const int64_t w = m + 1, total = pre * w * post;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = i % pre, rest = i / pre;
+    const int64_t j = rest % w, q = rest / w;
+    out[i] = (j == pos) ? B[p + pre * q] : A[p + pre * ((j - (j > pos ? 1 : 0)) + m * q)];
+  }
+}
+template <typename T>
+void insert_mode(Ctx* ctx, const T* A, const T* B, T* out, int64_t pre, int64_t m, int64_t pos, int64_t post) {
+  const int64_t total = pre * (m + 1) * post;
+  if (total == 0) return;
+  insert_mode_kernel<T><<<grid_for(ctx, total, 256), 256, 0, ctx->stream>>>(A, B, out, pre, m, pos, post);
+  LAUNCH_CHECK(ctx);
+}
+
+// out[w] = max over (a, a') of |E[a, w, a'] - delta(a, a')| for E stored [n, W, n] column-major (an environment whose
+// channel w is the identity has out[w] ~ eps).  One CTA per column (w, a'); the maxima meet through atomicMax on the bit
+// pattern of the non-negative double (a NaN compares larger than every finite value).
+template <typename T>
+__global__ void __launch_bounds__(256) ident_dev_kernel(const T* __restrict__ E, int64_t n, int64_t W, unsigned long long* __restrict__ out) {
+  __shared__ double red[8];
+  for (int64_t col = blockIdx.x; col < W * n; col += gridDim.x) {
+    const int64_t w = col % W, ap = col / W;
+    double m = 0.0;
+    for (int64_t a = threadIdx.x; a < n; a += blockDim.x) {
+      const T v = E[a + n * col];
+      const double dr = re(v) - (a == ap ? 1.0 : 0.0), di = im(v);
+      const double d = fabs(dr) + fabs(di);
+      if (!(d <= m)) m = d;
+    }
+    for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_xor_sync(0xffffffffu, m, o); if (!(t <= m)) m = t; }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int k = 1; k < (int)(blockDim.x >> 5); ++k) if (!(red[k] <= m)) m = red[k];
+      atomicMax(out + w, (unsigned long long)__double_as_longlong(m));
+    }
+  }
+}
+template <typename T>
+void identity_deviation(Ctx* ctx, const T* E, int64_t n, int64_t W, double* out_host) {
+  NSB_REQUIRE(W >= 1 && W <= 64, NSB_EINVAL, "identity_deviation: operator link too large");
+  unsigned long long* d = reinterpret_cast<unsigned long long*>(ctx->d_scratch);
+  NSB_CUDA(cudaMemsetAsync(d, 0, sizeof(unsigned long long) * W, ctx->stream));
+  const int grid = (int)std::min<int64_t>(W * n, (int64_t)ctx->num_sms * 8);
+  ident_dev_kernel<T><<<grid, 256, 0, ctx->stream>>>(E, n, W, d);
+  LAUNCH_CHECK(ctx);
+  NSB_CUDA(cudaMemcpyAsync(ctx->h_pinned, d, sizeof(double) * W, cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->sync();
+  for (int64_t w = 0; w < W; ++w) out_host[w] = ctx->h_pinned[w];   // same bit pattern
+}
+
 template <typename T>
 void concat_mode(Ctx* ctx, const T* A, const T* B, T* out, int64_t pre, int64_t a, int64_t b, int64_t post) {
   int64_t total = pre * (a + b) * post;
@@ -466,6 +523,8 @@ void col_norms2(Ctx* ctx, const T* A, int64_t rows, int64_t cols, int64_t ld, do
   template void gather_cols<T>(Ctx*, const T*, int64_t, int64_t, const int32_t*, int64_t, const double*, T*, int64_t); \
   template void gather_rows<T>(Ctx*, const T*, int64_t, const int32_t*, int64_t, int64_t, T*, int64_t);              \
   template void concat_mode<T>(Ctx*, const T*, const T*, T*, int64_t, int64_t, int64_t, int64_t);                      \
+  template void identity_deviation<T>(Ctx*, const T*, int64_t, int64_t, double*);                                      \
+  template void insert_mode<T>(Ctx*, const T*, const T*, T*, int64_t, int64_t, int64_t, int64_t);                      \
   template void fill_normal<T>(Ctx*, T*, int64_t, uint64_t, double);                                                   \
   template void set_identity<T>(Ctx*, T*, int64_t, int64_t, int64_t);                                                  \
   template void sum_slabs<T>(Ctx*, const T*, int, int64_t, T*);                                                        \

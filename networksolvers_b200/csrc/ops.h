@@ -41,6 +41,10 @@ template <typename T> void gather_cols(Ctx* ctx, const T* in, int64_t ld, int64_
 // gather rows: out[i, :] = in[idx[i], :]
 template <typename T> void gather_rows(Ctx* ctx, const T* in, int64_t ld, const int32_t* idx_dev, int64_t nrows, int64_t ncols, T* out, int64_t ldo);
 // concatenate along one mode: out[pre, a+b, post] from A[pre, a, post], B[pre, b, post] (B nullable => zero pad)
+// max_{a,a'} |E[a, w, a'] - delta| per channel w of an [n, W, n] tensor, returned on the host (synchronises)
+template <typename T> void identity_deviation(Ctx* ctx, const T* E, int64_t n, int64_t W, double* out_host);
+// out[pre, m + 1, post] = A[pre, m, post] with B[pre, post] inserted as slice `pos` of the middle mode
+template <typename T> void insert_mode(Ctx* ctx, const T* A, const T* B, T* out, int64_t pre, int64_t m, int64_t pos, int64_t post);
 template <typename T> void concat_mode(Ctx* ctx, const T* A, const T* B, T* out, int64_t pre, int64_t a, int64_t b, int64_t post);
 // Philox-4x32 N(0,1) fill (real and imaginary parts independent), scaled
 template <typename T> void fill_normal(Ctx* ctx, T* x, int64_t n, uint64_t seed, double scale);

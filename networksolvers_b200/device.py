@@ -221,7 +221,7 @@ class DeviceNetwork:
         return out.astype(np.int64)
 
     @classmethod
-    def synthetic(cls, operator: HostTTN, sites, chi, seed=1234, dtype=np.float64, ctx=None, ortho_region=None):
+    def synthetic(cls, operator: HostTTN, sites, chi, seed=1234, dtype=np.float64, ctx=None, ortho_region=None, canonical=False):
         """Network whose state tensors are filled on the device (Philox N(0,1), scaled so that environments stay
         O(1)) with uniform bond dimension chi capped by d^k at the ends: the synthetic state of SURVEY 8(d)
         config 2, without moving 25 GiB over PCIe."""
@@ -236,8 +236,12 @@ class DeviceNetwork:
             numel = int(np.prod([d[l] for l in legs]))
             scale = 1.0 / np.sqrt(max(numel / d[legs[-1]], 1.0)) if len(legs) > 1 else 1.0
             net.fill_random(v, d, seed + 7 * i, scale)
-        if ortho_region is not None:
-            net.set_ortho_region(ortho_region)
+        if canonical:
+            # random tensors carry no gauge: declare every vertex part of the orthogonality region, so that the first
+            # extract walks the whole network (one device QR per edge) exactly as for itn.random_mps / random_tensornetwork
+            net.set_ortho_region(list(g.vertices))
+        elif ortho_region is not None:
+            net.set_ortho_region(ortho_region)     # gauge flag only (tensors stay as filled): skips the walk
         return net
 
     def close(self):
@@ -437,4 +441,10 @@ class DeviceNetwork:
     def matvec_flops(self):
         f = C.c_double()
         self.ctx.check(self._lib.nsb_matvec_flops(self.handle, C.byref(f)))
+        return f.value
+
+    def matvec_flops_executed(self):
+        """Flops actually issued per H_eff application (dense count minus skipped identity channels)."""
+        f = C.c_double()
+        self.ctx.check(self._lib.nsb_matvec_flops_executed(self.handle, C.byref(f)))
         return f.value

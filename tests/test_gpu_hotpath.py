@@ -257,6 +257,39 @@ def test_chain_region_steps_are_permutation_free(cplx):
     assert c["matvecs"] == 15
 
 
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("nsites", [2, 1])
+def test_identity_channel_skipping(cplx, nsites):
+    """ctx option skip_identity: the channel of the left / right environment that is the identity (orthonormal bases,
+    MPO with a pass-through channel) is not contracted -- theta is spliced in instead.  Same H_eff theta as the dense
+    contraction to rounding, fewer flops issued, in both sweep directions; a non-canonical state has no such channel."""
+    ns = _ns()
+    g = ns.path_graph(10)
+    sites = ns.siteinds("S=1/2", g)
+    H = ns.ttno(ns.heisenberg(g), sites)
+    psi = ns.random_state(sites, 24, seed=11, dtype=complex if cplx else float)
+    net = ns.EigsolveProblem(state=psi, operator=H).net
+    ctx = net.ctx
+    regions = ([4, 5], [5, 6], [6, 5], [5, 4]) if nsites == 2 else ([4], [5], [6], [5], [4])
+    try:
+        for region in regions:
+            outs, flops = {}, {}
+            for skip in (1, 0):
+                ctx.set_option("skip_identity", skip)
+                net.extract(region)          # (re-positions: the compact copy of the first environment follows the option)
+                theta, _ = net.local_download()
+                outs[skip] = net.matvec_host(theta)
+                flops[skip] = (net.matvec_flops(), net.matvec_flops_executed())
+            err = np.abs(outs[1] - outs[0]).max() / np.abs(outs[0]).max()
+            assert err < 1e-13, (region, err)
+            assert flops[0][0] == flops[0][1] == flops[1][0]
+            assert flops[1][1] < 0.9 * flops[1][0], (region, flops)      # one of w = 5 channels on each side
+            ctx.set_option("skip_identity", 1)
+            net.extract(region); net.update_eigsolve(); net.insert((0.0, 1, 24))
+    finally:
+        ctx.set_option("skip_identity", 1)
+
+
 def test_sharded_matvec_two_gpus():
     """theta sharded along its last bond over 2 ranks + NCCL all-reduce == single-GPU matvec."""
     import os, subprocess, sys
