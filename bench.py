@@ -264,7 +264,7 @@ def main():
     for _ in range(args.warmup):
         step()
     barrier()
-    flops = net.matvec_flops_executed() if shard is None else flops_dense   # what the applications above really issued
+    flops = net.matvec_flops_executed()   # what the applications above really issued (whole job, all ranks)
     ctx.reset_counters()
     with ClockSampler(local_rank) as clk:
         ctx.tic()

@@ -161,6 +161,7 @@ int nsb_ctx_set_option(nsb_ctx* ctx, const char* key, int64_t value) {
   else if (k == "jacobi_precondition_min_n") { g_jacobi_precondition_min_n = (int)value; }
   else if (k == "big_cache_gib") { NSB_REQUIRE(value >= 0, NSB_EINVAL, "big_cache_gib >= 0"); ctx->c.big_cache_cap = (size_t)value << 30; if (value == 0) ctx->c.flush_big_cache(); }
   else if (k == "skip_identity") { g_skip_identity = value != 0; }
+  else if (k == "skip_identity_sharded") { g_skip_identity_sharded = value != 0; }
   else if (k == "merge_site_ops") { g_merge_site_ops = value != 0; }
   else if (k == "eigh_min_n") { g_eigh_min_n = (int)value; }
   else if (k == "eigh_coop") { g_eigh_coop = value != 0; }

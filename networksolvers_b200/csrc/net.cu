@@ -22,6 +22,7 @@
 namespace nsb {
 
 int g_skip_identity = 1;    // ctx option "skip_identity"
+int g_skip_identity_sharded = 1;   // the same inside the multi-GPU (sharded) application; ctx option "skip_identity_sharded"
 int g_merge_site_ops = 1;   // 2-site regions: apply W[a] W[b] as one small-operator pass (ctx option "merge_site_ops")
 
 // ------------------------------------------------------------------------------------------------
@@ -526,7 +527,7 @@ template <typename T>
 double Net<T>::skipped_flops(const DTensor<T>& x) const {
   // dry run of the conditions of apply_heff on the labels of x (the site-operator steps keep the big modes in place, so
   // the tensor that meets the last environment has x's link at the same end with the operator link next to it)
-  if (!g_skip_identity || shard_active || fit_mode || plan.size() < 2 || x.rank() < 2) return 0.0;
+  if (!g_skip_identity || (shard_active && (!g_skip_identity_sharded || ctx->shard_fused)) || fit_mode || plan.size() < 2 || x.rank() < 2) return 0.0;
   double f = 0.0;
   const double cplx = ScalarTraits<T>::is_complex ? 4.0 : 1.0;
   if (first_ident >= 0 && first_compact.valid() && plan.front().type == 0) {
@@ -580,6 +581,35 @@ int Net<T>::set_shard(int enable) {
   return shard_active ? 1 : 0;
 }
 
+// T1 = X * L over L's ket link, where L is the first environment of the plan: the channel with L[:, w*, :] = 1 is X itself --
+// contract with the W - 1 other channels (first_compact) and splice X in as the missing channel of the operator link.  Two
+// layouts occur on the permutation-free chain path: the ket link is X's first mode (result [w, bra, rest of X]) or X's last
+// mode (result [rest of X, w, bra]).  Returns false (X untouched) when the pattern does not apply.
+template <typename T>
+bool Net<T>::skip_first_identity(DTensor<T>& X) {
+  if (!(first_ident >= 0 && first_compact.valid() && !fit_mode && plan.size() >= 2 && plan[0].type == 0)) return false;
+  const DTensor<T>& E = envs.at({plan[0].u, plan[0].v}).t;
+  const int64_t Wd = E.dims[1];
+  const int r = X.rank();
+  std::vector<Label> pl;
+  int64_t pre = 0;
+  if (r >= 2 && E.dims[0] == E.dims[2] && contract_direct_labels(X, first_compact, &pl) && (int)pl.size() == r + 1) {
+    if (X.labels[0] == E.labels[0] && pl[0] == E.labels[1] && pl[1] == E.labels[2]) pre = 1;
+    else if (X.labels[r - 1] == E.labels[0] && pl[r - 1] == E.labels[1] && pl[r] == E.labels[2]) pre = X.numel() / X.dims[r - 1];
+  }
+  if (pre <= 0) return false;
+  DTensor<T> Xc = contract(ctx, X, first_compact, false, false, 1);
+  NSB_REQUIRE(Xc.labels == pl, NSB_EINTERNAL, "identity skipping: unexpected layout of the first contraction");
+  const int wpos = (pre == 1) ? 0 : r - 1;
+  std::vector<int64_t> fd = Xc.dims;
+  fd[wpos] = Wd;
+  DTensor<T> Xf(ctx, fd, Xc.labels);
+  const int64_t post = X.numel() / pre;   // pre = 1: all of X behind the operator link; else the extent of the bra link
+  insert_mode<T>(ctx, Xc.data(), X.data(), Xf.data(), pre, Wd - 1, first_ident, post);
+  X = Xf;
+  return true;
+}
+
 template <typename T>
 DTensor<T> Net<T>::apply_heff(const DTensor<T>& x) {
   DTensor<T> X = x;
@@ -587,7 +617,10 @@ DTensor<T> Net<T>::apply_heff(const DTensor<T>& x) {
     DTensor<T> out(ctx, x.dims, x.labels);
     if (shard_hi > shard_lo) {
       X = x.last_mode_slab(shard_lo, shard_hi);
-      for (size_t i = 0; i + 1 < plan.size(); ++i) {
+      double skipped = 0.0;    // whole-job count (summed over the ranks' slabs)
+      size_t i0 = 0;
+      if (g_skip_identity_sharded && skip_first_identity(X)) { i0 = 1; skipped += 2.0 * (double)x.numel() * (double)envs.at({plan[0].u, plan[0].v}).t.dims[2]; }
+      for (size_t i = i0; i + 1 < plan.size(); ++i) {
         auto& s = plan[i];
         if (s.type == 0) X = contract(ctx, X, envs.at({s.u, s.v}).t, false, false, 1);
         else if (s.type == 1) X = apply_small(ctx, s.op, X, W[s.v], w_out_labels(X, W[s.v], s.v, pos));
@@ -622,11 +655,34 @@ DTensor<T> Net<T>::apply_heff(const DTensor<T>& x) {
                                  (ncclComm_t)ctx->nccl_comm, ctx->stream);
         if (r != ncclSuccess) throw Error(NSB_ENCCL, std::string("ncclAllGather: ") + nccl_api().GetErrorString(r));
         ctx->cnt.matvecs++;
+        skipped_last_apply = skipped * (ScalarTraits<T>::is_complex ? 4.0 : 1.0);
         return out;
       }
-      X = contract(ctx, X, shard_env, false, false, 1).noprime();
+      // identity channel of the last environment: rows (b in slab, w*) of the slab's contraction index meet the identity,
+      // i.e. that block of X is this rank's contribution to columns [shard_lo, shard_hi) of the result
+      const Env& le = envs.at({plan.back().u, plan.back().v});
+      const int rr = X.rank();
+      const int64_t rows = shard_hi - shard_lo, Wd = shard_env.rank() == 3 ? shard_env.dims[1] : 0, N = shard_env.rank() == 3 ? shard_env.dims[2] : 0;
+      if (g_skip_identity && g_skip_identity_sharded && !ctx->shard_fused && le.ident >= 0 && shard_env.rank() == 3 && le.t.dims[0] == N && rr >= 3 &&
+          X.labels[rr - 2] == shard_env.labels[0] && X.labels[rr - 1] == shard_env.labels[1] && X.dims[rr - 2] == rows && X.dims[rr - 1] == Wd) {
+        const T one = from_complex<T>(1.0, 0.0);
+        const int64_t Kc = rows * Wd, P = X.numel() / Kc, k0 = rows * le.ident, k1 = rows * (le.ident + 1);
+        std::vector<int64_t> od(X.dims.begin(), X.dims.end() - 2);
+        std::vector<Label> ol(X.labels.begin(), X.labels.end() - 2);
+        od.push_back(N); ol.push_back(shard_env.labels[2]);
+        DTensor<T> o2(ctx, od, ol);
+        vec_zero<T>(ctx, o2.numel(), o2.data());
+        vec_copy<T>(ctx, P * rows, X.data() + P * k0, o2.data() + P * shard_lo);
+        if (k0 > 0) gemm<T>(ctx, OP_N, OP_N, P, N, k0, one, X.data(), P, 0, shard_env.data(), Kc, 0, one, o2.data(), P, 0, 1);
+        if (k1 < Kc) gemm<T>(ctx, OP_N, OP_N, P, N, Kc - k1, one, X.data() + P * k1, P, 0, shard_env.data() + k1, Kc, 0, one, o2.data(), P, 0, 1);
+        skipped += 2.0 * (double)P * (double)N * (double)N;
+        X = o2.noprime();
+      } else {
+        X = contract(ctx, X, shard_env, false, false, 1).noprime();
+      }
       if (X.labels != x.labels) X = permuted(ctx, X, x.labels);
       out = X;
+      skipped_last_apply = skipped * (ScalarTraits<T>::is_complex ? 4.0 : 1.0);
     } else {
       vec_zero<T>(ctx, out.numel(), out.data());
     }
@@ -639,33 +695,7 @@ DTensor<T> Net<T>::apply_heff(const DTensor<T>& x) {
   size_t i0 = 0, i1 = plan.size();
   const T one = from_complex<T>(1.0, 0.0);
   double skipped = 0.0;
-  if (first_ident >= 0 && first_compact.valid() && !fit_mode && plan.size() >= 2 && plan[0].type == 0) {
-    // T1 = x * L over L's ket link: the channel with L[:, w*, :] = 1 is x itself -- contract with the W - 1 other
-    // channels and splice x in as the missing channel of the operator link.  Two layouts occur on the permutation-free
-    // chain path: the ket link is x's first mode (result [w, bra, rest of x]) or x's last mode (result [rest of x, w, bra]).
-    const DTensor<T>& E = envs.at({plan[0].u, plan[0].v}).t;
-    const int64_t Wd = E.dims[1];
-    const int r = X.rank();
-    std::vector<Label> pl;
-    int64_t pre = 0;
-    if (r >= 2 && E.dims[0] == E.dims[2] && contract_direct_labels(X, first_compact, &pl) && (int)pl.size() == r + 1) {
-      if (X.labels[0] == E.labels[0] && pl[0] == E.labels[1] && pl[1] == E.labels[2]) pre = 1;
-      else if (X.labels[r - 1] == E.labels[0] && pl[r - 1] == E.labels[1] && pl[r] == E.labels[2]) pre = X.numel() / X.dims[r - 1];
-    }
-    if (pre > 0) {
-      DTensor<T> Xc = contract(ctx, X, first_compact, false, false, 1);
-      NSB_REQUIRE(Xc.labels == pl, NSB_EINTERNAL, "identity skipping: unexpected layout of the first contraction");
-      const int wpos = (pre == 1) ? 0 : r - 1;
-      std::vector<int64_t> fd = Xc.dims;
-      fd[wpos] = Wd;
-      DTensor<T> Xf(ctx, fd, Xc.labels);
-      const int64_t post = X.numel() / pre;   // extent of the bra link (x minus the modes in front of the operator link)
-      insert_mode<T>(ctx, Xc.data(), X.data(), Xf.data(), pre, Wd - 1, first_ident, post);
-      X = Xf;
-      i0 = 1;
-      skipped += 2.0 * (double)x.numel() * (double)E.dims[2];
-    }
-  }
+  if (skip_first_identity(X)) { i0 = 1; skipped += 2.0 * (double)x.numel() * (double)envs.at({plan[0].u, plan[0].v}).t.dims[2]; }
   int last_w = -1;
   if (g_skip_identity && !fit_mode && plan.size() >= 2 && plan.back().type == 0) {
     const Env& e = envs.at({plan.back().u, plan.back().v});

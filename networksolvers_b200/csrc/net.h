@@ -12,6 +12,7 @@
 namespace nsb {
 
 extern int g_merge_site_ops;
+extern int g_skip_identity_sharded;
 extern int g_skip_identity;   // skip the identity channel of the first / last environment of an H_eff application
 
 struct NetBase {
@@ -80,6 +81,7 @@ struct Net : public NetBase {
   int first_ident = -1;
   DTensor<T> first_compact;
   void prepare_identity_skip();
+  bool skip_first_identity(DTensor<T>& X);
   double skipped_flops(const DTensor<T>& x) const;   // real flops per application the skipping saves (dry run)
   double skipped_last_apply = -1.0;                  // what the last apply_heff actually skipped (< 0: none ran yet)
   // multi-GPU: theta sharded along its last bond across the ranks of ctx->nccl_comm
