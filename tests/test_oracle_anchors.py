@@ -177,3 +177,38 @@ def test_qn_oracle_hubbard_sector_ground_state():
     Eq, _ = dmrg(H, product_ttn_qn(g, "S=1", 3, idx), nsweeps=4, nsites=2, inserter_kwargs=dict(trunc=trunc))
     Ed, _ = dmrg(H, product_ttn(g, d, idx), nsweeps=4, nsites=2, inserter_kwargs=dict(trunc=trunc))
     assert abs(Eq - Ed) < 1e-9
+
+
+@pytest.mark.parametrize("graph,region", [(path_graph(8), [4, 5]), (path_graph(8), [3]), (named_comb_tree([2, 3, 2]), [(2, 1)])])
+def test_environments_of_an_orthonormal_state_have_one_identity_channel(graph, region):
+    """Basis of the device's identity-channel skipping (csrc/net.cu, Net::prepare_identity_skip): between orthonormal
+    bases every environment of the operator network has exactly one operator-link channel that is the identity
+    (the pass-through channel of the sum-of-products operator), so contracting it returns the local tensor itself.
+    Checked on the oracle's environments; replacing that channel by an exact identity leaves H_eff theta unchanged."""
+    from oracle.gauge import orthogonalize
+    from oracle.operator_map import optimal_map
+    from oracle.projttn import ProjTTN, position
+    from oracle.tensor import contract
+    d, ops, _ = spin_ops("S=1/2")
+    H = ttno(heisenberg_opsum(graph), graph, ops)
+    psi = orthogonalize(random_ttn(graph, d, 6, seed=3), region)
+    P = position(ProjTTN(H), psi, region)
+    theta = psi.tensors[region[0]]
+    for v in region[1:]:
+        theta = contract(theta, psi.tensors[v])
+    ref = optimal_map(P, theta)
+    assert len(P.environments) >= 1
+    for key, E in list(P.environments.items()):
+        ol = [l for l in E.labels if l[0] == "m"]
+        assert len(ol) == 1
+        links = [l for l in E.labels if l[0] == "l"]
+        A = E.array([links[0], ol[0], links[1]])
+        n = A.shape[0]
+        dev = [np.abs(A[:, w, :] - np.eye(n)).max() for w in range(A.shape[1])]
+        ident = [w for w, x in enumerate(dev) if x < 1e-12]
+        assert len(ident) == 1, (key, dev)
+        A2 = A.copy()
+        A2[:, ident[0], :] = np.eye(n)
+        P.environments[key] = type(E)(A2, [links[0], ol[0], links[1]])
+    out = optimal_map(P, theta)
+    assert np.abs(out.array(ref.labels) - ref.array(ref.labels)).max() < 1e-13 * np.abs(ref.array(ref.labels)).max()
