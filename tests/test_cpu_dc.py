@@ -121,3 +121,17 @@ def test_symmetric_panel_unit_scheme():
     cases = [(132, 0, 0, 7, 16), (132, 1, 1, 7, 32), (700, 64, 0, 444, 64), (700, 65, 1, 296, 0), (1100, 131, 3, 30, 32),
              (1100, 1090, 50, 444, 0), (1540, 7, 7, 296, 16)]
     assert mod.check(cases, verbose=False) < 1e-13
+
+
+def test_ozaki_int8_gemm_matches_fp64():
+    """tools/proto_ozaki.py (round-2 candidate for the H_eff GEMMs): an FP64 product assembled from exact 8-bit integer GEMMs
+    (error-free 7-bit slicing, int32 accumulation, anti-diagonal sums) reaches FP64 accuracy with 9 slices = 45 integer GEMMs."""
+    import importlib.util, os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "proto_ozaki.py")
+    spec = importlib.util.spec_from_file_location("proto_ozaki", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    res = mod.check(m=48, k=1024, n=40, verbose=False)
+    for name in ("gauss", "graded"):
+        assert res[(name, 9)][0] < 2.0 * max(res[(name, "fp64")][0], 2.3e-16), (name, res[(name, 9)])
+        assert res[(name, 9)][1] == 45 and res[(name, 8)][0] < 1e-13
