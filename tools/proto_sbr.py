@@ -1,0 +1,138 @@
+"""NumPy statement of a two-stage Hermitian tridiagonalisation (successive band reduction), the round-2 candidate that turns the
+n^3 part of the eigensolver (csrc/eigh.cu: 311 ms of HBM-bound column products at n = 8192) into GEMMs:
+
+  stage 1  full -> band (lower bandwidth b): QR of the panel below the band of every block column, two-sided compact-WY update
+           A <- Q^H A Q of the trailing matrix (all GEMM: 4/3 n^3 flop on the DMMA pipe, no per-column grid barrier);
+  stage 2  band -> tridiagonal by bulge chasing: sweep j annihilates column j below the sub-diagonal with a reflector of length
+           <= b and chases the bulge down the band with (n - j) / b further reflectors; O(n^2 b) flop on O(n b) data (the band
+           stays in L2 / shared memory).  Task (j, s) = step s of sweep j touches rows / columns [j + 1 + s b, j + 1 + (s + 2) b);
+           sweep j + 1 may run step s once sweep j has finished step s + 2 (checked below by replaying the tasks in that
+           wavefront order), i.e. ~ n / (3 b) tasks run concurrently;
+  stage 3  eigen-decomposition of the tridiagonal matrix (the existing divide & conquer);
+  stage 4  back-transformation U = Q1 (Q2 Z): Q2 = product of the chasing reflectors (applied in reverse order; the device
+           version would group them into WY blocks per diagonal of the task grid), Q1 = product of the stage-1 block reflectors.
+
+    python tools/proto_sbr.py
+Used by tests/test_cpu_dc.py::test_two_stage_tridiagonalisation_prototype."""
+import numpy as np
+
+
+def house(x):
+    """Returns (v, g, beta) with v[0] = 1 and G = I - g v v^H such that G x = beta e_0, beta real (g = conj(tau) of zlarfg)."""
+    x = np.asarray(x)
+    alpha = x[0]
+    sigma = np.vdot(x[1:], x[1:]).real
+    v = x.astype(complex if np.iscomplexobj(x) else float).copy()
+    if sigma == 0.0 and np.imag(alpha) == 0.0:
+        v[:] = 0.0; v[0] = 1.0
+        return v, 0.0, alpha
+    beta = -np.copysign(np.sqrt(abs(alpha) ** 2 + sigma), np.real(alpha))
+    tau = (beta - alpha) / beta
+    v = v / (alpha - beta)
+    v[0] = 1.0
+    return v, np.conj(tau), beta           # G = I - conj(tau) v v^H (= H^H of zlarfg) maps x to beta e_0
+
+
+def full_to_band(A, b):
+    """Stage 1.  Returns the band matrix (dense storage, entries below the b-th sub-diagonal are zero) and the block
+    reflectors [(row offset, V, T)] with Q1 = prod_k (I - V_k T_k V_k^H)."""
+    A = A.copy()
+    n = A.shape[0]
+    blocks = []
+    for k in range(0, n - b - 1, b):
+        r0 = k + b
+        w = min(b, n - k)
+        P = A[r0:, k:k + w]
+        Q, R = np.linalg.qr(P, mode="complete")          # device: Householder panel QR + compact WY (V, T)
+        A[r0:, k:k + w] = np.triu(R)                      # (m x w upper trapezoidal)
+        A[k:k + w, r0:] = A[r0:, k:k + w].conj().T
+        A[r0:, r0:] = Q.conj().T @ A[r0:, r0:] @ Q        # device: W = A V T - 1/2 V T^H (V^H A V T);  A -= W V^H + V W^H
+        blocks.append((r0, Q))
+    return A, blocks
+
+
+def band_to_tridiagonal(B, b, order="sweeps"):
+    """Stage 2 on dense storage.  order = "sweeps": sweep after sweep; "wavefront": task (j, s) at time 3 j + s (all tasks of
+    one time step are independent).  Returns T (tridiagonal, dense) and the reflector list [(row offset, v, tau)] in the order
+    they were applied."""
+    A = B.copy()
+    n = A.shape[0]
+    refl = []
+
+    def task(j, s):
+        # step 0 annihilates column j below the sub-diagonal; step s > 0 annihilates the first column of the bulge that
+        # step s - 1 created: column c = j + 1 + (s - 1) b, rows r0 .. r0 + b - 1 with r0 = j + 1 + s b
+        r0 = j + 1 + s * b
+        c = j if s == 0 else j + 1 + (s - 1) * b
+        r1 = min(r0 + b, n)
+        if r1 - r0 < 2:
+            return False
+        x = A[r0:r1, c]
+        if not np.any(x[1:]):
+            return r1 < n
+        v, tau, beta = house(x)
+        G = np.eye(r1 - r0, dtype=A.dtype) - tau * np.outer(v, v.conj())
+        # G x = beta e_0: similarity A <- G A G^H on rows / columns r0 .. r1 - 1
+        A[r0:r1, :] = G @ A[r0:r1, :]
+        A[:, r0:r1] = A[:, r0:r1] @ G.conj().T
+        refl.append((r0, v, tau))
+        return r1 < n
+
+    nsteps = lambda j: max(0, -(-(n - j - 1) // b))
+    if order == "sweeps":
+        for j in range(n - 2):
+            for s in range(nsteps(j)):
+                task(j, s)
+    else:
+        tmax = 3 * (n - 2) + nsteps(0)
+        for t in range(tmax + 1):
+            for j in range(min(n - 2, t // 3 + 1)):
+                s = t - 3 * j
+                if 0 <= s < nsteps(j):
+                    task(j, s)
+    return A, refl
+
+
+def two_stage_eigh(A, b, order="sweeps"):
+    n = A.shape[0]
+    Bm, blocks = full_to_band(A, b)
+    band_err = max((np.abs(np.tril(Bm, -b - 1)).max() if n > b + 1 else 0.0), 0.0)
+    T, refl = band_to_tridiagonal(Bm, b, order)
+    tri_err = np.abs(np.tril(T, -2)).max() if n > 2 else 0.0
+    d = np.real(np.diag(T)).copy()
+    e = np.diag(T, -1).copy()
+    # phases of a complex sub-diagonal are absorbed into a diagonal similarity (stage 3 works on a real tridiagonal matrix)
+    ph = np.ones(n, dtype=T.dtype)
+    for i in range(n - 1):
+        ph[i + 1] = ph[i] * (e[i] / abs(e[i]) if abs(e[i]) > 0 else 1.0)
+    Tr = np.diag(d) + np.diag(np.abs(e), -1) + np.diag(np.abs(e), 1)
+    w, Z = np.linalg.eigh(Tr)
+    U = (ph[:, None] * Z).astype(T.dtype)
+    for r0, v, tau in reversed(refl):                     # Q2 Z: A = G^H A' G, so the eigenvectors pick up G^H = I - conj(g) v v^H
+        U[r0:r0 + len(v), :] -= np.conj(tau) * np.outer(v, v.conj() @ U[r0:r0 + len(v), :])
+    for r0, Q in reversed(blocks):                        # Q1 (Q2 Z)
+        U[r0:, :] = Q @ U[r0:, :]
+    return w, U, band_err, tri_err
+
+
+def check(verbose=True):
+    rng = np.random.default_rng(0)
+    worst = 0.0
+    for n, b, cplx, order in [(40, 4, False, "sweeps"), (61, 8, False, "wavefront"), (96, 16, True, "sweeps"), (75, 6, True, "wavefront"),
+                              (130, 32, False, "wavefront"), (33, 40, False, "sweeps")]:
+        M = rng.standard_normal((n, n)) + (1j * rng.standard_normal((n, n)) if cplx else 0.0)
+        A = M + M.conj().T
+        w, U, be, te = two_stage_eigh(A, b, order)
+        nrm = np.linalg.norm(A, 2)
+        res = np.linalg.norm(A @ U - U * w[None, :]) / (nrm * n)
+        orth = np.linalg.norm(U.conj().T @ U - np.eye(n)) / n
+        err = np.abs(w - np.linalg.eigvalsh(A)).max() / nrm
+        worst = max(worst, res, orth, err, be / nrm, te / nrm)
+        if verbose:
+            print(f"n={n:4d} b={b:3d} {'c128' if cplx else 'f64 '} {order:9s} residual {res:.1e} orthogonality {orth:.1e} eigenvalues {err:.1e} "
+                  f"below band {be / nrm:.1e} below sub-diagonal {te / nrm:.1e}")
+    return worst
+
+
+if __name__ == "__main__":
+    print("worst", check())
