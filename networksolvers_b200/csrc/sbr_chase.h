@@ -1,0 +1,107 @@
+// Band -> tridiagonal by bulge chasing (stage 2 of a two-stage tridiagonalisation, tools/proto_sbr.py) -- the arithmetic of
+// one chasing task on packed band storage, written once for the host (one thread, tests/dc_cpu_harness.cpp) and for a
+// device thread team (a CTA: loops strided by the team's thread index, team barriers between the phases).
+// No CUDA types here.  NOT WIRED INTO libnsb200.so YET: round-2 groundwork, exercised on the CPU only
+// (tests/test_cpu_dc.py::test_bulge_chasing_on_band_storage); real FP64.
+//
+// Storage: lower band with room for the bulge, AB[(i - j) + j * ld] = A[i, j] for 0 <= i - j <= 2 b, ld >= 2 b + 1
+// (n x (2 b + 1) doubles: 8.4 MB at n = 8192, b = 64 -- resident in L2).
+//
+// Task (j, s), window rows r0 = j + 1 + s b .. r1 - 1 (r1 = min(r0 + b, n)), column c = j (s = 0) or r0 - b (s > 0):
+//   G = I - tau v v^T with G A[r0:r1, c] = beta e_0;
+//   E = A[r0:r1, c+1:r0]  <- G E        (the rest of the bulge the previous step left; empty for s = 0)
+//   D = A[r0:r1, r0:r1]   <- G D G      (symmetric rank-2 update, lower part)
+//   F = A[r1:r2, r0:r1]   <- F G        (r2 = min(r1 + b, n): creates the next bulge)
+// Sweep j + 1 may run step s once sweep j has finished step s + 2 (wavefront t = 3 j + s).
+// The reflectors of sweep j tile rows j + 1 .. n - 1, so they are stored as column j of a lower-triangular n x n matrix V2
+// (v[0] = 1 stored explicitly) with tau2[s + j * nsteps_max].
+#pragma once
+#include <cmath>
+#include <cstdint>
+
+#ifdef __CUDACC__
+#define NSB_HD __host__ __device__
+#else
+#define NSB_HD
+#endif
+
+namespace nsb {
+namespace sbr {
+
+struct Band {
+  double* ab; int64_t ld, n; int b;
+  NSB_HD double& at(int64_t i, int64_t j) const { return ab[(i - j) + j * ld]; }   // 0 <= i - j <= 2 b
+};
+
+// One host thread standing in for a team.
+struct SerialTeam {
+  int tid = 0, size = 1;
+  NSB_HD void sync() const {}
+  NSB_HD double sum(double x, double*) const { return x; }   // team-wide sum, valid in every thread
+};
+
+NSB_HD inline int64_t nsteps(int64_t n, int b, int64_t j) { return n - j - 1 <= 0 ? 0 : (n - j - 1 + b - 1) / b; }
+
+// Runs task (j, s).  v (>= b doubles, team-visible), work (>= 2 b doubles, team-visible) and red (team reduction scratch) are
+// scratch; on return v[0 .. len) holds the reflector and *tau_out its scalar.  Returns len (0 or 1: nothing to annihilate).
+template <class Team>
+NSB_HD int chase_task(const Team& tm, const Band& B, int64_t j, int s, double* v, double* tau_out, double* work, double* red) {
+  const int64_t n = B.n;
+  const int b = B.b;
+  const int64_t r0 = j + 1 + (int64_t)s * b, r1 = (r0 + b < n) ? r0 + b : n, c = (s == 0) ? j : r0 - b;
+  const int len = (int)(r1 - r0);
+  if (len < 2) { if (tm.tid == 0) *tau_out = 0.0; return len < 0 ? 0 : len; }
+  // ---- reflector from x = A[r0:r1, c]
+  double part = 0.0;
+  for (int i = 1 + tm.tid; i < len; i += tm.size) { const double x = B.at(r0 + i, c); part += x * x; }
+  const double sigma = tm.sum(part, red);
+  const double alpha = B.at(r0, c);
+  double tau = 0.0, beta = alpha, scale = 0.0;
+  if (sigma != 0.0) {
+    beta = -copysign(sqrt(alpha * alpha + sigma), alpha);
+    tau = (beta - alpha) / beta;
+    scale = 1.0 / (alpha - beta);
+  }
+  for (int i = tm.tid; i < len; i += tm.size) v[i] = (i == 0) ? 1.0 : scale * B.at(r0 + i, c);
+  tm.sync();
+  if (tm.tid == 0) { *tau_out = tau; B.at(r0, c) = beta; }
+  for (int i = 1 + tm.tid; i < len; i += tm.size) B.at(r0 + i, c) = 0.0;
+  if (tau == 0.0) return len;
+  // ---- E <- G E: columns c + 1 .. r0 - 1
+  for (int64_t cc = c + 1 + tm.tid; cc < r0; cc += tm.size) {
+    double w = 0.0;
+    for (int i = 0; i < len; ++i) w += v[i] * B.at(r0 + i, cc);
+    w *= tau;
+    for (int i = 0; i < len; ++i) B.at(r0 + i, cc) -= w * v[i];
+  }
+  // ---- D <- G D G (lower storage): p = tau D v, w = p - (tau/2) (v^T p) v, D -= v w^T + w v^T
+  double* p = work;
+  double dotp = 0.0;
+  for (int i = tm.tid; i < len; i += tm.size) {
+    double acc = 0.0;
+    for (int k = 0; k < len; ++k) acc += ((i >= k) ? B.at(r0 + i, r0 + k) : B.at(r0 + k, r0 + i)) * v[k];
+    p[i] = tau * acc;
+    dotp += v[i] * p[i];
+  }
+  tm.sync();
+  const double vtp = tm.sum(dotp, red);
+  const double hv = 0.5 * tau * vtp;
+  double* w = work + b;
+  for (int i = tm.tid; i < len; i += tm.size) w[i] = p[i] - hv * v[i];
+  tm.sync();
+  for (int k = tm.tid; k < len; k += tm.size)          // column k of the lower triangle
+    for (int i = k; i < len; ++i) B.at(r0 + i, r0 + k) -= v[i] * w[k] + w[i] * v[k];
+  // ---- F <- F G: rows r1 .. r2 - 1
+  const int64_t r2 = (r1 + b < n) ? r1 + b : n;
+  for (int64_t i = r1 + tm.tid; i < r2; i += tm.size) {
+    double u = 0.0;
+    for (int k = 0; k < len; ++k) u += B.at(i, r0 + k) * v[k];
+    u *= tau;
+    for (int k = 0; k < len; ++k) B.at(i, r0 + k) -= u * v[k];
+  }
+  tm.sync();
+  return len;
+}
+
+}  // namespace sbr
+}  // namespace nsb

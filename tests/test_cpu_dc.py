@@ -147,3 +147,42 @@ def test_two_stage_tridiagonalisation_prototype():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     assert mod.check(verbose=False) < 2e-14
+
+
+@pytest.mark.parametrize("n,b,wavefront", [(40, 4, 0), (61, 8, 1), (130, 32, 1), (97, 16, 0), (20, 32, 1)])
+def test_bulge_chasing_on_band_storage(lib, n, b, wavefront):
+    """csrc/sbr_chase.h (round-2 groundwork, not wired into the library): one chasing task on packed band storage, the same
+    code a device thread team would run.  All tasks in sweep or wavefront order turn a random symmetric band matrix into a
+    tridiagonal one with the same eigenvalues; the stored reflectors give back the eigenvectors."""
+    rng = np.random.default_rng(n + b)
+    M = rng.standard_normal((n, n))
+    A = np.tril(np.triu(M + M.T, -b), b)
+    ld = 2 * b + 1
+    ab = np.zeros((ld, n), order="F")
+    for jj in range(n):
+        m = min(b, n - 1 - jj)
+        ab[:m + 1, jj] = A[jj:jj + m + 1, jj]
+    nst = max(1, -(-(n - 1) // b))
+    V2 = np.zeros((n, n), order="F")
+    tau2 = np.zeros((nst, n), order="F")
+    lib.sbr_chase_all.restype = C.c_int64
+    ntask = lib.sbr_chase_all(C.c_int64(n), C.c_int(b), ab.ctypes.data_as(C.c_void_p), C.c_int64(ld), V2.ctypes.data_as(C.c_void_p),
+                              tau2.ctypes.data_as(C.c_void_p), C.c_int64(nst), C.c_int(wavefront))
+    assert ntask == sum(max(0, -(-(n - jj - 1) // b)) for jj in range(n - 2))
+    nrm = np.linalg.norm(A, 2)
+    assert np.abs(ab[2:, :]).max() < 50 * EPS * nrm          # everything below the sub-diagonal is gone
+    d, e = ab[0, :].copy(), ab[1, :n - 1].copy()
+    T = np.diag(d) + np.diag(e, 1) + np.diag(e, -1)
+    w, Z = np.linalg.eigh(T)
+    assert np.abs(w - np.linalg.eigvalsh(A)).max() < 100 * EPS * nrm
+    U = Z.copy()
+    for jj in range(n - 3, -1, -1):                          # Q2 Z: reflectors in reverse order of application
+        for s in range(max(0, -(-(n - jj - 1) // b)) - 1, -1, -1):
+            r0 = jj + 1 + s * b
+            r1 = min(r0 + b, n)
+            if r1 - r0 < 2 or tau2[s, jj] == 0.0:
+                continue
+            v = V2[r0:r1, jj]
+            U[r0:r1, :] -= tau2[s, jj] * np.outer(v, v @ U[r0:r1, :])
+    assert np.linalg.norm(A @ U - U * w[None, :]) / (nrm * n) < 30 * EPS
+    assert np.linalg.norm(U.T @ U - np.eye(n)) / n < 30 * EPS
