@@ -9,8 +9,9 @@ n^3 part of the eigensolver (csrc/eigh.cu: 311 ms of HBM-bound column products a
            sweep j + 1 may run step s once sweep j has finished step s + 2 (checked below by replaying the tasks in that
            wavefront order), i.e. ~ n / (3 b) tasks run concurrently;
   stage 3  eigen-decomposition of the tridiagonal matrix (the existing divide & conquer);
-  stage 4  back-transformation U = Q1 (Q2 Z): Q2 = product of the chasing reflectors (applied in reverse order; the device
-           version would group them into WY blocks per diagonal of the task grid), Q1 = product of the stage-1 block reflectors.
+  stage 4  back-transformation U = Q1 (Q2 Z): Q2 = product of the chasing reflectors, applied in reverse order -- on the device as
+           compact-WY blocks of g consecutive sweeps at one step s (apply_q2: groups descending, steps ascending inside a group);
+           Q1 = product of the stage-1 block reflectors (the machinery of Eigh::vectors).
 
     python tools/proto_sbr.py
 Used by tests/test_cpu_dc.py::test_two_stage_tridiagonalisation_prototype."""
@@ -75,7 +76,7 @@ def band_to_tridiagonal(B, b, order="sweeps"):
         # G x = beta e_0: similarity A <- G A G^H on rows / columns r0 .. r1 - 1
         A[r0:r1, :] = G @ A[r0:r1, :]
         A[:, r0:r1] = A[:, r0:r1] @ G.conj().T
-        refl.append((r0, v, tau))
+        refl.append((r0, v, tau, j, s))
         return r1 < n
 
     nsteps = lambda j: max(0, -(-(n - j - 1) // b))
@@ -93,7 +94,47 @@ def band_to_tridiagonal(B, b, order="sweeps"):
     return A, refl
 
 
-def two_stage_eigh(A, b, order="sweeps"):
+def apply_q2(U, refl, n, b, group=0):
+    """U <- Q2 U.  A = G^H A' G for every task, so the eigenvectors pick up G^H = I - conj(g) v v^H, last task first.
+    group = 0: reflector by reflector in reverse order of application (j descending, s descending).
+    group = g: the device order -- sweeps in groups J of g consecutive j (descending); within a group the steps s ASCENDING
+    (a task (j', s') with j' > j, s' > s acts on rows strictly below task (j, s), so they commute; descending s would not);
+    the g reflectors of one (J, s) are staggered by one row each, i.e. they form the unit lower trapezoidal V of a QR panel
+    and are applied as one compact-WY block  U[rows] -= V (T^H (V^H U[rows]))  -- three GEMMs."""
+    U = U.copy()
+    if not group:
+        for r0, v, tau, j, s_ in reversed(refl):
+            U[r0:r0 + len(v), :] -= np.conj(tau) * np.outer(v, v.conj() @ U[r0:r0 + len(v), :])
+        return U
+    by = {}
+    for r0, v, tau, j, s_ in refl:
+        by[(j, s_)] = (r0, v, tau)
+    jmax = max(j for j, _ in by) if by else -1
+    smax = max(s_ for _, s_ in by) if by else -1
+    for j0 in range((jmax // group) * group, -1, -group):
+        for s_ in range(0, smax + 1):
+            js = [j for j in range(j0, min(j0 + group, jmax + 1)) if (j, s_) in by]
+            if not js:
+                continue
+            rlo = min(by[(j, s_)][0] for j in js)
+            rhi = max(by[(j, s_)][0] + len(by[(j, s_)][1]) for j in js)
+            V = np.zeros((rhi - rlo, len(js)), dtype=U.dtype)
+            taus = np.zeros(len(js), dtype=U.dtype)
+            for c, j in enumerate(js):
+                r0, v, tau = by[(j, s_)]
+                V[r0 - rlo:r0 - rlo + len(v), c] = v
+                taus[c] = np.conj(tau)                     # G^H = I - conj(g) v v^H
+            # product G_{j_first}^H ... G_{j_last}^H applied to U means the LAST sweep acts first: H_0 H_1 .. H_{k-1} = I - V T V^H
+            T = np.zeros((len(js), len(js)), dtype=U.dtype)
+            for c in range(len(js)):                       # forward larft: T[:c, c] = -tau_c T[:c, :c] V[:, :c]^H V[:, c]
+                T[c, c] = taus[c]
+                if c:
+                    T[:c, c] = -taus[c] * (T[:c, :c] @ (V[:, :c].conj().T @ V[:, c]))
+            U[rlo:rhi, :] -= V @ (T @ (V.conj().T @ U[rlo:rhi, :]))
+    return U
+
+
+def two_stage_eigh(A, b, order="sweeps", group=0):
     n = A.shape[0]
     Bm, blocks = full_to_band(A, b)
     band_err = max((np.abs(np.tril(Bm, -b - 1)).max() if n > b + 1 else 0.0), 0.0)
@@ -108,8 +149,7 @@ def two_stage_eigh(A, b, order="sweeps"):
     Tr = np.diag(d) + np.diag(np.abs(e), -1) + np.diag(np.abs(e), 1)
     w, Z = np.linalg.eigh(Tr)
     U = (ph[:, None] * Z).astype(T.dtype)
-    for r0, v, tau in reversed(refl):                     # Q2 Z: A = G^H A' G, so the eigenvectors pick up G^H = I - conj(g) v v^H
-        U[r0:r0 + len(v), :] -= np.conj(tau) * np.outer(v, v.conj() @ U[r0:r0 + len(v), :])
+    U = apply_q2(U, refl, n, b, group=group)               # Q2 Z
     for r0, Q in reversed(blocks):                        # Q1 (Q2 Z)
         U[r0:, :] = Q @ U[r0:, :]
     return w, U, band_err, tri_err
@@ -118,18 +158,18 @@ def two_stage_eigh(A, b, order="sweeps"):
 def check(verbose=True):
     rng = np.random.default_rng(0)
     worst = 0.0
-    for n, b, cplx, order in [(40, 4, False, "sweeps"), (61, 8, False, "wavefront"), (96, 16, True, "sweeps"), (75, 6, True, "wavefront"),
-                              (130, 32, False, "wavefront"), (33, 40, False, "sweeps")]:
+    for n, b, cplx, order, group in [(40, 4, False, "sweeps", 0), (61, 8, False, "wavefront", 4), (96, 16, True, "sweeps", 16), (75, 6, True, "wavefront", 5),
+                                     (130, 32, False, "wavefront", 32), (33, 40, False, "sweeps", 8), (90, 8, False, "sweeps", 3)]:
         M = rng.standard_normal((n, n)) + (1j * rng.standard_normal((n, n)) if cplx else 0.0)
         A = M + M.conj().T
-        w, U, be, te = two_stage_eigh(A, b, order)
+        w, U, be, te = two_stage_eigh(A, b, order, group)
         nrm = np.linalg.norm(A, 2)
         res = np.linalg.norm(A @ U - U * w[None, :]) / (nrm * n)
         orth = np.linalg.norm(U.conj().T @ U - np.eye(n)) / n
         err = np.abs(w - np.linalg.eigvalsh(A)).max() / nrm
         worst = max(worst, res, orth, err, be / nrm, te / nrm)
         if verbose:
-            print(f"n={n:4d} b={b:3d} {'c128' if cplx else 'f64 '} {order:9s} residual {res:.1e} orthogonality {orth:.1e} eigenvalues {err:.1e} "
+            print(f"n={n:4d} b={b:3d} {'c128' if cplx else 'f64 '} {order:9s} group {group:2d} residual {res:.1e} orthogonality {orth:.1e} eigenvalues {err:.1e} "
                   f"below band {be / nrm:.1e} below sub-diagonal {te / nrm:.1e}")
     return worst
 
