@@ -34,21 +34,48 @@ def house(x):
     return v, np.conj(tau), beta           # G = I - conj(tau) v v^H (= H^H of zlarfg) maps x to beta e_0
 
 
+def panel_qr_wy(P):
+    """Householder QR of an m x w panel in compact-WY form: P = Q [R; 0], Q = I - V T V^H (V unit lower trapezoidal m x w,
+    T upper triangular w x w) -- the device panel factorisation (house_* kernels) followed by larft."""
+    P = P.astype(complex if np.iscomplexobj(P) else float).copy()
+    m, w = P.shape
+    k = min(m, w)
+    V = np.zeros((m, k), dtype=P.dtype)
+    taus = np.zeros(k, dtype=P.dtype)
+    for c in range(k):
+        v, g, beta = house(P[c:, c])                     # G = I - g v v^H, G x = beta e_0
+        P[c:, c + 1:] -= g * np.outer(v, v.conj() @ P[c:, c + 1:])
+        P[c, c] = beta
+        P[c + 1:, c] = 0.0
+        V[c:, c] = v
+        taus[c] = np.conj(g)                             # G = H^H with H = I - tau v v^H  =>  Q = H_0 H_1 .. = I - V T V^H
+    T = np.zeros((k, k), dtype=P.dtype)
+    for c in range(k):
+        T[c, c] = taus[c]
+        if c:
+            T[:c, c] = -taus[c] * (T[:c, :c] @ (V[:, :c].conj().T @ V[:, c]))
+    return V, T, np.triu(P[:k, :])
+
+
 def full_to_band(A, b):
     """Stage 1.  Returns the band matrix (dense storage, entries below the b-th sub-diagonal are zero) and the block
-    reflectors [(row offset, V, T)] with Q1 = prod_k (I - V_k T_k V_k^H)."""
+    reflectors [(row offset, V, T)] with Q1 = prod_k (I - V_k T_k V_k^H).  The trailing update is the GEMM sequence planned
+    for the device:  X = S V T,  W = X - 1/2 V T^H (V^H X),  S <- S - W V^H - V W^H  (= Q^H S Q)."""
     A = A.copy()
     n = A.shape[0]
     blocks = []
     for k in range(0, n - b - 1, b):
         r0 = k + b
         w = min(b, n - k)
-        P = A[r0:, k:k + w]
-        Q, R = np.linalg.qr(P, mode="complete")          # device: Householder panel QR + compact WY (V, T)
-        A[r0:, k:k + w] = np.triu(R)                      # (m x w upper trapezoidal)
+        V, T, R = panel_qr_wy(A[r0:, k:k + w])
+        A[r0:, k:k + w] = 0.0
+        A[r0:r0 + R.shape[0], k:k + w] = R
         A[k:k + w, r0:] = A[r0:, k:k + w].conj().T
-        A[r0:, r0:] = Q.conj().T @ A[r0:, r0:] @ Q        # device: W = A V T - 1/2 V T^H (V^H A V T);  A -= W V^H + V W^H
-        blocks.append((r0, Q))
+        S = A[r0:, r0:]
+        X = S @ V @ T
+        W = X - 0.5 * V @ (T.conj().T @ (V.conj().T @ X))
+        A[r0:, r0:] = S - W @ V.conj().T - V @ W.conj().T
+        blocks.append((r0, V, T))
     return A, blocks
 
 
@@ -150,8 +177,8 @@ def two_stage_eigh(A, b, order="sweeps", group=0):
     w, Z = np.linalg.eigh(Tr)
     U = (ph[:, None] * Z).astype(T.dtype)
     U = apply_q2(U, refl, n, b, group=group)               # Q2 Z
-    for r0, Q in reversed(blocks):                        # Q1 (Q2 Z)
-        U[r0:, :] = Q @ U[r0:, :]
+    for r0, V, T in reversed(blocks):                     # Q1 (Q2 Z): block reflectors, last panel first
+        U[r0:, :] -= V @ (T @ (V.conj().T @ U[r0:, :]))
     return w, U, band_err, tri_err
 
 
