@@ -57,7 +57,44 @@ def panel_qr_wy(P):
     return V, T, np.triu(P[:k, :])
 
 
-def full_to_band(A, b):
+def panel_qr_wy_gemm(P):
+    """The same compact-WY factorisation without a column-by-column Householder loop (tensor-core friendly panel, round-2
+    candidate): CholeskyQR2 gives an explicit orthonormal Q (two Gram GEMMs + two w x w Cholesky + two triangular solves),
+    Householder reconstruction (Ballard et al., "Reconstructing Householder vectors from TSQR", 2014) turns it into V and T:
+      S = -sign(diag) chosen during the unpivoted LU of Q - [S; 0] = L U,   V = L (unit lower trapezoidal),
+      T = -U S^H V_1^{-H}  (V_1 = top w x w block of V),   P = (I - V T V^H) [S R; 0].
+    Unpivoted LU is stable here because Q - [S; 0] is diagonally dominant by construction (|q_ii - s_i| >= 1).
+    CholeskyQR2 needs cond(P) < ~1e8; panels of a strongly graded density matrix need the shifted three-pass variant or a
+    fall-back to the Householder loop (decided per panel from the Cholesky pivots)."""
+    P = np.asarray(P)
+    m, w = P.shape
+    if m < w:
+        return panel_qr_wy(P)
+    dt = complex if np.iscomplexobj(P) else float
+    Q = P.astype(dt)
+    Rtot = np.eye(w, dtype=dt)
+    for _ in range(2):                                     # CholeskyQR2: second pass restores orthogonality to eps
+        G = Q.conj().T @ Q
+        Rc = np.linalg.cholesky(G).conj().T                # G = Rc^H Rc
+        Q = np.linalg.solve(Rc.conj().T, Q.conj().T).conj().T   # Q Rc^{-1}
+        Rtot = Rc @ Rtot
+    # unpivoted LU of Q - [S; 0] with S chosen on the fly
+    M = Q.copy()
+    S = np.zeros(w, dtype=dt)
+    for c in range(w):
+        d = M[c, c]
+        S[c] = -(d / abs(d)) if abs(d) > 0 else -1.0
+        M[c, c] -= S[c]
+        M[c + 1:, c] /= M[c, c]
+        M[c + 1:, c + 1:] -= np.outer(M[c + 1:, c], M[c, c + 1:])
+    V = np.tril(M, -1)[:, :w] + np.eye(m, w, dtype=dt)
+    U = np.triu(M[:w, :w])
+    T = -U @ np.diag(S.conj()) @ np.linalg.inv(V[:w, :w].conj().T)
+    R = np.diag(S) @ Rtot
+    return V, T, R
+
+
+def full_to_band(A, b, panel=None):
     """Stage 1.  Returns the band matrix (dense storage, entries below the b-th sub-diagonal are zero) and the block
     reflectors [(row offset, V, T)] with Q1 = prod_k (I - V_k T_k V_k^H).  The trailing update is the GEMM sequence planned
     for the device:  X = S V T,  W = X - 1/2 V T^H (V^H X),  S <- S - W V^H - V W^H  (= Q^H S Q)."""
@@ -67,7 +104,7 @@ def full_to_band(A, b):
     for k in range(0, n - b - 1, b):
         r0 = k + b
         w = min(b, n - k)
-        V, T, R = panel_qr_wy(A[r0:, k:k + w])
+        V, T, R = (panel or panel_qr_wy)(A[r0:, k:k + w])
         A[r0:, k:k + w] = 0.0
         A[r0:r0 + R.shape[0], k:k + w] = R
         A[k:k + w, r0:] = A[r0:, k:k + w].conj().T
@@ -161,9 +198,9 @@ def apply_q2(U, refl, n, b, group=0):
     return U
 
 
-def two_stage_eigh(A, b, order="sweeps", group=0):
+def two_stage_eigh(A, b, order="sweeps", group=0, panel=None):
     n = A.shape[0]
-    Bm, blocks = full_to_band(A, b)
+    Bm, blocks = full_to_band(A, b, panel)
     band_err = max((np.abs(np.tril(Bm, -b - 1)).max() if n > b + 1 else 0.0), 0.0)
     T, refl = band_to_tridiagonal(Bm, b, order)
     tri_err = np.abs(np.tril(T, -2)).max() if n > 2 else 0.0
@@ -189,7 +226,7 @@ def check(verbose=True):
                                      (130, 32, False, "wavefront", 32), (33, 40, False, "sweeps", 8), (90, 8, False, "sweeps", 3)]:
         M = rng.standard_normal((n, n)) + (1j * rng.standard_normal((n, n)) if cplx else 0.0)
         A = M + M.conj().T
-        w, U, be, te = two_stage_eigh(A, b, order, group)
+        w, U, be, te = two_stage_eigh(A, b, order, group, panel_qr_wy_gemm if (n + b) % 2 else None)
         nrm = np.linalg.norm(A, 2)
         res = np.linalg.norm(A @ U - U * w[None, :]) / (nrm * n)
         orth = np.linalg.norm(U.conj().T @ U - np.eye(n)) / n
