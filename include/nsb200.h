@@ -268,6 +268,13 @@ int nsb_range_finder_host(nsb_ctx* ctx, int32_t dtype, int64_t m, int64_t n, con
                           int32_t oversample, int32_t north_pass, double orthogonal_threshold, uint64_t seed,
                           void* Q /* m*(max_rank+oversample) */, int64_t* rank_out);
 
+/* EXPERIMENTAL (round-2 groundwork, not used by the hooks above; eigenvalues checked on a B200): band -> tridiagonal by bulge
+ * chasing, stage 2 of a two-stage tridiagonalisation (csrc/sbr.cu, csrc/sbr_chase.h, tools/proto_sbr.py).  ab: lower band
+ * storage ld x n column-major, ab[(i - j) + j ld] = A[i, j] for 0 <= i - j <= b, rows b + 1 .. 2 b zero (room for the bulge),
+ * ld >= 2 b + 1; on return row 0 holds the diagonal and row 1 the sub-diagonal of the tridiagonal matrix.  V2 (n x n) receives
+ * the reflectors of sweep j in column j (rows j + 1 ..), tau2 (ldtau x n) their scalars. */
+int nsb_sbr_chase_host(nsb_ctx* ctx, int64_t n, int32_t b, double* ab, int64_t ld, double* V2, double* tau2, int64_t ldtau);
+
 #ifdef __cplusplus
 }
 #endif

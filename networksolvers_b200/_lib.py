@@ -129,6 +129,7 @@ SIGNATURES = {
     "nsb_factorize_host": (C.c_int, [_vp, _i32, _i64, _i64, _vp, P(Trunc), _vp, _vp, P(_dbl), P(InsertInfo)]),
     "nsb_qr_host": (C.c_int, [_vp, _i32, _i64, _i64, _vp, _vp, _vp]),
     "nsb_range_finder_host": (C.c_int, [_vp, _i32, _i64, _i64, _vp, _i64, _i32, _i32, _dbl, C.c_uint64, _vp, P(_i64)]),
+    "nsb_sbr_chase_host": (C.c_int, [_vp, _i64, _i32, _vp, _i64, _vp, _vp, _i64]),
 }
 
 _lib = None

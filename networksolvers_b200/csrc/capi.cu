@@ -525,6 +525,26 @@ extern "C" __attribute__((visibility("default"))) int nsb_eigh_host(nsb_ctx* ctx
   NSB_CATCH(&ctx->c)
 }
 
+namespace nsb { void sbr_chase_device(Ctx* ctx, int64_t n, int b, double* ab, int64_t ld, double* V2, double* tau2, int64_t ldtau); }
+extern "C" __attribute__((visibility("default"))) int nsb_sbr_chase_host(nsb_ctx* ctx, int64_t n, int32_t b, double* ab, int64_t ld, double* V2, double* tau2,
+                                                                          int64_t ldtau) {
+  if (!ctx) return NSB_EINVAL;
+  NSB_TRY(&ctx->c)
+  NSB_CUDA(cudaSetDevice(ctx->c.device));
+  NSB_REQUIRE(ab && V2 && tau2 && n > 0 && b > 0 && ld >= 2 * (int64_t)b + 1 && ldtau >= 1, NSB_EINVAL, "bad arguments");
+  Ctx* c = &ctx->c;
+  DevBuf dab(c, sizeof(double) * (size_t)ld * n), dV(c, sizeof(double) * (size_t)n * n), dt(c, sizeof(double) * (size_t)ldtau * n);
+  NSB_CUDA(cudaMemcpyAsync(dab.ptr, ab, sizeof(double) * (size_t)ld * n, cudaMemcpyHostToDevice, c->stream));
+  NSB_CUDA(cudaMemsetAsync(dV.ptr, 0, sizeof(double) * (size_t)n * n, c->stream));
+  NSB_CUDA(cudaMemsetAsync(dt.ptr, 0, sizeof(double) * (size_t)ldtau * n, c->stream));
+  nsb::sbr_chase_device(c, n, b, (double*)dab.ptr, ld, (double*)dV.ptr, (double*)dt.ptr, ldtau);
+  NSB_CUDA(cudaMemcpyAsync(ab, dab.ptr, sizeof(double) * (size_t)ld * n, cudaMemcpyDeviceToHost, c->stream));
+  NSB_CUDA(cudaMemcpyAsync(V2, dV.ptr, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost, c->stream));
+  NSB_CUDA(cudaMemcpyAsync(tau2, dt.ptr, sizeof(double) * (size_t)ldtau * n, cudaMemcpyDeviceToHost, c->stream));
+  c->sync();
+  NSB_CATCH(&ctx->c)
+}
+
 template <typename T>
 static void qr_host_impl(Ctx* c, int64_t rows, int64_t cols, const void* M, void* Q, void* R) {
   int64_t k = std::min(rows, cols);

@@ -1,8 +1,8 @@
 // Band -> tridiagonal by bulge chasing (stage 2 of a two-stage tridiagonalisation, tools/proto_sbr.py) -- the arithmetic of
 // one chasing task on packed band storage, written once for the host (one thread, tests/dc_cpu_harness.cpp) and for a
 // device thread team (a CTA: loops strided by the team's thread index, team barriers between the phases).
-// No CUDA types here.  NOT WIRED INTO libnsb200.so YET: round-2 groundwork, exercised on the CPU only
-// (tests/test_cpu_dc.py::test_bulge_chasing_on_band_storage); real FP64.
+// No CUDA types here.  Round-2 groundwork: used by the experimental kernel of csrc/sbr.cu (test hook only, not by the
+// eigensolver yet) and exercised on the CPU by tests/test_cpu_dc.py::test_bulge_chasing_on_band_storage; real FP64.
 //
 // Storage: lower band with room for the bulge, AB[(i - j) + j * ld] = A[i, j] for 0 <= i - j <= 2 b, ld >= 2 b + 1
 // (n x (2 b + 1) doubles: 8.4 MB at n = 8192, b = 64 -- resident in L2).
@@ -30,7 +30,16 @@ namespace sbr {
 
 struct Band {
   double* ab; int64_t ld, n; int b;
-  NSB_HD double& at(int64_t i, int64_t j) const { return ab[(i - j) + j * ld]; }   // 0 <= i - j <= 2 b
+  // element (i, j), 0 <= i - j <= 2 b.  On the device the band is shared between CTAs that hand tasks to each other through
+  // flags, and L1 is not coherent across SMs: loads go to L2 (ld.global.cg), stores are write-through anyway.
+  NSB_HD double get(int64_t i, int64_t j) const {
+#ifdef __CUDA_ARCH__
+    return __ldcg(ab + (i - j) + j * ld);
+#else
+    return ab[(i - j) + j * ld];
+#endif
+  }
+  NSB_HD void set(int64_t i, int64_t j, double x) const { ab[(i - j) + j * ld] = x; }
 };
 
 // One host thread standing in for a team.
@@ -53,33 +62,33 @@ NSB_HD int chase_task(const Team& tm, const Band& B, int64_t j, int s, double* v
   if (len < 2) { if (tm.tid == 0) *tau_out = 0.0; return len < 0 ? 0 : len; }
   // ---- reflector from x = A[r0:r1, c]
   double part = 0.0;
-  for (int i = 1 + tm.tid; i < len; i += tm.size) { const double x = B.at(r0 + i, c); part += x * x; }
+  for (int i = 1 + tm.tid; i < len; i += tm.size) { const double x = B.get(r0 + i, c); part += x * x; }
   const double sigma = tm.sum(part, red);
-  const double alpha = B.at(r0, c);
+  const double alpha = B.get(r0, c);
   double tau = 0.0, beta = alpha, scale = 0.0;
   if (sigma != 0.0) {
     beta = -copysign(sqrt(alpha * alpha + sigma), alpha);
     tau = (beta - alpha) / beta;
     scale = 1.0 / (alpha - beta);
   }
-  for (int i = tm.tid; i < len; i += tm.size) v[i] = (i == 0) ? 1.0 : scale * B.at(r0 + i, c);
+  for (int i = tm.tid; i < len; i += tm.size) v[i] = (i == 0) ? 1.0 : scale * B.get(r0 + i, c);
   tm.sync();
-  if (tm.tid == 0) { *tau_out = tau; B.at(r0, c) = beta; }
-  for (int i = 1 + tm.tid; i < len; i += tm.size) B.at(r0 + i, c) = 0.0;
+  if (tm.tid == 0) { *tau_out = tau; B.set(r0, c, beta); }
+  for (int i = 1 + tm.tid; i < len; i += tm.size) B.set(r0 + i, c, 0.0);
   if (tau == 0.0) return len;
   // ---- E <- G E: columns c + 1 .. r0 - 1
   for (int64_t cc = c + 1 + tm.tid; cc < r0; cc += tm.size) {
     double w = 0.0;
-    for (int i = 0; i < len; ++i) w += v[i] * B.at(r0 + i, cc);
+    for (int i = 0; i < len; ++i) w += v[i] * B.get(r0 + i, cc);
     w *= tau;
-    for (int i = 0; i < len; ++i) B.at(r0 + i, cc) -= w * v[i];
+    for (int i = 0; i < len; ++i) B.set(r0 + i, cc, B.get(r0 + i, cc) - w * v[i]);
   }
   // ---- D <- G D G (lower storage): p = tau D v, w = p - (tau/2) (v^T p) v, D -= v w^T + w v^T
   double* p = work;
   double dotp = 0.0;
   for (int i = tm.tid; i < len; i += tm.size) {
     double acc = 0.0;
-    for (int k = 0; k < len; ++k) acc += ((i >= k) ? B.at(r0 + i, r0 + k) : B.at(r0 + k, r0 + i)) * v[k];
+    for (int k = 0; k < len; ++k) acc += ((i >= k) ? B.get(r0 + i, r0 + k) : B.get(r0 + k, r0 + i)) * v[k];
     p[i] = tau * acc;
     dotp += v[i] * p[i];
   }
@@ -90,14 +99,14 @@ NSB_HD int chase_task(const Team& tm, const Band& B, int64_t j, int s, double* v
   for (int i = tm.tid; i < len; i += tm.size) w[i] = p[i] - hv * v[i];
   tm.sync();
   for (int k = tm.tid; k < len; k += tm.size)          // column k of the lower triangle
-    for (int i = k; i < len; ++i) B.at(r0 + i, r0 + k) -= v[i] * w[k] + w[i] * v[k];
+    for (int i = k; i < len; ++i) B.set(r0 + i, r0 + k, B.get(r0 + i, r0 + k) - (v[i] * w[k] + w[i] * v[k]));
   // ---- F <- F G: rows r1 .. r2 - 1
   const int64_t r2 = (r1 + b < n) ? r1 + b : n;
   for (int64_t i = r1 + tm.tid; i < r2; i += tm.size) {
     double u = 0.0;
-    for (int k = 0; k < len; ++k) u += B.at(i, r0 + k) * v[k];
+    for (int k = 0; k < len; ++k) u += B.get(i, r0 + k) * v[k];
     u *= tau;
-    for (int k = 0; k < len; ++k) B.at(i, r0 + k) -= u * v[k];
+    for (int k = 0; k < len; ++k) B.set(i, r0 + k, B.get(i, r0 + k) - u * v[k]);
   }
   tm.sync();
   return len;

@@ -137,6 +137,17 @@ class Context:
                                             U.ctypes.data if vectors else None))
         return (w, U) if vectors else w
 
+    def sbr_chase(self, ab, b):
+        """EXPERIMENTAL: band -> tridiagonal by bulge chasing on the device (nsb_sbr_chase_host).  ab: (2 b + 1) x n lower band
+        storage (Fortran order, bulge rows zero); returns (ab_out, V2, tau2)."""
+        ab = np.asfortranarray(ab, dtype=np.float64).copy(order="F")
+        ld, n = ab.shape
+        nst = max(1, -(-(n - 1) // b))
+        V2 = np.zeros((n, n), order="F")
+        tau2 = np.zeros((nst, n), order="F")
+        self.check(self._lib.nsb_sbr_chase_host(self.handle, n, int(b), ab.ctypes.data, ld, V2.ctypes.data, tau2.ctypes.data, nst))
+        return ab, V2, tau2
+
     def qr(self, M):
         cplx = np.iscomplexobj(M)
         dt = np.complex128 if cplx else np.float64
