@@ -73,6 +73,7 @@ PhaseTimer::~PhaseTimer() {
 
 using namespace nsb;
 
+namespace nsb { extern int g_sbr_staged; }   // csrc/sbr.cu (experimental)
 struct nsb_ctx { Ctx c; int refs = 0; bool destroyed = false; cudaEvent_t ev0 = nullptr, ev1 = nullptr; };
 struct nsb_net { NetBase* n; nsb_ctx* ctx; };
 
@@ -160,6 +161,7 @@ int nsb_ctx_set_option(nsb_ctx* ctx, const char* key, int64_t value) {
   else if (k == "jacobi_inner_cap") { NSB_REQUIRE(value >= 1, NSB_EINVAL, "jacobi_inner_cap >= 1"); g_jacobi_inner_cap = (int)value; }
   else if (k == "jacobi_precondition_min_n") { g_jacobi_precondition_min_n = (int)value; }
   else if (k == "big_cache_gib") { NSB_REQUIRE(value >= 0, NSB_EINVAL, "big_cache_gib >= 0"); ctx->c.big_cache_cap = (size_t)value << 30; if (value == 0) ctx->c.flush_big_cache(); }
+  else if (k == "sbr_staged") { nsb::g_sbr_staged = value != 0; }
   else if (k == "skip_identity") { g_skip_identity = value != 0; }
   else if (k == "skip_identity_sharded") { g_skip_identity_sharded = value != 0; }
   else if (k == "merge_site_ops") { g_merge_site_ops = value != 0; }

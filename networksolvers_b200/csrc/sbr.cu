@@ -20,6 +20,8 @@
 
 namespace nsb {
 
+int g_sbr_staged = 0;
+
 namespace {
 
 struct DeviceTeam {
@@ -56,10 +58,12 @@ __device__ __forceinline__ void st_release(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+template <bool STAGED>
 __global__ void __launch_bounds__(128) sbr_chase_kernel(sbr::Band B, double* __restrict__ V2, double* __restrict__ tau2, int64_t ldtau,
                                                         int* __restrict__ done) {
   __shared__ double v[SBR_MAXB], work[2 * SBR_MAXB], red[32];
   __shared__ double s_tau;
+  extern __shared__ __align__(16) double stage[];   // STAGED: 3 b b doubles
   const DeviceTeam tm{(int)threadIdx.x, (int)blockDim.x};
   const int64_t n = B.n;
   const int b = B.b;
@@ -72,7 +76,7 @@ __global__ void __launch_bounds__(128) sbr_chase_kernel(sbr::Band B, double* __r
         if (tm.tid == 0) while (ld_acquire(done + (j - 1)) < need) __nanosleep(32);
         __syncthreads();
       }
-      const int len = sbr::chase_task(tm, B, j, s, v, &s_tau, work, red);
+      const int len = STAGED ? sbr::chase_task_staged(tm, B, j, s, v, &s_tau, work, red, stage) : sbr::chase_task(tm, B, j, s, v, &s_tau, work, red);
       __syncthreads();
       const int64_t r0 = j + 1 + (int64_t)s * b;
       if (len >= 2) for (int i = tm.tid; i < len; i += tm.size) V2[(r0 + i) + j * n] = v[i];
@@ -93,7 +97,13 @@ void sbr_chase_device(Ctx* ctx, int64_t n, int b, double* ab, int64_t ld, double
   NSB_CUDA(cudaMemsetAsync(done.ptr, 0, sizeof(int) * (size_t)n, ctx->stream));
   int per_sm = 0, coop = 0;
   NSB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
-  NSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sbr_chase_kernel, 128, 0));
+  // g_sbr_staged (ctx option "sbr_staged", default 0): the shared-memory form of the task (validated on the CPU, not yet run
+  // on hardware); 0: the element-wise form (validated on a B200, slow)
+  const bool staged = g_sbr_staged != 0;
+  const size_t smem = staged ? sizeof(double) * 3 * (size_t)b * b : 0;
+  void* kern = staged ? (void*)sbr_chase_kernel<true> : (void*)sbr_chase_kernel<false>;
+  if (staged) NSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  NSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem));
   NSB_REQUIRE(coop && per_sm >= 1, NSB_EUNSUPPORTED, "sbr_chase: cooperative launch unavailable");
   const int grid = (int)std::min<int64_t>(n - 2, (int64_t)std::min(per_sm, 4) * ctx->num_sms);   // all CTAs resident: no deadlock
   sbr::Band B{ab, ld, n, b};
@@ -102,14 +112,14 @@ void sbr_chase_device(Ctx* ctx, int64_t n, int b, double* ab, int64_t ld, double
   const bool dbg = getenv("NSB_DEBUG_EIGH") != nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (dbg) { NSB_CUDA(cudaEventCreate(&e0)); NSB_CUDA(cudaEventCreate(&e1)); NSB_CUDA(cudaEventRecord(e0, ctx->stream)); }
-  NSB_CUDA(cudaLaunchCooperativeKernel((void*)sbr_chase_kernel, dim3(grid), dim3(128), args, 0, ctx->stream));
+  NSB_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(128), args, smem, ctx->stream));
   ctx->cnt.kernel_launches++;
   if (dbg) NSB_CUDA(cudaEventRecord(e1, ctx->stream));
   ctx->sync();   // `done` is released at scope exit
   if (dbg) {
     float ms = 0.f;
     NSB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-    fprintf(stderr, "[sbr] n=%ld b=%d grid %d bulge chasing %.2f ms\n", (long)n, b, grid, ms);
+    fprintf(stderr, "[sbr] n=%ld b=%d grid %d %s bulge chasing %.2f ms\n", (long)n, b, grid, staged ? "staged" : "element-wise", ms);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
   }
 }

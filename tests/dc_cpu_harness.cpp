@@ -104,15 +104,17 @@ extern "C" {
 
 // ab: lower band storage (ld x n, ld >= 2 b + 1, rows b + 1 .. 2 b zero on entry); V2: n x n, zero on entry, receives the
 // reflectors of sweep j in column j (rows j + 1 ..); tau2: ldtau x n.  wavefront = 1 runs the tasks in the order
-// t = 3 j + s (all tasks of one t are independent), 0 sweep after sweep.  Returns the number of tasks run.
-int64_t sbr_chase_all(int64_t n, int b, double* ab, int64_t ld, double* V2, double* tau2, int64_t ldtau, int wavefront) {
+// t = 3 j + s (all tasks of one t are independent), 0 sweep after sweep; staged = 1 uses the shared-memory form of the task.
+// Returns the number of tasks run.
+int64_t sbr_chase_all(int64_t n, int b, double* ab, int64_t ld, double* V2, double* tau2, int64_t ldtau, int wavefront, int staged) {
   nsb::sbr::Band B{ab, ld, n, b};
   nsb::sbr::SerialTeam tm;
-  std::vector<double> v(b), work(2 * (size_t)b), red(64);
+  std::vector<double> v(b), work(2 * (size_t)b), red(64), stage(3 * (size_t)b * b);
   int64_t ntask = 0;
   auto run = [&](int64_t j, int s) {
     double tau = 0.0;
-    int len = nsb::sbr::chase_task(tm, B, j, s, v.data(), &tau, work.data(), red.data());
+    int len = staged ? nsb::sbr::chase_task_staged(tm, B, j, s, v.data(), &tau, work.data(), red.data(), stage.data())
+                     : nsb::sbr::chase_task(tm, B, j, s, v.data(), &tau, work.data(), red.data());
     const int64_t r0 = j + 1 + (int64_t)s * b;
     for (int i = 0; i < len && len >= 2; ++i) V2[(r0 + i) + j * n] = v[i];
     tau2[s + j * ldtau] = tau;

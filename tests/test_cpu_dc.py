@@ -149,8 +149,9 @@ def test_two_stage_tridiagonalisation_prototype():
     assert mod.check(verbose=False) < 2e-14
 
 
+@pytest.mark.parametrize("staged", [0, 1])
 @pytest.mark.parametrize("n,b,wavefront", [(40, 4, 0), (61, 8, 1), (130, 32, 1), (97, 16, 0), (20, 32, 1)])
-def test_bulge_chasing_on_band_storage(lib, n, b, wavefront):
+def test_bulge_chasing_on_band_storage(lib, n, b, wavefront, staged):
     """csrc/sbr_chase.h (round-2 groundwork, not wired into the library): one chasing task on packed band storage, the same
     code a device thread team would run.  All tasks in sweep or wavefront order turn a random symmetric band matrix into a
     tridiagonal one with the same eigenvalues; the stored reflectors give back the eigenvectors."""
@@ -167,7 +168,7 @@ def test_bulge_chasing_on_band_storage(lib, n, b, wavefront):
     tau2 = np.zeros((nst, n), order="F")
     lib.sbr_chase_all.restype = C.c_int64
     ntask = lib.sbr_chase_all(C.c_int64(n), C.c_int(b), ab.ctypes.data_as(C.c_void_p), C.c_int64(ld), V2.ctypes.data_as(C.c_void_p),
-                              tau2.ctypes.data_as(C.c_void_p), C.c_int64(nst), C.c_int(wavefront))
+                              tau2.ctypes.data_as(C.c_void_p), C.c_int64(nst), C.c_int(wavefront), C.c_int(staged))
     assert ntask == sum(max(0, -(-(n - jj - 1) // b)) for jj in range(n - 2))
     nrm = np.linalg.norm(A, 2)
     assert np.abs(ab[2:, :]).max() < 50 * EPS * nrm          # everything below the sub-diagonal is gone
