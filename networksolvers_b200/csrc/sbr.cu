@@ -4,7 +4,7 @@
 //
 // EXPERIMENTAL (round-2 groundwork): reachable only through the test hook nsb_sbr_chase_host; the eigensolver of
 // csrc/eigh.cu does not use it yet.  Checked on a B200 for the eigenvalues of the resulting tridiagonal matrix
-// (tests/test_gpu_eigh.py::test_experimental_bulge_chasing_kernel).
+// (tests/test_gpu_zz_experimental.py::test_experimental_bulge_chasing_kernel).
 //
 // One persistent cooperative kernel: CTA c runs sweeps c, c + G, c + 2 G, ... (G = grid size, all CTAs resident); step s of
 // sweep j starts once sweep j - 1 has finished step min(s + 2, last) (flag done[j - 1] >= s + 3, acquire / release through
