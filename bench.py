@@ -1,24 +1,40 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of the sweep hot path on B200.
+"""bench.py -- benchmarks of the sweep hot path on B200, one JSON line per run.
 
-Metric (BASELINE.json): H_eff matvec FP64 TFLOP/s (and 2-site DMRG region / sweep time) at chi = 4096 on the
-S=1/2 Heisenberg chain N = 100 (config 2), synthetic random state, real FP64.
-
+Default (BASELINE.json headline, config 2): S=1/2 Heisenberg chain N = 100, no QN, real FP64, chi = 4096.
 A "step" is one projected effective-Hamiltonian application theta' = H_eff theta (L . W . W . R contraction,
-src/operator_map.jl:3-10 of the reference) on an interior bond.  `value` = algorithmic flops
-(4 w d^2 chi^3 + 4 w^2 d^3 chi^2) x steps / device time, all operands resident in HBM.
-`e2e` = the same matvec through the reference-facing call with HOST buffers (nsb_matvec_host: H2D copy of
-theta, matvec, D2H copy of theta') timed inside the region.
+src/operator_map.jl:3-10 of the reference) on an interior bond.  `value` = flops actually issued x steps / device time
+with all operands resident in HBM; `e2e` = the same application through the reference-facing call with HOST buffers
+(nsb_matvec_host: H2D copy of theta, matvec, D2H copy of theta') inside the timed region.  The same run then times
+consecutive full region steps (extract -> 3-matvec Lanczos -> truncating insert) and, on one GPU, one complete measured
+2-site DMRG sweep over all 2 (N - 1) regions.
 
     python bench.py --gpus 1 --steps 10 --warmup 3
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
-    python bench.py --impl reference          # the reference-equivalent CPU path on the host cores
-"""
+    python bench.py --impl reference          # the reference-equivalent CPU path on the host cores (all threads)
+    python bench.py --config 1|3|4|5          # the other BASELINE configs (own metric each, same JSON contract)
+
+`roofline` is derived from the GEMM launches of the timed steps themselves: every launch is bracketed by CUDA events on
+the launching stream (nsb_gemm_profile_*), achieved = sum of issued flops / sum of launch durations."""
+import os
+import sys
+
+
+def _host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+if "reference" in sys.argv:
+    # torchrun exports OMP_NUM_THREADS=1: the CPU arm must use every host core whatever the launcher set (read at BLAS load)
+    for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_k] = str(_host_cores())
+
 import argparse
 import json
-import os
 import subprocess
-import sys
 import threading
 import time
 
@@ -28,8 +44,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 W_MPO, D_SITE = 5, 2
-# DRAM traffic per K3 launch measured by ncu --set full (profiles/), keyed by chi
-NCU_TRAFFIC_BYTES = {4096: 16.929995e9 + 533.289216e6}
+CPU_SLABS = 8     # the CPU sample is one right-bond slab (1 / CPU_SLABS) of the matvec at the GPU arm's chi
 
 
 def matvec_flops(chi_l, chi_r, d=D_SITE, w=W_MPO, cplx=False):
@@ -86,90 +101,135 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_problem(chi, nsites, ctx, dtype=np.float64, canonical=True):
-    import networksolvers_b200 as ns
-    g = ns.path_graph(nsites)
-    sites = ns.siteinds("S=1/2", g)
-    H = ns.ttno(ns.heisenberg(g), sites)
-    mid = nsites // 2
-    region = [mid, mid + 1]
-    net = ns.DeviceNetwork.synthetic(H, sites, chi, seed=1234, dtype=dtype, ctx=ctx, ortho_region=region, canonical=canonical)
-    return net, region
-
-
-def cpu_matvec_sample(chi, reps=3, threads=None):
-    """Reference-equivalent CPU path (oracle restatement of optimal_map, NumPy/BLAS) on the host cores for a
-    bounded sample: `reps` matvecs at bond dimension `chi` with synthetic environments."""
-    from oracle.operator_map import optimal_map
-    from oracle.projttn import ProjTTN
-    from oracle.models import TTN
-    from oracle.graph import path_graph
-    from oracle.tensor import Tensor, site, link, oplink
-    rng = np.random.default_rng(1234)
-    g = path_graph(4)
-    d, w = D_SITE, W_MPO
-    Wt = {}
-    for v in (2, 3):
-        Wt[v] = Tensor(rng.standard_normal((w, w, d, d)), [oplink(v - 1, v), oplink(v, v + 1), site(v, 0), site(v, 1)])
-    Hn = TTN(g, {1: None, 2: Wt[2], 3: Wt[3], 4: None}, ortho_region=[])
-    P = ProjTTN(Hn, pos=[2, 3])
-    P.environments[(1, 2)] = Tensor(rng.standard_normal((chi, w, chi)) / chi, [link(1, 2, 0), oplink(1, 2), link(1, 2, 1)])
-    P.environments[(4, 3)] = Tensor(rng.standard_normal((chi, w, chi)) / chi, [link(3, 4, 0), oplink(3, 4), link(3, 4, 1)])
-    theta = Tensor(rng.standard_normal((chi, d, d, chi)), [link(1, 2), site(2), site(3), link(3, 4)])
-    optimal_map(P, theta)            # warm-up (BLAS thread start-up, page faults)
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        optimal_map(P, theta)
-    dt = (time.perf_counter() - t0) / reps
-    return matvec_flops(chi, chi) / dt * 1e-12, dt
-
-
-def cpu_region_sample(chi, cutoff=0.0):
-    """Reference-equivalent CPU region step on the host cores, bounded sample: 3 H_eff matvecs (oracle optimal_map) +
-    the truncating factorisation of the (2 chi) x (2 chi) two-site tensor through the oracle's `factorize` rule
-    (LAPACK SVD for cutoff <= 1e-12, density-matrix eigen above), maxdim = chi."""
-    from oracle.tensor import Tensor, factorize, link, site
-    tf, dt_mv = cpu_matvec_sample(chi, reps=3)
-    rng = np.random.default_rng(4321)
-    theta = Tensor(rng.standard_normal((chi, D_SITE, D_SITE, chi)), [link(1, 2), site(2), site(3), link(3, 4)])
-    t0 = time.perf_counter()
-    factorize(theta, [link(1, 2), site(2)], link(2, 3), cutoff=cutoff, maxdim=chi)
-    dt_f = time.perf_counter() - t0
-    return {"chi": chi, "matvec_s": dt_mv, "factorize_s": dt_f, "region_s": 3 * dt_mv + dt_f}
+# ------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle restatement of the reference path on the host cores
+# ------------------------------------------------------------------------------------------------------------------
+def force_blas_threads():
+    """All host cores for the BLAS behind NumPy, whatever OMP_NUM_THREADS said when it was loaded."""
+    n = _host_cores()
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=n)
+    except Exception:
+        pass
+    return blas_threads()
 
 
 def blas_threads():
     try:
         from threadpoolctl import threadpool_info
         n = [p.get("num_threads") for p in threadpool_info() if p.get("user_api") == "blas"]
-        return max(n) if n else os.cpu_count()
+        return max(n) if n else _host_cores()
     except Exception:
-        return os.cpu_count()
+        return _host_cores()
+
+
+def blas_name():
+    try:
+        from threadpoolctl import threadpool_info
+        for p in threadpool_info():
+            if p.get("user_api") == "blas":
+                return f"{p.get('internal_api')} {p.get('version')}"
+    except Exception:
+        pass
+    return "unknown"
+
+
+class CpuSlabMatvec:
+    """Bounded CPU sample of the chi-sized matvec: one right-bond slab (1 / nslabs of theta's last bond, what one rank of the
+    sharded GPU application computes) through the oracle's optimal_map (src/operator_map.jl:3-10 restated) with synthetic
+    environments of the full bond dimension.  Flops = dense matvec count / nslabs exactly."""
+
+    def __init__(self, chi, nslabs=CPU_SLABS, cplx=False, w=W_MPO, d=D_SITE):
+        from oracle.projttn import ProjTTN
+        from oracle.models import TTN
+        from oracle.graph import path_graph
+        from oracle.tensor import Tensor, site, link, oplink
+        rng = np.random.default_rng(1234)
+        self.chi, self.nslabs, self.cplx = chi, nslabs, cplx
+        sl = max(chi // nslabs, 1)
+
+        def rnd(shape):
+            a = rng.standard_normal(shape)
+            return a + 1j * rng.standard_normal(shape) if cplx else a
+
+        g = path_graph(4)
+        Wt = {v: Tensor(rnd((w, w, d, d)), [oplink(v - 1, v), oplink(v, v + 1), site(v, 0), site(v, 1)]) for v in (2, 3)}
+        Hn = TTN(g, {1: None, 2: Wt[2], 3: Wt[3], 4: None}, ortho_region=[])
+        self.P = ProjTTN(Hn, pos=[2, 3])
+        self.P.environments[(1, 2)] = Tensor(rnd((chi, w, chi)) / chi, [link(1, 2, 0), oplink(1, 2), link(1, 2, 1)])
+        self.P.environments[(4, 3)] = Tensor(rnd((sl, w, chi)) / chi, [link(3, 4, 0), oplink(3, 4), link(3, 4, 1)])
+        self.theta = Tensor(rnd((chi, d, d, sl)), [link(1, 2), site(2), site(3), link(3, 4)])
+        self.flops = matvec_flops(chi, chi, d, w, cplx) * sl / chi
+
+    def step(self):
+        from oracle.operator_map import optimal_map
+        t0 = time.perf_counter()
+        optimal_map(self.P, self.theta)
+        return time.perf_counter() - t0
+
+
+def cpu_matvec_sample(chi, seconds=12.0, min_reps=2, cplx=False):
+    force_blas_threads()
+    s = CpuSlabMatvec(chi, cplx=cplx)
+    s.step()                                   # warm-up (BLAS thread start-up, page faults)
+    ts = []
+    t_end = time.perf_counter() + seconds
+    while len(ts) < min_reps or time.perf_counter() < t_end:
+        ts.append(s.step())
+        if len(ts) >= 50:
+            break
+    dt = float(np.mean(ts))
+    return s.flops / dt * 1e-12, dt, len(ts), s
+
+
+def cpu_factorize_sample(n, cutoff=0.0):
+    """Oracle `factorize` (LAPACK SVD for cutoff <= 1e-12, density-matrix eigen above; ITensors rule App. A.4) of an n x n
+    two-site tensor, maxdim n / 2."""
+    from oracle.tensor import Tensor, factorize, link, site
+    force_blas_threads()
+    rng = np.random.default_rng(4321)
+    chi = n // D_SITE
+    theta = Tensor(rng.standard_normal((chi, D_SITE, D_SITE, chi)), [link(1, 2), site(2), site(3), link(3, 4)])
+    t0 = time.perf_counter()
+    factorize(theta, [link(1, 2), site(2)], link(2, 3), cutoff=cutoff, maxdim=chi)
+    return time.perf_counter() - t0
 
 
 def run_reference(args, rank, world):
-    """`--impl reference`: the reference's own CPU implementation of the path cannot run (Julia, un-vendored
-    packages), so this times the oracle restatement on the host cores (kind = "port"), rank 0 only."""
+    """`--impl reference`: the reference's own implementation cannot run here (Julia + un-vendored ITensors / KrylovKit), so
+    this times the oracle restatement (kind = "port") on every host core, rank 0 only.  Same config as the GPU arm (chi);
+    each step is a bounded sample of it: one 1/8 right-bond slab of the matvec (flops counted accordingly)."""
     if rank != 0:
         return
-    chi = args.cpu_chi
-    for _ in range(max(args.warmup - 1, 0)):
-        cpu_matvec_sample(chi, reps=1)
-    vals = [cpu_matvec_sample(chi, reps=1) for _ in range(max(args.steps, 1))]
-    tf = float(np.mean([v[0] for v in vals]))
-    ms = float(np.mean([v[1] for v in vals]) * 1e3)
-    cores = blas_threads()
-    sample = f"{len(vals)} H_eff matvecs at chi={chi} (of chi={args.chi}), d=2, w=5, NumPy/BLAS, {cores} threads"
+    cores = force_blas_threads()
+    chi = args.chi
+    s = CpuSlabMatvec(chi)
+    for _ in range(max(args.warmup, 1)):
+        s.step()
+    ts = [s.step() for _ in range(max(args.steps, 1))]
+    dt = float(np.mean(ts))
+    tf = s.flops / dt * 1e-12
+    sample = (f"{len(ts)} steps, each one right-bond slab (1/{CPU_SLABS} of theta, {s.flops:.3e} flop) of the chi={chi} H_eff matvec "
+              f"(d=2, w=5) through the oracle restatement of optimal_map, NumPy + {blas_name()}, {cores} threads of {_host_cores()} cores")
     line = {"impl": "reference", "metric": "heff_matvec_fp64_tflops", "value": tf, "unit": "TFLOP/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"S=1/2 Heisenberg chain N={args.nsites}, 2-site H_eff matvec, chi={args.chi} "
-                                   f"(CPU sample at chi={chi})", "chi": args.chi, "cpu_sample_chi": chi},
+            "config": {"workload": workload_name(args), "chi": chi,
+                       "sample": f"1/{CPU_SLABS} right-bond slab of the matvec per step; rate metric"},
             "cpu_baseline": {"value": tf, "unit": "TFLOP/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": tf, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
 
+def workload_name(args):
+    return (f"S=1/2 Heisenberg chain N={args.nsites}, no QN, 2-site H_eff matvec on an interior bond, chi={args.chi}, d=2, w=5 "
+            f"(BASELINE config 2)")
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# helpers of the GPU arm
+# ------------------------------------------------------------------------------------------------------------------
 def pinned_array(shape, dtype):
     try:
         import torch
@@ -189,40 +249,75 @@ def emit(line):
 _REAL_STDOUT = 1
 
 
-def main():
-    global _REAL_STDOUT
-    sys.stdout.flush()
-    _REAL_STDOUT = os.dup(1)
-    os.dup2(2, 1)
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--chi", type=int, default=4096)
-    ap.add_argument("--nsites", type=int, default=100)
-    ap.add_argument("--cpu-chi", type=int, default=2048, help="bond dimension of the bounded CPU sample")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--fused", action="store_true", help="multi-GPU: fused GEMM + peer-store reduce-scatter epilogue instead of the "
-                    "NCCL all-reduce (correct but slower in round 1: the DMMA fragment layout issues 64-byte P2P stores)")
-    ap.add_argument("--no-region-step", action="store_true", help="skip the full region steps (extract + 3-matvec Lanczos + truncating insert)")
-    ap.add_argument("--full-sweep", action="store_true", help="also run one real 2-site DMRG sweep over all regions (minutes at chi=4096)")
-    ap.add_argument("--region-steps", type=int, default=3, help="consecutive region steps timed after the matvec benchmark")
-    ap.add_argument("--cutoff", type=float, default=0.0, help="inserter cutoff of the region steps (0: maxdim-limited, SVD-route label; "
-                    "1e-9: the reference's timed_dmrg setting, eigen-route label)")
-    ap.add_argument("--no-canonical", action="store_true", help="leave the synthetic state as filled (random tensors, gauge flag only) instead of "
-                    "orthonormalising it to the benchmark bond with device QRs during set-up (about a minute at chi=4096)")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+def roofline_from_profile(ctx, recs, ms_total, traffic_key=None):
+    """Roofline of the dominant kernel (the persistent TMA + DMMA GEMM) from the launches of the timed region."""
+    if not recs:
+        return None
+    peak = ctx.dmma_peak_tflops()
+    g_ms = sum(r[0] for r in recs)
+    g_fl = sum(r[1] for r in recs)
+    by = {}
+    for ms, fl, mnk in recs:
+        e = by.setdefault(mnk, [0, 0.0, 0.0])
+        e[0] += 1; e[1] += ms; e[2] += fl
+    launches = [{"M": k[0], "N": k[1], "K": k[2], "batch": k[3], "launches": v[0], "avg_ms": v[1] / v[0],
+                 "tflops": v[2] / v[1] * 1e-9 if v[1] > 0 else None} for k, v in sorted(by.items(), key=lambda kv: -kv[1][1])]
+    achieved = g_fl / g_ms * 1e-9
+    traffic = None
+    tnote = "no ncu --set full capture of this launch committed for this round"
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")))
+        if traffic_key and traffic_key in tj:
+            traffic = tj[traffic_key]["dram_bytes"]
+            tnote = tj[traffic_key].get("note", "")
+    except Exception:
+        pass
+    return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "traffic": traffic, "traffic_note": tnote,
+            "kernel": "gemm_tma_kernel (persistent TMA + mbarrier + DMMA GEMM): every GEMM launch of the timed steps",
+            "how": "CUDA events on the launching stream around each GEMM launch inside the timed region; achieved = issued flops / "
+                   "summed launch durations",
+            "gemm_ms_per_step_share": g_ms / ms_total if ms_total > 0 else None,
+            "launch_shapes": launches[:6],
+            "peak_source": "FP64 DMMA issue ceiling measured live by nsb_dmma_peak (register-resident mma.sync loop); "
+                           "MEASURED_PEAKS.json has no FP64 entry and the profiling guide states no FP64 fallback "
+                           "(148 SM x 64 FMA x 2 x 1.965 GHz = 37.2)"}
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-        return
+def build_problem(chi, nsites, ctx, dtype=np.float64, canonical=True, model="heisenberg"):
+    import networksolvers_b200 as ns
+    g = ns.path_graph(nsites)
+    sites = ns.siteinds("S=1/2", g)
+    H = ns.ttno(ns.heisenberg(g) if model == "heisenberg" else ns.transverse_ising(g, 1.0, 1.0), sites)
+    mid = nsites // 2
+    region = [mid, mid + 1]
+    net = ns.DeviceNetwork.synthetic(H, sites, chi, seed=1234, dtype=dtype, ctx=ctx, ortho_region=region, canonical=canonical)
+    return net, region
 
+
+def time_region_steps(ctx, net, regions, trunc, solver):
+    """Full region steps through the three hooks; returns (wall seconds per step, phase timers per step, newdims)."""
+    ctx.enable_timers(True)
+    steps, phases, newdims = [], [], []
+    for reg in regions:
+        ctx.reset_timers()
+        ctx.synchronize()
+        t0 = time.perf_counter()
+        net.extract(reg)
+        solver()
+        ins = net.insert(trunc)
+        ctx.synchronize()
+        steps.append(time.perf_counter() - t0)
+        phases.append(ctx.timers())
+        newdims.append(int(ins.newdim))
+    ctx.enable_timers(False)
+    return steps, phases, newdims
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# config 2 (headline)
+# ------------------------------------------------------------------------------------------------------------------
+def run_config2(args, rank, world, local_rank):
     import torch
     import networksolvers_b200 as ns
     dist = None
@@ -231,23 +326,33 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = ns.Context(local_rank)
-    net, region = build_problem(args.chi, args.nsites, ctx, canonical=not args.no_canonical)   # same seed on every rank: replicated state
     t_setup = time.perf_counter()
+    net, region = build_problem(args.chi, args.nsites, ctx, canonical=not args.no_canonical)   # same seed on every rank
     info = net.extract(region)
     ctx.synchronize()
     t_setup = time.perf_counter() - t_setup
     legs, dims = net.local_info()
     flops_dense = net.matvec_flops()
     assert abs(flops_dense - matvec_flops(dims[0], dims[-1])) < 1e-6 * flops_dense, (flops_dense, dims)
-    # throughput is computed from the flops actually issued: the identity channel of the left / right
-    # environment is skipped when present, the dense-equivalent figure is reported beside it
-    flops = net.matvec_flops_executed()
     shard = None
+    shard_err = None
     if world > 1:
         from networksolvers_b200.parallel import setup_sharded_matvec
         shard = setup_sharded_matvec(net, dist, rank, world, fused=args.fused)
         if not shard.active:
             shard = None
+        else:
+            # driver-side multi-GPU parity: sharded application against the single-GPU application of the same theta
+            y_sh = net.matvec_device(1, download=True)
+            shard.enable(False)
+            y_rep = net.matvec_device(1, download=True)
+            shard.enable(True)
+            shard_err = float(np.abs(y_sh - y_rep).max() / np.abs(y_rep).max())
+            t = torch.tensor([shard_err], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            shard_err = float(t.item())
+            assert shard_err <= 1e-12, f"sharded matvec differs from the replicated one: {shard_err}"
+            del y_sh, y_rep
 
     def barrier():
         if dist is not None:
@@ -256,39 +361,40 @@ def main():
         ctx.synchronize()
 
     def step():
-        if shard is not None:
-            shard.matvec()
-        else:
-            net.matvec_device(1)
+        net.matvec_device(1)
 
     for _ in range(args.warmup):
         step()
     barrier()
     flops = net.matvec_flops_executed()   # what the applications above really issued (whole job, all ranks)
     ctx.reset_counters()
+    ctx.gemm_profile(True)
     with ClockSampler(local_rank) as clk:
         ctx.tic()
         for _ in range(args.steps):
             step()
         ms_total = ctx.toc()
     barrier()
+    recs = ctx.gemm_profile_read()
+    ctx.gemm_profile(False)
     launches = ctx.counters()["kernel_launches"]
+    ms_local = ms_total
     if dist is not None:
         tmax = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         ms_total = float(tmax.item())
     ms_step = ms_total / args.steps
     tflops = flops / (ms_step * 1e-3) * 1e-12
+    replicas = world if (shard is None and world > 1) else 1
 
-    # ---- end-to-end through the host-buffer call (rank-local matvec; multi-GPU e2e uses the same sharded step
-    # after a host->device upload of theta) ----
+    # ---- end-to-end through the host-buffer call ----
     nbytes = int(np.prod(dims)) * 8
     hin, keep1 = pinned_array(dims, np.float64)
-    hin[...] = 0.0
     theta0, _ = net.local_download()
     hin[...] = theta0
+    del theta0
     hout, keep2 = pinned_array(dims, np.float64)
-    lib, C = ctx._lib, __import__("ctypes")
+    lib = ctx._lib
     e2e_steps = max(3, min(args.steps, 5))
     for _ in range(2):
         ctx.check(lib.nsb_matvec_host(net.handle, hin.ctypes.data, hout.ctypes.data))
@@ -301,125 +407,96 @@ def main():
         tt = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
-    e2e_tflops = flops * (world if shard is None and world > 1 else 1) / e2e_s * 1e-12
+    e2e_tflops = flops * replicas / e2e_s * 1e-12
 
-    # ---- roofline of the dominant kernel (the DMMA GEMM), measured live on this box ----
-    roof = None
-    if rank == 0:
-        chi_l, chi_r = dims[0], dims[-1]
-        peak = ctx.dmma_peak_tflops()
-        m1, n1, k1 = W_MPO * chi_l, D_SITE * D_SITE * chi_r, chi_l          # K1: T1 = L^T theta   (TN)
-        m3, n3, k3 = chi_l * D_SITE * D_SITE, chi_r, W_MPO * chi_r          # K3: theta' = T3 R    (NN)
-        t1 = ctx.gemm_bench(m1, n1, k1, "T", "N", reps=3)
-        t3 = ctx.gemm_bench(m3, n3, k3, "N", "N", reps=3)
-        gflops = 2.0 * m1 * n1 * k1 + 2.0 * m3 * n3 * k3
-        achieved = gflops / ((t1 + t3) * 1e-3) * 1e-12
-        roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": NCU_TRAFFIC_BYTES.get(int(chi_l)),
-                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the K3 launch from the committed ncu --set full "
-                                "capture (profiles/r01_ncu_full_gemm_tma_K3_chi4096.json); algorithmic bytes of that launch 3.9e9; "
-                                "sm__pipe_tensor_cycles_active 97.4 %, dram throughput 2.8 % of peak",
-                "kernel": "gemm_tma_kernel<double> (K1 TN + K3 NN launches of the matvec)",
-                "k1_ms": t1, "k3_ms": t3,
-                "peak_source": "FP64 DMMA issue ceiling measured live by nsb_dmma_peak (MEASURED_PEAKS.json has no FP64 "
-                               "entry; cuBLAS DGEMM on this pool reaches 35.5-36.0, profiles/r01_microbench_fp64_peaks.jsonl)"}
+    roof = roofline_from_profile(ctx, recs, ms_local, traffic_key=f"chi{args.chi}_matvec_gemm") if rank == 0 else None
 
     extra = {}
-    if not args.no_region_step and (world == 1 or shard is not None):   # sharded runs: every rank steps in lock step
-        # Consecutive full region steps of a left-to-right 2-site sweep through the three hooks (extract = gauge +
-        # theta build + environment update; eigsolve = 3-matvec Lanczos; insert = truncating factorisation), starting
-        # on the benchmark bond.  The first step re-uses the environments built during set-up; the later ones include
-        # the one environment update a sweep step needs.
-        ctx.enable_timers(True)
+    if not args.no_region_step and (world == 1 or shard is not None):
+        # Consecutive full region steps of a 2-site sweep through the three hooks, first to the right from the benchmark
+        # bond, then back to the left (both directions of the Euler tour).
         tr = (args.cutoff, 1, args.chi)
-        steps, phases, newdims = [], [], []
-        for r in range(max(args.region_steps, 1)):
-            reg = [region[0] + r, region[1] + r]
-            if reg[1] > args.nsites:
-                break
-            ctx.reset_timers()
-            ctx.synchronize()
-            t0 = time.perf_counter()
-            net.extract(reg)
-            val, sinfo = net.update_eigsolve()
-            ins = net.insert(tr)
-            ctx.synchronize()
-            steps.append(time.perf_counter() - t0)
-            phases.append(ctx.timers())
-            newdims.append(int(ins.newdim))
-        full = steps[1:] if len(steps) > 1 else steps
-        extra["region_step_s"] = float(np.mean(full))
+        nr = max(args.region_steps, 1)
+        right = [[region[0] + r, region[1] + r] for r in range(nr) if region[1] + r <= args.nsites]
+        left = [[right[-1][1] - r, right[-1][0] - r] for r in range(nr)]
+        steps, phases, newdims = time_region_steps(ctx, net, right + left, tr, lambda: net.update_eigsolve())
+        full = list(range(1, len(right))) + list(range(len(right) + 1, len(steps)))   # steps that include one environment update
+        extra["region_step_s"] = float(np.mean([steps[i] for i in full]))
         extra["region_steps_s"] = steps
-        extra["region_phase_ms"] = {k: float(np.mean([ph[k] for ph in (phases[1:] if len(phases) > 1 else phases)])) for k in phases[0]}
+        extra["region_directions"] = ["right"] * len(right) + ["left"] * len(left)
+        extra["region_phase_ms"] = {k: float(np.mean([phases[i][k] for i in full])) for k in phases[0]}
         extra["region_newdim"] = newdims
         extra["region_trunc"] = {"cutoff": args.cutoff, "maxdim": args.chi}
         extra["sweep_regions"] = 2 * (args.nsites - 1)
-        # interior region step x number of regions of an Euler-tour sweep (end regions are cheaper): upper estimate
         extra["sweep_s_extrapolated"] = extra["region_step_s"] * 2 * (args.nsites - 1)
         if world > 1:
-            extra["region_parallelism"] = "H_eff applications sharded + NCCL all-reduce; environment update and factorisation replicated"
-        ctx.enable_timers(False)
+            extra["region_parallelism"] = net.parallelism_note() if hasattr(net, "parallelism_note") else \
+                "H_eff applications sharded; environment update and factorisation replicated"
+        mi = ctx.mem_info()
+        extra["hbm_pool_used_gib"] = mi["pool_used"] / 2**30
 
-    if args.full_sweep and world == 1:
-        # One real 2-site DMRG sweep (all 2 (N - 1) regions of the Euler tour) through the public driver on a fresh
-        # synthetic state whose centre flag sits on the tour's first region (no long gauge walk before the sweep).
-        net.close()   # 95 GB of tensors and environments go back to the pool before the second network is built
+    if not args.no_full_sweep and (world == 1 or args.full_sweep):
+        # One real 2-site DMRG sweep (all 2 (N - 1) regions of the Euler tour) through the public driver, continuing on the
+        # same network: the gauge walk to the tour's first region and the environments it needs are set-up (not timed).
         g = ns.path_graph(args.nsites)
-        sites = ns.siteinds("S=1/2", g)
-        H = ns.ttno(ns.heisenberg(g), sites)
         plan = ns.euler_sweep(g, nsites=2)
-        first = list(plan[0][0])
-        net2 = ns.DeviceNetwork.synthetic(H, sites, args.chi, seed=1234, ctx=ctx, ortho_region=first, canonical=not args.no_canonical)
-        prob = ns.EigsolveProblem(net=net2)
+        t0 = time.perf_counter()
+        net.extract(list(plan[0][0]))
+        ctx.synchronize()
+        extra["full_sweep_setup_s"] = time.perf_counter() - t0
+        prob = ns.EigsolveProblem(net=net)
         ctx.enable_timers(True)
         ctx.reset_timers()
         ctx.reset_counters()
-        ctx.synchronize()
+        barrier()
         t0 = time.perf_counter()
-        tr = dict(cutoff=args.cutoff, maxdim=args.chi)
-        E, _ = ns.dmrg(prob, nsweeps=1, nsites=2, inserter_kwargs=dict(trunc=tr))
-        ctx.synchronize()
+        E, _ = ns.dmrg(prob, nsweeps=1, nsites=2, inserter_kwargs=dict(trunc=dict(cutoff=args.cutoff, maxdim=args.chi)))
+        barrier()
         extra["full_sweep_s"] = time.perf_counter() - t0
         extra["full_sweep_regions"] = len(plan)
         extra["full_sweep_phase_ms"] = ctx.timers()
         extra["full_sweep_launches"] = int(ctx.counters()["kernel_launches"])
-        extra["full_sweep_maxlinkdim"] = int(net2.maxlinkdim())
+        extra["full_sweep_maxlinkdim"] = int(net.maxlinkdim())
+        extra["full_sweep_energy"] = float(E)
         ctx.enable_timers(False)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        ctf, cdt = cpu_matvec_sample(args.cpu_chi, reps=3)
+        ctf, cdt, creps, s = cpu_matvec_sample(args.chi, seconds=12.0)
         cores = blas_threads()
         cpu = {"value": ctf, "unit": "TFLOP/s", "cores": cores, "kind": "port",
-               "sample": f"3 H_eff matvecs at chi={args.cpu_chi} (GPU arm: chi={args.chi}), oracle restatement of optimal_map "
-                         f"(NumPy/BLAS, {cores} threads); Julia reference not runnable here"}
+               "sample": f"{creps} x one right-bond slab (1/{CPU_SLABS}) of the chi={args.chi} H_eff matvec, oracle restatement of "
+                         f"optimal_map (NumPy + {blas_name()}, {cores} threads); Julia reference not runnable here"}
         if not args.no_region_step:
-            # the same bounded sample for a whole region step (3 matvecs + truncating factorisation, no environment
-            # update); both parts scale as chi^3, so x (chi / cpu_chi)^3 is the like-for-like estimate at the GPU's chi
-            cr = cpu_region_sample(args.cpu_chi, cutoff=args.cutoff)
-            cr["region_s_scaled_to_gpu_chi"] = cr["region_s"] * (args.chi / args.cpu_chi) ** 3
-            cr["note"] = "3 matvecs + oracle factorize (LAPACK) at the sample chi; scaled by (chi/cpu_chi)^3"
-            cpu["region_step"] = cr
+            # factorisation sample at a bounded size (LAPACK gesdd / syevd scale as n^3), scaled to the GPU arm's 2 chi
+            nf = min(2 * args.chi, 2048)
+            dt_f = cpu_factorize_sample(nf, cutoff=args.cutoff)
+            mv_full = cdt * CPU_SLABS
+            cpu["region_step"] = {"matvec_s_at_chi": mv_full, "factorize_s_sample": dt_f, "factorize_sample_n": nf,
+                                  "factorize_s_scaled": dt_f * (2 * args.chi / nf) ** 3,
+                                  "region_s_estimate": 3 * mv_full + dt_f * (2 * args.chi / nf) ** 3,
+                                  "note": "3 matvecs (slab sample x 8) + oracle factorize (LAPACK) scaled by (n / n_sample)^3; "
+                                          "no environment update counted"}
 
     if rank == 0:
-        line = {"metric": "heff_matvec_fp64_tflops", "value": tflops * (world if shard is None and world > 1 else 1),
+        line = {"metric": "heff_matvec_fp64_tflops", "value": tflops * replicas,
                 "unit": "TFLOP/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "strong" if shard is not None else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"S=1/2 Heisenberg chain N={args.nsites}, no QN, 2-site H_eff matvec on bond "
-                                       f"({region[0]},{region[1]}), chi={args.chi}, d=2, w=5 (BASELINE config 2)",
+                "config": {"workload": workload_name(args), "bond": region,
                            "chi": args.chi, "local_dims": dims, "flops_per_step": flops, "dense_flops_per_step": flops_dense,
                            "flops_note": "value / e2e use the flops actually issued; dense_flops_per_step is the reference's "
                                          "dense-W count 4 w d^2 chi^3 + 4 w^2 d^3 chi^2 (identity channels of L and R skipped)",
                            "l2": "inputs larger than L2 (L 0.64 GB, theta 0.5 GB, T1 2.5 GB per matvec)",
                            "state": ("random tensors orthonormalised to the benchmark bond (device QR gauge walk)" if not args.no_canonical else "random tensors, gauge flag only"),
-                           "parallelism": ("replicated" if shard is None else f"theta right-bond sharded x{world} + " +
-                                           ("fused GEMM/peer-store reduce-scatter + allgather" if args.fused else "NCCL allreduce"))
+                           "parallelism": ("replicated" if shard is None else net_parallelism(net, world, args))
                            if world > 1 else "single GPU", "setup_s": t_setup, "env_builds": info.env_builds},
                 "e2e": {"value": e2e_tflops, "unit": "TFLOP/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
                         "ms_per_step": e2e_s * 1e3},
                 "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roof,
-                "dense_equivalent_tflops": flops_dense / (ms_step * 1e-3) * 1e-12 * (world if shard is None and world > 1 else 1)}
+                "dense_equivalent_tflops": flops_dense / (ms_step * 1e-3) * 1e-12 * replicas}
+        if shard_err is not None:
+            line["sharded_vs_replicated_max_rel_err"] = shard_err
         if cpu is not None:
             line["cpu_baseline"] = cpu
         line.update(extra)
@@ -429,5 +506,253 @@ def main():
         dist.destroy_process_group()
 
 
+def net_parallelism(net, world, args):
+    if args.fused:
+        return f"theta right-bond sharded x{world} + fused GEMM/peer-store reduce-scatter + allgather"
+    return f"theta last-bond sharded x{world} + NCCL collective per application (see region_parallelism)"
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# other BASELINE configs (single GPU)
+# ------------------------------------------------------------------------------------------------------------------
+def _line(metric, value, unit, args, ms_step, hib, dtype, workload, extra_cfg, e2e, launches, clk, roof, cpu, extra):
+    line = {"metric": metric, "value": value, "unit": unit, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": hib, "scaling": "weak", "vs_baseline": None, "dtype": dtype,
+            "data": "synthetic", "config": dict({"workload": workload}, **extra_cfg), "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clk, "roofline": roof}
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    line.update(extra)
+    return line
+
+
+def run_config1(args):
+    """BASELINE config 1: S=1/2 Heisenberg N=20, 2-site DMRG, maxdim 100, cutoff 1e-12 from the Neel product state (the
+    reference's own CPU-runnable case).  A step = one full sweep at saturated bond dimension; e2e = the whole public call
+    ns.dmrg(H, psi0) from host tensors (upload, 5 sweeps, download) per sweep."""
+    import networksolvers_b200 as ns
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import neel, to_oracle_ttn
+    ctx = ns.default_context()
+    g = ns.path_graph(20)
+    sites = ns.siteinds("S=1/2", g)
+    H = ns.ttno(ns.heisenberg(g), sites)
+    psi0 = ns.product_state(sites, neel(g))
+    trunc = dict(cutoff=1e-12, maxdim=100)
+    prob = ns.EigsolveProblem(state=psi0, operator=H, ctx=ctx)
+    E, _ = ns.dmrg(prob, nsweeps=max(args.warmup, 4), nsites=2, inserter_kwargs=dict(trunc=trunc))
+    ctx.reset_counters()
+    ctx.gemm_profile(True)
+    with ClockSampler(0) as clk:
+        ctx.tic()
+        t0 = time.perf_counter()
+        E, _ = ns.dmrg(prob, nsweeps=args.steps, nsites=2, inserter_kwargs=dict(trunc=trunc))
+        ctx.synchronize()
+        wall = time.perf_counter() - t0
+        ms_total = ctx.toc()
+    recs = ctx.gemm_profile_read()
+    ctx.gemm_profile(False)
+    launches = ctx.counters()["kernel_launches"]
+    roof = roofline_from_profile(ctx, recs, ms_total)
+    if roof:
+        roof["note"] = "chi <= 100: the sweep is launch-latency bound, the GEMM share of the step says so"
+    t0 = time.perf_counter()
+    E2, psi = ns.dmrg(H, psi0, nsweeps=5, nsites=2, inserter_kwargs=dict(trunc=trunc), ctx=ctx)
+    host = psi.to_host()
+    e2e_s = (time.perf_counter() - t0) / 5
+    nbytes_in = sum(a.nbytes for a in psi0.tensors.values()) + sum(a.nbytes for a in H.tensors.values())
+    nbytes_out = sum(a.nbytes for a in host.tensors.values())
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import sweep as osw
+        cores = force_blas_threads()
+        t0 = time.perf_counter()
+        Eo, _ = osw.dmrg(to_oracle_ttn(H, True), to_oracle_ttn(psi0), nsweeps=5, nsites=2, inserter_kwargs=dict(trunc=trunc))
+        cs = (time.perf_counter() - t0) / 5
+        cpu = {"value": cs, "unit": "s/sweep", "cores": cores, "kind": "port",
+               "sample": f"oracle dmrg, the same 5 sweeps from the Neel state (NumPy + {blas_name()}), energy {Eo:.12f}"}
+    extra = {"energy": float(E2), "energy_exact_ed": -8.682473334399, "sweep_wall_s": wall / args.steps}
+    emit(_line("dmrg_two_site_sweep_s", ms_total / args.steps * 1e-3, "s/sweep", args, ms_total / args.steps, False, "f64",
+               "S=1/2 Heisenberg chain N=20 path_graph, 2-site DMRG maxdim=100 cutoff=1e-12 (BASELINE config 1, examples/dmrg.jl shape)",
+               {"maxlinkdim": int(prob.net.maxlinkdim()), "l2": "working set far below L2: latency-bound regime, nothing to flush"},
+               {"value": e2e_s, "unit": "s/sweep", "h2d_bytes_per_step": nbytes_in // 5, "d2h_bytes_per_step": nbytes_out // 5},
+               launches, clk.summary(), roof, cpu, extra))
+
+
+def run_config4(args):
+    """BASELINE config 4: 2-site TDVP quench, N=64, chi=1024, complex128, Heisenberg (w=5); dt=0.05, RK4 local solver, cutoff
+    1e-14 (examples/quench_evolution.jl:20-57).  A step = one complex H_eff application; then 2-site TDVP region steps
+    (4 matvecs + truncating factorisation)."""
+    import networksolvers_b200 as ns
+    ctx = ns.default_context()
+    chi, N = args.chi if args.chi != 4096 else 1024, 64
+    out = {}
+    for model in ("heisenberg", "ising"):
+        w = 5 if model == "heisenberg" else 3
+        t0 = time.perf_counter()
+        net, region = build_problem(chi, N, ctx, dtype=np.complex128, canonical=not args.no_canonical, model=model)
+        net.extract(region)
+        ctx.synchronize()
+        setup = time.perf_counter() - t0
+        legs, dims = net.local_info()
+        for _ in range(args.warmup):
+            net.matvec_device(1)
+        flops = net.matvec_flops_executed()
+        ctx.reset_counters()
+        ctx.gemm_profile(True)
+        with ClockSampler(0) as clk:
+            ctx.tic()
+            net.matvec_device(args.steps)
+            ms_total = ctx.toc()
+        recs = ctx.gemm_profile_read()
+        ctx.gemm_profile(False)
+        launches = ctx.counters()["kernel_launches"]
+        ms = ms_total / args.steps
+        roof = roofline_from_profile(ctx, recs, ms_total)
+        hin, k1 = pinned_array(dims, np.complex128)
+        th, _ = net.local_download()
+        hin[...] = th
+        hout, k2 = pinned_array(dims, np.complex128)
+        for _ in range(2):
+            ctx.check(ctx._lib.nsb_matvec_host(net.handle, hin.ctypes.data, hout.ctypes.data))
+        t0 = time.perf_counter()
+        for _ in range(3):
+            ctx.check(ctx._lib.nsb_matvec_host(net.handle, hin.ctypes.data, hout.ctypes.data))
+        e2e_s = (time.perf_counter() - t0) / 3
+        nbytes = int(np.prod(dims)) * 16
+        tr = (1e-14, 1, chi)
+        regs = [[region[0] + r, region[1] + r] for r in range(3)]
+        steps, phases, newdims = time_region_steps(ctx, net, regs, tr, lambda: net.update_exp(-0.05j, solver="rk", order=4, nsites=2))
+        res = {"matvec_ms": ms, "matvec_tflops_real": flops / ms * 1e-9, "setup_s": setup, "region_step_s": float(np.mean(steps[1:])),
+               "region_phase_ms": {k: float(np.mean([p[k] for p in phases[1:]])) for k in phases[0]}, "region_newdim": newdims,
+               "half_sweep_s_extrapolated": float(np.mean(steps[1:])) * (N - 1), "time_step_order4_s_extrapolated": float(np.mean(steps[1:])) * (N - 1) * 6}
+        if model == "heisenberg":
+            cpu = None
+            if not args.no_cpu_baseline:
+                ctf, cdt, creps, s = cpu_matvec_sample(chi, seconds=10.0, cplx=True)
+                cpu = {"value": ctf, "unit": "TFLOP/s", "cores": blas_threads(), "kind": "port",
+                       "sample": f"{creps} x one right-bond slab (1/{CPU_SLABS}) of the complex chi={chi} matvec, oracle optimal_map (NumPy + {blas_name()})"}
+            head = dict(ms=ms, flops=flops, e2e_s=e2e_s, nbytes=nbytes, launches=launches, clk=clk.summary(), roof=roof, cpu=cpu, dims=dims)
+        out[model] = res
+        net.close()
+    emit(_line("heff_matvec_c128_real_tflops", head["flops"] / head["ms"] * 1e-9, "TFLOP/s", args, head["ms"], True, "c128",
+               f"2-site TDVP quench on the S=1/2 Heisenberg chain N=64, chi={chi}, complex128, dt=0.05, RK4 (BASELINE config 4, "
+               "examples/quench_evolution.jl shape); Ising (w=3) beside it",
+               {"chi": chi, "local_dims": head["dims"], "flops_per_step": head["flops"], "flops_note": "real flops (4 per complex multiply-add pair)",
+                "l2": "inputs larger than L2 (T1 320 MiB per matvec)"},
+               {"value": head["flops"] / head["e2e_s"] * 1e-12, "unit": "TFLOP/s", "h2d_bytes_per_step": head["nbytes"], "d2h_bytes_per_step": head["nbytes"],
+                "ms_per_step": head["e2e_s"] * 1e3},
+               head["launches"], head["clk"], head["roof"], head["cpu"], {"models": out}))
+
+
+def run_config5(args):
+    """BASELINE config 5: Heisenberg on named_comb_tree (10 teeth x 6 = 60 sites), Euler-tour plan.  As SURVEY 8(d) states the
+    2-site tensor on a backbone edge at chi=512 is 2 TiB, so the run is 1-site DMRG + "densitymatrix" expansion at chi=512 on a
+    degree-3 backbone vertex (local tensor chi^3 d = 2 GiB).  A step = one H_eff application on that vertex."""
+    import networksolvers_b200 as ns
+    ctx = ns.default_context()
+    chi = args.chi if args.chi != 4096 else 512
+    g = ns.named_comb_tree([6] * 10)
+    sites = ns.siteinds("S=1/2", g)
+    H = ns.ttno(ns.heisenberg(g), sites)
+    v = (5, 1)
+    t0 = time.perf_counter()
+    net = ns.DeviceNetwork.synthetic(H, sites, chi, seed=7, dtype=np.float64, ctx=ctx, ortho_region=[v], canonical=not args.no_canonical)
+    net.extract([v])
+    ctx.synchronize()
+    setup = time.perf_counter() - t0
+    legs, dims = net.local_info()
+    for _ in range(args.warmup):
+        net.matvec_device(1)
+    flops = net.matvec_flops_executed()
+    ctx.reset_counters()
+    ctx.gemm_profile(True)
+    with ClockSampler(0) as clk:
+        ctx.tic()
+        net.matvec_device(args.steps)
+        ms_total = ctx.toc()
+    recs = ctx.gemm_profile_read()
+    ctx.gemm_profile(False)
+    c = ctx.counters()
+    ms = ms_total / args.steps
+    roof = roofline_from_profile(ctx, recs, ms_total)
+    hin, k1 = pinned_array(dims, np.float64)
+    th, _ = net.local_download()
+    hin[...] = th
+    hout, k2 = pinned_array(dims, np.float64)
+    for _ in range(2):
+        ctx.check(ctx._lib.nsb_matvec_host(net.handle, hin.ctypes.data, hout.ctypes.data))
+    t0 = time.perf_counter()
+    for _ in range(3):
+        ctx.check(ctx._lib.nsb_matvec_host(net.handle, hin.ctypes.data, hout.ctypes.data))
+    e2e_s = (time.perf_counter() - t0) / 3
+    nbytes = int(np.prod(dims)) * 8
+    ctx.enable_timers(True)
+    ctx.reset_timers()
+    t0 = time.perf_counter()
+    val, sinfo = net.update_eigsolve()
+    net.insert((1e-9, 1, chi))
+    ctx.synchronize()
+    region_s = time.perf_counter() - t0
+    ph = ctx.timers()
+    ctx.enable_timers(False)
+    extra = {"region_step_s": region_s, "region_phase_ms": ph, "nmatvec": int(sinfo.nmatvec), "setup_s": setup,
+             "permute_bytes_per_matvec": c["permute_bytes"] / args.steps, "hbm_pool_used_gib": ctx.mem_info()["pool_used"] / 2**30}
+    emit(_line("heff_matvec_fp64_tflops", flops / ms * 1e-9, "TFLOP/s", args, ms, True, "f64",
+               f"Heisenberg on named_comb_tree 10 x 6 (60 sites), 1-site H_eff on the degree-3 backbone vertex {v}, chi={chi} "
+               "(BASELINE config 5; the 2-site tensor on a backbone edge would be chi^4 d^2 = 2 TiB)",
+               {"chi": chi, "local_dims": dims, "flops_per_step": flops, "l2": f"local tensor {nbytes / 2**30:.2f} GiB > L2"},
+               {"value": flops / e2e_s * 1e-12, "unit": "TFLOP/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "ms_per_step": e2e_s * 1e3},
+               c["kernel_launches"], clk.summary(), roof, None, extra))
+
+
+def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5], help="BASELINE.json config (2 = headline)")
+    ap.add_argument("--chi", type=int, default=4096)
+    ap.add_argument("--nsites", type=int, default=100)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fused", action="store_true", help="multi-GPU: fused GEMM + peer-store reduce-scatter epilogue instead of the "
+                    "NCCL collective")
+    ap.add_argument("--no-region-step", action="store_true", help="skip the full region steps (extract + 3-matvec Lanczos + truncating insert)")
+    ap.add_argument("--no-full-sweep", action="store_true", help="single GPU: skip the measured full 2-site DMRG sweep (about 2.5 minutes at chi=4096)")
+    ap.add_argument("--full-sweep", action="store_true", help="multi-GPU: also run the measured full sweep (every rank in lock step)")
+    ap.add_argument("--region-steps", type=int, default=3, help="consecutive region steps timed in each sweep direction")
+    ap.add_argument("--cutoff", type=float, default=0.0, help="inserter cutoff of the region steps (0: maxdim-limited; 1e-9: the reference's "
+                    "timed_dmrg setting)")
+    ap.add_argument("--no-canonical", action="store_true", help="leave the synthetic state as filled (random tensors, gauge flag only) instead of "
+                    "orthonormalising it to the benchmark bond with device QRs during set-up")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if args.config == 2:
+        run_config2(args, rank, world, local_rank)
+        return
+    if rank != 0:
+        return            # the other configs are single-GPU measurements
+    {1: run_config1, 3: run_config3, 4: run_config4, 5: run_config5}[args.config](args)
+
+
+def run_config3(args):
+    from bench_qn import run_config3 as impl      # tools/bench_qn.py (Hubbard chain with QN conservation)
+    impl(args, emit, _line, ClockSampler, roofline_from_profile, pinned_array)
+
+
 if __name__ == "__main__":
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
     main()

@@ -122,7 +122,9 @@ typedef struct {
 typedef struct {
   int64_t newdim;  /* dimension of the new bond (2-site), or current bond for 1-site */
   double truncerr; /* discarded weight / total weight (NDTensors truncate! rule) */
-  int32_t decomp;  /* 0 none (1-site), 1 svd, 2 eigen, 3 qr */
+  int32_t decomp;  /* 0 none (1-site), 1 svd (one-sided Jacobi), 2 eigen (density matrix: the reference's route for cutoff > 1e-12,
+                      and the device route at n >= eigh_min_n with cutoff == 0), 3 svd label computed as Gram + eigh with
+                      Rayleigh-quotient refinement of the spectrum (0 < cutoff <= 1e-12, n >= eigh_min_n) */
   int32_t jacobi_sweeps;
 } nsb_insert_info;
 
@@ -153,6 +155,12 @@ int nsb_event_toc(nsb_ctx* ctx, double* ms_out);
 int nsb_timers_enable(nsb_ctx* ctx, int on);
 int nsb_timers_get(nsb_ctx* ctx, double* ms_out /* NSB_NUM_TIMERS */);
 int nsb_timers_reset(nsb_ctx* ctx);
+/* Per-launch timing of the GEMM kernels (CUDA events on the context's stream around every GEMM launch while enabled).
+ * nsb_gemm_profile_read synchronises and returns, for launch i < min(count, cap): elapsed ms, real flops issued and
+ * (M, N, K, batch).  bench.py derives its roofline from the GEMM launches of the timed region itself with this. */
+int nsb_gemm_profile_enable(nsb_ctx* ctx, int32_t on); /* also clears the records */
+int nsb_gemm_profile_read(nsb_ctx* ctx, int64_t cap, double* ms_out, double* flops_out, int64_t* mnkb_out /* 4*cap */,
+                          int64_t* count_out);
 int nsb_mem_info(nsb_ctx* ctx, int64_t* free_bytes, int64_t* total_bytes, int64_t* pool_used_bytes);
 
 /* multi-GPU: one process per GPU; rank 0 creates the id, the host side (torch.distributed, MPI ...)
@@ -212,6 +220,37 @@ int nsb_update_exp(nsb_net* net, double t_re, double t_im, int32_t solver, const
 int nsb_insert(nsb_net* net, const nsb_trunc* trunc /* inserter's */, int32_t normalize, int32_t set_ortho,
                nsb_insert_info* info);
 
+/* ---- single-process multi-device entry points -------------------------------------------------
+ * For a host with ONE thread of control (the Julia sweep driver of src/sweep_solve.jl:12-40): an nsb_multi owns one context
+ * and one replica network per device and the NCCL communicator joining them; every nsb_multi_* hook runs the corresponding
+ * single-device call on all devices concurrently (one host thread per device inside the library) and returns when all are
+ * done.  The replicas execute the sharded region step of nsb_net_set_shard in lock step; scalars returned are device 0's
+ * (identical on all).  nsb_multi_ctx / nsb_multi_net expose the per-device handles for the non-collective calls
+ * (options, counters, timers, nsb_site_download, nsb_linkdim, nsb_maxlinkdim, nsb_norm ... on device 0).
+ * nsb_local_sync is the collective that completes a sharded local tensor before nsb_local_download. */
+typedef struct nsb_multi nsb_multi;
+int nsb_multi_create(const int32_t* devices, int32_t ndev /* 1..8 */, nsb_multi** out);
+int nsb_multi_destroy(nsb_multi* m);
+const char* nsb_multi_last_error(nsb_multi* m);
+int nsb_multi_ndev(nsb_multi* m, int32_t* ndev);
+int nsb_multi_ctx(nsb_multi* m, int32_t r, nsb_ctx** out);
+int nsb_multi_net(nsb_multi* m, int32_t r, nsb_net** out);
+int nsb_multi_network_create(nsb_multi* m, int32_t nverts, const int32_t* edges, int32_t nedges, const int64_t* site_dims, int32_t dtype);
+int nsb_multi_site_upload(nsb_multi* m, int32_t v, int32_t rank, const int32_t* legs, const int64_t* dims, const void* host);
+int nsb_multi_mpo_upload(nsb_multi* m, int32_t v, int32_t rank, const int32_t* legs, const int64_t* dims, const void* host);
+int nsb_multi_site_fill_random(nsb_multi* m, int32_t v, int32_t rank, const int32_t* legs, const int64_t* dims, uint64_t seed, double scale);
+int nsb_multi_set_ortho_region(nsb_multi* m, const int32_t* verts, int32_t n);
+int nsb_multi_set_shard(nsb_multi* m, int32_t enable, int32_t* active);
+int nsb_multi_extract(nsb_multi* m, const int32_t* region, int32_t nreg, const nsb_trunc* trunc, const nsb_expand* expand, nsb_extract_info* info);
+int nsb_multi_update_eigsolve(nsb_multi* m, const nsb_krylov* params, double* eigval, nsb_solve_info* info);
+int nsb_multi_update_exp(nsb_multi* m, double t_re, double t_im, int32_t solver, const nsb_krylov* params, int32_t nsites, int32_t next_vertex,
+                         nsb_solve_info* info);
+int nsb_multi_insert(nsb_multi* m, const nsb_trunc* trunc, int32_t normalize, int32_t set_ortho, nsb_insert_info* info);
+int nsb_multi_matvec_device(nsb_multi* m, int32_t reps);
+int nsb_multi_local_download(nsb_multi* m, void* host);
+int nsb_multi_synchronize(nsb_multi* m);
+int nsb_local_sync(nsb_net* net);
+
 /* ---- fitting (src/fitting.jl) ----------------------------------------------------------------
  * Uploading a target tensor for every vertex switches the network to fitting mode: the ket layer of the
  * environments is the fixed target |x> (own link dimensions), the operator layer the uploaded operator (an identity
@@ -262,11 +301,26 @@ int nsb_factorize_host(nsb_ctx* ctx, int32_t dtype, int64_t rows, int64_t cols, 
 int nsb_eigh_host(nsb_ctx* ctx, int32_t dtype, int64_t n, const void* A, double* w, void* U);
 /* thin QR of a host matrix (rows x cols): Q (rows x k), R (k x cols), k = min(rows, cols). */
 int nsb_qr_host(nsb_ctx* ctx, int32_t dtype, int64_t rows, int64_t cols, const void* M, void* Q, void* R);
-/* blocked randomised range finder for a host matrix A (m x n): orthonormal Q (m x rank) with
- * rank <= max_rank + oversample (src/sketched_linear_algebra/range_finder.jl:6-64). */
-int nsb_range_finder_host(nsb_ctx* ctx, int32_t dtype, int64_t m, int64_t n, const void* A, int64_t max_rank,
-                          int32_t oversample, int32_t north_pass, double orthogonal_threshold, uint64_t seed,
-                          void* Q /* m*(max_rank+oversample) */, int64_t* rank_out);
+/* time `reps` device-resident thin QRs of a random rows x cols matrix (blocked compact-WY Householder); avg ms per QR */
+int nsb_qr_bench(nsb_ctx* ctx, int32_t dtype, int64_t rows, int64_t cols, int32_t reps, double* ms_out);
+/* Randomised range finder (src/sketched_linear_algebra/range_finder.jl:6-64), blocked: probes go through the linear map in
+ * panels, projection against the accepted vectors by GEMMs, the reference's per-vector acceptance rule (north_pass
+ * Gram-Schmidt passes, stop at the first residual below orthogonal_threshold; experimental `cutoff`: keep that vector, then
+ * stop) evaluated on the device with one host look per panel.  probes: caller-supplied domain vectors, column k = the k-th
+ * random_vector() (domain_size x min(max_rank + oversample, range, domain)), or NULL for Philox N(0,1) with `seed`.
+ * Q receives the orthonormal basis (range_size x rank).
+ *   nsb_range_finder_host: linear map = a host matrix A (m x n), uploaded once.
+ *   nsb_range_finder_heff: linear map = the projected operator at the current position (the closure
+ *                          psi -> optimal_map(P, psi) of src/eigsolve.jl:22); domain = range = the local tensor. */
+int nsb_range_finder_host(nsb_ctx* ctx, int32_t dtype, int64_t m, int64_t n, const void* A, const void* probes /* nullable */,
+                          int64_t max_rank, int32_t oversample, int32_t north_pass, double orthogonal_threshold, double cutoff,
+                          uint64_t seed, void* Q /* m*(max_rank+oversample) */, int64_t* rank_out);
+int nsb_range_finder_heff(nsb_net* net, const void* probes /* nullable */, uint64_t seed, int64_t max_rank, int32_t oversample,
+                          int32_t north_pass, double orthogonal_threshold, double cutoff, void* Q, int64_t* rank_out);
+/* One-shot random tensor for the next "ortho" subspace expansion (rows = basis size of the previous vertex, cols =
+ * expand_space(basis size), src/subspace/ortho_subspace.jl:4,56): replaces the device Philox draw, so that a host can
+ * reproduce random_itensor(basis_inds, ax) of its own generator. */
+int nsb_expand_set_probe(nsb_net* net, int64_t rows, int64_t cols, const void* host);
 
 /* EXPERIMENTAL (round-2 groundwork, not used by the hooks above; eigenvalues checked on a B200): band -> tridiagonal by bulge
  * chasing, stage 2 of a two-stage tridiagonalisation (csrc/sbr.cu, csrc/sbr_chase.h, tools/proto_sbr.py).  ab: lower band

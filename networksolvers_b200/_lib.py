@@ -85,12 +85,34 @@ SIGNATURES = {
     "nsb_timers_get": (C.c_int, [_vp, P(_dbl)]),
     "nsb_timers_reset": (C.c_int, [_vp]),
     "nsb_mem_info": (C.c_int, [_vp, P(_i64), P(_i64), P(_i64)]),
+    "nsb_gemm_profile_enable": (C.c_int, [_vp, _i32]),
+    "nsb_gemm_profile_read": (C.c_int, [_vp, _i64, P(_dbl), P(_dbl), P(_i64), P(_i64)]),
     "nsb_comm_unique_id": (C.c_int, [C.c_char_p]),
     "nsb_comm_init": (C.c_int, [_vp, C.c_char_p, C.c_int, C.c_int]),
     "nsb_comm_destroy": (C.c_int, [_vp]),
     "nsb_net_set_shard": (C.c_int, [_vp, _i32, P(_i32)]),
     "nsb_peer_window_create": (C.c_int, [_vp, _i64, C.c_char_p]),
     "nsb_peer_window_open": (C.c_int, [_vp, _i32, C.c_char_p]),
+    "nsb_multi_create": (C.c_int, [P(_i32), _i32, P(_vp)]),
+    "nsb_multi_destroy": (C.c_int, [_vp]),
+    "nsb_multi_last_error": (C.c_char_p, [_vp]),
+    "nsb_multi_ndev": (C.c_int, [_vp, P(_i32)]),
+    "nsb_multi_ctx": (C.c_int, [_vp, _i32, P(_vp)]),
+    "nsb_multi_net": (C.c_int, [_vp, _i32, P(_vp)]),
+    "nsb_multi_network_create": (C.c_int, [_vp, _i32, P(_i32), _i32, P(_i64), _i32]),
+    "nsb_multi_site_upload": (C.c_int, [_vp, _i32, _i32, P(_i32), P(_i64), _vp]),
+    "nsb_multi_mpo_upload": (C.c_int, [_vp, _i32, _i32, P(_i32), P(_i64), _vp]),
+    "nsb_multi_site_fill_random": (C.c_int, [_vp, _i32, _i32, P(_i32), P(_i64), C.c_uint64, _dbl]),
+    "nsb_multi_set_ortho_region": (C.c_int, [_vp, P(_i32), _i32]),
+    "nsb_multi_set_shard": (C.c_int, [_vp, _i32, P(_i32)]),
+    "nsb_multi_extract": (C.c_int, [_vp, P(_i32), _i32, P(Trunc), P(Expand), P(ExtractInfo)]),
+    "nsb_multi_update_eigsolve": (C.c_int, [_vp, P(Krylov), P(_dbl), P(SolveInfo)]),
+    "nsb_multi_update_exp": (C.c_int, [_vp, _dbl, _dbl, _i32, P(Krylov), _i32, _i32, P(SolveInfo)]),
+    "nsb_multi_insert": (C.c_int, [_vp, P(Trunc), _i32, _i32, P(InsertInfo)]),
+    "nsb_multi_matvec_device": (C.c_int, [_vp, _i32]),
+    "nsb_multi_local_download": (C.c_int, [_vp, _vp]),
+    "nsb_multi_synchronize": (C.c_int, [_vp]),
+    "nsb_local_sync": (C.c_int, [_vp]),
     "nsb_network_create": (C.c_int, [_vp, _i32, P(_i32), _i32, P(_i64), _i32, P(_vp)]),
     "nsb_network_destroy": (C.c_int, [_vp]),
     "nsb_site_upload": (C.c_int, [_vp, _i32, _i32, P(_i32), P(_i64), _vp]),
@@ -128,7 +150,10 @@ SIGNATURES = {
     "nsb_eigh_host": (C.c_int, [_vp, _i32, _i64, _vp, P(_dbl), _vp]),
     "nsb_factorize_host": (C.c_int, [_vp, _i32, _i64, _i64, _vp, P(Trunc), _vp, _vp, P(_dbl), P(InsertInfo)]),
     "nsb_qr_host": (C.c_int, [_vp, _i32, _i64, _i64, _vp, _vp, _vp]),
-    "nsb_range_finder_host": (C.c_int, [_vp, _i32, _i64, _i64, _vp, _i64, _i32, _i32, _dbl, C.c_uint64, _vp, P(_i64)]),
+    "nsb_qr_bench": (C.c_int, [_vp, _i32, _i64, _i64, _i32, P(_dbl)]),
+    "nsb_range_finder_host": (C.c_int, [_vp, _i32, _i64, _i64, _vp, _vp, _i64, _i32, _i32, _dbl, _dbl, C.c_uint64, _vp, P(_i64)]),
+    "nsb_range_finder_heff": (C.c_int, [_vp, _vp, C.c_uint64, _i64, _i32, _i32, _dbl, _dbl, _vp, P(_i64)]),
+    "nsb_expand_set_probe": (C.c_int, [_vp, _i64, _i64, _vp]),
     "nsb_sbr_chase_host": (C.c_int, [_vp, _i64, _i32, _vp, _i64, _vp, _vp, _i64]),
 }
 

@@ -5,6 +5,7 @@
 
 #include "net.h"
 #include "eigh.h"
+#include "rangefinder.h"
 #include <algorithm>
 
 namespace nsb {
@@ -73,7 +74,6 @@ PhaseTimer::~PhaseTimer() {
 
 using namespace nsb;
 
-namespace nsb { extern int g_sbr_staged; }   // csrc/sbr.cu (experimental)
 struct nsb_ctx { Ctx c; int refs = 0; bool destroyed = false; cudaEvent_t ev0 = nullptr, ev1 = nullptr; };
 struct nsb_net { NetBase* n; nsb_ctx* ctx; };
 
@@ -143,6 +143,7 @@ static void ctx_really_destroy(nsb_ctx* ctx) {
   if (ctx->c.nccl_comm) { try { nccl_api().CommDestroy((ncclComm_t)ctx->c.nccl_comm); } catch (...) {} ctx->c.nccl_comm = nullptr; }
   ctx->c.flush_big_cache();
   cudaStreamSynchronize(ctx->c.stream);
+  for (auto& g : ctx->c.gemm_prof) { cudaEventDestroy(g.e0); cudaEventDestroy(g.e1); }
   if (ctx->c.d_scratch) cudaFree(ctx->c.d_scratch);
   if (ctx->c.h_pinned) cudaFreeHost(ctx->c.h_pinned);
   cudaStreamDestroy(ctx->c.stream);
@@ -154,26 +155,28 @@ int nsb_ctx_set_option(nsb_ctx* ctx, const char* key, int64_t value) {
   NSB_TRY(&ctx->c)
   std::string k(key);
   if (k == "gemm_impl") { NSB_REQUIRE(value >= 0 && value <= 3, NSB_EINVAL, "gemm_impl must be 0..3"); ctx->c.gemm_impl = (int)value; }
-  else if (k == "jacobi_block_min_n") { NSB_REQUIRE(value >= 0, NSB_EINVAL, "jacobi_block_min_n must be >= 0"); g_jacobi_block_min_n = (int)value; }
-  else if (k == "jacobi_precondition") { g_jacobi_precondition = value != 0; }
+  else if (k == "jacobi_block_min_n") { NSB_REQUIRE(value >= 0, NSB_EINVAL, "jacobi_block_min_n must be >= 0"); ctx->c.opt.jacobi_block_min_n = (int)value; }
+  else if (k == "jacobi_precondition") { ctx->c.opt.jacobi_precondition = value != 0; }
   else if (k == "shard_fused") { ctx->c.shard_fused = value != 0; }
-  else if (k == "jacobi_pivot") { g_jacobi_pivot = value != 0; }
-  else if (k == "jacobi_inner_cap") { NSB_REQUIRE(value >= 1, NSB_EINVAL, "jacobi_inner_cap >= 1"); g_jacobi_inner_cap = (int)value; }
-  else if (k == "jacobi_precondition_min_n") { g_jacobi_precondition_min_n = (int)value; }
+  else if (k == "jacobi_pivot") { ctx->c.opt.jacobi_pivot = value != 0; }
+  else if (k == "jacobi_inner_cap") { NSB_REQUIRE(value >= 1, NSB_EINVAL, "jacobi_inner_cap >= 1"); ctx->c.opt.jacobi_inner_cap = (int)value; }
+  else if (k == "jacobi_precondition_min_n") { ctx->c.opt.jacobi_precondition_min_n = (int)value; }
   else if (k == "big_cache_gib") { NSB_REQUIRE(value >= 0, NSB_EINVAL, "big_cache_gib >= 0"); ctx->c.big_cache_cap = (size_t)value << 30; if (value == 0) ctx->c.flush_big_cache(); }
-  else if (k == "sbr_staged") { nsb::g_sbr_staged = value != 0; }
-  else if (k == "skip_identity") { g_skip_identity = value != 0; }
-  else if (k == "skip_identity_sharded") { g_skip_identity_sharded = value != 0; }
-  else if (k == "merge_site_ops") { g_merge_site_ops = value != 0; }
-  else if (k == "eigh_min_n") { g_eigh_min_n = (int)value; }
-  else if (k == "eigh_coop") { g_eigh_coop = value != 0; }
-  else if (k == "eigh_coop_ctas") { NSB_REQUIRE(value >= 1 && value <= 8, NSB_EINVAL, "eigh_coop_ctas 1..8"); g_eigh_coop_ctas = (int)value; }
-  else if (k == "eigh_direct_min_n") g_eigh_direct_min_n = (int)value;
-  else if (k == "eigh_sym") g_eigh_sym = value ? 1 : 0;
-  else if (k == "eigh_sym_tc") { NSB_REQUIRE(value == 0 || value == 16 || value == 32 || value == 64 || value == 128, NSB_EINVAL, "eigh_sym_tc must be 0, 16, 32, 64 or 128"); g_eigh_sym_tc = (int)value; }
-  else if (k == "eigh_split") { NSB_REQUIRE(value >= 1 && value <= 16, NSB_EINVAL, "eigh_split 1..16"); g_eigh_split = (int)value; }
-  else if (k == "eigh_wb") { NSB_REQUIRE(value >= 2 && value <= 256 && value % 2 == 0, NSB_EINVAL, "eigh_wb must be even, 2..256"); g_eigh_wb = (int)value; }
-  else if (k == "eigh_nb") { NSB_REQUIRE(value >= 2 && value <= 128 && value % 2 == 0, NSB_EINVAL, "eigh_nb must be even, 2..128"); g_eigh_nb = (int)value; }
+  else if (k == "sbr_staged") { ctx->c.opt.sbr_staged = value != 0; }
+  else if (k == "skip_identity") { ctx->c.opt.skip_identity = value != 0; }
+  else if (k == "skip_identity_sharded") { ctx->c.opt.skip_identity_sharded = value != 0; }
+  else if (k == "merge_site_ops") { ctx->c.opt.merge_site_ops = value != 0; }
+  else if (k == "eigh_min_n") { ctx->c.opt.eigh_min_n = (int)value; }
+  else if (k == "eigh_coop") { ctx->c.opt.eigh_coop = value != 0; }
+  else if (k == "eigh_coop_ctas") { NSB_REQUIRE(value >= 1 && value <= 8, NSB_EINVAL, "eigh_coop_ctas 1..8"); ctx->c.opt.eigh_coop_ctas = (int)value; }
+  else if (k == "eigh_direct_min_n") ctx->c.opt.eigh_direct_min_n = (int)value;
+  else if (k == "eigh_sym") ctx->c.opt.eigh_sym = value ? 1 : 0;
+  else if (k == "eigh_sym_tc") { NSB_REQUIRE(value == 0 || value == 16 || value == 32 || value == 64 || value == 128, NSB_EINVAL, "eigh_sym_tc must be 0, 16, 32, 64 or 128"); ctx->c.opt.eigh_sym_tc = (int)value; }
+  else if (k == "eigh_split") { NSB_REQUIRE(value >= 1 && value <= 16, NSB_EINVAL, "eigh_split 1..16"); ctx->c.opt.eigh_split = (int)value; }
+  else if (k == "eigh_wb") { NSB_REQUIRE(value >= 2 && value <= 256 && value % 2 == 0, NSB_EINVAL, "eigh_wb must be even, 2..256"); ctx->c.opt.eigh_wb = (int)value; }
+  else if (k == "eigh_nb") { NSB_REQUIRE(value >= 2 && value <= 128 && value % 2 == 0, NSB_EINVAL, "eigh_nb must be even, 2..128"); ctx->c.opt.eigh_nb = (int)value; }
+  else if (k == "qr_block_min") { NSB_REQUIRE(value >= 0, NSB_EINVAL, "qr_block_min >= 0"); ctx->c.opt.qr_block_min = (int)value; }
+  else if (k == "qn_block_sparse") { ctx->c.opt.qn_block_sparse = value != 0; }
   else throw Error(NSB_EINVAL, "unknown option " + k);
   NSB_CATCH(&ctx->c)
 }
@@ -217,6 +220,31 @@ int nsb_timers_get(nsb_ctx* ctx, double* ms_out) {
   return NSB_OK;
 }
 int nsb_timers_reset(nsb_ctx* ctx) { if (!ctx) return NSB_EINVAL; for (auto& t : ctx->c.timers_ms) t = 0; return NSB_OK; }
+int nsb_gemm_profile_enable(nsb_ctx* ctx, int32_t on) {
+  if (!ctx) return NSB_EINVAL;
+  NSB_TRY(&ctx->c)
+  ctx->c.sync();
+  for (auto& g : ctx->c.gemm_prof) { cudaEventDestroy(g.e0); cudaEventDestroy(g.e1); }
+  ctx->c.gemm_prof.clear();
+  ctx->c.gemm_profile = on != 0;
+  NSB_CATCH(&ctx->c)
+}
+int nsb_gemm_profile_read(nsb_ctx* ctx, int64_t cap, double* ms_out, double* flops_out, int64_t* mnkb_out, int64_t* count_out) {
+  if (!ctx || !count_out) return NSB_EINVAL;
+  NSB_TRY(&ctx->c)
+  ctx->c.sync();
+  const int64_t n = (int64_t)ctx->c.gemm_prof.size();
+  *count_out = n;
+  for (int64_t i = 0; i < n && i < cap; ++i) {
+    auto& g = ctx->c.gemm_prof[i];
+    float ms = 0.f;
+    NSB_CUDA(cudaEventElapsedTime(&ms, g.e0, g.e1));
+    if (ms_out) ms_out[i] = ms;
+    if (flops_out) flops_out[i] = g.flops;
+    if (mnkb_out) { mnkb_out[4 * i] = g.M; mnkb_out[4 * i + 1] = g.N; mnkb_out[4 * i + 2] = g.K; mnkb_out[4 * i + 3] = g.batch; }
+  }
+  NSB_CATCH(&ctx->c)
+}
 int nsb_mem_info(nsb_ctx* ctx, int64_t* free_bytes, int64_t* total_bytes, int64_t* pool_used_bytes) {
   if (!ctx) return NSB_EINVAL;
   NSB_TRY(&ctx->c)
@@ -380,6 +408,7 @@ int nsb_local_info(nsb_net* net, int32_t* rank, int32_t* legs, int64_t* dims) {
   NET_CALL(net, NSB_REQUIRE(rank, NSB_EINVAL, "null rank"); net->n->local_info(rank, legs, dims))
 }
 int nsb_local_download(nsb_net* net, void* host) { NET_CALL(net, NSB_REQUIRE(host, NSB_EINVAL, "null buffer"); net->n->local_download(host)) }
+int nsb_local_sync(nsb_net* net) { NET_CALL(net, net->n->local_sync()) }
 int nsb_local_upload(nsb_net* net, const void* host) { NET_CALL(net, NSB_REQUIRE(host, NSB_EINVAL, "null buffer"); net->n->local_upload(host)) }
 int nsb_matvec_host(nsb_net* net, const void* host_in, void* host_out) {
   NET_CALL(net, NSB_REQUIRE(host_in && host_out, NSB_EINVAL, "null buffer"); net->n->matvec_host(host_in, host_out))
@@ -567,54 +596,70 @@ extern "C" __attribute__((visibility("default"))) int nsb_qr_host(nsb_ctx* ctx, 
   NSB_CATCH(&ctx->c)
 }
 
-// Blocked randomised range finder: probes are drawn in panels of up to 32 vectors, Y = A * Omega by one GEMM,
-// then the reference's vector-at-a-time rule (north_pass Gram-Schmidt passes against all previous vectors,
-// stop at the first vector whose residual norm falls below orthogonal_threshold) is applied inside the panel.
 template <typename T>
-static int64_t range_finder_impl(Ctx* c, int64_t m, int64_t n, const void* A, int64_t max_rank, int oversample, int north_pass,
-                                 double thr, uint64_t seed, void* Qh) {
-  if (max_rank <= 0) return 0;
-  max_rank = std::min(max_rank, std::min(m, n));
-  int64_t sketch = std::min(max_rank + oversample, std::min(m, n));
-  DevBuf dA(c, sizeof(T) * m * n), dQ(c, sizeof(T) * m * sketch);
-  NSB_CUDA(cudaMemcpyAsync(dA.ptr, A, sizeof(T) * m * n, cudaMemcpyHostToDevice, c->stream));
-  T* Q = (T*)dQ.ptr;
-  int64_t have = 0;
-  const int64_t panel = 32;
-  DevBuf dOm(c, sizeof(T) * n * panel);
-  bool stop = false;
-  while (have < sketch && !stop) {
-    int64_t pb = std::min(panel, sketch - have);
-    fill_normal<T>(c, (T*)dOm.ptr, n * pb, seed + 7919 * (uint64_t)have, 1.0);
-    gemm<T>(c, OP_N, OP_N, m, pb, n, from_complex<T>(1.0, 0.0), (const T*)dA.ptr, m, 0, (const T*)dOm.ptr, n, 0, zero_<T>(),
-            Q + have * m, m, 0, 1);
-    for (int64_t j = 0; j < pb; ++j) {
-      T* q = Q + (have)*m;
-      for (int pass = 0; pass < north_pass; ++pass)
-        for (int64_t i = 0; i < have; ++i) {
-          double cr, ci;
-          vec_dot<T>(c, m, Q + i * m, q, &cr, &ci);
-          vec_axpy<T>(c, m, from_complex<T>(-cr, -ci), Q + i * m, q);
-        }
-      double nrm = vec_nrm2<T>(c, m, q);
-      if (nrm < thr) { stop = true; break; }
-      vec_scale<T>(c, m, from_complex<T>(1.0 / nrm, 0.0), q);
-      ++have;
-    }
+static double qr_bench_impl(Ctx* c, int64_t rows, int64_t cols, int reps) {
+  const int64_t k = std::min(rows, cols);
+  DevBuf dM(c, sizeof(T) * rows * cols), dW(c, sizeof(T) * rows * cols), dQ(c, sizeof(T) * rows * k), dR(c, sizeof(T) * k * cols);
+  fill_normal<T>(c, (T*)dM.ptr, rows * cols, 21, 1.0);
+  cudaEvent_t e0, e1;
+  NSB_CUDA(cudaEventCreate(&e0)); NSB_CUDA(cudaEventCreate(&e1));
+  double total = 0.0;
+  for (int i = 0; i < reps + 1; ++i) {
+    vec_copy<T>(c, rows * cols, (const T*)dM.ptr, (T*)dW.ptr);
+    NSB_CUDA(cudaEventRecord(e0, c->stream));
+    qr_thin<T>(c, (T*)dW.ptr, rows, cols, rows, (T*)dQ.ptr, rows, (T*)dR.ptr, k);
+    NSB_CUDA(cudaEventRecord(e1, c->stream));
+    NSB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    NSB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (i > 0) total += ms;
   }
-  NSB_CUDA(cudaMemcpyAsync(Qh, Q, sizeof(T) * m * have, cudaMemcpyDeviceToHost, c->stream));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return total / reps;
+}
+extern "C" __attribute__((visibility("default"))) int nsb_qr_bench(nsb_ctx* ctx, int32_t dtype, int64_t rows, int64_t cols, int32_t reps, double* ms_out) {
+  if (!ctx || !ms_out) return NSB_EINVAL;
+  NSB_TRY(&ctx->c)
+  NSB_CUDA(cudaSetDevice(ctx->c.device));
+  NSB_REQUIRE(rows > 0 && cols > 0 && reps > 0, NSB_EINVAL, "bad arguments");
+  *ms_out = dtype == NSB_F64 ? qr_bench_impl<double>(&ctx->c, rows, cols, reps) : qr_bench_impl<cdouble>(&ctx->c, rows, cols, reps);
+  NSB_CATCH(&ctx->c)
+}
+
+// Randomised range finder of a host matrix A (m x n): linear map = one GEMM per probe panel (rangefinder.cu).
+template <typename T>
+static int64_t range_finder_impl(Ctx* c, int64_t m, int64_t n, const void* A, const void* probes, int64_t max_rank, int oversample,
+                                 int north_pass, double thr, double cutoff, uint64_t seed, void* Qh) {
+  if (max_rank <= 0) return 0;
+  const int64_t sketch = std::min(std::min(max_rank, std::min(m, n)) + oversample, std::min(m, n));
+  DevBuf dA(c, sizeof(T) * m * n), dQ(c, sizeof(T) * m * std::max<int64_t>(sketch, 1)), dP(c, probes ? sizeof(T) * n * sketch : 0);
+  NSB_CUDA(cudaMemcpyAsync(dA.ptr, A, sizeof(T) * m * n, cudaMemcpyHostToDevice, c->stream));
+  if (probes) NSB_CUDA(cudaMemcpyAsync(dP.ptr, probes, sizeof(T) * n * sketch, cudaMemcpyHostToDevice, c->stream));
+  RangeMap<T> map = [&](const T* Om, T* Y, int64_t p) {
+    gemm<T>(c, OP_N, OP_N, m, p, n, from_complex<T>(1.0, 0.0), (const T*)dA.ptr, m, 0, Om, n, 0, zero_<T>(), Y, m, 0, 1);
+  };
+  const int64_t have = range_finder_blocked<T>(c, m, n, map, probes ? (const T*)dP.ptr : nullptr, seed, max_rank, oversample, north_pass, thr,
+                                               cutoff, (T*)dQ.ptr);
+  if (have > 0) NSB_CUDA(cudaMemcpyAsync(Qh, dQ.ptr, sizeof(T) * m * have, cudaMemcpyDeviceToHost, c->stream));
   c->sync();
   return have;
 }
-extern "C" __attribute__((visibility("default"))) int nsb_range_finder_host(nsb_ctx* ctx, int32_t dtype, int64_t m, int64_t n, const void* A, int64_t max_rank, int32_t oversample,
-                          int32_t north_pass, double orthogonal_threshold, uint64_t seed, void* Q, int64_t* rank_out) {
+extern "C" __attribute__((visibility("default"))) int nsb_range_finder_host(nsb_ctx* ctx, int32_t dtype, int64_t m, int64_t n, const void* A, const void* probes,
+                          int64_t max_rank, int32_t oversample, int32_t north_pass, double orthogonal_threshold, double cutoff, uint64_t seed,
+                          void* Q, int64_t* rank_out) {
   if (!ctx) return NSB_EINVAL;
   NSB_TRY(&ctx->c)
   NSB_CUDA(cudaSetDevice(ctx->c.device));
   NSB_REQUIRE(A && Q && rank_out && m > 0 && n > 0, NSB_EINVAL, "bad arguments");
-  *rank_out = dtype == NSB_F64 ? range_finder_impl<double>(&ctx->c, m, n, A, max_rank, oversample, north_pass, orthogonal_threshold, seed, Q)
-                               : range_finder_impl<cdouble>(&ctx->c, m, n, A, max_rank, oversample, north_pass, orthogonal_threshold, seed, Q);
+  *rank_out = dtype == NSB_F64 ? range_finder_impl<double>(&ctx->c, m, n, A, probes, max_rank, oversample, north_pass, orthogonal_threshold, cutoff, seed, Q)
+                               : range_finder_impl<cdouble>(&ctx->c, m, n, A, probes, max_rank, oversample, north_pass, orthogonal_threshold, cutoff, seed, Q);
   NSB_CATCH(&ctx->c)
 }
-
-
+extern "C" __attribute__((visibility("default"))) int nsb_range_finder_heff(nsb_net* net, const void* probes, uint64_t seed, int64_t max_rank, int32_t oversample,
+                          int32_t north_pass, double orthogonal_threshold, double cutoff, void* Q, int64_t* rank_out) {
+  NET_CALL(net, NSB_REQUIRE(Q && rank_out, NSB_EINVAL, "null argument");
+           *rank_out = net->n->range_finder_heff(probes, seed, max_rank, oversample, north_pass, orthogonal_threshold, cutoff, Q))
+}
+extern "C" __attribute__((visibility("default"))) int nsb_expand_set_probe(nsb_net* net, int64_t rows, int64_t cols, const void* host) {
+  NET_CALL(net, NSB_REQUIRE(host && rows > 0 && cols > 0, NSB_EINVAL, "bad arguments"); net->n->expand_set_probe(rows, cols, host))
+}

@@ -98,6 +98,34 @@ struct Ctx {
   std::string last_error;
   Counters cnt;
   int gemm_impl = 0;   // 0 = auto, 1 = naive, 2 = dmma cp.async, 3 = dmma TMA
+  // tuning / routing knobs of nsb_ctx_set_option: per context (two contexts of one process do not see each other's settings)
+  struct Options {
+    int skip_identity = 1;           // skip the identity channel of the first / last environment of an H_eff application
+    int skip_identity_sharded = 1;   // the same inside the multi-GPU (sharded) application
+    int merge_site_ops = 1;          // 2-site regions: apply W[a] W[b] as one small-operator pass
+    int eigh_min_n = 1024;           // factorize_left takes the Gram + eigh route from this size on (<= 0: never)
+    int eigh_direct_min_n = 96;      // same for the Hermitian (density-matrix) input of the expansion's `eigen`
+    int eigh_nb = 64;                // panel width of the tridiagonalisation (even, <= 128)
+    int eigh_coop = 1;               // tridiagonalisation panels as one cooperative kernel (2 grid barriers per column)
+    int eigh_coop_ctas = 3;          // CTAs per SM of the cooperative panel kernel
+    int eigh_sym = 1;                // real FP64, even n: symmetric (half-traffic) panel kernel
+    int eigh_sym_tc = 0;             // its column-block width (0: chosen per column from {64, 32, 16})
+    int eigh_split = 8;              // maximum number of row slabs of the split-K product Y = V^H U (back-transformation)
+    int eigh_wb = 128;               // reflectors per compact-WY block of the back-transformation
+    int jacobi_block_min_n = 48;     // column count from which the blocked (GEMM-rich) Jacobi is used
+    int jacobi_precondition = 1;     // QR-precondition the blocked Jacobi (Drmac-Veselic)
+    int jacobi_inner_cap = 1;        // inner sweeps per pair solve
+    int jacobi_pivot = 0;            // column pivoting in the preconditioning QR
+    int jacobi_precondition_min_n = 1024;
+    int sbr_staged = 0;              // experimental bulge-chasing kernel: shared-memory form of the task
+    int qr_block_min = 64;           // min(rows, cols) from which the blocked compact-WY Householder QR is used
+    int qn_block_sparse = 1;         // QN networks: block-sparse storage + grouped sector GEMMs (0: dense storage)
+  } opt;
+  // per-launch GEMM timing (nsb_gemm_profile_*): CUDA events recorded on the stream around every GEMM launch while enabled;
+  // resolved when read.  Feeds the roofline of bench.py from the launches of the timed region itself.
+  struct GemmProf { cudaEvent_t e0, e1; double flops; int64_t M, N, K, batch; };
+  bool gemm_profile = false;
+  std::vector<GemmProf> gemm_prof;
   // multi-GPU (optional): NCCL communicator + rank info, see shard.cu
   void* nccl_comm = nullptr;
   int rank = 0, nranks = 1;

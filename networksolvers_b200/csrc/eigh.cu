@@ -17,15 +17,6 @@
 
 namespace nsb {
 
-int g_eigh_min_n = 1024;
-int g_eigh_direct_min_n = 96;   // same for the Hermitian input of the expansion's `eigen` (no Gram squaring involved)
-int g_eigh_nb = 64;
-int g_eigh_coop = 1;    // tridiagonalisation panels as one cooperative kernel (2 grid barriers per column); 0: five launches per column
-int g_eigh_coop_ctas = 3;   // CTAs per SM of the cooperative panel kernel
-int g_eigh_sym = 1;     // real FP64, even n: symmetric (half-traffic) column-dot phase of the cooperative panel kernel
-int g_eigh_sym_tc = 0;  // column-block width of its work units (0: chosen per column from {64, 32, 16})
-int g_eigh_split = 8;  // maximum number of row slabs of the split-K product Y = V^H U in the back-transformation
-int g_eigh_wb = 128;   // reflectors per compact-WY block of the back-transformation (T factor in shared memory: <= 160 real, <= 96 complex)
 
 #define LAUNCH_CHECK(ctx) do { (ctx)->cnt.kernel_launches++; NSB_CUDA(cudaGetLastError()); } while (0)
 
@@ -1204,8 +1195,8 @@ __global__ void mirror_lower_kernel(T* __restrict__ A, int64_t lda, int64_t n) {
 }
 
 template <typename T>
-bool Eigh<T>::reads_lower_only(int64_t n, int64_t lda) {
-  return !ScalarTraits<T>::is_complex && g_eigh_coop && g_eigh_sym && n >= 4 && n % 2 == 0 && lda % 2 == 0 && n < (1ll << 30);
+bool Eigh<T>::reads_lower_only(const Ctx* ctx, int64_t n, int64_t lda) {
+  return !ScalarTraits<T>::is_complex && ctx->opt.eigh_coop && ctx->opt.eigh_sym && n >= 4 && n % 2 == 0 && lda % 2 == 0 && n < (1ll << 30);
 }
 
 template <typename T>
@@ -1213,7 +1204,7 @@ void Eigh<T>::factor(Ctx* c, T* A, int64_t n_, int64_t lda, bool lower_only_inpu
   ctx = c;
   n = n_;
   NSB_REQUIRE(n >= 1, NSB_EINVAL, "eigh: empty matrix");
-  const int nb = std::max(2, std::min(g_eigh_nb, MAXNB)) & ~1;
+  const int nb = std::max(2, std::min(ctx->opt.eigh_nb, MAXNB)) & ~1;
   const T one = from_complex<T>(1.0, 0.0), mone = from_complex<T>(-1.0, 0.0);
   Vall = DevBuf(ctx, sizeof(T) * (size_t)n * n);
   taus = DevBuf(ctx, sizeof(T) * n);
@@ -1235,11 +1226,11 @@ void Eigh<T>::factor(Ctx* c, T* A, int64_t n_, int64_t lda, bool lower_only_inpu
   // cooperative panel kernel: grid sized from the occupancy query so that every CTA is resident
   int coop_grid = 0;
   DevBuf part2;
-  if (g_eigh_coop) {
+  if (ctx->opt.eigh_coop) {
     int per_sm = 0, coop_ok = 0;
     NSB_CUDA(cudaDeviceGetAttribute(&coop_ok, cudaDevAttrCooperativeLaunch, ctx->device));
     NSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trd_panel_kernel<T, CPB>, 256, 0));
-    per_sm = std::min(per_sm, std::max(1, g_eigh_coop_ctas));
+    per_sm = std::min(per_sm, std::max(1, ctx->opt.eigh_coop_ctas));
     if (coop_ok && per_sm >= 1) {
       coop_grid = per_sm * ctx->num_sms;
       part = DevBuf(ctx, sizeof(double) * coop_grid);
@@ -1250,11 +1241,11 @@ void Eigh<T>::factor(Ctx* c, T* A, int64_t n_, int64_t lda, bool lower_only_inpu
   bool use_sym = false;
   DevBuf dotP, zP, pP, pack;
   if constexpr (!ScalarTraits<T>::is_complex) {
-    if (reads_lower_only(n, lda) && ((uintptr_t)A % 16) == 0 && ((uintptr_t)Vp0 % 16) == 0 && ((uintptr_t)Wp % 16) == 0) {
+    if (reads_lower_only(ctx, n, lda) && ((uintptr_t)A % 16) == 0 && ((uintptr_t)Vp0 % 16) == 0 && ((uintptr_t)Wp % 16) == 0) {
       int per_sm = 0, coop_ok = 0;
       NSB_CUDA(cudaDeviceGetAttribute(&coop_ok, cudaDevAttrCooperativeLaunch, ctx->device));
       NSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trd_panel_sym_kernel, 256, 0));
-      per_sm = std::min(per_sm, std::max(1, g_eigh_coop_ctas));
+      per_sm = std::min(per_sm, std::max(1, ctx->opt.eigh_coop_ctas));
       if (coop_ok && per_sm >= 1) {
         use_sym = true;
         coop_grid = per_sm * ctx->num_sms;
@@ -1280,7 +1271,7 @@ void Eigh<T>::factor(Ctx* c, T* A, int64_t n_, int64_t lda, bool lower_only_inpu
         pa.A = A; pa.lda = lda; pa.n = n; pa.p = p; pa.w = w; pa.Vp = Vp; pa.Wp = Wp; pa.ldp = n;
         pa.taus = dtau; pa.d = (double*)d_d.ptr; pa.e = (double*)e_d.ptr;
         pa.part = (double*)part.ptr; pa.part2 = (double*)part2.ptr;
-        pa.dotP = (double*)dotP.ptr; pa.zP = (double*)zP.ptr; pa.pP = (double*)pP.ptr; pa.force_tc = g_eigh_sym_tc;
+        pa.dotP = (double*)dotP.ptr; pa.zP = (double*)zP.ptr; pa.pP = (double*)pP.ptr; pa.force_tc = ctx->opt.eigh_sym_tc;
         void* kargs[] = {(void*)&pa};
         NSB_CUDA(cudaLaunchCooperativeKernel((void*)trd_panel_sym_kernel, dim3(coop_grid), dim3(256), kargs, 0, ctx->stream));
         ctx->cnt.kernel_launches++;
@@ -1347,7 +1338,7 @@ void Eigh<T>::vectors(const int32_t* idx_host, int64_t k, T* U, int64_t ldu) {
   if (k <= 0) return;
   // block width of the back-transformation: independent of the tridiagonalisation panels (any run of consecutive
   // reflectors has a compact-WY form); wide blocks make the three GEMMs per block efficient
-  const int nb = std::max(2, std::min(g_eigh_wb, ScalarTraits<T>::is_complex ? 96 : 160)) & ~1;   // T (nb x nb) must fit in shared memory
+  const int nb = std::max(2, std::min(ctx->opt.eigh_wb, ScalarTraits<T>::is_complex ? 96 : 160)) & ~1;   // T (nb x nb) must fit in shared memory
   const T one = from_complex<T>(1.0, 0.0), mone = from_complex<T>(-1.0, 0.0), zero = zero_<T>();
   DevBuf idx(ctx, sizeof(int32_t) * k);
   NSB_CUDA(cudaMemcpyAsync(idx.ptr, idx_host, sizeof(int32_t) * k, cudaMemcpyHostToDevice, ctx->stream));
@@ -1370,7 +1361,7 @@ void Eigh<T>::vectors(const int32_t* idx_host, int64_t k, T* U, int64_t ldu) {
   // split the rows into `split` slabs (one strided batch), stack the partial products and let the T-factor GEMM sum
   // them ([T T .. T] x stack), so that all SMs work on it.
   const int64_t tiles_y = ((nb + 127) / 128) * ((k + (ScalarTraits<T>::is_complex ? 63 : 127)) / (ScalarTraits<T>::is_complex ? 64 : 128));
-  const int split = (int)std::max<int64_t>(1, std::min<int64_t>(std::max(1, g_eigh_split), (int64_t)ctx->num_sms / std::max<int64_t>(tiles_y, 1)));
+  const int split = (int)std::max<int64_t>(1, std::min<int64_t>(std::max(1, ctx->opt.eigh_split), (int64_t)ctx->num_sms / std::max<int64_t>(tiles_y, 1)));
   DevBuf Sall(ctx, sizeof(T) * (size_t)nb * nb * nblocks), Tall(ctx, sizeof(T) * (size_t)nb * nb * split * nblocks);
   DevBuf Y(ctx, sizeof(T) * (size_t)nb * split * k), Y2(ctx, sizeof(T) * (size_t)nb * k);
   const size_t larft_smem = sizeof(T) * ((size_t)nb * nb + nb);

@@ -10,15 +10,6 @@
 
 namespace nsb {
 
-extern int g_eigh_direct_min_n;   // threshold for a Hermitian (density-matrix) input, see linalg.cu
-extern int g_eigh_min_n;   // factorize_left takes the Gram + eigh route from this size on (<= 0: never)
-extern int g_eigh_coop;    // 1: one cooperative kernel per tridiagonalisation panel; 0: five launches per column
-extern int g_eigh_coop_ctas;
-extern int g_eigh_sym;     // symmetric (half-traffic) panel kernel for real FP64 with even n
-extern int g_eigh_sym_tc;  // its column-block width (0 = per-column choice)
-extern int g_eigh_split;   // row slabs (split-K) of Y = V^H U in the back-transformation, upper bound
-extern int g_eigh_wb;      // reflectors per compact-WY block of the back-transformation (even, <= 256)
-extern int g_eigh_nb;      // panel width of the tridiagonalisation / back-transformation (even, <= 128)
 
 template <typename T>
 struct Eigh {
@@ -33,7 +24,7 @@ struct Eigh {
   void factor(Ctx* ctx, T* A, int64_t n, int64_t lda, bool lower_only_input = false);
   // True when factor() will take the symmetric panel kernel for this problem, i.e. a caller that builds A by a GEMM
   // may skip the strictly upper output tiles (GEMM_LOWER_ONLY).
-  static bool reads_lower_only(int64_t n, int64_t lda);
+  static bool reads_lower_only(const Ctx* ctx, int64_t n, int64_t lda);
   // U (n x k, ldu) = Q Z[:, idx[0..k)]: eigenvectors of the original matrix for the chosen eigenvalues.
   void vectors(const int32_t* idx_host, int64_t k, T* U, int64_t ldu);
 };

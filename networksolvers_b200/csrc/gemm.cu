@@ -658,7 +658,20 @@ void gemm(Ctx* ctx, int opa, int opb, int64_t M, int64_t N, int64_t K, T alpha, 
     for (int64_t tm = 0; tm < p.tiles_m; ++tm) kept += std::min<int64_t>(p.tiles_n, (tm * Cfg::BM + Cfg::BM - 1) / Cfg::BN + 1);
     frac = (double)kept / (double)(p.tiles_m * p.tiles_n);
   }
-  ctx->cnt.gemm_flops += frac * (ScalarTraits<T>::is_complex ? 8.0 : 2.0) * (double)M * (double)N * (double)K * (double)batch;
+  const double flops_issued = frac * (ScalarTraits<T>::is_complex ? 8.0 : 2.0) * (double)M * (double)N * (double)K * (double)batch;
+  ctx->cnt.gemm_flops += flops_issued;
+  struct ProfScope {   // events around this launch (all return paths)
+    Ctx* c; size_t idx; bool on;
+    ProfScope(Ctx* c_, double fl, int64_t M_, int64_t N_, int64_t K_, int64_t b_) : c(c_), idx(0), on(c_->gemm_profile && c_->gemm_prof.size() < 65536) {
+      if (!on) return;
+      Ctx::GemmProf g; g.flops = fl; g.M = M_; g.N = N_; g.K = K_; g.batch = b_;
+      cudaEventCreate(&g.e0); cudaEventCreate(&g.e1);
+      cudaEventRecord(g.e0, c->stream);
+      idx = c->gemm_prof.size();
+      c->gemm_prof.push_back(g);
+    }
+    ~ProfScope() { if (on) cudaEventRecord(c->gemm_prof[idx].e1, c->stream); }
+  } prof_scope(ctx, flops_issued, M, N, K, batch);
 
   if (impl == GEMM_NAIVE) {
     NSB_REQUIRE(batch <= 65535 && (N + 15) / 16 <= 65535, NSB_EINVAL, "gemm naive: grid too large");

@@ -133,11 +133,255 @@ __global__ void extract_r_kernel(const T* __restrict__ A, int64_t lda, int64_t k
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Blocked Householder QR in compact-WY form (K8: gauge moves, 1-site TDVP split, tall factorisations).
+//   panel (QR_NB columns): ONE launch per column -- CTA b of the launch re-derives the reflector scalars from the raw
+//     column j (kept unmodified in A: the strictly lower part of a factored column is dead storage, R's diagonal goes to
+//     `rdiag`), then
+//       b <  i : Gram entry S[b, i] = v_b^H v_i for the T factor,
+//       b == i : writes v_i (explicit unit diagonal, zeros above) into V and tau_i, rdiag_j,
+//       b >  i : applies H_i^H to panel column p + b;
+//   T factor from S by one CTA (larft recurrence); trailing update A2 <- (I - V T^H V^H) A2 and the formation of
+//   Q = H_1 .. H_k [I; 0] (blocks descending) as DMMA GEMMs, with Y = V^H C as a split-K batch whose slabs are summed by the
+//   T-factor GEMM ([T T .. T] x stack), exactly as the back-transformation of eigh.cu.
+// ------------------------------------------------------------------------------------------------
+constexpr int QR_NB = 64;
+
+// block-wide sum for up to 32 warps (block_sum above assumes <= 8); result valid in all threads
+template <int NV>
+__device__ __forceinline__ void block_sum32(double (&v)[NV], double* sh /* >= NV * 33 */) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = warp_sum_d(v[i]);
+  __syncthreads();
+  if (lane == 0)
+#pragma unroll
+    for (int i = 0; i < NV; ++i) sh[i * 33 + w] = v[i];
+  __syncthreads();
+  if (w == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      double x = lane < nw ? sh[i * 33 + lane] : 0.0;
+      x = warp_sum_d(x);
+      if (lane == 0) sh[i * 33 + 32] = x;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = sh[i * 33 + 32];
+}
+
+// ITEMS: rows per thread held in registers (column j and the CTA's own column are read once; rows beyond ITEMS * blockDim are
+// streamed a second time).
+template <typename T, int ITEMS>
+__global__ void __launch_bounds__(512) qr_panel_col_kernel(T* __restrict__ A, int64_t lda, int64_t rows, int64_t cols, int64_t p, int i,
+                                                           int w, T* __restrict__ V, int64_t ldv, T* __restrict__ tau,
+                                                           T* __restrict__ rdiag, T* __restrict__ S /* QR_NB x QR_NB */) {
+  __shared__ double sh[3 * 33];
+  const int b = blockIdx.x;
+  const int64_t j = p + i;
+  const T* cj = A + j * lda;
+  const int64_t c = p + b;
+  // second operand of this CTA: b < i: the finished reflector v_b; b > i: panel column p + b; b == i: none
+  const T* other = (b < i) ? (V + (p + b) * ldv) : ((b > i && c < cols) ? (A + c * lda) : nullptr);
+  const int64_t r0 = j + 1 + threadIdx.x, stride = blockDim.x;
+  T a[ITEMS], x[ITEMS];
+  double s[3] = {0.0, 0.0, 0.0};    // sum |a|^2, sum conj(a) x (re, im)
+#pragma unroll
+  for (int k = 0; k < ITEMS; ++k) {
+    const int64_t r = r0 + (int64_t)k * stride;
+    a[k] = (r < rows) ? cj[r] : zero_<T>();
+    x[k] = (r < rows && other) ? other[r] : zero_<T>();
+  }
+#pragma unroll
+  for (int k = 0; k < ITEMS; ++k) {
+    s[0] += abs2_(a[k]);
+    s[1] += re(a[k]) * re(x[k]) + im(a[k]) * im(x[k]);
+    s[2] += re(a[k]) * im(x[k]) - im(a[k]) * re(x[k]);
+  }
+  for (int64_t r = r0 + (int64_t)ITEMS * stride; r < rows; r += stride) {   // tall matrices: streamed remainder
+    const T ar_ = cj[r];
+    const T xr_ = other ? other[r] : zero_<T>();
+    s[0] += abs2_(ar_);
+    s[1] += re(ar_) * re(xr_) + im(ar_) * im(xr_);
+    s[2] += re(ar_) * im(xr_) - im(ar_) * re(xr_);
+  }
+  block_sum32<3>(s, sh);
+  const T alpha = cj[j];
+  const double sigma = s[0], ar = re(alpha), ai = im(alpha);
+  T t = zero_<T>(), scale = zero_<T>();
+  double beta = ar;
+  const bool trivial = (sigma == 0.0 && ai == 0.0);
+  if (!trivial) {
+    beta = -copysign(sqrt(ar * ar + ai * ai + sigma), ar);
+    t = from_complex<T>((beta - ar) / beta, -ai / beta);
+    const double dr = ar - beta, di = ai, den = dr * dr + di * di;
+    scale = from_complex<T>(dr / den, -di / den);
+  }
+  if (b == i) {
+    T* vj = V + j * ldv;
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+      const int64_t r = r0 + (int64_t)k * stride;
+      if (r < rows) vj[r] = mul_(scale, a[k]);
+    }
+    for (int64_t r = r0 + (int64_t)ITEMS * stride; r < rows; r += stride) vj[r] = mul_(scale, cj[r]);
+    if (threadIdx.x == 0) {
+      vj[j] = from_complex<T>(1.0, 0.0);
+      tau[j] = t;
+      rdiag[j] = trivial ? alpha : from_complex<T>(beta, 0.0);
+      S[i + i * QR_NB] = from_complex<T>(1.0, 0.0);
+    }
+    return;
+  }
+  // sum conj(v) x over the rows below j with v = scale * a:  conj(scale) * (s[1] + i s[2])
+  const T cs = mul_(conj_(scale), from_complex<T>(s[1], s[2]));
+  if (b < i) {   // S[b, i] = v_b^H v_i = conj(v_b[j]) + sum_r conj(v_b[r]) v_i[r] = conj(v_b[j]) + conj(sum_r conj(v_i[r]) v_b[r])
+    if (threadIdx.x == 0) {
+      const T y = other[j];
+      S[b + i * QR_NB] = add_(conj_(y), conj_(cs));
+    }
+    return;
+  }
+  if (!other || trivial) return;
+  T* cc = A + c * lda;
+  const T xj = cc[j];
+  const T dot = add_(xj, cs);                                            // v^H x  (v_j = 1)
+  const T f = mul_(conj_(t), dot);                                       // H^H x = x - conj(tau) (v^H x) v
+  const T mf = from_complex<T>(-re(f), -im(f));
+  const T mfs = mul_(mf, scale);
+#pragma unroll
+  for (int k = 0; k < ITEMS; ++k) {
+    const int64_t r = r0 + (int64_t)k * stride;
+    if (r < rows) { T xv = x[k]; fma_(xv, mfs, a[k]); cc[r] = xv; }
+  }
+  for (int64_t r = r0 + (int64_t)ITEMS * stride; r < rows; r += stride) { T xv = cc[r]; fma_(xv, mfs, cj[r]); cc[r] = xv; }
+  if (threadIdx.x == 0) cc[j] = add_(xj, mf);
+}
+
+template <typename T> struct QrItems;
+template <> struct QrItems<double> { static constexpr int N = 16; };
+template <> struct QrItems<cdouble> { static constexpr int N = 8; };
+
+// T factor of one panel from its Gram matrix (upper triangle of S) and tau; written `reps` times side by side as T (Tst) and
+// as T^H (THst), both with leading dimension QR_NB.
+template <typename T>
+__global__ void __launch_bounds__(256) qr_larft_kernel(const T* __restrict__ S, const T* __restrict__ tau, int w, T* __restrict__ Tst,
+                                                       T* __restrict__ THst, int reps) {
+  extern __shared__ __align__(16) char qr_larft_sm[];
+  T* Ts = reinterpret_cast<T*>(qr_larft_sm);
+  T* sc = Ts + QR_NB * QR_NB;
+  for (int e = threadIdx.x; e < w * w; e += blockDim.x) Ts[e] = zero_<T>();
+  __syncthreads();
+  for (int i = 0; i < w; ++i) {
+    for (int k = threadIdx.x; k < i; k += blockDim.x) sc[k] = S[k + (size_t)i * QR_NB];
+    __syncthreads();
+    const T ti = tau[i];
+    const T mti = from_complex<T>(-re(ti), -im(ti));
+    for (int r = threadIdx.x; r <= i; r += blockDim.x) {
+      if (r < i) {
+        T acc = zero_<T>();
+        for (int k = r; k < i; ++k) fma_(acc, Ts[r + k * w], sc[k]);
+        Ts[r + i * w] = mul_(mti, acc);
+      } else {
+        Ts[i + i * w] = ti;
+      }
+    }
+    __syncthreads();
+  }
+  for (int e = threadIdx.x; e < w * w * reps; e += blockDim.x) {
+    const int sidx = e / (w * w), rc = e - sidx * (w * w), r = rc % w, c = rc / w;
+    Tst[r + ((size_t)sidx * w + c) * QR_NB] = Ts[rc];
+    THst[c + ((size_t)sidx * w + r) * QR_NB] = conj_(Ts[rc]);
+  }
+}
+
+template <typename T>
+__global__ void extract_r_diag_kernel(const T* __restrict__ A, int64_t lda, const T* __restrict__ rdiag, int64_t k, int64_t cols,
+                                      T* __restrict__ R, int64_t ldr) {
+  const int64_t total = k * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i % k, c = i / k;
+    R[r + c * ldr] = (r < c) ? A[r + c * lda] : (r == c ? rdiag[r] : zero_<T>());
+  }
+}
+
+// C (mp x nc, ldc) <- (I - V Tm V^H) C with Tm given as `split` side-by-side copies (T for Q, T^H for Q^H); V: mp x w (ldv)
+template <typename T>
+static void apply_block_reflector(Ctx* ctx, const T* V, int64_t ldv, int64_t mp, int w, const T* Tstack, int split, T* Cm, int64_t ldc,
+                                  int64_t nc, T* Y, T* Y2) {
+  if (nc <= 0 || mp <= 0) return;
+  const T one = from_complex<T>(1.0, 0.0), mone = from_complex<T>(-1.0, 0.0), zero = zero_<T>();
+  int64_t sb = std::min<int64_t>(split, std::max<int64_t>(1, mp / 256));   // slabs of at least 256 rows
+  int64_t kc = (((mp + sb - 1) / sb) + 15) / 16 * 16;
+  const int64_t nf = mp / kc, rem = mp - nf * kc, st = nf + (rem > 0 ? 1 : 0);
+  const int64_t ldy = st * w;
+  if (nf > 0) gemm<T>(ctx, OP_C, OP_N, w, nc, kc, one, V, ldv, kc, Cm, ldc, kc, zero, Y, ldy, w, nf);
+  if (rem > 0) gemm<T>(ctx, OP_C, OP_N, w, nc, rem, one, V + nf * kc, ldv, 0, Cm + nf * kc, ldc, 0, zero, Y + nf * w, ldy, 0, 1);
+  gemm<T>(ctx, OP_N, OP_N, w, nc, st * w, one, Tstack, QR_NB, 0, Y, ldy, 0, zero, Y2, w, 0, 1);
+  gemm<T>(ctx, OP_N, OP_N, mp, nc, w, mone, V, ldv, 0, Y2, w, 0, one, Cm, ldc, 0, 1);
+}
+
+template <typename T>
+static void qr_thin_blocked(Ctx* ctx, T* A, int64_t rows, int64_t cols, int64_t lda, T* Q, int64_t ldq, T* R, int64_t ldr) {
+  const int64_t k = std::min(rows, cols);
+  const int64_t npanels = (k + QR_NB - 1) / QR_NB;
+  const int split = 8;
+  DevBuf Vb(ctx, sizeof(T) * (size_t)rows * k), taub(ctx, sizeof(T) * k), rdb(ctx, sizeof(T) * k);
+  DevBuf Sb(ctx, sizeof(T) * QR_NB * QR_NB), Tall(ctx, sizeof(T) * (size_t)QR_NB * QR_NB * split * npanels),
+      THb(ctx, sizeof(T) * (size_t)QR_NB * QR_NB * split);
+  const int64_t ncmax = std::max(cols, k);
+  DevBuf Y(ctx, sizeof(T) * (size_t)QR_NB * split * ncmax), Y2(ctx, sizeof(T) * (size_t)QR_NB * ncmax);
+  T* V = (T*)Vb.ptr;
+  T* tau = (T*)taub.ptr;
+  NSB_CUDA(cudaMemsetAsync(V, 0, sizeof(T) * (size_t)rows * k, ctx->stream));
+  const int threads = rows >= 2048 ? 512 : 256;
+  const size_t larft_smem = sizeof(T) * (QR_NB * QR_NB + QR_NB);
+  {
+    static bool configured[2] = {false, false};
+    bool& c = configured[ScalarTraits<T>::is_complex ? 1 : 0];
+    if (!c) { NSB_CUDA(cudaFuncSetAttribute(qr_larft_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)larft_smem)); c = true; }
+  }
+  for (int64_t pi = 0; pi < npanels; ++pi) {
+    const int64_t p = pi * QR_NB;
+    const int w = (int)std::min<int64_t>(QR_NB, k - p);
+    NSB_CUDA(cudaMemsetAsync(Sb.ptr, 0, sizeof(T) * QR_NB * QR_NB, ctx->stream));
+    for (int i = 0; i < w; ++i) {
+      qr_panel_col_kernel<T, QrItems<T>::N><<<w, threads, 0, ctx->stream>>>(A, lda, rows, cols, p, i, w, V, rows, tau, (T*)rdb.ptr, (T*)Sb.ptr);
+      LAUNCH_CHECK(ctx);
+    }
+    T* Tp = (T*)Tall.ptr + (size_t)pi * QR_NB * QR_NB * split;
+    qr_larft_kernel<T><<<1, 256, larft_smem, ctx->stream>>>((const T*)Sb.ptr, tau + p, w, Tp, (T*)THb.ptr, split);
+    LAUNCH_CHECK(ctx);
+    const int64_t nc = cols - (p + w);
+    if (nc > 0)   // A[p:, p+w:] <- Q_p^H A[p:, p+w:]
+      apply_block_reflector<T>(ctx, V + p + p * rows, rows, rows - p, w, (const T*)THb.ptr, split, A + p + (p + w) * lda, lda, nc,
+                               (T*)Y.ptr, (T*)Y2.ptr);
+  }
+  {
+    const int64_t total = k * cols;
+    const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)ctx->num_sms * 8);
+    extract_r_diag_kernel<T><<<grid, 256, 0, ctx->stream>>>(A, lda, (const T*)rdb.ptr, k, cols, R, ldr);
+    LAUNCH_CHECK(ctx);
+  }
+  set_identity<T>(ctx, Q, rows, k, ldq);
+  for (int64_t pi = npanels - 1; pi >= 0; --pi) {
+    const int64_t p = pi * QR_NB;
+    const int w = (int)std::min<int64_t>(QR_NB, k - p);
+    const T* Tp = (const T*)Tall.ptr + (size_t)pi * QR_NB * QR_NB * split;
+    apply_block_reflector<T>(ctx, V + p + p * rows, rows, rows - p, w, Tp, split, Q + p + p * ldq, ldq, k - p, (T*)Y.ptr, (T*)Y2.ptr);
+  }
+}
+
 template <typename T>
 void qr_thin(Ctx* ctx, T* A, int64_t rows, int64_t cols, int64_t lda, T* Q, int64_t ldq, T* R, int64_t ldr) {
   int64_t k = std::min(rows, cols);
   if (k == 0) return;
   ctx->cnt.qr_calls++;
+  if (ctx->opt.qr_block_min > 0 && k >= ctx->opt.qr_block_min && rows >= 2 * QR_NB) {
+    qr_thin_blocked<T>(ctx, A, rows, cols, lda, Q, ldq, R, ldr);
+    return;
+  }
   DevBuf tau(ctx, sizeof(T) * k);
   T* dtau = (T*)tau.ptr;
   int maxgrid = ctx->num_sms * 4;
@@ -531,11 +775,6 @@ __global__ void block_gather_kernel(const T* __restrict__ src, T* __restrict__ d
   }
 }
 
-int g_jacobi_block_min_n = 48;        // below this the unblocked kernel is used
-int g_jacobi_precondition = 1;
-int g_jacobi_inner_cap = 1;   // inner sweeps per pair solve; the outer iteration finishes the job (measured optimum)
-int g_jacobi_pivot = 0;       // column pivoting in the preconditioning QR (measured: same sweep count, more launches)
-int g_jacobi_precondition_min_n = 1024;   // QR preconditioning pays off only once the sweep count matters
 
 template <typename T>
 static int jacobi_blocked(Ctx* ctx, T* G, int64_t m, int64_t n, T* V, int64_t nv) {
@@ -592,7 +831,7 @@ static int jacobi_blocked(Ctx* ctx, T* G, int64_t m, int64_t n, T* V, int64_t nv
     NSB_CUDA(cudaMemsetAsync(dmax, 0, 2 * sizeof(unsigned long long), ctx->stream));
     for (int64_t r = 0; r < rounds; ++r) {
       gemm<T>(ctx, OP_C, OP_N, N2, N2, m, one, ga, m, m * N2, ga, m, m * N2, zero, (T*)Sb.ptr, N2, (int64_t)N2 * N2, npairs);
-      kern<<<(unsigned)npairs, 1024, smem, ctx->stream>>>((const T*)Sb.ptr, (T*)Rb.ptr, dmax, abs_floor, tol, g_jacobi_inner_cap, nullptr, 0);
+      kern<<<(unsigned)npairs, 1024, smem, ctx->stream>>>((const T*)Sb.ptr, (T*)Rb.ptr, dmax, abs_floor, tol, ctx->opt.jacobi_inner_cap, nullptr, 0);
       LAUNCH_CHECK(ctx);
       gemm<T>(ctx, OP_N, OP_N, m, N2, N2, one, ga, m, m * N2, (const T*)Rb.ptr, N2, (int64_t)N2 * N2, zero, gb, m, m * N2, npairs);
       gemm<T>(ctx, OP_N, OP_N, nv, N2, N2, one, va, nv, nv * N2, (const T*)Rb.ptr, N2, (int64_t)N2 * N2, zero, vb, nv, nv * N2, npairs);
@@ -634,9 +873,9 @@ static int jacobi_blocked(Ctx* ctx, T* G, int64_t m, int64_t n, T* V, int64_t nv
 template <typename T>
 static FactorInfo factorize_left_eigh(Ctx* ctx, const T* M, int64_t rows, int64_t cols, int64_t ld, bool trans_in, double cutoff,
                                       int64_t mindim, int64_t maxdim, bool sqrt_spectrum, DevBuf& U, DevBuf& C,
-                                      std::vector<double>& spectrum) {
+                                      std::vector<double>& spectrum, const FactorDist* dist) {
   FactorInfo info;
-  info.decomp = (cutoff <= 1e-12) ? 1 : 2;
+  info.decomp = 2;   // the density-matrix `eigen` route (whatever label the reference's cutoff rule gives; 3 = refined, below)
   const int64_t n = rows;
   const T one = from_complex<T>(1.0, 0.0), zero = zero_<T>();
   // sqrt_spectrum with a square input: M is itself the Hermitian PSD density matrix of `eigen(rho; ...)`
@@ -646,8 +885,17 @@ static FactorInfo factorize_left_eigh(Ctx* ctx, const T* M, int64_t rows, int64_
   {
     DevBuf rho(ctx, sizeof(T) * (size_t)n * n);
     // the Gram matrix only needs its lower triangle when the symmetric tridiagonalisation kernel will read it
-    const bool lower = !direct && Eigh<T>::reads_lower_only(n, n) && ctx->gemm_impl != GEMM_NAIVE;
-    if (direct) {
+    const bool refine = !direct && !sqrt_spectrum && cutoff > 0.0 && cutoff <= 1e-12;
+    const int G = (dist && !direct && !refine) ? dist->nranks : 1;
+    const bool gram_split = G > 1 && n % G == 0 && n / G >= 128;
+    if (!(G > 1)) dist = nullptr;
+    const bool lower = !direct && !gram_split && Eigh<T>::reads_lower_only(ctx, n, n) && ctx->gemm_impl != GEMM_NAIVE;
+    if (gram_split) {   // rho[:, slab] by its owner, all-gather completes the (full) matrix
+      const int64_t nc = n / G, c0 = nc * dist->rank;
+      if (!trans_in) gemm<T>(ctx, OP_N, OP_C, n, nc, cols, one, M, ld, 0, M + c0, ld, 0, zero, (T*)rho.ptr + c0 * n, n, 0, 1);
+      else gemm<T>(ctx, OP_T, OP_CONJ, n, nc, cols, one, M, ld, 0, M + c0 * ld, ld, 0, zero, (T*)rho.ptr + c0 * n, n, 0, 1);
+      dist->allgather_inplace(rho.ptr, sizeof(T) * (size_t)n * nc);
+    } else if (direct) {
       if (!trans_in) copy_block<T>(ctx, M, ld, (T*)rho.ptr, n, n, n);
       else transpose_conj<T>(ctx, M, cols, rows, ld, (T*)rho.ptr, n, false);
     } else if (!trans_in) {
@@ -665,11 +913,69 @@ static FactorInfo factorize_left_eigh(Ctx* ctx, const T* M, int64_t rows, int64_
     const double lam = eg.w[order[i]];
     spectrum[i] = (sqrt_spectrum && !direct) ? std::sqrt(std::max(lam, 0.0)) : lam;
   }
+  if (!direct && !sqrt_spectrum && cutoff > 0.0 && cutoff <= 1e-12) {
+    // The reference takes LAPACK SVD for cutoff <= 1e-12 (App. A.4) because the eigenvalues of rho carry an absolute error of
+    // eps * lambda_1, which is the size of the weights such a cutoff decides on.  Refinement: all eigenvectors, G = M^H U; the
+    // squared column norms of G are the Rayleigh quotients u_i^H rho u_i = |u_i^H M|^2, computed from M itself -- their error
+    // is quadratic in the eigenvector error (which only mixes states of nearly equal weight), so the truncation rule sees
+    // every sigma_i^2 with relative accuracy.  U = kept columns, C = (kept columns of G)^H.
+    info.decomp = 3;
+    DevBuf Uall(ctx, sizeof(T) * (size_t)n * n), G(ctx, sizeof(T) * (size_t)cols * n), nrm(ctx, sizeof(double) * n);
+    eg.vectors(order.data(), n, (T*)Uall.ptr, n);
+    if (!trans_in) gemm<T>(ctx, OP_C, OP_N, cols, n, rows, one, M, ld, 0, (const T*)Uall.ptr, n, 0, zero, (T*)G.ptr, cols, 0, 1);
+    else gemm<T>(ctx, OP_CONJ, OP_N, cols, n, rows, one, M, ld, 0, (const T*)Uall.ptr, n, 0, zero, (T*)G.ptr, cols, 0, 1);
+    col_norms2<T>(ctx, (const T*)G.ptr, cols, n, cols, (double*)nrm.ptr);
+    std::vector<double> P(n);
+    NSB_CUDA(cudaMemcpyAsync(P.data(), nrm.ptr, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->sync();
+    std::vector<int32_t> o2(n);
+    std::iota(o2.begin(), o2.end(), 0);
+    std::stable_sort(o2.begin(), o2.end(), [&](int32_t a, int32_t b) { return P[a] > P[b]; });
+    for (int64_t i = 0; i < n; ++i) spectrum[i] = P[o2[i]];
+    double terr2 = 0.0;
+    const int64_t nk = truncate_spectrum(spectrum, cutoff, mindim, maxdim, &terr2);
+    info.newdim = nk;
+    info.truncerr = terr2;
+    DevBuf idx(ctx, sizeof(int32_t) * nk), tmp(ctx, sizeof(T) * (size_t)cols * nk);
+    NSB_CUDA(cudaMemcpyAsync(idx.ptr, o2.data(), sizeof(int32_t) * nk, cudaMemcpyHostToDevice, ctx->stream));
+    U = DevBuf(ctx, sizeof(T) * rows * nk);
+    C = DevBuf(ctx, sizeof(T) * nk * cols);
+    gather_cols<T>(ctx, (const T*)Uall.ptr, n, rows, (const int32_t*)idx.ptr, nk, nullptr, (T*)U.ptr, rows);
+    gather_cols<T>(ctx, (const T*)G.ptr, cols, cols, (const int32_t*)idx.ptr, nk, nullptr, (T*)tmp.ptr, cols);
+    transpose_conj<T>(ctx, (const T*)tmp.ptr, cols, nk, cols, (T*)C.ptr, nk, true);
+    ctx->sync();
+    return info;
+  }
   double terr = 0.0;
   const int64_t nkeep = truncate_spectrum(spectrum, cutoff, mindim, maxdim, &terr);
   for (double& x : spectrum) x = std::max(x, 0.0);
   info.newdim = nkeep;
   info.truncerr = terr;
+  if (dist && nkeep >= 64 * dist->nranks) {
+    // kept eigenvectors by column slabs (equal chunks, the buffer is padded to a multiple of the rank count) + all-gather
+    const int G = dist->nranks;
+    const int64_t kc = (nkeep + G - 1) / G, k0 = std::min<int64_t>(nkeep, kc * dist->rank), kn = std::min<int64_t>(nkeep, k0 + kc) - k0;
+    U = DevBuf(ctx, sizeof(T) * rows * kc * G);
+    if (kn > 0) eg.vectors(order.data() + k0, kn, (T*)U.ptr + k0 * rows, rows);
+    dist->allgather_inplace(U.ptr, sizeof(T) * (size_t)rows * kc);
+    if (trans_in && dist->allow_c_transposed) {
+      // C^T (cols x nkeep) = buf conj(U): split over the same column slabs of U
+      C = DevBuf(ctx, sizeof(T) * cols * kc * G);
+      if (kn > 0) gemm<T>(ctx, OP_N, OP_CONJ, cols, kn, rows, one, M, ld, 0, (const T*)U.ptr + k0 * rows, rows, 0, zero, (T*)C.ptr + k0 * cols, cols, 0, 1);
+      dist->allgather_inplace(C.ptr, sizeof(T) * (size_t)cols * kc);
+      info.c_transposed = true;
+    } else if (!trans_in && cols % G == 0) {
+      const int64_t nc = cols / G, c0 = nc * dist->rank;
+      C = DevBuf(ctx, sizeof(T) * nkeep * cols);
+      gemm<T>(ctx, OP_C, OP_N, nkeep, nc, rows, one, (const T*)U.ptr, rows, 0, M + c0 * ld, ld, 0, zero, (T*)C.ptr + c0 * nkeep, nkeep, 0, 1);
+      dist->allgather_inplace(C.ptr, sizeof(T) * (size_t)nkeep * nc);
+    } else {
+      C = DevBuf(ctx, sizeof(T) * nkeep * cols);
+      gemm<T>(ctx, OP_C, trans_in ? OP_T : OP_N, nkeep, cols, rows, one, (const T*)U.ptr, rows, 0, M, ld, 0, zero, (T*)C.ptr, nkeep, 0, 1);
+    }
+    ctx->sync();
+    return info;
+  }
   U = DevBuf(ctx, sizeof(T) * rows * nkeep);
   C = DevBuf(ctx, sizeof(T) * nkeep * cols);
   eg.vectors(order.data(), nkeep, (T*)U.ptr, rows);
@@ -681,13 +987,13 @@ static FactorInfo factorize_left_eigh(Ctx* ctx, const T* M, int64_t rows, int64_
 template <typename T>
 FactorInfo factorize_left(Ctx* ctx, const T* M, int64_t rows, int64_t cols, int64_t ld, bool trans_in, double cutoff,
                           int64_t mindim, int64_t maxdim, bool sqrt_spectrum, DevBuf& U, DevBuf& C,
-                          std::vector<double>& spectrum) {
+                          std::vector<double>& spectrum, const FactorDist* dist) {
   // the density matrix of `eigen(rho; ...)` (square, sqrt_spectrum) is an eigenproblem already: the tridiagonalisation
   // route beats the latency-bound Jacobi iteration from ~100 rows on (README workload: 1-site DMRG 10.9 s -> 4.7 s)
-  const bool direct_eig = sqrt_spectrum && rows == cols && g_eigh_direct_min_n > 0 && rows >= g_eigh_direct_min_n;
-  if ((g_eigh_min_n > 0 && rows <= cols && rows >= g_eigh_min_n) || direct_eig) {
+  const bool direct_eig = sqrt_spectrum && rows == cols && ctx->opt.eigh_direct_min_n > 0 && rows >= ctx->opt.eigh_direct_min_n;
+  if ((ctx->opt.eigh_min_n > 0 && rows <= cols && rows >= ctx->opt.eigh_min_n) || direct_eig) {
     ctx->cnt.svd_calls++;
-    return factorize_left_eigh<T>(ctx, M, rows, cols, ld, trans_in, cutoff, mindim, std::min<int64_t>(maxdim, rows), sqrt_spectrum, U, C, spectrum);
+    return factorize_left_eigh<T>(ctx, M, rows, cols, ld, trans_in, cutoff, mindim, std::min<int64_t>(maxdim, rows), sqrt_spectrum, U, C, spectrum, dist);
   }
   FactorInfo info;
   ctx->cnt.svd_calls++;
@@ -715,7 +1021,7 @@ FactorInfo factorize_left(Ctx* ctx, const T* M, int64_t rows, int64_t cols, int6
   const int64_t n = rows, m = cols;
   DevBuf G(ctx, sizeof(T) * m * n), V(ctx, sizeof(T) * n * n), Qm;
   std::vector<int32_t> pcol;        // column permutation of the preconditioned path
-  const bool precond = (n >= g_jacobi_block_min_n) && g_jacobi_precondition && (n >= g_jacobi_precondition_min_n);
+  const bool precond = (n >= ctx->opt.jacobi_block_min_n) && ctx->opt.jacobi_precondition && (n >= ctx->opt.jacobi_precondition_min_n);
   if (!precond) {   // G = M^H (cols x rows)
     if (!trans_in) transpose_conj<T>(ctx, M, rows, cols, ld, (T*)G.ptr, m, true);
     else conj_copy_block<T>(ctx, M, ld, (T*)G.ptr, m, cols, rows);            // stored (cols x rows): conj only
@@ -728,7 +1034,7 @@ FactorInfo factorize_left(Ctx* ctx, const T* M, int64_t rows, int64_t cols, int6
     else transpose_conj<T>(ctx, M, cols, rows, ld, (T*)Mw.ptr, rows, false);
     Qm = DevBuf(ctx, sizeof(T) * rows * rows);
     DevBuf Rm(ctx, sizeof(T) * rows * cols);
-    if (g_jacobi_pivot) {
+    if (ctx->opt.jacobi_pivot) {
       qr_pivoted_thin<T>(ctx, (T*)Mw.ptr, rows, cols, rows, (T*)Qm.ptr, rows, (T*)Rm.ptr, rows, pcol);
     } else {
       pcol.resize(cols);
@@ -739,7 +1045,7 @@ FactorInfo factorize_left(Ctx* ctx, const T* M, int64_t rows, int64_t cols, int6
     ctx->sync();
   }
   set_identity<T>(ctx, (T*)V.ptr, n, n, n);
-  if (n >= g_jacobi_block_min_n) info.sweeps = jacobi_blocked<T>(ctx, (T*)G.ptr, m, n, (T*)V.ptr, n);
+  if (n >= ctx->opt.jacobi_block_min_n) info.sweeps = jacobi_blocked<T>(ctx, (T*)G.ptr, m, n, (T*)V.ptr, n);
   else info.sweeps = jacobi_onesided<T>(ctx, (T*)G.ptr, m, m, n, (T*)V.ptr, n, n);
 
   DevBuf norms(ctx, sizeof(double) * n);
@@ -788,7 +1094,7 @@ FactorInfo factorize_left(Ctx* ctx, const T* M, int64_t rows, int64_t cols, int6
 #define INST(T)                                                                                              \
   template void qr_thin<T>(Ctx*, T*, int64_t, int64_t, int64_t, T*, int64_t, T*, int64_t);                   \
   template FactorInfo factorize_left<T>(Ctx*, const T*, int64_t, int64_t, int64_t, bool, double, int64_t, int64_t, \
-                                        bool, DevBuf&, DevBuf&, std::vector<double>&);
+                                        bool, DevBuf&, DevBuf&, std::vector<double>&, const FactorDist*);
 INST(double)
 INST(cdouble)
 

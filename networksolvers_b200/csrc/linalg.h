@@ -1,6 +1,8 @@
 // Dense factorizations on device: Householder thin QR (gauge moves, K8) and the truncating
 // factorization of the inserter (K9) by one-sided Jacobi (Hestenes) SVD.
 #pragma once
+#include <functional>
+
 #include "common.h"
 
 namespace nsb {
@@ -16,13 +18,19 @@ void qr_thin(Ctx* ctx, T* A, int64_t rows, int64_t cols, int64_t lda, T* Q, int6
 // Batched 128 x 128 dense symmetric eigensolver (two-sided Jacobi inside one CTA); eigenvalue i <-> column i of R.
 void herm_eig_batch128(Ctx* ctx, const double* S, double* R, double* evals, int batch, double abs_floor, int max_sweeps);
 
-extern int g_jacobi_precondition;  // 1: QR-precondition the blocked Jacobi (Drmac-Veselic)
-extern int g_jacobi_pivot;
-extern int g_jacobi_inner_cap;
-extern int g_jacobi_precondition_min_n;
-extern int g_jacobi_block_min_n;   // column count from which the blocked (GEMM-rich) Jacobi is used
 
-struct FactorInfo { int64_t newdim = 0; double truncerr = 0; int decomp = 0; int sweeps = 0; };
+struct FactorInfo { int64_t newdim = 0; double truncerr = 0; int decomp = 0; int sweeps = 0; bool c_transposed = false; };
+
+// Multi-GPU factorisation (identical input on every rank): the GEMM-shaped parts of the Gram + eigh route are split by
+// column slabs, each slab computed by its owner and completed by an in-place all-gather (chunk of rank r at
+// buf + r * bytes_per_rank).  The tridiagonalisation and the divide & conquer run replicated.  With allow_c_transposed the
+// transposed-input case returns C^T (cols x newdim) instead of C (FactorInfo::c_transposed), which is the layout the
+// caller's site tensor wants and splits over its columns.
+struct FactorDist {
+  int rank = 0, nranks = 1;
+  std::function<void(void* buf, size_t bytes_per_rank)> allgather_inplace;
+  bool allow_c_transposed = false;
+};
 
 // Truncated left-orthogonal factorization M = U C (src/inserter.jl:23 / ITensors.factorize with ortho="left"):
 //   U (rows x newdim) orthonormal columns = leading left singular vectors, C = U^H M (newdim x cols).
@@ -35,6 +43,6 @@ struct FactorInfo { int64_t newdim = 0; double truncerr = 0; int decomp = 0; int
 template <typename T>
 FactorInfo factorize_left(Ctx* ctx, const T* M, int64_t rows, int64_t cols, int64_t ld, bool trans_in, double cutoff,
                           int64_t mindim, int64_t maxdim, bool sqrt_spectrum, DevBuf& U, DevBuf& C,
-                          std::vector<double>& spectrum);
+                          std::vector<double>& spectrum, const FactorDist* dist = nullptr);
 
 }  // namespace nsb

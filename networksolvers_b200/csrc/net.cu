@@ -14,6 +14,7 @@
 #include "net.h"
 
 #include "nccl_dyn.h"
+#include "rangefinder.h"
 
 #include <algorithm>
 #include <cmath>
@@ -21,9 +22,6 @@
 
 namespace nsb {
 
-int g_skip_identity = 1;    // ctx option "skip_identity"
-int g_skip_identity_sharded = 1;   // the same inside the multi-GPU (sharded) application; ctx option "skip_identity_sharded"
-int g_merge_site_ops = 1;   // 2-site regions: apply W[a] W[b] as one small-operator pass (ctx option "merge_site_ops")
 
 // ------------------------------------------------------------------------------------------------
 // small host dense helpers
@@ -414,14 +412,31 @@ int Net<T>::make_env(int u, int v) {
   NSB_REQUIRE(!fit_mode || xket[u].valid(), NSB_EINVAL, "make_env: fitting target tensor missing");
   DTensor<T> X = fit_mode ? xket[u] : psi[u];
   size_t start = 0;
-  if (!others.empty()) { X = contract(ctx, X, envs.at({others[0], u}).t, false, false, 1); start = 1; }
+  DTensor<T> bra = psi[u].primed();
+  // multi-GPU: split the contraction over the bra index of the (single) incoming environment across the ranks -- 1/G of
+  // every GEMM of the update -- and sum the partial environments with one all-reduce
+  bool split = false;
+  if (shard_enabled && ctx->nranks > 1 && ctx->nccl_comm && !fit_mode && !qn_on && others.size() == 1) {
+    const DTensor<T>& Ein = envs.at({others[0], u}).t;
+    const int G = ctx->nranks;
+    if (Ein.rank() == 3 && Ein.dims[2] >= 4 * G && Ein.dims[2] % G == 0) {
+      const int64_t per = Ein.dims[2] / G, lo = per * ctx->rank, hi = lo + per;
+      DTensor<T> bs;
+      if (slab_of(bra, Ein.labels[2], lo, hi, &bs)) {
+        X = contract(ctx, X, Ein.last_mode_slab(lo, hi), false, false, 1);
+        bra = bs;
+        start = 1;
+        split = true;
+      }
+    }
+  }
+  if (!split && !others.empty()) { X = contract(ctx, X, envs.at({others[0], u}).t, false, false, 1); start = 1; }
   {
     SmallOp<T> op;
     std::vector<int> reg{u};
     X = apply_small(ctx, op, X, W[u], w_out_labels(X, W[u], u, reg));
   }
   for (size_t i = start; i < others.size(); ++i) X = contract(ctx, X, envs.at({others[i], u}).t, false, false, 1);
-  DTensor<T> bra = psi[u].primed();
   std::vector<Label> want{fit_mode ? lxlink(u, v) : llink(u, v, 0), lop(u, v), llink(u, v, 1)};
   std::vector<Label> l1, l2;
   bool d1 = contract_direct_labels(bra, X, &l1), d2 = contract_direct_labels(X, bra, &l2);
@@ -430,9 +445,10 @@ int Net<T>::make_env(int u, int v) {
   else if (d2 && l2 == want) E = contract(ctx, X, bra, false, true, 1);
   else E = contract(ctx, X, bra, false, true, 0);
   if (E.labels != want) E = permuted(ctx, E, want);
+  if (split) comm_allreduce(E.data(), E.numel());
   Env env;
   env.t = E;
-  if (g_skip_identity && !fit_mode && E.rank() == 3 && E.dims[0] == E.dims[2] && E.dims[1] >= 2 && E.dims[1] <= 64) {
+  if (ctx->opt.skip_identity && !fit_mode && E.rank() == 3 && E.dims[0] == E.dims[2] && E.dims[1] >= 2 && E.dims[1] <= 64) {
     std::vector<double> dev(E.dims[1]);
     identity_deviation<T>(ctx, E.data(), E.dims[0], E.dims[1], dev.data());
     for (int64_t w = 0; w < E.dims[1]; ++w) if (dev[w] <= 1e-10) { env.ident = (int)w; break; }
@@ -464,7 +480,7 @@ void Net<T>::build_plan() {
     }
   }
   // merge two consecutive site-operator steps (chain-like 2-site regions) into one pass over the big intermediate
-  for (size_t i = 0; g_merge_site_ops && i + 1 < plan.size(); ++i) {
+  for (size_t i = 0; ctx->opt.merge_site_ops && i + 1 < plan.size(); ++i) {
     if (plan[i].type == 1 && plan[i + 1].type == 1) {
       int a = plan[i].v, b = plan[i + 1].v;
       const DTensor<T>&Wa = W[a], &Wb = W[b];
@@ -510,7 +526,7 @@ void Net<T>::prepare_identity_skip() {
   skipped_last_apply = -1.0;
   first_ident = -1;
   first_compact = DTensor<T>();
-  if (!g_skip_identity || fit_mode || plan.size() < 2 || plan.front().type != 0) return;
+  if (!ctx->opt.skip_identity || fit_mode || plan.size() < 2 || plan.front().type != 0) return;
   const Env& e = envs.at({plan.front().u, plan.front().v});
   const DTensor<T>& E = e.t;
   if (e.ident < 0 || E.rank() != 3) return;
@@ -527,7 +543,7 @@ template <typename T>
 double Net<T>::skipped_flops(const DTensor<T>& x) const {
   // dry run of the conditions of apply_heff on the labels of x (the site-operator steps keep the big modes in place, so
   // the tensor that meets the last environment has x's link at the same end with the operator link next to it)
-  if (!g_skip_identity || (shard_active && (!g_skip_identity_sharded || ctx->shard_fused)) || fit_mode || plan.size() < 2 || x.rank() < 2) return 0.0;
+  if (!ctx->opt.skip_identity || (shard_active && (!ctx->opt.skip_identity_sharded || ctx->shard_fused)) || fit_mode || plan.size() < 2 || x.rank() < 2) return 0.0;
   double f = 0.0;
   const double cplx = ScalarTraits<T>::is_complex ? 4.0 : 1.0;
   if (first_ident >= 0 && first_compact.valid() && plan.front().type == 0) {
@@ -546,203 +562,354 @@ template <typename T> struct NcclType;
 template <> struct NcclType<double> { static constexpr int mult = 1; };
 template <> struct NcclType<cdouble> { static constexpr int mult = 2; };
 
-// Multi-GPU partition of one H_eff application: theta is split along its last bond b across the
-// ranks; every step before the last environment acts on other modes, so it runs unchanged on the slab; the last
-// environment contraction sums over (b, m), so each rank contracts its slab with rows [lo, hi) of that
-// environment and the partial results are summed by one NCCL all-reduce.  State, environments and Krylov
-// vectors stay replicated (every rank runs the same sweep in lock step).
+// ------------------------------------------------------------------------------------------------
+// Multi-GPU partition of the region step.  One process per GPU, every rank runs the same sweep in lock step
+// on replicated site tensors and environments; what is split is the arithmetic:
+//
+//   H_eff application: the Krylov vectors are sharded along the LAST bond of theta (contiguous slabs, equal on every rank).
+//     RS ("reduce-scatter") positions -- the last environment of the plan contracts that bond (sweeping right): every step
+//        runs on the slab, the last contraction uses rows [lo, hi) of that environment and yields a partial full-size result,
+//        one ncclReduceScatter leaves theta' sharded like theta.
+//     AG ("all-gather") positions -- the first environment of the plan contracts that bond (sweeping left): one ncclAllGather
+//        completes the input, the first contraction is split along the environment's bra index (a column slab of the
+//        environment: a view), all later steps act on other modes, and the result is the slab of theta' -- no reduction.
+//     Dots and norms of the Lanczos / Runge-Kutta vectors are local partial sums + an all-reduce of two doubles.
+//     Bonds that do not divide evenly fall back to the round-1 form (AR: full vectors, all-reduce of theta').
+//   Environment update: the contraction over the incoming environment's bra index is split (1/G of every GEMM), partial
+//     results summed by one all-reduce.
+//   Factorisation (Net::insert -> factorize_left, linalg.cu): Gram matrix by output column slabs + all-gather, back-
+//     transformation of the kept eigenvectors by column slabs + all-gather, C = U^H theta by column slabs + all-gather; the
+//     tridiagonalisation and the divide & conquer run replicated on identical data.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+void Net<T>::nccl_check(int r, const char* what) {
+  if (r != (int)ncclSuccess) throw Error(NSB_ENCCL, std::string(what) + ": " + nccl_api().GetErrorString((ncclResult_t)r));
+}
+template <typename T>
+void Net<T>::comm_allreduce(T* buf, int64_t n) {
+  nccl_check(nccl_api().AllReduce(buf, buf, (size_t)n * NcclType<T>::mult, ncclDouble, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream), "ncclAllReduce");
+  ctx->cnt.kernel_launches++;
+}
+template <typename T>
+void Net<T>::comm_allgather(const T* send, T* recv, int64_t n_per_rank) {
+  nccl_check(nccl_api().AllGather(send, recv, (size_t)n_per_rank * NcclType<T>::mult, ncclDouble, (ncclComm_t)ctx->nccl_comm, ctx->stream), "ncclAllGather");
+  ctx->cnt.kernel_launches++;
+}
+template <typename T>
+void Net<T>::comm_reduce_scatter(const T* send, T* recv, int64_t n_per_rank) {
+  nccl_check(nccl_api().ReduceScatter(send, recv, (size_t)n_per_rank * NcclType<T>::mult, ncclDouble, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream),
+             "ncclReduceScatter");
+  ctx->cnt.kernel_launches++;
+}
+
+// slab [lo, hi) of mode `l` of t: a view when l is the last mode, a strided copy when it is the first one
+template <typename T>
+bool Net<T>::slab_of(const DTensor<T>& t, Label l, int64_t lo, int64_t hi, DTensor<T>* out) {
+  const int pos = t.find(l);
+  if (pos < 0) return false;
+  if (pos == t.rank() - 1) { *out = t.last_mode_slab(lo, hi); return true; }
+  if (pos == 0) {
+    std::vector<int64_t> d = t.dims;
+    d[0] = hi - lo;
+    DTensor<T> o(ctx, d, t.labels);
+    if (hi > lo) copy_block<T>(ctx, t.data() + lo, t.dims[0], o.data(), hi - lo, hi - lo, t.numel() / t.dims[0]);
+    *out = o;
+    return true;
+  }
+  return false;
+}
+
 template <typename T>
 void Net<T>::shard_prepare() {
   shard_active = false;
-  if (!shard_enabled || ctx->nranks <= 1 || !ctx->nccl_comm || plan.empty() || !theta.valid()) return;
+  shard_mode = 0;
+  theta_is_slab = false;
+  theta_slab = DTensor<T>();
+  if (!shard_enabled || ctx->nranks <= 1 || !ctx->nccl_comm || plan.size() < 2 || !theta.valid() || fit_mode || qn_on) return;
+  const int G = ctx->nranks;
+  const int64_t nb = theta.dims.back();
+  const Label lb = theta.labels.back();
+  if (label_kind(lb) != LK_LINK) return;
   const Step& last = plan.back();
-  if (last.type != 0) return;
-  const DTensor<T>& E = envs.at({last.u, last.v}).t;
-  Label lb = llink(last.u, last.v, 0);
-  if (theta.labels.back() != lb || E.labels[0] != lb) return;     // last bond of theta must be that environment's ket link
-  for (size_t i = 0; i + 1 < plan.size(); ++i)
-    if (plan[i].type == 0 && plan[i].u == last.u && plan[i].v == last.v) return;
-  int64_t nb = theta.dims.back();
-  int64_t per = (nb + ctx->nranks - 1) / ctx->nranks;
-  shard_lo = std::min<int64_t>(nb, per * ctx->rank);
-  shard_hi = std::min<int64_t>(nb, shard_lo + per);
-  int64_t rows = shard_hi - shard_lo, cols = E.numel() / nb;
-  std::vector<int64_t> d = E.dims;
-  d[0] = rows;
-  shard_env = DTensor<T>(ctx, d, E.labels);
-  if (rows > 0) copy_block<T>(ctx, E.data() + shard_lo, nb, shard_env.data(), rows, rows, cols);
-  shard_active = true;
+  const Step& first = plan.front();
+  auto env_of = [&](const Step& st) -> const DTensor<T>& { return envs.at({st.u, st.v}).t; };
+  int uses = 0;
+  for (auto& st : plan) if (st.type == 0 && env_of(st).find(lb) >= 0) ++uses;
+  if (uses != 1) return;
+  const bool even = (nb % G == 0) && nb >= G && !ctx->shard_fused;
+  if (last.type == 0 && env_of(last).rank() == 3 && env_of(last).labels[0] == lb) {
+    const DTensor<T>& E = env_of(last);
+    const int64_t per = even ? nb / G : (nb + G - 1) / G;
+    shard_lo = std::min<int64_t>(nb, per * ctx->rank);
+    shard_hi = std::min<int64_t>(nb, shard_lo + per);
+    const int64_t rows = shard_hi - shard_lo, cols = E.numel() / nb;
+    std::vector<int64_t> d = E.dims;
+    d[0] = rows;
+    shard_env = DTensor<T>(ctx, d, E.labels);
+    if (rows > 0) copy_block<T>(ctx, E.data() + shard_lo, nb, shard_env.data(), rows, rows, cols);
+    shard_mode = even ? 1 : 3;
+    shard_active = true;
+    return;
+  }
+  if (even && first.type == 0 && env_of(first).rank() == 3 && env_of(first).labels[0] == lb && env_of(first).dims[2] == nb) {
+    // the contraction must leave the bra link as the last mode (theta's last mode replaced by [operator link, bra link])
+    std::vector<Label> pl;
+    if (!contract_direct_labels(theta, env_of(first), &pl) || pl.empty() || pl.back() != env_of(first).labels[2]) return;
+    const int64_t per = nb / G;
+    shard_lo = per * ctx->rank;
+    shard_hi = shard_lo + per;
+    shard_env = DTensor<T>();
+    shard_mode = 2;
+    shard_active = true;
+  }
 }
 
 template <typename T>
 int Net<T>::set_shard(int enable) {
   shard_enabled = enable != 0;
+  if (theta_is_slab) ensure_theta_full();
   shard_prepare();
   return shard_active ? 1 : 0;
+}
+
+template <typename T>
+void Net<T>::ensure_theta_full() {
+  if (!theta_is_slab) return;
+  DTensor<T> full(ctx, theta.dims, theta.labels);
+  comm_allgather(theta_slab.data(), full.data(), theta_slab.numel());
+  theta = full;
+  theta_is_slab = false;
+  theta_slab = DTensor<T>();
 }
 
 // T1 = X * L over L's ket link, where L is the first environment of the plan: the channel with L[:, w*, :] = 1 is X itself --
 // contract with the W - 1 other channels (first_compact) and splice X in as the missing channel of the operator link.  Two
 // layouts occur on the permutation-free chain path: the ket link is X's first mode (result [w, bra, rest of X]) or X's last
 // mode (result [rest of X, w, bra]).  Returns false (X untouched) when the pattern does not apply.
+// bra_lo / bra_hi (AG positions): only the bra-link slab [bra_lo, bra_hi) of the result is formed; Xs is that slab of X.
 template <typename T>
-bool Net<T>::skip_first_identity(DTensor<T>& X) {
+bool Net<T>::skip_first_identity(DTensor<T>& X, int64_t bra_lo, int64_t bra_hi, const DTensor<T>* Xs) {
   if (!(first_ident >= 0 && first_compact.valid() && !fit_mode && plan.size() >= 2 && plan[0].type == 0)) return false;
   const DTensor<T>& E = envs.at({plan[0].u, plan[0].v}).t;
   const int64_t Wd = E.dims[1];
   const int r = X.rank();
+  const bool slab = bra_hi > bra_lo;
+  DTensor<T> comp = slab ? first_compact.last_mode_slab(bra_lo, bra_hi) : first_compact;
   std::vector<Label> pl;
   int64_t pre = 0;
-  if (r >= 2 && E.dims[0] == E.dims[2] && contract_direct_labels(X, first_compact, &pl) && (int)pl.size() == r + 1) {
-    if (X.labels[0] == E.labels[0] && pl[0] == E.labels[1] && pl[1] == E.labels[2]) pre = 1;
+  if (r >= 2 && E.dims[0] == E.dims[2] && contract_direct_labels(X, comp, &pl) && (int)pl.size() == r + 1) {
+    if (!slab && X.labels[0] == E.labels[0] && pl[0] == E.labels[1] && pl[1] == E.labels[2]) pre = 1;
     else if (X.labels[r - 1] == E.labels[0] && pl[r - 1] == E.labels[1] && pl[r] == E.labels[2]) pre = X.numel() / X.dims[r - 1];
   }
   if (pre <= 0) return false;
-  DTensor<T> Xc = contract(ctx, X, first_compact, false, false, 1);
+  DTensor<T> Xc = contract(ctx, X, comp, false, false, 1);
   NSB_REQUIRE(Xc.labels == pl, NSB_EINTERNAL, "identity skipping: unexpected layout of the first contraction");
   const int wpos = (pre == 1) ? 0 : r - 1;
   std::vector<int64_t> fd = Xc.dims;
   fd[wpos] = Wd;
   DTensor<T> Xf(ctx, fd, Xc.labels);
-  const int64_t post = X.numel() / pre;   // pre = 1: all of X behind the operator link; else the extent of the bra link
-  insert_mode<T>(ctx, Xc.data(), X.data(), Xf.data(), pre, Wd - 1, first_ident, post);
+  // pre = 1: all of X behind the operator link; else the extent of the bra link (its slab on AG positions)
+  const int64_t post = slab ? (bra_hi - bra_lo) : X.numel() / pre;
+  insert_mode<T>(ctx, Xc.data(), slab ? Xs->data() : X.data(), Xf.data(), pre, Wd - 1, first_ident, post);
   X = Xf;
   return true;
 }
 
 template <typename T>
-DTensor<T> Net<T>::apply_heff(const DTensor<T>& x) {
-  DTensor<T> X = x;
-  if (shard_active) {
-    DTensor<T> out(ctx, x.dims, x.labels);
-    if (shard_hi > shard_lo) {
-      X = x.last_mode_slab(shard_lo, shard_hi);
-      double skipped = 0.0;    // whole-job count (summed over the ranks' slabs)
-      size_t i0 = 0;
-      if (g_skip_identity_sharded && skip_first_identity(X)) { i0 = 1; skipped += 2.0 * (double)x.numel() * (double)envs.at({plan[0].u, plan[0].v}).t.dims[2]; }
-      for (size_t i = i0; i + 1 < plan.size(); ++i) {
-        auto& s = plan[i];
-        if (s.type == 0) X = contract(ctx, X, envs.at({s.u, s.v}).t, false, false, 1);
-        else if (s.type == 1) X = apply_small(ctx, s.op, X, W[s.v], w_out_labels(X, W[s.v], s.v, pos));
-        else X = apply_small(ctx, s.op, X, s.Wm, merged_out_labels(X, s.u, s.v));
-      }
-      // fused path: the last GEMM writes its tiles into the owners' staging windows over NVLink (P2P stores from the
-      // epilogue), the owner sums the partial slabs, one all-gather completes theta'
-      std::vector<Label> pl;
-      const int G = ctx->nranks;
-      const int64_t nb = x.dims.back();
-      bool fused = ctx->shard_fused && G <= 8 && nb % G == 0 && ctx->win_local &&
-                   ctx->win_bytes >= sizeof(T) * (size_t)x.numel() && contract_direct_labels(X, shard_env, &pl);
-      if (fused) {
-        for (auto& l : pl) l = label_setplev(l, 0);
-        int shared = 0;
-        for (Label l : X.labels) if (shard_env.find(l) >= 0) ++shared;
-        fused = (pl == x.labels) && shared == 2 && shard_env.find(X.labels.back()) >= 0 && shard_env.find(X.labels[X.rank() - 2]) >= 0;
-        for (int g = 0; g < G && fused; ++g) if (!ctx->win_peer[g]) fused = false;
-      }
-      if (fused) {
-        int64_t Kc = X.dims[X.rank() - 1] * X.dims[X.rank() - 2], P = X.numel() / Kc, N = nb;
-        PeerOut po;
-        for (int g = 0; g < G; ++g) po.ptr[g] = ctx->win_peer[g];
-        po.nranks = G; po.rank = ctx->rank; po.slab_cols = N / G; po.slab_elems = P * (N / G);
-        gemm<T>(ctx, OP_N, OP_N, P, N, Kc, from_complex<T>(1.0, 0.0), X.data(), P, 0, shard_env.data(), Kc, 0, zero_<T>(),
-                out.data(), P, 0, 1, GEMM_AUTO, &po);
-        // all ranks' stores must have landed before the owner reduces: a one-element all-reduce is the stream-ordered barrier
-        ncclResult_t r = nccl_api().AllReduce(ctx->d_scratch + 8, ctx->d_scratch + 8, 1, ncclDouble, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream);
-        if (r != ncclSuccess) throw Error(NSB_ENCCL, std::string("ncclAllReduce(barrier): ") + nccl_api().GetErrorString(r));
-        sum_slabs<T>(ctx, (const T*)ctx->win_local, G, po.slab_elems, out.data() + (int64_t)ctx->rank * po.slab_elems);
-        r = nccl_api().AllGather(out.data() + (int64_t)ctx->rank * po.slab_elems, out.data(), (size_t)po.slab_elems * NcclType<T>::mult, ncclDouble,
-                                 (ncclComm_t)ctx->nccl_comm, ctx->stream);
-        if (r != ncclSuccess) throw Error(NSB_ENCCL, std::string("ncclAllGather: ") + nccl_api().GetErrorString(r));
-        ctx->cnt.matvecs++;
-        skipped_last_apply = skipped * (ScalarTraits<T>::is_complex ? 4.0 : 1.0);
-        return out;
-      }
-      // identity channel of the last environment: rows (b in slab, w*) of the slab's contraction index meet the identity,
-      // i.e. that block of X is this rank's contribution to columns [shard_lo, shard_hi) of the result
-      const Env& le = envs.at({plan.back().u, plan.back().v});
-      const int rr = X.rank();
-      const int64_t rows = shard_hi - shard_lo, Wd = shard_env.rank() == 3 ? shard_env.dims[1] : 0, N = shard_env.rank() == 3 ? shard_env.dims[2] : 0;
-      if (g_skip_identity && g_skip_identity_sharded && !ctx->shard_fused && le.ident >= 0 && shard_env.rank() == 3 && le.t.dims[0] == N && rr >= 3 &&
-          X.labels[rr - 2] == shard_env.labels[0] && X.labels[rr - 1] == shard_env.labels[1] && X.dims[rr - 2] == rows && X.dims[rr - 1] == Wd) {
-        const T one = from_complex<T>(1.0, 0.0);
-        const int64_t Kc = rows * Wd, P = X.numel() / Kc, k0 = rows * le.ident, k1 = rows * (le.ident + 1);
-        std::vector<int64_t> od(X.dims.begin(), X.dims.end() - 2);
-        std::vector<Label> ol(X.labels.begin(), X.labels.end() - 2);
-        od.push_back(N); ol.push_back(shard_env.labels[2]);
-        DTensor<T> o2(ctx, od, ol);
-        vec_zero<T>(ctx, o2.numel(), o2.data());
-        vec_copy<T>(ctx, P * rows, X.data() + P * k0, o2.data() + P * shard_lo);
-        if (k0 > 0) gemm<T>(ctx, OP_N, OP_N, P, N, k0, one, X.data(), P, 0, shard_env.data(), Kc, 0, one, o2.data(), P, 0, 1);
-        if (k1 < Kc) gemm<T>(ctx, OP_N, OP_N, P, N, Kc - k1, one, X.data() + P * k1, P, 0, shard_env.data() + k1, Kc, 0, one, o2.data(), P, 0, 1);
-        skipped += 2.0 * (double)P * (double)N * (double)N;
-        X = o2.noprime();
-      } else {
-        X = contract(ctx, X, shard_env, false, false, 1).noprime();
-      }
-      if (X.labels != x.labels) X = permuted(ctx, X, x.labels);
-      out = X;
-      skipped_last_apply = skipped * (ScalarTraits<T>::is_complex ? 4.0 : 1.0);
-    } else {
-      vec_zero<T>(ctx, out.numel(), out.data());
-    }
-    ncclResult_t r = nccl_api().AllReduce(out.data(), out.data(), (size_t)out.numel() * NcclType<T>::mult, ncclDouble, ncclSum,
-                                          (ncclComm_t)ctx->nccl_comm, ctx->stream);
-    if (r != ncclSuccess) throw Error(NSB_ENCCL, std::string("ncclAllReduce: ") + nccl_api().GetErrorString(r));
-    ctx->cnt.matvecs++;
-    return out;
-  }
-  size_t i0 = 0, i1 = plan.size();
-  const T one = from_complex<T>(1.0, 0.0);
-  double skipped = 0.0;
-  if (skip_first_identity(X)) { i0 = 1; skipped += 2.0 * (double)x.numel() * (double)envs.at({plan[0].u, plan[0].v}).t.dims[2]; }
-  int last_w = -1;
-  if (g_skip_identity && !fit_mode && plan.size() >= 2 && plan.back().type == 0) {
-    const Env& e = envs.at({plan.back().u, plan.back().v});
-    if (e.ident >= 0 && e.t.rank() == 3 && e.t.dims[0] == e.t.dims[2]) { last_w = e.ident; i1 = plan.size() - 1; }
-  }
+DTensor<T> Net<T>::run_plan_steps(DTensor<T> X, size_t i0, size_t i1) {
   for (size_t i = i0; i < i1; ++i) {
     auto& s = plan[i];
     if (s.type == 0) X = contract(ctx, X, envs.at({s.u, s.v}).t, false, false, 1);
     else if (s.type == 1) X = apply_small(ctx, s.op, X, W[s.v], w_out_labels(X, W[s.v], s.v, pos));
     else X = apply_small(ctx, s.op, X, s.Wm, merged_out_labels(X, s.u, s.v));
   }
-  if (last_w >= 0) {
-    // The last environment R[(b, w), b'] is contracted over (ket link, operator link); the block w = w* of that
-    // contraction index meets the identity, so the result starts as that block of X and the other channels are added by
-    // at most two GEMMs (beta = 1).  Layouts: (b, w) are X's last two modes (out[p, b'] = X[p, K] R[K, b']) or its first
-    // two (out[b', q] = R[K, b']^T X[K, q]).
-    const DTensor<T>& E = envs.at({plan.back().u, plan.back().v}).t;
-    const int r = X.rank();
-    const int64_t nb = E.dims[0], Wd = E.dims[1], N = E.dims[2], Kc = nb * Wd;
-    const int64_t k0 = nb * last_w, k1 = nb * (last_w + 1);    // identity block [k0, k1) of the contraction index
-    if (r >= 3 && X.labels[r - 2] == E.labels[0] && X.labels[r - 1] == E.labels[1] && X.dims[r - 2] == nb && X.dims[r - 1] == Wd) {
-      const int64_t P = X.numel() / Kc;
-      std::vector<int64_t> od(X.dims.begin(), X.dims.end() - 2);
-      std::vector<Label> ol(X.labels.begin(), X.labels.end() - 2);
-      od.push_back(N); ol.push_back(E.labels[2]);
-      DTensor<T> out(ctx, od, ol);
-      vec_copy<T>(ctx, P * nb, X.data() + P * k0, out.data());
-      if (k0 > 0) gemm<T>(ctx, OP_N, OP_N, P, N, k0, one, X.data(), P, 0, E.data(), Kc, 0, one, out.data(), P, 0, 1);
-      if (k1 < Kc) gemm<T>(ctx, OP_N, OP_N, P, N, Kc - k1, one, X.data() + P * k1, P, 0, E.data() + k1, Kc, 0, one, out.data(), P, 0, 1);
-      X = out;
-      skipped += 2.0 * (double)P * (double)nb * (double)N;
-    } else if (r >= 3 && X.labels[0] == E.labels[0] && X.labels[1] == E.labels[1] && X.dims[0] == nb && X.dims[1] == Wd) {
-      const int64_t Q = X.numel() / Kc;
-      std::vector<int64_t> od{N};
-      std::vector<Label> ol{E.labels[2]};
-      od.insert(od.end(), X.dims.begin() + 2, X.dims.end());
-      ol.insert(ol.end(), X.labels.begin() + 2, X.labels.end());
-      DTensor<T> out(ctx, od, ol);
-      copy_block<T>(ctx, X.data() + k0, Kc, out.data(), N, nb, Q);
-      if (k0 > 0) gemm<T>(ctx, OP_T, OP_N, N, Q, k0, one, E.data(), Kc, 0, X.data(), Kc, 0, one, out.data(), N, 0, 1);
-      if (k1 < Kc) gemm<T>(ctx, OP_T, OP_N, N, Q, Kc - k1, one, E.data() + k1, Kc, 0, X.data() + k1, Kc, 0, one, out.data(), N, 0, 1);
-      X = out;
-      skipped += 2.0 * (double)Q * (double)nb * (double)N;
-    } else {
-      X = contract(ctx, X, E, false, false, 1);
-    }
+  return X;
+}
+
+// Contraction with the last environment of the plan E[(b, w), b'] over (ket link, operator link).  When the environment has an
+// identity channel w*, that block of the contraction index contributes X itself: the result starts as that block of X and the
+// other channels are added by at most two GEMMs (beta = 1).  Layouts: (b, w) are X's last two modes
+// (out[p, b'] = X[p, K] R[K, b']) or its first two (out[b', q] = R[K, b']^T X[K, q]).
+template <typename T>
+DTensor<T> Net<T>::last_env_contract(const DTensor<T>& X, double* skipped) {
+  const Env& e = envs.at({plan.back().u, plan.back().v});
+  const DTensor<T>& E = e.t;
+  const T one = from_complex<T>(1.0, 0.0);
+  const int last_w = (ctx->opt.skip_identity && !fit_mode && e.ident >= 0 && E.rank() == 3 && E.dims[0] == E.dims[2]) ? e.ident : -1;
+  if (last_w < 0) return contract(ctx, X, E, false, false, 1);
+  const int r = X.rank();
+  const int64_t nb = E.dims[0], Wd = E.dims[1], N = E.dims[2], Kc = nb * Wd;
+  const int64_t k0 = nb * last_w, k1 = nb * (last_w + 1);    // identity block [k0, k1) of the contraction index
+  if (r >= 3 && X.labels[r - 2] == E.labels[0] && X.labels[r - 1] == E.labels[1] && X.dims[r - 2] == nb && X.dims[r - 1] == Wd) {
+    const int64_t P = X.numel() / Kc;
+    std::vector<int64_t> od(X.dims.begin(), X.dims.end() - 2);
+    std::vector<Label> ol(X.labels.begin(), X.labels.end() - 2);
+    od.push_back(N); ol.push_back(E.labels[2]);
+    DTensor<T> out(ctx, od, ol);
+    vec_copy<T>(ctx, P * nb, X.data() + P * k0, out.data());
+    if (k0 > 0) gemm<T>(ctx, OP_N, OP_N, P, N, k0, one, X.data(), P, 0, E.data(), Kc, 0, one, out.data(), P, 0, 1);
+    if (k1 < Kc) gemm<T>(ctx, OP_N, OP_N, P, N, Kc - k1, one, X.data() + P * k1, P, 0, E.data() + k1, Kc, 0, one, out.data(), P, 0, 1);
+    *skipped += 2.0 * (double)P * (double)nb * (double)N;
+    return out;
   }
+  if (r >= 3 && X.labels[0] == E.labels[0] && X.labels[1] == E.labels[1] && X.dims[0] == nb && X.dims[1] == Wd) {
+    const int64_t Q = X.numel() / Kc;
+    std::vector<int64_t> od{N};
+    std::vector<Label> ol{E.labels[2]};
+    od.insert(od.end(), X.dims.begin() + 2, X.dims.end());
+    ol.insert(ol.end(), X.labels.begin() + 2, X.labels.end());
+    DTensor<T> out(ctx, od, ol);
+    copy_block<T>(ctx, X.data() + k0, Kc, out.data(), N, nb, Q);
+    if (k0 > 0) gemm<T>(ctx, OP_T, OP_N, N, Q, k0, one, E.data(), Kc, 0, X.data(), Kc, 0, one, out.data(), N, 0, 1);
+    if (k1 < Kc) gemm<T>(ctx, OP_T, OP_N, N, Q, Kc - k1, one, E.data() + k1, Kc, 0, X.data() + k1, Kc, 0, one, out.data(), N, 0, 1);
+    *skipped += 2.0 * (double)Q * (double)nb * (double)N;
+    return out;
+  }
+  return contract(ctx, X, E, false, false, 1);
+}
+
+// RS / AR positions: slab of theta -> partial full-size theta' of this rank (before the collective)
+template <typename T>
+DTensor<T> Net<T>::heff_partial_from_slab(const DTensor<T>& xs, double* skipped) {
+  DTensor<T> X = xs;
+  const T one = from_complex<T>(1.0, 0.0);
+  std::vector<int64_t> fulld = xs.dims;
+  fulld.back() = theta.dims.back();
+  size_t i0 = 0;
+  double full_numel = 1.0;
+  for (auto d : fulld) full_numel *= (double)d;
+  if (ctx->opt.skip_identity_sharded && skip_first_identity(X)) { i0 = 1; *skipped += 2.0 * full_numel * (double)envs.at({plan[0].u, plan[0].v}).t.dims[2]; }
+  X = run_plan_steps(X, i0, plan.size() - 1);
+  // identity channel of the last environment: rows (b in slab, w*) of the slab's contraction index meet the identity,
+  // i.e. that block of X is this rank's contribution to columns [shard_lo, shard_hi) of the result
+  const Env& le = envs.at({plan.back().u, plan.back().v});
+  const int rr = X.rank();
+  const int64_t rows = shard_hi - shard_lo, Wd = shard_env.rank() == 3 ? shard_env.dims[1] : 0, N = shard_env.rank() == 3 ? shard_env.dims[2] : 0;
+  if (ctx->opt.skip_identity && ctx->opt.skip_identity_sharded && le.ident >= 0 && shard_env.rank() == 3 && le.t.dims[0] == N && rr >= 3 &&
+      X.labels[rr - 2] == shard_env.labels[0] && X.labels[rr - 1] == shard_env.labels[1] && X.dims[rr - 2] == rows && X.dims[rr - 1] == Wd) {
+    const int64_t Kc = rows * Wd, P = X.numel() / Kc, k0 = rows * le.ident, k1 = rows * (le.ident + 1);
+    std::vector<int64_t> od(X.dims.begin(), X.dims.end() - 2);
+    std::vector<Label> ol(X.labels.begin(), X.labels.end() - 2);
+    od.push_back(N); ol.push_back(shard_env.labels[2]);
+    DTensor<T> o2(ctx, od, ol);
+    vec_zero<T>(ctx, o2.numel(), o2.data());
+    vec_copy<T>(ctx, P * rows, X.data() + P * k0, o2.data() + P * shard_lo);
+    if (k0 > 0) gemm<T>(ctx, OP_N, OP_N, P, N, k0, one, X.data(), P, 0, shard_env.data(), Kc, 0, one, o2.data(), P, 0, 1);
+    if (k1 < Kc) gemm<T>(ctx, OP_N, OP_N, P, N, Kc - k1, one, X.data() + P * k1, P, 0, shard_env.data() + k1, Kc, 0, one, o2.data(), P, 0, 1);
+    *skipped += 2.0 * (double)P * (double)N * (double)N;
+    X = o2.noprime();
+  } else {
+    X = contract(ctx, X, shard_env, false, false, 1).noprime();
+  }
+  if (X.labels != xs.labels) X = permuted(ctx, X, xs.labels);
+  return X;
+}
+
+// Sharded application: slab of theta in, slab of theta' out (RS and AG positions).
+template <typename T>
+DTensor<T> Net<T>::apply_heff_slab(const DTensor<T>& xs) {
+  NSB_REQUIRE(shard_active && (shard_mode == 1 || shard_mode == 2), NSB_EINTERNAL, "apply_heff_slab: position is not slab-sharded");
+  const int G = ctx->nranks;
+  double skipped = 0.0;
+  DTensor<T> out;
+  if (shard_mode == 1) {
+    DTensor<T> part = heff_partial_from_slab(xs, &skipped);
+    out = DTensor<T>(ctx, xs.dims, xs.labels);
+    comm_reduce_scatter(part.data(), out.data(), out.numel());
+    skipped *= 1.0;   // counted for the whole job inside heff_partial_from_slab
+  } else {
+    DTensor<T> xf(ctx, theta.dims, theta.labels);
+    comm_allgather(xs.data(), xf.data(), xs.numel());
+    DTensor<T> X = xf;
+    const DTensor<T>& E1 = envs.at({plan[0].u, plan[0].v}).t;
+    if (ctx->opt.skip_identity_sharded && skip_first_identity(X, shard_lo, shard_hi, &xs)) {
+      skipped += 2.0 * (double)xf.numel() * (double)E1.dims[2];
+    } else {
+      X = contract(ctx, xf, E1.last_mode_slab(shard_lo, shard_hi), false, false, 1);
+    }
+    X = run_plan_steps(X, 1, plan.size() - 1);
+    double sk = 0.0;
+    if (plan.back().type == 0) X = last_env_contract(X, &sk);
+    else X = run_plan_steps(X, plan.size() - 1, plan.size());
+    skipped += sk * (double)G;   // every rank skips its share: whole-job count
+    X = X.noprime();
+    if (X.labels != xs.labels) X = permuted(ctx, X, xs.labels);
+    NSB_REQUIRE(X.dims == xs.dims, NSB_EINTERNAL, "apply_heff_slab: unexpected result shape");
+    out = X;
+  }
+  ctx->cnt.matvecs++;
+  skipped_last_apply = skipped * (ScalarTraits<T>::is_complex ? 4.0 : 1.0);
+  return out;
+}
+
+template <typename T>
+DTensor<T> Net<T>::apply_heff(const DTensor<T>& x) {
+  DTensor<T> X = x;
+  if (shard_active && (shard_mode == 1 || shard_mode == 2)) {     // full vector in / out around the slab form
+    DTensor<T> os = apply_heff_slab(x.last_mode_slab(shard_lo, shard_hi));
+    DTensor<T> out(ctx, x.dims, x.labels);
+    comm_allgather(os.data(), out.data(), os.numel());
+    return out;
+  }
+  if (shard_active) {                                              // AR: uneven slabs or the fused epilogue
+    DTensor<T> out(ctx, x.dims, x.labels);
+    if (shard_hi > shard_lo) {
+      X = x.last_mode_slab(shard_lo, shard_hi);
+      double skipped = 0.0;    // whole-job count (summed over the ranks' slabs)
+      // fused path: the last GEMM writes its tiles into the owners' staging windows over NVLink (P2P stores from the
+      // epilogue), the owner sums the partial slabs, one all-gather completes theta'
+      std::vector<Label> pl;
+      const int G = ctx->nranks;
+      const int64_t nb = x.dims.back();
+      bool fused = ctx->shard_fused && G <= 8 && nb % G == 0 && ctx->win_local && ctx->win_bytes >= sizeof(T) * (size_t)x.numel();
+      if (fused) {
+        X = run_plan_steps(X, 0, plan.size() - 1);
+        fused = contract_direct_labels(X, shard_env, &pl);
+        if (fused) {
+          for (auto& l : pl) l = label_setplev(l, 0);
+          int shared = 0;
+          for (Label l : X.labels) if (shard_env.find(l) >= 0) ++shared;
+          fused = (pl == x.labels) && shared == 2 && shard_env.find(X.labels.back()) >= 0 && shard_env.find(X.labels[X.rank() - 2]) >= 0;
+          for (int g = 0; g < G && fused; ++g) if (!ctx->win_peer[g]) fused = false;
+        }
+        if (fused) {
+          int64_t Kc = X.dims[X.rank() - 1] * X.dims[X.rank() - 2], P = X.numel() / Kc, N = nb;
+          PeerOut po;
+          for (int g = 0; g < G; ++g) po.ptr[g] = ctx->win_peer[g];
+          po.nranks = G; po.rank = ctx->rank; po.slab_cols = N / G; po.slab_elems = P * (N / G);
+          gemm<T>(ctx, OP_N, OP_N, P, N, Kc, from_complex<T>(1.0, 0.0), X.data(), P, 0, shard_env.data(), Kc, 0, zero_<T>(),
+                  out.data(), P, 0, 1, GEMM_AUTO, &po);
+          // all ranks' stores must have landed before the owner reduces: a one-element all-reduce is the stream-ordered barrier
+          nccl_check(nccl_api().AllReduce(ctx->d_scratch + 8, ctx->d_scratch + 8, 1, ncclDouble, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream),
+                     "ncclAllReduce(barrier)");
+          sum_slabs<T>(ctx, (const T*)ctx->win_local, G, po.slab_elems, out.data() + (int64_t)ctx->rank * po.slab_elems);
+          comm_allgather(out.data() + (int64_t)ctx->rank * po.slab_elems, out.data(), po.slab_elems);
+          ctx->cnt.matvecs++;
+          skipped_last_apply = 0.0;
+          return out;
+        }
+        X = contract(ctx, X, shard_env, false, false, 1).noprime();
+        if (X.labels != x.labels) X = permuted(ctx, X, x.labels);
+        out = X;
+        skipped_last_apply = 0.0;
+      } else {
+        out = heff_partial_from_slab(X, &skipped);
+        skipped_last_apply = skipped * (ScalarTraits<T>::is_complex ? 4.0 : 1.0);
+      }
+    } else {
+      vec_zero<T>(ctx, out.numel(), out.data());
+    }
+    comm_allreduce(out.data(), out.numel());
+    ctx->cnt.matvecs++;
+    return out;
+  }
+  size_t i0 = 0, i1 = plan.size();
+  double skipped = 0.0;
+  if (skip_first_identity(X)) { i0 = 1; skipped += 2.0 * (double)x.numel() * (double)envs.at({plan[0].u, plan[0].v}).t.dims[2]; }
+  const bool last_is_env = plan.size() >= 2 && plan.back().type == 0;
+  if (last_is_env) i1 = plan.size() - 1;
+  X = run_plan_steps(X, i0, i1);
+  if (last_is_env) X = last_env_contract(X, &skipped);
   X = X.noprime();
   if (!fit_mode && X.labels != x.labels) X = permuted(ctx, X, x.labels);   // (fitting: the result lives on psi's links)
   ctx->cnt.matvecs++;
@@ -876,7 +1043,13 @@ bool Net<T>::expand_ortho(const nsb_trunc& trunc, const nsb_expand& ex) {
   DevBuf Yb(ctx, sizeof(T) * nb * axd), tmpbuf(ctx, sizeof(T) * cur * std::max(axd, kexp + cur));
   T* Y = (T*)Yb.ptr;
   T* tmp = (T*)tmpbuf.ptr;
-  fill_normal<T>(ctx, Y, nb * axd, expand_seed++, 1.0);
+  if (expand_probe.ptr && expand_probe_rows == nb && expand_probe_cols == axd) {   // caller's random_itensor(basis_inds, ax)
+    vec_copy<T>(ctx, nb * axd, (const T*)expand_probe.ptr, Y);
+    ctx->sync();
+    expand_probe = DevBuf(); expand_probe_rows = expand_probe_cols = 0;
+  } else {
+    fill_normal<T>(ctx, Y, nb * axd, expand_seed++, 1.0);
+  }
   auto project_out = [&](T* X, int64_t ncols) {   // X <- X - A (A^H X)
     gemm<T>(ctx, OP_C, OP_N, cur, ncols, nb, one, Ap.data(), nb, 0, X, nb, 0, zero, tmp, cur, 0, 1);
     gemm<T>(ctx, OP_N, OP_N, nb, ncols, cur, mone, Ap.data(), nb, 0, tmp, cur, 0, one, X, nb, 0, 1);
@@ -1082,21 +1255,56 @@ void Net<T>::extract(const int32_t* reg, int nreg, const nsb_trunc* trunc, const
 }
 
 template <typename T>
+DTensor<T> Net<T>::kvec_start() {
+  if (!krylov_sharded()) return clone(ctx, theta);
+  if (theta_is_slab) return clone(ctx, theta_slab);
+  return clone(ctx, theta.last_mode_slab(shard_lo, shard_hi));
+}
+template <typename T>
+void Net<T>::kdot(const DTensor<T>& a, const DTensor<T>& b, double* re_out, double* im_out) {
+  if (!krylov_sharded()) { vec_dot<T>(ctx, a.numel(), a.data(), b.data(), re_out, im_out); return; }
+  vec_dot_slot<T>(ctx, a.numel(), a.data(), b.data(), 0);
+  nccl_check(nccl_api().AllReduce(dot_slot_ptr(ctx, 0), dot_slot_ptr(ctx, 0), 2, ncclDouble, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream),
+             "ncclAllReduce(dot)");
+  double h[2];
+  dot_slots_fetch(ctx, 1, h);
+  if (re_out) *re_out = h[0];
+  if (im_out) *im_out = h[1];
+}
+template <typename T>
+double Net<T>::knrm2(const DTensor<T>& a) {
+  double r = 0.0;
+  kdot(a, a, &r, nullptr);
+  return std::sqrt(r > 0.0 ? r : 0.0);
+}
+template <typename T>
+void Net<T>::kstore_theta(const DTensor<T>& x) {
+  if (krylov_sharded()) { theta_slab = x; theta_is_slab = true; }
+  else { theta = x; theta_is_slab = false; }
+}
+template <typename T>
+const char* Net<T>::parallelism_note() const {
+  return "Krylov vectors sharded along theta's last bond (reduce-scatter / all-gather per H_eff application, scalar all-reduce per dot); "
+         "environment update split over the incoming environment's bra index + all-reduce; factorisation: Gram matrix, back-transformation "
+         "and C = U^H theta by column slabs + all-gather, tridiagonalisation and divide & conquer replicated; tensors replicated in HBM";
+}
+
+template <typename T>
 void Net<T>::update_eigsolve(const nsb_krylov* kp, double* eigval, nsb_solve_info* info) {
   NSB_REQUIRE(theta.valid() && !plan.empty(), NSB_EINVAL, "update_eigsolve: call nsb_extract first");
   nsb_krylov p = kp ? *kp : nsb_krylov{3, 1, 1e-14, 0, 0, 4, 0};
   NSB_REQUIRE(p.maxiter == 1, NSB_EUNSUPPORTED, "eigsolve: only maxiter == 1 (no restart) is implemented, as used by the reference");
   NSB_REQUIRE(p.krylovdim >= 1, NSB_EINVAL, "eigsolve: krylovdim must be >= 1");
-  const int64_t n = theta.numel();
-  const int kmax = (int)std::min<int64_t>(p.krylovdim, n);
+  const int kmax = (int)std::min<int64_t>(p.krylovdim, theta.numel());
   std::vector<DTensor<T>> V;
   std::vector<double> alphas, betas;
   double beta = 0.0, beta_prev = 0.0;
   int nmv = 0;
-  DTensor<T> v = clone(ctx, theta);
+  DTensor<T> v = kvec_start();      // full local tensor, or this rank's slab of it (multi-GPU)
+  const int64_t n = v.numel();
   {
     PhaseTimer pt(ctx, NSB_T_KRYLOV);
-    double nrm = vec_nrm2<T>(ctx, n, v.data());
+    double nrm = knrm2(v);
     NSB_REQUIRE(nrm > 0.0, NSB_EINVAL, "eigsolve: zero initial vector");
     vec_scale<T>(ctx, n, from_complex<T>(1.0 / nrm, 0.0), v.data());
   }
@@ -1105,27 +1313,37 @@ void Net<T>::update_eigsolve(const nsb_krylov* kp, double* eigval, nsb_solve_inf
     DTensor<T> w;
     {
       PhaseTimer pt(ctx, NSB_T_MATVEC);
-      w = apply_heff(v);
+      w = kapply(v);
       ++nmv;
     }
     PhaseTimer pt(ctx, NSB_T_KRYLOV);
     if (w.data() == v.data()) w = clone(ctx, w);
     double ar, ai;
-    vec_dot<T>(ctx, n, v.data(), w.data(), &ar, &ai);
+    kdot(v, w, &ar, &ai);
     double alpha = ar;
     vec_axpy<T>(ctx, n, from_complex<T>(-alpha, 0.0), v.data(), w.data());
     if (V.size() > 1) vec_axpy<T>(ctx, n, from_complex<T>(-beta_prev, 0.0), V[V.size() - 2].data(), w.data());
     // full re-orthogonalisation against the whole basis (second modified Gram-Schmidt pass)
     for (size_t i = 0; i < V.size(); ++i) {
       double cr, ci;
-      vec_dot<T>(ctx, n, V[i].data(), w.data(), &cr, &ci);
+      kdot(V[i], w, &cr, &ci);
       vec_axpy<T>(ctx, n, from_complex<T>(-cr, -ci), V[i].data(), w.data());
       if (i + 1 == V.size()) alpha += cr;
     }
     alphas.push_back(alpha);
-    beta = vec_nrm2<T>(ctx, n, w.data());
+    beta = knrm2(w);
     int K = (int)V.size();
-    if (K == kmax || beta <= p.tol || (p.eager && K >= 1)) break;
+    if (K == kmax || beta <= p.tol) break;
+    if (p.eager) {
+      // KrylovKit `eager`: test the wanted Ritz pair after every expansion and leave only when its residual
+      // |beta y_K| has converged; otherwise keep expanding up to krylovdim
+      std::vector<double> Te((size_t)K * K, 0.0), ev, evec;
+      for (int i = 0; i < K; ++i) Te[i + (size_t)i * K] = alphas[i];
+      for (int i = 0; i + 1 < K; ++i) { Te[i + (size_t)(i + 1) * K] = betas[i]; Te[(i + 1) + (size_t)i * K] = betas[i]; }
+      host_sym_eig(K, Te, ev, evec);
+      const int id = (p.which == 0) ? 0 : K - 1;
+      if (std::fabs(beta * evec[(K - 1) + (size_t)id * K]) <= p.tol) break;
+    }
     betas.push_back(beta);
     beta_prev = beta;
     vec_scale<T>(ctx, n, from_complex<T>(1.0 / beta, 0.0), w.data());
@@ -1141,9 +1359,9 @@ void Net<T>::update_eigsolve(const nsb_krylov* kp, double* eigval, nsb_solve_inf
   std::vector<const T*> ptrs(K);
   std::vector<T> coef(K);
   for (int i = 0; i < K; ++i) { ptrs[i] = V[i].data(); coef[i] = from_complex<T>(evecs[i + (size_t)idx * K], 0.0); }
-  DTensor<T> x(ctx, theta.dims, theta.labels);
+  DTensor<T> x(ctx, V[0].dims, V[0].labels);
   vec_lincomb<T>(ctx, n, K, ptrs.data(), coef.data(), x.data());
-  theta = x;
+  kstore_theta(x);
   if (eigval) *eigval = evals[idx];
   if (info) {
     info->nmatvec = nmv;
@@ -1168,7 +1386,7 @@ template <> struct CplxScalar<cdouble> {
 //   solver RK: src/local_solvers/runge_kutta.jl:2-25;  solver KRYLOV: KrylovKit.exponentiate (expintegrator, p = 1).
 template <typename T>
 DTensor<T> Net<T>::exp_solve(const std::function<DTensor<T>(const DTensor<T>&)>& Hraw, std::complex<double> t, const DTensor<T>& x0,
-                             int solver, const nsb_krylov* kp, int* nmv_out, int* lastK_out, int* conv_out, double* err_out) {
+                             int solver, const nsb_krylov* kp, int* nmv_out, int* lastK_out, int* conv_out, double* err_out, bool edge_local) {
   const int64_t n = x0.numel();
   typedef std::complex<double> C;
   auto S = [&](C z) { return CplxScalar<T>::make(z.real(), z.imag()); };
@@ -1224,7 +1442,7 @@ DTensor<T> Net<T>::exp_solve(const std::function<DTensor<T>(const DTensor<T>&)>&
       const int kmax = (int)std::min<int64_t>(p.krylovdim, n);
       bool done = false;
       while (!done) {
-        double beta = vec_nrm2<T>(ctx, n, w1.data());
+        double beta = edge_local ? vec_nrm2<T>(ctx, n, w1.data()) : knrm2(w1);
         if (beta < p.tol) { converged = 1; break; }
         std::vector<DTensor<T>> V;
         std::vector<double> alphas, betas;
@@ -1236,19 +1454,19 @@ DTensor<T> Net<T>::exp_solve(const std::function<DTensor<T>(const DTensor<T>&)>&
           DTensor<T> w = H(v);
           PhaseTimer pt(ctx, NSB_T_KRYLOV);
           double ar, ai;
-          vec_dot<T>(ctx, n, v.data(), w.data(), &ar, &ai);
+          if (edge_local) vec_dot<T>(ctx, n, v.data(), w.data(), &ar, &ai); else kdot(v, w, &ar, &ai);
           double a = ar;
           vec_axpy<T>(ctx, n, from_complex<T>(-a, 0.0), v.data(), w.data());
           if (V.size() > 1) vec_axpy<T>(ctx, n, from_complex<T>(-betas.back(), 0.0), V[V.size() - 2].data(), w.data());
           for (size_t i = 0; i < V.size(); ++i) {
             double cr, ci;
-            vec_dot<T>(ctx, n, V[i].data(), w.data(), &cr, &ci);
+            if (edge_local) vec_dot<T>(ctx, n, V[i].data(), w.data(), &cr, &ci); else kdot(V[i], w, &cr, &ci);
             vec_axpy<T>(ctx, n, from_complex<T>(-cr, -ci), V[i].data(), w.data());
             if (i + 1 == V.size()) a += cr;
           }
           alphas.push_back(a);
           r = w;
-          resnorm = vec_nrm2<T>(ctx, n, w.data());
+          resnorm = edge_local ? vec_nrm2<T>(ctx, n, w.data()) : knrm2(w);
         };
         expand();
         while (true) {
@@ -1338,8 +1556,12 @@ void Net<T>::update_exp(double tre, double tim, int solver, const nsb_krylov* kp
   int nmv = 0, lastK = 0, conv = 1;
   double err = 0.0;
   // forward step (src/applyexp.jl:28)
-  theta = exp_solve([&](const DTensor<T>& x) { return apply_heff(x); }, t, theta, solver, kp, &nmv, &lastK, &conv, &err);
+  {
+    DTensor<T> x0 = kvec_start();
+    kstore_theta(exp_solve([&](const DTensor<T>& x) { return kapply(x); }, t, x0, solver, kp, &nmv, &lastK, &conv, &err, false));
+  }
   if (nsites == 1 && next_vertex >= 0) {
+    ensure_theta_full();
     // src/applyexp.jl:30-42: QR-split the evolved site tensor toward the next region, move the projected
     // operator onto the edge (0-site H_eff = the two environments), evolve R backward by -t, recombine.
     NSB_REQUIRE(region.size() == 1, NSB_EINVAL, "update_exp: nsites == 1 needs a one-site region");
@@ -1401,7 +1623,7 @@ void Net<T>::update_exp(double tre, double tim, int solver, const nsb_krylov* kp
       ctx->cnt.matvecs++;
       return y;
     };
-    DTensor<T> Rt = exp_solve(Hedge, -t, R, solver, kp, &nmv, &lastK, &conv, &err);
+    DTensor<T> Rt = exp_solve(Hedge, -t, R, solver, kp, &nmv, &lastK, &conv, &err, true);   // replicated small problem on the edge
     // local_state = psi[v1] * R_t
     std::vector<Label> ql = order;
     ql.back() = ax;
@@ -1416,6 +1638,7 @@ void Net<T>::update_exp(double tre, double tim, int solver, const nsb_krylov* kp
 template <typename T>
 void Net<T>::insert(const nsb_trunc* trunc, int normalize, int set_ortho, nsb_insert_info* info) {
   NSB_REQUIRE(theta.valid() && !region.empty(), NSB_EINVAL, "insert: call nsb_extract first");
+  ensure_theta_full();
   nsb_trunc tr = trunc ? *trunc : nsb_trunc{0.0, 1, INT64_MAX};
   nsb_insert_info out{0, 0.0, 0, 0};
   int last = region.back();
@@ -1473,15 +1696,31 @@ void Net<T>::insert(const nsb_trunc* trunc, int normalize, int set_ortho, nsb_in
       fi = factorize_qn(M.data(), rows, cols, rk, ck, tr.cutoff, tr.mindim, tr.maxdim, false, Ub, Cb, newk);
       qn_store_link(v1, v2, newk);
     } else {
-      fi = factorize_left<T>(ctx, M.data(), rows, cols, trans ? cols : rows, trans, tr.cutoff, tr.mindim, tr.maxdim, false, Ub, Cb, spec);
+      FactorDist dist;
+      const bool use_dist = shard_enabled && ctx->nranks > 1 && ctx->nccl_comm;
+      if (use_dist) {
+        dist.rank = ctx->rank; dist.nranks = ctx->nranks; dist.allow_c_transposed = true;
+        dist.allgather_inplace = [this](void* buf, size_t bytes) {
+          nccl_check(nccl_api().AllGather((const char*)buf + bytes * (size_t)ctx->rank, buf, bytes / sizeof(double), ncclDouble,
+                                          (ncclComm_t)ctx->nccl_comm, ctx->stream), "ncclAllGather(factorize)");
+          ctx->cnt.kernel_launches++;
+        };
+      }
+      fi = factorize_left<T>(ctx, M.data(), rows, cols, trans ? cols : rows, trans, tr.cutoff, tr.mindim, tr.maxdim, false, Ub, Cb, spec,
+                             use_dist ? &dist : nullptr);
     }
     int64_t k = fi.newdim;
     std::vector<int64_t> ud, cd;
     std::vector<Label> ul = left, cl;
     for (Label l : left) ud.push_back(theta.dim_of(l));
     ud.push_back(k); ul.push_back(bond);
-    cd.push_back(k); cl.push_back(bond);
-    for (Label l : right) { cd.push_back(theta.dim_of(l)); cl.push_back(l); }
+    if (fi.c_transposed) {        // C^T: [right..., bond]
+      for (Label l : right) { cd.push_back(theta.dim_of(l)); cl.push_back(l); }
+      cd.push_back(k); cl.push_back(bond);
+    } else {
+      cd.push_back(k); cl.push_back(bond);
+      for (Label l : right) { cd.push_back(theta.dim_of(l)); cl.push_back(l); }
+    }
     DTensor<T> Ut, Ct;
     Ut.buf = std::make_shared<DevBuf>(std::move(Ub)); Ut.dims = ud; Ut.labels = ul;
     Ct.buf = std::make_shared<DevBuf>(std::move(Cb)); Ct.dims = cd; Ct.labels = cl;
@@ -1514,12 +1753,14 @@ void Net<T>::local_info(int32_t* rank, int32_t* legs, int64_t* dims) {
 template <typename T>
 void Net<T>::local_download(void* host) {
   NSB_REQUIRE(theta.valid(), NSB_EINVAL, "local_download: no local tensor");
+  ensure_theta_full();
   NSB_CUDA(cudaMemcpyAsync(host, theta.data(), sizeof(T) * theta.numel(), cudaMemcpyDeviceToHost, ctx->stream));
   ctx->sync();
 }
 template <typename T>
 void Net<T>::local_upload(const void* host) {
   NSB_REQUIRE(theta.valid(), NSB_EINVAL, "local_upload: no local tensor");
+  theta_is_slab = false;
   NSB_CUDA(cudaMemcpyAsync(theta.data(), host, sizeof(T) * theta.numel(), cudaMemcpyHostToDevice, ctx->stream));
   ctx->sync();
 }
@@ -1535,7 +1776,19 @@ void Net<T>::matvec_host(const void* in, void* outp) {
 template <typename T>
 void Net<T>::matvec_device(int reps, void* host_out) {
   NSB_REQUIRE(theta.valid() && !plan.empty(), NSB_EINVAL, "matvec: call nsb_extract first");
-  for (int i = 0; i < reps; ++i) last_out = apply_heff(theta);
+  if (krylov_sharded()) {   // what the sharded Krylov solvers do: slab in, slab out
+    DTensor<T> xs = theta_is_slab ? theta_slab : theta.last_mode_slab(shard_lo, shard_hi), os;
+    for (int i = 0; i < reps; ++i) os = apply_heff_slab(xs);
+    if (host_out && os.valid()) {
+      last_out = DTensor<T>(ctx, theta.dims, theta.labels);
+      comm_allgather(os.data(), last_out.data(), os.numel());
+    } else {
+      last_out = os;
+      host_out = nullptr;
+    }
+  } else {
+    for (int i = 0; i < reps; ++i) last_out = apply_heff(theta);
+  }
   if (host_out && last_out.valid()) {
     NSB_CUDA(cudaMemcpyAsync(host_out, last_out.data(), sizeof(T) * last_out.numel(), cudaMemcpyDeviceToHost, ctx->stream));
     ctx->sync();
@@ -1545,6 +1798,40 @@ template <typename T>
 double Net<T>::norm() {
   NSB_REQUIRE(ortho.size() == 1, NSB_EINVAL, "norm: needs a single-vertex orthogonality centre");
   return vec_nrm2<T>(ctx, psi[ortho[0]].numel(), psi[ortho[0]].data());
+}
+
+// range_finder(linear_map, random_vector) with linear_map = x -> optimal_map(P, x) at the current position
+// (src/sketched_linear_algebra/range_finder.jl:54-64 over the closure of src/eigsolve.jl:22)
+template <typename T>
+int64_t Net<T>::range_finder_heff(const void* probes_host, uint64_t seed, int64_t max_rank, int oversample, int north_pass, double thr,
+                                  double cutoff, void* Qhost) {
+  NSB_REQUIRE(theta.valid() && !plan.empty(), NSB_EINVAL, "range_finder: call nsb_extract first");
+  if (max_rank <= 0) return 0;
+  const int64_t n = theta.numel();
+  const int64_t sketch = std::min(std::min(max_rank, n) + (int64_t)oversample, n);
+  DevBuf dQ(ctx, sizeof(T) * (size_t)n * sketch), dP(ctx, probes_host ? sizeof(T) * (size_t)n * sketch : 0);
+  if (probes_host) NSB_CUDA(cudaMemcpyAsync(dP.ptr, probes_host, sizeof(T) * (size_t)n * sketch, cudaMemcpyHostToDevice, ctx->stream));
+  RangeMap<T> map = [&](const T* Om, T* Y, int64_t p) {
+    for (int64_t j = 0; j < p; ++j) {
+      DTensor<T> x(ctx, theta.dims, theta.labels);
+      vec_copy<T>(ctx, n, Om + j * n, x.data());
+      DTensor<T> y = apply_heff(x);
+      vec_copy<T>(ctx, n, y.data(), Y + j * n);
+    }
+  };
+  const int64_t have = range_finder_blocked<T>(ctx, n, n, map, probes_host ? (const T*)dP.ptr : nullptr, seed, max_rank, oversample, north_pass,
+                                               thr, cutoff, (T*)dQ.ptr);
+  if (have > 0) NSB_CUDA(cudaMemcpyAsync(Qhost, dQ.ptr, sizeof(T) * (size_t)n * have, cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->sync();
+  return have;
+}
+
+template <typename T>
+void Net<T>::expand_set_probe(int64_t rows, int64_t cols, const void* host) {
+  expand_probe = DevBuf(ctx, sizeof(T) * (size_t)rows * cols);
+  NSB_CUDA(cudaMemcpyAsync(expand_probe.ptr, host, sizeof(T) * (size_t)rows * cols, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->sync();
+  expand_probe_rows = rows; expand_probe_cols = cols;
 }
 
 template struct Net<double>;

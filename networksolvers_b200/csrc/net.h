@@ -11,9 +11,6 @@
 
 namespace nsb {
 
-extern int g_merge_site_ops;
-extern int g_skip_identity_sharded;
-extern int g_skip_identity;   // skip the identity channel of the first / last environment of an H_eff application
 
 struct NetBase {
   Ctx* ctx = nullptr;
@@ -38,12 +35,16 @@ struct NetBase {
   virtual double update_fit() = 0;
   virtual void local_info(int32_t* rank, int32_t* legs, int64_t* dims) = 0;
   virtual void local_download(void* host) = 0;
+  virtual void local_sync() = 0;   // multi-GPU: complete a sharded local tensor on every rank (collective)
   virtual void local_upload(const void* host) = 0;
   virtual void matvec_host(const void* in, void* out) = 0;
   virtual void matvec_device(int reps, void* host_out) = 0;
   virtual double matvec_flops() = 0;
   virtual double matvec_flops_executed() = 0;
   virtual double norm() = 0;
+  virtual int64_t range_finder_heff(const void* probes_host, uint64_t seed, int64_t max_rank, int oversample, int north_pass, double thr,
+                                    double cutoff, void* Qhost) = 0;
+  virtual void expand_set_probe(int64_t rows, int64_t cols, const void* host) = 0;
   virtual int set_shard(int enable) = 0;   // returns 1 if the current position is sharded across ranks
   // abelian quantum numbers (dense storage, block-wise factorisations)
   virtual void qn_enable(int nq, const int32_t* total) = 0;
@@ -81,14 +82,35 @@ struct Net : public NetBase {
   int first_ident = -1;
   DTensor<T> first_compact;
   void prepare_identity_skip();
-  bool skip_first_identity(DTensor<T>& X);
+  bool skip_first_identity(DTensor<T>& X, int64_t bra_lo = 0, int64_t bra_hi = 0, const DTensor<T>* Xs = nullptr);
+  DTensor<T> run_plan_steps(DTensor<T> X, size_t i0, size_t i1);
+  DTensor<T> last_env_contract(const DTensor<T>& X, double* skipped);
   double skipped_flops(const DTensor<T>& x) const;   // real flops per application the skipping saves (dry run)
   double skipped_last_apply = -1.0;                  // what the last apply_heff actually skipped (< 0: none ran yet)
   // multi-GPU: theta sharded along its last bond across the ranks of ctx->nccl_comm
   bool shard_enabled = false, shard_active = false;
+  int shard_mode = 0;                           // 0 none, 1 RS (reduce-scatter), 2 AG (all-gather), 3 AR (all-reduce of full vectors)
   int64_t shard_lo = 0, shard_hi = 0;
-  DTensor<T> shard_env;                         // rows [shard_lo, shard_hi) of the last environment
+  DTensor<T> shard_env;                         // rows [shard_lo, shard_hi) of the last environment (RS / AR positions)
+  bool theta_is_slab = false;                   // the local tensor currently lives as this rank's slab (after a sharded update)
+  DTensor<T> theta_slab;
   void shard_prepare();
+  void ensure_theta_full();
+  bool krylov_sharded() const { return shard_active && (shard_mode == 1 || shard_mode == 2); }
+  DTensor<T> apply_heff_slab(const DTensor<T>& xs);
+  DTensor<T> heff_partial_from_slab(const DTensor<T>& xs, double* skipped);
+  bool slab_of(const DTensor<T>& t, Label l, int64_t lo, int64_t hi, DTensor<T>* out);
+  void nccl_check(int r, const char* what);
+  void comm_allreduce(T* buf, int64_t n);
+  void comm_allgather(const T* send, T* recv, int64_t n_per_rank);
+  void comm_reduce_scatter(const T* send, T* recv, int64_t n_per_rank);
+  // Krylov vector algebra on full vectors or on slabs (partial sums + all-reduce of the scalars)
+  DTensor<T> kvec_start();
+  DTensor<T> kapply(const DTensor<T>& v) { return krylov_sharded() ? apply_heff_slab(v) : apply_heff(v); }
+  void kdot(const DTensor<T>& a, const DTensor<T>& b, double* re_out, double* im_out);
+  double knrm2(const DTensor<T>& a);
+  void kstore_theta(const DTensor<T>& x);
+  const char* parallelism_note() const;
   // QN bookkeeping: every basis state of a link carries the charge of the subtree on the side of qn_side[e]
   bool qn_on = false;
   int nq = 0;
@@ -142,7 +164,7 @@ struct Net : public NetBase {
   bool expand_ortho(const nsb_trunc& trunc, const nsb_expand& ex);
   uint64_t expand_seed = 0x5eed0001ull;       // Philox stream of the random "ortho" expansion (advanced per call)
   DTensor<T> exp_solve(const std::function<DTensor<T>(const DTensor<T>&)>& H, std::complex<double> t, const DTensor<T>& x0,
-                       int solver, const nsb_krylov* kp, int* nmv, int* lastK, int* conv, double* err);
+                       int solver, const nsb_krylov* kp, int* nmv, int* lastK, int* conv, double* err, bool edge_local);
 
   // NetBase
   void site_upload(int v, int rank, const int32_t* legs, const int64_t* dims, const void* host) override;
@@ -164,12 +186,18 @@ struct Net : public NetBase {
   double update_fit() override;
   void local_info(int32_t* rank, int32_t* legs, int64_t* dims) override;
   void local_download(void* host) override;
+  void local_sync() override { ensure_theta_full(); }
   void local_upload(const void* host) override;
   void matvec_host(const void* in, void* out) override;
   void matvec_device(int reps, void* host_out) override;
   double matvec_flops() override;
   double matvec_flops_executed() override;
   double norm() override;
+  int64_t range_finder_heff(const void* probes_host, uint64_t seed, int64_t max_rank, int oversample, int north_pass, double thr, double cutoff,
+                            void* Qhost) override;
+  void expand_set_probe(int64_t rows, int64_t cols, const void* host) override;
+  DevBuf expand_probe;                       // one-shot caller-supplied random tensor of the "ortho" expansion
+  int64_t expand_probe_rows = 0, expand_probe_cols = 0;
   int set_shard(int enable) override;
   void qn_enable(int nq, const int32_t* total) override;
   void qn_set_site(int v, const int32_t* charges) override;

@@ -181,6 +181,14 @@ static void fetch_slots(Ctx* ctx, int nslots) {
 }
 
 template <typename T>
+void vec_dot_slot(Ctx* ctx, int64_t n, const T* x, const T* y, int slot) { dot_async<T>(ctx, n, x, y, slot); }
+double* dot_slot_ptr(Ctx* ctx, int slot) { return ctx->d_scratch + 2 * slot; }
+void dot_slots_fetch(Ctx* ctx, int nslots, double* out_host) {
+  fetch_slots(ctx, nslots);
+  for (int i = 0; i < 2 * nslots; ++i) out_host[i] = ctx->h_pinned[i];
+}
+
+template <typename T>
 void vec_dot(Ctx* ctx, int64_t n, const T* x, const T* y, double* re_out, double* im_out) {
   dot_async<T>(ctx, n, x, y, 0);
   fetch_slots(ctx, 1);
@@ -526,6 +534,7 @@ void col_norms2(Ctx* ctx, const T* A, int64_t rows, int64_t cols, int64_t ld, do
   template void identity_deviation<T>(Ctx*, const T*, int64_t, int64_t, double*);                                      \
   template void insert_mode<T>(Ctx*, const T*, const T*, T*, int64_t, int64_t, int64_t, int64_t);                      \
   template void fill_normal<T>(Ctx*, T*, int64_t, uint64_t, double);                                                   \
+  template void vec_dot_slot<T>(Ctx*, int64_t, const T*, const T*, int);                                               \
   template void set_identity<T>(Ctx*, T*, int64_t, int64_t, int64_t);                                                  \
   template void sum_slabs<T>(Ctx*, const T*, int, int64_t, T*);                                                        \
   template void col_norms2<T>(Ctx*, const T*, int64_t, int64_t, int64_t, double*);

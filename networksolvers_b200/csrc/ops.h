@@ -23,6 +23,11 @@ void small_apply(Ctx* ctx, const T* X, T* out, const T* W, int nbig, const int64
 // ---- vector algebra (device-resident scalars avoided: results come back to the host, one sync) ----
 template <typename T> void vec_dot(Ctx* ctx, int64_t n, const T* x, const T* y, double* re_out, double* im_out);  // <x|y>
 template <typename T> double vec_nrm2(Ctx* ctx, int64_t n, const T* x);
+// asynchronous form: <x|y> lands in device slot `slot` (2 doubles at dot_slot_ptr); a collective may sum the slots over the
+// ranks before dot_slots_fetch brings the first nslots back (one stream synchronisation)
+template <typename T> void vec_dot_slot(Ctx* ctx, int64_t n, const T* x, const T* y, int slot);
+double* dot_slot_ptr(Ctx* ctx, int slot);
+void dot_slots_fetch(Ctx* ctx, int nslots, double* out_host /* 2 * nslots */);
 template <typename T> void vec_axpy(Ctx* ctx, int64_t n, T a, const T* x, T* y);                  // y += a x
 template <typename T> void vec_scale(Ctx* ctx, int64_t n, T a, T* x);                             // x *= a
 template <typename T> void vec_copy(Ctx* ctx, int64_t n, const T* x, T* y);

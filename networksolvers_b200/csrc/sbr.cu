@@ -20,7 +20,6 @@
 
 namespace nsb {
 
-int g_sbr_staged = 0;
 
 namespace {
 
@@ -99,7 +98,7 @@ void sbr_chase_device(Ctx* ctx, int64_t n, int b, double* ab, int64_t ld, double
   NSB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
   // g_sbr_staged (ctx option "sbr_staged", default 0): the shared-memory form of the task (validated on the CPU, not yet run
   // on hardware); 0: the element-wise form (validated on a B200, slow)
-  const bool staged = g_sbr_staged != 0;
+  const bool staged = ctx->opt.sbr_staged != 0;
   const size_t smem = staged ? sizeof(double) * 3 * (size_t)b * b : 0;
   void* kern = staged ? (void*)sbr_chase_kernel<true> : (void*)sbr_chase_kernel<false>;
   if (staged) NSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -73,6 +73,19 @@ class Context:
         self.check(self._lib.nsb_mem_info(self.handle, C.byref(f), C.byref(t), C.byref(u)))
         return dict(free=f.value, total=t.value, pool_used=u.value)
 
+    def gemm_profile(self, on=True):
+        """Start (and clear) / stop the per-launch CUDA-event timing of the GEMM kernels."""
+        self.check(self._lib.nsb_gemm_profile_enable(self.handle, 1 if on else 0))
+
+    def gemm_profile_read(self):
+        """[(ms, flops, (M, N, K, batch)), ...] of the GEMM launches since gemm_profile(True)."""
+        n = C.c_int64()
+        self.check(self._lib.nsb_gemm_profile_read(self.handle, 0, None, None, None, C.byref(n)))
+        cap = max(n.value, 1)
+        ms, fl, mnk = (C.c_double * cap)(), (C.c_double * cap)(), (C.c_int64 * (4 * cap))()
+        self.check(self._lib.nsb_gemm_profile_read(self.handle, cap, ms, fl, mnk, C.byref(n)))
+        return [(ms[i], fl[i], tuple(mnk[4 * i: 4 * i + 4])) for i in range(n.value)]
+
     # ---- dense helpers (kernels under the hooks, exposed for tests / benchmarks) ----
     @staticmethod
     def _dt(a):
@@ -159,7 +172,15 @@ class Context:
         self.check(self._lib.nsb_qr_host(self.handle, self._dt(Mf), rows, cols, Mf.ctypes.data, Q.ctypes.data, R.ctypes.data))
         return Q, R
 
-    def range_finder(self, A, max_rank, oversample=2, north_pass=2, orthogonal_threshold=1e-12, seed=1):
+    def qr_bench(self, rows, cols, dtype=np.float64, reps=3):
+        ms = C.c_double()
+        dt = L.NSB_C128 if np.dtype(dtype).kind == "c" else L.NSB_F64
+        self.check(self._lib.nsb_qr_bench(self.handle, dt, rows, cols, reps, C.byref(ms)))
+        return ms.value
+
+    def range_finder(self, A, max_rank, oversample=2, north_pass=2, orthogonal_threshold=1e-12, cutoff=0.0, seed=1, probes=None):
+        """Orthonormal basis of the range of the matrix A from random probes (range_finder.jl:54-64 with
+        linear_map = A).  probes: (n, sketch) array whose column k is the k-th random_vector(), or None (device Philox)."""
         cplx = np.iscomplexobj(A)
         dt = np.complex128 if cplx else np.float64
         Af = np.asfortranarray(A, dtype=dt)
@@ -167,8 +188,13 @@ class Context:
         cap = min(max_rank + oversample, m, n)
         Q = np.empty((m, max(cap, 1)), dtype=dt, order="F")
         rank = C.c_int64()
-        self.check(self._lib.nsb_range_finder_host(self.handle, self._dt(Af), m, n, Af.ctypes.data, max_rank, oversample,
-                                                    north_pass, orthogonal_threshold, seed, Q.ctypes.data, C.byref(rank)))
+        pr = None
+        if probes is not None:
+            pr = np.asfortranarray(probes, dtype=dt)
+            assert pr.shape[0] == n and pr.shape[1] >= cap, (pr.shape, n, cap)
+        self.check(self._lib.nsb_range_finder_host(self.handle, self._dt(Af), m, n, Af.ctypes.data,
+                                                    pr.ctypes.data if pr is not None else None, max_rank, oversample,
+                                                    north_pass, orthogonal_threshold, cutoff, seed, Q.ctypes.data, C.byref(rank)))
         return Q[:, : rank.value]
 
 
@@ -448,6 +474,27 @@ class DeviceNetwork:
             out = np.empty(dims, dtype=self.dtype, order="F")
         self.ctx.check(self._lib.nsb_matvec_device(self.handle, reps, out.ctypes.data if out is not None else None))
         return out
+
+    def range_finder(self, max_rank, oversample=2, north_pass=2, orthogonal_threshold=1e-12, cutoff=0.0, seed=1, probes=None):
+        """range_finder(linear_map, random_vector) with linear_map = the projected operator at the current position
+        (psi -> optimal_map(P, psi)); returns the basis as an array [local dims..., rank]."""
+        _, dims = self.local_info()
+        n = int(np.prod(dims))
+        cap = min(max_rank + oversample, n)
+        Q = np.empty((n, max(cap, 1)), dtype=self.dtype, order="F")
+        rank = C.c_int64()
+        pr = None
+        if probes is not None:
+            pr = np.asfortranarray(np.reshape(probes, (n, -1), order="F"), dtype=self.dtype)
+            assert pr.shape[1] >= cap
+        self.ctx.check(self._lib.nsb_range_finder_heff(self.handle, pr.ctypes.data if pr is not None else None, seed, max_rank,
+                                                        oversample, north_pass, orthogonal_threshold, cutoff, Q.ctypes.data, C.byref(rank)))
+        return Q[:, : rank.value].reshape(list(dims) + [rank.value], order="F")
+
+    def set_expand_probe(self, probe):
+        """One-shot random tensor (basis size x expand_space) for the next "ortho" expansion (instead of device Philox)."""
+        a = np.asfortranarray(probe, dtype=self.dtype)
+        self.ctx.check(self._lib.nsb_expand_set_probe(self.handle, a.shape[0], a.shape[1], a.ctypes.data))
 
     def matvec_flops(self):
         f = C.c_double()

@@ -49,8 +49,17 @@ def lanczos_eigsolve(operator, init: Tensor, *, krylovdim=3, maxiter=1, tol=1e-1
         alphas.append(float(np.real(alpha)))
         beta = w.norm()
         K = len(V)
-        if K == kmax or beta <= tol or (eager and K >= 1):
+        if K == kmax or beta <= tol:
             break
+        if eager:
+            # KrylovKit: `eager && K >= howmany` only triggers an early Ritz / convergence test; the loop is
+            # left when the wanted Ritz pair's residual |beta y_K| <= tol, otherwise the basis keeps growing
+            Te = np.diag(alphas)
+            for i, b in enumerate(betas[: K - 1]):
+                Te[i, i + 1] = Te[i + 1, i] = b
+            _, ve = np.linalg.eigh(Te)
+            if abs(beta * ve[-1, 0 if which == "SR" else K - 1]) <= tol:
+                break
         betas.append(beta)
         beta_prev = beta
         v = w / beta

@@ -23,7 +23,7 @@ def main():
     from oracle.graph import path_graph
     from oracle.tensor import Tensor, site, link, oplink, contract, noprime
     rng = np.random.default_rng(42)          # same data on every rank (replicated state)
-    chi, d, w = 13, 2, 5
+    chi, d, w = int(os.environ.get("NSB_TEST_CHI", "13")), 2, 5
     g = path_graph(4)
     Wt = {v: Tensor(rng.standard_normal((w, w, d, d)), [oplink(v - 1, v), oplink(v, v + 1), site(v, 0), site(v, 1)]) for v in (2, 3)}
     P = ProjTTN(TTN(g, {1: None, 2: Wt[2], 3: Wt[3], 4: None}, ortho_region=[]), pos=[2, 3])
@@ -50,6 +50,19 @@ def main():
     ref = t.clone()
     dist.broadcast(ref, src=0)
     assert torch.equal(t, ref)
+    # AG form (regions swept to the left: the FIRST environment contracts theta's last bond): all-gather the input slabs,
+    # split the first contraction along the environment's bra index -- the result is this rank's slab, no reduction.
+    # Roles mirrored: Renv is contracted first (over theta's last bond), Lenv last.
+    slabs = [torch.zeros(theta.data[..., 0:(hi - lo)].shape, dtype=torch.float64) for _ in range(world)] if chi % world == 0 else None
+    if slabs is not None:
+        dist.all_gather(slabs, torch.from_numpy(np.ascontiguousarray(theta.data[..., lo:hi])))
+        th_full = Tensor(np.concatenate([t.numpy() for t in slabs], axis=-1), theta.labels)
+        assert np.array_equal(th_full.data, theta.data)
+        R_cols = Tensor(Renv.data[:, :, lo:hi], Renv.labels)
+        Y = contract(contract(contract(contract(th_full, R_cols), Wt[3]), Wt[2]), Lenv)
+        out_slab = noprime(Y).array(theta.labels)
+        err2 = np.abs(out_slab - full[..., lo:hi]).max() / np.abs(full).max()
+        assert err2 < 1e-13, err2
     if rank == 0:
         print("GLOO_SHARD_OK", world, err)
     dist.destroy_process_group()

@@ -45,6 +45,46 @@ def main():
         t0 = t.clone()
         dist.broadcast(t0, src=0)
         assert torch.equal(t, t0), "ranks diverged"
+    # ---- whole region steps in both sweep directions, every phase sharded (Krylov vectors as slabs with reduce-scatter /
+    # all-gather applications, environment update split + all-reduce, factorisation by column slabs + all-gather) against
+    # the same steps on one GPU.  eigh_min_n is lowered so that the Gram + eigh route (the one that is split) runs at this size.
+    ctx.set_option("eigh_min_n", 128)
+    try:
+        for cplx in (False, True):
+            g = ns.path_graph(16)
+            sites = ns.siteinds("S=1/2", g)
+            H = ns.ttno(ns.heisenberg(g), sites)
+            psi = ns.random_state(sites, 128, seed=5, dtype=complex if cplx else float)
+            nets = [ns.EigsolveProblem(state=psi, operator=H, ctx=ctx).net for _ in range(2)]
+            for n_ in nets:
+                n_.extract([8, 9])
+            sh = setup_sharded_matvec(nets[1], dist, rank, world, fused=False, init=False)
+            assert sh.active
+            regions = [[8, 9], [9, 10], [10, 11], [11, 10], [10, 9], [9, 8]]
+            for reg in regions:
+                res = []
+                for n_ in nets:
+                    n_.extract(reg)
+                    th, _ = n_.local_download()
+                    hv = n_.matvec_host(th)
+                    val, info = n_.update_eigsolve()
+                    th2, _ = n_.local_download()
+                    ins = n_.insert((1e-12, 1, 128))
+                    res.append((th, hv, val, th2, ins.newdim, ins.truncerr, info.nmatvec))
+                a, b = res
+                # gauge-invariant comparisons (the two factorisation routes may differ by signs of basis vectors)
+                ea, eb = np.vdot(a[0], a[1]).real / np.vdot(a[0], a[0]).real, np.vdot(b[0], b[1]).real / np.vdot(b[0], b[0]).real
+                assert abs(ea - eb) <= 1e-11 * max(1.0, abs(ea)), (reg, "energy expectation", ea, eb)
+                assert abs(np.linalg.norm(a[0]) - np.linalg.norm(b[0])) <= 1e-11 * np.linalg.norm(a[0]), (reg, "theta norm")
+                assert abs(a[2] - b[2]) <= 1e-11 * max(1.0, abs(a[2])), (reg, a[2], b[2])
+                assert abs(np.linalg.norm(a[3]) - 1.0) <= 1e-12 and abs(np.linalg.norm(b[3]) - 1.0) <= 1e-12
+                assert a[4] == b[4] and abs(a[5] - b[5]) <= 1e-10 and a[6] == b[6] == 3, (reg, a[4:], b[4:])
+            t = torch.tensor([res[1][2], res[1][5]], dtype=torch.float64, device="cuda")
+            t0 = t.clone()
+            dist.broadcast(t0, src=0)
+            assert torch.equal(t, t0), "ranks diverged"
+    finally:
+        ctx.set_option("eigh_min_n", 1024)
     if rank == 0:
         print("NCCL_SHARD_OK", world)
     dist.barrier()

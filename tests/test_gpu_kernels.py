@@ -71,6 +71,24 @@ def test_qr(ctx, cplx, shape):
     assert np.abs(np.tril(R, -1)).max() == 0.0
 
 
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("shape", [(2048, 1024), (300, 200), (200, 300), (1024, 512), (130, 64), (777, 333)])
+def test_qr_blocked_compact_wy(ctx, cplx, shape):
+    """Blocked Householder QR (one launch per panel column + compact-WY GEMM updates): same contract as LAPACK geqrf/orgqr
+    up to the sign convention -- Q orthonormal, R upper triangular, Q R = M -- at 512-thread (rows >= 2048) and 256-thread
+    panel kernels, tall, wide and ragged panel counts; rank-deficient input with exactly zero columns."""
+    rng = np.random.default_rng(23)
+    M = _rand(rng, shape, cplx)
+    M[:, 5] = 0.0                       # zero column: trivial reflector inside a panel
+    M[:, min(70, shape[1] - 1)] = M[:, 3]     # linearly dependent column (second panel when there is one)
+    Q, R = ctx.qr(M)
+    k = min(shape)
+    assert Q.shape == (shape[0], k) and R.shape == (k, shape[1])
+    assert np.abs(Q.conj().T @ Q - np.eye(k)).max() < 5e-13
+    assert np.abs(Q @ R - M).max() < 1e-11
+    assert np.abs(np.tril(R, -1)).max() == 0.0
+
+
 def test_qr_rank_deficient(ctx):
     rng = np.random.default_rng(5)
     M = rng.standard_normal((30, 4)) @ rng.standard_normal((4, 12))
