@@ -209,6 +209,9 @@ int nsb_qn_enable(nsb_net* net, int32_t nq /* 1..4 */, const int32_t* total_char
 int nsb_qn_set_site(nsb_net* net, int32_t v, const int32_t* charges /* site_dim x nq, state-major */);
 int nsb_qn_set_link(nsb_net* net, int32_t u, int32_t v, const int32_t* charges /* linkdim x nq: subtree on u's side */);
 int nsb_qn_get_link(nsb_net* net, int32_t u, int32_t v, int32_t* charges_out /* linkdim x nq: subtree on u's side */);
+/* zero every entry of the site tensor of v that charge conservation forbids (after nsb_site_fill_random + nsb_qn_set_link:
+ * a random symmetric tensor; synthetic QN states of the benchmarks) */
+int nsb_qn_project(nsb_net* net, int32_t v);
 
 /* ---- the three hooks ---------------------------------------------------------------------- */
 int nsb_extract(nsb_net* net, const int32_t* region, int32_t nreg, const nsb_trunc* trunc /* extracter's */,

@@ -132,6 +132,7 @@ SIGNATURES = {
     "nsb_qn_set_site": (C.c_int, [_vp, _i32, P(_i32)]),
     "nsb_qn_set_link": (C.c_int, [_vp, _i32, _i32, P(_i32)]),
     "nsb_qn_get_link": (C.c_int, [_vp, _i32, _i32, P(_i32)]),
+    "nsb_qn_project": (C.c_int, [_vp, _i32]),
     "nsb_extract": (C.c_int, [_vp, P(_i32), _i32, P(Trunc), P(Expand), P(ExtractInfo)]),
     "nsb_update_eigsolve": (C.c_int, [_vp, P(Krylov), P(_dbl), P(SolveInfo)]),
     "nsb_update_exp": (C.c_int, [_vp, _dbl, _dbl, _i32, P(Krylov), _i32, _i32, P(SolveInfo)]),

@@ -47,6 +47,28 @@ void Ctx::free(void* p, size_t bytes) {
   }
   cudaFreeAsync(p, stream);
 }
+Ctx* Ctx::helper(int i) {
+  while ((int)helpers.size() <= i) {
+    std::unique_ptr<Ctx> h(new Ctx());
+    h->device = device; h->pool = pool; h->num_sms = num_sms; h->smem_optin = smem_optin; h->is_helper = true;
+    h->gemm_impl = gemm_impl; h->opt = opt;
+    NSB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    NSB_CUDA(cudaMalloc(&h->d_scratch, sizeof(double) * Ctx::SCRATCH_DOUBLES));
+    NSB_CUDA(cudaMallocHost(&h->h_pinned, sizeof(double) * Ctx::SCRATCH_DOUBLES));
+    helpers.push_back(std::move(h));
+  }
+  Ctx* h = helpers[i].get();
+  h->opt = opt; h->gemm_impl = gemm_impl;
+  return h;
+}
+Ctx::~Ctx() {
+  if (!is_helper) return;
+  flush_big_cache();
+  cudaStreamSynchronize(stream);
+  if (d_scratch) cudaFree(d_scratch);
+  if (h_pinned) cudaFreeHost(h_pinned);
+  cudaStreamDestroy(stream);
+}
 void Ctx::flush_big_cache() {
   for (auto& kv : big_cache) cudaFreeAsync(kv.second, stream);
   big_cache.clear();
@@ -141,6 +163,7 @@ int nsb_ctx_destroy(nsb_ctx* ctx) {
 static void ctx_really_destroy(nsb_ctx* ctx) {
   cudaSetDevice(ctx->c.device);
   if (ctx->c.nccl_comm) { try { nccl_api().CommDestroy((ncclComm_t)ctx->c.nccl_comm); } catch (...) {} ctx->c.nccl_comm = nullptr; }
+  ctx->c.helpers.clear();
   ctx->c.flush_big_cache();
   cudaStreamSynchronize(ctx->c.stream);
   for (auto& g : ctx->c.gemm_prof) { cudaEventDestroy(g.e0); cudaEventDestroy(g.e1); }
@@ -433,6 +456,7 @@ int nsb_qn_set_link(nsb_net* net, int32_t u, int32_t v, const int32_t* charges) 
 int nsb_qn_get_link(nsb_net* net, int32_t u, int32_t v, int32_t* charges_out) {
   NET_CALL(net, NSB_REQUIRE(charges_out, NSB_EINVAL, "null"); net->n->qn_get_link(u, v, charges_out))
 }
+int nsb_qn_project(nsb_net* net, int32_t v) { NET_CALL(net, net->n->qn_project(v)) }
 int nsb_norm(nsb_net* net, double* out) { NET_CALL(net, NSB_REQUIRE(out, NSB_EINVAL, "null"); *out = net->n->norm()) }
 
 #pragma GCC visibility pop

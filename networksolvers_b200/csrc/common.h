@@ -148,6 +148,15 @@ struct Ctx {
   size_t big_cached_bytes = 0;
   size_t big_cache_cap = 24ull << 30;
   static constexpr size_t BIG_MIN = 32ull << 20;
+  // helper contexts on the same device (own stream, scratch and block cache): independent small factorisations -- the symmetry
+  // sectors of a QN tensor -- run concurrently, one host thread per helper
+  std::vector<std::unique_ptr<Ctx>> helpers;
+  Ctx* helper(int i);
+  ~Ctx();
+  Ctx() = default;
+  Ctx(const Ctx&) = delete;
+  Ctx& operator=(const Ctx&) = delete;
+  bool is_helper = false;
   void* alloc(size_t bytes);
   void free(void* p, size_t bytes = 0);
   void flush_big_cache();

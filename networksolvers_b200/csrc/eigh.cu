@@ -1366,8 +1366,8 @@ void Eigh<T>::vectors(const int32_t* idx_host, int64_t k, T* U, int64_t ldu) {
   DevBuf Y(ctx, sizeof(T) * (size_t)nb * split * k), Y2(ctx, sizeof(T) * (size_t)nb * k);
   const size_t larft_smem = sizeof(T) * ((size_t)nb * nb + nb);
   {
-    static bool configured[2] = {false, false};
-    bool& c = configured[ScalarTraits<T>::is_complex ? 1 : 0];
+    static bool configured[2][64] = {{false}};
+    bool& c = configured[ScalarTraits<T>::is_complex ? 1 : 0][ctx->device & 63];
     if (!c) { NSB_CUDA(cudaFuncSetAttribute(larft_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(T) * (ScalarTraits<T>::is_complex ? (96 * 96 + 96) : (160 * 160 + 160))))); c = true; }
   }
   const bool dbg = eigh_debug();

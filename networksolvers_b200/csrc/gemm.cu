@@ -410,6 +410,75 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_dmma_kernel(const GemmPa
 }
 
 // ------------------------------------------------------------------------------------------------
+// gemm_grouped_kernel: one persistent launch for a whole list of independent GEMMs of unequal size -- the symmetry-sector
+// block products of a QN-conserving contraction (K13).  Problem p is C_p (M_p x N_p) = sum over its segments s of
+// op(A_s) (M_p x K_s) op(B_s) (K_s x N_p): the segments are the sector pairs that contribute to one output block, summed in
+// the accumulator registers, so every output tile is written exactly once (no beta passes, no atomics).  Operands are
+// offsets into three base buffers (block-sparse flat storage).  Same DMMA consumer and cp.async pipeline as
+// gemm_dmma_kernel; output tiles of all problems form one work list dealt round-robin to the CTAs.
+// ------------------------------------------------------------------------------------------------
+template <typename T, bool AK, bool BKM>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_grouped_kernel(const GroupedProblem* __restrict__ probs, int nprob,
+                                                                      const GroupedSegment* __restrict__ segs, int64_t total_tiles,
+                                                                      const T* __restrict__ Abase, const T* __restrict__ Bbase,
+                                                                      T* __restrict__ Cbase, GemmParams<T> proto) {
+  typedef TileCfg<T> Cfg;
+  typedef typename AccOf<T>::type Acc;
+  extern __shared__ __align__(1024) char smem[];
+  constexpr int A_BYTES = Cfg::BM * 128, B_BYTES = Cfg::BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = warp % Cfg::WARPS_M, wn = warp / Cfg::WARPS_M;
+  for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    int lo = 0, hi = nprob - 1;       // problem of this tile: last p with tile0 <= tile
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (probs[mid].tile0 <= tile) lo = mid; else hi = mid - 1;
+    }
+    const GroupedProblem pr = probs[lo];
+    const int64_t lt = tile - pr.tile0;
+    const int64_t tm = lt % pr.tiles_m, tn = lt / pr.tiles_m;
+    const int64_t m0 = tm * Cfg::BM, n0 = tn * Cfg::BN;
+    Acc acc;
+    acc_zero(acc);
+    for (int sidx = pr.seg0; sidx < pr.seg0 + pr.nseg; ++sidx) {
+      const GroupedSegment sg = segs[sidx];
+      const T* A = Abase + sg.a_off;
+      const T* B = Bbase + sg.b_off;
+      const int64_t nk = (sg.K + Cfg::BK - 1) / Cfg::BK;
+      const bool alA = sg.alignedA, alB = sg.alignedB;
+#pragma unroll
+      for (int s = 0; s < GEMM_STAGES - 1; ++s) {
+        if (s < nk) {
+          char* st = smem + s * STAGE_BYTES;
+          load_tile_cpasync<T, Cfg::BM>(st, A, sg.lda, m0, (int64_t)s * Cfg::BK, pr.M, sg.K, AK, alA, tid);
+          load_tile_cpasync<T, Cfg::BN>(st + A_BYTES, B, sg.ldb, n0, (int64_t)s * Cfg::BK, pr.N, sg.K, BKM, alB, tid);
+        }
+        cp_async_commit();
+      }
+      for (int64_t kt = 0; kt < nk; ++kt) {
+        cp_async_wait<GEMM_STAGES - 2>();
+        __syncthreads();
+        const int64_t kn = kt + GEMM_STAGES - 1;
+        if (kn < nk) {
+          char* st = smem + (kn % GEMM_STAGES) * STAGE_BYTES;
+          load_tile_cpasync<T, Cfg::BM>(st, A, sg.lda, m0, kn * Cfg::BK, pr.M, sg.K, AK, alA, tid);
+          load_tile_cpasync<T, Cfg::BN>(st + A_BYTES, B, sg.ldb, n0, kn * Cfg::BK, pr.N, sg.K, BKM, alB, tid);
+        }
+        cp_async_commit();
+        const char* cs = smem + (kt % GEMM_STAGES) * STAGE_BYTES;
+        compute_stage<AK, BKM>(cs, cs + A_BYTES, acc, wm, wn, g, t, proto.sa, proto.sb);
+      }
+      cp_async_wait<0>();
+      __syncthreads();  // all warps done with smem before the next segment's prologue overwrites it
+    }
+    GemmParams<T> p = proto;
+    p.M = pr.M; p.N = pr.N; p.ldc = pr.ldc;
+    store_tile(acc, p, Cbase + pr.c_off, m0, n0, wm, wn, g, t);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // gemm_tma_kernel: TMA producer warp + 8 DMMA consumer warps, full/empty mbarrier ring
 // ------------------------------------------------------------------------------------------------
 struct TmaMaps { CUtensorMap a; CUtensorMap b; };
@@ -580,7 +649,8 @@ static void launch_dmma(Ctx* ctx, const GemmParams<T>& p) {
   typedef TileCfg<T> Cfg;
   size_t smem = (size_t)GEMM_STAGES * (Cfg::BM + Cfg::BN) * 128;
   auto kern = gemm_dmma_kernel<T, AK, BKM>;
-  static bool configured = false;
+  static bool configured_dev[64] = {false};
+  bool& configured = configured_dev[ctx->device & 63];   // function attributes are per device
   if (!configured) {
     NSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
@@ -604,7 +674,8 @@ static bool launch_tma(Ctx* ctx, const GemmParams<T>& p) {
   if (!ok) return false;
   size_t smem = (size_t)GEMM_STAGES * (Cfg::BM + Cfg::BN) * 128 + 2 * GEMM_STAGES * sizeof(uint64_t);
   auto kern = gemm_tma_kernel<T, AK, BKM>;
-  static bool configured = false;
+  static bool configured_dev[64] = {false};
+  bool& configured = configured_dev[ctx->device & 63];   // function attributes are per device
   if (!configured) {
     NSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
@@ -699,6 +770,56 @@ void gemm(Ctx* ctx, int opa, int opb, int64_t M, int64_t N, int64_t K, T alpha, 
   g_last_impl = "dmma_cpasync";
 }
 
+template <typename T, bool AK, bool BKM>
+static void launch_grouped(Ctx* ctx, const GroupedProblem* probs, int nprob, const GroupedSegment* segs, int64_t total_tiles, const T* A,
+                           const T* B, T* C, const GemmParams<T>& proto) {
+  typedef TileCfg<T> Cfg;
+  size_t smem = (size_t)GEMM_STAGES * (Cfg::BM + Cfg::BN) * 128;
+  auto kern = gemm_grouped_kernel<T, AK, BKM>;
+  static bool configured_dev[64] = {false};
+  bool& configured = configured_dev[ctx->device & 63];
+  if (!configured) {
+    NSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  int grid = (int)std::min<int64_t>(total_tiles, ctx->num_sms);
+  kern<<<grid, GEMM_THREADS, smem, ctx->stream>>>(probs, nprob, segs, total_tiles, A, B, C, proto);
+  NSB_CUDA(cudaGetLastError());
+}
+
+template <typename T>
+void gemm_grouped(Ctx* ctx, int opa, int opb, const GroupedProblem* probs_dev, int nprob, const GroupedSegment* segs_dev, int64_t total_tiles,
+                  const T* Abase, const T* Bbase, T* Cbase, double flops) {
+  if (nprob <= 0 || total_tiles <= 0) return;
+  GemmParams<T> p{};
+  p.alpha = from_complex<T>(1.0, 0.0); p.beta = zero_<T>();
+  p.a_kmajor = (opa == OP_T || opa == OP_C);
+  p.b_kmajor = (opb == OP_N || opb == OP_CONJ);
+  p.sa = (ScalarTraits<T>::is_complex && (opa == OP_C || opa == OP_CONJ)) ? -1.0 : 1.0;
+  p.sb = (ScalarTraits<T>::is_complex && (opb == OP_C || opb == OP_CONJ)) ? -1.0 : 1.0;
+  p.lower_only = 0;
+  ctx->cnt.gemm_calls++;
+  ctx->cnt.kernel_launches++;
+  ctx->cnt.gemm_flops += flops;
+  const bool prof = ctx->gemm_profile && ctx->gemm_prof.size() < 65536;
+  size_t pidx = 0;
+  if (prof) {
+    Ctx::GemmProf g; g.flops = flops; g.M = -1; g.N = nprob; g.K = total_tiles; g.batch = 1;     // M = -1 marks a grouped launch
+    cudaEventCreate(&g.e0); cudaEventCreate(&g.e1);
+    cudaEventRecord(g.e0, ctx->stream);
+    pidx = ctx->gemm_prof.size();
+    ctx->gemm_prof.push_back(g);
+  }
+  struct Closer { Ctx* c; size_t i; bool on; ~Closer() { if (on) cudaEventRecord(c->gemm_prof[i].e1, c->stream); } } closer{ctx, pidx, prof};
+  if (p.a_kmajor && p.b_kmajor) launch_grouped<T, true, true>(ctx, probs_dev, nprob, segs_dev, total_tiles, Abase, Bbase, Cbase, p);
+  else if (p.a_kmajor && !p.b_kmajor) launch_grouped<T, true, false>(ctx, probs_dev, nprob, segs_dev, total_tiles, Abase, Bbase, Cbase, p);
+  else if (!p.a_kmajor && p.b_kmajor) launch_grouped<T, false, true>(ctx, probs_dev, nprob, segs_dev, total_tiles, Abase, Bbase, Cbase, p);
+  else launch_grouped<T, false, false>(ctx, probs_dev, nprob, segs_dev, total_tiles, Abase, Bbase, Cbase, p);
+  g_last_impl = "dmma_grouped";
+}
+int gemm_tile_m(bool cplx) { return cplx ? TileCfg<cdouble>::BM : TileCfg<double>::BM; }
+int gemm_tile_n(bool cplx) { return cplx ? TileCfg<cdouble>::BN : TileCfg<double>::BN; }
+
 // ------------------------------------------------------------------------------------------------
 // FP64 tensor-pipe ceiling probe: register-resident DMMA issue loop (no memory traffic)
 // ------------------------------------------------------------------------------------------------
@@ -735,6 +856,8 @@ double dmma_peak_tflops(Ctx* ctx) {
   return best;
 }
 
+template void gemm_grouped<double>(Ctx*, int, int, const GroupedProblem*, int, const GroupedSegment*, int64_t, const double*, const double*, double*, double);
+template void gemm_grouped<cdouble>(Ctx*, int, int, const GroupedProblem*, int, const GroupedSegment*, int64_t, const cdouble*, const cdouble*, cdouble*, double);
 template void gemm<double>(Ctx*, int, int, int64_t, int64_t, int64_t, double, const double*, int64_t, int64_t,
                            const double*, int64_t, int64_t, double, double*, int64_t, int64_t, int64_t, int, const PeerOut*, int);
 template void gemm<cdouble>(Ctx*, int, int, int64_t, int64_t, int64_t, cdouble, const cdouble*, int64_t, int64_t,

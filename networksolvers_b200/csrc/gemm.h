@@ -24,6 +24,17 @@ void gemm(Ctx* ctx, int opa, int opb, int64_t M, int64_t N, int64_t K, T alpha, 
           int64_t strideA, const T* B, int64_t ldb, int64_t strideB, T beta, T* C, int64_t ldc,
           int64_t strideC, int64_t batch, int impl = GEMM_AUTO, const PeerOut* peer = nullptr, int flags = 0);
 
+// Grouped GEMM (block-sparse sector products, K13): problem p is C_p = sum_{s in segments of p} op(A_s) op(B_s); all problems of
+// one launch share opa / opb.  Offsets are element offsets into the three base buffers; tile0 is the prefix sum of output tiles
+// (tiles_m x tiles_n per problem, tile sizes from gemm_tile_m / gemm_tile_n).  Tables live in device memory.
+struct GroupedSegment { int64_t a_off, b_off, K, lda, ldb; int32_t alignedA, alignedB; };
+struct GroupedProblem { int64_t c_off, M, N, ldc, tile0, tiles_m; int32_t seg0, nseg; };
+template <typename T>
+void gemm_grouped(Ctx* ctx, int opa, int opb, const GroupedProblem* probs_dev, int nprob, const GroupedSegment* segs_dev, int64_t total_tiles,
+                  const T* Abase, const T* Bbase, T* Cbase, double flops);
+int gemm_tile_m(bool cplx);
+int gemm_tile_n(bool cplx);
+
 const char* gemm_last_impl_name();
 
 // Measured FP64 DMMA issue ceiling of this device (register-resident mma.sync loop), TFLOP/s.

@@ -338,8 +338,8 @@ static void qr_thin_blocked(Ctx* ctx, T* A, int64_t rows, int64_t cols, int64_t 
   const int threads = rows >= 2048 ? 512 : 256;
   const size_t larft_smem = sizeof(T) * (QR_NB * QR_NB + QR_NB);
   {
-    static bool configured[2] = {false, false};
-    bool& c = configured[ScalarTraits<T>::is_complex ? 1 : 0];
+    static bool configured[2][64] = {{false}};
+    bool& c = configured[ScalarTraits<T>::is_complex ? 1 : 0][ctx->device & 63];
     if (!c) { NSB_CUDA(cudaFuncSetAttribute(qr_larft_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)larft_smem)); c = true; }
   }
   for (int64_t pi = 0; pi < npanels; ++pi) {
@@ -757,7 +757,8 @@ void herm_eig_batch128(Ctx* ctx, const double* S, double* R, double* evals, int 
   constexpr int N2 = 128;
   auto kern = herm_eig_kernel<double, N2>;
   size_t smem = sizeof(double) * ((size_t)N2 * (N2 + 1) / 2 + (size_t)N2 * N2 + 4 * (N2 / 2));
-  static bool configured = false;
+  static bool configured_dev[64] = {false};
+  bool& configured = configured_dev[ctx->device & 63];   // function attributes are per device
   if (!configured) { NSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = true; }
   unsigned long long* dmax = reinterpret_cast<unsigned long long*>(ctx->d_scratch);
   NSB_CUDA(cudaMemsetAsync(dmax, 0, 2 * sizeof(unsigned long long), ctx->stream));
@@ -817,7 +818,8 @@ static int jacobi_blocked(Ctx* ctx, T* G, int64_t m, int64_t n, T* V, int64_t nv
   NSB_CUDA(cudaMemcpyAsync(mapb.ptr, src_of_dst.data(), sizeof(int32_t) * nblk, cudaMemcpyHostToDevice, ctx->stream));
   auto kern = herm_eig_kernel<T, N2>;
   size_t smem = sizeof(T) * ((size_t)N2 * (N2 + 1) / 2 + (size_t)N2 * N2 + 4 * (N2 / 2));
-  static bool configured = false;
+  static bool configured_dev[64] = {false};
+  bool& configured = configured_dev[ctx->device & 63];   // function attributes are per device
   if (!configured) { NSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = true; }
   const T one = from_complex<T>(1.0, 0.0), zero = zero_<T>();
   // the Gram entries of orthogonal columns carry rounding noise ~ eps sqrt(m) (max over n^2/2 pairs several times that)

@@ -220,6 +220,7 @@ void Net<T>::mpo_upload(int v, int rank, const int32_t* legs, const int64_t* dim
   NSB_CUDA(cudaMemcpyAsync(t.data(), host, sizeof(T) * t.numel(), cudaMemcpyHostToDevice, ctx->stream));
   ctx->sync();
   W[v] = t;
+  if ((int)Whost.size() > v) Whost[v].clear();
   envs.clear();
   plan.clear();
 }
@@ -410,6 +411,17 @@ int Net<T>::make_env(int u, int v) {
   for (int n : others) built += make_env(n, u);
   NSB_REQUIRE(psi[u].valid() && W[u].valid(), NSB_EINVAL, "make_env: state or operator tensor missing");
   NSB_REQUIRE(!fit_mode || xket[u].valid(), NSB_EINVAL, "make_env: fitting target tensor missing");
+  if (qn_bs()) {     // QN network: the environment is built and kept as symmetry blocks (grouped sector GEMMs)
+    Env benv;
+    if (make_env_bt(u, v, others, &benv)) {
+      benv.deps.push_back({u, ver[u]});
+      for (int n : others) for (auto& d : envs.at({n, u}).deps) benv.deps.push_back(d);
+      envs[key] = benv;
+      ctx->cnt.env_builds++;
+      return built + 1;
+    }
+    for (int n : others) env_dense(n, u);      // not permutation-free on blocks: dense engine on dense copies
+  }
   DTensor<T> X = fit_mode ? xket[u] : psi[u];
   size_t start = 0;
   DTensor<T> bra = psi[u].primed();
@@ -453,6 +465,7 @@ int Net<T>::make_env(int u, int v) {
     identity_deviation<T>(ctx, E.data(), E.dims[0], E.dims[1], dev.data());
     for (int64_t w = 0; w < E.dims[1]; ++w) if (dev[w] <= 1e-10) { env.ident = (int)w; break; }
   }
+  if (qn_bs()) env.bt = bt_of(E);     // (dense fallback above) keep the block form too: later block contractions use it
   env.deps.push_back({u, ver[u]});
   for (int n : others) for (auto& d : envs.at({n, u}).deps) env.deps.push_back(d);
   envs[key] = env;
@@ -845,6 +858,13 @@ DTensor<T> Net<T>::apply_heff_slab(const DTensor<T>& xs) {
 template <typename T>
 DTensor<T> Net<T>::apply_heff(const DTensor<T>& x) {
   DTensor<T> X = x;
+  if (qn_bs() && theta_st && bt_apply_ok && x.labels == theta.labels && x.dims == theta.dims) {
+    // QN network: dense local tensor -> symmetry blocks -> sector-batched application -> dense
+    BTensor<T> xb = bt_of(x, theta_st), yb;
+    if (apply_heff_bt(xb, &yb)) return to_dense<T>(ctx, yb);
+    bt_apply_ok = false;
+  }
+  if (qn_bs()) for (auto& st : plan) if (st.type == 0) env_dense(st.u, st.v);     // dense engine needs dense environments
   if (shard_active && (shard_mode == 1 || shard_mode == 2)) {     // full vector in / out around the slab form
     DTensor<T> os = apply_heff_slab(x.last_mode_slab(shard_lo, shard_hi));
     DTensor<T> out(ctx, x.dims, x.labels);
@@ -995,6 +1015,7 @@ double Net<T>::matvec_flops() {
 
 template <typename T>
 double Net<T>::matvec_flops_executed() {
+  if (qn_bs() && bt_apply_ok && bt_last_apply_flops >= 0.0) return bt_last_apply_flops;   // sector GEMM flops of the last application
   // after an application at this position: what it really skipped; before: the dry run of the same conditions
   return matvec_flops() - (skipped_last_apply >= 0.0 ? skipped_last_apply : skipped_flops(theta));
 }
@@ -1117,13 +1138,13 @@ bool Net<T>::expand_densitymatrix(const nsb_trunc& trunc, const nsb_expand& ex) 
   for (int n : ext) make_env(n, prev);   // present already on every plan the reference generates
   DTensor<T> X = A;
   size_t start = 0;
-  if (!ext.empty()) { X = contract(ctx, X, envs.at({ext[0], prev}).t, false, false, 1); start = 1; }
+  if (!ext.empty()) { X = contract(ctx, X, env_dense(ext[0], prev), false, false, 1); start = 1; }
   {
     SmallOp<T> op;
     std::vector<int> reg{prev};
     X = apply_small(ctx, op, X, W[prev], w_out_labels(X, W[prev], prev, reg));
   }
-  for (size_t i = start; i < ext.size(); ++i) X = contract(ctx, X, envs.at({ext[i], prev}).t, false, false, 1);
+  for (size_t i = start; i < ext.size(); ++i) X = contract(ctx, X, env_dense(ext[i], prev), false, false, 1);
   // Operator links toward neighbours of `prev` that were skipped stay open, exactly as in the reference.
   std::vector<Label> basis, basis_p;
   for (Label l : A.labels) if (l != a) { basis.push_back(l); basis_p.push_back(label_setplev(l, 1)); }
@@ -1241,6 +1262,14 @@ void Net<T>::extract(const int32_t* reg, int nreg, const nsb_trunc* trunc, const
     built = position(r);
   }
   shard_prepare();
+  theta_st = nullptr;
+  bt_apply_ok = true;
+  bt_last_apply_flops = -1.0;
+  if (qn_bs()) {
+    bool ok = true;
+    for (Label l : theta.labels) if (label_kind(l) == LK_AUX) ok = false;
+    if (ok) theta_st = allowed_struct(theta);
+  }
   if (fit_mode) {
     PhaseTimer pt(ctx, NSB_T_MATVEC);
     theta = fit_local();
@@ -1256,6 +1285,12 @@ void Net<T>::extract(const int32_t* reg, int nreg, const nsb_trunc* trunc, const
 
 template <typename T>
 DTensor<T> Net<T>::kvec_start() {
+  if (krylov_blocks()) {     // QN network: the Krylov vectors are the flat block storage of the local tensor
+    BTensor<T> b = bt_of(theta, theta_st);
+    DTensor<T> f;
+    f.buf = b.buf; f.dims = {theta_st->total}; f.labels = {make_label(LK_AUX, 7)};
+    return f;
+  }
   if (!krylov_sharded()) return clone(ctx, theta);
   if (theta_is_slab) return clone(ctx, theta_slab);
   return clone(ctx, theta.last_mode_slab(shard_lo, shard_hi));
@@ -1278,7 +1313,30 @@ double Net<T>::knrm2(const DTensor<T>& a) {
   return std::sqrt(r > 0.0 ? r : 0.0);
 }
 template <typename T>
+DTensor<T> Net<T>::kapply(const DTensor<T>& v) {
+  if (krylov_blocks()) {
+    BTensor<T> xb, yb;
+    xb.st = theta_st; xb.buf = v.buf; xb.labels = theta.labels;
+    if (!(bt_apply_ok && apply_heff_bt(xb, &yb))) {
+      bt_apply_ok = false;
+      DTensor<T> yd = apply_heff(to_dense<T>(ctx, xb));
+      yb = bt_of(yd, theta_st);
+    }
+    DTensor<T> f;
+    f.buf = yb.buf; f.dims = v.dims; f.labels = v.labels;
+    return f;
+  }
+  return krylov_sharded() ? apply_heff_slab(v) : apply_heff(v);
+}
+template <typename T>
 void Net<T>::kstore_theta(const DTensor<T>& x) {
+  if (krylov_blocks()) {
+    BTensor<T> xb;
+    xb.st = theta_st; xb.buf = x.buf; xb.labels = theta.labels;
+    theta = to_dense<T>(ctx, xb);
+    theta_is_slab = false;
+    return;
+  }
   if (krylov_sharded()) { theta_slab = x; theta_is_slab = true; }
   else { theta = x; theta_is_slab = false; }
 }
@@ -1610,11 +1668,11 @@ void Net<T>::update_exp(double tre, double tim, int solver, const nsb_krylov* kp
       envs.erase({v1, v2});
       make_env(v2, v1);              // present already (incident to the current region)
       make_env(v1, v2);
-      E1 = envs.at({v1, v2}).t;      // [l(k), op, l'(k)]  ->  relabel its link to the auxiliary QR index
+      E1 = env_dense(v1, v2);        // [l(k), op, l'(k)]  ->  relabel its link to the auxiliary QR index
       std::vector<Label> nl = E1.labels;
       for (auto& x : nl) if (label_kind(x) == LK_LINK) x = make_label(LK_AUX, 3, label_plev(x));
       E1 = E1.relabeled(nl);
-      E2 = envs.at({v2, v1}).t;      // [l, op, l']
+      E2 = env_dense(v2, v1);        // [l, op, l']
     }
     auto Hedge = [&](const DTensor<T>& x) {      // src/operator_map.jl:17-20 (on-edge branch)
       DTensor<T> y = contract(ctx, x, E2, false, false, 1);        // [ax, op, l']
@@ -1630,7 +1688,11 @@ void Net<T>::update_exp(double tre, double tim, int solver, const nsb_krylov* kp
     DTensor<T> th = contract(ctx, Q.relabeled(ql), Rt, false, false, 1);
     if (th.labels != theta.labels) th = permuted(ctx, th, theta.labels);
     theta = th;
-    if (qn_on) { int e = eid.at({v1, v2}); qn_link[e] = saved_link; qn_side[e] = saved_side; }   // bond of theta is the original one
+    if (qn_on) {   // bond of theta is the original one
+      int e = eid.at({v1, v2});
+      qn_link[e] = saved_link; qn_side[e] = saved_side;
+      if ((int)link_mode.size() > e) link_mode[e] = nullptr;
+    }
   }
   if (info) { info->nmatvec = nmv; info->krylovdim = lastK; info->converged = conv; info->residual = err; info->reserved = 0; }
 }

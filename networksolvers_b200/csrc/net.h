@@ -6,6 +6,7 @@
 #include <map>
 #include <set>
 
+#include "bsparse.h"
 #include "linalg.h"
 #include "tensor.h"
 
@@ -51,6 +52,7 @@ struct NetBase {
   virtual void qn_set_site(int v, const int32_t* charges) = 0;
   virtual void qn_set_link(int u, int v, const int32_t* charges) = 0;
   virtual void qn_get_link(int u, int v, int32_t* charges_out) = 0;
+  virtual void qn_project(int v) = 0;
 };
 
 template <typename T>
@@ -68,14 +70,16 @@ struct Net : public NetBase {
   bool pos_on_edge = false;
   // ident: operator-link channel w with t[:, w, :] = identity to 1e-10 (the "nothing to the left / right yet" channel of an
   // MPO-like operator between orthonormal bases), -1 if none
-  struct Env { DTensor<T> t; std::vector<std::pair<int, uint64_t>> deps; int ident = -1; };
+  // bt: block-sparse form (QN networks with ctx option qn_block_sparse): then t carries dims / labels only until a dense
+  // consumer asks for it (env_dense)
+  struct Env { DTensor<T> t; std::vector<std::pair<int, uint64_t>> deps; int ident = -1; BTensor<T> bt; };
   std::map<std::pair<int, int>, Env> envs;      // key (u, v): everything on u's side, pointing into v
   // local problem
   DTensor<T> theta;
   std::vector<int> region;
   // type 0: environment (u -> v); 1: site operator at v; 2: the two site operators of a 2-site region merged into one
   // small operator (u = first site, v = second site, Wm = W[u] * W[v] over their shared operator link)
-  struct Step { int type; int u, v; SmallOp<T> op; DTensor<T> Wm; };
+  struct Step { int type; int u, v; SmallOp<T> op; DTensor<T> Wm; std::vector<T> Wm_host; };
   std::vector<Step> plan;
   DTensor<T> last_out;                          // result of the last nsb_matvec_device
   // identity-channel skipping (g_skip_identity): first environment of the plan without its identity channel
@@ -106,7 +110,8 @@ struct Net : public NetBase {
   void comm_reduce_scatter(const T* send, T* recv, int64_t n_per_rank);
   // Krylov vector algebra on full vectors or on slabs (partial sums + all-reduce of the scalars)
   DTensor<T> kvec_start();
-  DTensor<T> kapply(const DTensor<T>& v) { return krylov_sharded() ? apply_heff_slab(v) : apply_heff(v); }
+  bool krylov_blocks() const { return qn_bs() && (bool)theta_st; }
+  DTensor<T> kapply(const DTensor<T>& v);
   void kdot(const DTensor<T>& a, const DTensor<T>& b, double* re_out, double* im_out);
   double knrm2(const DTensor<T>& a);
   void kstore_theta(const DTensor<T>& x);
@@ -121,6 +126,25 @@ struct Net : public NetBase {
   std::vector<int64_t> leg_charges(int owner, Label l) const;
   std::vector<int64_t> multi_keys(int owner, const std::vector<Label>& labels, const std::vector<int64_t>& dims, bool complement) const;
   void qn_store_link(int v, int n, const std::vector<int64_t>& keys_on_v_side);
+  // ---- block-sparse engine for QN networks (bsparse.h): environments, local tensor and Krylov vectors as symmetry blocks ----
+  bool qn_bs() const { return qn_on && ctx->opt.qn_block_sparse != 0 && !fit_mode; }
+  std::shared_ptr<BCache> bcache;
+  std::vector<std::shared_ptr<BMode>> link_mode, site_mode, op_mode;    // per edge / vertex / edge, built on demand
+  std::shared_ptr<BMode> mode_for(Label l, int64_t dim);
+  std::vector<std::shared_ptr<BMode>> modes_for(const std::vector<Label>& labels, const std::vector<int64_t>& dims);
+  BTensor<T> bt_of(const DTensor<T>& t, std::shared_ptr<BStruct> st = nullptr);
+  std::shared_ptr<BStruct> allowed_struct(const DTensor<T>& th);         // symmetry-allowed blocks of a local tensor
+  std::shared_ptr<BStruct> allowed_struct_in(const DTensor<T>& th, const std::vector<int>& inside);
+  void qn_project(int v) override;
+  std::shared_ptr<BStruct> theta_st;                                     // block layout of the local tensor / Krylov vectors
+  bool bt_apply_ok = true;                                               // false: this position falls back to the dense engine
+  double bt_last_apply_flops = -1.0;
+  std::vector<std::vector<T>> Whost;                                     // host copies of the site operators (bapply_small)
+  const std::vector<T>& w_host(int v);
+  bool make_env_bt(int u, int v, const std::vector<int>& others, Env* out);
+  bool apply_heff_bt(const BTensor<T>& x, BTensor<T>* y);
+  const DTensor<T>& env_dense(int u, int v);
+  DTensor<T> fake_dense(const BTensor<T>& b) const { DTensor<T> f; f.labels = b.labels; f.dims = b.dims(); return f; }
   FactorInfo factorize_qn(const T* M, int64_t rows, int64_t cols, const std::vector<int64_t>& rk, const std::vector<int64_t>& ck,
                           double cutoff, int64_t mindim, int64_t maxdim, bool sqrt_spectrum, DevBuf& U, DevBuf& C,
                           std::vector<int64_t>& new_keys);

@@ -8,7 +8,10 @@
 #include "net.h"
 
 #include <algorithm>
+#include <atomic>
+#include <functional>
 #include <numeric>
+#include <thread>
 
 namespace nsb {
 
@@ -129,6 +132,7 @@ void Net<T>::qn_set_link(int u, int v, const int32_t* charges) {
   int64_t dim = psi[u].dim_of(llink(u, v));
   qn_link[e].assign(charges, charges + dim * nq);
   qn_side[e] = u;
+  if ((int)link_mode.size() > e) link_mode[e] = nullptr;
 }
 template <typename T>
 void Net<T>::qn_get_link(int u, int v, int32_t* out) {
@@ -189,6 +193,7 @@ std::vector<int64_t> Net<T>::multi_keys(int owner, const std::vector<Label>& lab
 template <typename T>
 void Net<T>::qn_store_link(int v, int n, const std::vector<int64_t>& keys) {
   int e = eid.at({v, n});
+  if ((int)link_mode.size() > e) link_mode[e] = nullptr;
   qn_link[e].assign(keys.size() * nq, 0);
   for (size_t i = 0; i < keys.size(); ++i) unpack_key(keys[i], nq, &qn_link[e][i * nq]);
   qn_side[e] = v;
@@ -208,22 +213,61 @@ FactorInfo Net<T>::factorize_qn(const T* M, int64_t rows, int64_t cols, const st
   struct Res { DevBuf U, C; std::vector<double> spec; int64_t r, c; DevBuf ridx, cidx; };
   std::vector<Res> res(blocks.size());
   std::vector<std::vector<double>> P(blocks.size());
-  for (size_t b = 0; b < blocks.size(); ++b) {
+  // The sectors are independent small factorisations, each a latency-bound chain of launches with host look-ups: run them
+  // concurrently, one host thread + helper context (own stream) per lane, largest blocks first.
+  std::vector<size_t> order(blocks.size());
+  std::iota(order.begin(), order.end(), (size_t)0);
+  std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) {
+    return blocks[a].rows.size() * blocks[a].cols.size() > blocks[b].rows.size() * blocks[b].cols.size(); });
+  double work = 0.0;
+  for (auto& B : blocks) work += (double)B.rows.size() * (double)B.cols.size() * (double)std::min(B.rows.size(), B.cols.size());
+  const int lanes = (blocks.size() >= 4 && work > 5e7) ? (int)std::min<size_t>(8, blocks.size()) : 1;
+  std::vector<int> sweeps(blocks.size(), 0);
+  auto do_block = [&](Ctx* c, size_t b) {
     Block& B = blocks[b];
     Res& R = res[b];
     R.r = (int64_t)B.rows.size(); R.c = (int64_t)B.cols.size();
-    R.ridx = DevBuf(ctx, sizeof(int32_t) * R.r); R.cidx = DevBuf(ctx, sizeof(int32_t) * R.c);
-    NSB_CUDA(cudaMemcpyAsync(R.ridx.ptr, B.rows.data(), sizeof(int32_t) * R.r, cudaMemcpyHostToDevice, ctx->stream));
-    NSB_CUDA(cudaMemcpyAsync(R.cidx.ptr, B.cols.data(), sizeof(int32_t) * R.c, cudaMemcpyHostToDevice, ctx->stream));
-    DevBuf Bm(ctx, sizeof(T) * R.r * R.c);
-    gather_block_kernel<T><<<grid1d(ctx, R.r * R.c), 256, 0, ctx->stream>>>(M, rows, (const int32_t*)R.ridx.ptr, R.r,
-                                                                            (const int32_t*)R.cidx.ptr, R.c, (T*)Bm.ptr);
-    LAUNCH_CHECK(ctx);
+    R.ridx = DevBuf(c, sizeof(int32_t) * R.r); R.cidx = DevBuf(c, sizeof(int32_t) * R.c);
+    NSB_CUDA(cudaMemcpyAsync(R.ridx.ptr, B.rows.data(), sizeof(int32_t) * R.r, cudaMemcpyHostToDevice, c->stream));
+    NSB_CUDA(cudaMemcpyAsync(R.cidx.ptr, B.cols.data(), sizeof(int32_t) * R.c, cudaMemcpyHostToDevice, c->stream));
+    DevBuf Bm(c, sizeof(T) * R.r * R.c);
+    gather_block_kernel<T><<<grid1d(c, R.r * R.c), 256, 0, c->stream>>>(M, rows, (const int32_t*)R.ridx.ptr, R.r,
+                                                                        (const int32_t*)R.cidx.ptr, R.c, (T*)Bm.ptr);
+    LAUNCH_CHECK(c);
     int64_t kb = std::min(R.r, R.c);
-    FactorInfo fi = factorize_left<T>(ctx, (const T*)Bm.ptr, R.r, R.c, R.r, false, 0.0, kb, kb, sqrt_spectrum, R.U, R.C, R.spec);
-    info.sweeps = std::max(info.sweeps, fi.sweeps);
+    FactorInfo fi = factorize_left<T>(c, (const T*)Bm.ptr, R.r, R.c, R.r, false, 0.0, kb, kb, sqrt_spectrum, R.U, R.C, R.spec);
+    sweeps[b] = fi.sweeps;
     P[b] = R.spec;
+    c->sync();
+  };
+  if (lanes <= 1) {
+    for (size_t b : order) do_block(ctx, b);
+  } else {
+    ctx->sync();                                   // M is complete before the helper streams read it
+    std::vector<Ctx*> hc(lanes);
+    for (int l = 0; l < lanes; ++l) hc[l] = ctx->helper(l);
+    std::atomic<size_t> next{0};
+    std::vector<std::string> errs(lanes);
+    std::vector<int> codes(lanes, 0);
+    std::vector<std::thread> th;
+    for (int l = 0; l < lanes; ++l)
+      th.emplace_back([&, l] {
+        cudaSetDevice(ctx->device);
+        try {
+          for (size_t i = next++; i < order.size(); i = next++) do_block(hc[l], order[i]);
+        } catch (const Error& e) { codes[l] = e.code; errs[l] = e.what(); }
+        catch (const std::exception& e) { codes[l] = NSB_EINTERNAL; errs[l] = e.what(); }
+      });
+    for (auto& t : th) t.join();
+    for (int l = 0; l < lanes; ++l) {
+      ctx->cnt.kernel_launches += hc[l]->cnt.kernel_launches; ctx->cnt.gemm_calls += hc[l]->cnt.gemm_calls;
+      ctx->cnt.gemm_flops += hc[l]->cnt.gemm_flops; ctx->cnt.svd_calls += hc[l]->cnt.svd_calls;
+      ctx->cnt.jacobi_sweeps += hc[l]->cnt.jacobi_sweeps; ctx->cnt.qr_calls += hc[l]->cnt.qr_calls;
+      hc[l]->cnt = Counters();
+      if (codes[l] != 0) throw Error(codes[l], errs[l]);
+    }
   }
+  for (int sw : sweeps) info.sweeps = std::max(info.sweeps, sw);
   double terr = 0.0;
   std::vector<int64_t> keep = truncate_merged(P, cutoff, mindim, maxdim, &terr);
   int64_t ktot = std::accumulate(keep.begin(), keep.end(), (int64_t)0);
@@ -289,7 +333,206 @@ void Net<T>::qr_qn(const T* M, int64_t rows, int64_t cols, const std::vector<int
   *kout = ktot;
 }
 
+// ------------------------------------------------------------------------------------------------
+// block-sparse engine: modes, conversions, environment build and H_eff application on symmetry blocks
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+std::shared_ptr<BMode> Net<T>::mode_for(Label l, int64_t dim) {
+  const int kind = label_kind(l), id = label_id(l);
+  if (kind == LK_SITE) {
+    if ((int)site_mode.size() != nverts) site_mode.assign(nverts, nullptr);
+    if (!site_mode[id] || site_mode[id]->dim != dim) site_mode[id] = make_mode_small(dim);
+    return site_mode[id];
+  }
+  if (kind == LK_OP) {
+    if (op_mode.size() != edges.size()) op_mode.assign(edges.size(), nullptr);
+    if (!op_mode[id] || op_mode[id]->dim != dim) op_mode[id] = make_mode_small(dim);
+    return op_mode[id];
+  }
+  NSB_REQUIRE(kind == LK_LINK, NSB_EUNSUPPORTED, "block-sparse engine: auxiliary labels are not sectorised");
+  if (link_mode.size() != edges.size()) link_mode.assign(edges.size(), nullptr);
+  NSB_REQUIRE((int64_t)qn_link[id].size() == dim * nq, NSB_EINTERNAL, "QN charge table does not match the link dimension");
+  if (!link_mode[id] || link_mode[id]->dim != dim) {
+    std::vector<int64_t> keys(dim);
+    for (int64_t i = 0; i < dim; ++i) keys[i] = pack_key(&qn_link[id][i * nq], nq);
+    link_mode[id] = make_mode_from_keys(keys);
+  }
+  return link_mode[id];
+}
+
+template <typename T>
+std::vector<std::shared_ptr<BMode>> Net<T>::modes_for(const std::vector<Label>& labels, const std::vector<int64_t>& dims) {
+  std::vector<std::shared_ptr<BMode>> m;
+  for (size_t i = 0; i < labels.size(); ++i) m.push_back(mode_for(labels[i], dims[i]));
+  return m;
+}
+
+template <typename T>
+BTensor<T> Net<T>::bt_of(const DTensor<T>& t, std::shared_ptr<BStruct> st) {
+  if (!bcache) bcache = make_bcache();
+  return from_dense<T>(ctx, t, modes_for(t.labels, t.dims), st);
+}
+
+template <typename T>
+const std::vector<T>& Net<T>::w_host(int v) {
+  if ((int)Whost.size() != nverts) Whost.assign(nverts, std::vector<T>());
+  if (Whost[v].empty()) {
+    Whost[v].resize(W[v].numel());
+    NSB_CUDA(cudaMemcpyAsync(Whost[v].data(), W[v].data(), sizeof(T) * W[v].numel(), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->sync();
+  }
+  return Whost[v];
+}
+
+// All blocks of a local tensor that charge conservation allows: the charges of the outer subtrees (one per link leg) and of
+// the sites add up to the total charge.
+template <typename T>
+std::shared_ptr<BStruct> Net<T>::allowed_struct(const DTensor<T>& th) { return allowed_struct_in(th, region); }
+
+// Zero every entry of psi[v] that charge conservation forbids (gather the allowed blocks, scatter them back): turns a
+// randomly filled tensor into a random symmetric one (synthetic QN states of the benchmarks).
+template <typename T>
+void Net<T>::qn_project(int v) {
+  NSB_REQUIRE(qn_on && v >= 0 && v < nverts && psi[v].valid(), NSB_EINVAL, "qn_project: bad vertex or QN not enabled");
+  std::vector<int> inside{v};
+  BTensor<T> b = bt_of(psi[v], allowed_struct_in(psi[v], inside));
+  psi[v] = to_dense<T>(ctx, b);
+  ver[v]++;
+}
+
+template <typename T>
+std::shared_ptr<BStruct> Net<T>::allowed_struct_in(const DTensor<T>& th, const std::vector<int>& region) {
+  auto st = std::make_shared<BStruct>();
+  st->modes = modes_for(th.labels, th.dims);
+  const int r = th.rank();
+  // charge vector of every sector of every mode, as seen from the region
+  std::vector<std::vector<std::vector<int64_t>>> sc(r);
+  for (int m = 0; m < r; ++m) {
+    const Label l = th.labels[m];
+    std::vector<int64_t> ch;                                 // per dense state
+    if (label_kind(l) == LK_SITE) ch = qn_site[label_id(l)];
+    else {
+      auto e = edges[label_id(l)];
+      const bool first_in = std::find(region.begin(), region.end(), e.first) != region.end();
+      const int inside = first_in ? e.first : e.second, outside = first_in ? e.second : e.first;
+      ch = side_charge(inside, outside);                     // subtree on the outer vertex's side
+    }
+    const BMode& md = *st->modes[m];
+    sc[m].assign(md.nsec(), std::vector<int64_t>(nq, 0));
+    std::vector<char> seen(md.nsec(), 0);
+    for (int64_t i = 0; i < md.dim; ++i) {
+      const int s = md.state_sector[i];
+      if (!seen[s]) { seen[s] = 1; for (int c = 0; c < nq; ++c) sc[m][s][c] = ch[i * nq + c]; }
+    }
+  }
+  std::vector<int32_t> cur(r, 0);
+  std::vector<int64_t> sum(nq, 0);
+  std::function<void(int)> rec = [&](int m) {
+    if (m == r) {
+      for (int c = 0; c < nq; ++c) if (sum[c] != qn_total[c]) return;
+      st->add_block(cur);
+      return;
+    }
+    for (int s = 0; s < st->modes[m]->nsec(); ++s) {
+      cur[m] = s;
+      for (int c = 0; c < nq; ++c) sum[c] += sc[m][s][c];
+      rec(m + 1);
+      for (int c = 0; c < nq; ++c) sum[c] -= sc[m][s][c];
+    }
+  };
+  // mode 0 is the outermost loop here; the block order follows it (any fixed order is fine)
+  rec(0);
+  st->finalize();
+  return st;
+}
+
+template <typename T>
+const DTensor<T>& Net<T>::env_dense(int u, int v) {
+  Env& e = envs.at({u, v});
+  if (!e.t.valid() && e.bt.valid()) {
+    DTensor<T> d = to_dense<T>(ctx, e.bt);
+    e.t.buf = d.buf;
+  }
+  return e.t;
+}
+
+template <typename T>
+bool Net<T>::make_env_bt(int u, int v, const std::vector<int>& others, Env* out) {
+  if (!bcache) bcache = make_bcache();
+  for (int n : others) if (!envs.at({n, u}).bt.valid()) return false;
+  BTensor<T> A = bt_of(psi[u]);
+  BTensor<T> X = A;
+  size_t start = 0;
+  if (!others.empty()) {
+    X = bcontract<T>(ctx, *bcache, X, envs.at({others[0], u}).bt, false, false, 1);
+    if (!X.valid()) return false;
+    start = 1;
+  }
+  {
+    std::vector<int> reg{u};
+    DTensor<T> fx = fake_dense(X);
+    X = bapply_small<T>(ctx, *bcache, X, w_host(u), W[u].labels, W[u].dims, w_out_labels(fx, W[u], u, reg), (uint64_t)(u + 1));
+  }
+  for (size_t i = start; i < others.size(); ++i) {
+    X = bcontract<T>(ctx, *bcache, X, envs.at({others[i], u}).bt, false, false, 1);
+    if (!X.valid()) return false;
+  }
+  BTensor<T> bra = A.primed();
+  const std::vector<Label> want{llink(u, v, 0), lop(u, v), llink(u, v, 1)};
+  BTensor<T> E = bcontract<T>(ctx, *bcache, bra, X, true, false, 1);
+  if (!E.valid() || E.labels != want) E = bcontract<T>(ctx, *bcache, X, bra, false, true, 1);
+  if (!E.valid() || E.labels != want) return false;
+  out->bt = E;
+  out->t = DTensor<T>();
+  out->t.labels = want;
+  out->t.dims = E.dims();
+  return true;
+}
+
+template <typename T>
+bool Net<T>::apply_heff_bt(const BTensor<T>& x, BTensor<T>* y) {
+  const double f0 = ctx->cnt.gemm_flops;
+  BTensor<T> X = x;
+  for (size_t i = 0; i < plan.size(); ++i) {
+    auto& s = plan[i];
+    if (s.type == 0) {
+      const Env& e = envs.at({s.u, s.v});
+      if (!e.bt.valid()) return false;
+      X = bcontract<T>(ctx, *bcache, X, e.bt, false, false, 1);
+      if (!X.valid()) return false;
+    } else if (s.type == 1) {
+      DTensor<T> fx = fake_dense(X);
+      X = bapply_small<T>(ctx, *bcache, X, w_host(s.v), W[s.v].labels, W[s.v].dims, w_out_labels(fx, W[s.v], s.v, pos), (uint64_t)(s.v + 1));
+    } else {
+      if (s.Wm_host.empty()) {
+        s.Wm_host.resize(s.Wm.numel());
+        NSB_CUDA(cudaMemcpyAsync(s.Wm_host.data(), s.Wm.data(), sizeof(T) * s.Wm.numel(), cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->sync();
+      }
+      DTensor<T> fx = fake_dense(X);
+      X = bapply_small<T>(ctx, *bcache, X, s.Wm_host, s.Wm.labels, s.Wm.dims, merged_out_labels(fx, s.u, s.v),
+                          (uint64_t)(1000000 + (uint64_t)s.u * (uint64_t)nverts + (uint64_t)s.v));
+    }
+  }
+  X = X.noprime();
+  if (X.labels != x.labels) return false;
+  *y = conform<T>(ctx, *bcache, X, x.st, x.labels);
+  ctx->cnt.matvecs++;
+  bt_last_apply_flops = ctx->cnt.gemm_flops - f0;
+  return true;
+}
+
 #define INST(T)                                                                                                          \
+  template std::shared_ptr<BMode> Net<T>::mode_for(Label, int64_t);                                                      \
+  template std::vector<std::shared_ptr<BMode>> Net<T>::modes_for(const std::vector<Label>&, const std::vector<int64_t>&); \
+  template BTensor<T> Net<T>::bt_of(const DTensor<T>&, std::shared_ptr<BStruct>);                                        \
+  template const std::vector<T>& Net<T>::w_host(int);                                                                    \
+  template std::shared_ptr<BStruct> Net<T>::allowed_struct(const DTensor<T>&);                                           \
+  template std::shared_ptr<BStruct> Net<T>::allowed_struct_in(const DTensor<T>&, const std::vector<int>&);               \
+  template void Net<T>::qn_project(int);                                                                                  \
+  template const DTensor<T>& Net<T>::env_dense(int, int);                                                                \
+  template bool Net<T>::make_env_bt(int, int, const std::vector<int>&, Env*);                                            \
+  template bool Net<T>::apply_heff_bt(const BTensor<T>&, BTensor<T>*);                                                   \
   template void Net<T>::qn_enable(int, const int32_t*);                                                                  \
   template void Net<T>::qn_set_site(int, const int32_t*);                                                                \
   template void Net<T>::qn_set_link(int, int, const int32_t*);                                                           \

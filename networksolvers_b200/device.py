@@ -281,6 +281,41 @@ class DeviceNetwork:
             net.set_ortho_region(ortho_region)     # gauge flag only (tensors stay as filled): skips the walk
         return net
 
+    @classmethod
+    def synthetic_qn(cls, operator: HostTTN, sites, link_charges, total, site_charges, seed=1234, dtype=np.float64, ctx=None):
+        """Random QN-conserving state filled on the device: `link_charges[(u, v)]` is the (dim, nq) table of charges of the
+        subtree on u's side for every edge (it fixes the sector dimensions), every site tensor is filled with Philox N(0,1)
+        numbers and projected onto its symmetry-allowed blocks (nsb_qn_project).  The orthogonality region is all vertices,
+        so the first extract orthonormalises the state sector by sector."""
+        from .models import product_state
+        g = sites.graph
+        placeholder = product_state(sites, {v: 0 for v in g.vertices}, conserve_qns=False)
+        net = cls(operator, placeholder, dtype=dtype, ctx=ctx)
+        i32p = C.POINTER(C.c_int32)
+        tot = np.ascontiguousarray(total, dtype=np.int32)
+        net.ctx.check(net._lib.nsb_qn_enable(net.handle, len(tot), tot.ctypes.data_as(i32p)))
+        sc = np.ascontiguousarray(site_charges, dtype=np.int32)
+        for v in net.verts:
+            net.ctx.check(net._lib.nsb_qn_set_site(net.handle, net.vid[v], sc.ctypes.data_as(i32p)))
+        dims = {}
+        for (u, v), arr in link_charges.items():
+            dims[(u, v)] = dims[(v, u)] = len(arr)
+        for i, v in enumerate(g.vertices):
+            legs = canonical_legs(g, v)
+            d = {l: (sites.dim if l[0] == "site" else dims[(l[1], l[2])]) for l in legs}
+            numel = int(np.prod([d[l] for l in legs]))
+            scale = 1.0 / np.sqrt(max(numel / d[legs[-1]], 1.0)) if len(legs) > 1 else 1.0
+            net.fill_random(v, d, seed + 7 * i, scale)
+        for (u, v), arr in link_charges.items():
+            a = np.ascontiguousarray(arr, dtype=np.int32)
+            net.ctx.check(net._lib.nsb_qn_set_link(net.handle, net.vid[u], net.vid[v], a.ctypes.data_as(i32p)))
+        for v in net.verts:
+            net.ctx.check(net._lib.nsb_qn_project(net.handle, net.vid[v]))
+        net.qn_enabled = True
+        net._qn_static = dict(total=np.array(total), site={v: np.array(site_charges) for v in net.verts})
+        net.set_ortho_region(list(g.vertices))
+        return net
+
     def close(self):
         if getattr(self, "handle", None) is not None and self.handle.value:
             self._lib.nsb_network_destroy(self.handle)
@@ -399,6 +434,10 @@ class DeviceNetwork:
         d = C.c_double()
         self.ctx.check(self._lib.nsb_norm(self.handle, C.byref(d)))
         return d.value
+
+    def env_drop_all(self):
+        """Forget the cached environments (a freshly constructed ProjTTN)."""
+        self.ctx.check(self._lib.nsb_env_drop_all(self.handle))
 
     def env_count(self):
         n = C.c_int32()

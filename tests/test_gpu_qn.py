@@ -97,3 +97,63 @@ def test_tdvp_qn_two_site_fidelity():
     vx = ed_time_evolution(heisenberg_opsum(og), og, ops, psi0.to_dense(), tp, normalize=True)
     assert 1 - abs(np.vdot(vx, host.to_dense())) < 1e-8
     assert check_state_symmetric(to_oracle_ttn_qn(host), tol=1e-13)
+
+
+@pytest.mark.parametrize("model", ["hubbard", "s1"])
+def test_block_sparse_engine_matches_dense_storage(model):
+    """K13: environments, local tensor and Krylov vectors as symmetry blocks with grouped sector GEMMs (ctx option
+    qn_block_sparse, default on) against the dense-storage path of the same library on the same state: H_eff application to
+    1e-13, Ritz value / kept dimension / truncation error of a whole region step, both sweep directions; the sector GEMMs
+    execute a fraction of the dense-equivalent flops."""
+    import networksolvers_b200 as ns
+    g = ns.path_graph(10)
+    if model == "hubbard":
+        sites = ns.siteinds("Electron", g, conserve_qns=True)
+        H = ns.ttno(ns.hubbard(g, 1.0, 4.0), sites)
+        psi0 = ns.product_state(sites, {v: ("Up" if v % 2 else "Dn") for v in g.vertices})
+    else:
+        sites = ns.siteinds("S=1", g, conserve_qns=True)
+        H = ns.ttno(ns.heisenberg(g), sites)
+        psi0 = ns.product_state(sites, neel(g))
+    trunc = dict(cutoff=1e-12, maxdim=[8, 16, 48])
+    ctx = ns.default_context()
+    prob = ns.EigsolveProblem(state=psi0, operator=H)
+    ns.dmrg(prob, nsweeps=3, nsites=2, inserter_kwargs=dict(trunc=trunc))       # grows the bonds (block-sparse path)
+    host = prob.net.to_host()
+    res = {}
+    try:
+        for bs in (1, 0):
+            ctx.set_option("qn_block_sparse", bs)
+            net = ns.EigsolveProblem(state=host, operator=H).net
+            out = []
+            for reg in ([5, 6], [6, 7], [7, 6], [6, 5]):
+                net.extract(reg)
+                th, _ = net.local_download()
+                hv = net.matvec_host(th)
+                fl = (net.matvec_flops_executed(), net.matvec_flops())
+                if bs == 1:
+                    # the same local tensor through dense-storage environments of the same network
+                    ctx.set_option("qn_block_sparse", 0)
+                    net.env_drop_all()
+                    net.extract(reg)
+                    hv_dense = net.matvec_host(th)
+                    ctx.set_option("qn_block_sparse", 1)
+                    net.env_drop_all()
+                    net.extract(reg)
+                    assert np.abs(hv - hv_dense).max() <= 1e-13 * np.abs(hv_dense).max() * 10, reg
+                val, info = net.update_eigsolve()
+                th2, _ = net.local_download()
+                ins = net.insert((1e-12, 1, 48))
+                ev = np.vdot(th, hv).real / np.vdot(th, th).real
+                out.append((ev, fl, val, np.linalg.norm(th2), ins.newdim, ins.truncerr, info.nmatvec))
+            res[bs] = out
+    finally:
+        ctx.set_option("qn_block_sparse", 1)
+    # gauge-invariant quantities of the two storage forms (degenerate multiplets may rotate inside their subspace)
+    for a, b in zip(res[1], res[0]):
+        assert abs(a[0] - b[0]) <= 1e-11 * max(1.0, abs(b[0]))
+        assert abs(a[2] - b[2]) <= 1e-11 * max(1.0, abs(b[2]))
+        assert abs(a[3] - 1.0) <= 1e-12 and a[6] == b[6] == 3
+        assert a[4] == b[4] and abs(a[5] - b[5]) <= 1e-11
+        assert a[1][1] == b[1][1]                                     # same dense-equivalent count
+        assert a[1][0] < 0.5 * a[1][1], a[1]                          # the sector GEMMs skip the symmetry-forbidden blocks
