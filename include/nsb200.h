@@ -161,6 +161,7 @@ int nsb_timers_reset(nsb_ctx* ctx);
 int nsb_gemm_profile_enable(nsb_ctx* ctx, int32_t on); /* also clears the records */
 int nsb_gemm_profile_read(nsb_ctx* ctx, int64_t cap, double* ms_out, double* flops_out, int64_t* mnkb_out /* 4*cap */,
                           int64_t* count_out);
+int nsb_profiler(nsb_ctx* ctx, int32_t on); /* cudaProfilerStart / cudaProfilerStop around a region (ncu --profile-from-start off) */
 int nsb_mem_info(nsb_ctx* ctx, int64_t* free_bytes, int64_t* total_bytes, int64_t* pool_used_bytes);
 
 /* multi-GPU: one process per GPU; rank 0 creates the id, the host side (torch.distributed, MPI ...)
@@ -173,6 +174,10 @@ int nsb_comm_destroy(nsb_ctx* ctx);
  * partial theta'.  `*active` reports whether the current position is shardable (the last bond of theta must
  * carry the last environment); otherwise the matvec stays replicated.  All ranks must make the same calls. */
 int nsb_net_set_shard(nsb_net* net, int32_t enable, int32_t* active);
+/* Test hook: theta' = H_eff theta computed on ONE device with the arithmetic of an `nranks`-way partition (every rank's partial
+ * result / result slab formed exactly as that rank would, the collective replaced by a local sum / concatenation); mode_out:
+ * 1 reduce-scatter position, 2 all-gather position, 3 all-reduce (uneven bond).  Lets a single-GPU box check the N > 1 path. */
+int nsb_shard_emulate(nsb_net* net, int32_t nranks, void* host_out, int32_t* mode_out);
 /* Fused GEMM + reduce-scatter (ctx option "shard_fused" = 1): the last GEMM of the sharded matvec writes every output
  * tile straight into the owning rank's staging window over NVLink peer memory (P2P stores from the epilogue), the owner
  * sums the nranks partial slabs locally and one all-gather completes theta'.  Every rank creates a window of at least

@@ -85,12 +85,14 @@ SIGNATURES = {
     "nsb_timers_get": (C.c_int, [_vp, P(_dbl)]),
     "nsb_timers_reset": (C.c_int, [_vp]),
     "nsb_mem_info": (C.c_int, [_vp, P(_i64), P(_i64), P(_i64)]),
+    "nsb_profiler": (C.c_int, [_vp, _i32]),
     "nsb_gemm_profile_enable": (C.c_int, [_vp, _i32]),
     "nsb_gemm_profile_read": (C.c_int, [_vp, _i64, P(_dbl), P(_dbl), P(_i64), P(_i64)]),
     "nsb_comm_unique_id": (C.c_int, [C.c_char_p]),
     "nsb_comm_init": (C.c_int, [_vp, C.c_char_p, C.c_int, C.c_int]),
     "nsb_comm_destroy": (C.c_int, [_vp]),
     "nsb_net_set_shard": (C.c_int, [_vp, _i32, P(_i32)]),
+    "nsb_shard_emulate": (C.c_int, [_vp, _i32, _vp, P(_i32)]),
     "nsb_peer_window_create": (C.c_int, [_vp, _i64, C.c_char_p]),
     "nsb_peer_window_open": (C.c_int, [_vp, _i32, C.c_char_p]),
     "nsb_multi_create": (C.c_int, [P(_i32), _i32, P(_vp)]),

@@ -2,6 +2,7 @@
 #include "nccl_dyn.h"
 
 #include <random>
+#include <cuda_profiler_api.h>
 
 #include "net.h"
 #include "eigh.h"
@@ -200,6 +201,7 @@ int nsb_ctx_set_option(nsb_ctx* ctx, const char* key, int64_t value) {
   else if (k == "eigh_nb") { NSB_REQUIRE(value >= 2 && value <= 128 && value % 2 == 0, NSB_EINVAL, "eigh_nb must be even, 2..128"); ctx->c.opt.eigh_nb = (int)value; }
   else if (k == "qr_block_min") { NSB_REQUIRE(value >= 0, NSB_EINVAL, "qr_block_min >= 0"); ctx->c.opt.qr_block_min = (int)value; }
   else if (k == "qn_block_sparse") { ctx->c.opt.qn_block_sparse = value != 0; }
+  else if (k == "nccl_sync") { ctx->c.opt.nccl_sync = value != 0; }
   else throw Error(NSB_EINVAL, "unknown option " + k);
   NSB_CATCH(&ctx->c)
 }
@@ -268,6 +270,13 @@ int nsb_gemm_profile_read(nsb_ctx* ctx, int64_t cap, double* ms_out, double* flo
   }
   NSB_CATCH(&ctx->c)
 }
+int nsb_profiler(nsb_ctx* ctx, int32_t on) {   // cudaProfilerStart / Stop: `ncu --profile-from-start off` then sees only the marked region
+  if (!ctx) return NSB_EINVAL;
+  NSB_TRY(&ctx->c)
+  ctx->c.sync();
+  if (on) NSB_CUDA(cudaProfilerStart()); else NSB_CUDA(cudaProfilerStop());
+  NSB_CATCH(&ctx->c)
+}
 int nsb_mem_info(nsb_ctx* ctx, int64_t* free_bytes, int64_t* total_bytes, int64_t* pool_used_bytes) {
   if (!ctx) return NSB_EINVAL;
   NSB_TRY(&ctx->c)
@@ -300,6 +309,18 @@ int nsb_comm_init(nsb_ctx* ctx, const char id[128], int rank, int nranks) {
   ctx->c.nccl_comm = comm;
   ctx->c.rank = rank;
   ctx->c.nranks = nranks;
+  // bring every channel of the three collectives the region step uses up now (NCCL connects lazily inside the first call of each
+  // kind): the first H_eff application then runs on established connections
+  {
+    const size_t n = (size_t)nranks * 512;
+    DevBuf a(&ctx->c, sizeof(double) * n), b(&ctx->c, sizeof(double) * n);
+    NSB_CUDA(cudaMemsetAsync(a.ptr, 0, sizeof(double) * n, ctx->c.stream));
+    auto chk = [&](ncclResult_t rr, const char* what) { if (rr != ncclSuccess) throw Error(NSB_ENCCL, std::string(what) + ": " + nccl_api().GetErrorString(rr)); };
+    chk(nccl_api().AllReduce(a.ptr, a.ptr, n, ncclDouble, ncclSum, comm, ctx->c.stream), "ncclAllReduce(warm-up)");
+    chk(nccl_api().ReduceScatter(a.ptr, b.ptr, 512, ncclDouble, ncclSum, comm, ctx->c.stream), "ncclReduceScatter(warm-up)");
+    chk(nccl_api().AllGather(b.ptr, a.ptr, 512, ncclDouble, comm, ctx->c.stream), "ncclAllGather(warm-up)");
+    ctx->c.sync();
+  }
   NSB_CATCH(&ctx->c)
 }
 int nsb_comm_destroy(nsb_ctx* ctx) {
@@ -443,6 +464,9 @@ int nsb_matvec_flops_executed(nsb_net* net, double* flops) {
 }
 int nsb_net_set_shard(nsb_net* net, int32_t enable, int32_t* active) {
   NET_CALL(net, int a = net->n->set_shard(enable); if (active) *active = a)
+}
+int nsb_shard_emulate(nsb_net* net, int32_t nranks, void* host_out, int32_t* mode_out) {
+  NET_CALL(net, NSB_REQUIRE(host_out, NSB_EINVAL, "null buffer"); net->n->shard_emulate(nranks, host_out, mode_out))
 }
 int nsb_qn_enable(nsb_net* net, int32_t nq, const int32_t* total) {
   NET_CALL(net, NSB_REQUIRE(total, NSB_EINVAL, "null"); net->n->qn_enable(nq, total))

@@ -119,6 +119,7 @@ struct Ctx {
     int jacobi_precondition_min_n = 1024;
     int sbr_staged = 0;              // experimental bulge-chasing kernel: shared-memory form of the task
     int qr_block_min = 64;           // min(rows, cols) from which the blocked compact-WY Householder QR is used
+    int nccl_sync = 0;               // host-synchronise the stream around every collective
     int qn_block_sparse = 1;         // QN networks: block-sparse storage + grouped sector GEMMs (0: dense storage)
   } opt;
   // per-launch GEMM timing (nsb_gemm_profile_*): CUDA events recorded on the stream around every GEMM launch while enabled;

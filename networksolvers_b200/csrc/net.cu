@@ -598,21 +598,30 @@ template <typename T>
 void Net<T>::nccl_check(int r, const char* what) {
   if (r != (int)ncclSuccess) throw Error(NSB_ENCCL, std::string(what) + ": " + nccl_api().GetErrorString((ncclResult_t)r));
 }
+// ctx option "nccl_sync": host-synchronise the stream before and after every collective (diagnostic / belt and braces)
+#define NSB_COMM_SYNC() do { if (ctx->opt.nccl_sync) ctx->sync(); } while (0)
+
 template <typename T>
 void Net<T>::comm_allreduce(T* buf, int64_t n) {
+  NSB_COMM_SYNC();
   nccl_check(nccl_api().AllReduce(buf, buf, (size_t)n * NcclType<T>::mult, ncclDouble, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream), "ncclAllReduce");
   ctx->cnt.kernel_launches++;
+  NSB_COMM_SYNC();
 }
 template <typename T>
 void Net<T>::comm_allgather(const T* send, T* recv, int64_t n_per_rank) {
+  NSB_COMM_SYNC();
   nccl_check(nccl_api().AllGather(send, recv, (size_t)n_per_rank * NcclType<T>::mult, ncclDouble, (ncclComm_t)ctx->nccl_comm, ctx->stream), "ncclAllGather");
   ctx->cnt.kernel_launches++;
+  NSB_COMM_SYNC();
 }
 template <typename T>
 void Net<T>::comm_reduce_scatter(const T* send, T* recv, int64_t n_per_rank) {
+  NSB_COMM_SYNC();
   nccl_check(nccl_api().ReduceScatter(send, recv, (size_t)n_per_rank * NcclType<T>::mult, ncclDouble, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream),
              "ncclReduceScatter");
   ctx->cnt.kernel_launches++;
+  NSB_COMM_SYNC();
 }
 
 // slab [lo, hi) of mode `l` of t: a view when l is the last mode, a strided copy when it is the first one
@@ -818,6 +827,75 @@ DTensor<T> Net<T>::heff_partial_from_slab(const DTensor<T>& xs, double* skipped)
   return X;
 }
 
+// AG positions: complete input xf (xs = this rank's slab of it) -> this rank's slab of theta'; the first contraction is
+// split along the first environment's bra index, no reduction is needed.
+template <typename T>
+DTensor<T> Net<T>::heff_slab_from_full(const DTensor<T>& xf, const DTensor<T>& xs, double* skipped) {
+  const int G = ctx->nranks;
+  DTensor<T> X = xf;
+  const DTensor<T>& E1 = envs.at({plan[0].u, plan[0].v}).t;
+  if (ctx->opt.skip_identity_sharded && skip_first_identity(X, shard_lo, shard_hi, &xs)) {
+    *skipped += 2.0 * (double)xf.numel() * (double)E1.dims[2];
+  } else {
+    X = contract(ctx, xf, E1.last_mode_slab(shard_lo, shard_hi), false, false, 1);
+  }
+  X = run_plan_steps(X, 1, plan.size() - 1);
+  double sk = 0.0;
+  if (plan.back().type == 0) X = last_env_contract(X, &sk);
+  else X = run_plan_steps(X, plan.size() - 1, plan.size());
+  *skipped += sk * (double)G;   // every rank skips its share: whole-job count
+  X = X.noprime();
+  if (X.labels != xs.labels) X = permuted(ctx, X, xs.labels);
+  NSB_REQUIRE(X.dims == xs.dims, NSB_EINTERNAL, "apply_heff_slab: unexpected result shape");
+  return X;
+}
+
+// Test hook: the arithmetic of the G-rank partition on ONE device -- for every rank r the partial result (RS / AR positions)
+// or the result slab (AG positions) is computed exactly as rank r would, and the collective is replaced by a local sum /
+// concatenation.  Lets the single-GPU test tier check the multi-GPU arithmetic at any rank count.
+template <typename T>
+void Net<T>::shard_emulate(int G, void* host_out, int32_t* mode_out) {
+  NSB_REQUIRE(theta.valid() && !plan.empty() && G >= 1, NSB_EINVAL, "shard_emulate: call nsb_extract first");
+  const int rank0 = ctx->rank, nranks0 = ctx->nranks;
+  void* comm0 = ctx->nccl_comm;
+  const bool en0 = shard_enabled;
+  DTensor<T> acc(ctx, theta.dims, theta.labels);
+  vec_zero<T>(ctx, acc.numel(), acc.data());
+  int mode = 0;
+  try {
+    for (int r = 0; r < G; ++r) {
+      ctx->rank = r; ctx->nranks = G; ctx->nccl_comm = (void*)1; shard_enabled = true;
+      shard_prepare();
+      mode = shard_active ? shard_mode : 0;
+      double sk = 0.0;
+      if (G == 1 || !shard_active) {     // this position is not partitioned at this rank count: every rank applies H_eff on its own
+        shard_active = false;
+        DTensor<T> y = apply_heff(theta);
+        vec_copy<T>(ctx, y.numel(), y.data(), acc.data());
+        break;
+      }
+      if (shard_hi <= shard_lo) continue;
+      DTensor<T> xs = theta.last_mode_slab(shard_lo, shard_hi);
+      if (shard_mode == 2) {
+        DTensor<T> ys = heff_slab_from_full(theta, xs, &sk);
+        vec_copy<T>(ctx, ys.numel(), ys.data(), acc.last_mode_slab(shard_lo, shard_hi).data());
+      } else {
+        DTensor<T> part = heff_partial_from_slab(xs, &sk);
+        vec_axpy<T>(ctx, acc.numel(), from_complex<T>(1.0, 0.0), part.data(), acc.data());
+      }
+    }
+  } catch (...) {
+    ctx->rank = rank0; ctx->nranks = nranks0; ctx->nccl_comm = comm0; shard_enabled = en0;
+    shard_prepare();
+    throw;
+  }
+  ctx->rank = rank0; ctx->nranks = nranks0; ctx->nccl_comm = comm0; shard_enabled = en0;
+  shard_prepare();
+  if (mode_out) *mode_out = mode;
+  NSB_CUDA(cudaMemcpyAsync(host_out, acc.data(), sizeof(T) * acc.numel(), cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->sync();
+}
+
 // Sharded application: slab of theta in, slab of theta' out (RS and AG positions).
 template <typename T>
 DTensor<T> Net<T>::apply_heff_slab(const DTensor<T>& xs) {
@@ -833,22 +911,7 @@ DTensor<T> Net<T>::apply_heff_slab(const DTensor<T>& xs) {
   } else {
     DTensor<T> xf(ctx, theta.dims, theta.labels);
     comm_allgather(xs.data(), xf.data(), xs.numel());
-    DTensor<T> X = xf;
-    const DTensor<T>& E1 = envs.at({plan[0].u, plan[0].v}).t;
-    if (ctx->opt.skip_identity_sharded && skip_first_identity(X, shard_lo, shard_hi, &xs)) {
-      skipped += 2.0 * (double)xf.numel() * (double)E1.dims[2];
-    } else {
-      X = contract(ctx, xf, E1.last_mode_slab(shard_lo, shard_hi), false, false, 1);
-    }
-    X = run_plan_steps(X, 1, plan.size() - 1);
-    double sk = 0.0;
-    if (plan.back().type == 0) X = last_env_contract(X, &sk);
-    else X = run_plan_steps(X, plan.size() - 1, plan.size());
-    skipped += sk * (double)G;   // every rank skips its share: whole-job count
-    X = X.noprime();
-    if (X.labels != xs.labels) X = permuted(ctx, X, xs.labels);
-    NSB_REQUIRE(X.dims == xs.dims, NSB_EINTERNAL, "apply_heff_slab: unexpected result shape");
-    out = X;
+    out = heff_slab_from_full(xf, xs, &skipped);
   }
   ctx->cnt.matvecs++;
   skipped_last_apply = skipped * (ScalarTraits<T>::is_complex ? 4.0 : 1.0);

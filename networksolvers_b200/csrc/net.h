@@ -47,6 +47,7 @@ struct NetBase {
                                     double cutoff, void* Qhost) = 0;
   virtual void expand_set_probe(int64_t rows, int64_t cols, const void* host) = 0;
   virtual int set_shard(int enable) = 0;   // returns 1 if the current position is sharded across ranks
+  virtual void shard_emulate(int G, void* host_out, int32_t* mode_out) = 0;
   // abelian quantum numbers (dense storage, block-wise factorisations)
   virtual void qn_enable(int nq, const int32_t* total) = 0;
   virtual void qn_set_site(int v, const int32_t* charges) = 0;
@@ -103,6 +104,8 @@ struct Net : public NetBase {
   bool krylov_sharded() const { return shard_active && (shard_mode == 1 || shard_mode == 2); }
   DTensor<T> apply_heff_slab(const DTensor<T>& xs);
   DTensor<T> heff_partial_from_slab(const DTensor<T>& xs, double* skipped);
+  DTensor<T> heff_slab_from_full(const DTensor<T>& xf, const DTensor<T>& xs, double* skipped);
+  void shard_emulate(int G, void* host_out, int32_t* mode_out) override;
   bool slab_of(const DTensor<T>& t, Label l, int64_t lo, int64_t hi, DTensor<T>* out);
   void nccl_check(int r, const char* what);
   void comm_allreduce(T* buf, int64_t n);

@@ -73,6 +73,10 @@ class Context:
         self.check(self._lib.nsb_mem_info(self.handle, C.byref(f), C.byref(t), C.byref(u)))
         return dict(free=f.value, total=t.value, pool_used=u.value)
 
+    def profiler(self, on=True):
+        """cudaProfilerStart / Stop (for `ncu --profile-from-start off`)."""
+        self.check(self._lib.nsb_profiler(self.handle, 1 if on else 0))
+
     def gemm_profile(self, on=True):
         """Start (and clear) / stop the per-launch CUDA-event timing of the GEMM kernels."""
         self.check(self._lib.nsb_gemm_profile_enable(self.handle, 1 if on else 0))
@@ -534,6 +538,14 @@ class DeviceNetwork:
         """One-shot random tensor (basis size x expand_space) for the next "ortho" expansion (instead of device Philox)."""
         a = np.asfortranarray(probe, dtype=self.dtype)
         self.ctx.check(self._lib.nsb_expand_set_probe(self.handle, a.shape[0], a.shape[1], a.ctypes.data))
+
+    def shard_emulate(self, nranks):
+        """H_eff theta with the arithmetic of an nranks-way partition on this one device (test hook); returns (theta', mode)."""
+        _, dims = self.local_info()
+        out = np.empty(dims, dtype=self.dtype, order="F")
+        mode = C.c_int32()
+        self.ctx.check(self._lib.nsb_shard_emulate(self.handle, int(nranks), out.ctypes.data, C.byref(mode)))
+        return out, mode.value
 
     def matvec_flops(self):
         f = C.c_double()

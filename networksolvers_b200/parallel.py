@@ -77,6 +77,9 @@ def setup_sharded_matvec(net, dist, rank, world, fused=False, init=True):
     net.ctx.set_option("shard_fused", 1 if fused else 0)
     active = C.c_int32()
     net.ctx.check(net._lib.nsb_net_set_shard(net.handle, 1, C.byref(active)))
+    if active.value and init:
+        net.matvec_device(1)          # one discarded application: NCCL sets its channels up for these buffer sizes
+        net.ctx.synchronize()
     return ShardedMatvec(net, bool(active.value))
 
 
