@@ -1911,6 +1911,17 @@ void Net<T>::matvec_device(int reps, void* host_out) {
       last_out = os;
       host_out = nullptr;
     }
+  } else if (krylov_blocks() && bt_apply_ok) {   // QN network: as the Krylov solvers do -- block vector in, block vector out
+    DTensor<T> v = kvec_start(), w;
+    for (int i = 0; i < reps; ++i) w = kapply(v);
+    if (host_out && w.valid()) {
+      BTensor<T> yb;
+      yb.st = theta_st; yb.buf = w.buf; yb.labels = theta.labels;
+      last_out = to_dense<T>(ctx, yb);
+    } else {
+      last_out = w;
+      host_out = nullptr;
+    }
   } else {
     for (int i = 0; i < reps; ++i) last_out = apply_heff(theta);
   }
