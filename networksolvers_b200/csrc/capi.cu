@@ -1,4 +1,6 @@
 // extern "C" boundary of libnsb200.so (declared in include/nsb200.h).  Nothing throws across it.
+#include <ctime>
+#include <cstdlib>
 #include "nccl_dyn.h"
 
 #include <random>
@@ -93,6 +95,31 @@ PhaseTimer::~PhaseTimer() {
   cudaEventDestroy(e1);
 }
 
+namespace {
+struct HostProfTable {
+  bool on;
+  std::map<std::string, std::pair<uint64_t, double>> acc;
+  HostProfTable() { const char* e = getenv("NSB_HOST_PROF"); on = e && e[0] == '1'; }
+  ~HostProfTable() {
+    if (!on) return;
+    for (auto& kv : acc) fprintf(stderr, "[host-prof] %-28s calls %8llu  total %10.3f ms  avg %9.2f us\n", kv.first.c_str(),
+                                 (unsigned long long)kv.second.first, kv.second.second * 1e3, kv.second.second * 1e6 / (double)kv.second.first);
+  }
+};
+HostProfTable g_host_prof;
+double wall_now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec; }
+}  // namespace
+HostProf::HostProf(Ctx* c, const char* n) : ctx(c), name(n), t0(0.0), active(g_host_prof.on && !c->is_helper) {
+  if (active) t0 = wall_now();
+}
+HostProf::~HostProf() {
+  if (!active) return;
+  cudaStreamSynchronize(ctx->stream);
+  auto& e = g_host_prof.acc[name];
+  e.first++;
+  e.second += wall_now() - t0;
+}
+
 }  // namespace nsb
 
 using namespace nsb;
@@ -185,6 +212,7 @@ int nsb_ctx_set_option(nsb_ctx* ctx, const char* key, int64_t value) {
   else if (k == "jacobi_pivot") { ctx->c.opt.jacobi_pivot = value != 0; }
   else if (k == "jacobi_inner_cap") { NSB_REQUIRE(value >= 1, NSB_EINVAL, "jacobi_inner_cap >= 1"); ctx->c.opt.jacobi_inner_cap = (int)value; }
   else if (k == "jacobi_precondition_min_n") { ctx->c.opt.jacobi_precondition_min_n = (int)value; }
+  else if (k == "jacobi_cluster_max_n") { NSB_REQUIRE(value >= 0 && value <= 4096, NSB_EINVAL, "jacobi_cluster_max_n 0..4096"); ctx->c.opt.jacobi_cluster_max_n = (int)value; }
   else if (k == "big_cache_gib") { NSB_REQUIRE(value >= 0, NSB_EINVAL, "big_cache_gib >= 0"); ctx->c.big_cache_cap = (size_t)value << 30; if (value == 0) ctx->c.flush_big_cache(); }
   else if (k == "sbr_staged") { ctx->c.opt.sbr_staged = value != 0; }
   else if (k == "skip_identity") { ctx->c.opt.skip_identity = value != 0; }

@@ -117,6 +117,8 @@ struct Ctx {
     int jacobi_inner_cap = 1;        // inner sweeps per pair solve
     int jacobi_pivot = 0;            // column pivoting in the preconditioning QR
     int jacobi_precondition_min_n = 1024;
+    int jacobi_cluster_max_n = 112;  // column count up to which the one-sided Jacobi runs as ONE launch (0: never); measured cross-over
+                                     // with the blocked (GEMM) Jacobi on B200: faster per sweep up to n ~ 120
     int sbr_staged = 0;              // experimental bulge-chasing kernel: shared-memory form of the task
     int qr_block_min = 64;           // min(rows, cols) from which the blocked compact-WY Householder QR is used
     int nccl_sync = 0;               // host-synchronise the stream around every collective
@@ -188,5 +190,13 @@ struct PhaseTimer {  // accumulates elapsed device time of a phase into ctx->tim
   ~PhaseTimer();
 };
 extern bool g_timers_enabled;
+
+// Host-side wall-clock profile of named scopes (diagnostic, env NSB_HOST_PROF=1): the scope synchronises the stream on exit so
+// that enqueued device work is charged to it; totals are printed to stderr when the process ends.
+struct HostProf {
+  Ctx* ctx; const char* name; double t0; bool active;
+  HostProf(Ctx* c, const char* n);
+  ~HostProf();
+};
 
 }  // namespace nsb

@@ -4,6 +4,8 @@
 #include "gemm.h"
 #include "eigh.h"
 
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <cmath>
 #include <numeric>
@@ -206,6 +208,9 @@ __global__ void __launch_bounds__(512) qr_panel_col_kernel(T* __restrict__ A, in
     s[1] += re(ar_) * re(xr_) + im(ar_) * im(xr_);
     s[2] += re(ar_) * im(xr_) - im(ar_) * re(xr_);
   }
+  // row j of this CTA's own column is read by every thread BEFORE the barriers of the block sum and rewritten by thread 0
+  // at the very end: reading it after the barriers would race with that store (a warp running ahead of a stalled one)
+  const T xj = (b > i && other) ? other[j] : zero_<T>();
   block_sum32<3>(s, sh);
   const T alpha = cj[j];
   const double sigma = s[0], ar = re(alpha), ai = im(alpha);
@@ -245,7 +250,6 @@ __global__ void __launch_bounds__(512) qr_panel_col_kernel(T* __restrict__ A, in
   }
   if (!other || trivial) return;
   T* cc = A + c * lda;
-  const T xj = cc[j];
   const T dot = add_(xj, cs);                                            // v^H x  (v_j = 1)
   const T f = mul_(conj_(t), dot);                                       // H^H x = x - conj(tau) (v^H x) v
   const T mf = from_complex<T>(-re(f), -im(f));
@@ -591,6 +595,236 @@ static int jacobi_onesided(Ctx* ctx, T* G, int64_t ldg, int64_t m, int64_t n, T*
   return sweep;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// One-sided (Hestenes) Jacobi for small matrices as ONE launch (the latency-bound regime: chi <~ 128, where a truncating
+// factorisation used to cost n - 1 launches per sweep and one host synchronisation per sweep).  One warp per column pair of
+// the round-robin round; a column pair of up to 32 * JC_ITEMS rows stays in registers between the Gram pass and the rotation.
+//   * jacobi_smem_kernel: one CTA of 16 warps, the matrix and the accumulated rotations resident in shared memory (224 KB:
+//     up to 118 x 118 real), rounds separated by __syncthreads.  One SM is instruction-issue bound from ~50 pairs per round
+//     on (measured 2.3 us per round at n = 64, 4.6 us at n = 100), which is what bounds the useful size.
+//   * jacobi_cluster_kernel: beyond that, one thread-block cluster of up to 8 CTAs x 16 warps on the L2-resident matrix,
+//     rounds separated by the hardware cluster barrier (barrier.cluster release / acquire) instead of a kernel boundary.
+// Convergence (no rotation in a full sweep) is decided on the device; the squared column norms and the sweep count are left
+// in `out` ([0, n) norms, [n] sweeps) for the single read-back the truncation rule needs anyway.
+// ------------------------------------------------------------------------------------------------
+constexpr int JC_WARPS = 16;        // warps per CTA of the cluster kernel
+constexpr int JS_THREADS = 512;     // threads of the shared-memory kernel (16 warps: 128 registers each, no spills)
+constexpr size_t JS_SMEM_MAX = 224 * 1024;
+template <typename T> struct JcItems;
+template <> struct JcItems<double> { static constexpr int N = 8; };
+template <> struct JcItems<cdouble> { static constexpr int N = 4; };
+
+// One column pair (gp, gq: m rows; vp, vq: nv rows), executed by one warp: Gram entries, rotation, update.  Returns whether
+// the pair was rotated (same value in every lane: the xor butterfly leaves identical bits everywhere).
+template <typename T, int IT>
+__device__ __forceinline__ bool jc_pair_it(T* gp, T* gq, int m, T* vp, T* vq, int nv, double tol2, int lane) {
+  const bool in_regs = m <= 32 * IT;
+  T a[IT], b[IT];
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  if (in_regs) {
+#pragma unroll
+    for (int k = 0; k < IT; ++k) {
+      const int r = lane + 32 * k;
+      a[k] = (r < m) ? gp[r] : zero_<T>();
+      b[k] = (r < m) ? gq[r] : zero_<T>();
+    }
+#pragma unroll
+    for (int k = 0; k < IT; ++k) {
+      s0 += abs2_(a[k]);
+      s1 += abs2_(b[k]);
+      s2 += re(a[k]) * re(b[k]) + im(a[k]) * im(b[k]);   // conj(a) * b
+      s3 += re(a[k]) * im(b[k]) - im(a[k]) * re(b[k]);
+    }
+  } else {
+    for (int r = lane; r < m; r += 32) {
+      const T x = gp[r], y = gq[r];
+      s0 += abs2_(x);
+      s1 += abs2_(y);
+      s2 += re(x) * re(y) + im(x) * im(y);
+      s3 += re(x) * im(y) - im(x) * re(y);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    if (ScalarTraits<T>::is_complex) s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+  }
+  const double gabs2 = s2 * s2 + s3 * s3;
+  if (gabs2 == 0.0 || gabs2 <= tol2 * s0 * s1) return false;
+  // rotation (c, s e^{i phi}) that annihilates a^H b; reciprocal square roots instead of the sqrt / div chain (each FP64 divide
+  // or square root is a long dependent sequence, and this scalar chain is the critical path of a round)
+  const double rg = rsqrt(gabs2);
+  const double zeta = (s1 - s0) * 0.5 * rg;
+  const double w = 1.0 + zeta * zeta;
+  const double tt = copysign(1.0, zeta) / (fabs(zeta) + w * rsqrt(w));
+  const double c = rsqrt(1.0 + tt * tt), sn = c * tt;
+  const double pr = s2 * rg, pi = -s3 * rg;   // e^{-i phi}
+  const T cq = from_complex<T>(c * pr, c * pi), sq = from_complex<T>(-sn * pr, -sn * pi);
+  const T cc = from_complex<T>(c, 0.0), ss = from_complex<T>(sn, 0.0);
+  if (in_regs) {
+#pragma unroll
+    for (int k = 0; k < IT; ++k) {
+      const int r = lane + 32 * k;
+      if (r < m) {
+        T na = mul_(cc, a[k]); fma_(na, sq, b[k]);
+        T nb = mul_(ss, a[k]); fma_(nb, cq, b[k]);
+        gp[r] = na; gq[r] = nb;
+      }
+    }
+  } else {
+    for (int r = lane; r < m; r += 32) {
+      const T x = gp[r], y = gq[r];
+      T na = mul_(cc, x); fma_(na, sq, y);
+      T nb = mul_(ss, x); fma_(nb, cq, y);
+      gp[r] = na; gq[r] = nb;
+    }
+  }
+  for (int r = lane; r < nv; r += 32) {
+    const T x = vp[r], y = vq[r];
+    T na = mul_(cc, x); fma_(na, sq, y);
+    T nb = mul_(ss, x); fma_(nb, cq, y);
+    vp[r] = na; vq[r] = nb;
+  }
+  return true;
+}
+
+// register depth by column length: the Gram and rotation loops of a short column do not pay for the longest one
+template <typename T>
+__device__ __forceinline__ bool jc_pair(T* gp, T* gq, int m, T* vp, T* vq, int nv, double tol2, int lane) {
+  constexpr int ITMAX = JcItems<T>::N;
+  if (m <= 32) return jc_pair_it<T, 1>(gp, gq, m, vp, vq, nv, tol2, lane);
+  if (m <= 64) return jc_pair_it<T, 2>(gp, gq, m, vp, vq, nv, tol2, lane);
+  if (m <= 128 || ITMAX == 4) return jc_pair_it<T, 4>(gp, gq, m, vp, vq, nv, tol2, lane);
+  return jc_pair_it<T, ITMAX>(gp, gq, m, vp, vq, nv, tol2, lane);
+}
+
+__device__ __forceinline__ bool jc_pair_of(int i, int round, int ring, int n, int* p, int* q) {
+  int a, b;
+  if (i == 0) { a = ring; b = round % ring; }
+  else { a = (round + i) % ring; b = (round + ring - i) % ring; }
+  if (a > b) { const int t = a; a = b; b = t; }
+  *p = a; *q = b;
+  return b < n;   // false: padded column
+}
+
+template <typename T>
+__device__ __forceinline__ void jc_finish(const T* G, int64_t ldg, int m, int n, int sweep, int gw, int nw, int lane, double* out) {
+  for (int c = gw; c < n; c += nw) {
+    const T* gc = G + (int64_t)c * ldg;
+    double s = 0.0;
+    for (int r = lane; r < m; r += 32) s += abs2_(gc[r]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[c] = s;
+  }
+  if (gw == 0 && lane == 0) out[n] = (double)sweep;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(JS_THREADS) jacobi_smem_kernel(T* G, int64_t ldg, int m, T* V, int64_t ldv, int nv, int n, int npad,
+                                                                 double tol2, int max_sweeps, int v_in_smem, double* out) {
+  extern __shared__ __align__(16) unsigned char jc_smem_raw[];
+  T* Gs = reinterpret_cast<T*>(jc_smem_raw);
+  T* Vs = Gs + (size_t)m * n;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int npairs = npad / 2, ring = npad - 1;
+  for (int e = threadIdx.x; e < m * n; e += blockDim.x) Gs[e] = G[(e % m) + (int64_t)(e / m) * ldg];
+  if (v_in_smem)
+    for (int e = threadIdx.x; e < nv * n; e += blockDim.x) Vs[e] = V[(e % nv) + (int64_t)(e / nv) * ldv];
+  __syncthreads();
+  T* Vb = v_in_smem ? Vs : V;
+  const int64_t ldvb = v_in_smem ? nv : ldv;
+  int sweep = 0;
+  for (; sweep < max_sweeps; ++sweep) {
+    int my_rot = 0;
+    for (int round = 0; round < ring; ++round) {
+      for (int i = warp; i < npairs; i += nw) {
+        int p, q;
+        if (!jc_pair_of(i, round, ring, n, &p, &q)) continue;
+        if (jc_pair<T>(Gs + (size_t)p * m, Gs + (size_t)q * m, m, Vb + p * ldvb, Vb + q * ldvb, nv, tol2, lane)) ++my_rot;
+      }
+      __syncthreads();
+    }
+    if (!__syncthreads_or(my_rot)) { ++sweep; break; }
+  }
+  for (int e = threadIdx.x; e < m * n; e += blockDim.x) G[(e % m) + (int64_t)(e / m) * ldg] = Gs[e];
+  if (v_in_smem)
+    for (int e = threadIdx.x; e < nv * n; e += blockDim.x) V[(e % nv) + (int64_t)(e / nv) * ldv] = Vs[e];
+  jc_finish<T>(Gs, m, m, n, sweep, warp, nw, lane, out);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(JC_WARPS * 32) jacobi_cluster_kernel(T* G, int64_t ldg, int m, T* V, int64_t ldv, int nv, int n,
+                                                                       int npad, double tol2, int max_sweeps, unsigned int* rot,
+                                                                       double* out) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nw = (int)cluster.num_blocks() * JC_WARPS, gw = (int)cluster.block_rank() * JC_WARPS + warp;
+  const int npairs = npad / 2, ring = npad - 1;
+  int sweep = 0;
+  for (; sweep < max_sweeps; ++sweep) {
+    unsigned int my_rot = 0;
+    for (int round = 0; round < ring; ++round) {
+      for (int i = gw; i < npairs; i += nw) {
+        int p, q;
+        if (!jc_pair_of(i, round, ring, n, &p, &q)) continue;
+        if (jc_pair<T>(G + (int64_t)p * ldg, G + (int64_t)q * ldg, m, V + (int64_t)p * ldv, V + (int64_t)q * ldv, nv, tol2, lane)) ++my_rot;
+      }
+      if (round == ring - 1 && lane == 0 && my_rot) atomicAdd(rot + sweep, my_rot);
+      cluster.sync();   // release / acquire at cluster scope: the columns written in this round are visible to their next owners
+    }
+    const unsigned int total = *reinterpret_cast<volatile unsigned int*>(rot + sweep);   // same value in every thread
+    if (total == 0u) { ++sweep; break; }
+  }
+  jc_finish<T>(G, ldg, m, n, sweep, gw, nw, lane, out);
+}
+
+// columns of G (m x n) orthogonalised in place, rotations accumulated in V (nv x n); out_dev: n + 1 doubles (see above)
+template <typename T>
+static void jacobi_single_launch(Ctx* ctx, T* G, int64_t ldg, int64_t m, int64_t n, T* V, int64_t ldv, int64_t nv, double* out_dev) {
+  const int npad = (int)((n % 2) ? n + 1 : n);
+  const int npairs = std::max(npad / 2, 1);
+  const int max_sweeps = 40;
+  // the Gram entries of orthogonal columns carry rounding noise ~ eps sqrt(m) (max over n^2 / 2 pairs several times that)
+  const double tol = 10.0 * std::sqrt((double)std::max<int64_t>(m, 1)) * 2.220446049250313e-16;
+  const double tol2 = tol * tol;
+  const size_t gbytes = sizeof(T) * (size_t)m * n, vbytes = sizeof(T) * (size_t)nv * n;
+  if (gbytes + vbytes <= JS_SMEM_MAX) {   // (measured: with V left in global memory the single CTA loses to the cluster form)
+    const int v_in_smem = 1;
+    const size_t smem = gbytes + vbytes;
+    static bool configured[2][64] = {{false}};
+    bool& c = configured[ScalarTraits<T>::is_complex ? 1 : 0][ctx->device & 63];
+    if (!c) { NSB_CUDA(cudaFuncSetAttribute(jacobi_smem_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JS_SMEM_MAX)); c = true; }
+    int threads = 32 * std::min(npairs, JS_THREADS / 32);
+    threads = std::max(threads, 128);   // (the staging loops and the final norms use every warp)
+    jacobi_smem_kernel<T><<<1, threads, smem, ctx->stream>>>(G, ldg, (int)m, V, ldv, (int)nv, (int)n, npad, tol2, max_sweeps, v_in_smem, out_dev);
+    LAUNCH_CHECK(ctx);
+    return;
+  }
+  DevBuf rot(ctx, sizeof(unsigned int) * max_sweeps);
+  NSB_CUDA(cudaMemsetAsync(rot.ptr, 0, sizeof(unsigned int) * max_sweeps, ctx->stream));
+  int csize = 1;
+  while (csize < 8 && csize * JC_WARPS < npairs) csize *= 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(csize);
+  cfg.blockDim = dim3(JC_WARPS * 32);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = csize;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  NSB_CUDA(cudaLaunchKernelEx(&cfg, jacobi_cluster_kernel<T>, G, ldg, (int)m, V, ldv, (int)nv, (int)n, npad, tol2, max_sweeps,
+                              (unsigned int*)rot.ptr, out_dev));
+  LAUNCH_CHECK(ctx);
+}
 
 // ------------------------------------------------------------------------------------------------
 // blocked one-sided Jacobi: column blocks of width B are paired (round-robin over blocks); for each pair the
@@ -1007,9 +1241,12 @@ FactorInfo factorize_left(Ctx* ctx, const T* M, int64_t rows, int64_t cols, int6
     // tall matrix: thin QR first, then factorise the square R from the left so that U = Q U_r is orthonormal
     // by construction (product of orthogonal transformations)
     DevBuf Mc(ctx, sizeof(T) * rows * cols), Q(ctx, sizeof(T) * rows * cols), R(ctx, sizeof(T) * cols * cols);
-    if (!trans_in) copy_block<T>(ctx, M, ld, (T*)Mc.ptr, rows, rows, cols);
-    else transpose_conj<T>(ctx, M, cols, rows, ld, (T*)Mc.ptr, rows, false);
-    qr_thin<T>(ctx, (T*)Mc.ptr, rows, cols, rows, (T*)Q.ptr, rows, (T*)R.ptr, cols);
+    {
+      HostProf hp(ctx, "factorize.tall_qr");
+      if (!trans_in) copy_block<T>(ctx, M, ld, (T*)Mc.ptr, rows, rows, cols);
+      else transpose_conj<T>(ctx, M, cols, rows, ld, (T*)Mc.ptr, rows, false);
+      qr_thin<T>(ctx, (T*)Mc.ptr, rows, cols, rows, (T*)Q.ptr, rows, (T*)R.ptr, cols);
+    }
     DevBuf Ur;
     ctx->cnt.svd_calls--;
     FactorInfo fi = factorize_left<T>(ctx, (const T*)R.ptr, cols, cols, cols, false, cutoff, mindim, maxdim, sqrt_spectrum, Ur, C, spectrum);
@@ -1021,6 +1258,7 @@ FactorInfo factorize_left(Ctx* ctx, const T* M, int64_t rows, int64_t cols, int6
   }
   const bool left = true;           // rows <= cols: rotate the row side, U = accumulated rotations
   const int64_t n = rows, m = cols;
+  HostProf hp_all(ctx, "factorize.jacobi_route");
   DevBuf G(ctx, sizeof(T) * m * n), V(ctx, sizeof(T) * n * n), Qm;
   std::vector<int32_t> pcol;        // column permutation of the preconditioned path
   const bool precond = (n >= ctx->opt.jacobi_block_min_n) && ctx->opt.jacobi_precondition && (n >= ctx->opt.jacobi_precondition_min_n);
@@ -1047,14 +1285,26 @@ FactorInfo factorize_left(Ctx* ctx, const T* M, int64_t rows, int64_t cols, int6
     ctx->sync();
   }
   set_identity<T>(ctx, (T*)V.ptr, n, n, n);
-  if (n >= ctx->opt.jacobi_block_min_n) info.sweeps = jacobi_blocked<T>(ctx, (T*)G.ptr, m, n, (T*)V.ptr, n);
-  else info.sweeps = jacobi_onesided<T>(ctx, (T*)G.ptr, m, m, n, (T*)V.ptr, n, n);
-
-  DevBuf norms(ctx, sizeof(double) * n);
-  col_norms2<T>(ctx, (T*)G.ptr, m, n, m, (double*)norms.ptr);
-  std::vector<double> P(n);
-  NSB_CUDA(cudaMemcpyAsync(P.data(), norms.ptr, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
-  ctx->sync();
+  DevBuf norms(ctx, sizeof(double) * (n + 1));
+  std::vector<double> P(n + 1);
+  // small matrices: the whole Jacobi iteration as one cluster launch (no launch per round, no host round trip per sweep)
+  const bool cluster = !precond && ctx->opt.jacobi_cluster_max_n > 0 && n >= 2 && n <= ctx->opt.jacobi_cluster_max_n && m <= 8192;
+  if (cluster) {
+    HostProf hp(ctx, "factorize.jacobi_1launch");
+    jacobi_single_launch<T>(ctx, (T*)G.ptr, m, m, n, (T*)V.ptr, n, n, (double*)norms.ptr);
+    NSB_CUDA(cudaMemcpyAsync(P.data(), norms.ptr, sizeof(double) * (n + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->sync();
+    info.sweeps = (int)P[n];
+    ctx->cnt.jacobi_sweeps += info.sweeps;
+  } else {
+    HostProf hp(ctx, "factorize.jacobi_rounds");
+    if (n >= ctx->opt.jacobi_block_min_n) info.sweeps = jacobi_blocked<T>(ctx, (T*)G.ptr, m, n, (T*)V.ptr, n);
+    else info.sweeps = jacobi_onesided<T>(ctx, (T*)G.ptr, m, m, n, (T*)V.ptr, n, n);
+    col_norms2<T>(ctx, (T*)G.ptr, m, n, m, (double*)norms.ptr);
+    NSB_CUDA(cudaMemcpyAsync(P.data(), norms.ptr, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->sync();
+  }
+  P.resize(n);
   std::vector<int32_t> order(n);
   std::iota(order.begin(), order.end(), 0);
   std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return P[a] > P[b]; });
@@ -1065,6 +1315,7 @@ FactorInfo factorize_left(Ctx* ctx, const T* M, int64_t rows, int64_t cols, int6
   info.newdim = nkeep;
   info.truncerr = terr;
 
+  HostProf hp_out(ctx, "factorize.gather_UC");
   DevBuf idx(ctx, sizeof(int32_t) * nkeep), scl(ctx, sizeof(double) * nkeep);
   NSB_CUDA(cudaMemcpyAsync(idx.ptr, order.data(), sizeof(int32_t) * nkeep, cudaMemcpyHostToDevice, ctx->stream));
   U = DevBuf(ctx, sizeof(T) * rows * nkeep);

@@ -1301,13 +1301,16 @@ void Net<T>::extract(const int32_t* reg, int nreg, const nsb_trunc* trunc, const
   if (nreg == 2) NSB_REQUIRE(eid.count({r[0], r[1]}), NSB_EINVAL, "extract: two-site region must be an edge");
   nsb_trunc tr = trunc ? *trunc : nsb_trunc{0.0, 1, INT64_MAX};
   int qr_steps, built;
+  HostProf hp_all(ctx, "extract");
   {
     PhaseTimer pt(ctx, NSB_T_GAUGE);
+    HostProf hp(ctx, "extract.gauge");
     qr_steps = orthogonalize(r);
   }
   region = r;
   {
     PhaseTimer pt(ctx, NSB_T_THETA);
+    HostProf hp(ctx, "extract.theta");
     theta = build_theta(r);
   }
   bool expanded = false;
@@ -1322,6 +1325,7 @@ void Net<T>::extract(const int32_t* reg, int nreg, const nsb_trunc* trunc, const
   }
   {
     PhaseTimer pt(ctx, NSB_T_ENV);
+    HostProf hp(ctx, "extract.env");
     built = position(r);
   }
   shard_prepare();
@@ -1421,6 +1425,7 @@ void Net<T>::update_eigsolve(const nsb_krylov* kp, double* eigval, nsb_solve_inf
   std::vector<double> alphas, betas;
   double beta = 0.0, beta_prev = 0.0;
   int nmv = 0;
+  HostProf hp_all(ctx, "eigsolve");
   DTensor<T> v = kvec_start();      // full local tensor, or this rank's slab of it (multi-GPU)
   const int64_t n = v.numel();
   {
@@ -1434,6 +1439,7 @@ void Net<T>::update_eigsolve(const nsb_krylov* kp, double* eigval, nsb_solve_inf
     DTensor<T> w;
     {
       PhaseTimer pt(ctx, NSB_T_MATVEC);
+      HostProf hp(ctx, "eigsolve.matvec");
       w = kapply(v);
       ++nmv;
     }
@@ -1774,6 +1780,7 @@ void Net<T>::insert(const nsb_trunc* trunc, int normalize, int set_ortho, nsb_in
     out.newdim = 0;
   } else {
     PhaseTimer pt(ctx, NSB_T_FACTORIZE);
+    HostProf hp(ctx, "insert.two_site");
     int v1 = region[0], v2 = region[1];
     Label bond = llink(v1, v2);
     std::vector<Label> left, right;

@@ -165,12 +165,14 @@ def test_factorize_blocked_jacobi(ctx, cplx, shape):
     M = _rand(rng, shape, cplx) * np.exp(-0.05 * np.arange(shape[1]))[None, :]
     ctx.set_option("jacobi_block_min_n", 0)
     ctx.set_option("jacobi_precondition_min_n", 0)
+    ctx.set_option("jacobi_cluster_max_n", 0)
     try:
         U, Cm, spec, info = ctx.factorize(M, cutoff=0.0)
         U2, C2, spec2, info2 = ctx.factorize(M, cutoff=1e-10, maxdim=shape[1] // 3)
     finally:
         ctx.set_option("jacobi_block_min_n", 48)
         ctx.set_option("jacobi_precondition_min_n", 1024)
+        ctx.set_option("jacobi_cluster_max_n", 112)
     s = np.linalg.svd(M, compute_uv=False)
     k = min(shape)
     assert info["newdim"] == k
@@ -183,3 +185,50 @@ def test_factorize_blocked_jacobi(ctx, cplx, shape):
     Ub, sb, Vb = np.linalg.svd(M, full_matrices=False)
     best = (Ub[:, :nk] * sb[:nk]) @ Vb[:nk]
     assert np.abs(U2 @ C2 - best).max() < 1e-10 * max(1.0, s[0])
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("shape", [(2, 2), (3, 3), (31, 31), (32, 64), (100, 100), (130, 100), (128, 128), (166, 166), (255, 300),
+                                   (256, 256), (4, 5000)])
+def test_factorize_cluster_jacobi(ctx, cplx, shape):
+    """The single-launch Jacobi kernels (one CTA with the matrix in shared memory; beyond 224 KB a thread-block cluster of up to
+    8 CTAs on the L2-resident matrix; register-resident column pairs up to 256 / 128 rows, streamed beyond)
+    against a known graded spectrum (12 decades of sigma^2): every sigma to ~1e-14 sigma_1, U orthonormal, U C = M, and the
+    truncation rule of the oracle on the same spectrum."""
+    from oracle.tensor import truncate_spectrum
+    rng = np.random.default_rng(31)
+    rows, cols = shape
+    k = min(shape)
+    Uo, _ = np.linalg.qr(_rand(rng, (rows, k), cplx))
+    Vo, _ = np.linalg.qr(_rand(rng, (cols, k), cplx))
+    sig = 10.0 ** (-6.0 * np.arange(k) / max(k - 1, 1))
+    M = (Uo * sig) @ Vo.conj().T
+    ctx.set_option("jacobi_cluster_max_n", 256)     # (default 112: above it the blocked Jacobi is faster)
+    try:
+        U, Cm, spec, info = ctx.factorize(M, cutoff=0.0)
+        U2, C2, spec2, info2 = ctx.factorize(M, cutoff=1e-10, maxdim=max(k // 2, 1))
+    finally:
+        ctx.set_option("jacobi_cluster_max_n", 112)
+    assert info["newdim"] == k and info["decomp"] == 1 and 1 <= info["sweeps"] <= 40
+    assert (np.abs(spec - sig**2) <= 4e-13 * sig * sig[0]).all()   # |d sigma| <~ 1e-13 sigma_1 over 12 decades of sigma^2
+    assert np.abs(U.conj().T @ U - np.eye(k)).max() < 1e-12
+    assert np.abs(U @ Cm - M).max() < 1e-13
+    nk, terr = truncate_spectrum(sig**2, cutoff=1e-10, mindim=1, maxdim=max(k // 2, 1))
+    assert info2["newdim"] == nk and abs(info2["truncerr"] - terr) <= 1e-8 * max(terr, 1e-30) + 1e-18
+    best = (Uo[:, :nk] * sig[:nk]) @ Vo[:, :nk].conj().T
+    assert np.abs(U2 @ C2 - best).max() < 1e-10
+
+
+def test_factorize_cluster_matches_round_kernels(ctx):
+    """Same matrix through the cluster launch and through the launch-per-round kernels: equal spectra and kept subspaces."""
+    rng = np.random.default_rng(37)
+    M = rng.standard_normal((40, 40)) * np.exp(-0.3 * np.arange(40))[None, :]
+    U, Cm, spec, info = ctx.factorize(M, cutoff=1e-12, maxdim=20)
+    ctx.set_option("jacobi_cluster_max_n", 0)
+    try:
+        U0, C0, spec0, info0 = ctx.factorize(M, cutoff=1e-12, maxdim=20)
+    finally:
+        ctx.set_option("jacobi_cluster_max_n", 112)
+    assert info["newdim"] == info0["newdim"]
+    assert np.abs(spec - spec0).max() <= 1e-13 * spec0[0]
+    assert np.abs(U @ Cm - U0 @ C0).max() < 1e-12

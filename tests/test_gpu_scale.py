@@ -80,3 +80,25 @@ def test_factorize_round_trip_at_scale(n, cplx):
     resid = np.linalg.norm(U @ C - M) ** 2 / np.linalg.norm(M) ** 2
     assert abs(resid - terr) <= 1e-6 * terr + 1e-14
     assert np.abs(spec[:k] - sig[:k] ** 2).max() <= 5e-12          # LAPACK-level absolute accuracy on sigma^2
+
+
+def test_synthetic_setup_is_bitwise_reproducible():
+    """Two builds of the same synthetic state (Philox fill, gauge walk = one blocked compact-WY QR per edge, environments) hold
+    bit-identical tensors and give a bit-identical H_eff application: what the multi-GPU path relies on when every rank builds
+    its replica independently (guards the write-after-read hazard the QR panel kernel once had on row j of the updated column)."""
+    import networksolvers_b200 as ns
+    g = ns.path_graph(24)
+    sites = ns.siteinds("S=1/2", g)
+    H = ns.ttno(ns.heisenberg(g), sites)
+    ctx = ns.default_context()
+    outs = []
+    for _ in range(3):
+        net = ns.DeviceNetwork.synthetic(H, sites, 1024, seed=1234, ctx=ctx, ortho_region=[12, 13], canonical=True)
+        net.extract([12, 13])
+        theta, _ = net.local_download()
+        y = net.matvec_device(1, download=True)
+        outs.append((np.array(theta), np.array(y), np.array(net.site(3)[0]), np.array(net.site(20)[0])))
+        net.close()
+    for o in outs[1:]:
+        for a, b in zip(outs[0], o):
+            assert np.array_equal(a, b)
