@@ -413,20 +413,34 @@ def run_config2(args, rank, world, local_rank):
     replicas = world if (shard is None and world > 1) else 1
 
     # ---- end-to-end through the host-buffer call ----
-    nbytes = int(np.prod(dims)) * 8
-    hin, keep1 = pinned_array(dims, np.float64)
+    # Multi-GPU: the caller holds theta distributed like the sharded Krylov solvers do -- every rank passes its slab of the last
+    # bond through nsb_matvec_host_slab (1 / N of the PCIe traffic per rank); single GPU: the whole vector (nsb_matvec_host).
+    lo, hi, last_dim = net.shard_range()
+    sdims = list(dims[:-1]) + [hi - lo]
+    nbytes = int(np.prod(sdims)) * 8            # per rank
+    hin, keep1 = pinned_array(sdims, np.float64)
     theta0, _ = net.local_download()
-    hin[...] = theta0
-    del theta0
-    hout, keep2 = pinned_array(dims, np.float64)
+    hin[...] = theta0[..., lo:hi]
+    hout, keep2 = pinned_array(sdims, np.float64)
     lib = ctx._lib
+    e2e_call = lib.nsb_matvec_host_slab if shard is not None else lib.nsb_matvec_host
     e2e_steps = max(3, min(args.steps, 5))
     for _ in range(2):
-        ctx.check(lib.nsb_matvec_host(net.handle, hin.ctypes.data, hout.ctypes.data))
+        ctx.check(e2e_call(net.handle, hin.ctypes.data, hout.ctypes.data))
+    if shard is not None and rank == 0:          # the slab call against the replicated call on the same input
+        yfull = net.matvec_host(theta0)
+        slab_err = float(np.abs(hout - yfull[..., lo:hi]).max() / np.abs(yfull).max())
+        assert slab_err <= 1e-12 or os.environ.get("NSB_BENCH_STRICT") != "1", slab_err
+    elif shard is not None:
+        net.matvec_host(theta0)                  # (collective inside: every rank takes part)
+        slab_err = None
+    else:
+        slab_err = None
+    del theta0
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        ctx.check(lib.nsb_matvec_host(net.handle, hin.ctypes.data, hout.ctypes.data))
+        ctx.check(e2e_call(net.handle, hin.ctypes.data, hout.ctypes.data))
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     if dist is not None:
         tt = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
@@ -520,8 +534,11 @@ def run_config2(args, rank, world, local_rank):
                            "state": ("random tensors orthonormalised to the benchmark bond (device QR gauge walk)" if not args.no_canonical else "random tensors, gauge flag only"),
                            "parallelism": ("replicated" if shard is None else net_parallelism(net, world, args))
                            if world > 1 else "single GPU", "setup_s": t_setup, "env_builds": info.env_builds},
-                "e2e": {"value": e2e_tflops, "unit": "TFLOP/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
-                        "ms_per_step": e2e_s * 1e3},
+                "e2e": {"value": e2e_tflops, "unit": "TFLOP/s", "h2d_bytes_per_step": nbytes * (world if shard is not None else 1),
+                        "d2h_bytes_per_step": nbytes * (world if shard is not None else 1), "ms_per_step": e2e_s * 1e3,
+                        "call": ("nsb_matvec_host_slab: every rank moves its slab of theta / theta' (bytes are the whole job's, "
+                                 f"{nbytes} per rank)" if shard is not None else "nsb_matvec_host"),
+                        **({"slab_vs_full_call_max_rel_err": slab_err} if slab_err is not None else {})},
                 "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roof,
                 "dense_equivalent_tflops": flops_dense / (ms_step * 1e-3) * 1e-12 * replicas}
         if shard_err is not None:

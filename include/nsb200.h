@@ -276,6 +276,12 @@ int nsb_local_download(nsb_net* net, void* host);
 int nsb_local_upload(nsb_net* net, const void* host);
 /* theta' = H_eff theta through the reference-facing call with HOST buffers (H2D + matvec + D2H). */
 int nsb_matvec_host(nsb_net* net, const void* host_in, void* host_out);
+/* The same with the vector DISTRIBUTED over the ranks of the communicator, as the sharded Krylov solvers hold it
+ * (theta sharded along its last bond): every rank passes only its slab [lo, hi) of the last mode (contiguous in
+ * the column-major local tensor) and receives the matching slab of theta'.  nsb_shard_range reports the slab; when the
+ * position is not slab-sharded (single GPU, uneven bond) the range is the whole mode and the call equals nsb_matvec_host. */
+int nsb_shard_range(nsb_net* net, int64_t* lo, int64_t* hi, int64_t* last_dim);
+int nsb_matvec_host_slab(nsb_net* net, const void* host_in_slab, void* host_out_slab);
 /* theta' = H_eff theta, `reps` times, device resident (output kept internally; download optional). */
 int nsb_matvec_device(nsb_net* net, int32_t reps, void* host_out /* nullable */);
 /* analytic flop count (real flops) of one H_eff application at the current position */

@@ -485,6 +485,10 @@ int nsb_local_upload(nsb_net* net, const void* host) { NET_CALL(net, NSB_REQUIRE
 int nsb_matvec_host(nsb_net* net, const void* host_in, void* host_out) {
   NET_CALL(net, NSB_REQUIRE(host_in && host_out, NSB_EINVAL, "null buffer"); net->n->matvec_host(host_in, host_out))
 }
+int nsb_matvec_host_slab(nsb_net* net, const void* host_in, void* host_out) {
+  NET_CALL(net, NSB_REQUIRE(host_in && host_out, NSB_EINVAL, "null buffer"); net->n->matvec_host_slab(host_in, host_out))
+}
+int nsb_shard_range(nsb_net* net, int64_t* lo, int64_t* hi, int64_t* last_dim) { NET_CALL(net, net->n->shard_range(lo, hi, last_dim)) }
 int nsb_matvec_device(nsb_net* net, int32_t reps, void* host_out) { NET_CALL(net, net->n->matvec_device(reps, host_out)) }
 int nsb_matvec_flops(nsb_net* net, double* flops) { NET_CALL(net, NSB_REQUIRE(flops, NSB_EINVAL, "null"); *flops = net->n->matvec_flops()) }
 int nsb_matvec_flops_executed(nsb_net* net, double* flops) {

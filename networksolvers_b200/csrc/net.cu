@@ -1906,6 +1906,26 @@ void Net<T>::matvec_host(const void* in, void* outp) {
   ctx->sync();
 }
 template <typename T>
+void Net<T>::shard_range(int64_t* lo, int64_t* hi, int64_t* last_dim) {
+  NSB_REQUIRE(theta.valid(), NSB_EINVAL, "shard_range: call nsb_extract first");
+  const int64_t d = theta.dims.back();
+  if (last_dim) *last_dim = d;
+  if (krylov_sharded()) { if (lo) *lo = shard_lo; if (hi) *hi = shard_hi; }
+  else { if (lo) *lo = 0; if (hi) *hi = d; }
+}
+template <typename T>
+void Net<T>::matvec_host_slab(const void* in, void* outp) {
+  NSB_REQUIRE(theta.valid() && !plan.empty(), NSB_EINVAL, "matvec: call nsb_extract first");
+  if (!krylov_sharded()) { matvec_host(in, outp); return; }
+  // slab in, slab out: what the sharded Krylov solvers do, with this rank's 1 / G of the host <-> device traffic
+  DTensor<T> full(ctx, theta.dims, theta.labels);                 // (only its slab is touched: a view needs a parent)
+  DTensor<T> xs = full.last_mode_slab(shard_lo, shard_hi);
+  NSB_CUDA(cudaMemcpyAsync(xs.data(), in, sizeof(T) * xs.numel(), cudaMemcpyHostToDevice, ctx->stream));
+  DTensor<T> os = apply_heff_slab(xs);
+  NSB_CUDA(cudaMemcpyAsync(outp, os.data(), sizeof(T) * os.numel(), cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->sync();
+}
+template <typename T>
 void Net<T>::matvec_device(int reps, void* host_out) {
   NSB_REQUIRE(theta.valid() && !plan.empty(), NSB_EINVAL, "matvec: call nsb_extract first");
   if (krylov_sharded()) {   // what the sharded Krylov solvers do: slab in, slab out

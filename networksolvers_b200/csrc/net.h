@@ -39,6 +39,8 @@ struct NetBase {
   virtual void local_sync() = 0;   // multi-GPU: complete a sharded local tensor on every rank (collective)
   virtual void local_upload(const void* host) = 0;
   virtual void matvec_host(const void* in, void* out) = 0;
+  virtual void matvec_host_slab(const void* in, void* out) = 0;
+  virtual void shard_range(int64_t* lo, int64_t* hi, int64_t* last_dim) = 0;
   virtual void matvec_device(int reps, void* host_out) = 0;
   virtual double matvec_flops() = 0;
   virtual double matvec_flops_executed() = 0;
@@ -216,6 +218,8 @@ struct Net : public NetBase {
   void local_sync() override { ensure_theta_full(); }
   void local_upload(const void* host) override;
   void matvec_host(const void* in, void* out) override;
+  void matvec_host_slab(const void* in, void* out) override;
+  void shard_range(int64_t* lo, int64_t* hi, int64_t* last_dim) override;
   void matvec_device(int reps, void* host_out) override;
   double matvec_flops() override;
   double matvec_flops_executed() override;

@@ -510,6 +510,20 @@ class DeviceNetwork:
         self.ctx.check(self._lib.nsb_matvec_host(self.handle, a.ctypes.data, out.ctypes.data))
         return out
 
+    def shard_range(self):
+        """(lo, hi, last_dim): this rank's slab of the local tensor's last mode at the current position (the whole mode when the
+        position is not slab-sharded)."""
+        lo, hi, d = C.c_int64(), C.c_int64(), C.c_int64()
+        self.ctx.check(self._lib.nsb_shard_range(self.handle, C.byref(lo), C.byref(hi), C.byref(d)))
+        return lo.value, hi.value, d.value
+
+    def matvec_host_slab(self, x_slab):
+        """H_eff application with the vector distributed over the ranks: this rank's slab in, the matching slab out."""
+        a = np.asfortranarray(x_slab, dtype=self.dtype)
+        out = np.empty(a.shape, dtype=self.dtype, order="F")
+        self.ctx.check(self._lib.nsb_matvec_host_slab(self.handle, a.ctypes.data, out.ctypes.data))
+        return out
+
     def matvec_device(self, reps=1, download=False):
         out = None
         if download:

@@ -67,6 +67,11 @@ def main():
                     n_.extract(reg)
                     th, _ = n_.local_download()
                     hv = n_.matvec_host(th)
+                    # distributed host-buffer call: this rank's slab in, the matching slab of theta' out
+                    lo, hi, d = n_.shard_range()
+                    assert (n_ is nets[0]) == ((lo, hi) == (0, d)) or world == 1, (lo, hi, d)
+                    hs = n_.matvec_host_slab(th[..., lo:hi])
+                    assert np.abs(hs - hv[..., lo:hi]).max() <= 1e-12 * np.abs(hv).max(), (reg, "slab call")
                     val, info = n_.update_eigsolve()
                     th2, _ = n_.local_download()
                     ins = n_.insert((1e-12, 1, 128))

@@ -430,3 +430,19 @@ def test_tdvp_two_site_with_expansion_quench_example():
                   updater_kwargs=dict(solver=o_rk, order=4), inserter_kwargs=ik)
     vo = state_vector(po)
     assert 1 - abs(np.vdot(vo, v)) < 1e-9
+
+
+def test_matvec_host_slab_equals_matvec_host_when_unsharded():
+    """nsb_matvec_host_slab / nsb_shard_range on one GPU: the slab is the whole last mode and the call is nsb_matvec_host
+    (the 2-GPU form of the same call is checked by tests/_nccl_shard_worker.py)."""
+    ns = _ns()
+    g = ns.path_graph(10)
+    sites = ns.siteinds("S=1/2", g)
+    H = ns.ttno(ns.heisenberg(g), sites)
+    psi = ns.random_state(sites, 24, seed=3)
+    net = ns.EigsolveProblem(state=psi, operator=H).net
+    net.extract([5, 6])
+    _, dims = net.local_info()
+    assert net.shard_range() == (0, dims[-1], dims[-1])
+    th, _ = net.local_download()
+    assert np.array_equal(net.matvec_host_slab(th), net.matvec_host(th))
