@@ -477,6 +477,9 @@ def run_config2(args, rank, world, local_rank):
                 "and divide & conquer replicated; tensors replicated in HBM")
         mi = ctx.mem_info()
         extra["hbm_pool_used_gib"] = mi["pool_used"] / 2**30
+        er, ef = net.env_bytes()
+        extra["env_hbm_gib_per_gpu"] = er / 2**30
+        extra["env_hbm_gib_if_replicated"] = ef / 2**30
 
     if not args.no_full_sweep and (world == 1 or args.full_sweep):
         # One real 2-site DMRG sweep (all 2 (N - 1) regions of the Euler tour) through the public driver, continuing on the

@@ -203,6 +203,10 @@ int nsb_linkdim(nsb_net* net, int32_t u, int32_t v, int64_t* dim);
 int nsb_maxlinkdim(nsb_net* net, int64_t* dim);
 int nsb_env_drop_all(nsb_net* net); /* forget cached environments (ProjTTN(H) freshly constructed) */
 int nsb_env_count(nsb_net* net, int32_t* n);
+/* bytes of environment tensors resident on this GPU, and what they would occupy replicated.  They differ on a multi-GPU
+ * communicator with ctx option "shard_envs" (default on): environments not incident to the current region are kept as 1 / G
+ * slabs per GPU and re-formed by an all-gather when the sweep returns to them. */
+int nsb_env_bytes(nsb_net* net, int64_t* resident, int64_t* replicated);
 
 /* ---- abelian quantum numbers (QN-conserving ITensors: `siteinds(...; conserve_qns=true)`, examples/dmrg.jl:10) ----
  * Tensors stay dense (symmetry-forbidden entries are exact zeros); with QNs enabled the three factorisations on the

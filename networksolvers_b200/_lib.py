@@ -144,6 +144,7 @@ SIGNATURES = {
     "nsb_local_upload": (C.c_int, [_vp, _vp]),
     "nsb_matvec_host": (C.c_int, [_vp, _vp, _vp]),
     "nsb_matvec_host_slab": (C.c_int, [_vp, _vp, _vp]),
+    "nsb_env_bytes": (C.c_int, [_vp, P(C.c_int64), P(C.c_int64)]),
     "nsb_shard_range": (C.c_int, [_vp, P(C.c_int64), P(C.c_int64), P(C.c_int64)]),
     "nsb_matvec_device": (C.c_int, [_vp, _i32, _vp]),
     "nsb_matvec_flops": (C.c_int, [_vp, P(_dbl)]),

@@ -230,6 +230,7 @@ int nsb_ctx_set_option(nsb_ctx* ctx, const char* key, int64_t value) {
   else if (k == "qr_block_min") { NSB_REQUIRE(value >= 0, NSB_EINVAL, "qr_block_min >= 0"); ctx->c.opt.qr_block_min = (int)value; }
   else if (k == "qn_block_sparse") { ctx->c.opt.qn_block_sparse = value != 0; }
   else if (k == "nccl_sync") { ctx->c.opt.nccl_sync = value != 0; }
+  else if (k == "shard_envs") { ctx->c.opt.shard_envs = value != 0; }
   else throw Error(NSB_EINVAL, "unknown option " + k);
   NSB_CATCH(&ctx->c)
 }
@@ -488,6 +489,7 @@ int nsb_matvec_host(nsb_net* net, const void* host_in, void* host_out) {
 int nsb_matvec_host_slab(nsb_net* net, const void* host_in, void* host_out) {
   NET_CALL(net, NSB_REQUIRE(host_in && host_out, NSB_EINVAL, "null buffer"); net->n->matvec_host_slab(host_in, host_out))
 }
+int nsb_env_bytes(nsb_net* net, int64_t* resident, int64_t* replicated) { NET_CALL(net, net->n->env_bytes(resident, replicated)) }
 int nsb_shard_range(nsb_net* net, int64_t* lo, int64_t* hi, int64_t* last_dim) { NET_CALL(net, net->n->shard_range(lo, hi, last_dim)) }
 int nsb_matvec_device(nsb_net* net, int32_t reps, void* host_out) { NET_CALL(net, net->n->matvec_device(reps, host_out)) }
 int nsb_matvec_flops(nsb_net* net, double* flops) { NET_CALL(net, NSB_REQUIRE(flops, NSB_EINVAL, "null"); *flops = net->n->matvec_flops()) }

@@ -121,6 +121,7 @@ struct Ctx {
                                      // with the blocked (GEMM) Jacobi on B200: faster per sweep up to n ~ 120
     int sbr_staged = 0;              // experimental bulge-chasing kernel: shared-memory form of the task
     int qr_block_min = 64;           // min(rows, cols) from which the blocked compact-WY Householder QR is used
+    int shard_envs = 1;              // multi-GPU: environments away from the current region are kept as 1 / G slabs per GPU
     int nccl_sync = 0;               // host-synchronise the stream around every collective
     int qn_block_sparse = 1;         // QN networks: block-sparse storage + grouped sector GEMMs (0: dense storage)
   } opt;

@@ -411,6 +411,7 @@ int Net<T>::make_env(int u, int v) {
   for (int n : others) built += make_env(n, u);
   NSB_REQUIRE(psi[u].valid() && W[u].valid(), NSB_EINVAL, "make_env: state or operator tensor missing");
   NSB_REQUIRE(!fit_mode || xket[u].valid(), NSB_EINVAL, "make_env: fitting target tensor missing");
+  for (int n : others) env_promote(envs.at({n, u}));     // (multi-GPU: inputs that live as slabs)
   if (qn_bs()) {     // QN network: the environment is built and kept as symmetry blocks (grouped sector GEMMs)
     Env benv;
     if (make_env_bt(u, v, others, &benv)) {
@@ -470,7 +471,69 @@ int Net<T>::make_env(int u, int v) {
   for (int n : others) for (auto& d : envs.at({n, u}).deps) env.deps.push_back(d);
   envs[key] = env;
   ctx->cnt.env_builds++;
+  if (env_sharding_on())      // the inputs are done with: keep only their slabs unless the current region touches them
+    for (int n : others) if (!env_is_hot(n, u)) env_demote(envs.at({n, u}));
   return built + 1;
+}
+
+// ---- multi-GPU: environments sharded in HBM ---------------------------------------
+template <typename T>
+bool Net<T>::env_sharding_on() const {
+  return shard_enabled && ctx->opt.shard_envs && ctx->nranks > 1 && ctx->nccl_comm && !fit_mode && !qn_on;
+}
+template <typename T>
+bool Net<T>::env_is_hot(int u, int v) const {
+  (void)u;
+  return std::find(hot_region.begin(), hot_region.end(), v) != hot_region.end() ||
+         std::find(pos.begin(), pos.end(), v) != pos.end();
+}
+template <typename T>
+void Net<T>::env_promote(Env& e) {
+  if (e.t.valid() || !e.shard.valid()) return;
+  DTensor<T> full(ctx, e.t.dims, e.t.labels);
+  comm_allgather(e.shard.data(), full.data(), e.shard.numel());
+  e.t = full;
+  e.shard = DTensor<T>();      // (cut again on the next demotion: a device copy of 1 / G of the tensor)
+}
+template <typename T>
+void Net<T>::env_demote(Env& e) {
+  if (!e.t.valid() || e.t.rank() != 3) return;
+  const int G = ctx->nranks;
+  const int64_t nb = e.t.dims[2];
+  if (nb % G != 0 || nb < 4 * G) return;
+  if (!e.shard.valid()) {
+    const int64_t per = nb / G;
+    DTensor<T> src = e.t.last_mode_slab(per * ctx->rank, per * (ctx->rank + 1));
+    e.shard = DTensor<T>(ctx, src.dims, src.labels);
+    vec_copy<T>(ctx, src.numel(), src.data(), e.shard.data());
+  }
+  DTensor<T> meta;             // dims / labels stay readable, the buffer goes back to the pool
+  meta.dims = e.t.dims;
+  meta.labels = e.t.labels;
+  e.t = meta;
+}
+template <typename T>
+void Net<T>::env_bytes(int64_t* resident, int64_t* replicated) {
+  int64_t r = 0, f = 0;
+  for (auto& kv : envs) {
+    const Env& e = kv.second;
+    int64_t n = 1;
+    for (int64_t d : e.t.dims) n *= d;
+    if (e.t.dims.empty()) n = 0;
+    f += n * (int64_t)sizeof(T);
+    if (e.t.valid()) r += n * (int64_t)sizeof(T);
+    if (e.shard.valid()) r += e.shard.numel() * (int64_t)sizeof(T);
+  }
+  if (resident) *resident = r;
+  if (replicated) *replicated = f;
+}
+template <typename T>
+void Net<T>::env_rebalance() {
+  if (!env_sharding_on()) return;
+  for (auto& kv : envs) {
+    if (env_is_hot(kv.first.first, kv.first.second)) env_promote(kv.second);
+    else env_demote(kv.second);
+  }
 }
 
 template <typename T>
@@ -523,10 +586,12 @@ int Net<T>::position(const std::vector<int>& reg) {
   }
   pos = reg;
   pos_on_edge = false;
+  hot_region = reg;
   int built = 0;
   for (int v : reg)
     for (int n : adj[v])
       if (std::find(reg.begin(), reg.end(), n) == reg.end()) built += make_env(n, v);
+  env_rebalance();
   build_plan();
   prepare_identity_skip();
   return built;
@@ -690,6 +755,8 @@ template <typename T>
 int Net<T>::set_shard(int enable) {
   shard_enabled = enable != 0;
   if (theta_is_slab) ensure_theta_full();
+  if (!shard_enabled) { for (auto& kv : envs) env_promote(kv.second); }   // replicated again
+  else env_rebalance();
   shard_prepare();
   return shard_active ? 1 : 0;
 }

@@ -41,6 +41,7 @@ struct NetBase {
   virtual void matvec_host(const void* in, void* out) = 0;
   virtual void matvec_host_slab(const void* in, void* out) = 0;
   virtual void shard_range(int64_t* lo, int64_t* hi, int64_t* last_dim) = 0;
+  virtual void env_bytes(int64_t* resident, int64_t* replicated) = 0;
   virtual void matvec_device(int reps, void* host_out) = 0;
   virtual double matvec_flops() = 0;
   virtual double matvec_flops_executed() = 0;
@@ -75,7 +76,9 @@ struct Net : public NetBase {
   // MPO-like operator between orthonormal bases), -1 if none
   // bt: block-sparse form (QN networks with ctx option qn_block_sparse): then t carries dims / labels only until a dense
   // consumer asks for it (env_dense)
-  struct Env { DTensor<T> t; std::vector<std::pair<int, uint64_t>> deps; int ident = -1; BTensor<T> bt; };
+  // shard: multi-GPU, ctx option shard_envs -- this rank's slab of t's last mode.  Environments that are not incident to the
+  // current region live only as such slabs (1 / G of the HBM on every GPU); an all-gather re-forms t when the sweep comes back.
+  struct Env { DTensor<T> t; std::vector<std::pair<int, uint64_t>> deps; int ident = -1; BTensor<T> bt; DTensor<T> shard; };
   std::map<std::pair<int, int>, Env> envs;      // key (u, v): everything on u's side, pointing into v
   // local problem
   DTensor<T> theta;
@@ -102,6 +105,13 @@ struct Net : public NetBase {
   bool theta_is_slab = false;                   // the local tensor currently lives as this rank's slab (after a sharded update)
   DTensor<T> theta_slab;
   void shard_prepare();
+  bool env_sharding_on() const;
+  bool env_is_hot(int u, int v) const;          // incident to the current region (or to the position being entered)
+  void env_promote(Env& e);                     // slab -> full tensor (all-gather); no-op when t is resident
+  void env_demote(Env& e);                      // keep only the slab; no-op when the environment cannot be split evenly
+  void env_rebalance();                         // promote the hot environments, demote all others
+  std::vector<int> hot_region;                  // region whose incident environments must stay resident
+  Env& env_at(int u, int v) { Env& e = envs.at({u, v}); env_promote(e); return e; }
   void ensure_theta_full();
   bool krylov_sharded() const { return shard_active && (shard_mode == 1 || shard_mode == 2); }
   DTensor<T> apply_heff_slab(const DTensor<T>& xs);
@@ -220,6 +230,7 @@ struct Net : public NetBase {
   void matvec_host(const void* in, void* out) override;
   void matvec_host_slab(const void* in, void* out) override;
   void shard_range(int64_t* lo, int64_t* hi, int64_t* last_dim) override;
+  void env_bytes(int64_t* resident, int64_t* replicated) override;
   void matvec_device(int reps, void* host_out) override;
   double matvec_flops() override;
   double matvec_flops_executed() override;

@@ -449,6 +449,7 @@ std::shared_ptr<BStruct> Net<T>::allowed_struct_in(const DTensor<T>& th, const s
 template <typename T>
 const DTensor<T>& Net<T>::env_dense(int u, int v) {
   Env& e = envs.at({u, v});
+  env_promote(e);
   if (!e.t.valid() && e.bt.valid()) {
     DTensor<T> d = to_dense<T>(ctx, e.bt);
     e.t.buf = d.buf;

@@ -510,6 +510,12 @@ class DeviceNetwork:
         self.ctx.check(self._lib.nsb_matvec_host(self.handle, a.ctypes.data, out.ctypes.data))
         return out
 
+    def env_bytes(self):
+        """(resident, replicated): bytes of environment tensors on this GPU, and their size if every one were held in full."""
+        r, f = C.c_int64(), C.c_int64()
+        self.ctx.check(self._lib.nsb_env_bytes(self.handle, C.byref(r), C.byref(f)))
+        return r.value, f.value
+
     def shard_range(self):
         """(lo, hi, last_dim): this rank's slab of the local tensor's last mode at the current position (the whole mode when the
         position is not slab-sharded)."""

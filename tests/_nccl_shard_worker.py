@@ -88,6 +88,19 @@ def main():
             t0 = t.clone()
             dist.broadcast(t0, src=0)
             assert torch.equal(t, t0), "ranks diverged"
+            # environments away from the region live as 1 / G slabs on the sharded network, in full on the other
+            r0, f0 = nets[0].env_bytes()
+            r1, f1 = nets[1].env_bytes()
+            assert r0 == f0 and f1 == f0 and r1 < f1, (r0, f0, r1, f1)
+            # ... and come back bit for bit: the energy expectation at the far end of the chain agrees with the replica
+            for reg in ([3, 2], [2, 3]):
+                vals = []
+                for n_ in nets:
+                    n_.extract(reg)
+                    th, _ = n_.local_download()
+                    hv = n_.matvec_host(th)
+                    vals.append(np.vdot(th, hv).real / np.vdot(th, th).real)
+                assert abs(vals[0] - vals[1]) <= 1e-11 * max(1.0, abs(vals[0])), (reg, vals)
     finally:
         ctx.set_option("eigh_min_n", 1024)
     if rank == 0:
