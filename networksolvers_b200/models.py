@@ -85,7 +85,8 @@ class OpSum:
         self.terms = []
 
     def add(self, coef, *ops_and_sites):
-        assert len(ops_and_sites) in (2, 4)
+        """os.add(c, "Sz", i) / os.add(c, "S+", i, "S-", j) / ... any number of (operator name, vertex) pairs."""
+        assert len(ops_and_sites) >= 2 and len(ops_and_sites) % 2 == 0
         self.terms.append((coef,) + tuple(ops_and_sites))
         return self
 
@@ -250,7 +251,26 @@ def random_state(sites: SiteSet, link_space, seed=1234, dtype=float):
     return HostTTN(g, tensors, legs, site_dim=sites.dim)
 
 
-def ttno(opsum: OpSum, sites: SiteSet, root=None, dtype=float):
+def _is_local_opsum(opsum: OpSum, g) -> bool:
+    for term in opsum.terms:
+        if len(term) == 3:
+            continue
+        if len(term) == 5 and term[2] != term[4] and g.has_edge(term[2], term[4]):
+            continue
+        return False
+    return True
+
+
+def ttno(opsum: OpSum, sites: SiteSet, root=None, dtype=float, cutoff=1e-14):
+    """Tree tensor network operator of an OpSum (`itn.ttn(opsum, sites)` / `itn.mpo`, examples/dmrg.jl:18,59).
+    One-site and nearest-neighbour two-site terms: the exact finite-state-machine construction below.  Anything else
+    (long-range or multi-site terms): sum of product operators compressed by SVD (`ttno_general`)."""
+    if not _is_local_opsum(opsum, sites.graph):
+        return ttno_general(opsum, sites, dtype=dtype, cutoff=cutoff)
+    return _ttno_local(opsum, sites, root=root, dtype=dtype)
+
+
+def _ttno_local(opsum: OpSum, sites: SiteSet, root=None, dtype=float):
     """Exact finite-state-machine TTNO for one-site and nearest-neighbour two-site terms.  Operator link
     states toward the root: 0 = identity so far, 1 = a complete term lies below, 2+k = term k of that edge
     started below.  Link dimension 2 + (#terms on the edge): 5 for Heisenberg, 3 for Ising."""
@@ -299,6 +319,152 @@ def ttno(opsum: OpSum, sites: SiteSet, root=None, dtype=float):
 
 
 mpo = ttno
+
+
+# ---- general OpSum -> compressed TTNO (operator construction with compression) ------------------
+def _site_first(H: HostTTN) -> HostTTN:
+    """Same operator with every tensor laid out [site, site_out, links in neighbour order]."""
+    g = H.graph
+    tensors, legs = {}, {}
+    for v in g.vertices:
+        want = [("site", v), ("site_out", v)] + [("link", v, n) for n in g.neighbors(v)]
+        perm = [H.legs[v].index(l) for l in want]
+        tensors[v] = np.ascontiguousarray(np.transpose(H.tensors[v], perm))
+        legs[v] = want
+    return HostTTN(g, tensors, legs, ortho_region=[], site_dim=H.site_dim)
+
+
+def operator_direct_sum(A: HostTTN, B: HostTTN) -> HostTTN:
+    """A + B as operators: block-diagonal operator links (link dimensions add), shared site legs."""
+    A, B = _site_first(A), _site_first(B)
+    g = A.graph
+    if len(g.vertices) == 1:
+        v = g.vertices[0]
+        return HostTTN(g, {v: A.tensors[v] + B.tensors[v]}, A.legs, ortho_region=[], site_dim=A.site_dim)
+    tensors = {}
+    for v in g.vertices:
+        ta, tb = A.tensors[v], B.tensors[v]
+        la, lb = ta.shape[2:], tb.shape[2:]
+        t = np.zeros(ta.shape[:2] + tuple(x + y for x, y in zip(la, lb)), dtype=np.result_type(ta, tb))
+        t[(slice(None), slice(None)) + tuple(slice(0, x) for x in la)] = ta
+        t[(slice(None), slice(None)) + tuple(slice(x, x + y) for x, y in zip(la, lb))] = tb
+        tensors[v] = t
+    return HostTTN(g, tensors, A.legs, ortho_region=[], site_dim=A.site_dim)
+
+
+def compress_operator(H: HostTTN, cutoff=1e-14, maxdim=None) -> HostTTN:
+    """Exact-to-`cutoff` compression of the operator links of a tree tensor network operator: QR sweep toward the root
+    (every tensor orthonormal toward it), then an Euler tour from the root that truncates each edge by SVD with the centre
+    on it (discarded squared singular values / total <= cutoff, at most maxdim kept) and returns by QR.  The operator is
+    treated as a state with site dimension d^2 (Frobenius norm), as ITensor does for `MPO(opsum)`."""
+    H = _site_first(H)
+    g = H.graph
+    if len(g.vertices) == 1:
+        return H
+    T = {v: np.array(t) for v, t in H.tensors.items()}
+    root = g.vertices[0]
+    post, parent = _dfs(g, root)
+
+    def axis(v, n):
+        return 2 + g.neighbors(v).index(n)
+
+    def split_toward(v, n, truncate):
+        """T[v] = (isometry toward n) * R; R is absorbed by n.  Centre moves v -> n."""
+        ax = axis(v, n)
+        t = np.moveaxis(T[v], ax, -1)
+        shp = t.shape
+        M = t.reshape(-1, shp[-1])
+        if truncate:
+            U, S, Vh = np.linalg.svd(M, full_matrices=False)
+            p = S ** 2
+            tot = p.sum()
+            k = len(S)
+            disc = 0.0
+            while k > 1 and (disc + p[k - 1] <= cutoff * tot or (maxdim is not None and k > maxdim)):
+                disc += p[k - 1]
+                k -= 1
+            Q, R = U[:, :k], S[:k, None] * Vh[:k]
+        else:
+            Q, R = np.linalg.qr(M)
+        T[v] = np.moveaxis(Q.reshape(shp[:-1] + (Q.shape[1],)), -1, ax)
+        an = axis(n, v)
+        T[n] = np.moveaxis(np.tensordot(R, np.moveaxis(T[n], an, 0), axes=(1, 0)), 0, an)
+
+    for v in post:                      # children before parents
+        if parent[v] is not None:
+            split_toward(v, parent[v], truncate=False)
+
+    def tour(v):
+        for c in g.neighbors(v):
+            if parent.get(c) == v:
+                split_toward(v, c, truncate=True)
+                tour(c)
+                split_toward(c, v, truncate=False)
+
+    import sys
+    lim = sys.getrecursionlimit()
+    sys.setrecursionlimit(max(lim, 4 * len(g.vertices) + 100))
+    try:
+        tour(root)
+    finally:
+        sys.setrecursionlimit(lim)
+    return HostTTN(g, T, H.legs, ortho_region=[], site_dim=H.site_dim)
+
+
+def ttno_general(opsum: OpSum, sites: SiteSet, dtype=float, cutoff=1e-14, batch=24) -> HostTTN:
+    """OpSum with arbitrary supports -> compressed TTNO: the terms enter `batch` at a time as a sum of product operators
+    (one operator-link state per term), each partial sum is compressed before the next batch is added, so the link dimension
+    never exceeds (compressed dimension + batch).  Operators repeated on one vertex are multiplied in the order written.
+    Fermionic strings are the caller's business (as in `hubbard` above)."""
+    op, d = sites.type.op, sites.dim
+    terms = []
+    for term in opsum.terms:
+        c, rest = term[0], term[1:]
+        ops = {}
+        for name, v in zip(rest[0::2], rest[1::2]):
+            m = np.asarray(op(name))
+            ops[v] = m if v not in ops else ops[v] @ m
+        terms.append((c, ops))
+    if not terms:
+        raise ValueError("empty OpSum")
+    cplx = any(np.iscomplexobj(m) for _, ops in terms for m in ops.values()) or any(np.iscomplexobj(c) for c, _ in terms)
+    dt = complex if (cplx or np.dtype(dtype).kind == "c") else dtype
+    acc = None
+    for i in range(0, len(terms), batch):
+        part = _product_matrix_sum(sites, terms[i:i + batch], dt)
+        acc = part if acc is None else operator_direct_sum(acc, part)
+        acc = compress_operator(acc, cutoff=cutoff)
+    # layout of ttno(): [links in neighbour order, site, site_out]
+    g = sites.graph
+    tensors, legs = {}, {}
+    for v in g.vertices:
+        nl = len(g.neighbors(v))
+        tensors[v] = np.ascontiguousarray(np.moveaxis(acc.tensors[v], (0, 1), (nl, nl + 1)))
+        legs[v] = [("link", v, n) for n in g.neighbors(v)] + [("site", v), ("site_out", v)]
+    return HostTTN(g, tensors, legs, ortho_region=[], site_dim=d)
+
+
+def _product_matrix_sum(sites: SiteSet, terms, dtype):
+    """sum_k c_k prod_v M_k(v) with explicit matrices: one operator-link state per term (cf. product_operator_sum)."""
+    g = sites.graph
+    d = sites.dim
+    nt = len(terms)
+    root = g.vertices[0]
+    tensors, legs = {}, {}
+    for v in g.vertices:
+        nb = g.neighbors(v)
+        legs[v] = [("site", v), ("site_out", v)] + [("link", v, n) for n in nb]
+        t = np.zeros([d, d] + [nt] * len(nb), dtype=dtype)
+        for k, (c, ops) in enumerate(terms):
+            m = ops[v] if v in ops else np.eye(d)
+            if v == root:
+                m = c * m
+            if nb:
+                t[(slice(None), slice(None)) + (k,) * len(nb)] = np.asarray(m, dtype=dtype).T      # (in, out): <out| m |in>
+            else:
+                t += np.asarray(m, dtype=dtype).T
+        tensors[v] = t
+    return HostTTN(g, tensors, legs, ortho_region=[], site_dim=d)
 
 
 # ---- fitting helpers (src/fitting.jl:90-112) -----------------------------------------------------------------

@@ -446,3 +446,34 @@ def test_matvec_host_slab_equals_matvec_host_when_unsharded():
     assert net.shard_range() == (0, dims[-1], dims[-1])
     th, _ = net.local_download()
     assert np.array_equal(net.matvec_host_slab(th), net.matvec_host(th))
+
+
+def test_dmrg_with_compressed_long_range_ttno():
+    """A Hamiltonian the nearest-neighbour builder cannot express (J1-J2 chain, N = 12) through the general OpSum -> compressed
+    TTNO construction: per-sweep energies equal the oracle's on the same operator tensors (1e-10), final energy = ED."""
+    ns = _ns()
+    g = ns.path_graph(12)
+    V = g.vertices
+    sites = ns.siteinds("S=1/2", g)
+    os_ = ns.OpSum()
+    for r, J in ((1, 1.0), (2, 0.35)):
+        for i in range(len(V) - r):
+            os_.add(J, "Sz", V[i], "Sz", V[i + r])
+            os_.add(J / 2, "S+", V[i], "S-", V[i + r])
+            os_.add(J / 2, "S-", V[i], "S+", V[i + r])
+    H = ns.ttno(os_, sites)
+    assert H.maxlinkdim() == 8
+    psi0 = ns.product_state(sites, neel(g))
+    trunc = dict(cutoff=1e-12, maxdim=64)
+    rec = SweepRecorder()
+    E, psi = ns.dmrg(H, psi0, nsweeps=5, nsites=2, inserter_kwargs=dict(trunc=trunc), sweep_callback=rec.sweep)
+    Eo, _, orec = _oracle_sweeps(to_oracle_ttn(H, True), to_oracle_ttn(psi0), nsweeps=5, nsites=2, inserter_kwargs=dict(trunc=trunc))
+    for a, b in zip(rec.energies, orec["E"]):
+        assert abs(a - b) <= 1e-10 * abs(b), (rec.energies, orec["E"])
+    from functools import reduce
+    op, d = sites.type.op, 2
+    Hd = np.zeros((d ** 12,) * 2)
+    for term in os_.terms:
+        mats = {v: np.asarray(op(nm)).real for nm, v in zip(term[1::2], term[2::2])}
+        Hd += term[0] * reduce(np.kron, [mats.get(v, np.eye(d)) for v in V])
+    assert abs(E - np.linalg.eigvalsh(Hd)[0]) < 1e-8
