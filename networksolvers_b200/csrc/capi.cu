@@ -223,6 +223,7 @@ int nsb_ctx_set_option(nsb_ctx* ctx, const char* key, int64_t value) {
   else if (k == "eigh_coop_ctas") { NSB_REQUIRE(value >= 1 && value <= 8, NSB_EINVAL, "eigh_coop_ctas 1..8"); ctx->c.opt.eigh_coop_ctas = (int)value; }
   else if (k == "eigh_direct_min_n") ctx->c.opt.eigh_direct_min_n = (int)value;
   else if (k == "eigh_sym") ctx->c.opt.eigh_sym = value ? 1 : 0;
+  else if (k == "eigh_l2_persist") ctx->c.opt.eigh_l2_persist = value ? 1 : 0;
   else if (k == "eigh_sym_tc") { NSB_REQUIRE(value == 0 || value == 16 || value == 32 || value == 64 || value == 128, NSB_EINVAL, "eigh_sym_tc must be 0, 16, 32, 64 or 128"); ctx->c.opt.eigh_sym_tc = (int)value; }
   else if (k == "eigh_split") { NSB_REQUIRE(value >= 1 && value <= 16, NSB_EINVAL, "eigh_split 1..16"); ctx->c.opt.eigh_split = (int)value; }
   else if (k == "eigh_wb") { NSB_REQUIRE(value >= 2 && value <= 256 && value % 2 == 0, NSB_EINVAL, "eigh_wb must be even, 2..256"); ctx->c.opt.eigh_wb = (int)value; }

@@ -110,6 +110,7 @@ struct Ctx {
     int eigh_coop_ctas = 3;          // CTAs per SM of the cooperative panel kernel
     int eigh_sym = 1;                // real FP64, even n: symmetric (half-traffic) panel kernel
     int eigh_sym_tc = 0;             // its column-block width (0: chosen per column from {64, 32, 16})
+    int eigh_l2_persist = 1;         // tridiagonalisation: pin part of the trailing matrix in L2 (access-policy window)
     int eigh_split = 8;              // maximum number of row slabs of the split-K product Y = V^H U (back-transformation)
     int eigh_wb = 128;               // reflectors per compact-WY block of the back-transformation
     int jacobi_block_min_n = 48;     // column count from which the blocked (GEMM-rich) Jacobi is used
