@@ -788,7 +788,7 @@ template <typename T>
 static void jacobi_single_launch(Ctx* ctx, T* G, int64_t ldg, int64_t m, int64_t n, T* V, int64_t ldv, int64_t nv, double* out_dev) {
   const int npad = (int)((n % 2) ? n + 1 : n);
   const int npairs = std::max(npad / 2, 1);
-  const int max_sweeps = 40;
+  const int max_sweeps = 60;
   // the Gram entries of orthogonal columns carry rounding noise ~ eps sqrt(m) (max over n^2 / 2 pairs several times that)
   const double tol = 10.0 * std::sqrt((double)std::max<int64_t>(m, 1)) * 2.220446049250313e-16;
   const double tol2 = tol * tol;

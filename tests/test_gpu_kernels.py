@@ -209,7 +209,7 @@ def test_factorize_cluster_jacobi(ctx, cplx, shape):
         U2, C2, spec2, info2 = ctx.factorize(M, cutoff=1e-10, maxdim=max(k // 2, 1))
     finally:
         ctx.set_option("jacobi_cluster_max_n", 112)
-    assert info["newdim"] == k and info["decomp"] == 1 and 1 <= info["sweeps"] <= 40
+    assert info["newdim"] == k and info["decomp"] == 1 and 1 <= info["sweeps"] < 60
     assert (np.abs(spec - sig**2) <= 4e-13 * sig * sig[0]).all()   # |d sigma| <~ 1e-13 sigma_1 over 12 decades of sigma^2
     assert np.abs(U.conj().T @ U - np.eye(k)).max() < 1e-12
     assert np.abs(U @ Cm - M).max() < 1e-13
