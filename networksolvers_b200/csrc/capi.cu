@@ -212,6 +212,8 @@ int nsb_ctx_set_option(nsb_ctx* ctx, const char* key, int64_t value) {
   else if (k == "jacobi_pivot") { ctx->c.opt.jacobi_pivot = value != 0; }
   else if (k == "jacobi_inner_cap") { NSB_REQUIRE(value >= 1, NSB_EINVAL, "jacobi_inner_cap >= 1"); ctx->c.opt.jacobi_inner_cap = (int)value; }
   else if (k == "jacobi_precondition_min_n") { ctx->c.opt.jacobi_precondition_min_n = (int)value; }
+  else if (k == "jacobi_dsmem_min_n") { NSB_REQUIRE(value >= 0, NSB_EINVAL, "jacobi_dsmem_min_n >= 0"); ctx->c.opt.jacobi_dsmem_min_n = (int)value; }
+  else if (k == "jacobi_dsmem_max_n") { NSB_REQUIRE(value >= 0 && value <= 256, NSB_EINVAL, "jacobi_dsmem_max_n 0..256"); ctx->c.opt.jacobi_dsmem_max_n = (int)value; }
   else if (k == "jacobi_cluster_max_n") { NSB_REQUIRE(value >= 0 && value <= 4096, NSB_EINVAL, "jacobi_cluster_max_n 0..4096"); ctx->c.opt.jacobi_cluster_max_n = (int)value; }
   else if (k == "big_cache_gib") { NSB_REQUIRE(value >= 0, NSB_EINVAL, "big_cache_gib >= 0"); ctx->c.big_cache_cap = (size_t)value << 30; if (value == 0) ctx->c.flush_big_cache(); }
   else if (k == "sbr_staged") { ctx->c.opt.sbr_staged = value != 0; }
@@ -228,6 +230,7 @@ int nsb_ctx_set_option(nsb_ctx* ctx, const char* key, int64_t value) {
   else if (k == "eigh_split") { NSB_REQUIRE(value >= 1 && value <= 16, NSB_EINVAL, "eigh_split 1..16"); ctx->c.opt.eigh_split = (int)value; }
   else if (k == "eigh_wb") { NSB_REQUIRE(value >= 2 && value <= 256 && value % 2 == 0, NSB_EINVAL, "eigh_wb must be even, 2..256"); ctx->c.opt.eigh_wb = (int)value; }
   else if (k == "eigh_nb") { NSB_REQUIRE(value >= 2 && value <= 128 && value % 2 == 0, NSB_EINVAL, "eigh_nb must be even, 2..128"); ctx->c.opt.eigh_nb = (int)value; }
+  else if (k == "qr_smem") { ctx->c.opt.qr_smem = value != 0; }
   else if (k == "qr_block_min") { NSB_REQUIRE(value >= 0, NSB_EINVAL, "qr_block_min >= 0"); ctx->c.opt.qr_block_min = (int)value; }
   else if (k == "qn_block_sparse") { ctx->c.opt.qn_block_sparse = value != 0; }
   else if (k == "nccl_sync") { ctx->c.opt.nccl_sync = value != 0; }

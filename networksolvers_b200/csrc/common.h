@@ -118,9 +118,12 @@ struct Ctx {
     int jacobi_inner_cap = 1;        // inner sweeps per pair solve
     int jacobi_pivot = 0;            // column pivoting in the preconditioning QR
     int jacobi_precondition_min_n = 1024;
+    int jacobi_dsmem_min_n = 41;     // column range of the cluster / distributed-shared-memory tournament Jacobi (needs columns of
+    int jacobi_dsmem_max_n = 256;    // <= 256 real / 128 complex rows; other shapes fall through to the kernels below)
     int jacobi_cluster_max_n = 112;  // column count up to which the one-sided Jacobi runs as ONE launch (0: never); measured cross-over
                                      // with the blocked (GEMM) Jacobi on B200: faster per sweep up to n ~ 120
     int sbr_staged = 0;              // experimental bulge-chasing kernel: shared-memory form of the task
+    int qr_smem = 1;                 // thin QR of a matrix that fits in shared memory (with its Q) as one launch
     int qr_block_min = 64;           // min(rows, cols) from which the blocked compact-WY Householder QR is used
     int shard_envs = 1;              // multi-GPU: environments away from the current region are kept as 1 / G slabs per GPU
     int nccl_sync = 0;               // host-synchronise the stream around every collective

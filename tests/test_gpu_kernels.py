@@ -59,11 +59,21 @@ def test_gemm_unaligned_leading_dimension(ctx, impl):
 
 
 @pytest.mark.parametrize("cplx", [False, True])
-@pytest.mark.parametrize("shape", [(1, 1), (7, 3), (3, 7), (64, 64), (150, 40), (40, 150)])
-def test_qr(ctx, cplx, shape):
+@pytest.mark.parametrize("smem", [1, 0])
+@pytest.mark.parametrize("shape", [(1, 1), (7, 3), (3, 7), (64, 64), (150, 40), (40, 150), (128, 100), (33, 1)])
+def test_qr(ctx, cplx, shape, smem):
+    """Thin QR: the single-launch shared-memory kernel (smem = 1: everything here fits) and the column-at-a-time / blocked
+    kernels (smem = 0) it replaces at these sizes."""
     rng = np.random.default_rng(11)
     M = _rand(rng, shape, cplx)
-    Q, R = ctx.qr(M)
+    if shape == (128, 100):
+        M[:, 7] = 0.0                   # trivial reflector
+        M[:, 50] = M[:, 2]              # dependent column
+    ctx.set_option("qr_smem", smem)
+    try:
+        Q, R = ctx.qr(M)
+    finally:
+        ctx.set_option("qr_smem", 1)
     k = min(shape)
     assert Q.shape == (shape[0], k) and R.shape == (k, shape[1])
     assert np.abs(Q.conj().T @ Q - np.eye(k)).max() < 1e-13
@@ -81,7 +91,11 @@ def test_qr_blocked_compact_wy(ctx, cplx, shape):
     M = _rand(rng, shape, cplx)
     M[:, 5] = 0.0                       # zero column: trivial reflector inside a panel
     M[:, min(70, shape[1] - 1)] = M[:, 3]     # linearly dependent column (second panel when there is one)
-    Q, R = ctx.qr(M)
+    ctx.set_option("qr_smem", 0)        # (130 x 64 would fit the single-launch kernel)
+    try:
+        Q, R = ctx.qr(M)
+    finally:
+        ctx.set_option("qr_smem", 1)
     k = min(shape)
     assert Q.shape == (shape[0], k) and R.shape == (k, shape[1])
     assert np.abs(Q.conj().T @ Q - np.eye(k)).max() < 5e-13
@@ -166,6 +180,7 @@ def test_factorize_blocked_jacobi(ctx, cplx, shape):
     ctx.set_option("jacobi_block_min_n", 0)
     ctx.set_option("jacobi_precondition_min_n", 0)
     ctx.set_option("jacobi_cluster_max_n", 0)
+    ctx.set_option("jacobi_dsmem_max_n", 0)
     try:
         U, Cm, spec, info = ctx.factorize(M, cutoff=0.0)
         U2, C2, spec2, info2 = ctx.factorize(M, cutoff=1e-10, maxdim=shape[1] // 3)
@@ -173,6 +188,7 @@ def test_factorize_blocked_jacobi(ctx, cplx, shape):
         ctx.set_option("jacobi_block_min_n", 48)
         ctx.set_option("jacobi_precondition_min_n", 1024)
         ctx.set_option("jacobi_cluster_max_n", 112)
+        ctx.set_option("jacobi_dsmem_max_n", 256)
     s = np.linalg.svd(M, compute_uv=False)
     k = min(shape)
     assert info["newdim"] == k
@@ -203,12 +219,14 @@ def test_factorize_cluster_jacobi(ctx, cplx, shape):
     Vo, _ = np.linalg.qr(_rand(rng, (cols, k), cplx))
     sig = 10.0 ** (-6.0 * np.arange(k) / max(k - 1, 1))
     M = (Uo * sig) @ Vo.conj().T
-    ctx.set_option("jacobi_cluster_max_n", 256)     # (default 112: above it the blocked Jacobi is faster)
+    ctx.set_option("jacobi_cluster_max_n", 256)     # (defaults: 112, and the tournament kernel takes 41 .. 256 first)
+    ctx.set_option("jacobi_dsmem_max_n", 0)
     try:
         U, Cm, spec, info = ctx.factorize(M, cutoff=0.0)
         U2, C2, spec2, info2 = ctx.factorize(M, cutoff=1e-10, maxdim=max(k // 2, 1))
     finally:
         ctx.set_option("jacobi_cluster_max_n", 112)
+        ctx.set_option("jacobi_dsmem_max_n", 256)
     assert info["newdim"] == k and info["decomp"] == 1 and 1 <= info["sweeps"] < 60
     assert (np.abs(spec - sig**2) <= 4e-13 * sig * sig[0]).all()   # |d sigma| <~ 1e-13 sigma_1 over 12 decades of sigma^2
     assert np.abs(U.conj().T @ U - np.eye(k)).max() < 1e-12
@@ -232,3 +250,38 @@ def test_factorize_cluster_matches_round_kernels(ctx):
     assert info["newdim"] == info0["newdim"]
     assert np.abs(spec - spec0).max() <= 1e-13 * spec0[0]
     assert np.abs(U @ Cm - U0 @ C0).max() < 1e-12
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("shape", [(2, 2), (5, 7), (40, 40), (120, 120), (128, 128), (166, 166), (130, 200), (255, 256), (256, 256)])
+def test_factorize_dsmem_tournament_jacobi(ctx, cplx, shape):
+    """The cluster / distributed-shared-memory tournament Jacobi (one warp per slot, columns handed between CTAs through
+    st.shared::cluster), forced at every size it accepts (columns of <= 256 real / 128 complex rows), against a known graded
+    spectrum and the oracle's truncation rule; 1, 2, 4 and 8 CTAs, padded slots (odd n, n not a multiple of the cluster)."""
+    from oracle.tensor import truncate_spectrum
+    if cplx and max(shape) > 128:
+        pytest.skip("complex columns longer than 128 rows do not fit the register depth: routed to the other kernels")
+    rng = np.random.default_rng(41)
+    rows, cols = shape
+    k = min(shape)
+    Uo, _ = np.linalg.qr(_rand(rng, (rows, k), cplx))
+    Vo, _ = np.linalg.qr(_rand(rng, (cols, k), cplx))
+    sig = 10.0 ** (-6.0 * np.arange(k) / max(k - 1, 1))
+    M = (Uo * sig) @ Vo.conj().T
+    ctx.set_option("jacobi_cluster_max_n", 0)
+    ctx.set_option("jacobi_dsmem_min_n", 0)
+    ctx.reset_counters()
+    try:
+        U, Cm, spec, info = ctx.factorize(M, cutoff=0.0)
+        U2, C2, spec2, info2 = ctx.factorize(M, cutoff=1e-10, maxdim=max(k // 2, 1))
+    finally:
+        ctx.set_option("jacobi_cluster_max_n", 112)
+        ctx.set_option("jacobi_dsmem_min_n", 41)
+    assert info["newdim"] == k and info["decomp"] == 1 and 1 <= info["sweeps"] < 60
+    assert (np.abs(spec - sig**2) <= 4e-13 * sig * sig[0]).all()
+    assert np.abs(U.conj().T @ U - np.eye(k)).max() < 1e-12
+    assert np.abs(U @ Cm - M).max() < 1e-13
+    nk, terr = truncate_spectrum(sig**2, cutoff=1e-10, mindim=1, maxdim=max(k // 2, 1))
+    assert info2["newdim"] == nk and abs(info2["truncerr"] - terr) <= 1e-8 * max(terr, 1e-30) + 1e-18
+    best = (Uo[:, :nk] * sig[:nk]) @ Vo[:, :nk].conj().T
+    assert np.abs(U2 @ C2 - best).max() < 1e-10

@@ -9,8 +9,9 @@ rng = np.random.default_rng(0)
 for n in (16, 32, 48, 64, 80, 100, 128, 166, 256):
     M = rng.standard_normal((n, n)) * np.exp(-0.1 * np.arange(n))[None, :]
     rec = dict(bench="small_svd", n=n)
-    for name, mx in (("cluster", 256), ("rounds", 0)):
+    for name, mx, dx in (("cluster", 256, 0), ("rounds", 0, 0), ("dsmem", 0, 256)):
         ctx.set_option("jacobi_cluster_max_n", mx)
+        ctx.set_option("jacobi_dsmem_max_n", dx)
         ctx.factorize(M, cutoff=1e-12)
         ctx.synchronize()
         t0 = time.perf_counter()
@@ -20,5 +21,6 @@ for n in (16, 32, 48, 64, 80, 100, 128, 166, 256):
         ctx.synchronize()
         rec[name + "_ms"] = (time.perf_counter() - t0) / reps * 1e3
         rec[name + "_sweeps"] = info["sweeps"]
-    ctx.set_option("jacobi_cluster_max_n", 256)
+    ctx.set_option("jacobi_cluster_max_n", 112)
+    ctx.set_option("jacobi_dsmem_max_n", 256)
     print(json.dumps(rec), flush=True)
