@@ -212,6 +212,7 @@ int nsb_ctx_set_option(nsb_ctx* ctx, const char* key, int64_t value) {
   else if (k == "jacobi_pivot") { ctx->c.opt.jacobi_pivot = value != 0; }
   else if (k == "jacobi_inner_cap") { NSB_REQUIRE(value >= 1, NSB_EINVAL, "jacobi_inner_cap >= 1"); ctx->c.opt.jacobi_inner_cap = (int)value; }
   else if (k == "jacobi_precondition_min_n") { ctx->c.opt.jacobi_precondition_min_n = (int)value; }
+  else if (k == "jacobi_dsmem_spc") { NSB_REQUIRE(value >= 1 && value <= 16, NSB_EINVAL, "jacobi_dsmem_spc 1..16"); ctx->c.opt.jacobi_dsmem_spc = (int)value; }
   else if (k == "jacobi_dsmem_min_n") { NSB_REQUIRE(value >= 0, NSB_EINVAL, "jacobi_dsmem_min_n >= 0"); ctx->c.opt.jacobi_dsmem_min_n = (int)value; }
   else if (k == "jacobi_dsmem_max_n") { NSB_REQUIRE(value >= 0 && value <= 256, NSB_EINVAL, "jacobi_dsmem_max_n 0..256"); ctx->c.opt.jacobi_dsmem_max_n = (int)value; }
   else if (k == "jacobi_cluster_max_n") { NSB_REQUIRE(value >= 0 && value <= 4096, NSB_EINVAL, "jacobi_cluster_max_n 0..4096"); ctx->c.opt.jacobi_cluster_max_n = (int)value; }

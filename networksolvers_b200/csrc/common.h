@@ -118,6 +118,7 @@ struct Ctx {
     int jacobi_inner_cap = 1;        // inner sweeps per pair solve
     int jacobi_pivot = 0;            // column pivoting in the preconditioning QR
     int jacobi_precondition_min_n = 1024;
+    int jacobi_dsmem_spc = 16;       // tournament Jacobi: preferred maximum of slots (column pairs) per CTA of the cluster
     int jacobi_dsmem_min_n = 41;     // column range of the cluster / distributed-shared-memory tournament Jacobi (needs columns of
     int jacobi_dsmem_max_n = 256;    // <= 256 real / 128 complex rows; other shapes fall through to the kernels below)
     int jacobi_cluster_max_n = 112;  // column count up to which the one-sided Jacobi runs as ONE launch (0: never); measured cross-over

@@ -1069,8 +1069,11 @@ static bool jacobi_dsmem(Ctx* ctx, T* G, int64_t ldg, int64_t m, int64_t n, T* V
   if (len > 32 * ITMAX) return false;
   const int npad = (int)((n % 2) ? n + 1 : n);
   const int s0 = std::max(npad / 2, 1);
+  // slots per CTA: one SM issues a round of 16 slots in ~1 us; spreading the slots over more CTAs of the cluster shortens the
+  // round until the cluster barrier dominates (ctx option jacobi_dsmem_spc = most slots per CTA, while the cluster has room)
+  const int spc_pref = std::max(1, std::min(JD_WARPS, ctx->opt.jacobi_dsmem_spc));
   int csize = 1;
-  while (csize < 8 && csize * JD_WARPS < s0) csize *= 2;
+  while (csize < 8 && csize * spc_pref < s0) csize *= 2;
   if (csize * JD_WARPS < s0) return false;
   const int spc = (s0 + csize - 1) / csize;
   const size_t smem = sizeof(T) * (size_t)spc * 2 * (size_t)(m + nv) + sizeof(int) * (size_t)spc * 2;
