@@ -118,7 +118,8 @@ struct Ctx {
     int jacobi_inner_cap = 1;        // inner sweeps per pair solve
     int jacobi_pivot = 0;            // column pivoting in the preconditioning QR
     int jacobi_precondition_min_n = 1024;
-    int jacobi_dsmem_spc = 16;       // tournament Jacobi: preferred maximum of slots (column pairs) per CTA of the cluster
+    int jacobi_dsmem_spc = 4;        // tournament Jacobi: preferred maximum of slots (column pairs) per CTA while the cluster (<= 8 CTAs) has room
+                                     // (measured: n = 64 1.98 -> 1.30 ms, n = 128 7.0 -> 5.1 ms against 16 slots per CTA)
     int jacobi_dsmem_min_n = 41;     // column range of the cluster / distributed-shared-memory tournament Jacobi (needs columns of
     int jacobi_dsmem_max_n = 256;    // <= 256 real / 128 complex rows; other shapes fall through to the kernels below)
     int jacobi_cluster_max_n = 112;  // column count up to which the one-sided Jacobi runs as ONE launch (0: never); measured cross-over

@@ -18,5 +18,5 @@ for n in (48, 64, 100, 128, 166, 256):
         ctx.synchronize()
         rec[f"spc{spc}_ms"] = round((time.perf_counter() - t0) / 5 * 1e3, 3)
         rec["sweeps"] = info["sweeps"]
-    ctx.set_option("jacobi_dsmem_spc", 16)
+    ctx.set_option("jacobi_dsmem_spc", 4)
     print(json.dumps(rec), flush=True)
