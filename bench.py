@@ -274,7 +274,7 @@ def roofline_from_profile(ctx, recs, ms_total, traffic_key=None):
         pass
     return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "traffic": traffic, "traffic_note": tnote,
-            "kernel": "gemm_tma_kernel (persistent TMA + mbarrier + DMMA GEMM): every GEMM launch of the timed steps",
+            "kernel": "gemm_tma_kernel (persistent TMA + mbarrier + DMMA GEMM): every GEMM launch of the timed steps (launches below m n k = 2e7 -- only the small-chi configs have them -- run on the plain FP64 kernel)",
             "how": "CUDA events on the launching stream around each GEMM launch inside the timed region; achieved = issued flops / "
                    "summed launch durations",
             "gemm_ms_per_step_share": g_ms / ms_total if ms_total > 0 else None,

@@ -206,6 +206,7 @@ int nsb_ctx_set_option(nsb_ctx* ctx, const char* key, int64_t value) {
   NSB_TRY(&ctx->c)
   std::string k(key);
   if (k == "gemm_impl") { NSB_REQUIRE(value >= 0 && value <= 3, NSB_EINVAL, "gemm_impl must be 0..3"); ctx->c.gemm_impl = (int)value; }
+  else if (k == "gemm_naive_max_work") { NSB_REQUIRE(value >= 0, NSB_EINVAL, "gemm_naive_max_work >= 0"); ctx->c.opt.gemm_naive_max_work = value; }
   else if (k == "jacobi_block_min_n") { NSB_REQUIRE(value >= 0, NSB_EINVAL, "jacobi_block_min_n must be >= 0"); ctx->c.opt.jacobi_block_min_n = (int)value; }
   else if (k == "jacobi_precondition") { ctx->c.opt.jacobi_precondition = value != 0; }
   else if (k == "shard_fused") { ctx->c.shard_fused = value != 0; }

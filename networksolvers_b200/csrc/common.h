@@ -100,6 +100,7 @@ struct Ctx {
   int gemm_impl = 0;   // 0 = auto, 1 = naive, 2 = dmma cp.async, 3 = dmma TMA
   // tuning / routing knobs of nsb_ctx_set_option: per context (two contexts of one process do not see each other's settings)
   struct Options {
+    int64_t gemm_naive_max_work = 20000000;   // GEMM_AUTO: m n k batch below which the plain (non-tensor) kernel is used
     int skip_identity = 1;           // skip the identity channel of the first / last environment of an H_eff application
     int skip_identity_sharded = 1;   // the same inside the multi-GPU (sharded) application
     int merge_site_ops = 1;          // 2-site regions: apply W[a] W[b] as one small-operator pass

@@ -718,8 +718,13 @@ void gemm(Ctx* ctx, int opa, int opb, int64_t M, int64_t N, int64_t K, T alpha, 
   if (impl == GEMM_AUTO) impl = ctx->gemm_impl;
   if (peer && (impl == GEMM_AUTO || impl == GEMM_NAIVE)) impl = GEMM_TMA;
   if (impl == GEMM_AUTO) {
+    // measured on B200 in a stream of back-to-back calls (profiles/r02_perf_small_gemm.log): the persistent DMMA kernels have
+    // a floor of 8 us plus ~1 us per k-step of a single tile and need their tensor maps encoded on the host per call; the plain
+    // one-thread-per-element kernel is faster up to m n k ~ 4e7 (166 x 664 x 166: 17 us against 31 us; 49 x 196 x 196: 11
+    // against 33 .. 43 us) -- the launch-bound small-chi regime runs on it
     double work = (double)M * (double)N * (double)(K > 0 ? K : 1) * (double)batch;
-    impl = (work < 32.0 * 32.0 * 32.0) ? GEMM_NAIVE : GEMM_TMA;
+    const bool naive_ok = batch <= 65535 && (N + 15) / 16 <= 65535;   // (grid limits of the plain kernel)
+    impl = (naive_ok && work < (double)ctx->opt.gemm_naive_max_work) ? GEMM_NAIVE : GEMM_TMA;
   }
   ctx->cnt.gemm_calls++;
   ctx->cnt.kernel_launches++;
