@@ -321,6 +321,51 @@ def _ttno_local(opsum: OpSum, sites: SiteSet, root=None, dtype=float):
 mpo = ttno
 
 
+# ---- host-side observables for callbacks (`itn.expect(state(problem), "Sz", v)`, examples/quench_evolution.jl:41-47) ------
+def _link_axis(psi: HostTTN, u, n):
+    for i, l in enumerate(psi.legs[u]):
+        if l[0] == "link" and set(l[1:]) == {u, n}:
+            return i
+    raise KeyError((u, n))
+
+
+def _subtree_env(psi: HostTTN, u, p, cache):
+    """E[bra, ket] of the subtree hanging off vertex u, seen through u's link toward p (<psi|psi> with that link open)."""
+    if (u, p) in cache:
+        return cache[(u, p)]
+    T = psi.tensors[u]
+    X = T
+    for c in psi.graph.neighbors(u):
+        if c == p:
+            continue
+        ax = _link_axis(psi, u, c)
+        Ec = _subtree_env(psi, c, u, cache)                       # [bra, ket]
+        X = np.moveaxis(np.tensordot(Ec, X, axes=(1, ax)), 0, ax)   # ket link -> bra link
+    axp = _link_axis(psi, u, p)
+    other = [i for i in range(T.ndim) if i != axp]
+    E = np.tensordot(np.conj(T), X, axes=(other, other))         # [bra link, ket link]
+    cache[(u, p)] = E
+    return E
+
+
+def expect(psi: HostTTN, op, v, sites: SiteSet = None):
+    """<psi| op_v |psi> / <psi|psi> for a tree tensor network state on the host (`op`: operator name looked up in `sites`, or a
+    d x d matrix <out|op|in>).  One pass over the tree, O(chi^3) per vertex."""
+    M = np.asarray(sites.type.op(op) if isinstance(op, str) else op)
+    cache = {}
+    T = psi.tensors[v]
+    X = T
+    for c in psi.graph.neighbors(v):
+        ax = _link_axis(psi, v, c)
+        X = np.moveaxis(np.tensordot(_subtree_env(psi, c, v, cache), X, axes=(1, ax)), 0, ax)
+    sax = psi.legs[v].index(("site", v))
+    OX = np.moveaxis(np.tensordot(M, X, axes=(1, sax)), 0, sax)
+    num = np.vdot(T, OX)
+    den = np.vdot(T, X)
+    val = num / den
+    return float(val.real) if abs(val.imag) <= 1e-12 * max(1.0, abs(val)) else complex(val)
+
+
 # ---- general OpSum -> compressed TTNO (SURVEY 8(f) row 3: operator construction with compression) ------------------
 def _site_first(H: HostTTN) -> HostTTN:
     """Same operator with every tensor laid out [site, site_out, links in neighbour order]."""

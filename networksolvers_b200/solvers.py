@@ -289,7 +289,10 @@ class RegionIterator:
         for which in range(1, len(self.region_plan) + 1):
             self.which_region = which
             _, kwargs = self.region_plan[which - 1]
-            self.problem = region_iterator_action(self.problem, self, **kwargs)
+            # the reference dispatches `region_iterator_action!` on the problem type (examples/timed_dmrg/timed_eigsolve.jl:41-75
+            # wraps an EigsolveProblem and times the hooks): a problem object may bring its own action as a method
+            action = getattr(self.problem, "region_iterator_action", None)
+            self.problem = action(self, **kwargs) if action is not None else region_iterator_action(self.problem, self, **kwargs)
             yield self
 
 
