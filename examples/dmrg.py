@@ -1,6 +1,6 @@
 """examples/dmrg.jl of the reference through networksolvers_b200 (needs a B200).
 
-    python examples/dmrg.py dmrg [--N 10] [--nsites 2] [--site-type "S=1"]
+    python examples/dmrg.py dmrg [--N 10] [--nsites 2] [--site-type "S=1"] [--conserve-qns]
     python examples/dmrg.py tree_dmrg
     python examples/dmrg.py sweep_loop_version
 """
@@ -22,11 +22,11 @@ def heisenberg_opsum(g):
     return os_
 
 
-def dmrg(N=10, nsites=2, site_type="S=1", dry_run=False):
+def dmrg(N=10, nsites=2, site_type="S=1", conserve_qns=False, dry_run=False):
     """examples/dmrg.jl:10-47: chain of N sites, product start (even -> Up, odd -> Dn), 5 sweeps, cutoff 1e-12,
     maxdim [10, 40, 80, 160], density-matrix subspace expansion with factor 1.1."""
     g = ns.path_graph(N)
-    s = ns.siteinds(site_type, g)
+    s = ns.siteinds(site_type, g, conserve_qns=conserve_qns)
     H = ns.mpo(heisenberg_opsum(g), s)
     state = {v: ("Up" if j % 2 == 0 else "Dn") for j, v in enumerate(g.vertices, start=1)}
     psi = ns.product_state(s, state)
@@ -92,10 +92,11 @@ if __name__ == "__main__":
     ap.add_argument("--N", type=int, default=10)
     ap.add_argument("--nsites", type=int, default=2)
     ap.add_argument("--site-type", default="S=1")
+    ap.add_argument("--conserve-qns", action="store_true", help="Sz conservation: block-sparse tensors on the device")
     ap.add_argument("--dry-run", action="store_true")
     a = ap.parse_args()
     if a.which == "dmrg":
-        dmrg(a.N, a.nsites, a.site_type, a.dry_run)
+        dmrg(a.N, a.nsites, a.site_type, a.conserve_qns, a.dry_run)
     elif a.which == "tree_dmrg":
         tree_dmrg(a.dry_run)
     else:

@@ -15,7 +15,7 @@ from quench_evolution import dense_hamiltonian  # noqa: E402
 
 
 def inner(a, b):
-    return np.vdot(a.to_host().to_dense(), b.to_host().to_dense())
+    return ns.inner(a.to_host(), b.to_host())
 
 
 def tdvp(N=10, total_time=1.0, time_step=0.1, dry_run=False):
@@ -39,14 +39,12 @@ def tdvp(N=10, total_time=1.0, time_step=0.1, dry_run=False):
     res_rk4 = ns.tdvp(H, psi0, time_range, inserter_kwargs=inserter_kwargs, updater_kwargs=updater_kwargs,
                       tdvp_order=tdvp_order, outputlevel=outputlevel)
     print("maxlinkdim(res_rk4) =", res_rk4.maxlinkdim())
-    if N <= 12:
-        print("inner(res_rk4, res_2site) =", inner(res_rk4, res_2site))
+    print("inner(res_rk4, res_2site) =", inner(res_rk4, res_2site))
     print("Calling TDVP with exponentiate solver (res_1site)")
     res_1site = ns.tdvp(H, psi0, time_range, nsites=2, inserter_kwargs=inserter_kwargs, tdvp_order=tdvp_order,
                         outputlevel=outputlevel)
-    if N <= 12:
-        print("inner(res_1site, res_rk4) =", inner(res_1site, res_rk4))
-        print("inner(res_1site, res_2site) =", inner(res_1site, res_2site))
+    print("inner(res_1site, res_rk4) =", inner(res_1site, res_rk4))
+    print("inner(res_1site, res_2site) =", inner(res_1site, res_2site))
     return res_2site
 
 

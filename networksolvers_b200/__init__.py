@@ -9,7 +9,7 @@ from ._lib import NsbError, LIB_PATH  # noqa: F401
 from .graphs import NamedGraph, path_graph, named_comb_tree, star_of_chains, default_root_vertex  # noqa: F401
 from .models import (SiteType, SiteSet, siteinds, OpSum, heisenberg, transverse_ising, hubbard, HostTTN, product_state,  # noqa: F401
                      random_state, ttno, mpo, identity_operator, delta_state, random_tensornetwork, GraphSites, product_operator_sum,
-                     ttno_general, compress_operator, operator_direct_sum, expect)
+                     ttno_general, compress_operator, operator_direct_sum, expect, inner)
 from .device import Context, DeviceNetwork, default_context  # noqa: F401
 from .region_plans import (euler_tour_edges, euler_tour_vertices, euler_sweep, post_order_dfs_plan,  # noqa: F401
                            post_order_dfs_sweep, tdvp_sub_time_steps, first_order_sweep, tdvp_regions)

@@ -348,6 +348,34 @@ def _subtree_env(psi: HostTTN, u, p, cache):
     return E
 
 
+def _pair_env(a: HostTTN, b: HostTTN, u, p, cache):
+    """E[link of a (bra), link of b (ket)] of the subtree at u seen through the link toward p, for <a|b>."""
+    if (u, p) in cache:
+        return cache[(u, p)]
+    X = b.tensors[u]
+    # bring b's tensor to a's leg order (same graph, same canonical legs in practice)
+    if b.legs[u] != a.legs[u]:
+        X = np.transpose(X, [b.legs[u].index(l) for l in a.legs[u]])
+    for c in a.graph.neighbors(u):
+        if c == p:
+            continue
+        ax = _link_axis(a, u, c)
+        X = np.moveaxis(np.tensordot(_pair_env(a, b, c, u, cache), X, axes=(1, ax)), 0, ax)
+    T = a.tensors[u]
+    if p is None:
+        return np.vdot(T, X)
+    axp = _link_axis(a, u, p)
+    other = [i for i in range(T.ndim) if i != axp]
+    E = np.tensordot(np.conj(T), X, axes=(other, other))
+    cache[(u, p)] = E
+    return E
+
+
+def inner(a: HostTTN, b: HostTTN):
+    """<a|b> of two tree tensor network states on the same graph (`itn.inner(a, b; alg="exact")`), one pass over the tree."""
+    return _pair_env(a, b, a.graph.vertices[0], None, {})
+
+
 def expect(psi: HostTTN, op, v, sites: SiteSet = None):
     """<psi| op_v |psi> / <psi|psi> for a tree tensor network state on the host (`op`: operator name looked up in `sites`, or a
     d x d matrix <out|op|in>).  One pass over the tree, O(chi^3) per vertex."""

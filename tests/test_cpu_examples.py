@@ -39,6 +39,16 @@ def test_expect_matches_dense_state():
                     assert abs(ns.expect(psi, name, v, s) - ref) < 1e-12
 
 
+def test_inner_matches_dense_states():
+    import networksolvers_b200 as ns
+    for g in (ns.path_graph(6), ns.named_comb_tree([2, 3, 2])):
+        s = ns.siteinds("S=1/2", g)
+        for dt in (float, complex):
+            a, b = ns.random_state(s, 4, seed=3, dtype=dt), ns.random_state(s, 3, seed=5, dtype=dt)
+            ref = np.vdot(a.to_dense(), b.to_dense())
+            assert abs(ns.inner(a, b) - ref) < 1e-12 * max(1.0, abs(ref))
+
+
 def test_problem_types_may_bring_their_own_region_action():
     """RegionIterator calls `problem.region_iterator_action` when the problem object defines one, with the region's keyword
     pack, and keeps whatever it returns as the problem -- no device needed to see the dispatch."""
