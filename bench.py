@@ -246,6 +246,16 @@ def emit(line):
     os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 
+def _watchdog_emit(make_line, extra, cpu, seconds):
+    """The full sweep did not return within `seconds`: print the line of what was measured and leave."""
+    extra = dict(extra)
+    extra["full_sweep_error"] = f"watchdog: sweep not finished after {seconds:.0f} s, line printed without it"
+    try:
+        emit(make_line(extra, cpu))
+    finally:
+        os._exit(0)
+
+
 _REAL_STDOUT = 1
 
 
@@ -452,79 +462,40 @@ def run_config2(args, rank, world, local_rank):
 
     extra = {}
     if not args.no_region_step and (world == 1 or shard is not None):
-        # Consecutive full region steps of a 2-site sweep through the three hooks, first to the right from the benchmark
-        # bond, then back to the left (both directions of the Euler tour).
-        tr = (args.cutoff, 1, args.chi)
-        nr = max(args.region_steps, 1)
-        right = [[region[0] + r, region[1] + r] for r in range(nr) if region[1] + r <= args.nsites]
-        left = [[right[-1][1] - r, right[-1][0] - r] for r in range(nr)]
-        steps, phases, newdims = time_region_steps(ctx, net, right + left, tr, lambda: net.update_eigsolve())
-        full = list(range(1, len(right))) + list(range(len(right) + 1, len(steps)))   # steps that include one environment update
-        # medians: the first step that updates an environment after set-up also pays one-off allocations of the step's work buffers
-        extra["region_step_s"] = float(np.median([steps[i] for i in full]))
-        extra["region_steps_s"] = steps
-        extra["region_directions"] = ["right"] * len(right) + ["left"] * len(left)
-        extra["region_phase_ms"] = {k: float(np.median([phases[i][k] for i in full])) for k in phases[0]}
-        extra["region_newdim"] = newdims
-        extra["region_trunc"] = {"cutoff": args.cutoff, "maxdim": args.chi}
-        extra["sweep_regions"] = 2 * (args.nsites - 1)
-        extra["sweep_s_extrapolated"] = extra["region_step_s"] * 2 * (args.nsites - 1)
-        if world > 1:
-            extra["region_parallelism"] = (
-                "Krylov vectors sharded along theta's last bond (ncclReduceScatter when sweeping right, ncclAllGather when sweeping left, "
-                "scalar all-reduce per dot); environment update split over the incoming environment's bra index + all-reduce; "
-                "factorisation: Gram matrix, back-transformation and C = U^H theta by column slabs + all-gather, tridiagonalisation "
-                "and divide & conquer replicated; tensors replicated in HBM")
-        mi = ctx.mem_info()
-        extra["hbm_pool_used_gib"] = mi["pool_used"] / 2**30
-        er, ef = net.env_bytes()
-        extra["env_hbm_gib_per_gpu"] = er / 2**30
-        extra["env_hbm_gib_if_replicated"] = ef / 2**30
+        # (guarded: whatever happens below, the headline line of the timed matvec steps above is still printed)
+        try:
+            # Consecutive full region steps of a 2-site sweep through the three hooks, first to the right from the benchmark
+            # bond, then back to the left (both directions of the Euler tour).
+            tr = (args.cutoff, 1, args.chi)
+            nr = max(args.region_steps, 1)
+            right = [[region[0] + r, region[1] + r] for r in range(nr) if region[1] + r <= args.nsites]
+            left = [[right[-1][1] - r, right[-1][0] - r] for r in range(nr)]
+            steps, phases, newdims = time_region_steps(ctx, net, right + left, tr, lambda: net.update_eigsolve())
+            full = list(range(1, len(right))) + list(range(len(right) + 1, len(steps)))   # steps that include one environment update
+            # medians: the first step that updates an environment after set-up also pays one-off allocations of the step's work buffers
+            extra["region_step_s"] = float(np.median([steps[i] for i in full]))
+            extra["region_steps_s"] = steps
+            extra["region_directions"] = ["right"] * len(right) + ["left"] * len(left)
+            extra["region_phase_ms"] = {k: float(np.median([phases[i][k] for i in full])) for k in phases[0]}
+            extra["region_newdim"] = newdims
+            extra["region_trunc"] = {"cutoff": args.cutoff, "maxdim": args.chi}
+            extra["sweep_regions"] = 2 * (args.nsites - 1)
+            extra["sweep_s_extrapolated"] = extra["region_step_s"] * 2 * (args.nsites - 1)
+            if world > 1:
+                extra["region_parallelism"] = (
+                    "Krylov vectors sharded along theta's last bond (ncclReduceScatter when sweeping right, ncclAllGather when sweeping left, "
+                    "scalar all-reduce per dot); environment update split over the incoming environment's bra index + all-reduce; "
+                    "factorisation: Gram matrix, back-transformation and C = U^H theta by column slabs + all-gather, tridiagonalisation "
+                    "and divide & conquer replicated; tensors replicated in HBM")
+            mi = ctx.mem_info()
+            extra["hbm_pool_used_gib"] = mi["pool_used"] / 2**30
+            er, ef = net.env_bytes()
+            extra["env_hbm_gib_per_gpu"] = er / 2**30
+            extra["env_hbm_gib_if_replicated"] = ef / 2**30
+        except Exception as e:      # noqa: BLE001
+            extra["region_step_error"] = f"{type(e).__name__}: {e}"[:300]
 
-    if not args.no_full_sweep and (world == 1 or args.full_sweep):
-        # One real 2-site DMRG sweep (all 2 (N - 1) regions of the Euler tour) through the public driver, continuing on the
-        # same network: the gauge walk to the tour's first region and the environments it needs are set-up (not timed).
-        g = ns.path_graph(args.nsites)
-        plan = ns.euler_sweep(g, nsites=2)
-        t0 = time.perf_counter()
-        net.extract(list(plan[0][0]))
-        ctx.synchronize()
-        extra["full_sweep_setup_s"] = time.perf_counter() - t0
-        prob = ns.EigsolveProblem(net=net)
-        ctx.enable_timers(True)
-        ctx.reset_timers()
-        ctx.reset_counters()
-        barrier()
-        t0 = time.perf_counter()
-        E, _ = ns.dmrg(prob, nsweeps=1, nsites=2, inserter_kwargs=dict(trunc=dict(cutoff=args.cutoff, maxdim=args.chi)))
-        barrier()
-        extra["full_sweep_s"] = time.perf_counter() - t0
-        extra["full_sweep_regions"] = len(plan)
-        extra["full_sweep_phase_ms"] = ctx.timers()
-        extra["full_sweep_launches"] = int(ctx.counters()["kernel_launches"])
-        extra["full_sweep_maxlinkdim"] = int(net.maxlinkdim())
-        extra["full_sweep_energy"] = float(E)
-        ctx.enable_timers(False)
-
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        ctf, cdt, creps, s = cpu_matvec_sample(args.chi, seconds=12.0)
-        cores = blas_threads()
-        cpu = {"value": ctf, "unit": "TFLOP/s", "cores": cores, "kind": "port",
-               "sample": f"{creps} x one right-bond slab (1/{CPU_SLABS}) of the chi={args.chi} H_eff matvec, oracle restatement of "
-                         f"optimal_map (NumPy + {blas_name()}, {cores} threads); Julia reference not runnable here"}
-        if not args.no_region_step:
-            # factorisation sample at a bounded size (LAPACK gesdd / syevd scale as n^3), scaled to the GPU arm's 2 chi
-            nf = min(2 * args.chi, 2048)
-            dt_f = cpu_factorize_sample(nf, cutoff=args.cutoff)
-            mv_full = cdt * CPU_SLABS
-            cpu["region_step"] = {"matvec_s_at_chi": mv_full, "factorize_s_sample": dt_f, "factorize_sample_n": nf,
-                                  "factorize_s_scaled": dt_f * (2 * args.chi / nf) ** 3,
-                                  "region_s_estimate": 3 * mv_full + dt_f * (2 * args.chi / nf) ** 3,
-                                  "note": "3 matvecs (slab sample x 8) + oracle factorize (LAPACK) scaled by (n / n_sample)^3; "
-                                          "no environment update counted"}
-
-    if rank == 0:
+    def make_line(extra, cpu):
         line = {"metric": "heff_matvec_fp64_tflops", "value": tflops * replicas,
                 "unit": "TFLOP/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -552,7 +523,67 @@ def run_config2(args, rank, world, local_rank):
         if cpu is not None:
             line["cpu_baseline"] = cpu
         line.update(extra)
-        emit(line)
+        return line
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            ctf, cdt, creps, s = cpu_matvec_sample(args.chi, seconds=12.0)
+            cores = blas_threads()
+            cpu = {"value": ctf, "unit": "TFLOP/s", "cores": cores, "kind": "port",
+                   "sample": f"{creps} x one right-bond slab (1/{CPU_SLABS}) of the chi={args.chi} H_eff matvec, oracle restatement of "
+                             f"optimal_map (NumPy + {blas_name()}, {cores} threads); Julia reference not runnable here"}
+            if not args.no_region_step:
+                # factorisation sample at a bounded size (LAPACK gesdd / syevd scale as n^3), scaled to the GPU arm's 2 chi
+                nf = min(2 * args.chi, 2048)
+                dt_f = cpu_factorize_sample(nf, cutoff=args.cutoff)
+                mv_full = cdt * CPU_SLABS
+                cpu["region_step"] = {"matvec_s_at_chi": mv_full, "factorize_s_sample": dt_f, "factorize_sample_n": nf,
+                                      "factorize_s_scaled": dt_f * (2 * args.chi / nf) ** 3,
+                                      "region_s_estimate": 3 * mv_full + dt_f * (2 * args.chi / nf) ** 3,
+                                      "note": "3 matvecs (slab sample x 8) + oracle factorize (LAPACK) scaled by (n / n_sample)^3; "
+                                              "no environment update counted"}
+        except Exception as e:      # noqa: BLE001
+            cpu = None
+            extra["cpu_baseline_error"] = f"{type(e).__name__}: {e}"[:300]
+
+    if not args.no_full_sweep and (world == 1 or args.full_sweep):
+        # A watchdog prints the line without the sweep if the sweep does not come back (the matvec numbers are the headline).
+        dog = threading.Timer(args.sweep_watchdog_s, _watchdog_emit, args=(make_line, extra, cpu, args.sweep_watchdog_s))
+        dog.daemon = True
+        if rank == 0:
+            dog.start()
+        try:
+            # One real 2-site DMRG sweep (all 2 (N - 1) regions of the Euler tour) through the public driver, continuing on the
+            # same network: the gauge walk to the tour's first region and the environments it needs are set-up (not timed).
+            g = ns.path_graph(args.nsites)
+            plan = ns.euler_sweep(g, nsites=2)
+            t0 = time.perf_counter()
+            net.extract(list(plan[0][0]))
+            ctx.synchronize()
+            extra["full_sweep_setup_s"] = time.perf_counter() - t0
+            prob = ns.EigsolveProblem(net=net)
+            ctx.enable_timers(True)
+            ctx.reset_timers()
+            ctx.reset_counters()
+            barrier()
+            t0 = time.perf_counter()
+            E, _ = ns.dmrg(prob, nsweeps=1, nsites=2, inserter_kwargs=dict(trunc=dict(cutoff=args.cutoff, maxdim=args.chi)))
+            barrier()
+            extra["full_sweep_s"] = time.perf_counter() - t0
+            extra["full_sweep_regions"] = len(plan)
+            extra["full_sweep_phase_ms"] = ctx.timers()
+            extra["full_sweep_launches"] = int(ctx.counters()["kernel_launches"])
+            extra["full_sweep_maxlinkdim"] = int(net.maxlinkdim())
+            extra["full_sweep_energy"] = float(E)
+            ctx.enable_timers(False)
+        except Exception as e:      # noqa: BLE001
+            extra["full_sweep_error"] = f"{type(e).__name__}: {e}"[:300]
+        finally:
+            dog.cancel()
+
+    if rank == 0:
+        emit(make_line(extra, cpu))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -777,6 +808,8 @@ def main():
     ap.add_argument("--no-region-step", action="store_true", help="skip the full region steps (extract + 3-matvec Lanczos + truncating insert)")
     ap.add_argument("--no-full-sweep", action="store_true", help="single GPU: skip the measured full 2-site DMRG sweep (about 2.5 minutes at chi=4096)")
     ap.add_argument("--full-sweep", action="store_true", help="multi-GPU: also run the measured full sweep (every rank in lock step)")
+    ap.add_argument("--sweep-watchdog-s", type=float, default=900.0, help="print the line without the full sweep if the sweep has not "
+                    "returned after this many seconds (measured: 138 s at chi=4096, N=100)")
     ap.add_argument("--region-steps", type=int, default=3, help="consecutive region steps timed in each sweep direction")
     ap.add_argument("--cutoff", type=float, default=0.0, help="inserter cutoff of the region steps (0: maxdim-limited; 1e-9: the reference's "
                     "timed_dmrg setting)")
