@@ -286,11 +286,20 @@ ns.region_plan(T::B200ApplyExpProblem; nsites, time_step, sweep_kwargs...) =
 ns.region_plan(P::Union{B200EigsolveProblem,B200FittingProblem}; nsites, sweep_kwargs...) =
   ns.euler_sweep(graph(P.net); nsites, sweep_kwargs...)                                  # src/iterators.jl:102-104
 
-# printers call itn.maxlinkdim(state(E)) (src/eigsolve.jl:39, src/applyexp.jl:56): answer from the device without a download
-function ns.eigsolve_sweep_printer(region_iterator; outputlevel, sweep, nsweeps, kws...)
+# The reference's printers call itn.maxlinkdim(state(E)) (src/eigsolve.jl:39, src/applyexp.jl:56), which through `ns.state` above
+# would download the whole state once per sweep.  The printers below answer from the device; they are separate functions (the
+# reference's own methods are left alone) and the default `sweep_printer` of this module's entry points.
+function eigsolve_sweep_printer(region_iterator; outputlevel, sweep, nsweeps, kws...)
+  outputlevel >= 1 || return nothing
   E = ns.problem(region_iterator)
-  (outputlevel >= 1 && E isa B200EigsolveProblem) || return nothing
   println("After sweep $sweep/$nsweeps eigenvalue=$(E.eigenvalue) maxlinkdim=$(maxlinkdim(E.net))")
+  flush(stdout)
+end
+function applyexp_sweep_printer(region_iterator; outputlevel, sweep, nsweeps, process_time=identity, kws...)
+  outputlevel >= 1 || return nothing
+  T = ns.problem(region_iterator)
+  println("  Current time = $(process_time(T.current_time)), maxlinkdim=$(maxlinkdim(T.net))")
+  flush(stdout)
 end
 
 # ---- hooks ------------------------------------------------------------------------------------------------------------
@@ -385,17 +394,19 @@ function ns.inserter(P::B200Problem, local_tensor, region_iterator; normalize=fa
 end
 
 # ---- entry points with the reference's signatures ---------------------------------------------------------------------
-function eigsolve(H, init_state; devices=[0], kws...)                                     # src/eigsolve.jl:69-74
-  prob = ns.eigsolve(B200EigsolveProblem(; net=DeviceNet(H, init_state; devices)); kws...)
-  return prob                                                                             # (eigenvalue, state) as the reference returns
+function eigsolve(H, init_state; devices=[0], sweep_printer=eigsolve_sweep_printer, kws...)   # src/eigsolve.jl:69-74
+  # (eigenvalue, state) as the reference returns; the state is downloaded once, at the end
+  return ns.eigsolve(B200EigsolveProblem(; net=DeviceNet(H, init_state; devices)); sweep_printer, kws...)
 end
 dmrg(args...; kws...) = eigsolve(args...; kws...)
 
-function applyexp(H, init_state, exponents; devices=[0], kws...)                          # src/applyexp.jl:84-89
-  return ns.applyexp(B200ApplyExpProblem(; net=DeviceNet(H, init_state; devices, eltype=ComplexF64)), exponents; kws...)
+function applyexp(H, init_state, exponents; devices=[0], sweep_printer=applyexp_sweep_printer, kws...)   # src/applyexp.jl:84-89
+  prob = B200ApplyExpProblem(; net=DeviceNet(H, init_state; devices, eltype=ComplexF64))
+  return ns.applyexp(prob, exponents; sweep_printer, kws...)
 end
-function tdvp(H, init_state, time_points; kws...)                                          # src/applyexp.jl:93-103
-  return applyexp(H, init_state, [-im * t for t in time_points]; sweep_printer=ns.applyexp_sweep_printer, kws...)
+function tdvp(H, init_state, time_points; process_time=ns.process_real_times,
+              sweep_printer=(a...; k...) -> applyexp_sweep_printer(a...; process_time, k...), kws...)   # src/applyexp.jl:93-103
+  return applyexp(H, init_state, [-im * t for t in time_points]; sweep_printer, kws...)
 end
 
 function fit_tensornetwork(target, operator, init_state; nsweeps=25, nsites=1, outputlevel=0, normalize=true,
