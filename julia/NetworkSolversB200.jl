@@ -107,13 +107,18 @@ function upload!(d::DeviceNet, tn, v; operator=false)
   order, legs = encode_legs(d, tn, v; operator)
   A = Array{d.eltype}(it.array(it.dense(tn[v]), order...))     # dense column-major copy in that index order (QN tensors: dense image)
   dims = collect(Int64, size(A))
-  if d.multi != C_NULL
-    f = operator ? :nsb_multi_mpo_upload : :nsb_multi_site_upload
-    check(d, ccall((f, lib), Cint, (Ptr{Cvoid}, Int32, Int32, Ptr{Int32}, Ptr{Int64}, Ptr{Cvoid}), d.multi, d.vid[v], ndims(A), legs, dims, A))
+  # (the symbol of a ccall must be a literal: one call per entry point)
+  m, n, vv, r = d.multi, d.net, d.vid[v], Int32(ndims(A))
+  rc = if d.multi != C_NULL && operator
+    ccall((:nsb_multi_mpo_upload, lib), Cint, (Ptr{Cvoid}, Int32, Int32, Ptr{Int32}, Ptr{Int64}, Ptr{Cvoid}), m, vv, r, legs, dims, A)
+  elseif d.multi != C_NULL
+    ccall((:nsb_multi_site_upload, lib), Cint, (Ptr{Cvoid}, Int32, Int32, Ptr{Int32}, Ptr{Int64}, Ptr{Cvoid}), m, vv, r, legs, dims, A)
+  elseif operator
+    ccall((:nsb_mpo_upload, lib), Cint, (Ptr{Cvoid}, Int32, Int32, Ptr{Int32}, Ptr{Int64}, Ptr{Cvoid}), n, vv, r, legs, dims, A)
   else
-    f = operator ? :nsb_mpo_upload : :nsb_site_upload
-    check(d, ccall((f, lib), Cint, (Ptr{Cvoid}, Int32, Int32, Ptr{Int32}, Ptr{Int64}, Ptr{Cvoid}), d.net, d.vid[v], ndims(A), legs, dims, A))
+    ccall((:nsb_site_upload, lib), Cint, (Ptr{Cvoid}, Int32, Int32, Ptr{Int32}, Ptr{Int64}, Ptr{Cvoid}), n, vv, r, legs, dims, A)
   end
+  check(d, rc)
 end
 
 # abelian quantum numbers: one row of integer charges per basis state of every site and link index (conserve_qns = true,

@@ -139,3 +139,10 @@ def test_the_shim_does_not_overwrite_reference_methods():
     for m in defs:
         name, first_args = m.group(1), m.group(2)
         assert "::B200" in first_args or "::Union{B200" in first_args, (name, first_args)
+
+
+def test_every_ccall_names_its_symbol_literally():
+    """Julia resolves `ccall((:symbol, lib), ...)` at compile time: the symbol must be a literal, not a variable."""
+    s = _strip_strings_and_comments(SRC)
+    assert len(re.findall(r"ccall\(\(", s)) >= 40
+    assert re.findall(r"ccall\(\((?!:nsb_\w+, lib\))", s) == []
