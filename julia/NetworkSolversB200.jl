@@ -15,7 +15,6 @@ module NetworkSolversB200
 import NetworkSolvers as ns
 import ITensors as it
 import ITensorNetworks as itn
-import NamedGraphs as ng
 import Graphs
 using ConstructionBase: setproperties
 
@@ -81,7 +80,7 @@ vertex_ids(d::DeviceNet, region) = Int32[d.vid[v] for v in region]
 #   site index            -> (v, NSB_SITE);   primed site index (operators) -> (v, NSB_SITE_OUT)
 #   link to neighbour n   -> (v, n)
 function ordered_inds(tn, v; operator=false)
-  nbrs = collect(ng.neighbors(tn, v))
+  nbrs = collect(Graphs.neighbors(tn, v))
   links = [only(it.commoninds(tn[v], tn[n])) for n in nbrs]
   sites = [i for i in it.inds(tn[v]) if !(i in links)]
   operator && (sites = sort(sites; by=it.plev))            # (s, s')
@@ -141,7 +140,7 @@ function upload_qns!(d::DeviceNet, psi, total)
     c = permutedims(charges(d.siteinds[v], names))   # state-major rows
     check(d, ccall((:nsb_qn_set_site, lib), Cint, (Ptr{Cvoid}, Int32, Ptr{Int32}), d.net, d.vid[v], c))
   end
-  for e in ng.edges(psi)
+  for e in Graphs.edges(psi)
     u, v = Graphs.src(e), Graphs.dst(e)
     l = only(it.commoninds(psi[u], psi[v]))
     c = permutedims(charges(l, names; flip=(it.dir(it.inds(psi[u])[findfirst(==(l), it.inds(psi[u]))]) == it.In)))
@@ -157,18 +156,19 @@ Counterpart of `permute_indices(init_state)`, `permute_indices(H)`, `itn.ProjTTN
 environments are built lazily on the device by the first `extracter`.
 """
 function DeviceNet(H, psi; devices=[0], eltype=nothing)
-  g = ng.underlying_graph(psi)
-  verts = collect(ng.vertices(psi))
+  g = itn.underlying_graph(psi)                 # the NamedGraph (examples/quench_evolution.jl:33 uses the same call)
+  verts = collect(Graphs.vertices(psi))
   vid = Dict{Any,Int32}(v => Int32(i - 1) for (i, v) in enumerate(verts))
   elt = isnothing(eltype) ? promote_type(it.scalartype(psi), it.scalartype(H)) : eltype
   elt = elt <: Complex ? ComplexF64 : Float64
   dtype = elt <: Complex ? NSB_C128 : NSB_F64
   edges = Int32[]
-  for e in ng.edges(psi); append!(edges, (vid[Graphs.src(e)], vid[Graphs.dst(e)])); end
-  sinds = Dict{Any,Any}(v => only(itn.siteinds(psi, v)) for v in verts)
+  for e in Graphs.edges(psi); append!(edges, (vid[Graphs.src(e)], vid[Graphs.dst(e)])); end
+  si = itn.siteinds(psi)                          # as src/permute_indices.jl:5 reads them
+  sinds = Dict{Any,Any}(v => only(si[v]) for v in verts)
   sdims = Int64[it.dim(sinds[v]) for v in verts]
   linds = Dict{Any,Any}()
-  for e in ng.edges(psi)
+  for e in Graphs.edges(psi)
     u, v = Graphs.src(e), Graphs.dst(e)
     linds[(u, v)] = linds[(v, u)] = only(it.commoninds(psi[u], psi[v]))
   end
@@ -228,7 +228,7 @@ Every site tensor comes back in the library's canonical order (first link, site,
 changed on the device are re-made (same tags), all others are the host's original `Index` objects.
 """
 function download_state(d::DeviceNet)
-  for e in ng.edges(d.graph)
+  for e in Graphs.edges(d.graph)
     u, v = Graphs.src(e), Graphs.dst(e)
     n = linkdim(d, u, v)
     if it.dim(d.linkinds[(u, v)]) != n
@@ -352,8 +352,8 @@ function next_hop(d::DeviceNet, region_iterator, nsites)
   nsites == 1 || return Int32(-1)
   curr, nxt = ns.current_region(region_iterator), ns.next_region(region_iterator)
   (isnothing(nxt) || nxt == curr) && return Int32(-1)
-  path = ng.vertex_path(d.graph, first(curr), first(nxt))       # NamedGraphs: vertices along the unique tree path
-  return d.vid[path[2]]
+  next_edge = first(itn.edge_sequence_between_regions(d.graph, curr, nxt))    # the reference's own call (src/applyexp.jl:34)
+  return d.vid[Graphs.dst(next_edge)]
 end
 
 function ns.updater(T::B200ApplyExpProblem, local_state, region_iterator; nsites, time_step, solver=ns.runge_kutta_solver,
