@@ -203,7 +203,7 @@ function DeviceNet(H, psi; devices=[0], eltype=nothing)
   end
   if it.hasqns(psi[first(verts)])
     d.multi == C_NULL || error("QN conservation with devices > 1: upload the charges to every replica (nsb_multi_net) -- not wired in this shim")
-    upload_qns!(d, psip, it.flux(psip))
+    upload_qns!(d, psip, reduce(+, [it.flux(psip[v]) for v in verts]))      # total charge = sum of the tensors' fluxes
   end
   return d
 end
