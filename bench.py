@@ -493,6 +493,8 @@ def run_config2(args, rank, world, local_rank):
             extra["env_hbm_gib_per_gpu"] = er / 2**30
             extra["env_hbm_gib_if_replicated"] = ef / 2**30
         except Exception as e:      # noqa: BLE001
+            if world > 1:
+                raise                # (ranks in lock step: one rank carrying on alone would leave the others inside a collective)
             extra["region_step_error"] = f"{type(e).__name__}: {e}"[:300]
 
     def make_line(extra, cpu):
@@ -578,6 +580,8 @@ def run_config2(args, rank, world, local_rank):
             extra["full_sweep_energy"] = float(E)
             ctx.enable_timers(False)
         except Exception as e:      # noqa: BLE001
+            if world > 1:
+                raise
             extra["full_sweep_error"] = f"{type(e).__name__}: {e}"[:300]
         finally:
             dog.cancel()
